@@ -1,0 +1,171 @@
+/*
+ * ultraface_b200.h — C ABI of the B200-native face-detection hot path.
+ *
+ * Drop-in boundary for sgasse/infercam_onnx's `infer_server::nn` module
+ * (citations: /root/reference/infer_server/src/nn.rs). A Rust `ultraface-sys`
+ * crate binds exactly these symbols (see INTEGRATION.md and rust/); the Python
+ * mirror used by the tests is infercam_onnx_b200/nn.py.
+ *
+ * Conventions: every function returns UF_OK (0) or a uf_status error code and
+ * never aborts the process; uf_last_error() returns a thread-local message for
+ * the last failing call on this thread. All entry points are thread-safe on one
+ * handle (`UltrafaceModel` must be Send + Sync: it is borrowed across .await in
+ * inferer.rs:29-50); calls on one handle are serialised internally.
+ * No torch types, plain pointers and sizes only.
+ */
+#ifndef ULTRAFACE_B200_H
+#define ULTRAFACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define UF_API __attribute__((visibility("default")))
+#else
+#define UF_API
+#endif
+
+typedef enum uf_status {
+    UF_OK = 0,
+    UF_ERR_INVALID_ARG = 1,
+    UF_ERR_IO = 2,          /* model file missing / unreadable (nn.rs:156-162 would download) */
+    UF_ERR_ONNX = 3,        /* malformed protobuf / missing initialiser */
+    UF_ERR_UNSUPPORTED = 4, /* graph uses an operator/shape outside the UltraFace family */
+    UF_ERR_CUDA = 5,        /* CUDA runtime error (message carries cudaGetErrorString) */
+    UF_ERR_NO_DEVICE = 6,   /* no CUDA device: there is NO CPU fallback */
+    UF_ERR_CAPACITY = 7     /* batch larger than max_batch, or K larger than the model's */
+} uf_status;
+
+/* Opaque model handle. Replaces `struct UltrafaceModel` (nn.rs:45-51). */
+typedef struct uf_model uf_model;
+
+/*
+ * One detection. Replaces the element type of `Vec<(Bbox, f32)>` (nn.rs:12,25):
+ * Bbox = [x_top_left, y_top_left, x_bottom_right, y_bottom_right], relative
+ * coordinates (unclamped), followed by the confidence. Rust tuples have no
+ * stable layout, so the wrapper converts uf_det -> (Bbox, f32).
+ */
+typedef struct uf_det {
+    float x0, y0, x1, y1;
+    float conf;
+} uf_det;
+
+/* Normalisation presets for nn.rs:82-91. */
+#define UF_NORM_REFERENCE 0u /* (x/255 - mean[c]) / std[c], ImageNet constants (nn.rs:86-88) */
+#define UF_NORM_127_128 1u   /* (x - 127) / 128, the upstream UltraFace convention */
+
+typedef struct uf_config {
+    uint32_t struct_size;    /* = sizeof(uf_config) */
+    const char* onnx_path;   /* UltraFace ONNX file (nn.rs:145-157 cache path); required */
+    uint32_t net_w, net_h;   /* UltrafaceVariant::width_height (nn.rs:36-41): 640x480 / 320x240 */
+    float max_iou;           /* nn.rs:55 */
+    float min_confidence;    /* nn.rs:55 */
+    int32_t device;          /* CUDA device ordinal */
+    uint32_t max_batch;      /* largest n accepted by uf_infer_batch* (>=1) */
+    uint32_t norm_preset;    /* UF_NORM_* */
+    uint32_t chunk;          /* frames per pipeline stage; 0 = auto */
+    uint32_t slots;          /* pipeline depth (streams); 0 = auto */
+    uint32_t resize_round_intermediate; /* 0 = image 0.24.x (f32 between passes); 1 = pre-0.24 */
+    uint32_t flags;          /* UF_FLAG_* */
+} uf_config;
+
+#define UF_FLAG_FORCE_GENERIC 1u /* debug: run every conv through the generic direct kernel */
+#define UF_FLAG_NO_GRAPH 2u      /* do not capture CUDA graphs for the batch-1 path */
+#define UF_FLAG_NO_FUSION 4u     /* debug: keep depthwise and pointwise convs as separate kernels */
+
+typedef struct uf_info {
+    uint32_t net_w, net_h;
+    uint32_t num_priors;     /* K: 4420 @320x240, 17640 @640x480 */
+    uint32_t num_layers;     /* device conv launches per chunk (after fusion) */
+    uint32_t num_tensors;    /* materialised activation tensors (uf_tensor_*) */
+    uint32_t max_batch, chunk, slots;
+    uint64_t weight_bytes;
+    uint64_t workspace_bytes;
+    uint64_t algorithmic_bytes_per_frame; /* SURVEY.md §8(d) figure for this graph, from 640x480 input */
+    uint64_t macs_per_frame;
+} uf_info;
+
+/* ---- load / free: replaces UltrafaceModel::new + get_model (nn.rs:55-67,143-175) ---- */
+UF_API int uf_model_load(const char* onnx_path, uint32_t net_w, uint32_t net_h, float max_iou,
+                  float min_confidence, int32_t device, uint32_t max_batch, uf_model** out);
+UF_API int uf_model_load_ex(const uf_config* cfg, uf_model** out);
+UF_API void uf_model_free(uf_model* m);
+UF_API int uf_model_info(const uf_model* m, uf_info* out);
+
+/* ---- per-frame call: replaces `InferModel::run(&self, &RgbImage)` (nn.rs:24-26,178-186) ----
+ * rgb: contiguous HWC u8, w*h*3 bytes, any size (RgbImage::as_raw()).
+ * out: up to cap detections in descending confidence (selection order, nn.rs:134-137);
+ * *n_out = number selected (if > cap only the first cap were written). */
+UF_API int uf_infer(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uf_det* out, uint32_t cap,
+             uint32_t* n_out);
+
+/* ---- batched call (what a stream batcher in inferer.rs:29-50 would call) ----
+ * rgb[i]: host pointer to frame i (pinned or pageable), w[i] x h[i]; out: n x cap; n_out: n. */
+UF_API int uf_infer_batch(uf_model* m, const uint8_t* const* rgb, const uint32_t* w, const uint32_t* h,
+                   uint32_t n, uf_det* out, uint32_t cap, uint32_t* n_out);
+
+/* Same, n frames of identical size contiguous in DEVICE memory (HBM-resident input). */
+UF_API int uf_infer_batch_device(uf_model* m, const uint8_t* d_rgb, uint32_t w, uint32_t h, uint32_t n,
+                          uf_det* out, uint32_t cap, uint32_t* n_out);
+
+/* ---- parity hooks (host buffers) ---- */
+/* Raw network outputs of frames [first, first+n) of the last batch: tract's outputs[0]
+ * `scores` n x K x 2 and outputs[1] `boxes` n x K x 4 (nn.rs:111-120). */
+UF_API int uf_raw_outputs(uf_model* m, uint32_t first, uint32_t n, float* scores, float* boxes);
+/* nn.rs:74-80 alone: out_u8 = net_h x net_w x 3. */
+UF_API int uf_preproc_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t* out_u8);
+/* nn.rs:70-94: out = 1 x 3 x net_h x net_w f32 (NCHW). */
+UF_API int uf_preproc_f32(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, float* out);
+/* nn.rs:109-140 + 198-260 alone on caller-supplied raw tensors (scores K x 2, boxes K x 4). */
+UF_API int uf_postproc(uf_model* m, const float* scores, const float* boxes, uint32_t K, uf_det* out,
+                uint32_t cap, uint32_t* n_out, int32_t* out_prior_idx /* nullable, cap */);
+/* Materialised activation tensors of the last batch, addressed by ONNX value name. */
+UF_API int uf_tensor_count(const uf_model* m, uint32_t* n);
+UF_API int uf_tensor_info(const uf_model* m, uint32_t i, const char** onnx_name, uint32_t* c, uint32_t* h,
+                   uint32_t* w);
+/* Copies tensor i of frame `frame` of the last batch's FIRST chunk as NCHW f32 (c*h*w floats). */
+UF_API int uf_tensor_read(uf_model* m, uint32_t i, uint32_t frame, float* out_nchw);
+
+/* ---- pinned host memory for the frames fed to uf_infer_batch ---- */
+UF_API int uf_host_alloc(size_t bytes, void** out);
+UF_API void uf_host_free(void* p);
+
+/* ---- measurement: per-kernel-family CUDA-event timing on the launching streams ---- */
+typedef struct uf_kernel_stat {
+    char name[48];
+    uint64_t launches;
+    double device_ms;          /* sum of CUDA-event durations */
+    uint64_t algorithmic_bytes; /* SURVEY.md 8(d) convention: sum over Conv nodes of (in+out)*4 */
+    uint64_t compulsory_bytes;  /* what the launch must move (fusion removes the intermediate) */
+    uint64_t flops;
+} uf_kernel_stat;
+UF_API int uf_profile_enable(uf_model* m, int on); /* on: event pair around every launch (serialises slots) */
+UF_API int uf_profile_reset(uf_model* m);
+UF_API int uf_profile_read(uf_model* m, uf_kernel_stat* out, uint32_t cap, uint32_t* n_out);
+/* number of kernel launches issued by this handle since load (the library's own kernels only) */
+UF_API int uf_launch_count(const uf_model* m, uint64_t* n);
+
+/* ---- host-only entry points (no GPU needed): loader / lowering / tap tables ---- */
+/* Parses + lowers the ONNX file and writes a JSON description (ops after folding with weight
+ * checksums, heads, prior count, MACs, bytes) into out[cap]; *needed = bytes incl. NUL. */
+UF_API int uf_onnx_inspect(const char* onnx_path, uint32_t net_w, uint32_t net_h, char* out, size_t cap,
+                           size_t* needed);
+/* One axis of the triangle resize (image 0.24.5 sample.rs): returns max taps via *max_taps; when
+ * left/ntaps/w are non-NULL fills left[dst_len], ntaps[dst_len], w[dst_len * w_pitch]. */
+UF_API int uf_resize_taps(uint32_t src_len, uint32_t dst_len, int32_t* left, int32_t* ntaps, float* w,
+                          uint32_t w_pitch, uint32_t* max_taps);
+
+UF_API const char* uf_last_error(void);
+UF_API const char* uf_version(void);
+UF_API int uf_device_count(int32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULTRAFACE_B200_H */

@@ -1,0 +1,1012 @@
+// engine.cu — model handle, weight prepack, chunked stream pipeline and the C ABI
+// (include/ultraface_b200.h). Host-side replacement for `UltrafaceModel::{new,run}`
+// (/root/reference/infer_server/src/nn.rs:55-67,178-186): the reference runs one frame at a
+// time through tract on one CPU thread; here a batch is cut into chunks, each chunk flows
+// H2D -> K1 resize -> conv stack -> K8 tail -> K9-11 post -> D2H on its own CUDA stream
+// ("slot"), so the copy of chunk i+1 overlaps the kernels of chunk i. No CPU fallback exists:
+// without a CUDA device uf_model_load fails with UF_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ultraface_b200.h"
+#include "kernels.h"
+#include "onnx_graph.h"
+#include "plan.h"
+#include "resize_taps.h"
+
+namespace uf {
+
+struct CudaError : public std::exception {
+    std::string msg;
+    explicit CudaError(std::string m) : msg(std::move(m)) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+struct ArgError : public std::exception {
+    std::string msg;
+    int code;
+    ArgError(int c, std::string m) : msg(std::move(m)), code(c) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                            std::to_string(__LINE__) + ")");                                       \
+    } while (0)
+
+static thread_local std::string g_last_error;
+
+enum class Impl { Generic, Stem, Depthwise, Pointwise, FusedDwPw, SmallDense, Add, Relu, Copy };
+
+static const char* impl_name(Impl i) {
+    switch (i) {
+        case Impl::Generic: return "conv_generic";
+        case Impl::Stem: return "stem_3x3s2_u8";
+        case Impl::Depthwise: return "depthwise3x3";
+        case Impl::Pointwise: return "pointwise1x1";
+        case Impl::FusedDwPw: return "fused_dw3x3_pw1x1";
+        case Impl::SmallDense: return "small_dense3x3";
+        case Impl::Add: return "eltwise_add";
+        case Impl::Relu: return "eltwise_relu";
+        case Impl::Copy: return "eltwise_copy";
+    }
+    return "?";
+}
+
+struct Step {
+    Impl impl = Impl::Generic;
+    int op = -1, op2 = -1;  // plan op indices (op2: the pointwise of a fused pair)
+    uint64_t alg_bytes = 0;  // SURVEY.md §8(d) convention: sum over Conv nodes of (in+out)*4, per frame
+    uint64_t min_bytes = 0;  // compulsory traffic of this launch (fusion removes the intermediate), per frame
+    uint64_t flops = 0;      // per frame
+};
+
+struct TapsEntry {
+    AxisTaps v, h;
+    int *d_vleft = nullptr, *d_vn = nullptr, *d_hleft = nullptr, *d_hn = nullptr;
+    float *d_vw = nullptr, *d_hw = nullptr;
+    ResizeTapsDev dev{};
+};
+
+constexpr int DET_FAST = 128;  // detections per frame copied back with the counts in one D2H
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t* d_in = nullptr;
+    size_t d_in_cap = 0;
+    uint8_t* d_resized = nullptr;
+    float* d_arena = nullptr;
+    float *d_dets = nullptr, *d_sel = nullptr;
+    int *d_counts = nullptr, *d_det_idx = nullptr;
+    unsigned long long* d_sort = nullptr;
+    int* h_counts = nullptr;   // pinned [chunk]
+    float* h_dets = nullptr;   // pinned [chunk][DET_FAST][5]
+    // pending work description
+    bool pending = false;
+    uint32_t first = 0, n = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;  // profiling pairs
+    std::vector<int> ev_stat;                             // stat index per pair
+    size_t ev_used = 0;
+};
+
+struct KernelStat {
+    std::string name;
+    uint64_t launches = 0;
+    double ms = 0;
+    uint64_t alg_bytes = 0, min_bytes = 0, flops = 0;
+};
+
+}  // namespace uf
+
+using namespace uf;
+
+struct uf_model {
+    std::mutex mu;
+    uf_config cfg{};
+    std::string onnx_path;
+    Plan plan;
+    int K = 0;
+    uint32_t chunk = 0, nslots = 0;
+    std::vector<Step> steps;
+    std::vector<size_t> w_off, b_off;  // per plan op, floats into d_weights
+    float* d_weights = nullptr;
+    uint64_t weight_bytes = 0, workspace_bytes = 0;
+    float* d_lut = nullptr;
+    float* d_priors = nullptr;
+    float *d_scores = nullptr, *d_boxes = nullptr;  // raw outputs of the last batch [max_batch][K][2|4]
+    std::vector<Slot> slots;
+    std::map<std::pair<int, int>, TapsEntry> taps;
+    uint32_t last_n = 0;
+    uint64_t launches = 0;
+    bool profiling = false;
+    std::vector<KernelStat> stats;
+    std::map<std::string, int> stat_index;
+    // hook scratch (uf_postproc / uf_preproc_*), grown on demand
+    void* d_hook = nullptr;
+    size_t d_hook_cap = 0;
+    std::vector<uint8_t> tensor_readable;  // per plan tensor: materialised in the arena
+
+    ~uf_model();
+};
+
+namespace uf {
+
+static inline int64_t align4(int64_t v) { return (v + 3) / 4 * 4; }
+
+static TView make_view(const uf_model& m, const Slot& s, int t) {
+    const TensorDesc& td = m.plan.tensors[t];
+    const BufferDesc& b = m.plan.buffers[td.buf];
+    TView v;
+    v.p = s.d_arena + b.arena_off * (int64_t)m.chunk + td.base_off;
+    v.frame_stride = align4(b.frame_floats);
+    v.pix_stride = td.pix_stride;
+    v.C = td.C; v.H = td.H; v.W = td.W;
+    return v;
+}
+
+static bool view_vec_ok(const TensorDesc& td) { return td.C % 4 == 0 && td.pix_stride % 4 == 0 && td.base_off % 4 == 0; }
+
+static int stat_id(uf_model& m, const std::string& name) {
+    auto it = m.stat_index.find(name);
+    if (it != m.stat_index.end()) return it->second;
+    KernelStat k;
+    k.name = name;
+    m.stats.push_back(k);
+    m.stat_index[name] = (int)m.stats.size() - 1;
+    return (int)m.stats.size() - 1;
+}
+
+// ---- profiling helpers: an event pair around one launch on the slot's stream
+struct ProfScope {
+    uf_model& m;
+    Slot& s;
+    bool on;
+    ProfScope(uf_model& mm, Slot& ss, const std::string& name, uint64_t alg, uint64_t minb, uint64_t flops)
+        : m(mm), s(ss), on(mm.profiling) {
+        m.launches++;
+        if (!on) return;
+        int id = stat_id(m, name);
+        m.stats[id].launches++;
+        m.stats[id].alg_bytes += alg;
+        m.stats[id].min_bytes += minb;
+        m.stats[id].flops += flops;
+        if (s.ev_used == s.ev.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            s.ev.emplace_back(a, b);
+            s.ev_stat.push_back(0);
+        }
+        s.ev_stat[s.ev_used] = id;
+        cudaEventRecord(s.ev[s.ev_used].first, s.stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(s.ev[s.ev_used].second, s.stream);
+        s.ev_used++;
+    }
+};
+
+static void collect_profile(uf_model& m, Slot& s) {
+    for (size_t i = 0; i < s.ev_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.ev[i].first, s.ev[i].second) == cudaSuccess) m.stats[s.ev_stat[i]].ms += ms;
+    }
+    s.ev_used = 0;
+}
+
+// ---- build: weights, steps, buffers -------------------------------------------------------
+static void pack_weights(uf_model& m) {
+    std::vector<float> blob;
+    m.w_off.assign(m.plan.ops.size(), 0);
+    m.b_off.assign(m.plan.ops.size(), 0);
+    for (size_t i = 0; i < m.plan.ops.size(); ++i) {
+        const Op& op = m.plan.ops[i];
+        if (op.kind != OpKind::Conv) continue;
+        const int cin_g = op.cin / op.groups, k = op.k;
+        while (blob.size() % 4) blob.push_back(0.f);
+        m.w_off[i] = blob.size();
+        // ONNX [co][ci_g][ky][kx] -> [ky][kx][ci_g][co]: the one layout every conv kernel reads
+        // (depthwise: [tap][C]; pointwise: [Cin][Cout]; dense: [ky][kx][ci][co])
+        blob.resize(blob.size() + (size_t)k * k * cin_g * op.cout);
+        float* dst = blob.data() + m.w_off[i];
+        for (int co = 0; co < op.cout; ++co)
+            for (int ci = 0; ci < cin_g; ++ci)
+                for (int ky = 0; ky < k; ++ky)
+                    for (int kx = 0; kx < k; ++kx)
+                        dst[((size_t)(ky * k + kx) * cin_g + ci) * op.cout + co] =
+                            op.w[(((size_t)co * cin_g + ci) * k + ky) * k + kx];
+        while (blob.size() % 4) blob.push_back(0.f);
+        m.b_off[i] = blob.size();
+        blob.insert(blob.end(), op.b.begin(), op.b.end());
+    }
+    while (blob.size() % 4) blob.push_back(0.f);
+    m.weight_bytes = blob.size() * sizeof(float);
+    CK(cudaMalloc(&m.d_weights, std::max<size_t>(m.weight_bytes, 16)));
+    CK(cudaMemcpy(m.d_weights, blob.data(), m.weight_bytes, cudaMemcpyHostToDevice));
+}
+
+static void build_steps(uf_model& m) {
+    const Plan& p = m.plan;
+    const bool force_generic = m.cfg.flags & UF_FLAG_FORCE_GENERIC;
+    const bool no_fusion = m.cfg.flags & UF_FLAG_NO_FUSION;
+    std::vector<int> uses(p.tensors.size(), 0);
+    for (auto& op : p.ops) {
+        if (op.in >= 0) uses[op.in]++;
+        if (op.in2 >= 0) uses[op.in2]++;
+    }
+    m.tensor_readable.assign(p.tensors.size(), 1);
+    m.tensor_readable[0] = 0;  // graph input is u8
+    auto bytes_of = [&](int t) { const TensorDesc& d = p.tensors[t]; return 4ull * d.C * d.H * d.W; };
+    auto macs_of = [&](const Op& op) {
+        const TensorDesc& o = p.tensors[op.out];
+        return (uint64_t)o.H * o.W * op.cout * (op.cin / op.groups) * op.k * op.k;
+    };
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+        const Op& op = p.ops[i];
+        Step st;
+        st.op = (int)i;
+        if (op.kind != OpKind::Conv) {
+            st.impl = op.kind == OpKind::Add ? Impl::Add : op.kind == OpKind::Relu ? Impl::Relu : Impl::Copy;
+            st.min_bytes = bytes_of(op.in) + bytes_of(op.out) + (op.in2 >= 0 ? bytes_of(op.in2) : 0);
+            m.steps.push_back(st);
+            continue;
+        }
+        const TensorDesc& in = p.tensors[op.in];
+        const TensorDesc& out = p.tensors[op.out];
+        st.alg_bytes = bytes_of(op.in) + bytes_of(op.out);
+        st.min_bytes = (in.is_input ? 3ull * in.H * in.W : bytes_of(op.in)) + bytes_of(op.out) +
+                       (op.in2 >= 0 ? bytes_of(op.in2) : 0);
+        st.flops = 2 * macs_of(op);
+        st.impl = Impl::Generic;
+        const bool dw = op.k == 3 && op.groups == op.cin && op.cin == op.cout && op.pad == 1 && op.dil == 1 &&
+                        (op.stride == 1 || op.stride == 2) && op.in2 < 0 && !in.is_input && view_vec_ok(in) && view_vec_ok(out);
+        const bool pw = op.k == 1 && op.groups == 1 && op.stride == 1 && op.pad == 0 && !in.is_input && view_vec_ok(in);
+        if (!force_generic) {
+            if (in.is_input) {
+                if (op.k == 3 && op.stride == 2 && op.pad == 1 && op.dil == 1 && op.groups == 1 && op.cin == 3 &&
+                    op.cout == 16 && op.in2 < 0 && view_vec_ok(out))
+                    st.impl = Impl::Stem;
+            } else if (dw) {
+                st.impl = Impl::Depthwise;
+                if (!no_fusion && i + 1 < p.ops.size()) {
+                    const Op& nx = p.ops[i + 1];
+                    const bool nx_pw = nx.kind == OpKind::Conv && nx.k == 1 && nx.groups == 1 && nx.stride == 1 &&
+                                       nx.pad == 0 && nx.in == op.out && nx.in2 < 0;
+                    if (nx_pw && uses[op.out] == 1 && !out.in_concat && fused_dwpw_supported(op.cout, nx.cout)) {
+                        st.impl = Impl::FusedDwPw;
+                        st.op2 = (int)i + 1;
+                        st.alg_bytes += bytes_of(nx.in) + bytes_of(nx.out);
+                        st.min_bytes = bytes_of(op.in) + bytes_of(nx.out);
+                        st.flops += 2 * macs_of(nx);
+                        m.tensor_readable[op.out] = 0;
+                        m.steps.push_back(st);
+                        ++i;
+                        continue;
+                    }
+                }
+            } else if (pw) {
+                st.impl = Impl::Pointwise;
+            } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.groups == 1 && op.in2 < 0 &&
+                       small_dense_supported(op.cin, op.cout) && view_vec_ok(in) && view_vec_ok(out)) {
+                st.impl = Impl::SmallDense;
+            }
+        }
+        m.steps.push_back(st);
+    }
+}
+
+static void build_lut(uf_model& m) {
+    // nn.rs:85-88: (px as f32 / 255.0 - mean[c]) / std[c]; f32 operations in that order
+    static const float mean[3] = {0.485f, 0.456f, 0.406f};
+    static const float stdv[3] = {0.229f, 0.224f, 0.225f};
+    std::vector<float> lut(768);
+    for (int c = 0; c < 3; ++c)
+        for (int v = 0; v < 256; ++v) {
+            float r;
+            if (m.cfg.norm_preset == UF_NORM_127_128) {
+                volatile float d = (float)v - 127.0f;
+                r = d / 128.0f;
+            } else {
+                volatile float q = (float)v / 255.0f;
+                volatile float d = q - mean[c];
+                r = d / stdv[c];
+            }
+            lut[c * 256 + v] = r;
+        }
+    CK(cudaMalloc(&m.d_lut, 768 * sizeof(float)));
+    CK(cudaMemcpy(m.d_lut, lut.data(), 768 * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+static void alloc_slots(uf_model& m) {
+    const int K = m.K;
+    const size_t H = m.plan.net_h, W = m.plan.net_w;
+    const size_t sort_cap = post_sort_scratch_elems(K);
+    m.slots.resize(m.nslots);
+    uint64_t ws = 0;
+    for (auto& s : m.slots) {
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        s.d_in_cap = (size_t)m.chunk * 640 * 480 * 3;
+        CK(cudaMalloc(&s.d_in, s.d_in_cap));
+        CK(cudaMalloc(&s.d_resized, (size_t)m.chunk * H * W * 3));
+        const size_t arena = (size_t)m.plan.arena_frame_floats * m.chunk * sizeof(float);
+        CK(cudaMalloc(&s.d_arena, arena));
+        CK(cudaMemsetAsync(s.d_arena, 0, arena, s.stream));
+        CK(cudaMalloc(&s.d_dets, (size_t)m.chunk * K * 5 * sizeof(float)));
+        CK(cudaMalloc(&s.d_sel, (size_t)m.chunk * K * 4 * sizeof(float)));
+        CK(cudaMalloc(&s.d_det_idx, (size_t)m.chunk * K * sizeof(int)));
+        CK(cudaMalloc(&s.d_counts, (size_t)m.chunk * sizeof(int)));
+        CK(cudaMalloc(&s.d_sort, (size_t)m.chunk * sort_cap * sizeof(unsigned long long)));
+        CK(cudaMallocHost(&s.h_counts, (size_t)m.chunk * sizeof(int)));
+        CK(cudaMallocHost(&s.h_dets, (size_t)m.chunk * DET_FAST * 5 * sizeof(float)));
+        ws += s.d_in_cap + (size_t)m.chunk * H * W * 3 + arena + (size_t)m.chunk * K * (5 + 4 + 1) * 4 +
+              (size_t)m.chunk * sort_cap * 8;
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    CK(cudaMalloc(&m.d_scores, (size_t)m.cfg.max_batch * K * 2 * sizeof(float)));
+    CK(cudaMalloc(&m.d_boxes, (size_t)m.cfg.max_batch * K * 4 * sizeof(float)));
+    ws += (size_t)m.cfg.max_batch * K * 6 * sizeof(float);
+    m.workspace_bytes = ws;
+}
+
+static TapsEntry& get_taps(uf_model& m, int sw, int sh) {
+    auto key = std::make_pair(sw, sh);
+    auto it = m.taps.find(key);
+    if (it != m.taps.end()) return it->second;
+    TapsEntry e;
+    e.v = build_axis_taps(sh, m.plan.net_h);
+    e.h = build_axis_taps(sw, m.plan.net_w);
+    auto up_i = [](const std::vector<int32_t>& v, int** d) {
+        CK(cudaMalloc(d, v.size() * sizeof(int)));
+        CK(cudaMemcpy(*d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+    };
+    auto up_f = [](const std::vector<float>& v, float** d) {
+        CK(cudaMalloc(d, v.size() * sizeof(float)));
+        CK(cudaMemcpy(*d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    };
+    up_i(e.v.left, &e.d_vleft); up_i(e.v.ntaps, &e.d_vn); up_f(e.v.w, &e.d_vw);
+    up_i(e.h.left, &e.d_hleft); up_i(e.h.ntaps, &e.d_hn); up_f(e.h.w, &e.d_hw);
+    // CTA tile: 64 x 8 destination pixels unless the source span would not fit in shared memory
+    int tw = 64, th = 8;
+    int cols = max_tile_span(e.h, tw);
+    while ((size_t)th * cols * 3 * sizeof(float) > 96 * 1024 && (tw > 8 || th > 1)) {
+        if (th > 1) th /= 2; else tw /= 2;
+        cols = max_tile_span(e.h, tw);
+    }
+    if ((size_t)th * cols * 3 * sizeof(float) > 200 * 1024)
+        throw ArgError(UF_ERR_UNSUPPORTED, "resize ratio too large for the shared-memory tile (source " +
+                                               std::to_string(sw) + "x" + std::to_string(sh) + ")");
+    e.dev = ResizeTapsDev{e.d_vleft, e.d_vn, e.d_vw, e.v.max_taps, e.d_hleft, e.d_hn, e.d_hw, e.h.max_taps, tw, th, cols};
+    return m.taps.emplace(key, std::move(e)).first->second;
+}
+
+// ---- execution -----------------------------------------------------------------------------
+static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames) {
+    const Plan& p = m.plan;
+    for (const Step& st : m.steps) {
+        const Op& op = p.ops[st.op];
+        ProfScope ps(m, s, impl_name(st.impl), st.alg_bytes * frames, st.min_bytes * frames, st.flops * frames);
+        const float* w = m.d_weights + m.w_off[st.op];
+        const float* b = m.d_weights + m.b_off[st.op];
+        TView out = make_view(m, s, op.out);
+        TView in = p.tensors[op.in].is_input ? TView{} : make_view(m, s, op.in);
+        TView res;
+        if (op.in2 >= 0) res = make_view(m, s, op.in2);
+        switch (st.impl) {
+            case Impl::Generic: {
+                ConvParams cp{op.cin, op.cout, op.k, op.stride, op.pad, op.dil, op.groups, op.relu ? 1 : 0};
+                launch_conv_generic(in, p.tensors[op.in].is_input ? &input : nullptr, m.d_lut, out,
+                                    op.in2 >= 0 ? &res : nullptr, w, b, cp, frames, s.stream);
+                break;
+            }
+            case Impl::Stem: launch_stem(input, m.d_lut, out, w, b, op.relu, frames, s.stream); break;
+            case Impl::Depthwise: launch_depthwise(in, out, w, b, op.stride, op.relu, frames, s.stream); break;
+            case Impl::Pointwise:
+                launch_pointwise(in, out, op.in2 >= 0 ? &res : nullptr, w, b, op.relu, frames, s.stream);
+                break;
+            case Impl::FusedDwPw: {
+                const Op& pw = p.ops[st.op2];
+                TView o2 = make_view(m, s, pw.out);
+                launch_fused_dwpw(in, o2, w, b, op.stride, op.relu, m.d_weights + m.w_off[st.op2],
+                                  m.d_weights + m.b_off[st.op2], pw.relu, frames, s.stream);
+                break;
+            }
+            case Impl::SmallDense: launch_small_dense(in, out, w, b, op.dil, op.relu, frames, s.stream); break;
+            case Impl::Add: launch_add(in, res, out, op.relu, frames, s.stream); break;
+            case Impl::Relu: launch_relu(in, out, frames, s.stream); break;
+            case Impl::Copy: launch_copy(in, out, frames, s.stream); break;
+        }
+    }
+}
+
+static void wait_slot(uf_model& m, Slot& s) {
+    CK(cudaStreamSynchronize(s.stream));
+    if (m.profiling) collect_profile(m, s);
+}
+
+// copy results of a finished slot into the caller's arrays
+static void harvest(uf_model& m, Slot& s, uf_det* out, uint32_t cap, uint32_t* n_out) {
+    if (!s.pending) return;
+    wait_slot(m, s);
+    s.pending = false;
+    const int K = m.K;
+    for (uint32_t i = 0; i < s.n; ++i) {
+        const uint32_t cnt = (uint32_t)s.h_counts[i];
+        const uint32_t g = s.first + i;
+        if (n_out) n_out[g] = cnt;
+        if (!out || cap == 0) continue;
+        const uint32_t take = std::min(cnt, cap);
+        const uint32_t fast = std::min<uint32_t>(take, DET_FAST);
+        memcpy(out + (size_t)g * cap, s.h_dets + (size_t)i * DET_FAST * 5, (size_t)fast * sizeof(uf_det));
+        if (take > fast)  // rare: more than DET_FAST faces in one frame
+            CK(cudaMemcpy(out + (size_t)g * cap + fast, s.d_dets + ((size_t)i * K + fast) * 5,
+                          (size_t)(take - fast) * sizeof(uf_det), cudaMemcpyDeviceToHost));
+    }
+}
+
+// tail + post + D2H for `frames` frames whose conv outputs sit in slot s; global frame offset `first`
+static void run_tail_post(uf_model& m, Slot& s, uint32_t first, int frames) {
+    const int K = m.K;
+    TView conf, loc;
+    {
+        const BufferDesc& cb = m.plan.buffers[m.plan.conf_buf];
+        const BufferDesc& lb = m.plan.buffers[m.plan.loc_buf];
+        conf.p = s.d_arena + cb.arena_off * (int64_t)m.chunk; conf.frame_stride = align4(cb.frame_floats);
+        loc.p = s.d_arena + lb.arena_off * (int64_t)m.chunk; loc.frame_stride = align4(lb.frame_floats);
+    }
+    float* scores = m.d_scores + (size_t)first * K * 2;
+    float* boxes = m.d_boxes + (size_t)first * K * 4;
+    {
+        ProfScope ps(m, s, "tail_softmax_decode", (uint64_t)frames * K * 6 * 4 * 2, (uint64_t)frames * K * 6 * 4 * 2, 0);
+        launch_tail(conf.p, loc.p, conf.frame_stride, loc.frame_stride, m.d_priors, K, m.plan.center_variance,
+                    m.plan.size_variance, scores, boxes, frames, s.stream);
+    }
+    {
+        ProfScope ps(m, s, "post_threshold_sort_nms", (uint64_t)frames * K * 6 * 4, (uint64_t)frames * K * 6 * 4, 0);
+        PostBuffers pb{s.d_sort, (int)post_sort_scratch_elems(K), s.d_sel, s.d_dets, s.d_det_idx, s.d_counts};
+        launch_post(scores, boxes, K, m.cfg.min_confidence, m.cfg.max_iou, pb, frames, s.stream);
+    }
+    CK(cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)frames * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpy2DAsync(s.h_dets, (size_t)DET_FAST * 5 * sizeof(float), s.d_dets, (size_t)K * 5 * sizeof(float),
+                         (size_t)std::min(DET_FAST, K) * 5 * sizeof(float), frames, cudaMemcpyDeviceToHost, s.stream));
+}
+
+struct FrameSrc {
+    const uint8_t* p;
+    uint32_t w, h;
+};
+
+// One chunk of host frames on slot s.
+static void run_chunk_host(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t first, uint32_t n) {
+    const int W = m.plan.net_w, H = m.plan.net_h;
+    const size_t out_frame = (size_t)W * H * 3;
+    // total staging bytes for frames that need a resize
+    size_t need = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        if ((int)fr[i].w != W || (int)fr[i].h != H) need += (size_t)fr[i].w * fr[i].h * 3;
+    if (need > s.d_in_cap) {
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaFree(s.d_in));
+        s.d_in = nullptr;
+        CK(cudaMalloc(&s.d_in, need));
+        s.d_in_cap = need;
+    }
+    size_t off = 0;
+    uint32_t i = 0;
+    while (i < n) {
+        // run of frames with identical size (and, for the copy, contiguous host addresses)
+        uint32_t j = i + 1;
+        const size_t fb = (size_t)fr[i].w * fr[i].h * 3;
+        while (j < n && fr[j].w == fr[i].w && fr[j].h == fr[i].h) ++j;
+        const bool ident = (int)fr[i].w == W && (int)fr[i].h == H;
+        uint8_t* dst = ident ? s.d_resized + (size_t)i * out_frame : s.d_in + off;
+        uint32_t a = i;
+        while (a < j) {  // merge host-contiguous frames into one cudaMemcpyAsync
+            uint32_t b = a + 1;
+            while (b < j && fr[b].p == fr[b - 1].p + fb) ++b;
+            CK(cudaMemcpyAsync(dst + (size_t)(a - i) * fb, fr[a].p, (size_t)(b - a) * fb, cudaMemcpyHostToDevice, s.stream));
+            a = b;
+        }
+        if (!ident) {
+            TapsEntry& t = get_taps(m, fr[i].w, fr[i].h);
+            ProfScope ps(m, s, "resize_triangle", (uint64_t)(j - i) * (fb + out_frame), (uint64_t)(j - i) * (fb + out_frame), 0);
+            launch_resize(s.d_in + off, (long long)fb, fr[i].w, fr[i].h, s.d_resized + (size_t)i * out_frame,
+                          (long long)out_frame, W, H, (int)(j - i), t.dev, m.cfg.resize_round_intermediate, s.stream);
+            off += (size_t)(j - i) * fb;
+        }
+        i = j;
+    }
+    U8View input{s.d_resized, (long long)out_frame, H, W};
+    run_cnn(m, s, input, (int)n);
+    run_tail_post(m, s, first, (int)n);
+    s.pending = true; s.first = first; s.n = n;
+}
+
+// One chunk of device-resident frames (identical size, contiguous) on slot s.
+static void run_chunk_device(uf_model& m, Slot& s, const uint8_t* d_rgb, uint32_t w, uint32_t h, uint32_t first, uint32_t n) {
+    const int W = m.plan.net_w, H = m.plan.net_h;
+    const size_t out_frame = (size_t)W * H * 3, fb = (size_t)w * h * 3;
+    U8View input{s.d_resized, (long long)out_frame, H, W};
+    if ((int)w == W && (int)h == H) {
+        input.p = d_rgb;  // identity resize (sample.rs early return): the stem reads the caller's frames
+        input.frame_stride = (long long)fb;
+    } else {
+        TapsEntry& t = get_taps(m, w, h);
+        ProfScope ps(m, s, "resize_triangle", (uint64_t)n * (fb + out_frame), (uint64_t)n * (fb + out_frame), 0);
+        launch_resize(d_rgb, (long long)fb, w, h, s.d_resized, (long long)out_frame, W, H, (int)n, t.dev,
+                      m.cfg.resize_round_intermediate, s.stream);
+    }
+    run_cnn(m, s, input, (int)n);
+    run_tail_post(m, s, first, (int)n);
+    s.pending = true; s.first = first; s.n = n;
+}
+
+template <typename F>
+static void run_pipeline(uf_model& m, uint32_t n, uf_det* out, uint32_t cap, uint32_t* n_out, F&& submit) {
+    if (n > m.cfg.max_batch) throw ArgError(UF_ERR_CAPACITY, "batch of " + std::to_string(n) + " exceeds max_batch " + std::to_string(m.cfg.max_batch));
+    CK(cudaSetDevice(m.cfg.device));
+    const uint32_t nslots = m.profiling ? 1 : m.nslots;  // profiling: one stream, so event pairs time kernels alone
+    uint32_t c = 0;
+    for (uint32_t first = 0; first < n; first += m.chunk, ++c) {
+        Slot& s = m.slots[c % nslots];
+        harvest(m, s, out, cap, n_out);
+        submit(s, first, std::min(m.chunk, n - first));
+    }
+    for (uint32_t k = 0; k < nslots; ++k) harvest(m, m.slots[(c + k) % nslots], out, cap, n_out);
+    m.last_n = n;
+}
+
+static void* hook_scratch(uf_model& m, size_t bytes) {
+    if (bytes > m.d_hook_cap) {
+        if (m.d_hook) CK(cudaFree(m.d_hook));
+        m.d_hook = nullptr;
+        CK(cudaMalloc(&m.d_hook, bytes));
+        m.d_hook_cap = bytes;
+    }
+    return m.d_hook;
+}
+
+static uf_model* load_model(const uf_config& cfg_in) {
+    uf_config cfg = cfg_in;
+    if (!cfg.onnx_path) throw ArgError(UF_ERR_INVALID_ARG, "onnx_path is NULL");
+    if (cfg.net_w == 0 || cfg.net_h == 0 || cfg.net_w > 8192 || cfg.net_h > 8192) throw ArgError(UF_ERR_INVALID_ARG, "bad network input size");
+    if (cfg.max_batch == 0) cfg.max_batch = 1;
+    if (cfg.norm_preset > UF_NORM_127_128) throw ArgError(UF_ERR_INVALID_ARG, "unknown norm_preset");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        throw ArgError(UF_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) throw ArgError(UF_ERR_INVALID_ARG, "device ordinal out of range");
+    OnnxModel om = load_onnx_file(cfg.onnx_path);
+    std::unique_ptr<uf_model> m(new uf_model());
+    m->onnx_path = cfg.onnx_path;
+    m->cfg = cfg;
+    m->cfg.onnx_path = m->onnx_path.c_str();
+    m->plan = lower_ultraface(om, (int)cfg.net_w, (int)cfg.net_h);
+    m->K = m->plan.num_priors;
+    CK(cudaSetDevice(cfg.device));
+    // chunk: big enough to amortise launches, small enough that a chunk's activations
+    // (~arena_frame_floats*4 B per frame) do not dwarf the 126 MB L2
+    uint32_t chunk = cfg.chunk;
+    if (chunk == 0) chunk = (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 64 : 16;
+    chunk = std::min(chunk, cfg.max_batch);
+    m->chunk = chunk;
+    uint32_t nslots = cfg.slots ? cfg.slots : 3;
+    const uint32_t nchunks = (cfg.max_batch + chunk - 1) / chunk;
+    m->nslots = std::max<uint32_t>(1, std::min(nslots, nchunks));
+    pack_weights(*m);
+    build_steps(*m);
+    build_lut(*m);
+    CK(cudaMalloc(&m->d_priors, (size_t)m->K * 4 * sizeof(float)));
+    CK(cudaMemcpy(m->d_priors, m->plan.priors.data(), (size_t)m->K * 4 * sizeof(float), cudaMemcpyHostToDevice));
+    cudaError_t pe = (cudaError_t)post_configure();
+    if (pe != cudaSuccess) throw CudaError(std::string("post_configure: ") + cudaGetErrorString(pe));
+    alloc_slots(*m);
+    return m.release();
+}
+
+}  // namespace uf
+
+uf_model::~uf_model() {
+    cudaSetDevice(cfg.device);
+    for (auto& s : slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        cudaFree(s.d_in); cudaFree(s.d_resized); cudaFree(s.d_arena); cudaFree(s.d_dets); cudaFree(s.d_sel);
+        cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort);
+        cudaFreeHost(s.h_counts); cudaFreeHost(s.h_dets);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (auto& kv : taps) {
+        TapsEntry& t = kv.second;
+        cudaFree(t.d_vleft); cudaFree(t.d_vn); cudaFree(t.d_vw); cudaFree(t.d_hleft); cudaFree(t.d_hn); cudaFree(t.d_hw);
+    }
+    cudaFree(d_weights); cudaFree(d_lut); cudaFree(d_priors); cudaFree(d_scores); cudaFree(d_boxes); cudaFree(d_hook);
+}
+
+// ---- C ABI -----------------------------------------------------------------------------------
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return UF_OK;
+    } catch (const ArgError& e) { g_last_error = e.msg; return e.code;
+    } catch (const IoError& e) { g_last_error = e.msg; return UF_ERR_IO;
+    } catch (const UnsupportedError& e) { g_last_error = e.msg; return UF_ERR_UNSUPPORTED;
+    } catch (const CudaError& e) { g_last_error = e.msg; cudaGetLastError(); return UF_ERR_CUDA;
+    } catch (const std::bad_alloc&) { g_last_error = "out of host memory"; return UF_ERR_INVALID_ARG;
+    } catch (const std::exception& e) { g_last_error = e.what(); return UF_ERR_ONNX; }
+}
+
+#define REQUIRE(cond, msg) do { if (!(cond)) throw ArgError(UF_ERR_INVALID_ARG, msg); } while (0)
+
+extern "C" {
+
+int uf_model_load_ex(const uf_config* cfg, uf_model** out) {
+    return guarded([&] {
+        REQUIRE(cfg && out, "null argument");
+        REQUIRE(cfg->struct_size == sizeof(uf_config), "uf_config.struct_size mismatch");
+        *out = nullptr;
+        *out = load_model(*cfg);
+    });
+}
+
+int uf_model_load(const char* onnx_path, uint32_t net_w, uint32_t net_h, float max_iou, float min_confidence,
+                  int32_t device, uint32_t max_batch, uf_model** out) {
+    uf_config c;
+    memset(&c, 0, sizeof(c));
+    c.struct_size = sizeof(c);
+    c.onnx_path = onnx_path;
+    c.net_w = net_w; c.net_h = net_h;
+    c.max_iou = max_iou; c.min_confidence = min_confidence;
+    c.device = device; c.max_batch = max_batch;
+    return uf_model_load_ex(&c, out);
+}
+
+void uf_model_free(uf_model* m) { delete m; }
+
+int uf_model_info(const uf_model* m, uf_info* o) {
+    return guarded([&] {
+        REQUIRE(m && o, "null argument");
+        memset(o, 0, sizeof(*o));
+        o->net_w = m->plan.net_w; o->net_h = m->plan.net_h;
+        o->num_priors = m->K;
+        o->num_layers = (uint32_t)m->steps.size();
+        uint32_t nt = 0;
+        for (auto r : m->tensor_readable) nt += r;
+        o->num_tensors = nt;
+        o->max_batch = m->cfg.max_batch; o->chunk = m->chunk; o->slots = m->nslots;
+        o->weight_bytes = m->weight_bytes; o->workspace_bytes = m->workspace_bytes;
+        // preproc (640x480 u8 in + f32 NCHW out) + conv nodes + post (K*6*4)
+        const uint64_t pre = 640ull * 480 * 3 + 4ull * 3 * m->plan.net_w * m->plan.net_h;
+        o->algorithmic_bytes_per_frame = pre + m->plan.conv_bytes_per_frame + 24ull * m->K;
+        o->macs_per_frame = m->plan.macs_per_frame;
+    });
+}
+
+int uf_infer_batch(uf_model* m, const uint8_t* const* rgb, const uint32_t* w, const uint32_t* h, uint32_t n,
+                   uf_det* out, uint32_t cap, uint32_t* n_out) {
+    return guarded([&] {
+        REQUIRE(m && (n == 0 || (rgb && w && h)) && n_out, "null argument");
+        REQUIRE(cap == 0 || out, "out is NULL with cap > 0");
+        std::vector<FrameSrc> fr(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            REQUIRE(rgb[i] && w[i] > 0 && h[i] > 0 && w[i] <= 16384 && h[i] <= 16384, "bad frame " + std::to_string(i));
+            fr[i] = FrameSrc{rgb[i], w[i], h[i]};
+        }
+        std::lock_guard<std::mutex> lk(m->mu);
+        run_pipeline(*m, n, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
+            run_chunk_host(*m, s, fr.data() + first, first, cnt);
+        });
+    });
+}
+
+int uf_infer(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uf_det* out, uint32_t cap, uint32_t* n_out) {
+    const uint8_t* ptrs[1] = {rgb};
+    return uf_infer_batch(m, ptrs, &w, &h, 1, out, cap, n_out);
+}
+
+int uf_infer_batch_device(uf_model* m, const uint8_t* d_rgb, uint32_t w, uint32_t h, uint32_t n, uf_det* out,
+                          uint32_t cap, uint32_t* n_out) {
+    return guarded([&] {
+        REQUIRE(m && (n == 0 || d_rgb) && n_out && w > 0 && h > 0, "bad argument");
+        REQUIRE(cap == 0 || out, "out is NULL with cap > 0");
+        std::lock_guard<std::mutex> lk(m->mu);
+        const size_t fb = (size_t)w * h * 3;
+        run_pipeline(*m, n, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
+            run_chunk_device(*m, s, d_rgb + (size_t)first * fb, w, h, first, cnt);
+        });
+    });
+}
+
+int uf_raw_outputs(uf_model* m, uint32_t first, uint32_t n, float* scores, float* boxes) {
+    return guarded([&] {
+        REQUIRE(m, "null model");
+        std::lock_guard<std::mutex> lk(m->mu);
+        REQUIRE((uint64_t)first + n <= m->last_n, "frame range outside the last batch");
+        CK(cudaSetDevice(m->cfg.device));
+        if (scores) CK(cudaMemcpy(scores, m->d_scores + (size_t)first * m->K * 2, (size_t)n * m->K * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (boxes) CK(cudaMemcpy(boxes, m->d_boxes + (size_t)first * m->K * 4, (size_t)n * m->K * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+static void preproc_to_slot0(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h) {
+    Slot& s = m->slots[0];
+    const int W = m->plan.net_w, H = m->plan.net_h;
+    const size_t fb = (size_t)w * h * 3;
+    if ((int)w == W && (int)h == H) {
+        CK(cudaMemcpyAsync(s.d_resized, rgb, fb, cudaMemcpyHostToDevice, s.stream));
+    } else {
+        if (fb > s.d_in_cap) {
+            CK(cudaStreamSynchronize(s.stream));
+            CK(cudaFree(s.d_in));
+            s.d_in = nullptr;
+            CK(cudaMalloc(&s.d_in, fb));
+            s.d_in_cap = fb;
+        }
+        CK(cudaMemcpyAsync(s.d_in, rgb, fb, cudaMemcpyHostToDevice, s.stream));
+        TapsEntry& t = get_taps(*m, w, h);
+        m->launches++;
+        launch_resize(s.d_in, (long long)fb, w, h, s.d_resized, (long long)W * H * 3, W, H, 1, t.dev,
+                      m->cfg.resize_round_intermediate, s.stream);
+    }
+}
+
+int uf_preproc_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t* out_u8) {
+    return guarded([&] {
+        REQUIRE(m && rgb && out_u8 && w > 0 && h > 0, "bad argument");
+        std::lock_guard<std::mutex> lk(m->mu);
+        CK(cudaSetDevice(m->cfg.device));
+        preproc_to_slot0(m, rgb, w, h);
+        Slot& s = m->slots[0];
+        CK(cudaMemcpyAsync(out_u8, s.d_resized, (size_t)m->plan.net_w * m->plan.net_h * 3, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+    });
+}
+
+int uf_preproc_f32(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, float* out) {
+    return guarded([&] {
+        REQUIRE(m && rgb && out && w > 0 && h > 0, "bad argument");
+        std::lock_guard<std::mutex> lk(m->mu);
+        CK(cudaSetDevice(m->cfg.device));
+        preproc_to_slot0(m, rgb, w, h);
+        Slot& s = m->slots[0];
+        const size_t nfl = (size_t)3 * m->plan.net_w * m->plan.net_h;
+        float* d = (float*)hook_scratch(*m, nfl * sizeof(float));
+        m->launches++;
+        launch_normalise_nchw(s.d_resized, m->plan.net_w, m->plan.net_h, m->d_lut, d, s.stream);
+        CK(cudaMemcpyAsync(out, d, nfl * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+    });
+}
+
+int uf_postproc(uf_model* m, const float* scores, const float* boxes, uint32_t K, uf_det* out, uint32_t cap,
+                uint32_t* n_out, int32_t* out_prior_idx) {
+    return guarded([&] {
+        REQUIRE(m && n_out && (K == 0 || (scores && boxes)), "null argument");
+        REQUIRE(cap == 0 || out, "out is NULL with cap > 0");
+        REQUIRE(K <= (1u << 20), "K too large");
+        *n_out = 0;
+        if (K == 0) return;
+        std::lock_guard<std::mutex> lk(m->mu);
+        CK(cudaSetDevice(m->cfg.device));
+        Slot& s = m->slots[0];
+        const size_t sort_cap = post_sort_scratch_elems((int)K);
+        // layout: scores | boxes | sel | dets | idx | count | sort keys
+        size_t o_scores = 0, o_boxes = o_scores + (size_t)K * 2 * 4, o_sel = o_boxes + (size_t)K * 4 * 4,
+               o_dets = o_sel + (size_t)K * 4 * 4, o_idx = o_dets + (size_t)K * 5 * 4, o_cnt = o_idx + (size_t)K * 4,
+               o_sort = (o_cnt + 4 + 15) / 16 * 16, total = o_sort + sort_cap * 8;
+        char* d = (char*)hook_scratch(*m, total);
+        CK(cudaMemcpyAsync(d + o_scores, scores, (size_t)K * 2 * 4, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(d + o_boxes, boxes, (size_t)K * 4 * 4, cudaMemcpyHostToDevice, s.stream));
+        PostBuffers pb{(unsigned long long*)(d + o_sort), (int)sort_cap, (float*)(d + o_sel), (float*)(d + o_dets),
+                       (int*)(d + o_idx), (int*)(d + o_cnt)};
+        m->launches++;
+        launch_post((const float*)(d + o_scores), (const float*)(d + o_boxes), (int)K, m->cfg.min_confidence,
+                    m->cfg.max_iou, pb, 1, s.stream);
+        int cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, d + o_cnt, 4, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+        *n_out = (uint32_t)cnt;
+        const uint32_t take = std::min<uint32_t>((uint32_t)cnt, cap);
+        if (take) {
+            CK(cudaMemcpy(out, d + o_dets, (size_t)take * sizeof(uf_det), cudaMemcpyDeviceToHost));
+            if (out_prior_idx) CK(cudaMemcpy(out_prior_idx, d + o_idx, (size_t)take * 4, cudaMemcpyDeviceToHost));
+        }
+    });
+}
+
+int uf_tensor_count(const uf_model* m, uint32_t* n) {
+    return guarded([&] {
+        REQUIRE(m && n, "null argument");
+        *n = (uint32_t)m->plan.tensors.size();
+    });
+}
+
+int uf_tensor_info(const uf_model* m, uint32_t i, const char** onnx_name, uint32_t* c, uint32_t* h, uint32_t* w) {
+    return guarded([&] {
+        REQUIRE(m && i < m->plan.tensors.size(), "tensor index out of range");
+        const TensorDesc& t = m->plan.tensors[i];
+        if (onnx_name) *onnx_name = m->tensor_readable[i] ? t.name.c_str() : "";
+        if (c) *c = t.C;
+        if (h) *h = t.H;
+        if (w) *w = t.W;
+    });
+}
+
+int uf_tensor_read(uf_model* m, uint32_t i, uint32_t frame, float* out_nchw) {
+    return guarded([&] {
+        REQUIRE(m && out_nchw && i < m->plan.tensors.size(), "bad argument");
+        REQUIRE(m->tensor_readable[i], "tensor is not materialised (graph input, or fused away)");
+        std::lock_guard<std::mutex> lk(m->mu);
+        REQUIRE(frame < m->last_n, "frame outside the last batch");
+        const uint32_t nchunks = (m->last_n + m->chunk - 1) / m->chunk, c = frame / m->chunk;
+        REQUIRE(c + m->nslots >= nchunks, "that chunk's workspace has been reused by a later chunk");
+        CK(cudaSetDevice(m->cfg.device));
+        Slot& s = m->slots[c % m->nslots];
+        TView v = make_view(*m, s, (int)i);
+        const size_t nfl = (size_t)v.C * v.H * v.W;
+        float* d = (float*)hook_scratch(*m, nfl * sizeof(float));
+        launch_nhwc_to_nchw(v, (int)(frame % m->chunk), d, s.stream);
+        CK(cudaMemcpyAsync(out_nchw, d, nfl * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+    });
+}
+
+int uf_host_alloc(size_t bytes, void** out) {
+    return guarded([&] {
+        REQUIRE(out, "null argument");
+        *out = nullptr;
+        CK(cudaMallocHost(out, bytes ? bytes : 1));
+    });
+}
+
+void uf_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int uf_profile_enable(uf_model* m, int on) {
+    return guarded([&] {
+        REQUIRE(m, "null model");
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->profiling = on != 0;
+    });
+}
+
+int uf_profile_reset(uf_model* m) {
+    return guarded([&] {
+        REQUIRE(m, "null model");
+        std::lock_guard<std::mutex> lk(m->mu);
+        for (auto& s : m->stats) { s.launches = 0; s.ms = 0; s.alg_bytes = 0; s.min_bytes = 0; s.flops = 0; }
+    });
+}
+
+int uf_profile_read(uf_model* m, uf_kernel_stat* out, uint32_t cap, uint32_t* n_out) {
+    return guarded([&] {
+        REQUIRE(m && n_out, "null argument");
+        std::lock_guard<std::mutex> lk(m->mu);
+        *n_out = (uint32_t)m->stats.size();
+        for (uint32_t i = 0; i < cap && i < m->stats.size(); ++i) {
+            memset(&out[i], 0, sizeof(out[i]));
+            snprintf(out[i].name, sizeof(out[i].name), "%s", m->stats[i].name.c_str());
+            out[i].launches = m->stats[i].launches;
+            out[i].device_ms = m->stats[i].ms;
+            out[i].algorithmic_bytes = m->stats[i].alg_bytes;
+            out[i].compulsory_bytes = m->stats[i].min_bytes;
+            out[i].flops = m->stats[i].flops;
+        }
+    });
+}
+
+int uf_launch_count(const uf_model* m, uint64_t* n) {
+    return guarded([&] {
+        REQUIRE(m && n, "null argument");
+        *n = m->launches;
+    });
+}
+
+int uf_onnx_inspect(const char* onnx_path, uint32_t net_w, uint32_t net_h, char* out, size_t cap, size_t* needed) {
+    return guarded([&] {
+        REQUIRE(onnx_path && needed, "null argument");
+        OnnxModel om = load_onnx_file(onnx_path);
+        Plan p = lower_ultraface(om, (int)net_w, (int)net_h);
+        std::string j = "{";
+        auto kv = [&](const std::string& k, const std::string& v, bool last = false) { j += "\"" + k + "\": " + v + (last ? "" : ", "); };
+        kv("num_priors", std::to_string(p.num_priors));
+        kv("macs_per_frame", std::to_string(p.macs_per_frame));
+        kv("conv_bytes_per_frame", std::to_string(p.conv_bytes_per_frame));
+        kv("arena_frame_floats", std::to_string(p.arena_frame_floats));
+        kv("priors_from_graph", p.priors_from_graph ? "true" : "false");
+        kv("center_variance", std::to_string(p.center_variance));
+        kv("size_variance", std::to_string(p.size_variance));
+        double ps = 0;
+        for (float v : p.priors) ps += v;
+        kv("priors_sum", std::to_string(ps));
+        std::string w = p.warnings;
+        for (auto& c : w) if (c == '"') c = '\'';
+        kv("warnings", "\"" + w + "\"");
+        std::string heads = "[";
+        for (size_t i = 0; i < p.heads.size(); ++i) {
+            const Head& h = p.heads[i];
+            heads += std::string(i ? ", " : "") + "{\"fm_w\": " + std::to_string(h.fm_w) + ", \"fm_h\": " + std::to_string(h.fm_h) +
+                     ", \"anchors\": " + std::to_string(h.anchors) + ", \"prior_off\": " + std::to_string(h.prior_off) + "}";
+        }
+        kv("heads", heads + "]");
+        std::string ops = "[";
+        for (size_t i = 0; i < p.ops.size(); ++i) {
+            const Op& o = p.ops[i];
+            double ws = 0, wa = 0, bs = 0;
+            for (float v : o.w) { ws += v; wa += std::fabs(v); }
+            for (float v : o.b) bs += v;
+            const TensorDesc& t = p.tensors[o.out];
+            char buf[640];
+            snprintf(buf, sizeof(buf),
+                     "%s{\"kind\": %d, \"out\": \"%s\", \"cin\": %d, \"cout\": %d, \"k\": %d, \"stride\": %d, \"pad\": %d, "
+                     "\"dil\": %d, \"groups\": %d, \"relu\": %d, \"residual\": %d, \"h\": %d, \"w\": %d, \"pix_stride\": %d, "
+                     "\"base_off\": %lld, \"w_sum\": %.9g, \"w_abs\": %.9g, \"b_sum\": %.9g}",
+                     i ? ", " : "", (int)o.kind, t.name.c_str(), o.cin, o.cout, o.k, o.stride, o.pad, o.dil, o.groups, o.relu ? 1 : 0,
+                     o.in2 >= 0 ? 1 : 0, t.H, t.W, t.pix_stride, (long long)t.base_off, ws, wa, bs);
+            ops += buf;
+        }
+        kv("ops", ops + "]", true);
+        j += "}";
+        *needed = j.size() + 1;
+        if (out && cap) {
+            size_t n = std::min(cap - 1, j.size());
+            memcpy(out, j.data(), n);
+            out[n] = 0;
+        }
+    });
+}
+
+int uf_resize_taps(uint32_t src_len, uint32_t dst_len, int32_t* left, int32_t* ntaps, float* w, uint32_t w_pitch,
+                   uint32_t* max_taps) {
+    return guarded([&] {
+        REQUIRE(src_len > 0 && dst_len > 0 && max_taps, "bad argument");
+        AxisTaps t = build_axis_taps((int)src_len, (int)dst_len);
+        *max_taps = (uint32_t)t.max_taps;
+        if (left && ntaps && w) {
+            REQUIRE(w_pitch >= (uint32_t)t.max_taps, "w_pitch smaller than max taps");
+            for (uint32_t o = 0; o < dst_len; ++o) {
+                left[o] = t.left[o];
+                ntaps[o] = t.ntaps[o];
+                for (uint32_t i = 0; i < w_pitch; ++i) w[(size_t)o * w_pitch + i] = i < (uint32_t)t.max_taps ? t.w[(size_t)o * t.max_taps + i] : 0.f;
+            }
+        }
+    });
+}
+
+const char* uf_last_error(void) { return g_last_error.c_str(); }
+const char* uf_version(void) { return "ultraface_b200 0.1 (sm_100a)"; }
+
+int uf_device_count(int32_t* n) {
+    return guarded([&] {
+        REQUIRE(n, "null argument");
+        int c = 0;
+        if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+        *n = c;
+    });
+}
+
+}  // extern "C"

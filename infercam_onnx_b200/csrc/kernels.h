@@ -1,0 +1,90 @@
+// kernels.h — launchers of the sm_100a kernels (K1..K11 of SURVEY.md §2).
+// Activations are NHWC fp32; the graph input is HWC u8 (RgbImage layout, nn.rs:24-26).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace uf {
+
+// NHWC fp32 view: addr(n,y,x,c) = p + n*frame_stride + (y*W + x)*pix_stride + c
+struct TView {
+    float* p = nullptr;
+    long long frame_stride = 0;
+    int pix_stride = 0;
+    int C = 0, H = 0, W = 0;
+};
+
+// HWC u8 frames (3 channels, dense)
+struct U8View {
+    const uint8_t* p = nullptr;
+    long long frame_stride = 0;
+    int H = 0, W = 0;
+};
+
+struct ConvParams {
+    int cin, cout, k, stride, pad, dil, groups, relu;
+};
+
+// Device-side tap tables of one (src,dst) size pair — image 0.24.5 sample.rs, see resize_taps.h
+struct ResizeTapsDev {
+    const int* vleft; const int* vn; const float* vw; int vmax;
+    const int* hleft; const int* hn; const float* hw; int hmax;
+    int tile_w, tile_h, max_cols;  // CTA tile of the destination and widest source span of a tile
+};
+
+// ---- K1: bit-exact triangle resize (nn.rs:74-80), frames HWC u8 -> HWC u8
+void launch_resize(const uint8_t* src, long long src_frame_stride, int sw, int sh, uint8_t* dst,
+                   long long dst_frame_stride, int dw, int dh, int frames, const ResizeTapsDev& t,
+                   int round_intermediate, cudaStream_t s);
+// ---- K2 (parity hook): LUT normalise + HWC->NCHW (nn.rs:82-91)
+void launch_normalise_nchw(const uint8_t* hwc, int w, int h, const float* lut, float* out, cudaStream_t s);
+
+// ---- convolutions. `lut` (3x256 floats) is used when the input is the u8 frame.
+void launch_conv_generic(const TView& in, const U8View* in_u8, const float* lut, const TView& out,
+                         const TView* res, const float* w_kkio, const float* b, const ConvParams& p,
+                         int frames, cudaStream_t s);
+// K3 stem: 3x3 s2 p1, 3 -> 16, u8 input through the LUT, bias + ReLU
+void launch_stem(const U8View& in, const float* lut, const TView& out, const float* w_kkio,
+                 const float* b, int relu, int frames, cudaStream_t s);
+// K4 depthwise 3x3 (pad 1, stride 1|2), weights [9][C]
+void launch_depthwise(const TView& in, const TView& out, const float* w_tc, const float* b, int stride,
+                      int relu, int frames, cudaStream_t s);
+// K5 pointwise 1x1, weights [Cin][Cout]; optional residual added before ReLU
+void launch_pointwise(const TView& in, const TView& out, const TView* res, const float* w_io,
+                      const float* b, int relu, int frames, cudaStream_t s);
+// K4+K5 fused: depthwise 3x3 (+bias+ReLU) kept in shared memory -> pointwise 1x1 (+bias, +-ReLU)
+bool fused_dwpw_supported(int C, int N);
+void launch_fused_dwpw(const TView& in, const TView& out, const float* dw_w_tc, const float* dw_b,
+                       int stride, int dw_relu, const float* pw_w_io, const float* pw_b, int pw_relu, int frames,
+                       cudaStream_t s);
+// K6 small dense 3x3 (stride 1, pad = dil), Cin,Cout in {8,12,16}, weights [3][3][Cin][Cout]
+bool small_dense_supported(int cin, int cout);
+void launch_small_dense(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil,
+                        int relu, int frames, cudaStream_t s);
+// fallbacks for graphs that do not fuse completely
+void launch_add(const TView& a, const TView& b, const TView& out, int relu, int frames, cudaStream_t s);
+void launch_relu(const TView& a, const TView& out, int frames, cudaStream_t s);
+void launch_copy(const TView& a, const TView& out, int frames, cudaStream_t s);
+// NHWC view -> dense NCHW (uf_tensor_read)
+void launch_nhwc_to_nchw(const TView& a, int frame, float* out, cudaStream_t s);
+
+// ---- K8: softmax over 2 classes + prior-box decode; conf [F,K,2], loc [F,K,4] raw head outputs
+void launch_tail(const float* conf, const float* loc, long long conf_frame_stride,
+                 long long loc_frame_stride, const float* priors, int K, float center_var,
+                 float size_var, float* scores, float* boxes, int frames, cudaStream_t s);
+
+// ---- K9-K11: threshold + sort + greedy NMS, one CTA per frame (nn.rs:109-140,198-260)
+struct PostBuffers {
+    unsigned long long* sort_scratch;  // [frames][sort_cap] keys, used when candidates exceed smem
+    int sort_cap;                      // power of two >= K
+    float* sel_boxes;                  // [frames][K][4] selected boxes (16-byte aligned working copy)
+    float* dets;                       // [frames][K][5]
+    int* det_idx;                      // [frames][K] prior index of each detection (nullable)
+    int* counts;                       // [frames]
+};
+void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
+                 const PostBuffers& pb, int frames, cudaStream_t s);
+size_t post_sort_scratch_elems(int K);  // sort_cap for a given K
+int post_configure();                   // opt in to large dynamic smem; returns cudaError_t
+
+}  // namespace uf

@@ -1,0 +1,623 @@
+// kernels_conv.cu — K3..K7: the UltraFace conv stack (replaces tract's SimplePlan::run,
+// /root/reference/infer_server/src/nn.rs:181). NHWC fp32 activations, fp32 accumulate
+// (BASELINE.json north_star: raw tensors within 1e-4 abs of the reference => no tf32/bf16 here).
+// Bias, folded BatchNorm, residual add and ReLU live in the epilogue of the producing conv.
+#include "kernels.h"
+
+namespace uf {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ---------------------------------------------------------------------------------------------
+// Generic direct convolution: one thread per output element, co fastest (coalesced stores,
+// coalesced weight reads from [ky][kx][ci][co]). Correct for every Conv the lowering accepts;
+// used for the shapes without a specialised kernel (e.g. the 256->6/12 3x3 heads on the 4x5 map)
+// and as the in-library cross-check (UF_FLAG_FORCE_GENERIC).
+// ---------------------------------------------------------------------------------------------
+template <bool U8IN>
+__global__ void __launch_bounds__(256)
+conv_generic_kernel(TView in, U8View in8, const float* __restrict__ lut, TView out, TView res, int has_res,
+                    const float* __restrict__ w, const float* __restrict__ b, ConvParams p, long long total) {
+    const int cin_g = p.cin / p.groups, cout_g = p.cout / p.groups;
+    const int Hi = U8IN ? in8.H : in.H, Wi = U8IN ? in8.W : in.W;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(idx % p.cout);
+        long long pix = idx / p.cout;
+        const int x = (int)(pix % out.W);
+        pix /= out.W;
+        const int y = (int)(pix % out.H);
+        const int n = (int)(pix / out.H);
+        const int g = co / cout_g;
+        float acc = b[co];
+        for (int ky = 0; ky < p.k; ++ky) {
+            const int iy = y * p.stride - p.pad + ky * p.dil;
+            if (iy < 0 || iy >= Hi) continue;
+            for (int kx = 0; kx < p.k; ++kx) {
+                const int ix = x * p.stride - p.pad + kx * p.dil;
+                if (ix < 0 || ix >= Wi) continue;
+                const float* wp = w + ((size_t)(ky * p.k + kx) * cin_g) * p.cout + co;
+                if (U8IN) {
+                    const uint8_t* ip = in8.p + (size_t)n * in8.frame_stride + ((size_t)iy * Wi + ix) * 3 + g * cin_g;
+                    for (int ci = 0; ci < cin_g; ++ci)
+                        acc = fmaf(lut[(g * cin_g + ci) * 256 + ip[ci]], wp[(size_t)ci * p.cout], acc);
+                } else {
+                    const float* ip = in.p + (size_t)n * in.frame_stride + ((size_t)iy * Wi + ix) * in.pix_stride + g * cin_g;
+                    for (int ci = 0; ci < cin_g; ++ci) acc = fmaf(ip[ci], wp[(size_t)ci * p.cout], acc);
+                }
+            }
+        }
+        const size_t opix = (size_t)y * out.W + x;
+        if (has_res) acc += res.p[(size_t)n * res.frame_stride + opix * res.pix_stride + co];
+        if (p.relu) acc = fmaxf(acc, 0.0f);
+        out.p[(size_t)n * out.frame_stride + opix * out.pix_stride + co] = acc;
+    }
+}
+
+static int grid_for(long long total, int block, int per_sm = 16) {
+    long long g = (total + block - 1) / block;
+    long long cap = 148LL * per_sm;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+void launch_conv_generic(const TView& in, const U8View* in_u8, const float* lut, const TView& out,
+                         const TView* res, const float* w_kkio, const float* b, const ConvParams& p,
+                         int frames, cudaStream_t s) {
+    long long total = (long long)frames * out.H * out.W * p.cout;
+    TView r = res ? *res : TView{};
+    if (in_u8)
+        conv_generic_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(in, *in_u8, lut, out, r, res != nullptr, w_kkio, b, p, total);
+    else
+        conv_generic_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(in, U8View{}, lut, out, r, res != nullptr, w_kkio, b, p, total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 stem: 3x3 stride 2 pad 1, 3 -> 16 channels, input = resized u8 frame normalised through
+// the LUT while it is staged (K2 fused: the f32 NCHW tensor of nn.rs:82-91 is never written).
+// CTA = 16x16 output pixels; 33x33x3 normalised inputs + weights in shared memory; each thread
+// keeps 16 accumulators and writes its pixel's 64 contiguous bytes.
+// ---------------------------------------------------------------------------------------------
+constexpr int STEM_T = 16;
+constexpr int STEM_IN = 2 * STEM_T + 1;
+
+__global__ void __launch_bounds__(STEM_T * STEM_T)
+stem_kernel(U8View in, const float* __restrict__ lut, TView out, const float* __restrict__ w,
+            const float* __restrict__ b, int relu) {
+    __shared__ float s_in[STEM_IN * STEM_IN * 3];
+    __shared__ __align__(16) float s_w[27 * 16];
+    __shared__ float s_lut[768];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+    for (int i = tid; i < 27 * 16; i += blockDim.x) s_w[i] = w[i];
+    __syncthreads();
+    const int ox0 = blockIdx.x * STEM_T, oy0 = blockIdx.y * STEM_T, n = blockIdx.z;
+    const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
+    const uint8_t* ip = in.p + (size_t)n * in.frame_stride;
+    for (int i = tid; i < STEM_IN * STEM_IN * 3; i += blockDim.x) {
+        const int c = i % 3, px = (i / 3) % STEM_IN, py = i / (3 * STEM_IN);
+        const int ix = ix0 + px, iy = iy0 + py;
+        float v = 0.0f;  // zero padding is applied in normalised space, as in the ONNX Conv
+        if (ix >= 0 && ix < in.W && iy >= 0 && iy < in.H) v = s_lut[c * 256 + ip[((size_t)iy * in.W + ix) * 3 + c]];
+        s_in[i] = v;
+    }
+    __syncthreads();
+    const int tx = tid % STEM_T, ty = tid / STEM_T;
+    const int ox = ox0 + tx, oy = oy0 + ty;
+    if (ox >= out.W || oy >= out.H) return;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = b[c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float v = s_in[((ty * 2 + ky) * STEM_IN + tx * 2 + kx) * 3 + ci];
+                const float4* wp = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * 3 + ci) * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 ww = wp[q];
+                    acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
+                    acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+                    acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
+                    acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+                }
+            }
+    float* op = out.p + (size_t)n * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 v = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        st4(op + q * 4, v);
+    }
+}
+
+void launch_stem(const U8View& in, const float* lut, const TView& out, const float* w_kkio, const float* b,
+                 int relu, int frames, cudaStream_t s) {
+    dim3 grid((out.W + STEM_T - 1) / STEM_T, (out.H + STEM_T - 1) / STEM_T, frames);
+    stem_kernel<<<grid, STEM_T * STEM_T, 0, s>>>(in, lut, out, w_kkio, b, relu);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 depthwise 3x3, pad 1, stride 1|2: one thread = one output pixel x 4 channels (float4), channel
+// quads fastest so a warp reads/writes contiguous NHWC bytes; the 3x3 neighbourhood re-reads hit L1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+depthwise3x3_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int stride,
+                    int relu, long long total) {
+    const int C4 = out.C >> 2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C4) * 4;
+        long long pix = idx / C4;
+        const int x = (int)(pix % out.W);
+        pix /= out.W;
+        const int y = (int)(pix % out.H);
+        const int n = (int)(pix / out.H);
+        float4 acc = ldg4(b + c);
+        const float* ip = in.p + (size_t)n * in.frame_stride + c;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = y * stride - 1 + ky;
+            if (iy < 0 || iy >= in.H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = x * stride - 1 + kx;
+                if (ix < 0 || ix >= in.W) continue;
+                const float4 v = ld4(ip + ((size_t)iy * in.W + ix) * in.pix_stride);
+                const float4 ww = ldg4(w + (ky * 3 + kx) * out.C + c);
+                acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+                acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+            }
+        }
+        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        st4(out.p + (size_t)n * out.frame_stride + ((size_t)y * out.W + x) * out.pix_stride + c, acc);
+    }
+}
+
+void launch_depthwise(const TView& in, const TView& out, const float* w_tc, const float* b, int stride, int relu,
+                      int frames, cudaStream_t s) {
+    long long total = (long long)frames * out.H * out.W * (out.C / 4);
+    depthwise3x3_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(in, out, w_tc, b, stride, relu, total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 pointwise 1x1 = GEMM  out[M=frames*H*W][N=Cout] = in[M][K=Cin] * W[K][N] (+bias, +res, ReLU).
+// SIMT fp32 (1e-4 parity contract). CTA tile BM x BN, BK = 32; A tile kept [m][k] (k contiguous,
+// +4 pad), B tile [k][n]; thread (tx,ty) owns columns tx*4..+3 and the interleaved rows
+// ty + i*RT, so LDS.128 of A rows from neighbouring ty hit different banks and every
+// k4-step is TM + 4 LDS.128 for 16*TM FFMA.
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN>
+__global__ void __launch_bounds__(256)
+pointwise_kernel(TView in, TView out, TView res, int has_res, const float* __restrict__ w,
+                 const float* __restrict__ b, int relu, long long M, int K, int N) {
+    constexpr int BK = 32, TN = 4;
+    constexpr int TXN = BN / TN;        // threads along n
+    constexpr int RT = 256 / TXN;       // threads along m
+    constexpr int TM = BM / RT;         // rows per thread
+    constexpr int LDA = BK + 4;
+    __shared__ __align__(16) float As[BM * LDA];
+    __shared__ __align__(16) float Bs[BK * BN];
+    const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int HW = in.H * in.W;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // A tile: BM rows x BK floats, float4 along k (Cin % 4 == 0 guaranteed by the dispatcher)
+        for (int i = tid; i < BM * (BK / 4); i += 256) {
+            const int r = i / (BK / 4), kq = (i % (BK / 4)) * 4;
+            const long long m = m0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && k0 + kq < K) {
+                const long long f = m / HW;
+                const int pix = (int)(m - f * HW);
+                v = ld4(in.p + f * in.frame_stride + (size_t)pix * in.pix_stride + k0 + kq);
+            }
+            st4(As + r * LDA + kq, v);
+        }
+        // B tile: BK x BN from W[K][N]
+        for (int i = tid; i < BK * BN; i += 256) {
+            const int kk = i / BN, nn = i % BN;
+            Bs[i] = (k0 + kk < K && n0 + nn < N) ? __ldg(w + (size_t)(k0 + kk) * N + n0 + nn) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kq = 0; kq < BK; kq += 4) {
+            float4 bv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = ld4(Bs + (kq + j) * BN + tx * TN);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                const float4 a = ld4(As + (ty + i * RT) * LDA + kq);
+                acc[i][0] = fmaf(a.x, bv[0].x, acc[i][0]); acc[i][1] = fmaf(a.x, bv[0].y, acc[i][1]);
+                acc[i][2] = fmaf(a.x, bv[0].z, acc[i][2]); acc[i][3] = fmaf(a.x, bv[0].w, acc[i][3]);
+                acc[i][0] = fmaf(a.y, bv[1].x, acc[i][0]); acc[i][1] = fmaf(a.y, bv[1].y, acc[i][1]);
+                acc[i][2] = fmaf(a.y, bv[1].z, acc[i][2]); acc[i][3] = fmaf(a.y, bv[1].w, acc[i][3]);
+                acc[i][0] = fmaf(a.z, bv[2].x, acc[i][0]); acc[i][1] = fmaf(a.z, bv[2].y, acc[i][1]);
+                acc[i][2] = fmaf(a.z, bv[2].z, acc[i][2]); acc[i][3] = fmaf(a.z, bv[2].w, acc[i][3]);
+                acc[i][0] = fmaf(a.w, bv[3].x, acc[i][0]); acc[i][1] = fmaf(a.w, bv[3].y, acc[i][1]);
+                acc[i][2] = fmaf(a.w, bv[3].z, acc[i][2]); acc[i][3] = fmaf(a.w, bv[3].w, acc[i][3]);
+            }
+        }
+        __syncthreads();
+    }
+    const int nb = n0 + tx * TN;
+    if (nb >= N) return;
+    float bias[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bias[j] = (nb + j < N) ? b[nb + j] : 0.f;
+    const bool vec = (nb + TN <= N) && ((out.pix_stride & 3) == 0) && ((N & 3) == 0) &&
+                     ((reinterpret_cast<size_t>(out.p) & 15) == 0) && ((out.frame_stride & 3) == 0);
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long m = m0 + ty + i * RT;
+        if (m >= M) continue;
+        const long long f = m / HW;
+        const int pix = (int)(m - f * HW);
+        float v[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) v[j] = acc[i][j] + bias[j];
+        if (has_res) {
+            const float* rp = res.p + f * res.frame_stride + (size_t)pix * res.pix_stride + nb;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) if (nb + j < N) v[j] += rp[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        float* op = out.p + f * out.frame_stride + (size_t)pix * out.pix_stride + nb;
+        if (vec) {
+            st4(op, make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) if (nb + j < N) op[j] = v[j];
+        }
+    }
+}
+
+void launch_pointwise(const TView& in, const TView& out, const TView* res, const float* w_io, const float* b,
+                      int relu, int frames, cudaStream_t s) {
+    const long long M = (long long)frames * in.H * in.W;
+    const int K = in.C, N = out.C;
+    TView r = res ? *res : TView{};
+    if (N > 32) {
+        dim3 grid((unsigned)((M + 127) / 128), (N + 63) / 64);
+        pointwise_kernel<128, 64><<<grid, 256, 0, s>>>(in, out, r, res != nullptr, w_io, b, relu, M, K, N);
+    } else if (N > 16) {
+        dim3 grid((unsigned)((M + 127) / 128), 1);
+        pointwise_kernel<128, 32><<<grid, 256, 0, s>>>(in, out, r, res != nullptr, w_io, b, relu, M, K, N);
+    } else {
+        dim3 grid((unsigned)((M + 127) / 128), 1);
+        pointwise_kernel<128, 16><<<grid, 256, 0, s>>>(in, out, r, res != nullptr, w_io, b, relu, M, K, N);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4+K5 fused: depthwise 3x3 (+bias+ReLU) -> pointwise 1x1 (+bias, +-ReLU). Every depthwise conv
+// of UltraFace feeds exactly one 1x1 conv (conv_dw blocks, the SSD `sep` heads, the extras), so
+// the depthwise result never has to reach HBM: a CTA computes the depthwise output of BM
+// consecutive output pixels (linear index over frames*H*W) for all C channels into shared memory
+// (phase 1, float4 over channels, coalesced NHWC reads, halo re-reads served by L1) and then runs
+// the BM x C x N GEMM against the 1x1 weights from there (phase 2, same register tiling as
+// pointwise_kernel). gridDim.y splits N so tiny maps still fill 148 SMs (phase 1 is recomputed per
+// split: 9 MAC/elt against N MAC/elt).
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK>
+__global__ void __launch_bounds__(256)
+fused_dwpw_kernel(TView in, TView out, const float* __restrict__ dw_w, const float* __restrict__ dw_b, int stride,
+                  int dw_relu, const float* __restrict__ pw_w, const float* __restrict__ pw_b, int pw_relu, long long M,
+                  int n_per_cta) {
+    constexpr int TN = 4, TXN = BN / TN, RT = 256 / TXN, TM = BM / RT;
+    extern __shared__ __align__(16) float smem[];
+    const int C = in.C, N = out.C, LDA = C + 4;
+    float* As = smem;                       // [BM][LDA] depthwise output
+    float* Bs = As + BM * LDA;              // [BK][BN]
+    int* s_xy = reinterpret_cast<int*>(Bs + BK * BN);  // [BM] packed (y << 16 | x), -1 = out of range
+    long long* s_base = reinterpret_cast<long long*>(s_xy + BM);  // [BM] frame offset into `in`
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int HWo = out.H * out.W;
+    for (int r = tid; r < BM; r += 256) {
+        const long long m = m0 + r;
+        if (m < M) {
+            const long long f = m / HWo;
+            const int pix = (int)(m - f * HWo);
+            const int y = pix / out.W;
+            s_xy[r] = (y << 16) | (pix - y * out.W);
+            s_base[r] = f * in.frame_stride;
+        } else {
+            s_xy[r] = -1;
+            s_base[r] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- phase 1: depthwise into shared memory
+    const int C4 = C >> 2;
+    for (int it = tid; it < BM * C4; it += 256) {
+        const int r = it / C4, c = (it - r * C4) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int xy = s_xy[r];
+        if (xy >= 0) {
+            const int y = xy >> 16, x = xy & 0xffff;
+            acc = ldg4(dw_b + c);
+            const float* ip = in.p + s_base[r] + c;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = y * stride - 1 + ky;
+                if (iy < 0 || iy >= in.H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = x * stride - 1 + kx;
+                    if (ix < 0 || ix >= in.W) continue;
+                    const float4 v = ld4(ip + ((size_t)iy * in.W + ix) * in.pix_stride);
+                    const float4 ww = ldg4(dw_w + (ky * 3 + kx) * C + c);
+                    acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+                    acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+                }
+            }
+            if (dw_relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        }
+        st4(As + r * LDA + c, acc);
+    }
+    // ---- phase 2: GEMM over this CTA's slice of N
+    const int tx = tid % TXN, ty = tid / TXN;
+    const int n_begin = blockIdx.y * n_per_cta;
+    const int n_end = min(N, n_begin + n_per_cta);
+    for (int n0 = n_begin; n0 < n_end; n0 += BN) {
+        float acc[TM][TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+        for (int k0 = 0; k0 < C; k0 += BK) {
+            __syncthreads();  // As complete (first pass) / previous Bs consumed
+            for (int i = tid; i < BK * BN; i += 256) {
+                const int kk = i / BN, nn = i % BN;
+                Bs[i] = (k0 + kk < C && n0 + nn < n_end) ? __ldg(pw_w + (size_t)(k0 + kk) * N + n0 + nn) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kq = 0; kq < BK; kq += 4) {
+                float4 bv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bv[j] = ld4(Bs + (kq + j) * BN + tx * TN);
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    const float4 a = ld4(As + (ty + i * RT) * LDA + k0 + kq);
+                    acc[i][0] = fmaf(a.x, bv[0].x, acc[i][0]); acc[i][1] = fmaf(a.x, bv[0].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.x, bv[0].z, acc[i][2]); acc[i][3] = fmaf(a.x, bv[0].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.y, bv[1].x, acc[i][0]); acc[i][1] = fmaf(a.y, bv[1].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.y, bv[1].z, acc[i][2]); acc[i][3] = fmaf(a.y, bv[1].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.z, bv[2].x, acc[i][0]); acc[i][1] = fmaf(a.z, bv[2].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.z, bv[2].z, acc[i][2]); acc[i][3] = fmaf(a.z, bv[2].w, acc[i][3]);
+                    acc[i][0] = fmaf(a.w, bv[3].x, acc[i][0]); acc[i][1] = fmaf(a.w, bv[3].y, acc[i][1]);
+                    acc[i][2] = fmaf(a.w, bv[3].z, acc[i][2]); acc[i][3] = fmaf(a.w, bv[3].w, acc[i][3]);
+                }
+            }
+        }
+        const int nb = n0 + tx * TN;
+        if (nb < n_end) {
+            float bias[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bias[j] = (nb + j < N) ? pw_b[nb + j] : 0.f;
+            const bool vec = (nb + TN <= N) && ((out.pix_stride & 3) == 0) && ((N & 3) == 0) &&
+                             ((reinterpret_cast<size_t>(out.p) & 15) == 0) && ((out.frame_stride & 3) == 0);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                const long long m = m0 + ty + i * RT;
+                if (m >= M) continue;
+                const long long f = m / HWo;
+                const int pix = (int)(m - f * HWo);
+                float v[TN];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    v[j] = acc[i][j] + bias[j];
+                    if (pw_relu) v[j] = fmaxf(v[j], 0.f);
+                }
+                float* op = out.p + f * out.frame_stride + (size_t)pix * out.pix_stride + nb;
+                if (vec) {
+                    st4(op, make_float4(v[0], v[1], v[2], v[3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) if (nb + j < N) op[j] = v[j];
+                }
+            }
+        }
+    }
+}
+
+bool fused_dwpw_supported(int C, int N) { return C % 4 == 0 && C >= 16 && C <= 256 && N >= 1; }
+
+template <int BM, int BN, int BK>
+static void launch_fused_t(const TView& in, const TView& out, const float* dw_w, const float* dw_b, int stride,
+                           int dw_relu, const float* pw_w, const float* pw_b, int pw_relu, int frames, cudaStream_t s) {
+    const long long M = (long long)frames * out.H * out.W;
+    const int N = out.C, C = in.C;
+    const int m_tiles = (int)((M + BM - 1) / BM);
+    const int n_tiles = (N + BN - 1) / BN;
+    // split N across CTAs only while the grid is smaller than ~2 waves
+    int split = 1;
+    while (split < n_tiles && (long long)m_tiles * split < 2 * 148) ++split;
+    const int tiles_per = (n_tiles + split - 1) / split;
+    const int n_per_cta = tiles_per * BN;
+    const int gy = (N + n_per_cta - 1) / n_per_cta;
+    const size_t smem = (size_t)(BM * (C + 4) + BK * BN) * sizeof(float) + BM * (sizeof(int) + sizeof(long long));
+    auto kern = fused_dwpw_kernel<BM, BN, BK>;
+    static bool configured[64] = {};  // per template instantiation and device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        configured[dev & 63] = true;
+    }
+    kern<<<dim3(m_tiles, gy), 256, smem, s>>>(in, out, dw_w, dw_b, stride, dw_relu, pw_w, pw_b, pw_relu, M, n_per_cta);
+}
+
+void launch_fused_dwpw(const TView& in, const TView& out, const float* dw_w_tc, const float* dw_b, int stride,
+                       int dw_relu, const float* pw_w_io, const float* pw_b, int pw_relu, int frames, cudaStream_t s) {
+    const int C = in.C, N = out.C;
+#define UF_F(BM, BN, BK) launch_fused_t<BM, BN, BK>(in, out, dw_w_tc, dw_b, stride, dw_relu, pw_w_io, pw_b, pw_relu, frames, s)
+    if (C == 16) {
+        if (N > 16) UF_F(128, 32, 16); else UF_F(128, 16, 16);
+    } else if (C > 128) {
+        if (N > 32) UF_F(64, 64, 32); else if (N > 16) UF_F(64, 32, 32); else UF_F(64, 16, 32);
+    } else {
+        if (N > 32) UF_F(128, 64, 32); else if (N > 16) UF_F(128, 32, 32); else UF_F(128, 16, 32);
+    }
+#undef UF_F
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 small dense 3x3 (RFB branches: 8->16, 8->12, 12->16, 16->16 with dilation 1/2/3/5; stride 1,
+// pad == dil). Weights [3][3][CIN][COUT] in shared memory, read as broadcast float4; each thread
+// computes two horizontally adjacent pixels x COUT so one weight LDS.128 feeds 8 FFMA.
+// ---------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128)
+small_dense3x3_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int dil,
+                      int relu, long long total_pairs) {
+    __shared__ __align__(16) float s_w[9 * CIN * COUT];
+    __shared__ float s_b[COUT];
+    for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) s_w[i] = w[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_b[i] = b[i];
+    __syncthreads();
+    const int Wp = (out.W + 1) >> 1;  // pixel pairs per row
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_pairs;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int xp = (int)(idx % Wp);
+        long long t = idx / Wp;
+        const int y = (int)(t % out.H);
+        const int n = (int)(t / out.H);
+        const int x0 = xp * 2;
+        const bool has1 = x0 + 1 < out.W;
+        float acc0[COUT], acc1[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { acc0[c] = s_b[c]; acc1[c] = s_b[c]; }
+        const float* ip = in.p + (size_t)n * in.frame_stride;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = y + (ky - 1) * dil;
+            if (iy < 0 || iy >= in.H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix0 = x0 + (kx - 1) * dil, ix1 = ix0 + 1;
+                const bool ok0 = ix0 >= 0 && ix0 < in.W;
+                const bool ok1 = has1 && ix1 >= 0 && ix1 < in.W;
+                if (!ok0 && !ok1) continue;
+                const float* p0 = ip + ((size_t)iy * in.W + (ok0 ? ix0 : 0)) * in.pix_stride;
+                const float* p1 = ip + ((size_t)iy * in.W + (ok1 ? ix1 : 0)) * in.pix_stride;
+#pragma unroll
+                for (int cq = 0; cq < CIN; cq += 4) {
+                    float4 a0 = ok0 ? ld4(p0 + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 a1 = ok1 ? ld4(p1 + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float av0[4] = {a0.x, a0.y, a0.z, a0.w};
+                    const float av1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const float4* wp = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CIN + cq + ci) * COUT);
+#pragma unroll
+                        for (int q = 0; q < COUT / 4; ++q) {
+                            const float4 ww = wp[q];
+                            acc0[q * 4 + 0] = fmaf(av0[ci], ww.x, acc0[q * 4 + 0]);
+                            acc0[q * 4 + 1] = fmaf(av0[ci], ww.y, acc0[q * 4 + 1]);
+                            acc0[q * 4 + 2] = fmaf(av0[ci], ww.z, acc0[q * 4 + 2]);
+                            acc0[q * 4 + 3] = fmaf(av0[ci], ww.w, acc0[q * 4 + 3]);
+                            acc1[q * 4 + 0] = fmaf(av1[ci], ww.x, acc1[q * 4 + 0]);
+                            acc1[q * 4 + 1] = fmaf(av1[ci], ww.y, acc1[q * 4 + 1]);
+                            acc1[q * 4 + 2] = fmaf(av1[ci], ww.z, acc1[q * 4 + 2]);
+                            acc1[q * 4 + 3] = fmaf(av1[ci], ww.w, acc1[q * 4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        float* op = out.p + (size_t)n * out.frame_stride + ((size_t)y * out.W + x0) * out.pix_stride;
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+            float4 v = make_float4(acc0[q * 4], acc0[q * 4 + 1], acc0[q * 4 + 2], acc0[q * 4 + 3]);
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            st4(op + q * 4, v);
+        }
+        if (has1) {
+#pragma unroll
+            for (int q = 0; q < COUT / 4; ++q) {
+                float4 v = make_float4(acc1[q * 4], acc1[q * 4 + 1], acc1[q * 4 + 2], acc1[q * 4 + 3]);
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                st4(op + out.pix_stride + q * 4, v);
+            }
+        }
+    }
+}
+
+bool small_dense_supported(int cin, int cout) {
+    return (cin == 8 && (cout == 16 || cout == 12)) || (cin == 12 && cout == 16) || (cin == 16 && cout == 16);
+}
+
+void launch_small_dense(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil, int relu,
+                        int frames, cudaStream_t s) {
+    const long long total = (long long)frames * out.H * ((out.W + 1) / 2);
+    const int grid = grid_for(total, 128, 32);
+#define UF_SD(CI, CO) small_dense3x3_kernel<CI, CO><<<grid, 128, 0, s>>>(in, out, w_kkio, b, dil, relu, total)
+    if (in.C == 8 && out.C == 16) UF_SD(8, 16);
+    else if (in.C == 8 && out.C == 12) UF_SD(8, 12);
+    else if (in.C == 12 && out.C == 16) UF_SD(12, 16);
+    else if (in.C == 16 && out.C == 16) UF_SD(16, 16);
+#undef UF_SD
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fallback element-wise ops (only reached by graphs whose Add/Relu/Concat do not fuse) and the
+// NHWC -> NCHW reader behind uf_tensor_read.
+// ---------------------------------------------------------------------------------------------
+__global__ void eltwise_kernel(TView a, TView b, int has_b, TView out, int relu, long long total) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % out.C);
+        long long pix = idx / out.C;
+        const int hw = out.H * out.W;
+        const long long n = pix / hw;
+        const int p = (int)(pix - n * hw);
+        float v = a.p[n * a.frame_stride + (size_t)p * a.pix_stride + c];
+        if (has_b) v += b.p[n * b.frame_stride + (size_t)p * b.pix_stride + c];
+        if (relu) v = fmaxf(v, 0.f);
+        out.p[n * out.frame_stride + (size_t)p * out.pix_stride + c] = v;
+    }
+}
+
+void launch_add(const TView& a, const TView& b, const TView& out, int relu, int frames, cudaStream_t s) {
+    long long total = (long long)frames * out.H * out.W * out.C;
+    eltwise_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, b, 1, out, relu, total);
+}
+void launch_relu(const TView& a, const TView& out, int frames, cudaStream_t s) {
+    long long total = (long long)frames * out.H * out.W * out.C;
+    eltwise_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, TView{}, 0, out, 1, total);
+}
+void launch_copy(const TView& a, const TView& out, int frames, cudaStream_t s) {
+    long long total = (long long)frames * out.H * out.W * out.C;
+    eltwise_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, TView{}, 0, out, 0, total);
+}
+
+__global__ void nhwc_to_nchw_kernel(TView a, int frame, float* __restrict__ out) {
+    const int total = a.C * a.H * a.W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i / (a.H * a.W), p = i - c * (a.H * a.W);
+        out[i] = a.p[(size_t)frame * a.frame_stride + (size_t)p * a.pix_stride + c];
+    }
+}
+void launch_nhwc_to_nchw(const TView& a, int frame, float* out, cudaStream_t s) {
+    int total = a.C * a.H * a.W;
+    nhwc_to_nchw_kernel<<<(total + 255) / 256, 256, 0, s>>>(a, frame, out);
+}
+
+}  // namespace uf

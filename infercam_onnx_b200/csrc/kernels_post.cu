@@ -1,0 +1,230 @@
+// kernels_post.cu — K8 (softmax + prior decode) and K9-K11 (threshold, sort, greedy NMS).
+//
+// K8 restates the in-graph tail of the UltraFace ONNX that tract executes
+// (/root/reference/infer_server/src/nn.rs:181):
+//   scores = softmax(conf, axis=2)
+//   c  = loc[:2] * center_variance * prior[2:] + prior[:2]
+//   wh = exp(loc[2:] * size_variance) * prior[2:]
+//   boxes = [c - wh/2, c + wh/2]
+// K9-K11 restate `postproc` + `non_maximum_suppression` + `iou` + `bbox_area`
+// (nn.rs:109-140, 198-260): strict `conf > min_confidence`, processing order = confidence
+// descending with ties broken towards the HIGHER prior index (stable ascending sort + pop()
+// from the back), suppression on strict `iou > max_iou`, EPS = 1e-7 inside the denominator,
+// every f32 operation rounded separately (no FMA) in the reference's left-to-right order.
+#include "kernels.h"
+
+namespace uf {
+
+__global__ void __launch_bounds__(256)
+tail_kernel(const float* __restrict__ conf, const float* __restrict__ loc, long long conf_fs, long long loc_fs,
+            const float* __restrict__ priors, int K, float cv, float sv, float* __restrict__ scores,
+            float* __restrict__ boxes, long long total) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long f = idx / K;
+        const int k = (int)(idx - f * K);
+        const float2 c = *reinterpret_cast<const float2*>(conf + f * conf_fs + 2 * (size_t)k);
+        const float4 l = *reinterpret_cast<const float4*>(loc + f * loc_fs + 4 * (size_t)k);
+        const float4 p = __ldg(reinterpret_cast<const float4*>(priors) + k);
+        const float m = fmaxf(c.x, c.y);
+        const float e0 = expf(c.x - m), e1 = expf(c.y - m);
+        const float s = e0 + e1;
+        *reinterpret_cast<float2*>(scores + (size_t)idx * 2) = make_float2(e0 / s, e1 / s);
+        const float cx = __fadd_rn(__fmul_rn(__fmul_rn(l.x, cv), p.z), p.x);
+        const float cy = __fadd_rn(__fmul_rn(__fmul_rn(l.y, cv), p.w), p.y);
+        const float w = __fmul_rn(expf(__fmul_rn(l.z, sv)), p.z);
+        const float h = __fmul_rn(expf(__fmul_rn(l.w, sv)), p.w);
+        const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+        *reinterpret_cast<float4*>(boxes + (size_t)idx * 4) =
+            make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+    }
+}
+
+void launch_tail(const float* conf, const float* loc, long long conf_frame_stride, long long loc_frame_stride,
+                 const float* priors, int K, float center_var, float size_var, float* scores, float* boxes,
+                 int frames, cudaStream_t s) {
+    long long total = (long long)frames * K;
+    long long g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    tail_kernel<<<(int)g, 256, 0, s>>>(conf, loc, conf_frame_stride, loc_frame_stride, priors, K, center_var,
+                                       size_var, scores, boxes, total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// post_kernel: one CTA per frame.
+//   1. count candidates (score > min_conf), pick the key array (shared memory if it fits)
+//   2. fill keys = (orderable(score) << 32 | prior index), pad to a power of two with 0
+//   3. bitonic sort, descending  => position order == the reference's pop() order
+//   4. greedy NMS in chunks of PT candidates: (A) every candidate of the chunk is tested against
+//      all boxes selected so far, (B) survivors are resolved against each other with a
+//      PT x PT bit matrix built by warp ballots and swept by one warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int PT = 256;      // threads per CTA == NMS chunk
+constexpr int PW = PT / 32;  // mask words per row
+constexpr int POST_SMEM_KEYS = 8192;
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// nn.rs:251-260 (the reference names the y-extent `width` and the x-extent `height`; same product)
+__device__ __forceinline__ float bbox_area(float x0, float y0, float x1, float y1) {
+    const float width = __fsub_rn(y1, y0);
+    const float height = __fsub_rn(x1, x0);
+    return (width < 0.0f || height < 0.0f) ? 0.0f : __fmul_rn(width, height);
+}
+
+// nn.rs:227-243
+__device__ __forceinline__ float iou(const float4 a, const float4 b) {
+    const float o = bbox_area(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fminf(a.z, b.z), fminf(a.w, b.w));
+    const float d = __fadd_rn(__fsub_rn(__fadd_rn(bbox_area(a.x, a.y, a.z, a.w), bbox_area(b.x, b.y, b.z, b.w)), o), 1.0e-7f);
+    return __fdiv_rn(o, d);
+}
+
+__global__ void __launch_bounds__(PT)
+post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, int K, float min_conf,
+            float max_iou, PostBuffers pb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // POST_SMEM_KEYS
+    float4* cbox = reinterpret_cast<float4*>(skeys + POST_SMEM_KEYS);             // PT
+    unsigned* mask = reinterpret_cast<unsigned*>(cbox + PT);                      // PT * PW
+    unsigned* alive_w = mask + PT * PW;                                           // PW
+    int* kept = reinterpret_cast<int*>(alive_w + PW);                             // PT
+    float* cscore = reinterpret_cast<float*>(kept + PT);                          // PT
+    int* cidx = reinterpret_cast<int*>(cscore + PT);                              // PT
+    __shared__ int s_cnt, s_nk;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
+    const float* sc = scores + (size_t)f * K * 2;
+    const float4* bx = reinterpret_cast<const float4*>(boxes + (size_t)f * K * 4);
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    // 1. count (strict >, NaN compares false: nn.rs:127)
+    int local = 0;
+    for (int k = tid; k < K; k += PT) local += sc[2 * (size_t)k + 1] > min_conf ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    const int n = s_cnt;
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    unsigned long long* keys = (n_pad <= POST_SMEM_KEYS) ? skeys : pb.sort_scratch + (size_t)f * pb.sort_cap;
+    __syncthreads();
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    // 2. fill (order irrelevant: keys are unique, the sort fixes the order)
+    for (int k0 = 0; k0 < K; k0 += PT) {
+        const int k = k0 + tid;
+        float v = 0.f;
+        bool c = false;
+        if (k < K) { v = sc[2 * (size_t)k + 1]; c = v > min_conf; }
+        const unsigned bal = __ballot_sync(0xffffffffu, c);
+        int basepos = 0;
+        if (lane == 0 && bal) basepos = atomicAdd(&s_cnt, __popc(bal));
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+        if (c) keys[basepos + __popc(bal & ((1u << lane) - 1))] = ((unsigned long long)f2ord(v) << 32) | (unsigned)k;
+    }
+    for (int i = n + tid; i < n_pad; i += PT) keys[i] = 0ull;
+    __syncthreads();
+    // 3. bitonic sort, descending
+    for (int k2 = 2; k2 <= n_pad; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_pad; i += PT) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k2) == 0;
+                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // 4. greedy NMS
+    float4* sel = reinterpret_cast<float4*>(pb.sel_boxes) + (size_t)f * K;
+    float* dets = pb.dets + (size_t)f * K * 5;
+    int* didx = pb.det_idx ? pb.det_idx + (size_t)f * K : nullptr;
+    int n_sel = 0;
+    for (int base = 0; base < n; base += PT) {
+        const int cnt = min(PT, n - base);
+        const bool valid = tid < cnt;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            const unsigned k = (unsigned)(keys[base + tid] & 0xffffffffull);
+            b = bx[k];
+            cscore[tid] = sc[2 * (size_t)k + 1];
+            cidx[tid] = (int)k;
+        }
+        bool alive = valid;
+        // (A) against everything selected so far (uniform loop, broadcast loads)
+        for (int s = 0; s < n_sel; ++s) {
+            const float4 sb = sel[s];
+            if (alive && iou(b, sb) > max_iou) alive = false;
+        }
+        cbox[tid] = b;
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) alive_w[warp] = bal;
+        __syncthreads();
+        // (B) bit matrix: row j, bit i  <=>  j alive, i alive, i after j, iou(i, j) > max_iou
+        for (int j = 0; j < cnt; ++j) {
+            const bool aj = (alive_w[j >> 5] >> (j & 31)) & 1u;  // CTA-uniform
+            unsigned word = 0;
+            if (aj) {
+                const bool pred = alive && tid > j && iou(b, cbox[j]) > max_iou;
+                word = __ballot_sync(0xffffffffu, pred);
+            }
+            if (lane == 0) mask[j * PW + warp] = word;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned rem = lane < PW ? ~alive_w[lane] : 0xffffffffu;
+            int nk = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const unsigned wj = __shfl_sync(0xffffffffu, rem, j >> 5);
+                if ((wj >> (j & 31)) & 1u) continue;  // suppressed or dead: warp-uniform
+                if (lane < PW) rem |= mask[j * PW + lane];
+                if (lane == 0) kept[nk] = j;
+                ++nk;
+            }
+            if (lane == 0) s_nk = nk;
+        }
+        __syncthreads();
+        const int nk = s_nk;
+        if (tid < nk) {
+            const int j = kept[tid];
+            const float4 kb = cbox[j];
+            sel[n_sel + tid] = kb;
+            float* d = dets + (size_t)(n_sel + tid) * 5;
+            d[0] = kb.x; d[1] = kb.y; d[2] = kb.z; d[3] = kb.w; d[4] = cscore[j];
+            if (didx) didx[n_sel + tid] = cidx[j];
+        }
+        n_sel += nk;
+        __syncthreads();  // sel[] visible to the next chunk's phase A; cbox/mask free for reuse
+    }
+    if (tid == 0) pb.counts[f] = n_sel;
+}
+
+static size_t post_smem_bytes() {
+    return POST_SMEM_KEYS * sizeof(unsigned long long) + PT * sizeof(float4) + PT * PW * sizeof(unsigned) +
+           PW * sizeof(unsigned) + PT * sizeof(int) + PT * sizeof(float) + PT * sizeof(int);
+}
+
+int post_configure() {
+    return (int)cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem_bytes());
+}
+
+size_t post_sort_scratch_elems(int K) {
+    size_t c = 1;
+    while (c < (size_t)K) c <<= 1;
+    return c;
+}
+
+void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
+                 const PostBuffers& pb, int frames, cudaStream_t s) {
+    post_kernel<<<frames, PT, post_smem_bytes(), s>>>(scores, boxes, K, min_conf, max_iou, pb);
+}
+
+}  // namespace uf

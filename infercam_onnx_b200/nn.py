@@ -1,0 +1,280 @@
+"""Python mirror of the reference's `infer_server::nn` public surface over the C ABI.
+
+Same names, argument meaning and error behaviour as
+/root/reference/infer_server/src/nn.rs — `Bbox` (nn.rs:12), `InferModel` (nn.rs:24-26),
+`UltrafaceVariant` + `width_height` (nn.rs:29-42), `UltrafaceModel::new(variant, max_iou,
+min_confidence)` (nn.rs:55) and `run(&RgbImage) -> Result<Vec<(Bbox, f32)>>` (nn.rs:178-186) —
+so the parity tests read like the reference's own integration test
+(infer_server/tests/integration_tests.rs). Rust's `anyhow::Error` becomes `UltrafaceError`.
+Everything numeric happens in libultraface_b200.so on the GPU; this file only marshals.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import json
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+
+Bbox = Tuple[float, float, float, float]  # [x_top_left, y_top_left, x_bottom_right, y_bottom_right], relative
+
+
+class UltrafaceError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{_capi.STATUS.get(code, code)}: {message}")
+        self.code = code
+
+
+class UltrafaceVariant(enum.Enum):
+    """nn.rs:29-42"""
+    W640H480 = (640, 480)
+    W320H240 = (320, 240)
+
+    def width_height(self) -> Tuple[int, int]:
+        return self.value
+
+    def model_file_name(self) -> str:
+        """nn.rs:144-147"""
+        return {UltrafaceVariant.W640H480: "ultraface-RFB-640.onnx", UltrafaceVariant.W320H240: "ultraface-RFB-320.onnx"}[self]
+
+
+class InferModel:
+    """nn.rs:24-26"""
+
+    def run(self, input: np.ndarray) -> List[Tuple[Bbox, float]]:  # noqa: A002 - the reference's parameter name
+        raise NotImplementedError
+
+
+def _check(rc: int) -> None:
+    if rc != _capi.UF_OK:
+        raise UltrafaceError(rc, _capi.load().uf_last_error().decode(errors="replace"))
+
+
+def default_model_path(variant: UltrafaceVariant) -> str:
+    """nn.rs:149-157: `dirs::cache_dir()/infercam_onnx/<model_name>` (no download here: no network)."""
+    cache = os.environ.get("XDG_CACHE_HOME") or os.path.join(os.path.expanduser("~"), ".cache")
+    return os.path.join(cache, "infercam_onnx", variant.model_file_name())
+
+
+class UltrafaceModel(InferModel):
+    """Loaded Ultraface model, ready for inference with post-processing thresholds (nn.rs:44-67)."""
+
+    def __init__(self, handle: int, variant_wh: Tuple[int, int], max_iou: float, min_confidence: float):
+        self._h = C.c_void_p(handle)
+        self.width, self.height = variant_wh
+        self.max_iou, self.min_confidence = max_iou, min_confidence
+        info = _capi.uf_info()
+        _check(_capi.load().uf_model_info(self._h, C.byref(info)))
+        self.info = info
+        self.num_priors = int(info.num_priors)
+        self.max_batch = int(info.max_batch)
+
+    @classmethod
+    def new(cls, variant: UltrafaceVariant, max_iou: float, min_confidence: float, *, onnx_path: Optional[str] = None,
+            device: int = 0, max_batch: int = 1, norm_preset: int = _capi.UF_NORM_REFERENCE, chunk: int = 0,
+            slots: int = 0, flags: int = 0, resize_round_intermediate: bool = False,
+            size: Optional[Tuple[int, int]] = None) -> "UltrafaceModel":
+        """`UltrafaceModel::new` (nn.rs:55). The keyword arguments are extra knobs the reference
+        hard-codes (cache path, nn.rs:149-157) or does not have (device, batch); `size` overrides the
+        variant's (width, height) for graphs exported at another resolution."""
+        lib = _capi.load()
+        wh = size or variant.width_height()
+        path = onnx_path or default_model_path(variant)
+        cfg = _capi.uf_config()
+        cfg.struct_size = C.sizeof(_capi.uf_config)
+        cfg.onnx_path = os.fsencode(path)
+        cfg.net_w, cfg.net_h = wh
+        cfg.max_iou, cfg.min_confidence = max_iou, min_confidence
+        cfg.device, cfg.max_batch, cfg.norm_preset = device, max_batch, norm_preset
+        cfg.chunk, cfg.slots, cfg.flags = chunk, slots, flags
+        cfg.resize_round_intermediate = int(resize_round_intermediate)
+        h = C.c_void_p()
+        _check(lib.uf_model_load_ex(C.byref(cfg), C.byref(h)))
+        return cls(h.value, wh, max_iou, min_confidence)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _capi.load().uf_model_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # Drop
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- InferModel::run (nn.rs:178-186)
+    def run(self, input: np.ndarray, cap: int = 256) -> List[Tuple[Bbox, float]]:  # noqa: A002
+        img = _as_rgb(input)
+        h, w = img.shape[:2]
+        out = (_capi.uf_det * cap)()
+        n = C.c_uint32()
+        _check(_capi.load().uf_infer(self._h, img.ctypes.data_as(C.c_void_p), w, h, out, cap, C.byref(n)))
+        if n.value > cap:
+            return self.run(img, cap=int(n.value))
+        return [((d.x0, d.y0, d.x1, d.y1), d.conf) for d in out[: n.value]]
+
+    # ---- batched calls
+    def run_batch(self, frames: Sequence[np.ndarray], cap: int = 256) -> List[np.ndarray]:
+        """Host frames (any sizes) -> per-frame [n_i, 5] arrays (x0, y0, x1, y1, conf)."""
+        imgs = [_as_rgb(f) for f in frames]
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        ws = (C.c_uint32 * n)(*[im.shape[1] for im in imgs])
+        hs = (C.c_uint32 * n)(*[im.shape[0] for im in imgs])
+        return self._run_batch_raw(lambda out, cnt: _capi.load().uf_infer_batch(self._h, ptrs, ws, hs, n, out, cap, cnt), n, cap)
+
+    def run_batch_ptr(self, host_ptr: int, w: int, h: int, n: int, cap: int = 256) -> List[np.ndarray]:
+        """n frames of w x h contiguous in (pinned) HOST memory at host_ptr."""
+        fb = w * h * 3
+        ptrs = (C.c_void_p * n)(*[host_ptr + i * fb for i in range(n)])
+        ws = (C.c_uint32 * n)(*([w] * n))
+        hs = (C.c_uint32 * n)(*([h] * n))
+        return self._run_batch_raw(lambda out, cnt: _capi.load().uf_infer_batch(self._h, ptrs, ws, hs, n, out, cap, cnt), n, cap)
+
+    def run_batch_device(self, device_ptr: int, w: int, h: int, n: int, cap: int = 256) -> List[np.ndarray]:
+        """n frames of w x h contiguous in DEVICE memory at device_ptr."""
+        return self._run_batch_raw(
+            lambda out, cnt: _capi.load().uf_infer_batch_device(self._h, C.c_void_p(device_ptr), w, h, n, out, cap, cnt), n, cap)
+
+    def _run_batch_raw(self, call, n: int, cap: int) -> List[np.ndarray]:
+        out = np.zeros((max(n, 1), cap, 5), np.float32)
+        cnt = (C.c_uint32 * max(n, 1))()
+        _check(call(out.ctypes.data_as(C.POINTER(_capi.uf_det)), cnt))
+        return [out[i, : min(cnt[i], cap)].copy() for i in range(n)], [int(cnt[i]) for i in range(n)]
+
+    # ---- parity hooks
+    def raw_outputs(self, first: int, n: int) -> Tuple[np.ndarray, np.ndarray]:
+        s = np.empty((n, self.num_priors, 2), np.float32)
+        b = np.empty((n, self.num_priors, 4), np.float32)
+        _check(_capi.load().uf_raw_outputs(self._h, first, n, s.ctypes.data_as(C.POINTER(C.c_float)),
+                                           b.ctypes.data_as(C.POINTER(C.c_float))))
+        return s, b
+
+    def preproc_u8(self, input: np.ndarray) -> np.ndarray:  # noqa: A002
+        img = _as_rgb(input)
+        out = np.empty((self.height, self.width, 3), np.uint8)
+        _check(_capi.load().uf_preproc_u8(self._h, img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0],
+                                          out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def preproc(self, input: np.ndarray) -> np.ndarray:  # noqa: A002
+        """nn.rs:70-94 -> f32 [1,3,H,W]"""
+        img = _as_rgb(input)
+        out = np.empty((1, 3, self.height, self.width), np.float32)
+        _check(_capi.load().uf_preproc_f32(self._h, img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0],
+                                           out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def postproc(self, scores: np.ndarray, boxes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """nn.rs:109-140 on caller-supplied raw tensors -> ([n,5] detections, [n] prior indices)."""
+        scores = np.ascontiguousarray(scores, np.float32).reshape(-1, 2)
+        boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 4)
+        K = scores.shape[0]
+        out = np.zeros((max(K, 1), 5), np.float32)
+        idx = np.zeros(max(K, 1), np.int32)
+        n = C.c_uint32()
+        _check(_capi.load().uf_postproc(self._h, scores.ctypes.data_as(C.POINTER(C.c_float)),
+                                        boxes.ctypes.data_as(C.POINTER(C.c_float)), K,
+                                        out.ctypes.data_as(C.POINTER(_capi.uf_det)), K, C.byref(n),
+                                        idx.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out[: n.value].copy(), idx[: n.value].copy()
+
+    def tensors(self) -> dict:
+        """ONNX value name -> (index, C, H, W) of every materialised activation tensor."""
+        lib = _capi.load()
+        n = C.c_uint32()
+        _check(lib.uf_tensor_count(self._h, C.byref(n)))
+        out = {}
+        for i in range(n.value):
+            name = C.c_char_p()
+            c, h, w = C.c_uint32(), C.c_uint32(), C.c_uint32()
+            _check(lib.uf_tensor_info(self._h, i, C.byref(name), C.byref(c), C.byref(h), C.byref(w)))
+            if name.value:
+                out[name.value.decode()] = (i, c.value, h.value, w.value)
+        return out
+
+    def tensor_read(self, index: int, frame: int, chw: Tuple[int, int, int]) -> np.ndarray:
+        out = np.empty(chw, np.float32)
+        _check(_capi.load().uf_tensor_read(self._h, index, frame, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    # ---- measurement
+    def profile_enable(self, on: bool) -> None:
+        _check(_capi.load().uf_profile_enable(self._h, int(on)))
+
+    def profile_reset(self) -> None:
+        _check(_capi.load().uf_profile_reset(self._h))
+
+    def profile_read(self) -> List[dict]:
+        arr = (_capi.uf_kernel_stat * 64)()
+        n = C.c_uint32()
+        _check(_capi.load().uf_profile_read(self._h, arr, 64, C.byref(n)))
+        return [dict(name=a.name.decode(), launches=int(a.launches), device_ms=float(a.device_ms),
+                     algorithmic_bytes=int(a.algorithmic_bytes), compulsory_bytes=int(a.compulsory_bytes),
+                     flops=int(a.flops)) for a in arr[: min(n.value, 64)]]
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        _check(_capi.load().uf_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+
+def _as_rgb(a: np.ndarray) -> np.ndarray:
+    """`&RgbImage` (nn.rs:25): contiguous HWC u8, any W x H."""
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+        raise UltrafaceError(1, f"expected an HxWx3 uint8 RGB image, got {a.dtype} {a.shape}")
+    return np.ascontiguousarray(a)
+
+
+def onnx_inspect(path: str, width: int, height: int) -> dict:
+    """Host-only: parse + lower an ONNX file and describe the launch plan (no GPU needed)."""
+    lib = _capi.load()
+    need = C.c_size_t()
+    _check(lib.uf_onnx_inspect(os.fsencode(path), width, height, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _check(lib.uf_onnx_inspect(os.fsencode(path), width, height, buf, need.value, C.byref(need)))
+    return json.loads(buf.value.decode())
+
+
+def resize_taps(src_len: int, dst_len: int):
+    """Host-only: (left, ntaps, w[dst, max_taps]) of one resize axis as the GPU kernel will use them."""
+    lib = _capi.load()
+    mt = C.c_uint32()
+    _check(lib.uf_resize_taps(src_len, dst_len, None, None, None, 0, C.byref(mt)))
+    left = np.zeros(dst_len, np.int32)
+    nt = np.zeros(dst_len, np.int32)
+    w = np.zeros((dst_len, mt.value), np.float32)
+    _check(lib.uf_resize_taps(src_len, dst_len, left.ctypes.data_as(C.POINTER(C.c_int32)),
+                              nt.ctypes.data_as(C.POINTER(C.c_int32)), w.ctypes.data_as(C.POINTER(C.c_float)),
+                              mt.value, C.byref(mt)))
+    return left, nt, w
+
+
+def device_count() -> int:
+    n = C.c_int32()
+    _check(_capi.load().uf_device_count(C.byref(n)))
+    return int(n.value)
+
+
+class PinnedFrames:
+    """n x h x w x 3 u8 frames in pinned host memory (uf_host_alloc), exposed as a numpy array."""
+
+    def __init__(self, n: int, h: int, w: int):
+        self.shape = (n, h, w, 3)
+        self.nbytes = n * h * w * 3
+        p = C.c_void_p()
+        _check(_capi.load().uf_host_alloc(self.nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr)).reshape(self.shape)
+
+    def free(self) -> None:
+        if self.ptr:
+            self.array = None
+            _capi.load().uf_host_free(C.c_void_p(self.ptr))
+            self.ptr = None

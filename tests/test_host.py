@@ -1,0 +1,125 @@
+"""CPU tests of the host side of the product: the C-ABI library loads and exports every declared
+symbol, the ONNX loader/lowering (no GPU needed) agrees with the oracle's independent reader, the
+resize tap tables are bit-identical to the oracle's, and errors are loud (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from infercam_onnx_b200 import _capi, nn
+from infercam_onnx_b200.onnx_fixture import generate_priors
+from oracle import hotpath
+from oracle.onnx_reader import load_onnx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ultraface_b200.h")).read()
+    declared = set(re.findall(r"UF_API\s+[\w\s\*]+?\b(uf_\w+)\s*\(", header))
+    assert len(declared) >= 24
+    lib = ctypes.CDLL(_capi.lib_path() if os.path.exists(_capi.lib_path()) else _capi._build.build())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ultraface_b200.h but not exported"
+    assert declared == set(_capi.SIGNATURES), "ctypes binding and header disagree"
+    assert b"sm_100a" in _capi.load().uf_version()
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_capi.uf_det) == 20
+    assert ctypes.sizeof(_capi.uf_kernel_stat) == 48 + 8 * 5
+
+
+@pytest.mark.parametrize("wh,variant,K,macs", [((320, 240), "RFB", 4420, 100.4e6), ((640, 480), "RFB", 17640, 399.2e6),
+                                               ((320, 240), "slim", 4420, 81.4e6)])
+def test_lowering_matches_survey_figures(make_onnx, wh, variant, K, macs):
+    d = nn.onnx_inspect(make_onnx(*wh, variant=variant), *wh)
+    assert d["num_priors"] == K
+    assert abs(d["macs_per_frame"] - macs) / macs < 0.005
+    assert d["priors_from_graph"] and d["warnings"] == ""
+    assert [h["anchors"] for h in d["heads"]] == [3, 2, 2, 3]
+    assert abs(d["priors_sum"] - float(generate_priors(*wh).astype(np.float64).sum())) < 1e-3
+    convs = [o for o in d["ops"] if o["kind"] == 0]
+    assert len(convs) == (52 if variant == "RFB" else 42) and len(convs) == len(d["ops"])  # everything fused
+    if wh == (320, 240) and variant == "RFB":
+        assert abs(d["conv_bytes_per_frame"] - 27.90e6) < 0.02e6
+        assert sum(o["residual"] for o in convs) == 1  # RFB shortcut add fused into a conv epilogue
+        assert sorted({o["pix_stride"] for o in convs if o["cout"] == 16 and o["dil"] > 1}) == [48]  # concat-free
+
+
+def test_bn_folding_matches_numpy(make_onnx):
+    path = make_onnx(320, 240, with_bn=True, seed=3)
+    d = nn.onnx_inspect(path, 320, 240)
+    g = load_onnx(path)
+    nodes = {n.outputs[0]: n for n in g.nodes}
+    consumers = {}
+    for n in g.nodes:
+        for i in n.inputs:
+            consumers.setdefault(i, []).append(n)
+    checked = 0
+    convs = [n for n in g.nodes if n.op == "Conv"]
+    assert len(convs) == len(d["ops"])
+    for n, o in zip(convs, d["ops"]):
+        w = g.initializers[n.inputs[1]].astype(np.float64)
+        b = g.initializers[n.inputs[2]].astype(np.float64) if len(n.inputs) > 2 else np.zeros(w.shape[0])
+        nxt = consumers.get(n.outputs[0], [])
+        if len(nxt) == 1 and nxt[0].op == "BatchNormalization":
+            gam, bet, mu, var = (g.initializers[k].astype(np.float64) for k in nxt[0].inputs[1:5])
+            s = gam / np.sqrt(var + nxt[0].attrs.get("epsilon", 1e-5))
+            w = w * s[:, None, None, None]
+            b = (b - mu) * s + bet
+            checked += 1
+        assert o["w_abs"] == pytest.approx(np.abs(w).sum(), rel=1e-4)
+        assert o["b_sum"] == pytest.approx(b.sum(), abs=1e-3)
+    assert checked >= 30
+    assert nodes  # silence linters
+
+
+def test_resize_taps_bit_identical_to_oracle():
+    for s, dlen in [(640, 320), (480, 240), (427, 240), (427, 480), (462, 240), (676, 480), (960, 240), (1280, 320),
+                    (720, 240), (1920, 320), (1080, 240), (100, 320), (320, 320), (641, 320), (7, 320)]:
+        l, n, w = nn.resize_taps(s, dlen)
+        ol, on, ow = hotpath.axis_taps(s, dlen)
+        np.testing.assert_array_equal(l, ol)
+        np.testing.assert_array_equal(n, on)
+        np.testing.assert_array_equal(w, ow)
+
+
+def test_errors_are_loud(tmp_path, make_onnx):
+    with pytest.raises(nn.UltrafaceError) as e:
+        nn.onnx_inspect(str(tmp_path / "missing.onnx"), 320, 240)
+    assert e.value.code == 2  # UF_ERR_IO (the reference would try to download: nn.rs:156-162)
+    bad = tmp_path / "bad.onnx"
+    bad.write_bytes(b"\x3a\xff\xff\xff\xff\x0f garbage")
+    with pytest.raises(nn.UltrafaceError) as e:
+        nn.onnx_inspect(str(bad), 320, 240)
+    assert e.value.code == 3  # UF_ERR_ONNX
+    with pytest.raises(nn.UltrafaceError) as e:  # declared 320x240 graph, asked for 640x480
+        nn.onnx_inspect(make_onnx(320, 240), 640, 480)
+    assert e.value.code == 4
+    with pytest.raises(nn.UltrafaceError):
+        nn._as_rgb(np.zeros((4, 4), np.uint8))
+
+
+def test_no_cpu_fallback(make_onnx):
+    """Without a CUDA device the product refuses to load: nothing routes through the oracle."""
+    if nn.device_count() > 0:
+        pytest.skip("CUDA device present")
+    with pytest.raises(nn.UltrafaceError) as e:
+        nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240))
+    assert e.value.code == 6
+    src = ""
+    pkg = os.path.join(ROOT, "infercam_onnx_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cc", ".h")):
+                src += open(os.path.join(dp, f)).read()
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), "product must not import the oracle"
+
+
+def test_variant_mirror():
+    assert nn.UltrafaceVariant.W640H480.width_height() == (640, 480)  # nn.rs:36-41
+    assert nn.UltrafaceVariant.W320H240.width_height() == (320, 240)
+    assert nn.default_model_path(nn.UltrafaceVariant.W320H240).endswith("infercam_onnx/ultraface-RFB-320.onnx")
