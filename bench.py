@@ -293,7 +293,8 @@ def main():
     model.profile_reset()
     for _ in range(args.steps):
         step_device()
-    stats = model.profile_read()
+    layers = model.profile_read()
+    stats = model.profile_by_family()
     model.profile_enable(False)
     peak, peak_src = measured_peaks()
     tot_ms = sum(s["device_ms"] for s in stats) or 1.0
@@ -317,7 +318,10 @@ def main():
                              "launches_per_step": s["launches"] // args.steps,
                              "alg_GBps": s["algorithmic_bytes"] / (s["device_ms"] / 1e3) / 1e9 if s["device_ms"] else None,
                              "TFLOPs": s["flops"] / (s["device_ms"] / 1e3) / 1e12 if s["device_ms"] else None}
-                            for s in sorted(stats, key=lambda s: -s["device_ms"])]}
+                            for s in sorted(stats, key=lambda s: -s["device_ms"])],
+                "top_layers": [{"name": s["name"], "ms_per_step": s["device_ms"] / args.steps,
+                                "alg_GBps": s["algorithmic_bytes"] / (s["device_ms"] / 1e3) / 1e9 if s["device_ms"] else None}
+                               for s in sorted(layers, key=lambda s: -s["device_ms"])[:8]]}
 
     # p50 batch-1 latency (BASELINE.json configs[1]): one pinned 640x480 frame -> detections on the host
     lat = []

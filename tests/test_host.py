@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_capi.uf_det) == 20
-    assert ctypes.sizeof(_capi.uf_kernel_stat) == 48 + 8 * 5
+    assert ctypes.sizeof(_capi.uf_kernel_stat) == 64 + 8 * 5
 
 
 @pytest.mark.parametrize("wh,variant,K,macs", [((320, 240), "RFB", 4420, 100.4e6), ((640, 480), "RFB", 17640, 399.2e6),

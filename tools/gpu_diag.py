@@ -115,9 +115,9 @@ def speed():
         m.profile_reset()
         for _ in range(5):
             m.run_batch_device(d.data_ptr(), 640, 480, 256, cap=128)
-        for s in sorted(m.profile_read(), key=lambda s: -s["device_ms"]):
+        for s in sorted(m.profile_by_family(), key=lambda s: -s["device_ms"]) + [dict(name="-- per layer --", device_ms=1e-9, launches=0, algorithmic_bytes=0, compulsory_bytes=0, flops=0)] + sorted(m.profile_read(), key=lambda s: -s["device_ms"])[:30]:
             ms = s["device_ms"] / 5
-            print(f"   {s['name']:26s} {ms:8.3f} ms/batch  launches {s['launches'] // 5:4d}  alg {s['algorithmic_bytes'] / 5 / ms / 1e6:8.1f} GB/s"
+            print(f"   {s['name']:48s} {ms:8.3f} ms/batch  launches {s['launches'] // 5:4d}  alg {s['algorithmic_bytes'] / 5 / ms / 1e6:8.1f} GB/s"
                   f"  min {s['compulsory_bytes'] / 5 / ms / 1e6:8.1f} GB/s  {s['flops'] / 5 / ms / 1e9:7.2f} TFLOP/s")
         m.profile_enable(False)
         m.close()
