@@ -49,7 +49,7 @@ struct ArgError : public std::exception {
 
 static thread_local std::string g_last_error;
 
-enum class Impl { Generic, Stem, Depthwise, Pointwise, FusedDwPw, SmallDense, Add, Relu, Copy };
+enum class Impl { Generic, Stem, Depthwise, Pointwise, FusedDwPw, FusedPix, SmallDense, Conv3x3Warp, Add, Relu, Copy };
 
 static const char* impl_name(Impl i) {
     switch (i) {
@@ -58,6 +58,8 @@ static const char* impl_name(Impl i) {
         case Impl::Depthwise: return "depthwise3x3";
         case Impl::Pointwise: return "pointwise1x1";
         case Impl::FusedDwPw: return "fused_dw3x3_pw1x1";
+        case Impl::FusedPix: return "fused_dw3x3_pw1x1_pix";
+        case Impl::Conv3x3Warp: return "conv3x3_warp";
         case Impl::SmallDense: return "small_dense3x3";
         case Impl::Add: return "eltwise_add";
         case Impl::Relu: return "eltwise_relu";
@@ -289,7 +291,7 @@ static void build_steps(uf_model& m) {
                     const bool nx_pw = nx.kind == OpKind::Conv && nx.k == 1 && nx.groups == 1 && nx.stride == 1 &&
                                        nx.pad == 0 && nx.in == op.out && nx.in2 < 0;
                     if (nx_pw && uses[op.out] == 1 && !out.in_concat && fused_dwpw_supported(op.cout, nx.cout)) {
-                        st.impl = Impl::FusedDwPw;
+                        st.impl = fused_dwpw_pix_supported(op.cout, nx.cout, op.stride) ? Impl::FusedPix : Impl::FusedDwPw;
                         st.op2 = (int)i + 1;
                         st.alg_bytes += bytes_of(nx.in) + bytes_of(nx.out);
                         st.min_bytes = bytes_of(op.in) + bytes_of(nx.out);
@@ -305,6 +307,9 @@ static void build_steps(uf_model& m) {
             } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.groups == 1 && op.in2 < 0 &&
                        small_dense_supported(op.cin, op.cout) && view_vec_ok(in) && view_vec_ok(out)) {
                 st.impl = Impl::SmallDense;
+            } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.groups == 1 && op.in2 < 0 &&
+                       conv3x3_warp_supported(op.cin, op.cout) && view_vec_ok(in)) {
+                st.impl = Impl::Conv3x3Warp;
             }
         }
         m.steps.push_back(st);
@@ -440,7 +445,15 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames) {
                                   m.d_weights + m.b_off[st.op2], pw.relu, frames, s.stream);
                 break;
             }
+            case Impl::FusedPix: {
+                const Op& pw = p.ops[st.op2];
+                TView o2 = make_view(m, s, pw.out);
+                launch_fused_dwpw_pix(in, o2, w, b, op.stride, op.relu, m.d_weights + m.w_off[st.op2],
+                                      m.d_weights + m.b_off[st.op2], pw.relu, frames, s.stream);
+                break;
+            }
             case Impl::SmallDense: launch_small_dense(in, out, w, b, op.dil, op.relu, frames, s.stream); break;
+            case Impl::Conv3x3Warp: launch_conv3x3_warp(in, out, w, b, op.dil, op.relu, frames, s.stream); break;
             case Impl::Add: launch_add(in, res, out, op.relu, frames, s.stream); break;
             case Impl::Relu: launch_relu(in, out, frames, s.stream); break;
             case Impl::Copy: launch_copy(in, out, frames, s.stream); break;
@@ -512,7 +525,7 @@ static void run_chunk_host(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t fi
     // total staging bytes for frames that need a resize
     size_t need = 0;
     for (uint32_t i = 0; i < n; ++i)
-        if ((int)fr[i].w != W || (int)fr[i].h != H) need += (size_t)fr[i].w * fr[i].h * 3;
+        if ((int)fr[i].w != W || (int)fr[i].h != H) need += (size_t)fr[i].w * fr[i].h * 3 + 16;
     if (need > s.d_in_cap) {
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaFree(s.d_in));
@@ -528,6 +541,7 @@ static void run_chunk_host(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t fi
         const size_t fb = (size_t)fr[i].w * fr[i].h * 3;
         while (j < n && fr[j].w == fr[i].w && fr[j].h == fr[i].h) ++j;
         const bool ident = (int)fr[i].w == W && (int)fr[i].h == H;
+        if (!ident) off = (off + 15) / 16 * 16;  // keep every run 16-byte aligned for the fast resize path
         uint8_t* dst = ident ? s.d_resized + (size_t)i * out_frame : s.d_in + off;
         uint32_t a = i;
         while (a < j) {  // merge host-contiguous frames into one cudaMemcpyAsync

@@ -57,6 +57,15 @@ bool fused_dwpw_supported(int C, int N);
 void launch_fused_dwpw(const TView& in, const TView& out, const float* dw_w_tc, const float* dw_b,
                        int stride, int dw_relu, const float* pw_w_io, const float* pw_b, int pw_relu, int frames,
                        cudaStream_t s);
+// pixel-per-thread form of the fused kernel for C in {16,32,64} (large, memory-bound maps)
+bool fused_dwpw_pix_supported(int C, int N, int stride);
+void launch_fused_dwpw_pix(const TView& in, const TView& out, const float* dw_w_tc, const float* dw_b,
+                           int stride, int dw_relu, const float* pw_w_io, const float* pw_b, int pw_relu,
+                           int frames, cudaStream_t s);
+// K6b warp-per-pixel 3x3 (stride 1, pad = dil) for many input channels and <= 16 outputs (last SSD heads)
+bool conv3x3_warp_supported(int cin, int cout);
+void launch_conv3x3_warp(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil,
+                         int relu, int frames, cudaStream_t s);
 // K6 small dense 3x3 (stride 1, pad = dil), Cin,Cout in {8,12,16}, weights [3][3][Cin][Cout]
 bool small_dense_supported(int cin, int cout);
 void launch_small_dense(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil,

@@ -95,12 +95,15 @@ stem_kernel(U8View in, const float* __restrict__ lut, TView out, const float* __
     const int ox0 = blockIdx.x * STEM_T, oy0 = blockIdx.y * STEM_T, n = blockIdx.z;
     const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
     const uint8_t* ip = in.p + (size_t)n * in.frame_stride;
-    for (int i = tid; i < STEM_IN * STEM_IN * 3; i += blockDim.x) {
-        const int c = i % 3, px = (i / 3) % STEM_IN, py = i / (3 * STEM_IN);
+    for (int i = tid; i < STEM_IN * STEM_IN; i += blockDim.x) {
+        const int py = i / STEM_IN, px = i - py * STEM_IN;  // division by a constant
         const int ix = ix0 + px, iy = iy0 + py;
-        float v = 0.0f;  // zero padding is applied in normalised space, as in the ONNX Conv
-        if (ix >= 0 && ix < in.W && iy >= 0 && iy < in.H) v = s_lut[c * 256 + ip[((size_t)iy * in.W + ix) * 3 + c]];
-        s_in[i] = v;
+        float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;  // zero padding is applied in normalised space, as in the ONNX Conv
+        if (ix >= 0 && ix < in.W && iy >= 0 && iy < in.H) {
+            const uint8_t* q = ip + ((size_t)iy * in.W + ix) * 3;
+            v0 = s_lut[q[0]]; v1 = s_lut[256 + q[1]]; v2 = s_lut[512 + q[2]];
+        }
+        s_in[i * 3 + 0] = v0; s_in[i * 3 + 1] = v1; s_in[i * 3 + 2] = v2;
     }
     __syncthreads();
     const int tx = tid % STEM_T, ty = tid / STEM_T;
@@ -194,7 +197,7 @@ void launch_depthwise(const TView& in, const TView& out, const float* w_tc, cons
 template <int BM, int BN>
 __global__ void __launch_bounds__(256)
 pointwise_kernel(TView in, TView out, TView res, int has_res, const float* __restrict__ w,
-                 const float* __restrict__ b, int relu, long long M, int K, int N) {
+                 const float* __restrict__ b, int relu, int M, int K, int N) {
     constexpr int BK = 32, TN = 4;
     constexpr int TXN = BN / TN;        // threads along n
     constexpr int RT = 256 / TXN;       // threads along m
@@ -203,7 +206,7 @@ pointwise_kernel(TView in, TView out, TView res, int has_res, const float* __res
     __shared__ __align__(16) float As[BM * LDA];
     __shared__ __align__(16) float Bs[BK * BN];
     const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
-    const long long m0 = (long long)blockIdx.x * BM;
+    const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int HW = in.H * in.W;
     float acc[TM][TN];
@@ -216,12 +219,12 @@ pointwise_kernel(TView in, TView out, TView res, int has_res, const float* __res
         // A tile: BM rows x BK floats, float4 along k (Cin % 4 == 0 guaranteed by the dispatcher)
         for (int i = tid; i < BM * (BK / 4); i += 256) {
             const int r = i / (BK / 4), kq = (i % (BK / 4)) * 4;
-            const long long m = m0 + r;
+            const int m = m0 + r;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m < M && k0 + kq < K) {
-                const long long f = m / HW;
-                const int pix = (int)(m - f * HW);
-                v = ld4(in.p + f * in.frame_stride + (size_t)pix * in.pix_stride + k0 + kq);
+                const int f = m / HW;
+                const int pix = m - f * HW;
+                v = ld4(in.p + (size_t)f * in.frame_stride + (size_t)pix * in.pix_stride + k0 + kq);
             }
             st4(As + r * LDA + kq, v);
         }
@@ -260,15 +263,15 @@ pointwise_kernel(TView in, TView out, TView res, int has_res, const float* __res
                      ((reinterpret_cast<size_t>(out.p) & 15) == 0) && ((out.frame_stride & 3) == 0);
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        const long long m = m0 + ty + i * RT;
+        const int m = m0 + ty + i * RT;
         if (m >= M) continue;
-        const long long f = m / HW;
-        const int pix = (int)(m - f * HW);
+        const int f = m / HW;
+        const int pix = m - f * HW;
         float v[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) v[j] = acc[i][j] + bias[j];
         if (has_res) {
-            const float* rp = res.p + f * res.frame_stride + (size_t)pix * res.pix_stride + nb;
+            const float* rp = res.p + (size_t)f * res.frame_stride + (size_t)pix * res.pix_stride + nb;
 #pragma unroll
             for (int j = 0; j < TN; ++j) if (nb + j < N) v[j] += rp[j];
         }
@@ -276,7 +279,7 @@ pointwise_kernel(TView in, TView out, TView res, int has_res, const float* __res
 #pragma unroll
             for (int j = 0; j < TN; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        float* op = out.p + f * out.frame_stride + (size_t)pix * out.pix_stride + nb;
+        float* op = out.p + (size_t)f * out.frame_stride + (size_t)pix * out.pix_stride + nb;
         if (vec) {
             st4(op, make_float4(v[0], v[1], v[2], v[3]));
         } else {
@@ -288,7 +291,7 @@ pointwise_kernel(TView in, TView out, TView res, int has_res, const float* __res
 
 void launch_pointwise(const TView& in, const TView& out, const TView* res, const float* w_io, const float* b,
                       int relu, int frames, cudaStream_t s) {
-    const long long M = (long long)frames * in.H * in.W;
+    const int M = frames * in.H * in.W;
     const int K = in.C, N = out.C;
     TView r = res ? *res : TView{};
     if (N > 32) {
@@ -316,7 +319,7 @@ void launch_pointwise(const TView& in, const TView& out, const TView* res, const
 template <int BM, int BN, int BK>
 __global__ void __launch_bounds__(256)
 fused_dwpw_kernel(TView in, TView out, const float* __restrict__ dw_w, const float* __restrict__ dw_b, int stride,
-                  int dw_relu, const float* __restrict__ pw_w, const float* __restrict__ pw_b, int pw_relu, long long M,
+                  int dw_relu, const float* __restrict__ pw_w, const float* __restrict__ pw_b, int pw_relu, int M,
                   int n_per_cta) {
     constexpr int TN = 4, TXN = BN / TN, RT = 256 / TXN, TM = BM / RT;
     extern __shared__ __align__(16) float smem[];
@@ -325,20 +328,23 @@ fused_dwpw_kernel(TView in, TView out, const float* __restrict__ dw_w, const flo
     float* Bs = As + BM * LDA;              // [BK][BN]
     int* s_xy = reinterpret_cast<int*>(Bs + BK * BN);  // [BM] packed (y << 16 | x), -1 = out of range
     long long* s_base = reinterpret_cast<long long*>(s_xy + BM);  // [BM] frame offset into `in`
+    long long* s_obase = s_base + BM;                             // [BM] pixel offset into `out`
     const int tid = threadIdx.x;
-    const long long m0 = (long long)blockIdx.x * BM;
+    const int m0 = blockIdx.x * BM;
     const int HWo = out.H * out.W;
     for (int r = tid; r < BM; r += 256) {
-        const long long m = m0 + r;
+        const int m = m0 + r;
         if (m < M) {
-            const long long f = m / HWo;
-            const int pix = (int)(m - f * HWo);
+            const int f = m / HWo;
+            const int pix = m - f * HWo;
             const int y = pix / out.W;
             s_xy[r] = (y << 16) | (pix - y * out.W);
-            s_base[r] = f * in.frame_stride;
+            s_base[r] = (long long)f * in.frame_stride;
+            s_obase[r] = (long long)f * out.frame_stride + (long long)pix * out.pix_stride;
         } else {
             s_xy[r] = -1;
             s_base[r] = 0;
+            s_obase[r] = 0;
         }
     }
     __syncthreads();
@@ -415,17 +421,15 @@ fused_dwpw_kernel(TView in, TView out, const float* __restrict__ dw_w, const flo
                              ((reinterpret_cast<size_t>(out.p) & 15) == 0) && ((out.frame_stride & 3) == 0);
 #pragma unroll
             for (int i = 0; i < TM; ++i) {
-                const long long m = m0 + ty + i * RT;
-                if (m >= M) continue;
-                const long long f = m / HWo;
-                const int pix = (int)(m - f * HWo);
+                const int rr = ty + i * RT;
+                if (m0 + rr >= M) continue;
                 float v[TN];
 #pragma unroll
                 for (int j = 0; j < TN; ++j) {
                     v[j] = acc[i][j] + bias[j];
                     if (pw_relu) v[j] = fmaxf(v[j], 0.f);
                 }
-                float* op = out.p + f * out.frame_stride + (size_t)pix * out.pix_stride + nb;
+                float* op = out.p + s_obase[rr] + nb;
                 if (vec) {
                     st4(op, make_float4(v[0], v[1], v[2], v[3]));
                 } else {
@@ -442,9 +446,9 @@ bool fused_dwpw_supported(int C, int N) { return C % 4 == 0 && C >= 16 && C <= 2
 template <int BM, int BN, int BK>
 static void launch_fused_t(const TView& in, const TView& out, const float* dw_w, const float* dw_b, int stride,
                            int dw_relu, const float* pw_w, const float* pw_b, int pw_relu, int frames, cudaStream_t s) {
-    const long long M = (long long)frames * out.H * out.W;
+    const int M = frames * out.H * out.W;
     const int N = out.C, C = in.C;
-    const int m_tiles = (int)((M + BM - 1) / BM);
+    const int m_tiles = (M + BM - 1) / BM;
     const int n_tiles = (N + BN - 1) / BN;
     // split N across CTAs only while the grid is smaller than ~2 waves
     int split = 1;
@@ -452,7 +456,7 @@ static void launch_fused_t(const TView& in, const TView& out, const float* dw_w,
     const int tiles_per = (n_tiles + split - 1) / split;
     const int n_per_cta = tiles_per * BN;
     const int gy = (N + n_per_cta - 1) / n_per_cta;
-    const size_t smem = (size_t)(BM * (C + 4) + BK * BN) * sizeof(float) + BM * (sizeof(int) + sizeof(long long));
+    const size_t smem = (size_t)(BM * (C + 4) + BK * BN) * sizeof(float) + BM * (sizeof(int) + 2 * sizeof(long long));
     auto kern = fused_dwpw_kernel<BM, BN, BK>;
     static bool configured[64] = {};  // per template instantiation and device
     int dev = 0;
@@ -476,6 +480,222 @@ void launch_fused_dwpw(const TView& in, const TView& out, const float* dw_w_tc, 
         if (N > 32) UF_F(128, 64, 32); else if (N > 16) UF_F(128, 32, 32); else UF_F(128, 16, 32);
     }
 #undef UF_F
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6b: 3x3 conv with many input channels and few outputs (the last SSD heads: 256 -> 6 / 12 on the
+// 4x5 (8x10) map). One warp per output pixel: lanes split Cin in float4 chunks (coalesced 512 B
+// reads of the NHWC pixel and of the [tap][ci][co] weights), N accumulators per lane, warp-shuffle
+// reduction at the end. K = 9*Cin = 2304 is far too deep for one thread per output.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256)
+conv3x3_warp_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int dil, int relu,
+                    int total_pix) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= total_pix) return;
+    const int hw = out.H * out.W;
+    const int f = wid / hw, pix = wid - f * hw;
+    const int y = pix / out.W, x = pix - y * out.W;
+    const int C = in.C;
+    float acc[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[j] = 0.f;
+    const float* ip = in.p + (size_t)f * in.frame_stride;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y + (ky - 1) * dil;
+        if (iy < 0 || iy >= in.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = x + (kx - 1) * dil;
+            if (ix < 0 || ix >= in.W) continue;
+            const float* px = ip + ((size_t)iy * in.W + ix) * in.pix_stride;
+            const float* wt = w + (size_t)(ky * 3 + kx) * C * N;
+            for (int c = lane * 4; c < C; c += 128) {
+                const float4 v = ld4(px + c);
+                const float4* wp = reinterpret_cast<const float4*>(wt + (size_t)c * N);  // 4*N contiguous floats
+                float wv[4 * N];
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    const float4 t4 = __ldg(wp + q);
+                    wv[q * 4] = t4.x; wv[q * 4 + 1] = t4.y; wv[q * 4 + 2] = t4.z; wv[q * 4 + 3] = t4.w;
+                }
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    acc[j] = fmaf(v.x, wv[j], acc[j]);
+                    acc[j] = fmaf(v.y, wv[N + j], acc[j]);
+                    acc[j] = fmaf(v.z, wv[2 * N + j], acc[j]);
+                    acc[j] = fmaf(v.w, wv[3 * N + j], acc[j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    float* op = out.p + (size_t)f * out.frame_stride + (size_t)pix * out.pix_stride;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (lane == j) {
+            float v = acc[j] + b[j];
+            if (relu) v = fmaxf(v, 0.f);
+            op[j] = v;
+        }
+    }
+}
+
+bool conv3x3_warp_supported(int cin, int cout) {
+    return cin % 4 == 0 && cin >= 64 && (cout == 4 || cout == 6 || cout == 8 || cout == 12 || cout == 16);
+}
+
+void launch_conv3x3_warp(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil, int relu,
+                         int frames, cudaStream_t s) {
+    const int total = frames * out.H * out.W;
+    const int grid = (total * 32 + 255) / 256;
+#define UF_W(NN) conv3x3_warp_kernel<NN><<<grid, 256, 0, s>>>(in, out, w_kkio, b, dil, relu, total)
+    switch (out.C) {
+        case 4: UF_W(4); break;
+        case 6: UF_W(6); break;
+        case 8: UF_W(8); break;
+        case 12: UF_W(12); break;
+        case 16: UF_W(16); break;
+    }
+#undef UF_W
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4+K5 fused, pixel-per-thread form for C <= 64: CTA = 8 x TY output pixels of one frame. The
+// input tile (+1 halo, stride-scaled) is staged in shared memory with coalesced float4 loads and a
+// padded pixel pitch of C+4 floats (conflict-free LDS.128 for 8 neighbouring pixels); each thread
+// keeps the C depthwise results of its pixel in registers and runs the 1x1 conv against weights
+// broadcast from shared memory (one LDS.128 per 4 FFMA, no barriers after the fill), NT outputs
+// at a time. Used for the large, memory-bound maps (16/32/64 channels).
+// ---------------------------------------------------------------------------------------------
+template <int C, int S, int TY, int NT>
+__global__ void __launch_bounds__(8 * TY)
+fused_dwpw_pix_kernel(TView in, TView out, const float* __restrict__ dw_w, const float* __restrict__ dw_b, int dw_relu,
+                      const float* __restrict__ pw_w, const float* __restrict__ pw_b, int pw_relu, int tiles_x,
+                      int tiles_y, int n_pad) {
+    constexpr int TX = 8, IW = (TX - 1) * S + 3, IH = (TY - 1) * S + 3, P = C + 4, NTHR = TX * TY, C4 = C / 4;
+    extern __shared__ __align__(16) float smem[];
+    float* s_in = smem;                      // IH*IW*P
+    float* s_dw = s_in + IH * IW * P;        // 9*C + C (bias)
+    float* s_pw = s_dw + 10 * C;             // C * n_pad
+    float* s_pb = s_pw + C * n_pad;          // n_pad
+    const int tid = threadIdx.x;
+    const int N = out.C;
+    int bid = blockIdx.x;
+    const int txi = bid % tiles_x; bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int f = bid / tiles_y;
+    const int x0 = txi * TX, y0 = tyi * TY;
+    const int gx0 = x0 * S - 1, gy0 = y0 * S - 1;
+    const float* ip = in.p + (size_t)f * in.frame_stride;
+    for (int i = tid; i < IH * IW * C4; i += NTHR) {
+        const int pix = i / C4, q = i - pix * C4;   // constants: shifts
+        const int py = pix / IW, px = pix - py * IW;
+        const int gy = gy0 + py, gx = gx0 + px;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < in.H && gx >= 0 && gx < in.W) v = ld4(ip + ((size_t)gy * in.W + gx) * in.pix_stride + q * 4);
+        st4(s_in + pix * P + q * 4, v);
+    }
+    for (int i = tid; i < 9 * C; i += NTHR) s_dw[i] = dw_w[i];
+    for (int i = tid; i < C; i += NTHR) s_dw[9 * C + i] = dw_b[i];
+    for (int i = tid; i < C * n_pad; i += NTHR) {
+        const int ci = i / n_pad, n = i - ci * n_pad;
+        s_pw[i] = n < N ? pw_w[(size_t)ci * N + n] : 0.f;
+    }
+    for (int i = tid; i < n_pad; i += NTHR) s_pb[i] = i < N ? pw_b[i] : 0.f;
+    __syncthreads();
+    const int tx = tid % TX, ty = tid / TX;
+    const int ox = x0 + tx, oy = y0 + ty;
+    if (ox >= out.W || oy >= out.H) return;
+    float d[C];
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+        float4 a = ld4(s_dw + 9 * C + c);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 v = ld4(s_in + ((ty * S + ky) * IW + tx * S + kx) * P + c);
+                const float4 ww = ld4(s_dw + (ky * 3 + kx) * C + c);
+                a.x = fmaf(v.x, ww.x, a.x); a.y = fmaf(v.y, ww.y, a.y); a.z = fmaf(v.z, ww.z, a.z); a.w = fmaf(v.w, ww.w, a.w);
+            }
+        if (dw_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        d[c] = a.x; d[c + 1] = a.y; d[c + 2] = a.z; d[c + 3] = a.w;
+    }
+    float* op = out.p + (size_t)f * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
+    const bool vec = ((N & 3) == 0) && ((out.pix_stride & 3) == 0) && ((reinterpret_cast<size_t>(out.p) & 15) == 0) &&
+                     ((out.frame_stride & 3) == 0);
+    for (int n0 = 0; n0 < n_pad; n0 += NT) {
+        float o[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) o[j] = s_pb[n0 + j];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            const float a = d[ci];
+            const float4* wp = reinterpret_cast<const float4*>(s_pw + ci * n_pad + n0);
+#pragma unroll
+            for (int q = 0; q < NT / 4; ++q) {
+                const float4 ww = wp[q];
+                o[q * 4 + 0] = fmaf(a, ww.x, o[q * 4 + 0]); o[q * 4 + 1] = fmaf(a, ww.y, o[q * 4 + 1]);
+                o[q * 4 + 2] = fmaf(a, ww.z, o[q * 4 + 2]); o[q * 4 + 3] = fmaf(a, ww.w, o[q * 4 + 3]);
+            }
+        }
+        if (pw_relu) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        if (vec && n0 + NT <= N) {
+#pragma unroll
+            for (int q = 0; q < NT / 4; ++q) st4(op + n0 + q * 4, make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) if (n0 + j < N) op[n0 + j] = o[j];
+        }
+    }
+}
+
+bool fused_dwpw_pix_supported(int C, int N, int stride) {
+    if (N > 64) return false;
+    if (C == 16 || C == 32) return stride == 1 || stride == 2;
+    if (C == 64) return stride == 1;
+    return false;
+}
+
+template <int C, int S, int TY, int NT>
+static void launch_pix_t(const TView& in, const TView& out, const float* dw_w, const float* dw_b, int dw_relu,
+                         const float* pw_w, const float* pw_b, int pw_relu, int frames, cudaStream_t s) {
+    constexpr int TX = 8, IW = (TX - 1) * S + 3, IH = (TY - 1) * S + 3;
+    const int n_pad = (out.C + NT - 1) / NT * NT;
+    const int tiles_x = (out.W + TX - 1) / TX, tiles_y = (out.H + TY - 1) / TY;
+    const size_t smem = (size_t)(IH * IW * (C + 4) + 10 * C + C * n_pad + n_pad) * sizeof(float);
+    auto kern = fused_dwpw_pix_kernel<C, S, TY, NT>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured[dev & 63] = true;
+    }
+    kern<<<tiles_x * tiles_y * frames, TX * TY, smem, s>>>(in, out, dw_w, dw_b, dw_relu, pw_w, pw_b, pw_relu, tiles_x,
+                                                          tiles_y, n_pad);
+}
+
+void launch_fused_dwpw_pix(const TView& in, const TView& out, const float* dw_w_tc, const float* dw_b, int stride,
+                           int dw_relu, const float* pw_w_io, const float* pw_b, int pw_relu, int frames,
+                           cudaStream_t s) {
+    const int C = in.C, N = out.C;
+#define UF_P(CC, SS, TYY, NTT) launch_pix_t<CC, SS, TYY, NTT>(in, out, dw_w_tc, dw_b, dw_relu, pw_w_io, pw_b, pw_relu, frames, s)
+    if (C == 16) { if (stride == 1) UF_P(16, 1, 32, 32); else UF_P(16, 2, 16, 32); }
+    else if (C == 32) { if (stride == 1) UF_P(32, 1, 32, 32); else UF_P(32, 2, 16, 32); }
+    else if (C == 64) { if (N > 16) UF_P(64, 1, 32, 32); else if (N > 8) UF_P(64, 1, 32, 16); else UF_P(64, 1, 32, 8); }
+#undef UF_P
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -64,9 +64,105 @@ resize_triangle_kernel(const uint8_t* __restrict__ src, long long src_frame_stri
     }
 }
 
+// Fast path of K1 for 4-byte-aligned rows (source width % 4 == 0, the usual 640/1280/1920 frames):
+// same arithmetic, same order, but 4 source bytes per load in the vertical pass, no integer
+// divisions (block = 32 x tile_h threads: y indexes the tile row, x strides the columns) and the
+// u8 tile is staged in shared memory so the global stores are 4-byte words of contiguous rows.
+constexpr int RF_TW = 64, RF_TH = 8;
+
+__global__ void __launch_bounds__(32 * RF_TH)
+resize_triangle_fast_kernel(const uint8_t* __restrict__ src, long long src_frame_stride, int sw, int sh,
+                            uint8_t* __restrict__ dst, long long dst_frame_stride, int dw, int dh,
+                            ResizeTapsDev t, int pitch /* floats per tmp row, multiple of 4 */, int round_intermediate) {
+    extern __shared__ __align__(16) float tmp_s[];                       // RF_TH x pitch
+    uint8_t* out_s = reinterpret_cast<uint8_t*>(tmp_s + RF_TH * pitch);  // RF_TH x RF_TW*3
+    const int tx = threadIdx.x, r = threadIdx.y;
+    const int ox0 = blockIdx.x * RF_TW, oy0 = blockIdx.y * RF_TH;
+    const int ox1 = min(ox0 + RF_TW, dw);
+    const int tw = ox1 - ox0;
+    const int oy = oy0 + r;
+    const bool row_ok = oy < dh;
+    const int col0 = t.hleft[ox0] & ~3;  // aligned down to 4 pixels = 12 bytes
+    const int col1 = t.hleft[ox1 - 1] + t.hn[ox1 - 1];
+    const int nwords = ((col1 - col0) * 3 + 3) >> 2;
+    const size_t row_bytes = (size_t)sw * 3;
+    if (row_ok) {
+        const int l = t.vleft[oy], n = t.vn[oy];
+        const float* w = t.vw + (size_t)oy * t.vmax;
+        const uint8_t* sp = src + (size_t)blockIdx.z * src_frame_stride + (size_t)l * row_bytes + (size_t)col0 * 3;
+        for (int wd = tx; wd < nwords; wd += 32) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int i = 0; i < n; ++i) {
+                const unsigned u = __ldg(reinterpret_cast<const unsigned*>(sp + (size_t)i * row_bytes) + wd);
+                const float wi = w[i];
+                a0 = __fadd_rn(a0, __fmul_rn((float)(u & 0xffu), wi));
+                a1 = __fadd_rn(a1, __fmul_rn((float)((u >> 8) & 0xffu), wi));
+                a2 = __fadd_rn(a2, __fmul_rn((float)((u >> 16) & 0xffu), wi));
+                a3 = __fadd_rn(a3, __fmul_rn((float)(u >> 24), wi));
+            }
+            if (round_intermediate) {
+                a0 = roundf(fminf(fmaxf(a0, 0.f), 255.f)); a1 = roundf(fminf(fmaxf(a1, 0.f), 255.f));
+                a2 = roundf(fminf(fmaxf(a2, 0.f), 255.f)); a3 = roundf(fminf(fmaxf(a3, 0.f), 255.f));
+            }
+            *reinterpret_cast<float4*>(tmp_s + r * pitch + wd * 4) = make_float4(a0, a1, a2, a3);
+        }
+    }
+    __syncthreads();
+    if (row_ok) {
+        for (int oxl = tx; oxl < tw; oxl += 32) {
+            const int ox = ox0 + oxl;
+            const int l = t.hleft[ox] - col0, n = t.hn[ox];
+            const float* w = t.hw + (size_t)ox * t.hmax;
+            const float* tp = tmp_s + r * pitch + l * 3;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int i = 0; i < n; ++i) {
+                const float wi = w[i];
+                a0 = __fadd_rn(a0, __fmul_rn(tp[i * 3 + 0], wi));
+                a1 = __fadd_rn(a1, __fmul_rn(tp[i * 3 + 1], wi));
+                a2 = __fadd_rn(a2, __fmul_rn(tp[i * 3 + 2], wi));
+            }
+            a0 = a0 < 0.f ? 0.f : (a0 > 255.f ? 255.f : a0);
+            a1 = a1 < 0.f ? 0.f : (a1 > 255.f ? 255.f : a1);
+            a2 = a2 < 0.f ? 0.f : (a2 > 255.f ? 255.f : a2);
+            uint8_t* op = out_s + r * (RF_TW * 3) + oxl * 3;
+            op[0] = (uint8_t)roundf(a0); op[1] = (uint8_t)roundf(a1); op[2] = (uint8_t)roundf(a2);
+        }
+    }
+    __syncthreads();
+    if (row_ok) {
+        uint8_t* d = dst + (size_t)blockIdx.z * dst_frame_stride + ((size_t)oy * dw + ox0) * 3;
+        if (tw == RF_TW && ((reinterpret_cast<size_t>(d) & 3) == 0)) {
+            const unsigned* o4 = reinterpret_cast<const unsigned*>(out_s + r * (RF_TW * 3));
+            for (int i = tx; i < RF_TW * 3 / 4; i += 32) reinterpret_cast<unsigned*>(d)[i] = o4[i];
+        } else {
+            for (int i = tx; i < tw * 3; i += 32) d[i] = out_s[r * (RF_TW * 3) + i];
+        }
+    }
+}
+
 void launch_resize(const uint8_t* src, long long src_frame_stride, int sw, int sh, uint8_t* dst,
                    long long dst_frame_stride, int dw, int dh, int frames, const ResizeTapsDev& t,
                    int round_intermediate, cudaStream_t s) {
+    // fast path: rows and frames 4-byte aligned, CTA tile 64 x 8 as built by the engine
+    const bool aligned = (sw % 4 == 0) && ((reinterpret_cast<size_t>(src) & 3) == 0) && (src_frame_stride % 4 == 0);
+    if (aligned && t.tile_w == RF_TW && t.tile_h == RF_TH) {
+        const int pitch = ((t.max_cols + 4) * 3 + 3) / 4 * 4;  // +4: col0 is aligned down by up to 3 pixels
+        const size_t smem = (size_t)RF_TH * pitch * sizeof(float) + (size_t)RF_TH * RF_TW * 3;
+        if (smem <= 200 * 1024) {
+            static bool configured[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!configured[dev & 63]) {
+                cudaFuncSetAttribute(resize_triangle_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                configured[dev & 63] = true;
+            }
+            dim3 grid((dw + RF_TW - 1) / RF_TW, (dh + RF_TH - 1) / RF_TH, frames);
+            resize_triangle_fast_kernel<<<grid, dim3(32, RF_TH), smem, s>>>(src, src_frame_stride, sw, sh, dst,
+                                                                            dst_frame_stride, dw, dh, t, pitch,
+                                                                            round_intermediate);
+            return;
+        }
+    }
     dim3 grid((dw + t.tile_w - 1) / t.tile_w, (dh + t.tile_h - 1) / t.tile_h, frames);
     size_t smem = (size_t)t.tile_h * t.max_cols * 3 * sizeof(float);
     if (smem > 48 * 1024)
