@@ -17,6 +17,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/ultraface_b200.h"
@@ -49,7 +50,7 @@ struct ArgError : public std::exception {
 
 static thread_local std::string g_last_error;
 
-enum class Impl { Generic, Stem, Depthwise, Pointwise, FusedDwPw, FusedPix, SmallDense, Conv3x3Warp, Add, Relu, Copy };
+enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwPw, FusedPix, FusedTma, SmallDense, Conv3x3Warp, Add, Relu, Copy };
 
 static const char* impl_name(Impl i) {
     switch (i) {
@@ -57,8 +58,10 @@ static const char* impl_name(Impl i) {
         case Impl::Stem: return "stem_3x3s2_u8";
         case Impl::Depthwise: return "depthwise3x3";
         case Impl::Pointwise: return "pointwise1x1";
+        case Impl::PointwiseTC: return "pointwise1x1_tcgen05";
         case Impl::FusedDwPw: return "fused_dw3x3_pw1x1";
         case Impl::FusedPix: return "fused_dw3x3_pw1x1_pix";
+        case Impl::FusedTma: return "fused_dw3x3_pw1x1_tma";
         case Impl::Conv3x3Warp: return "conv3x3_warp";
         case Impl::SmallDense: return "small_dense3x3";
         case Impl::Add: return "eltwise_add";
@@ -75,6 +78,13 @@ struct Step {
     uint64_t min_bytes = 0;  // compulsory traffic of this launch (fusion removes the intermediate), per frame
     uint64_t flops = 0;      // per frame
     std::string label;       // "<kernel family>[<shape>]" for the per-launch profile
+    int tc = -1;             // index into uf_model::tc_weights for PointwiseTC steps
+    std::vector<float> host_w;  // FusedTma: weights in kernel-parameter layout (host copy)
+};
+
+struct TcWeights {           // 3xTF32 split of one 1x1 conv's weights, [N][K] K-major, plus their tensor maps
+    float *d_hi = nullptr, *d_lo = nullptr;
+    TmaMap tm_hi, tm_lo;
 };
 
 struct TapsEntry {
@@ -104,6 +114,11 @@ struct Slot {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;  // profiling pairs
     std::vector<int> ev_stat;                             // stat index per pair
     size_t ev_used = 0;
+    std::vector<TmaMap> tm_a;                             // per step: activation tensor map (PointwiseTC / FusedTma input)
+    std::vector<TmaMap> tm_o;                             // per step: output tensor map (FusedTma)
+    // CUDA graphs of the kernel chain (conv stack + tail + post + D2H), keyed by (first frame, frames, stem inside?)
+    std::map<std::tuple<uint32_t, int, int>, cudaGraphExec_t> graphs;
+    std::map<std::tuple<uint32_t, int, int>, int> graph_seen, graph_nodes;
 };
 
 struct KernelStat {
@@ -123,7 +138,7 @@ struct uf_model {
     std::string onnx_path;
     Plan plan;
     int K = 0;
-    uint32_t chunk = 0, nslots = 0;
+    uint32_t chunk = 0, host_chunk = 0, nslots = 0;
     std::vector<Step> steps;
     std::vector<size_t> w_off, b_off;  // per plan op, floats into d_weights
     float* d_weights = nullptr;
@@ -133,7 +148,7 @@ struct uf_model {
     float *d_scores = nullptr, *d_boxes = nullptr;  // raw outputs of the last batch [max_batch][K][2|4]
     std::vector<Slot> slots;
     std::map<std::pair<int, int>, TapsEntry> taps;
-    uint32_t last_n = 0;
+    uint32_t last_n = 0, last_step = 1;
     uint64_t launches = 0;
     bool profiling = false;
     std::vector<KernelStat> stats;
@@ -142,6 +157,7 @@ struct uf_model {
     void* d_hook = nullptr;
     size_t d_hook_cap = 0;
     std::vector<uint8_t> tensor_readable;  // per plan tensor: materialised in the arena
+    std::vector<TcWeights> tc_weights;
 
     ~uf_model();
 };
@@ -279,6 +295,14 @@ static void build_steps(uf_model& m) {
         const bool dw = op.k == 3 && op.groups == op.cin && op.cin == op.cout && op.pad == 1 && op.dil == 1 &&
                         (op.stride == 1 || op.stride == 2) && op.in2 < 0 && !in.is_input && view_vec_ok(in) && view_vec_ok(out);
         const bool pw = op.k == 1 && op.groups == 1 && op.stride == 1 && op.pad == 0 && !in.is_input && view_vec_ok(in);
+        const bool no_tc = m.cfg.flags & UF_FLAG_NO_TC;
+        // the TMA view of the activations is 2-D [frames*H*W][K]: frames must be densely packed
+        auto tc_ok = [&](const Op& o) {
+            const TensorDesc& ti = p.tensors[o.in];
+            return !no_tc && o.k == 1 && o.groups == 1 && o.stride == 1 && o.pad == 0 && !ti.is_input && view_vec_ok(ti) &&
+                   pointwise_tc_supported(o.cin, o.cout) &&
+                   align4(p.buffers[ti.buf].frame_floats) == (int64_t)ti.H * ti.W * ti.pix_stride;
+        };
         if (!force_generic) {
             if (in.is_input) {
                 if (op.k == 3 && op.stride == 2 && op.pad == 1 && op.dil == 1 && op.groups == 1 && op.cin == 3 &&
@@ -290,8 +314,16 @@ static void build_steps(uf_model& m) {
                     const Op& nx = p.ops[i + 1];
                     const bool nx_pw = nx.kind == OpKind::Conv && nx.k == 1 && nx.groups == 1 && nx.stride == 1 &&
                                        nx.pad == 0 && nx.in == op.out && nx.in2 < 0;
-                    if (nx_pw && uses[op.out] == 1 && !out.in_concat && fused_dwpw_supported(op.cout, nx.cout)) {
-                        st.impl = fused_dwpw_pix_supported(op.cout, nx.cout, op.stride) ? Impl::FusedPix : Impl::FusedDwPw;
+                    const bool pix = fused_dwpw_pix_supported(op.cout, nx.cout, op.stride);
+                    const TensorDesc& o2 = p.tensors[nx.out];
+                    const bool fusable = nx_pw && uses[op.out] == 1 && !out.in_concat && fused_dwpw_supported(op.cout, nx.cout);
+                    // 16/32-channel pairs on the big maps: TMA-pipelined fused kernel (memory-bound)
+                    const bool tma = fusable && !no_tc && fused_dwpw_tma_supported(op.cout, nx.cout, op.stride) &&
+                                     o2.pix_stride == o2.C && o2.base_off % 4 == 0 && !o2.in_concat;
+                    // wide pairs: depthwise kernel + tensor-core GEMM beats the SIMT fusion (those maps are L2-resident)
+                    const bool split_tc = nx_pw && !tma && tc_ok(nx) && (op.cout >= 128 || (op.cout == 64 && nx.cout >= 32));
+                    if (fusable && !split_tc) {
+                        st.impl = tma ? Impl::FusedTma : pix ? Impl::FusedPix : Impl::FusedDwPw;
                         st.op2 = (int)i + 1;
                         st.alg_bytes += bytes_of(nx.in) + bytes_of(nx.out);
                         st.min_bytes = bytes_of(op.in) + bytes_of(nx.out);
@@ -303,7 +335,7 @@ static void build_steps(uf_model& m) {
                     }
                 }
             } else if (pw) {
-                st.impl = Impl::Pointwise;
+                st.impl = tc_ok(op) ? Impl::PointwiseTC : Impl::Pointwise;
             } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.groups == 1 && op.in2 < 0 &&
                        small_dense_supported(op.cin, op.cout) && view_vec_ok(in) && view_vec_ok(out)) {
                 st.impl = Impl::SmallDense;
@@ -313,6 +345,55 @@ static void build_steps(uf_model& m) {
             }
         }
         m.steps.push_back(st);
+    }
+}
+
+static void build_tc_weights(uf_model& m) {
+    for (Step& st : m.steps) {
+        if (st.impl != Impl::PointwiseTC) continue;
+        const Op& op = m.plan.ops[st.op];
+        const int N = op.cout, K = op.cin;
+        std::vector<float> hi((size_t)N * K), lo((size_t)N * K);
+        for (size_t i = 0; i < hi.size(); ++i) {  // op.w is [cout][cin][1][1] = [N][K], K contiguous
+            uint32_t u;
+            memcpy(&u, &op.w[i], 4);
+            u &= 0xffffe000u;
+            float h;
+            memcpy(&h, &u, 4);
+            hi[i] = h;
+            lo[i] = op.w[i] - h;
+        }
+        TcWeights t;
+        CK(cudaMalloc(&t.d_hi, hi.size() * sizeof(float)));
+        CK(cudaMalloc(&t.d_lo, lo.size() * sizeof(float)));
+        CK(cudaMemcpy(t.d_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(t.d_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+        const uint32_t box = (uint32_t)pointwise_tc_n_umma(N);
+        if (!make_tmap_f32_2d(&t.tm_hi, t.d_hi, N, K, (uint64_t)K * 4, box) ||
+            !make_tmap_f32_2d(&t.tm_lo, t.d_lo, N, K, (uint64_t)K * 4, box))
+            throw CudaError("cuTensorMapEncodeTiled failed for 1x1 weights of '" + m.plan.tensors[op.out].name + "'");
+        st.tc = (int)m.tc_weights.size();
+        m.tc_weights.push_back(t);
+        m.weight_bytes += 2 * hi.size() * sizeof(float);
+    }
+}
+
+// weights of the FusedTma steps in the layout of FusedWeights<C,N>: [dw 9*C][dw bias][pw C*N (ci major)][pw bias]
+static void build_param_weights(uf_model& m) {
+    for (Step& st : m.steps) {
+        if (st.impl != Impl::FusedTma) continue;
+        const Op& dw = m.plan.ops[st.op];
+        const Op& pw = m.plan.ops[st.op2];
+        const int C = dw.cout, N = pw.cout;
+        st.host_w.assign(fused_dwpw_tma_weight_floats(C, N), 0.f);
+        float* p = st.host_w.data();
+        for (int t = 0; t < 9; ++t)
+            for (int c = 0; c < C; ++c) p[t * C + c] = dw.w[(size_t)c * 9 + t];  // ONNX [c][1][ky][kx]
+        for (int c = 0; c < C; ++c) p[9 * C + c] = dw.b[c];
+        float* q = p + 10 * C;
+        for (int ci = 0; ci < C; ++ci)
+            for (int n = 0; n < N; ++n) q[ci * N + n] = pw.w[(size_t)n * C + ci];  // ONNX [n][ci][1][1]
+        for (int n = 0; n < N; ++n) q[C * N + n] = pw.b[n];
     }
 }
 
@@ -377,6 +458,27 @@ static void alloc_slots(uf_model& m) {
               (size_t)m.chunk * sort_cap * 8;
         CK(cudaStreamSynchronize(s.stream));
     }
+    for (auto& s : m.slots) {
+        s.tm_a.resize(m.steps.size());
+        s.tm_o.resize(m.steps.size());
+        for (size_t i = 0; i < m.steps.size(); ++i) {
+            if (m.steps[i].impl == Impl::FusedTma) {
+                const Op& dw = m.plan.ops[m.steps[i].op];
+                const Op& pw = m.plan.ops[m.steps[i].op2];
+                int iw, ih, ow, oh;
+                fused_dwpw_tma_boxes(dw.stride, &iw, &ih, &ow, &oh);
+                if (!make_tmap_nhwc(&s.tm_a[i], make_view(m, s, dw.in), (int)m.chunk, 16, iw, ih, 64) ||
+                    !make_tmap_nhwc(&s.tm_o[i], make_view(m, s, pw.out), (int)m.chunk, 32, ow, oh, 128))
+                    throw CudaError("cuTensorMapEncodeTiled failed for fused layer '" + m.plan.tensors[pw.out].name + "'");
+                continue;
+            }
+            if (m.steps[i].impl != Impl::PointwiseTC) continue;
+            const Op& op = m.plan.ops[m.steps[i].op];
+            TView v = make_view(m, s, op.in);
+            if (!make_tmap_f32_2d(&s.tm_a[i], v.p, (uint64_t)m.chunk * v.H * v.W, (uint64_t)v.C, (uint64_t)v.pix_stride * 4, 128))
+                throw CudaError("cuTensorMapEncodeTiled failed for the activations of '" + m.plan.tensors[op.out].name + "'");
+        }
+    }
     CK(cudaMalloc(&m.d_scores, (size_t)m.cfg.max_batch * K * 2 * sizeof(float)));
     CK(cudaMalloc(&m.d_boxes, (size_t)m.cfg.max_batch * K * 4 * sizeof(float)));
     ws += (size_t)m.cfg.max_batch * K * 6 * sizeof(float);
@@ -415,9 +517,11 @@ static TapsEntry& get_taps(uf_model& m, int sw, int sh) {
 }
 
 // ---- execution -----------------------------------------------------------------------------
-static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames) {
+static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_t first_step = 0,
+                    size_t last_step = (size_t)-1) {
     const Plan& p = m.plan;
-    for (const Step& st : m.steps) {
+    for (size_t si = first_step; si < m.steps.size() && si < last_step; ++si) {
+        const Step& st = m.steps[si];
         const Op& op = p.ops[st.op];
         ProfScope ps(m, s, st.label, st.alg_bytes * frames, st.min_bytes * frames, st.flops * frames);
         const float* w = m.d_weights + m.w_off[st.op];
@@ -438,6 +542,12 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames) {
             case Impl::Pointwise:
                 launch_pointwise(in, out, op.in2 >= 0 ? &res : nullptr, w, b, op.relu, frames, s.stream);
                 break;
+            case Impl::PointwiseTC: {
+                const TcWeights& tw = m.tc_weights[st.tc];
+                launch_pointwise_tc(s.tm_a[si], tw.tm_hi, tw.tm_lo, in, out, op.in2 >= 0 ? &res : nullptr, b, op.relu,
+                                    frames, s.stream);
+                break;
+            }
             case Impl::FusedDwPw: {
                 const Op& pw = p.ops[st.op2];
                 TView o2 = make_view(m, s, pw.out);
@@ -450,6 +560,12 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames) {
                 TView o2 = make_view(m, s, pw.out);
                 launch_fused_dwpw_pix(in, o2, w, b, op.stride, op.relu, m.d_weights + m.w_off[st.op2],
                                       m.d_weights + m.b_off[st.op2], pw.relu, frames, s.stream);
+                break;
+            }
+            case Impl::FusedTma: {
+                const Op& pw = p.ops[st.op2];
+                TView o2 = make_view(m, s, pw.out);
+                launch_fused_dwpw_tma(s.tm_a[si], s.tm_o[si], in, o2, st.host_w.data(), op.stride, op.relu, pw.relu, frames, s.stream);
                 break;
             }
             case Impl::SmallDense: launch_small_dense(in, out, w, b, op.dil, op.relu, frames, s.stream); break;
@@ -513,6 +629,54 @@ static void run_tail_post(uf_model& m, Slot& s, uint32_t first, int frames) {
                          (size_t)std::min(DET_FAST, K) * 5 * sizeof(float), frames, cudaMemcpyDeviceToHost, s.stream));
 }
 
+// conv stack + tail + post + D2H for one chunk. The chain is ~45 short kernels; replaying it as a CUDA graph
+// removes the per-launch CPU cost and most of the inter-kernel gaps (this is what bounds batch-1 latency).
+// The first step is kept outside the graph when it reads the caller's device buffer (pointer changes per call).
+static void run_body(uf_model& m, Slot& s, const U8View& input, uint32_t first, int frames) {
+    const bool use_graph = !m.profiling && !(m.cfg.flags & UF_FLAG_NO_GRAPH);
+    const bool stem_inside = input.p == s.d_resized;
+    if (!use_graph) {
+        run_cnn(m, s, input, frames);
+        run_tail_post(m, s, first, frames);
+        return;
+    }
+    const auto key = std::make_tuple(first, frames, stem_inside ? 1 : 0);
+    auto it = s.graphs.find(key);
+    if (it == s.graphs.end()) {
+        // first sighting: run eagerly (kernels set their function attributes on first use); capture on the second
+        if (s.graph_seen[key]++ == 0) {
+            run_cnn(m, s, input, frames);
+            run_tail_post(m, s, first, frames);
+            return;
+        }
+        if (!stem_inside) run_cnn(m, s, input, frames, 0, 1);
+        const uint64_t launches_before = m.launches;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            run_cnn(m, s, input, frames, stem_inside ? 0 : 1);
+            run_tail_post(m, s, first, frames);
+        } catch (...) {
+            cudaStreamEndCapture(s.stream, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        CK(cudaStreamEndCapture(s.stream, &g));
+        cudaGraphExec_t ge = nullptr;
+        cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        s.graphs[key] = ge;
+        s.graph_nodes[key] = (int)(m.launches - launches_before);
+        m.launches = launches_before;  // capture recorded the kernels, it did not launch them
+        it = s.graphs.find(key);
+    } else if (!stem_inside) {
+        run_cnn(m, s, input, frames, 0, 1);
+    }
+    CK(cudaGraphLaunch(it->second, s.stream));
+    m.launches += (uint64_t)s.graph_nodes[key];
+}
+
 struct FrameSrc {
     const uint8_t* p;
     uint32_t w, h;
@@ -560,8 +724,7 @@ static void run_chunk_host(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t fi
         i = j;
     }
     U8View input{s.d_resized, (long long)out_frame, H, W};
-    run_cnn(m, s, input, (int)n);
-    run_tail_post(m, s, first, (int)n);
+    run_body(m, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
 }
 
@@ -579,24 +742,24 @@ static void run_chunk_device(uf_model& m, Slot& s, const uint8_t* d_rgb, uint32_
         launch_resize(d_rgb, (long long)fb, w, h, s.d_resized, (long long)out_frame, W, H, (int)n, t.dev,
                       m.cfg.resize_round_intermediate, s.stream);
     }
-    run_cnn(m, s, input, (int)n);
-    run_tail_post(m, s, first, (int)n);
+    run_body(m, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
 }
 
 template <typename F>
-static void run_pipeline(uf_model& m, uint32_t n, uf_det* out, uint32_t cap, uint32_t* n_out, F&& submit) {
+static void run_pipeline(uf_model& m, uint32_t n, uint32_t step, uf_det* out, uint32_t cap, uint32_t* n_out, F&& submit) {
     if (n > m.cfg.max_batch) throw ArgError(UF_ERR_CAPACITY, "batch of " + std::to_string(n) + " exceeds max_batch " + std::to_string(m.cfg.max_batch));
     CK(cudaSetDevice(m.cfg.device));
     const uint32_t nslots = m.profiling ? 1 : m.nslots;  // profiling: one stream, so event pairs time kernels alone
     uint32_t c = 0;
-    for (uint32_t first = 0; first < n; first += m.chunk, ++c) {
+    for (uint32_t first = 0; first < n; first += step, ++c) {
         Slot& s = m.slots[c % nslots];
         harvest(m, s, out, cap, n_out);
-        submit(s, first, std::min(m.chunk, n - first));
+        submit(s, first, std::min(step, n - first));
     }
     for (uint32_t k = 0; k < nslots; ++k) harvest(m, m.slots[(c + k) % nslots], out, cap, n_out);
     m.last_n = n;
+    m.last_step = step;
 }
 
 static void* hook_scratch(uf_model& m, size_t bytes) {
@@ -631,15 +794,20 @@ static uf_model* load_model(const uf_config& cfg_in) {
     CK(cudaSetDevice(cfg.device));
     // chunk: big enough to amortise launches, small enough that a chunk's activations
     // (~arena_frame_floats*4 B per frame) do not dwarf the 126 MB L2
+    // chunk = frames per launch for device-resident input (big: fewer, fuller launches);
+    // host_chunk = frames per pipeline stage for host input (small: the H2D copy overlaps the kernels)
     uint32_t chunk = cfg.chunk;
-    if (chunk == 0) chunk = (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 64 : 16;
+    if (chunk == 0) chunk = (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 128 : 32;
     chunk = std::min(chunk, cfg.max_batch);
     m->chunk = chunk;
-    uint32_t nslots = cfg.slots ? cfg.slots : 3;
-    const uint32_t nchunks = (cfg.max_batch + chunk - 1) / chunk;
+    m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 32 : 8));
+    uint32_t nslots = cfg.slots ? cfg.slots : 4;
+    const uint32_t nchunks = (cfg.max_batch + m->host_chunk - 1) / m->host_chunk;
     m->nslots = std::max<uint32_t>(1, std::min(nslots, nchunks));
     pack_weights(*m);
     build_steps(*m);
+    build_tc_weights(*m);
+    build_param_weights(*m);
     label_steps(*m);
     build_lut(*m);
     CK(cudaMalloc(&m->d_priors, (size_t)m->K * 4 * sizeof(float)));
@@ -657,6 +825,7 @@ uf_model::~uf_model() {
     for (auto& s : slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto& g : s.graphs) cudaGraphExecDestroy(g.second);
         cudaFree(s.d_in); cudaFree(s.d_resized); cudaFree(s.d_arena); cudaFree(s.d_dets); cudaFree(s.d_sel);
         cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_dets);
@@ -667,6 +836,7 @@ uf_model::~uf_model() {
         TapsEntry& t = kv.second;
         cudaFree(t.d_vleft); cudaFree(t.d_vn); cudaFree(t.d_vw); cudaFree(t.d_hleft); cudaFree(t.d_hn); cudaFree(t.d_hw);
     }
+    for (auto& t : tc_weights) { cudaFree(t.d_hi); cudaFree(t.d_lo); }
     cudaFree(d_weights); cudaFree(d_lut); cudaFree(d_priors); cudaFree(d_scores); cudaFree(d_boxes); cudaFree(d_hook);
 }
 
@@ -741,7 +911,8 @@ int uf_infer_batch(uf_model* m, const uint8_t* const* rgb, const uint32_t* w, co
             fr[i] = FrameSrc{rgb[i], w[i], h[i]};
         }
         std::lock_guard<std::mutex> lk(m->mu);
-        run_pipeline(*m, n, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
+        // host frames: small pipeline stages so the H2D copy of stage i+1 hides behind the kernels of stage i
+        run_pipeline(*m, n, m->host_chunk, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
             run_chunk_host(*m, s, fr.data() + first, first, cnt);
         });
     });
@@ -759,7 +930,7 @@ int uf_infer_batch_device(uf_model* m, const uint8_t* d_rgb, uint32_t w, uint32_
         REQUIRE(cap == 0 || out, "out is NULL with cap > 0");
         std::lock_guard<std::mutex> lk(m->mu);
         const size_t fb = (size_t)w * h * 3;
-        run_pipeline(*m, n, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
+        run_pipeline(*m, n, m->chunk, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
             run_chunk_device(*m, s, d_rgb + (size_t)first * fb, w, h, first, cnt);
         });
     });
@@ -890,14 +1061,14 @@ int uf_tensor_read(uf_model* m, uint32_t i, uint32_t frame, float* out_nchw) {
         REQUIRE(m->tensor_readable[i], "tensor is not materialised (graph input, or fused away)");
         std::lock_guard<std::mutex> lk(m->mu);
         REQUIRE(frame < m->last_n, "frame outside the last batch");
-        const uint32_t nchunks = (m->last_n + m->chunk - 1) / m->chunk, c = frame / m->chunk;
+        const uint32_t nchunks = (m->last_n + m->last_step - 1) / m->last_step, c = frame / m->last_step;
         REQUIRE(c + m->nslots >= nchunks, "that chunk's workspace has been reused by a later chunk");
         CK(cudaSetDevice(m->cfg.device));
         Slot& s = m->slots[c % m->nslots];
         TView v = make_view(*m, s, (int)i);
         const size_t nfl = (size_t)v.C * v.H * v.W;
         float* d = (float*)hook_scratch(*m, nfl * sizeof(float));
-        launch_nhwc_to_nchw(v, (int)(frame % m->chunk), d, s.stream);
+        launch_nhwc_to_nchw(v, (int)(frame % m->last_step), d, s.stream);
         CK(cudaMemcpyAsync(out_nchw, d, nfl * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaGetLastError());

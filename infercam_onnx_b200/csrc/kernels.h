@@ -70,6 +70,24 @@ void launch_conv3x3_warp(const TView& in, const TView& out, const float* w_kkio,
 bool small_dense_supported(int cin, int cout);
 void launch_small_dense(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil,
                         int relu, int frames, cudaStream_t s);
+// K5 on tcgen05 (3xTF32, fp32-level accuracy): TMA-fed, TMEM accumulators, warp-specialised (kernels_tc.cu)
+struct alignas(64) TmaMap { unsigned char bytes[128]; };  // mirrors CUtensorMap
+bool make_tmap_f32_2d(TmaMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                      uint32_t box_rows);
+bool pointwise_tc_supported(int K, int N);
+int pointwise_tc_n_umma(int N);
+// tm_a: activations [frames*H*W][K] (row pitch pix_stride), box 128 rows; tm_whi/tm_wlo: weights [N][K], box n_umma rows
+void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TView& in,
+                         const TView& out, const TView* res, const float* bias, int relu, int frames, cudaStream_t s);
+// K4+K5 fused, TMA-pipelined persistent form (C in {16,32,64}, N in {32,64}); tm_in: 4-D map of the input view
+// with box (16, in_w, in_h, 1) and 64B swizzle; tm_out: 4-D map of the output view with box (32, out_w, out_h, 1), 128B swizzle
+bool make_tmap_nhwc(TmaMap* out, const TView& v, int frames, uint32_t box_c, uint32_t box_w, uint32_t box_h, int swizzle_bytes);
+bool fused_dwpw_tma_supported(int C, int N, int stride);
+void fused_dwpw_tma_boxes(int stride, int* in_w, int* in_h, int* out_w, int* out_h);
+size_t fused_dwpw_tma_weight_floats(int C, int N);
+// host_w: [dw 9*C][dw bias C][pw C*N][pw bias N] in HOST memory (passed by value as a __grid_constant__ parameter)
+void launch_fused_dwpw_tma(const TmaMap& tm_in, const TmaMap& tm_out, const TView& in, const TView& out,
+                           const float* host_w, int stride, int dw_relu, int pw_relu, int frames, cudaStream_t s);
 // fallbacks for graphs that do not fuse completely
 void launch_add(const TView& a, const TView& b, const TView& out, int relu, int frames, cudaStream_t s);
 void launch_relu(const TView& a, const TView& out, int frames, cudaStream_t s);

@@ -1,0 +1,603 @@
+// kernels_tc.cu — K5 on the 5th-generation tensor cores: pointwise (1x1) convolution as a GEMM
+//   out[M = frames*H*W][N = Cout] = in[M][K = Cin] * W[N][K]^T (+bias, +residual, ReLU)
+// with tcgen05.mma (kind::tf32), accumulators in TMEM, operands staged by TMA (128B swizzle),
+// for the layers where the channel counts make it a real dense contraction (K >= 32).
+//
+// Accuracy: the reference computes in fp32 and the contract is 1e-4 abs on the raw outputs
+// (BASELINE.json north_star). One TF32 pass (10-bit mantissa) does not meet that through 15 layers,
+// so every product is split 3xTF32:  a = a_hi + a_lo,  w = w_hi + w_lo  (hi = top 19 bits, exact
+// split) and  a*w ~= a_lo*w_hi + a_hi*w_lo + a_hi*w_hi  accumulated in fp32 in TMEM (the dropped
+// a_lo*w_lo term is ~2^-22 relative). w_hi/w_lo are precomputed at load; a_hi/a_lo are produced in
+// shared memory by four converter warps between the TMA and the MMA.
+//
+// Warp roles (320 threads, 1 CTA/SM, persistent over 128-row tiles):
+//   warps 0-3  converters : wait full[s] -> split the 128x32 fp32 A block in place into hi / lo
+//                           -> fence.proxy.async -> arrive conv[s]
+//   warps 4-7  epilogue   : wait acc_full[a] -> tcgen05.ld TMEM -> bias/residual/ReLU -> global
+//                           -> arrive acc_empty[a]     (warp w may touch TMEM lanes 32*(w%4)..+31)
+//   warp  8    TMA producer (one lane): A block [128 rows][32 k], W_hi and W_lo blocks [N][32 k]
+//   warp  9    MMA issuer (one lane) + TMEM allocation; tcgen05.commit frees smem stages / publishes
+//              the accumulator. Two accumulator buffers in TMEM overlap the epilogue of tile i with
+//              the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace uf {
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a wrong descriptor must abort the kernel (cudaErrorLaunchFailure), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    while (clock64() - t0 < 4000000000LL) {  // ~2 s at 1.9 GHz
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    printf("ultraface_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows at a
+// 128-byte pitch, 8-row groups 1024 bytes apart (SBO), version 1 (Blackwell), layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+constexpr int TC_BM = 128;        // rows per tile = UMMA M
+constexpr int TC_BK = 32;         // fp32 per K block = one 128-byte swizzle row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+
+struct TcParams {
+    TView out, res;
+    int has_res, relu;
+    const float* bias;
+    int M, K, N, n_umma, stages, tmem_cols;
+};
+
+__global__ void __launch_bounds__(320, 1)
+pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
+             const __grid_constant__ CUtensorMap tm_wlo, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = p.n_umma * TC_BK * 4;
+    const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                   // [stages] TMA landed
+    uint64_t* conv = full + p.stages;        // [stages] A split into hi/lo
+    uint64_t* empty = conv + p.stages;       // [stages] MMAs that read the stage are done
+    uint64_t* acc_full = empty + p.stages;   // [2]
+    uint64_t* acc_empty = acc_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = (p.M + TC_BM - 1) / TC_BM;
+    const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&conv[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t tx_bytes = (uint32_t)(TC_A_BYTES + 2 * b_bytes);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full[s], tx_bytes);
+                    tma_load_2d(st, &tm_a, &full[s], kb * TC_BK, tile * TC_BM);
+                    tma_load_2d(st + 2 * TC_A_BYTES, &tm_whi, &full[s], kb * TC_BK, 0);
+                    tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &tm_wlo, &full[s], kb * TC_BK, 0);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_umma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int a = it & 1;
+                const uint32_t aph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(&acc_empty[a], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(a * p.n_umma);
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    mbar_wait(&conv[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, w_hi = st + 2 * TC_A_BYTES, w_lo = w_hi + b_bytes;
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {  // small terms first, a_hi*w_hi last
+                        const uint32_t ab = term == 0 ? a_lo : a_hi;
+                        const uint32_t wb = term == 1 ? w_lo : w_hi;
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes
+                            umma_tf32(d, umma_desc_sw128(ab + k * 32), umma_desc_sw128(wb + k * 32), idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&acc_full[a]);
+            }
+        }
+    } else if (warp < 4) {
+        // ===== converters: fp32 -> (tf32 hi, tf32 lo), element-wise so the swizzled layout is preserved =====
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
+                float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+                float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + TC_A_BYTES);
+#pragma unroll
+                for (int j = 0; j < TC_A_BYTES / 16 / 128; ++j) {
+                    const int i = threadIdx.x + j * 128;
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&conv[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 4..7: TMEM -> registers -> per-warp smem transpose -> coalesced global =====
+        // A TMEM lane is an output row, so a lane owns a whole row; writing rows straight from the
+        // lanes would touch 32 different cache lines per store. Each warp stages 32 rows x 32 columns
+        // in its own padded smem tile and writes them back 4 rows per instruction (8 lanes x 16 B =
+        // one 128-byte line per row), with bias / residual / ReLU applied in the coalesced phase.
+        const int q = warp & 3;
+        float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15)) + q * (32 * 36);
+        const int HW = p.out.H * p.out.W;
+        const bool vec = ((p.N & 3) == 0) && ((p.out.pix_stride & 3) == 0) && ((reinterpret_cast<size_t>(p.out.p) & 15) == 0) &&
+                         ((p.out.frame_stride & 3) == 0) &&
+                         (!p.has_res || (((p.res.pix_stride & 3) == 0) && ((reinterpret_cast<size_t>(p.res.p) & 15) == 0) &&
+                                         ((p.res.frame_stride & 3) == 0)));
+        const int cl = (lane & 7) * 4;   // column (within the 32-column chunk) this lane handles when storing
+        const int rl = lane >> 3;        // row (within a group of 4) this lane handles when storing
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int a = it & 1;
+            const uint32_t aph = (uint32_t)((it >> 1) & 1);
+            mbar_wait(&acc_full[a], aph);
+            tc_fence_after();
+            const int m_base = tile * TC_BM + q * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_umma);
+            for (int c0 = 0; c0 < p.n_umma; c0 += 32) {
+                float v[32];
+                tmem_ld16(taddr + c0, v);  // warp-collective: executed by every lane
+                if (c0 + 16 < p.n_umma) tmem_ld16(taddr + c0 + 16, v + 16);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                const int n = c0 + cl;
+                float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < p.N) {
+                    bq.x = p.bias[n];
+                    if (n + 1 < p.N) bq.y = p.bias[n + 1];
+                    if (n + 2 < p.N) bq.z = p.bias[n + 2];
+                    if (n + 3 < p.N) bq.w = p.bias[n + 3];
+                }
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += 4) {
+                    const int r = r0 + rl;
+                    const int m = m_base + r;
+                    if (m < p.M && n < p.N) {
+                        const int f = m / HW;
+                        const int pix = m - f * HW;
+                        float4 x = *reinterpret_cast<const float4*>(stage + r * 36 + cl);
+                        x.x += bq.x; x.y += bq.y; x.z += bq.z; x.w += bq.w;
+                        float* op = p.out.p + (size_t)f * p.out.frame_stride + (size_t)pix * p.out.pix_stride + n;
+                        const float* rp = p.has_res ? p.res.p + (size_t)f * p.res.frame_stride + (size_t)pix * p.res.pix_stride + n : nullptr;
+                        if (vec && n + 4 <= p.N) {
+                            if (rp) { const float4 rr = *reinterpret_cast<const float4*>(rp); x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w; }
+                            if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                            *reinterpret_cast<float4*>(op) = x;
+                        } else {
+                            const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (n + j < p.N) {
+                                    float y = xv[j] + (rp ? rp[j] : 0.f);
+                                    op[j] = p.relu ? fmaxf(y, 0.f) : y;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[a]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point, so the
+// library does not link libcuda) and the launcher.
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp32 matrix [rows][cols] with a row pitch of row_stride_bytes; box = box_rows x 32 floats, 128B swizzle,
+// out-of-bounds elements read as zero.
+bool make_tmap_f32_2d(TmaMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                      uint32_t box_rows) {
+    static_assert(sizeof(TmaMap) == sizeof(CUtensorMap), "TmaMap must mirror CUtensorMap");
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {TC_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim,
+                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4+K5 fused, TMA-pipelined persistent form for the large memory-bound maps (C = 16/32/64):
+//   * the input tile (+halo) arrives by TMA as 16-channel slices [IH][IW][16] (64B swizzle,
+//     out-of-bounds = zero padding for free), double-buffered behind mbarriers, so the loads of
+//     the next slice / next tile overlap the arithmetic of the current one;
+//   * thread = output pixel: depthwise 3x3 per slice into registers (C values), then the 1x1 conv
+//     against weights broadcast from shared memory, 32 outputs per pass;
+//   * results are staged in a 128B-swizzled tile and leave by TMA store (edge tiles clipped by the
+//     tensor map), so neither loads nor stores cost address arithmetic or uncoalesced sectors.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Weights travel as a __grid_constant__ kernel parameter: with the loops fully unrolled every FFMA takes
+// its weight as a constant-bank operand, so the 1x1 conv costs no shared-memory bandwidth at all
+// (broadcasting weights from smem costs one wavefront per weight per warp and caps FFMA at 25 %).
+template <int C, int N>
+struct FusedWeights {
+    float dw[9 * C];   // [tap][c]
+    float dwb[C];
+    float pw[C * N];   // [ci][n]
+    float pwb[N];
+};
+
+template <int C, int N, int S, int TY>
+__global__ void __launch_bounds__(8 * TY, (8 * TY == 256) ? 2 : 3)
+fused_dwpw_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                      const __grid_constant__ FusedWeights<C, N> wts, int dw_relu, int pw_relu, int tiles_x, int tiles_y,
+                      int total_tiles) {
+    constexpr int TX = 8, IW = (TX - 1) * S + 3, IH = (TY - 1) * S + 3, NSL = C / 16, NTHR = TX * TY;
+    constexpr int SLICE_BYTES = IH * IW * 64;
+    constexpr int SLICE_ALLOC = (SLICE_BYTES + 1023) / 1024 * 1024;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* in_buf = smem;                                   // 2 x SLICE_ALLOC
+    uint8_t* out_stage = smem + 2 * SLICE_ALLOC;              // NTHR x 128 B
+    uint64_t* full = reinterpret_cast<uint64_t*>(out_stage + NTHR * 128);  // [2]
+    const int tid = threadIdx.x;
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_units = my_tiles * NSL;
+
+    auto tile_coords = [&](int t, int& f, int& y0, int& x0) {
+        int b = blockIdx.x + t * gridDim.x;
+        const int txi = b % tiles_x; b /= tiles_x;
+        const int tyi = b % tiles_y;
+        f = b / tiles_y;
+        x0 = txi * TX; y0 = tyi * TY;
+    };
+    auto issue = [&](int u) {  // thread 0 only
+        int f, y0, x0;
+        tile_coords(u / NSL, f, y0, x0);
+        uint64_t* bar = &full[u & 1];
+        mbar_expect_tx(bar, SLICE_BYTES);
+        tma_load_4d(in_buf + (u & 1) * SLICE_ALLOC, &tm_in, bar, (u % NSL) * 16, x0 * S - 1, y0 * S - 1, f);
+    };
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && n_units > 0) {
+        issue(0);
+        if (n_units > 1) issue(1);
+    }
+    const int tx = tid % TX, ty = tid / TX;
+    int u = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+        float d[C];
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl, ++u) {
+            mbar_wait(&full[u & 1], (uint32_t)((u >> 1) & 1));
+            const uint8_t* buf = in_buf + (u & 1) * SLICE_ALLOC;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = sl * 16 + q * 4;
+                float a0 = wts.dwb[c], a1 = wts.dwb[c + 1], a2 = wts.dwb[c + 2], a3 = wts.dwb[c + 3];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int r = (ty * S + ky) * IW + tx * S + kx;  // 64-byte row of the box
+                        const float4 v = *reinterpret_cast<const float4*>(buf + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+                        const int wo = (ky * 3 + kx) * C + c;
+                        a0 = fmaf(v.x, wts.dw[wo], a0); a1 = fmaf(v.y, wts.dw[wo + 1], a1);
+                        a2 = fmaf(v.z, wts.dw[wo + 2], a2); a3 = fmaf(v.w, wts.dw[wo + 3], a3);
+                    }
+                if (dw_relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                d[c] = a0; d[c + 1] = a1; d[c + 2] = a2; d[c + 3] = a3;
+            }
+            if (tid == 0 && sl == NSL - 1) bulk_wait_read0();  // the previous tile's store has left the staging tile
+            __syncthreads();                                    // everyone is done with this slice buffer
+            if (tid == 0 && u + 2 < n_units) issue(u + 2);
+        }
+        int f, y0, x0;
+        tile_coords(t, f, y0, x0);
+#pragma unroll
+        for (int n0 = 0; n0 < N; n0 += 32) {
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = wts.pwb[n0 + j];
+#pragma unroll
+            for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = fmaf(d[ci], wts.pw[ci * N + n0 + j], o[j]);
+            }
+            if (n0 > 0) {  // second pass of a 64-output layer: wait until the first pass' store has read the tile
+                if (tid == 0) bulk_wait_read0();
+                __syncthreads();
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 v = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+                if (pw_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                *reinterpret_cast<float4*>(out_stage + tid * 128 + ((q ^ (tid & 7)) << 4)) = v;  // 128B swizzle
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                tma_store_4d(&tm_out, out_stage, n0, x0, y0, f);
+                bulk_commit();
+            }
+        }
+    }
+    if (tid == 0) bulk_wait0();  // smem must outlive the last store
+}
+
+// NHWC fp32 view as a 4-D tensor map (C, W, H, frames); box = (box_c, box_w, box_h, 1)
+bool make_tmap_nhwc(TmaMap* out, const TView& v, int frames, uint32_t box_c, uint32_t box_w, uint32_t box_h, int swizzle_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)frames};
+    cuuint64_t gstride[3] = {(cuuint64_t)v.pix_stride * 4, (cuuint64_t)v.W * v.pix_stride * 4, (cuuint64_t)v.frame_stride * 4};
+    cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool fused_dwpw_tma_supported(int C, int N, int stride) {
+    if (C == 16) return N == 32 && stride == 1;
+    return C == 32 && (N == 32 || N == 64) && (stride == 1 || stride == 2);
+}
+
+void fused_dwpw_tma_boxes(int stride, int* in_w, int* in_h, int* out_w, int* out_h) {
+    const int TX = 8, TY = stride == 1 ? 32 : 16;
+    *in_w = (TX - 1) * stride + 3; *in_h = (TY - 1) * stride + 3; *out_w = TX; *out_h = TY;
+}
+
+template <int C, int N, int S, int TY>
+static void launch_tma_t(const TmaMap& tm_in, const TmaMap& tm_out, const TView& out, const float* host_w, int dw_relu,
+                         int pw_relu, int frames, cudaStream_t s) {
+    constexpr int TX = 8, IW = (TX - 1) * S + 3, IH = (TY - 1) * S + 3;
+    constexpr int SLICE_ALLOC = (IH * IW * 64 + 1023) / 1024 * 1024;
+    static_assert(sizeof(FusedWeights<C, N>) + 2 * sizeof(CUtensorMap) + 64 <= 32764, "kernel parameter space exceeded");
+    const int tiles_x = (out.W + TX - 1) / TX, tiles_y = (out.H + TY - 1) / TY;
+    const int total = tiles_x * tiles_y * frames;
+    const size_t smem = 2 * SLICE_ALLOC + TX * TY * 128 + 16 + 1024;
+    auto kern = fused_dwpw_tma_kernel<C, N, S, TY>;
+    static bool configured[64] = {};
+    static int ctas_per_sm[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        int nb = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TX * TY, smem);
+        ctas_per_sm[dev & 63] = nb < 1 ? 1 : nb;
+        configured[dev & 63] = true;
+    }
+    int grid = 148 * ctas_per_sm[dev & 63];
+    if (grid > total) grid = total;
+    kern<<<grid, TX * TY, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tm_in), *reinterpret_cast<const CUtensorMap*>(&tm_out),
+                                     *reinterpret_cast<const FusedWeights<C, N>*>(host_w), dw_relu, pw_relu, tiles_x, tiles_y, total);
+}
+
+size_t fused_dwpw_tma_weight_floats(int C, int N) { return (size_t)10 * C + (size_t)C * N + N; }
+
+// host_w: [dw 9*C][dw bias C][pw C*N][pw bias N] on the HOST (it is copied into the kernel parameter space)
+void launch_fused_dwpw_tma(const TmaMap& tm_in, const TmaMap& tm_out, const TView& in, const TView& out, const float* host_w,
+                           int stride, int dw_relu, int pw_relu, int frames, cudaStream_t s) {
+#define UF_T(CC, NN, SS, TYY) launch_tma_t<CC, NN, SS, TYY>(tm_in, tm_out, out, host_w, dw_relu, pw_relu, frames, s)
+    const int C = in.C, N = out.C;
+    if (C == 16 && N == 32 && stride == 1) UF_T(16, 32, 1, 32);
+    else if (C == 32 && N == 32 && stride == 1) UF_T(32, 32, 1, 32);
+    else if (C == 32 && N == 32 && stride == 2) UF_T(32, 32, 2, 16);
+    else if (C == 32 && N == 64 && stride == 2) UF_T(32, 64, 2, 16);
+    else if (C == 32 && N == 64 && stride == 1) UF_T(32, 64, 1, 32);
+#undef UF_T
+}
+
+bool pointwise_tc_supported(int K, int N) { return K >= 32 && K % 4 == 0 && N >= 1 && N <= 256; }
+
+int pointwise_tc_n_umma(int N) { return (N + 15) / 16 * 16; }
+
+void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TView& in, const TView& out,
+                         const TView* res, const float* bias, int relu, int frames, cudaStream_t s) {
+    TcParams p;
+    p.out = out;
+    p.res = res ? *res : TView{};
+    p.has_res = res != nullptr;
+    p.relu = relu;
+    p.bias = bias;
+    p.M = frames * in.H * in.W;
+    p.K = in.C;
+    p.N = out.C;
+    p.n_umma = pointwise_tc_n_umma(p.N);
+    const int stage_bytes = 2 * TC_A_BYTES + 2 * p.n_umma * TC_BK * 4;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 4) stages = 4;
+    const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    int cols = 32;
+    while (cols < 2 * p.n_umma) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 4) * sizeof(uint64_t) + 48 + 4 * 32 * 36 * sizeof(float) + 1024;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured[dev & 63] = true;
+    }
+    (void)kblocks;
+    const int tiles = (p.M + TC_BM - 1) / TC_BM;
+    const int grid = tiles < 148 ? tiles : 148;
+    pw_tc_kernel<<<grid, 320, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tm_a), *reinterpret_cast<const CUtensorMap*>(&tm_whi),
+                                         *reinterpret_cast<const CUtensorMap*>(&tm_wlo), p);
+}
+
+}  // namespace uf
