@@ -115,7 +115,8 @@ struct Slot {
     std::vector<int> ev_stat;                             // stat index per pair
     size_t ev_used = 0;
     std::vector<TmaMap> tm_a;                             // per step: activation tensor map (PointwiseTC / FusedTma input)
-    std::vector<TmaMap> tm_o;                             // per step: output tensor map (FusedTma)
+    std::vector<TmaMap> tm_o;                             // per step: output tensor map (FusedTma, PointwiseTC)
+    std::vector<uint8_t> tm_o_ok;                         // per step: tm_o is valid
     // CUDA graphs of the kernel chain (conv stack + tail + post + D2H), keyed by (first frame, frames, stem inside?)
     std::map<std::tuple<uint32_t, int, int>, cudaGraphExec_t> graphs;
     std::map<std::tuple<uint32_t, int, int>, int> graph_seen, graph_nodes;
@@ -461,6 +462,7 @@ static void alloc_slots(uf_model& m) {
     for (auto& s : m.slots) {
         s.tm_a.resize(m.steps.size());
         s.tm_o.resize(m.steps.size());
+        s.tm_o_ok.assign(m.steps.size(), 0);
         for (size_t i = 0; i < m.steps.size(); ++i) {
             if (m.steps[i].impl == Impl::FusedTma) {
                 const Op& dw = m.plan.ops[m.steps[i].op];
@@ -477,6 +479,13 @@ static void alloc_slots(uf_model& m) {
             TView v = make_view(m, s, op.in);
             if (!make_tmap_f32_2d(&s.tm_a[i], v.p, (uint64_t)m.chunk * v.H * v.W, (uint64_t)v.C, (uint64_t)v.pix_stride * 4, 128))
                 throw CudaError("cuTensorMapEncodeTiled failed for the activations of '" + m.plan.tensors[op.out].name + "'");
+            // TMA-store epilogue when the output rows are 16-byte aligned and frames are densely packed
+            TView o = make_view(m, s, op.out);
+            const TensorDesc& od = m.plan.tensors[op.out];
+            if (op.in2 < 0 && o.pix_stride % 4 == 0 && od.base_off % 4 == 0 && o.C % 4 == 0 &&
+                o.frame_stride == (long long)o.H * o.W * o.pix_stride)
+                s.tm_o_ok[i] = make_tmap_f32_2d_store(&s.tm_o[i], o.p, (uint64_t)m.chunk * o.H * o.W, (uint64_t)o.C,
+                                                      (uint64_t)o.pix_stride * 4) ? 1 : 0;
         }
     }
     CK(cudaMalloc(&m.d_scores, (size_t)m.cfg.max_batch * K * 2 * sizeof(float)));
@@ -544,8 +553,8 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                 break;
             case Impl::PointwiseTC: {
                 const TcWeights& tw = m.tc_weights[st.tc];
-                launch_pointwise_tc(s.tm_a[si], tw.tm_hi, tw.tm_lo, in, out, op.in2 >= 0 ? &res : nullptr, b, op.relu,
-                                    frames, s.stream);
+                launch_pointwise_tc(s.tm_a[si], tw.tm_hi, tw.tm_lo, s.tm_o_ok[si] ? &s.tm_o[si] : nullptr, in, out,
+                                    op.in2 >= 0 ? &res : nullptr, op.b.data(), op.relu, frames, s.stream);
                 break;
             }
             case Impl::FusedDwPw: {
@@ -724,7 +733,8 @@ static void run_chunk_host(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t fi
         i = j;
     }
     U8View input{s.d_resized, (long long)out_frame, H, W};
-    run_body(m, s, input, first, (int)n);
+    static const bool copy_only = getenv("UF_DEBUG_COPY_ONLY") != nullptr;  // experiment: H2D pipeline alone
+    if (!copy_only) run_body(m, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
 }
 
@@ -801,6 +811,7 @@ static uf_model* load_model(const uf_config& cfg_in) {
     chunk = std::min(chunk, cfg.max_batch);
     m->chunk = chunk;
     m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 32 : 8));
+    if (const char* e = getenv("UF_HOST_CHUNK")) m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint32_t)atoi(e)));
     uint32_t nslots = cfg.slots ? cfg.slots : 4;
     const uint32_t nchunks = (cfg.max_batch + m->host_chunk - 1) / m->host_chunk;
     m->nslots = std::max<uint32_t>(1, std::min(nslots, nchunks));

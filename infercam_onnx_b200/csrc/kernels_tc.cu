@@ -94,6 +94,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows at a
 // 128-byte pitch, 8-row groups 1024 bytes apart (SBO), version 1 (Blackwell), layout SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -107,13 +130,15 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 struct TcParams {
     TView out, res;
     int has_res, relu;
-    const float* bias;
     int M, K, N, n_umma, stages, tmem_cols;
+    int tma_store;      // epilogue leaves through TMA (dense, 16-byte aligned rows, no residual)
+    float bias[256];    // constant-bank operands of the epilogue
 };
 
 __global__ void __launch_bounds__(320, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
-             const __grid_constant__ CUtensorMap tm_wlo, const TcParams p) {
+             const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_out,
+             const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -241,7 +266,49 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         // in its own padded smem tile and writes them back 4 rows per instruction (8 lanes x 16 B =
         // one 128-byte line per row), with bias / residual / ReLU applied in the coalesced phase.
         const int q = warp & 3;
-        float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15)) + q * (32 * 36);
+        if (p.tma_store) {
+            // fast path: +bias (constant bank) / ReLU in registers -> 128B-swizzled 32x32 tile per warp -> TMA store
+            // (rows past M and columns past N are clipped by the tensor map): no address arithmetic at all.
+            uint8_t* st = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) + q * 4096;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int a = it & 1;
+                const uint32_t aph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(&acc_full[a], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_umma);
+                for (int c0 = 0; c0 < p.n_umma; c0 += 32) {
+                    float v[32];
+                    tmem_ld16(taddr + c0, v);
+                    if (c0 + 16 < p.n_umma) {
+                        tmem_ld16(taddr + c0 + 16, v + 16);
+                    } else {
+#pragma unroll
+                        for (int j = 16; j < 32; ++j) v[j] = 0.f;
+                    }
+                    if (lane == 0) bulk_wait_read0();  // this warp's previous store has left the staging tile
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 x;
+                        x.x = v[j] + p.bias[(c0 + j) & 255]; x.y = v[j + 1] + p.bias[(c0 + j + 1) & 255];
+                        x.z = v[j + 2] + p.bias[(c0 + j + 2) & 255]; x.w = v[j + 3] + p.bias[(c0 + j + 3) & 255];
+                        if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        *reinterpret_cast<float4*>(st + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4)) = x;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tm_out, st, c0, tile * TC_BM + q * 32);
+                        bulk_commit();
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[a]);
+            }
+            if (lane == 0) bulk_wait0();
+        } else {
+                float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15)) + q * (32 * 36);
         const int HW = p.out.H * p.out.W;
         const bool vec = ((p.N & 3) == 0) && ((p.out.pix_stride & 3) == 0) && ((reinterpret_cast<size_t>(p.out.p) & 15) == 0) &&
                          ((p.out.frame_stride & 3) == 0) &&
@@ -267,10 +334,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 const int n = c0 + cl;
                 float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n < p.N) {
-                    bq.x = p.bias[n];
-                    if (n + 1 < p.N) bq.y = p.bias[n + 1];
-                    if (n + 2 < p.N) bq.z = p.bias[n + 2];
-                    if (n + 3 < p.N) bq.w = p.bias[n + 3];
+                    bq.x = p.bias[n & 255];
+                    if (n + 1 < p.N) bq.y = p.bias[(n + 1) & 255];
+                    if (n + 2 < p.N) bq.z = p.bias[(n + 2) & 255];
+                    if (n + 3 < p.N) bq.w = p.bias[(n + 3) & 255];
                 }
 #pragma unroll
                 for (int r0 = 0; r0 < 32; r0 += 4) {
@@ -303,6 +370,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[a]);
+        }
         }
     }
     tc_fence_before();
@@ -360,23 +428,6 @@ bool make_tmap_f32_2d(TmaMap* out, const float* base, uint64_t rows, uint64_t co
 //   * results are staged in a 128B-swizzled tile and leave by TMA store (edge tiles clipped by the
 //     tensor map), so neither loads nor stores cost address arithmetic or uncoalesced sectors.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                     reinterpret_cast<uint64_t>(map)),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // Weights travel as a __grid_constant__ kernel parameter: with the loops fully unrolled every FFMA takes
 // its weight as a constant-bank operand, so the 1x1 conv costs no shared-memory bandwidth at all
 // (broadcasting weights from smem costs one wavefront per weight per warp and caps FFMA at 25 %).
@@ -564,28 +615,44 @@ bool pointwise_tc_supported(int K, int N) { return K >= 32 && K % 4 == 0 && N >=
 
 int pointwise_tc_n_umma(int N) { return (N + 15) / 16 * 16; }
 
-void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TView& in, const TView& out,
-                         const TView* res, const float* bias, int relu, int frames, cudaStream_t s) {
+// fp32 matrix [rows][cols] (row pitch row_stride_bytes) for the epilogue's TMA store: box 32 x 32, 128B swizzle
+bool make_tmap_f32_2d_store(TmaMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim,
+                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// host_bias: N floats in HOST memory (copied into the kernel parameter space); tm_out may be null (legacy epilogue)
+void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TmaMap* tm_out, const TView& in,
+                         const TView& out, const TView* res, const float* host_bias, int relu, int frames, cudaStream_t s) {
     TcParams p;
     p.out = out;
     p.res = res ? *res : TView{};
     p.has_res = res != nullptr;
     p.relu = relu;
-    p.bias = bias;
     p.M = frames * in.H * in.W;
     p.K = in.C;
     p.N = out.C;
     p.n_umma = pointwise_tc_n_umma(p.N);
+    p.tma_store = (tm_out != nullptr && res == nullptr) ? 1 : 0;
+    for (int i = 0; i < 256; ++i) p.bias[i] = i < p.N ? host_bias[i] : 0.f;
     const int stage_bytes = 2 * TC_A_BYTES + 2 * p.n_umma * TC_BK * 4;
-    int stages = (200 * 1024) / stage_bytes;
+    int stages = (198 * 1024) / stage_bytes;
     if (stages > 4) stages = 4;
-    const int kblocks = (p.K + TC_BK - 1) / TC_BK;
     if (stages < 2) stages = 2;
     p.stages = stages;
     int cols = 32;
     while (cols < 2 * p.n_umma) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 4) * sizeof(uint64_t) + 48 + 4 * 32 * 36 * sizeof(float) + 1024;
+    // stages | barriers + tmem slot | (pad to 1 KB) | 4 per-warp staging tiles of 4.6 KB (legacy) / 4 KB (TMA store)
+    const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 4) * sizeof(uint64_t) + 16 + 1024 + 4 * 32 * 36 * sizeof(float) + 1024;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -593,11 +660,11 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
         cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured[dev & 63] = true;
     }
-    (void)kblocks;
     const int tiles = (p.M + TC_BM - 1) / TC_BM;
     const int grid = tiles < 148 ? tiles : 148;
+    const TmaMap& to = tm_out ? *tm_out : tm_a;  // unused when tma_store == 0
     pw_tc_kernel<<<grid, 320, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tm_a), *reinterpret_cast<const CUtensorMap*>(&tm_whi),
-                                         *reinterpret_cast<const CUtensorMap*>(&tm_wlo), p);
+                                         *reinterpret_cast<const CUtensorMap*>(&tm_wlo), *reinterpret_cast<const CUtensorMap*>(&to), p);
 }
 
 }  // namespace uf
