@@ -357,8 +357,8 @@ def main():
                            "mean_detections_per_frame": float(np.mean(counts)),
                            "algorithmic_bytes_per_frame": int(info.algorithmic_bytes_per_frame),
                            "macs_per_frame": int(info.macs_per_frame)},
-                "e2e": {"value": n_frames * args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": B * SRC_W * SRC_H * 3,
-                        "d2h_bytes_per_step": B * (4 + 128 * 20), "ms_per_step": t_e2e / args.steps * 1e3,
+                "e2e": {"value": n_frames * args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": n_frames * SRC_W * SRC_H * 3,
+                        "d2h_bytes_per_step": n_frames * (4 + 128 * 20), "ms_per_step": t_e2e / args.steps * 1e3,
                         "api": "uf_infer_batch (C ABI) from pinned host frames"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "latency_batch1_ms": {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)], "iters": len(lat)},

@@ -79,7 +79,7 @@ struct Step {
     uint64_t flops = 0;      // per frame
     std::string label;       // "<kernel family>[<shape>]" for the per-launch profile
     int tc = -1;             // index into uf_model::tc_weights for PointwiseTC steps
-    std::vector<float> host_w;  // FusedTma: weights in kernel-parameter layout (host copy)
+    std::vector<float> host_w;  // FusedTma / Stem / SmallDense: weights in kernel-parameter layout (host copy)
 };
 
 struct TcWeights {           // 3xTF32 split of one 1x1 conv's weights, [N][K] K-major, plus their tensor maps
@@ -337,7 +337,7 @@ static void build_steps(uf_model& m) {
                 }
             } else if (pw) {
                 st.impl = tc_ok(op) ? Impl::PointwiseTC : Impl::Pointwise;
-            } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.groups == 1 && op.in2 < 0 &&
+            } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.dil <= 8 && op.groups == 1 && op.in2 < 0 &&
                        small_dense_supported(op.cin, op.cout) && view_vec_ok(in) && view_vec_ok(out)) {
                 st.impl = Impl::SmallDense;
             } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.groups == 1 && op.in2 < 0 &&
@@ -382,6 +382,19 @@ static void build_tc_weights(uf_model& m) {
 // weights of the FusedTma steps in the layout of FusedWeights<C,N>: [dw 9*C][dw bias][pw C*N (ci major)][pw bias]
 static void build_param_weights(uf_model& m) {
     for (Step& st : m.steps) {
+        if (st.impl == Impl::Stem || st.impl == Impl::SmallDense) {
+            // [ky][kx][ci][co] weights followed by the biases
+            const Op& op = m.plan.ops[st.op];
+            const int k = op.k, ci_n = op.cin, co_n = op.cout;
+            st.host_w.assign((size_t)k * k * ci_n * co_n + co_n, 0.f);
+            for (int co = 0; co < co_n; ++co)
+                for (int ci = 0; ci < ci_n; ++ci)
+                    for (int ky = 0; ky < k; ++ky)
+                        for (int kx = 0; kx < k; ++kx)
+                            st.host_w[((size_t)(ky * k + kx) * ci_n + ci) * co_n + co] = op.w[(((size_t)co * ci_n + ci) * k + ky) * k + kx];
+            for (int co = 0; co < co_n; ++co) st.host_w[(size_t)k * k * ci_n * co_n + co] = op.b[co];
+            continue;
+        }
         if (st.impl != Impl::FusedTma) continue;
         const Op& dw = m.plan.ops[st.op];
         const Op& pw = m.plan.ops[st.op2];
@@ -546,7 +559,7 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                                     op.in2 >= 0 ? &res : nullptr, w, b, cp, frames, s.stream);
                 break;
             }
-            case Impl::Stem: launch_stem(input, m.d_lut, out, w, b, op.relu, frames, s.stream); break;
+            case Impl::Stem: launch_stem(input, m.d_lut, out, st.host_w.data(), op.relu, frames, s.stream); break;
             case Impl::Depthwise: launch_depthwise(in, out, w, b, op.stride, op.relu, frames, s.stream); break;
             case Impl::Pointwise:
                 launch_pointwise(in, out, op.in2 >= 0 ? &res : nullptr, w, b, op.relu, frames, s.stream);
@@ -577,7 +590,7 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                 launch_fused_dwpw_tma(s.tm_a[si], s.tm_o[si], in, o2, st.host_w.data(), op.stride, op.relu, pw.relu, frames, s.stream);
                 break;
             }
-            case Impl::SmallDense: launch_small_dense(in, out, w, b, op.dil, op.relu, frames, s.stream); break;
+            case Impl::SmallDense: launch_small_dense(in, out, st.host_w.data(), op.dil, op.relu, frames, s.stream); break;
             case Impl::Conv3x3Warp: launch_conv3x3_warp(in, out, w, b, op.dil, op.relu, frames, s.stream); break;
             case Impl::Add: launch_add(in, res, out, op.relu, frames, s.stream); break;
             case Impl::Relu: launch_relu(in, out, frames, s.stream); break;

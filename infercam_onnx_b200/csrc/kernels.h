@@ -44,8 +44,9 @@ void launch_conv_generic(const TView& in, const U8View* in_u8, const float* lut,
                          const TView* res, const float* w_kkio, const float* b, const ConvParams& p,
                          int frames, cudaStream_t s);
 // K3 stem: 3x3 s2 p1, 3 -> 16, u8 input through the LUT, bias + ReLU
-void launch_stem(const U8View& in, const float* lut, const TView& out, const float* w_kkio,
-                 const float* b, int relu, int frames, cudaStream_t s);
+// host_w: 27*16 weights [ky][kx][ci][co] + 16 biases in HOST memory (passed as a __grid_constant__ parameter)
+void launch_stem(const U8View& in, const float* lut, const TView& out, const float* host_w, int relu, int frames,
+                 cudaStream_t s);
 // K4 depthwise 3x3 (pad 1, stride 1|2), weights [9][C]
 void launch_depthwise(const TView& in, const TView& out, const float* w_tc, const float* b, int stride,
                       int relu, int frames, cudaStream_t s);
@@ -68,8 +69,9 @@ void launch_conv3x3_warp(const TView& in, const TView& out, const float* w_kkio,
                          int relu, int frames, cudaStream_t s);
 // K6 small dense 3x3 (stride 1, pad = dil), Cin,Cout in {8,12,16}, weights [3][3][Cin][Cout]
 bool small_dense_supported(int cin, int cout);
-void launch_small_dense(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil,
-                        int relu, int frames, cudaStream_t s);
+// host_w: 9*Cin*Cout weights [ky][kx][ci][co] + Cout biases in HOST memory (kernel-parameter constants); dil <= 8
+void launch_small_dense(const TView& in, const TView& out, const float* host_w, int dil, int relu, int frames,
+                        cudaStream_t s);
 // K5 on tcgen05 (3xTF32, fp32-level accuracy): TMA-fed, TMEM accumulators, warp-specialised (kernels_tc.cu)
 struct alignas(64) TmaMap { unsigned char bytes[128]; };  // mirrors CUtensorMap
 bool make_tmap_f32_2d(TmaMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,

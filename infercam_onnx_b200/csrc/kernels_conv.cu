@@ -82,15 +82,19 @@ void launch_conv_generic(const TView& in, const U8View* in_u8, const float* lut,
 constexpr int STEM_T = 16;
 constexpr int STEM_IN = 2 * STEM_T + 1;
 
+// weights travel in the kernel parameter space: every FFMA takes its weight as a constant-bank operand
+// (broadcasting them from shared memory costs one smem wavefront per FFMA and caps the FMA pipe at 25 %)
+struct StemWeights {
+    float w[27 * 16];  // [ky][kx][ci][co]
+    float b[16];
+};
+
 __global__ void __launch_bounds__(STEM_T * STEM_T)
-stem_kernel(U8View in, const float* __restrict__ lut, TView out, const float* __restrict__ w,
-            const float* __restrict__ b, int relu) {
+stem_kernel(U8View in, const float* __restrict__ lut, TView out, const __grid_constant__ StemWeights wts, int relu) {
     __shared__ float s_in[STEM_IN * STEM_IN * 3];
-    __shared__ __align__(16) float s_w[27 * 16];
     __shared__ float s_lut[768];
     const int tid = threadIdx.x;
     for (int i = tid; i < 768; i += blockDim.x) s_lut[i] = lut[i];
-    for (int i = tid; i < 27 * 16; i += blockDim.x) s_w[i] = w[i];
     __syncthreads();
     const int ox0 = blockIdx.x * STEM_T, oy0 = blockIdx.y * STEM_T, n = blockIdx.z;
     const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
@@ -111,7 +115,7 @@ stem_kernel(U8View in, const float* __restrict__ lut, TView out, const float* __
     if (ox >= out.W || oy >= out.H) return;
     float acc[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = b[c];
+    for (int c = 0; c < 16; ++c) acc[c] = wts.b[c];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -119,15 +123,8 @@ stem_kernel(U8View in, const float* __restrict__ lut, TView out, const float* __
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
                 const float v = s_in[((ty * 2 + ky) * STEM_IN + tx * 2 + kx) * 3 + ci];
-                const float4* wp = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * 3 + ci) * 16);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 ww = wp[q];
-                    acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
-                    acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
-                    acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
-                    acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
-                }
+                for (int co = 0; co < 16; ++co) acc[co] = fmaf(v, wts.w[((ky * 3 + kx) * 3 + ci) * 16 + co], acc[co]);
             }
     float* op = out.p + (size_t)n * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
 #pragma unroll
@@ -138,10 +135,11 @@ stem_kernel(U8View in, const float* __restrict__ lut, TView out, const float* __
     }
 }
 
-void launch_stem(const U8View& in, const float* lut, const TView& out, const float* w_kkio, const float* b,
-                 int relu, int frames, cudaStream_t s) {
+// host_w: 27*16 weights [ky][kx][ci][co] followed by 16 biases, in HOST memory
+void launch_stem(const U8View& in, const float* lut, const TView& out, const float* host_w, int relu, int frames,
+                 cudaStream_t s) {
     dim3 grid((out.W + STEM_T - 1) / STEM_T, (out.H + STEM_T - 1) / STEM_T, frames);
-    stem_kernel<<<grid, STEM_T * STEM_T, 0, s>>>(in, lut, out, w_kkio, b, relu);
+    stem_kernel<<<grid, STEM_T * STEM_T, 0, s>>>(in, lut, out, *reinterpret_cast<const StemWeights*>(host_w), relu);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -704,79 +702,67 @@ void launch_fused_dwpw_pix(const TView& in, const TView& out, const float* dw_w_
 // computes two horizontally adjacent pixels x COUT so one weight LDS.128 feeds 8 FFMA.
 // ---------------------------------------------------------------------------------------------
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(128)
-small_dense3x3_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int dil,
-                      int relu, long long total_pairs) {
-    __shared__ __align__(16) float s_w[9 * CIN * COUT];
-    __shared__ float s_b[COUT];
-    for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) s_w[i] = w[i];
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_b[i] = b[i];
+struct SmallDenseWeights {
+    float w[9 * CIN * COUT];  // [ky][kx][ci][co]
+    float b[COUT];
+};
+
+// CTA = 8 x 16 output pixels of one frame, thread = pixel x all COUT. The input tile (+dilation halo) is staged
+// in shared memory with coalesced float4 loads and a padded pixel pitch (conflict-free LDS.128); weights are
+// constant-bank operands, so the inner loop is pure FFMA: 9*CIN*COUT per thread against 9*CIN/4 LDS.128.
+constexpr int SD_TX = 8, SD_TY = 16;
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(SD_TX * SD_TY)
+small_dense3x3_kernel(TView in, TView out, const __grid_constant__ SmallDenseWeights<CIN, COUT> wts, int dil, int relu,
+                      int tiles_x, int tiles_y) {
+    constexpr int P = CIN + 4, C4 = CIN / 4, NTHR = SD_TX * SD_TY;
+    extern __shared__ __align__(16) float s_in[];  // (SD_TY+2d) x (SD_TX+2d) x P
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int txi = bid % tiles_x; bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int f = bid / tiles_y;
+    const int x0 = txi * SD_TX, y0 = tyi * SD_TY;
+    const int IW = SD_TX + 2 * dil, IH = SD_TY + 2 * dil;
+    const float* ip = in.p + (size_t)f * in.frame_stride;
+    for (int i = tid; i < IH * IW * C4; i += NTHR) {
+        const int pix = i / C4, q = i - pix * C4;
+        const int py = pix / IW, px = pix - py * IW;
+        const int gy = y0 - dil + py, gx = x0 - dil + px;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < in.H && gx >= 0 && gx < in.W) v = ld4(ip + ((size_t)gy * in.W + gx) * in.pix_stride + q * 4);
+        st4(s_in + pix * P + q * 4, v);
+    }
     __syncthreads();
-    const int Wp = (out.W + 1) >> 1;  // pixel pairs per row
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_pairs;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int xp = (int)(idx % Wp);
-        long long t = idx / Wp;
-        const int y = (int)(t % out.H);
-        const int n = (int)(t / out.H);
-        const int x0 = xp * 2;
-        const bool has1 = x0 + 1 < out.W;
-        float acc0[COUT], acc1[COUT];
+    const int tx = tid % SD_TX, ty = tid / SD_TX;
+    const int ox = x0 + tx, oy = y0 + ty;
+    if (ox >= out.W || oy >= out.H) return;
+    float acc[COUT];
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) { acc0[c] = s_b[c]; acc1[c] = s_b[c]; }
-        const float* ip = in.p + (size_t)n * in.frame_stride;
+    for (int c = 0; c < COUT; ++c) acc[c] = wts.b[c];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = y + (ky - 1) * dil;
-            if (iy < 0 || iy >= in.H) continue;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix0 = x0 + (kx - 1) * dil, ix1 = ix0 + 1;
-                const bool ok0 = ix0 >= 0 && ix0 < in.W;
-                const bool ok1 = has1 && ix1 >= 0 && ix1 < in.W;
-                if (!ok0 && !ok1) continue;
-                const float* p0 = ip + ((size_t)iy * in.W + (ok0 ? ix0 : 0)) * in.pix_stride;
-                const float* p1 = ip + ((size_t)iy * in.W + (ok1 ? ix1 : 0)) * in.pix_stride;
+        for (int kx = 0; kx < 3; ++kx) {
+            const float* sp = s_in + ((ty + ky * dil) * IW + tx + kx * dil) * P;
 #pragma unroll
-                for (int cq = 0; cq < CIN; cq += 4) {
-                    float4 a0 = ok0 ? ld4(p0 + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 a1 = ok1 ? ld4(p1 + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float av0[4] = {a0.x, a0.y, a0.z, a0.w};
-                    const float av1[4] = {a1.x, a1.y, a1.z, a1.w};
+            for (int cq = 0; cq < CIN; cq += 4) {
+                const float4 a = ld4(sp + cq);
+                const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                    for (int ci = 0; ci < 4; ++ci) {
-                        const float4* wp = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CIN + cq + ci) * COUT);
+                for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
-                        for (int q = 0; q < COUT / 4; ++q) {
-                            const float4 ww = wp[q];
-                            acc0[q * 4 + 0] = fmaf(av0[ci], ww.x, acc0[q * 4 + 0]);
-                            acc0[q * 4 + 1] = fmaf(av0[ci], ww.y, acc0[q * 4 + 1]);
-                            acc0[q * 4 + 2] = fmaf(av0[ci], ww.z, acc0[q * 4 + 2]);
-                            acc0[q * 4 + 3] = fmaf(av0[ci], ww.w, acc0[q * 4 + 3]);
-                            acc1[q * 4 + 0] = fmaf(av1[ci], ww.x, acc1[q * 4 + 0]);
-                            acc1[q * 4 + 1] = fmaf(av1[ci], ww.y, acc1[q * 4 + 1]);
-                            acc1[q * 4 + 2] = fmaf(av1[ci], ww.z, acc1[q * 4 + 2]);
-                            acc1[q * 4 + 3] = fmaf(av1[ci], ww.w, acc1[q * 4 + 3]);
-                        }
-                    }
-                }
+                    for (int co = 0; co < COUT; ++co)
+                        acc[co] = fmaf(av[ci], wts.w[((ky * 3 + kx) * CIN + cq + ci) * COUT + co], acc[co]);
             }
         }
-        float* op = out.p + (size_t)n * out.frame_stride + ((size_t)y * out.W + x0) * out.pix_stride;
+    float* op = out.p + (size_t)f * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
 #pragma unroll
-        for (int q = 0; q < COUT / 4; ++q) {
-            float4 v = make_float4(acc0[q * 4], acc0[q * 4 + 1], acc0[q * 4 + 2], acc0[q * 4 + 3]);
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            st4(op + q * 4, v);
-        }
-        if (has1) {
-#pragma unroll
-            for (int q = 0; q < COUT / 4; ++q) {
-                float4 v = make_float4(acc1[q * 4], acc1[q * 4 + 1], acc1[q * 4 + 2], acc1[q * 4 + 3]);
-                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                st4(op + out.pix_stride + q * 4, v);
-            }
-        }
+    for (int q = 0; q < COUT / 4; ++q) {
+        float4 v = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        st4(op + q * 4, v);
     }
 }
 
@@ -784,16 +770,29 @@ bool small_dense_supported(int cin, int cout) {
     return (cin == 8 && (cout == 16 || cout == 12)) || (cin == 12 && cout == 16) || (cin == 16 && cout == 16);
 }
 
-void launch_small_dense(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil, int relu,
-                        int frames, cudaStream_t s) {
-    const long long total = (long long)frames * out.H * ((out.W + 1) / 2);
-    const int grid = grid_for(total, 128, 32);
-#define UF_SD(CI, CO) small_dense3x3_kernel<CI, CO><<<grid, 128, 0, s>>>(in, out, w_kkio, b, dil, relu, total)
-    if (in.C == 8 && out.C == 16) UF_SD(8, 16);
-    else if (in.C == 8 && out.C == 12) UF_SD(8, 12);
-    else if (in.C == 12 && out.C == 16) UF_SD(12, 16);
-    else if (in.C == 16 && out.C == 16) UF_SD(16, 16);
-#undef UF_SD
+template <int CIN, int COUT>
+static void launch_sd_t(const TView& in, const TView& out, const float* host_w, int dil, int relu, int frames, cudaStream_t s) {
+    const int tiles_x = (out.W + SD_TX - 1) / SD_TX, tiles_y = (out.H + SD_TY - 1) / SD_TY;
+    const size_t smem = (size_t)(SD_TY + 2 * dil) * (SD_TX + 2 * dil) * (CIN + 4) * sizeof(float);
+    auto kern = small_dense3x3_kernel<CIN, COUT>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        configured[dev & 63] = true;
+    }
+    kern<<<tiles_x * tiles_y * frames, SD_TX * SD_TY, smem, s>>>(in, out, *reinterpret_cast<const SmallDenseWeights<CIN, COUT>*>(host_w),
+                                                                dil, relu, tiles_x, tiles_y);
+}
+
+// host_w: 9*CIN*COUT weights [ky][kx][ci][co] followed by COUT biases, in HOST memory; dil <= 8
+void launch_small_dense(const TView& in, const TView& out, const float* host_w, int dil, int relu, int frames,
+                        cudaStream_t s) {
+    if (in.C == 8 && out.C == 16) launch_sd_t<8, 16>(in, out, host_w, dil, relu, frames, s);
+    else if (in.C == 8 && out.C == 12) launch_sd_t<8, 12>(in, out, host_w, dil, relu, frames, s);
+    else if (in.C == 12 && out.C == 16) launch_sd_t<12, 16>(in, out, host_w, dil, relu, frames, s);
+    else if (in.C == 16 && out.C == 16) launch_sd_t<16, 16>(in, out, host_w, dil, relu, frames, s);
 }
 
 // ---------------------------------------------------------------------------------------------
