@@ -146,43 +146,73 @@ void launch_stem(const U8View& in, const float* lut, const TView& out, const flo
 // K4 depthwise 3x3, pad 1, stride 1|2: one thread = one output pixel x 4 channels (float4), channel
 // quads fastest so a warp reads/writes contiguous NHWC bytes; the 3x3 neighbourhood re-reads hit L1.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-depthwise3x3_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int stride,
-                    int relu, long long total) {
+// thread = 4 channels x one column x a strip of R vertically adjacent outputs: the 9 weights (per channel, so
+// they cannot be warp-uniform constants) are loaded once, all (R-1)*S+3 input rows are fetched up front
+// (independent 16-byte loads in flight) and reused across the strip, halving the loads per output.
+template <int S, int R>
+__global__ void __launch_bounds__(128)
+depthwise3x3_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int relu,
+                    int strips, long long total) {
+    constexpr int NR = (R - 1) * S + 3;
     const int C4 = out.C >> 2;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % C4) * 4;
-        long long pix = idx / C4;
-        const int x = (int)(pix % out.W);
-        pix /= out.W;
-        const int y = (int)(pix % out.H);
-        const int n = (int)(pix / out.H);
-        float4 acc = ldg4(b + c);
-        const float* ip = in.p + (size_t)n * in.frame_stride + c;
+        long long t = idx / C4;
+        const int x = (int)(t % out.W);
+        t /= out.W;
+        const int ys = (int)(t % strips);
+        const int n = (int)(t / strips);
+        const int oy0 = ys * R;
+        const int iy0 = oy0 * S - 1, ix0 = x * S - 1;
+        float4 wv[9];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = y * stride - 1 + ky;
-            if (iy < 0 || iy >= in.H) continue;
+        for (int k = 0; k < 9; ++k) wv[k] = ldg4(w + k * out.C + c);
+        const float4 bias = ldg4(b + c);
+        const float* ip = in.p + (size_t)n * in.frame_stride + c;
+        float4 v[NR][3];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int iy = iy0 + r;
+            const bool rok = iy >= 0 && iy < in.H;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int ix = x * stride - 1 + kx;
-                if (ix < 0 || ix >= in.W) continue;
-                const float4 v = ld4(ip + ((size_t)iy * in.W + ix) * in.pix_stride);
-                const float4 ww = ldg4(w + (ky * 3 + kx) * out.C + c);
-                acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
-                acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+                const int ix = ix0 + kx;
+                v[r][kx] = (rok && ix >= 0 && ix < in.W) ? ld4(ip + ((size_t)iy * in.W + ix) * in.pix_stride)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-        st4(out.p + (size_t)n * out.frame_stride + ((size_t)y * out.W + x) * out.pix_stride + c, acc);
+#pragma unroll
+        for (int o = 0; o < R; ++o) {
+            const int oy = oy0 + o;
+            if (oy >= out.H) break;
+            float4 acc = bias;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 a = v[o * S + ky][kx];
+                    const float4 ww = wv[ky * 3 + kx];
+                    acc.x = fmaf(a.x, ww.x, acc.x); acc.y = fmaf(a.y, ww.y, acc.y);
+                    acc.z = fmaf(a.z, ww.z, acc.z); acc.w = fmaf(a.w, ww.w, acc.w);
+                }
+            if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+            st4(out.p + (size_t)n * out.frame_stride + ((size_t)oy * out.W + x) * out.pix_stride + c, acc);
+        }
     }
 }
 
 void launch_depthwise(const TView& in, const TView& out, const float* w_tc, const float* b, int stride, int relu,
                       int frames, cudaStream_t s) {
-    long long total = (long long)frames * out.H * out.W * (out.C / 4);
-    depthwise3x3_kernel<<<grid_for(total, 256, 32), 256, 0, s>>>(in, out, w_tc, b, stride, relu, total);
+    if (stride == 1) {
+        const int strips = (out.H + 3) / 4;
+        const long long total = (long long)frames * strips * out.W * (out.C / 4);
+        depthwise3x3_kernel<1, 4><<<grid_for(total, 128, 64), 128, 0, s>>>(in, out, w_tc, b, relu, strips, total);
+    } else {
+        const int strips = (out.H + 1) / 2;
+        const long long total = (long long)frames * strips * out.W * (out.C / 4);
+        depthwise3x3_kernel<2, 2><<<grid_for(total, 128, 64), 128, 0, s>>>(in, out, w_tc, b, relu, strips, total);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
