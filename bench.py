@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-iters", type=int, default=300)
+    ap.add_argument("--in-flight", type=int, default=3,
+                    help="host threads calling uf_infer_batch concurrently on the one handle in the e2e leg (a stream "
+                         "batcher keeps several batches in flight so the copies of one overlap the kernels of another)")
     return ap.parse_args()
 
 
@@ -247,7 +250,7 @@ def main():
     path, w, h = make_model_file(tmp.name, args)
     B = args.batch
     model = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, size=(w, h), device=local,
-                                  max_batch=B, chunk=args.chunk, slots=args.slots)
+                                  max_batch=B, chunk=args.chunk, slots=args.slots, lanes=args.in_flight)
     info = model.info
     frames = synth_frames(B, seed=rank)             # stream shard of this rank (236 MB > 126 MB L2)
     d_frames = torch.from_numpy(frames).cuda()      # device-resident copy for `value`
@@ -261,9 +264,35 @@ def main():
     def step_host():
         return model.run_batch_ptr(pinned.ptr, SRC_W, SRC_H, B, cap=cap)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, threads=1):
         for _ in range(warmup):
             out = fn()
+        if threads > 1:  # the same K steps, issued by `threads` host threads on the one handle
+            import threading
+            share = [steps // threads + (1 if i < steps % threads else 0) for i in range(threads)]
+            last = [None] * threads
+
+            def worker(i):
+                for _ in range(share[i]):
+                    last[i] = fn()
+            inner = fn
+
+            def run_all():
+                ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads) if share[i]]
+                [t.start() for t in ts]
+                [t.join() for t in ts]
+                return last[0]
+            for _ in range(2):
+                run_all()  # warm every lane (CUDA graphs are captured on the second visit of a stage shape)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            out = run_all()
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            return max_over_ranks(e0.elapsed_time(e1) / 1e3), max_over_ranks(wall), out
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # every step returns only after its streams have drained (results are on the host), so events
@@ -283,7 +312,8 @@ def main():
     t_dev, wall_dev, out_dev = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop()
     launches = (model.launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))
-    t_e2e, wall_e2e, out_e2e = timed(step_host, args.steps, max(args.warmup, 3))
+    t_e2e_sync, wall_e2e_sync, out_e2e = timed(step_host, args.steps, max(args.warmup, 3))
+    t_e2e, wall_e2e, _ = timed(step_host, args.steps, max(args.warmup, 3), threads=max(1, args.in_flight))
     dets, counts = out_dev
     assert counts == out_e2e[1], "device-resident and host-fed runs disagree"
 
@@ -359,7 +389,9 @@ def main():
                            "macs_per_frame": int(info.macs_per_frame)},
                 "e2e": {"value": n_frames * args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": n_frames * SRC_W * SRC_H * 3,
                         "d2h_bytes_per_step": n_frames * (4 + 128 * 20), "ms_per_step": t_e2e / args.steps * 1e3,
-                        "api": "uf_infer_batch (C ABI) from pinned host frames"},
+                        "api": "uf_infer_batch (C ABI) from pinned host frames, %d calls in flight per GPU (host threads on one "
+                               "handle, as a stream batcher would)" % max(1, args.in_flight),
+                        "one_call_at_a_time": {"value": n_frames * args.steps / t_e2e_sync, "ms_per_step": t_e2e_sync / args.steps * 1e3}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "latency_batch1_ms": {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)], "iters": len(lat)},
                 "wall_check": {"value_wall_s": wall_dev, "value_event_s": t_dev, "e2e_wall_s": wall_e2e}}

@@ -10,7 +10,11 @@
  * never aborts the process; uf_last_error() returns a thread-local message for
  * the last failing call on this thread. All entry points are thread-safe on one
  * handle (`UltrafaceModel` must be Send + Sync: it is borrowed across .await in
- * inferer.rs:29-50); calls on one handle are serialised internally.
+ * inferer.rs:29-50). A handle owns `lanes` independent pipelines: up to that many
+ * calls from different host threads run concurrently (the kernels of one batch
+ * overlap the host-to-device copies of the next), further callers wait their turn.
+ * The parity hooks (uf_raw_outputs, uf_tensor_read) refer to the last batch of
+ * lane 0, which is the lane a single-threaded caller always gets.
  * No torch types, plain pointers and sizes only.
  */
 #ifndef ULTRAFACE_B200_H
@@ -73,6 +77,7 @@ typedef struct uf_config {
     uint32_t slots;          /* pipeline depth (streams); 0 = auto */
     uint32_t resize_round_intermediate; /* 0 = image 0.24.x (f32 between passes); 1 = pre-0.24 */
     uint32_t flags;          /* UF_FLAG_* */
+    uint32_t lanes;          /* concurrent calls served in parallel on one handle; 0 = auto (2) */
 } uf_config;
 
 #define UF_FLAG_FORCE_GENERIC 1u /* debug: run every conv through the generic direct kernel */

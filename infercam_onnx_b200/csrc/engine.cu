@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -111,6 +112,7 @@ struct Slot {
     // pending work description
     bool pending = false;
     uint32_t first = 0, n = 0;
+    uint64_t batch_id = 0;  // which uf_infer_batch* call the slot's activations belong to
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;  // profiling pairs
     std::vector<int> ev_stat;                             // stat index per pair
     size_t ev_used = 0;
@@ -120,6 +122,17 @@ struct Slot {
     // CUDA graphs of the kernel chain (conv stack + tail + post + D2H), keyed by (first frame, frames, stem inside?)
     std::map<std::tuple<uint32_t, int, int>, cudaGraphExec_t> graphs;
     std::map<std::tuple<uint32_t, int, int>, int> graph_seen, graph_nodes;
+};
+
+// One lane = everything a call mutates: its pipeline slots and the raw outputs of its last batch. Calls from
+// different host threads on one handle run on different lanes (weights, plan, tap tables are shared), so the
+// kernels of one batch overlap the H2D copies of the next: that is how a stream batcher keeps PCIe busy.
+struct Lane {
+    std::mutex mu;
+    std::vector<Slot> slots;
+    float *d_scores = nullptr, *d_boxes = nullptr;  // raw outputs of the lane's last batch [max_batch][K][2|4]
+    uint32_t last_n = 0;
+    uint64_t batch_id = 0;
 };
 
 struct KernelStat {
@@ -134,7 +147,7 @@ struct KernelStat {
 using namespace uf;
 
 struct uf_model {
-    std::mutex mu;
+    std::mutex aux_mu;  // tap-table cache, profile statistics, hook scratch
     uf_config cfg{};
     std::string onnx_path;
     Plan plan;
@@ -146,11 +159,10 @@ struct uf_model {
     uint64_t weight_bytes = 0, workspace_bytes = 0;
     float* d_lut = nullptr;
     float* d_priors = nullptr;
-    float *d_scores = nullptr, *d_boxes = nullptr;  // raw outputs of the last batch [max_batch][K][2|4]
-    std::vector<Slot> slots;
+    std::vector<std::unique_ptr<Lane>> lanes;
+    std::atomic<uint32_t> lane_rr{0};
     std::map<std::pair<int, int>, TapsEntry> taps;
-    uint32_t last_n = 0, last_step = 1;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     bool profiling = false;
     std::vector<KernelStat> stats;
     std::map<std::string, int> stat_index;
@@ -199,6 +211,7 @@ struct ProfScope {
         : m(mm), s(ss), on(mm.profiling) {
         m.launches++;
         if (!on) return;
+        std::lock_guard<std::mutex> lk(m.aux_mu);
         int id = stat_id(m, name);
         m.stats[id].launches++;
         m.stats[id].alg_bytes += alg;
@@ -222,6 +235,7 @@ struct ProfScope {
 };
 
 static void collect_profile(uf_model& m, Slot& s) {
+    std::lock_guard<std::mutex> lk(m.aux_mu);
     for (size_t i = 0; i < s.ev_used; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s.ev[i].first, s.ev[i].second) == cudaSuccess) m.stats[s.ev_stat[i]].ms += ms;
@@ -446,13 +460,13 @@ static void build_lut(uf_model& m) {
     CK(cudaMemcpy(m.d_lut, lut.data(), 768 * sizeof(float), cudaMemcpyHostToDevice));
 }
 
-static void alloc_slots(uf_model& m) {
+static void alloc_lane(uf_model& m, Lane& ln) {
     const int K = m.K;
     const size_t H = m.plan.net_h, W = m.plan.net_w;
     const size_t sort_cap = post_sort_scratch_elems(K);
-    m.slots.resize(m.nslots);
+    ln.slots.resize(m.nslots);
     uint64_t ws = 0;
-    for (auto& s : m.slots) {
+    for (auto& s : ln.slots) {
         CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         s.d_in_cap = (size_t)m.chunk * 640 * 480 * 3;
@@ -472,7 +486,7 @@ static void alloc_slots(uf_model& m) {
               (size_t)m.chunk * sort_cap * 8;
         CK(cudaStreamSynchronize(s.stream));
     }
-    for (auto& s : m.slots) {
+    for (auto& s : ln.slots) {
         s.tm_a.resize(m.steps.size());
         s.tm_o.resize(m.steps.size());
         s.tm_o_ok.assign(m.steps.size(), 0);
@@ -501,13 +515,14 @@ static void alloc_slots(uf_model& m) {
                                                       (uint64_t)o.pix_stride * 4) ? 1 : 0;
         }
     }
-    CK(cudaMalloc(&m.d_scores, (size_t)m.cfg.max_batch * K * 2 * sizeof(float)));
-    CK(cudaMalloc(&m.d_boxes, (size_t)m.cfg.max_batch * K * 4 * sizeof(float)));
+    CK(cudaMalloc(&ln.d_scores, (size_t)m.cfg.max_batch * K * 2 * sizeof(float)));
+    CK(cudaMalloc(&ln.d_boxes, (size_t)m.cfg.max_batch * K * 4 * sizeof(float)));
     ws += (size_t)m.cfg.max_batch * K * 6 * sizeof(float);
-    m.workspace_bytes = ws;
+    m.workspace_bytes += ws;
 }
 
 static TapsEntry& get_taps(uf_model& m, int sw, int sh) {
+    std::lock_guard<std::mutex> lk(m.aux_mu);  // std::map nodes are stable: the reference outlives the lock
     auto key = std::make_pair(sw, sh);
     auto it = m.taps.find(key);
     if (it != m.taps.end()) return it->second;
@@ -625,7 +640,7 @@ static void harvest(uf_model& m, Slot& s, uf_det* out, uint32_t cap, uint32_t* n
 }
 
 // tail + post + D2H for `frames` frames whose conv outputs sit in slot s; global frame offset `first`
-static void run_tail_post(uf_model& m, Slot& s, uint32_t first, int frames) {
+static void run_tail_post(uf_model& m, Lane& ln, Slot& s, uint32_t first, int frames) {
     const int K = m.K;
     TView conf, loc;
     {
@@ -634,8 +649,8 @@ static void run_tail_post(uf_model& m, Slot& s, uint32_t first, int frames) {
         conf.p = s.d_arena + cb.arena_off * (int64_t)m.chunk; conf.frame_stride = align4(cb.frame_floats);
         loc.p = s.d_arena + lb.arena_off * (int64_t)m.chunk; loc.frame_stride = align4(lb.frame_floats);
     }
-    float* scores = m.d_scores + (size_t)first * K * 2;
-    float* boxes = m.d_boxes + (size_t)first * K * 4;
+    float* scores = ln.d_scores + (size_t)first * K * 2;
+    float* boxes = ln.d_boxes + (size_t)first * K * 4;
     {
         ProfScope ps(m, s, "tail_softmax_decode", (uint64_t)frames * K * 6 * 4 * 2, (uint64_t)frames * K * 6 * 4 * 2, 0);
         launch_tail(conf.p, loc.p, conf.frame_stride, loc.frame_stride, m.d_priors, K, m.plan.center_variance,
@@ -654,12 +669,12 @@ static void run_tail_post(uf_model& m, Slot& s, uint32_t first, int frames) {
 // conv stack + tail + post + D2H for one chunk. The chain is ~45 short kernels; replaying it as a CUDA graph
 // removes the per-launch CPU cost and most of the inter-kernel gaps (this is what bounds batch-1 latency).
 // The first step is kept outside the graph when it reads the caller's device buffer (pointer changes per call).
-static void run_body(uf_model& m, Slot& s, const U8View& input, uint32_t first, int frames) {
+static void run_body(uf_model& m, Lane& ln, Slot& s, const U8View& input, uint32_t first, int frames) {
     const bool use_graph = !m.profiling && !(m.cfg.flags & UF_FLAG_NO_GRAPH);
     const bool stem_inside = input.p == s.d_resized;
     if (!use_graph) {
         run_cnn(m, s, input, frames);
-        run_tail_post(m, s, first, frames);
+        run_tail_post(m, ln, s, first, frames);
         return;
     }
     const auto key = std::make_tuple(first, frames, stem_inside ? 1 : 0);
@@ -668,16 +683,16 @@ static void run_body(uf_model& m, Slot& s, const U8View& input, uint32_t first, 
         // first sighting: run eagerly (kernels set their function attributes on first use); capture on the second
         if (s.graph_seen[key]++ == 0) {
             run_cnn(m, s, input, frames);
-            run_tail_post(m, s, first, frames);
+            run_tail_post(m, ln, s, first, frames);
             return;
         }
         if (!stem_inside) run_cnn(m, s, input, frames, 0, 1);
-        const uint64_t launches_before = m.launches;
+        const uint64_t launches_before = m.launches.load();
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
         try {
             run_cnn(m, s, input, frames, stem_inside ? 0 : 1);
-            run_tail_post(m, s, first, frames);
+            run_tail_post(m, ln, s, first, frames);
         } catch (...) {
             cudaStreamEndCapture(s.stream, &g);
             if (g) cudaGraphDestroy(g);
@@ -689,8 +704,9 @@ static void run_body(uf_model& m, Slot& s, const U8View& input, uint32_t first, 
         cudaGraphDestroy(g);
         if (e != cudaSuccess) throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
         s.graphs[key] = ge;
-        s.graph_nodes[key] = (int)(m.launches - launches_before);
-        m.launches = launches_before;  // capture recorded the kernels, it did not launch them
+        const uint64_t recorded = m.launches.load() - launches_before;  // (other lanes may add real launches meanwhile:
+        s.graph_nodes[key] = (int)recorded;                             //  the count is only used for the launch statistic)
+        m.launches -= recorded;  // capture recorded the kernels, it did not launch them
         it = s.graphs.find(key);
     } else if (!stem_inside) {
         run_cnn(m, s, input, frames, 0, 1);
@@ -705,7 +721,7 @@ struct FrameSrc {
 };
 
 // One chunk of host frames on slot s.
-static void run_chunk_host(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t first, uint32_t n) {
+static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, uint32_t first, uint32_t n) {
     const int W = m.plan.net_w, H = m.plan.net_h;
     const size_t out_frame = (size_t)W * H * 3;
     // total staging bytes for frames that need a resize
@@ -747,12 +763,12 @@ static void run_chunk_host(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t fi
     }
     U8View input{s.d_resized, (long long)out_frame, H, W};
     static const bool copy_only = getenv("UF_DEBUG_COPY_ONLY") != nullptr;  // experiment: H2D pipeline alone
-    if (!copy_only) run_body(m, s, input, first, (int)n);
+    if (!copy_only) run_body(m, ln, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
 }
 
 // One chunk of device-resident frames (identical size, contiguous) on slot s.
-static void run_chunk_device(uf_model& m, Slot& s, const uint8_t* d_rgb, uint32_t w, uint32_t h, uint32_t first, uint32_t n) {
+static void run_chunk_device(uf_model& m, Lane& ln, Slot& s, const uint8_t* d_rgb, uint32_t w, uint32_t h, uint32_t first, uint32_t n) {
     const int W = m.plan.net_w, H = m.plan.net_h;
     const size_t out_frame = (size_t)W * H * 3, fb = (size_t)w * h * 3;
     U8View input{s.d_resized, (long long)out_frame, H, W};
@@ -765,25 +781,54 @@ static void run_chunk_device(uf_model& m, Slot& s, const uint8_t* d_rgb, uint32_
         launch_resize(d_rgb, (long long)fb, w, h, s.d_resized, (long long)out_frame, W, H, (int)n, t.dev,
                       m.cfg.resize_round_intermediate, s.stream);
     }
-    run_body(m, s, input, first, (int)n);
+    run_body(m, ln, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
 }
 
+// `taper`: shrink the last pipeline stages (host input). The copy of stage i+1 hides behind the kernels of stage
+// i, but nothing hides the kernels of the LAST stage, so the tail of the batch is cut into smaller stages.
 template <typename F>
-static void run_pipeline(uf_model& m, uint32_t n, uint32_t step, uf_det* out, uint32_t cap, uint32_t* n_out, F&& submit) {
+static void run_pipeline(uf_model& m, Lane& ln, uint32_t n, uint32_t step, bool taper, uf_det* out, uint32_t cap,
+                         uint32_t* n_out, F&& submit) {
     if (n > m.cfg.max_batch) throw ArgError(UF_ERR_CAPACITY, "batch of " + std::to_string(n) + " exceeds max_batch " + std::to_string(m.cfg.max_batch));
     CK(cudaSetDevice(m.cfg.device));
     const uint32_t nslots = m.profiling ? 1 : m.nslots;  // profiling: one stream, so event pairs time kernels alone
     uint32_t c = 0;
-    for (uint32_t first = 0; first < n; first += step, ++c) {
-        Slot& s = m.slots[c % nslots];
+    ++ln.batch_id;
+    for (uint32_t first = 0; first < n; ++c) {
+        uint32_t cnt = std::min(step, n - first);
+        if (taper && !m.profiling) {
+            const uint32_t rem = n - first;
+            if (rem <= step && rem > 16) cnt = std::max<uint32_t>(16, (rem / 2 + 7) / 8 * 8);
+        }
+        Slot& s = ln.slots[c % nslots];
         harvest(m, s, out, cap, n_out);
-        submit(s, first, std::min(step, n - first));
+        submit(s, first, cnt);
+        s.batch_id = ln.batch_id;
+        first += cnt;
     }
-    for (uint32_t k = 0; k < nslots; ++k) harvest(m, m.slots[(c + k) % nslots], out, cap, n_out);
-    m.last_n = n;
-    m.last_step = step;
+    for (uint32_t k = 0; k < nslots; ++k) harvest(m, ln.slots[(c + k) % nslots], out, cap, n_out);
+    ln.last_n = n;
 }
+
+// Picks a lane for a call: the first one that is free, else waits for one round-robin. Profiling and the
+// parity hooks always use lane 0 (a single-threaded caller therefore always sees its own last batch there).
+struct LaneLock {
+    Lane* lane = nullptr;
+    std::unique_lock<std::mutex> lk;
+    LaneLock(uf_model& m, bool force0) {
+        if (!force0 && !m.profiling) {
+            for (auto& l : m.lanes) {
+                std::unique_lock<std::mutex> t(l->mu, std::try_to_lock);
+                if (t.owns_lock()) { lane = l.get(); lk = std::move(t); return; }
+            }
+            lane = m.lanes[m.lane_rr++ % m.lanes.size()].get();
+        } else {
+            lane = m.lanes[0].get();
+        }
+        lk = std::unique_lock<std::mutex>(lane->mu);
+    }
+};
 
 static void* hook_scratch(uf_model& m, size_t bytes) {
     if (bytes > m.d_hook_cap) {
@@ -823,7 +868,7 @@ static uf_model* load_model(const uf_config& cfg_in) {
     if (chunk == 0) chunk = (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 128 : 32;
     chunk = std::min(chunk, cfg.max_batch);
     m->chunk = chunk;
-    m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 32 : 8));
+    m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 64 : 16));
     if (const char* e = getenv("UF_HOST_CHUNK")) m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint32_t)atoi(e)));
     uint32_t nslots = cfg.slots ? cfg.slots : 4;
     const uint32_t nchunks = (cfg.max_batch + m->host_chunk - 1) / m->host_chunk;
@@ -838,7 +883,12 @@ static uf_model* load_model(const uf_config& cfg_in) {
     CK(cudaMemcpy(m->d_priors, m->plan.priors.data(), (size_t)m->K * 4 * sizeof(float), cudaMemcpyHostToDevice));
     cudaError_t pe = (cudaError_t)post_configure();
     if (pe != cudaSuccess) throw CudaError(std::string("post_configure: ") + cudaGetErrorString(pe));
-    alloc_slots(*m);
+    uint32_t nlanes = cfg.lanes ? cfg.lanes : 2;
+    nlanes = std::max<uint32_t>(1, std::min<uint32_t>(nlanes, 8));
+    for (uint32_t i = 0; i < nlanes; ++i) {
+        m->lanes.emplace_back(new Lane());
+        alloc_lane(*m, *m->lanes.back());
+    }
     return m.release();
 }
 
@@ -846,7 +896,8 @@ static uf_model* load_model(const uf_config& cfg_in) {
 
 uf_model::~uf_model() {
     cudaSetDevice(cfg.device);
-    for (auto& s : slots) {
+    for (auto& lane : lanes)
+    for (auto& s : lane->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto& g : s.graphs) cudaGraphExecDestroy(g.second);
@@ -861,7 +912,8 @@ uf_model::~uf_model() {
         cudaFree(t.d_vleft); cudaFree(t.d_vn); cudaFree(t.d_vw); cudaFree(t.d_hleft); cudaFree(t.d_hn); cudaFree(t.d_hw);
     }
     for (auto& t : tc_weights) { cudaFree(t.d_hi); cudaFree(t.d_lo); }
-    cudaFree(d_weights); cudaFree(d_lut); cudaFree(d_priors); cudaFree(d_scores); cudaFree(d_boxes); cudaFree(d_hook);
+    for (auto& lane : lanes) { cudaFree(lane->d_scores); cudaFree(lane->d_boxes); }
+    cudaFree(d_weights); cudaFree(d_lut); cudaFree(d_priors); cudaFree(d_hook);
 }
 
 // ---- C ABI -----------------------------------------------------------------------------------
@@ -934,10 +986,11 @@ int uf_infer_batch(uf_model* m, const uint8_t* const* rgb, const uint32_t* w, co
             REQUIRE(rgb[i] && w[i] > 0 && h[i] > 0 && w[i] <= 16384 && h[i] <= 16384, "bad frame " + std::to_string(i));
             fr[i] = FrameSrc{rgb[i], w[i], h[i]};
         }
-        std::lock_guard<std::mutex> lk(m->mu);
+        LaneLock ll(*m, false);
+        Lane& ln = *ll.lane;
         // host frames: small pipeline stages so the H2D copy of stage i+1 hides behind the kernels of stage i
-        run_pipeline(*m, n, m->host_chunk, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
-            run_chunk_host(*m, s, fr.data() + first, first, cnt);
+        run_pipeline(*m, ln, n, m->host_chunk, true, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
+            run_chunk_host(*m, ln, s, fr.data() + first, first, cnt);
         });
     });
 }
@@ -952,10 +1005,11 @@ int uf_infer_batch_device(uf_model* m, const uint8_t* d_rgb, uint32_t w, uint32_
     return guarded([&] {
         REQUIRE(m && (n == 0 || d_rgb) && n_out && w > 0 && h > 0, "bad argument");
         REQUIRE(cap == 0 || out, "out is NULL with cap > 0");
-        std::lock_guard<std::mutex> lk(m->mu);
+        LaneLock ll(*m, false);
+        Lane& ln = *ll.lane;
         const size_t fb = (size_t)w * h * 3;
-        run_pipeline(*m, n, m->chunk, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
-            run_chunk_device(*m, s, d_rgb + (size_t)first * fb, w, h, first, cnt);
+        run_pipeline(*m, ln, n, m->chunk, false, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
+            run_chunk_device(*m, ln, s, d_rgb + (size_t)first * fb, w, h, first, cnt);
         });
     });
 }
@@ -963,16 +1017,17 @@ int uf_infer_batch_device(uf_model* m, const uint8_t* d_rgb, uint32_t w, uint32_
 int uf_raw_outputs(uf_model* m, uint32_t first, uint32_t n, float* scores, float* boxes) {
     return guarded([&] {
         REQUIRE(m, "null model");
-        std::lock_guard<std::mutex> lk(m->mu);
-        REQUIRE((uint64_t)first + n <= m->last_n, "frame range outside the last batch");
+        LaneLock ll(*m, true);
+        Lane& ln = *ll.lane;
+        REQUIRE((uint64_t)first + n <= ln.last_n, "frame range outside the last batch");
         CK(cudaSetDevice(m->cfg.device));
-        if (scores) CK(cudaMemcpy(scores, m->d_scores + (size_t)first * m->K * 2, (size_t)n * m->K * 2 * sizeof(float), cudaMemcpyDeviceToHost));
-        if (boxes) CK(cudaMemcpy(boxes, m->d_boxes + (size_t)first * m->K * 4, (size_t)n * m->K * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (scores) CK(cudaMemcpy(scores, ln.d_scores + (size_t)first * m->K * 2, (size_t)n * m->K * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (boxes) CK(cudaMemcpy(boxes, ln.d_boxes + (size_t)first * m->K * 4, (size_t)n * m->K * 4 * sizeof(float), cudaMemcpyDeviceToHost));
     });
 }
 
-static void preproc_to_slot0(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h) {
-    Slot& s = m->slots[0];
+static void preproc_to_slot0(uf_model* m, Lane& ln, const uint8_t* rgb, uint32_t w, uint32_t h) {
+    Slot& s = ln.slots[0];
     const int W = m->plan.net_w, H = m->plan.net_h;
     const size_t fb = (size_t)w * h * 3;
     if ((int)w == W && (int)h == H) {
@@ -996,10 +1051,11 @@ static void preproc_to_slot0(uf_model* m, const uint8_t* rgb, uint32_t w, uint32
 int uf_preproc_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t* out_u8) {
     return guarded([&] {
         REQUIRE(m && rgb && out_u8 && w > 0 && h > 0, "bad argument");
-        std::lock_guard<std::mutex> lk(m->mu);
+        LaneLock ll(*m, true);
+        Lane& ln = *ll.lane;
         CK(cudaSetDevice(m->cfg.device));
-        preproc_to_slot0(m, rgb, w, h);
-        Slot& s = m->slots[0];
+        preproc_to_slot0(m, ln, rgb, w, h);
+        Slot& s = ln.slots[0];
         CK(cudaMemcpyAsync(out_u8, s.d_resized, (size_t)m->plan.net_w * m->plan.net_h * 3, cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaGetLastError());
@@ -1009,10 +1065,11 @@ int uf_preproc_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint8
 int uf_preproc_f32(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, float* out) {
     return guarded([&] {
         REQUIRE(m && rgb && out && w > 0 && h > 0, "bad argument");
-        std::lock_guard<std::mutex> lk(m->mu);
+        LaneLock ll(*m, true);
+        Lane& ln = *ll.lane;
         CK(cudaSetDevice(m->cfg.device));
-        preproc_to_slot0(m, rgb, w, h);
-        Slot& s = m->slots[0];
+        preproc_to_slot0(m, ln, rgb, w, h);
+        Slot& s = ln.slots[0];
         const size_t nfl = (size_t)3 * m->plan.net_w * m->plan.net_h;
         float* d = (float*)hook_scratch(*m, nfl * sizeof(float));
         m->launches++;
@@ -1031,9 +1088,10 @@ int uf_postproc(uf_model* m, const float* scores, const float* boxes, uint32_t K
         REQUIRE(K <= (1u << 20), "K too large");
         *n_out = 0;
         if (K == 0) return;
-        std::lock_guard<std::mutex> lk(m->mu);
+        LaneLock ll(*m, true);
+        Lane& ln = *ll.lane;
         CK(cudaSetDevice(m->cfg.device));
-        Slot& s = m->slots[0];
+        Slot& s = ln.slots[0];
         const size_t sort_cap = post_sort_scratch_elems((int)K);
         // layout: scores | boxes | sel | dets | idx | count | sort keys
         auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
@@ -1083,16 +1141,19 @@ int uf_tensor_read(uf_model* m, uint32_t i, uint32_t frame, float* out_nchw) {
     return guarded([&] {
         REQUIRE(m && out_nchw && i < m->plan.tensors.size(), "bad argument");
         REQUIRE(m->tensor_readable[i], "tensor is not materialised (graph input, or fused away)");
-        std::lock_guard<std::mutex> lk(m->mu);
-        REQUIRE(frame < m->last_n, "frame outside the last batch");
-        const uint32_t nchunks = (m->last_n + m->last_step - 1) / m->last_step, c = frame / m->last_step;
-        REQUIRE(c + m->nslots >= nchunks, "that chunk's workspace has been reused by a later chunk");
+        LaneLock ll(*m, true);
+        Lane& ln = *ll.lane;
+        REQUIRE(frame < ln.last_n, "frame outside the last batch");
+        Slot* found = nullptr;
+        for (auto& sl : ln.slots)
+            if (sl.batch_id == ln.batch_id && frame >= sl.first && frame < sl.first + sl.n) found = &sl;
+        REQUIRE(found != nullptr, "that frame's workspace has been reused by a later pipeline stage");
         CK(cudaSetDevice(m->cfg.device));
-        Slot& s = m->slots[c % m->nslots];
+        Slot& s = *found;
         TView v = make_view(*m, s, (int)i);
         const size_t nfl = (size_t)v.C * v.H * v.W;
         float* d = (float*)hook_scratch(*m, nfl * sizeof(float));
-        launch_nhwc_to_nchw(v, (int)(frame % m->last_step), d, s.stream);
+        launch_nhwc_to_nchw(v, (int)(frame - s.first), d, s.stream);
         CK(cudaMemcpyAsync(out_nchw, d, nfl * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaGetLastError());
@@ -1114,7 +1175,7 @@ void uf_host_free(void* p) {
 int uf_profile_enable(uf_model* m, int on) {
     return guarded([&] {
         REQUIRE(m, "null model");
-        std::lock_guard<std::mutex> lk(m->mu);
+        LaneLock ll(*m, true);
         m->profiling = on != 0;
     });
 }
@@ -1122,7 +1183,7 @@ int uf_profile_enable(uf_model* m, int on) {
 int uf_profile_reset(uf_model* m) {
     return guarded([&] {
         REQUIRE(m, "null model");
-        std::lock_guard<std::mutex> lk(m->mu);
+        std::lock_guard<std::mutex> lk(m->aux_mu);
         for (auto& s : m->stats) { s.launches = 0; s.ms = 0; s.alg_bytes = 0; s.min_bytes = 0; s.flops = 0; }
     });
 }
@@ -1130,7 +1191,7 @@ int uf_profile_reset(uf_model* m) {
 int uf_profile_read(uf_model* m, uf_kernel_stat* out, uint32_t cap, uint32_t* n_out) {
     return guarded([&] {
         REQUIRE(m && n_out, "null argument");
-        std::lock_guard<std::mutex> lk(m->mu);
+        std::lock_guard<std::mutex> lk(m->aux_mu);
         *n_out = (uint32_t)m->stats.size();
         for (uint32_t i = 0; i < cap && i < m->stats.size(); ++i) {
             memset(&out[i], 0, sizeof(out[i]));
@@ -1147,7 +1208,7 @@ int uf_profile_read(uf_model* m, uf_kernel_stat* out, uint32_t cap, uint32_t* n_
 int uf_launch_count(const uf_model* m, uint64_t* n) {
     return guarded([&] {
         REQUIRE(m && n, "null argument");
-        *n = m->launches;
+        *n = m->launches.load();
     });
 }
 

@@ -1,0 +1,44 @@
+"""Stream -> GPU sharding for the multi-GPU path.
+
+Frames are independent (`run(&self)`, /root/reference/infer_server/src/nn.rs:179) and the reference keys every
+stream by `hashed(name)` (infer_server/src/lib.rs:39-46, router.rs:58), so the path shards by stream with no
+data-path collective: rank r of n owns the streams with `stream_id % n == r`. The only cross-rank traffic in this
+repo is the benchmark's timing barrier / max-reduce (torch.distributed: NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import List, Sequence
+
+
+def stream_id(name: str) -> int:
+    """Stable 64-bit id of a stream name (the reference uses Rust's DefaultHasher, which is not stable across
+    builds; any fixed hash gives the same partitioning property)."""
+    return int.from_bytes(hashlib.blake2b(name.encode(), digest_size=8).digest(), "little")
+
+
+def owner(stream: int, world_size: int) -> int:
+    return stream % world_size
+
+
+def shard_streams(n_streams: int, rank: int, world_size: int) -> List[int]:
+    """Stream ids owned by `rank` (disjoint over ranks, union = range(n_streams), sizes differ by at most 1)."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    return list(range(rank, n_streams, world_size))
+
+
+def batches(streams: Sequence[int], batch: int) -> List[List[int]]:
+    """One step takes one frame from each stream of a batch; a rank with S streams needs ceil(S/batch) steps."""
+    return [list(streams[i:i + batch]) for i in range(0, len(streams), batch)]
+
+
+def aggregate_throughput(dist, frames_this_rank: int, seconds_this_rank: float) -> float:
+    """Whole-job frames/s = total frames of all ranks / max time over ranks (bench.py contract)."""
+    import torch
+    t = torch.tensor([float(frames_this_rank), 0.0], dtype=torch.float64)
+    m = torch.tensor([float(seconds_this_rank)], dtype=torch.float64)
+    if dist is not None and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    return float(t[0].item() / m[0].item())

@@ -296,6 +296,31 @@ def test_device_resident_input_equals_host_input(make_onnx):
         m.close()
 
 
+def test_concurrent_calls_on_one_handle(make_onnx):
+    """`UltrafaceModel` is Send + Sync (inferer.rs:29-50): calls from several host threads on one handle run on
+    separate lanes and must give exactly the single-threaded results."""
+    import threading
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=48, lanes=3)
+    try:
+        sets = [_noise(48, seed=40 + i) for i in range(3)]
+        expect = [m.run_batch(list(fs), cap=128) for fs in sets]
+        got = [None] * 3
+
+        def work(i):
+            for _ in range(4):
+                got[i] = m.run_batch(list(sets[i]), cap=128)
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        for i in range(3):
+            assert got[i][1] == expect[i][1]
+            for a, b in zip(got[i][0], expect[i][0]):
+                np.testing.assert_array_equal(a, b)
+    finally:
+        m.close()
+
+
 def test_full_size_batch_properties(make_onnx):
     """BASELINE config sizes (batch 256, 640x480): size-independent properties instead of the oracle —
     duplicated frames give identical results wherever they sit in the batch, detections are sorted,
