@@ -43,6 +43,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a wrong descriptor must abort the kernel (cudaErrorLaunchFailure), never hang the GPU.
+#ifdef UF_TC_TIMING
+__device__ long long g_tc_timing[16];  // per role: [0] total cycles, [1] cycles spent waiting (block 0, one thread per role)
+#define TC_T0() long long t_role0 = clock64(), t_wait = 0
+#define TC_WAIT(stmt) do { long long t_w = clock64(); stmt; t_wait += clock64() - t_w; } while (0)
+#define TC_DONE(role) do { if (blockIdx.x == 0) { g_tc_timing[(role) * 2] = clock64() - t_role0; g_tc_timing[(role) * 2 + 1] = t_wait; } } while (0)
+#else
+#define TC_T0() do {} while (0)
+#define TC_WAIT(stmt) stmt
+#define TC_DONE(role) do {} while (0)
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     const long long t0 = clock64();
@@ -159,12 +170,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&conv[s], 128);
+            mbar_init(&conv[s], 4);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 128);
+            mbar_init(&acc_empty[a], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -181,12 +192,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     if (warp == 8) {
         // ===== TMA producer =====
         if (lane == 0) {
+            TC_T0();
             int s = 0;
             uint32_t ph = 0;
             const uint32_t tx_bytes = (uint32_t)(TC_A_BYTES + 2 * b_bytes);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&empty[s], ph ^ 1);
+                    TC_WAIT(mbar_wait(&empty[s], ph ^ 1));
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full[s], tx_bytes);
                     tma_load_2d(st, &tm_a, &full[s], kb * TC_BK, tile * TC_BM);
@@ -195,25 +207,27 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
+            TC_DONE(0);
         }
     } else if (warp == 9) {
         // ===== MMA issuer =====
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_umma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            TC_T0();
             int s = 0;
             uint32_t ph = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int a = it & 1;
                 const uint32_t aph = (uint32_t)((it >> 1) & 1);
-                mbar_wait(&acc_empty[a], aph ^ 1);
+                TC_WAIT(mbar_wait(&acc_empty[a], aph ^ 1));
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(a * p.n_umma);
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[s], ph);
-                    mbar_wait(&conv[s], ph);
+                    TC_WAIT(mbar_wait(&full[s], ph));
+                    TC_WAIT(mbar_wait(&conv[s], ph));
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, w_hi = st + 2 * TC_A_BYTES, w_lo = w_hi + b_bytes;
@@ -232,14 +246,16 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 }
                 umma_commit(&acc_full[a]);
             }
+            TC_DONE(1);
         }
     } else if (warp < 4) {
         // ===== converters: fp32 -> (tf32 hi, tf32 lo), element-wise so the swizzled layout is preserved =====
+        TC_T0();
         int s = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(&full[s], ph);
+                TC_WAIT(mbar_wait(&full[s], ph));
                 float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + TC_A_BYTES);
 #pragma unroll
@@ -251,14 +267,17 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
                     h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
                     h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-                    hi[i] = h;
+                    // hi is not written back: kind::tf32 ignores the low 13 mantissa bits of its operands, i.e. the
+                    // raw fp32 tile already *is* a_hi (checked by the 1e-4 layer-parity tests)
                     lo[i] = l;
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-                mbar_arrive(&conv[s]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv[s]);
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
+        if (threadIdx.x == 0) TC_DONE(2);
     } else {
         // ===== epilogue warps 4..7: TMEM -> registers -> per-warp smem transpose -> coalesced global =====
         // A TMEM lane is an output row, so a lane owns a whole row; writing rows straight from the
@@ -270,11 +289,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             // fast path: +bias (constant bank) / ReLU in registers -> 128B-swizzled 32x32 tile per warp -> TMA store
             // (rows past M and columns past N are clipped by the tensor map): no address arithmetic at all.
             uint8_t* st = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) + q * 4096;
+            TC_T0();
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
                 const int a = it & 1;
                 const uint32_t aph = (uint32_t)((it >> 1) & 1);
-                mbar_wait(&acc_full[a], aph);
+                TC_WAIT(mbar_wait(&acc_full[a], aph));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_umma);
                 for (int c0 = 0; c0 < p.n_umma; c0 += 32) {
@@ -304,9 +324,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[a]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[a]);
             }
             if (lane == 0) bulk_wait0();
+            if (threadIdx.x == 128) TC_DONE(3);
         } else {
                 float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15)) + q * (32 * 36);
         const int HW = p.out.H * p.out.W;
@@ -369,7 +391,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[a]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
         }
         }
     }
@@ -610,6 +633,10 @@ void launch_fused_dwpw_tma(const TmaMap& tm_in, const TmaMap& tm_out, const TVie
     else if (C == 32 && N == 64 && stride == 1) UF_T(32, 64, 1, 32);
 #undef UF_T
 }
+
+#ifdef UF_TC_TIMING
+void tc_timing_read(long long* out16) { cudaMemcpyFromSymbol(out16, g_tc_timing, sizeof(long long) * 16); }
+#endif
 
 bool pointwise_tc_supported(int K, int N) { return K >= 32 && K % 4 == 0 && N >= 1 && N <= 256; }
 
