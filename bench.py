@@ -393,7 +393,7 @@ def main():
                                "handle, as a stream batcher would)" % max(1, args.in_flight),
                         "one_call_at_a_time": {"value": n_frames * args.steps / t_e2e_sync, "ms_per_step": t_e2e_sync / args.steps * 1e3}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "latency_batch1_ms": {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)], "iters": len(lat)},
+                "latency_batch1_ms": ({"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)], "iters": len(lat)} if lat else None),
                 "wall_check": {"value_wall_s": wall_dev, "value_event_s": t_dev, "e2e_wall_s": wall_e2e}}
         print(json.dumps(line), flush=True)
     model.close()

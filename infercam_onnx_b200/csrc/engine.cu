@@ -119,6 +119,8 @@ struct Slot {
     std::vector<TmaMap> tm_a;                             // per step: activation tensor map (PointwiseTC / FusedTma input)
     std::vector<TmaMap> tm_o;                             // per step: output tensor map (FusedTma, PointwiseTC)
     std::vector<uint8_t> tm_o_ok;                         // per step: tm_o is valid
+    std::vector<TmaMap> tm_r;                             // per step: residual tensor map (PointwiseTC with Add)
+    std::vector<uint8_t> tm_r_ok;
     // CUDA graphs of the kernel chain (conv stack + tail + post + D2H), keyed by (first frame, frames, stem inside?)
     std::map<std::tuple<uint32_t, int, int>, cudaGraphExec_t> graphs;
     std::map<std::tuple<uint32_t, int, int>, int> graph_seen, graph_nodes;
@@ -490,6 +492,8 @@ static void alloc_lane(uf_model& m, Lane& ln) {
         s.tm_a.resize(m.steps.size());
         s.tm_o.resize(m.steps.size());
         s.tm_o_ok.assign(m.steps.size(), 0);
+        s.tm_r.resize(m.steps.size());
+        s.tm_r_ok.assign(m.steps.size(), 0);
         for (size_t i = 0; i < m.steps.size(); ++i) {
             if (m.steps[i].impl == Impl::FusedTma) {
                 const Op& dw = m.plan.ops[m.steps[i].op];
@@ -509,10 +513,19 @@ static void alloc_lane(uf_model& m, Lane& ln) {
             // TMA-store epilogue when the output rows are 16-byte aligned and frames are densely packed
             TView o = make_view(m, s, op.out);
             const TensorDesc& od = m.plan.tensors[op.out];
-            if (op.in2 < 0 && o.pix_stride % 4 == 0 && od.base_off % 4 == 0 && o.C % 4 == 0 &&
-                o.frame_stride == (long long)o.H * o.W * o.pix_stride)
+            auto storable = [&](const TView& t, const TensorDesc& td) {
+                return t.pix_stride % 4 == 0 && td.base_off % 4 == 0 && t.C % 4 == 0 &&
+                       t.frame_stride == (long long)t.H * t.W * t.pix_stride;
+            };
+            if (storable(o, od))
                 s.tm_o_ok[i] = make_tmap_f32_2d_store(&s.tm_o[i], o.p, (uint64_t)m.chunk * o.H * o.W, (uint64_t)o.C,
                                                       (uint64_t)o.pix_stride * 4) ? 1 : 0;
+            if (op.in2 >= 0) {
+                TView r = make_view(m, s, op.in2);
+                if (storable(r, m.plan.tensors[op.in2]))
+                    s.tm_r_ok[i] = make_tmap_f32_2d_store(&s.tm_r[i], r.p, (uint64_t)m.chunk * r.H * r.W, (uint64_t)r.C,
+                                                          (uint64_t)r.pix_stride * 4) ? 1 : 0;
+            }
         }
     }
     CK(cudaMalloc(&ln.d_scores, (size_t)m.cfg.max_batch * K * 2 * sizeof(float)));
@@ -537,8 +550,17 @@ static TapsEntry& get_taps(uf_model& m, int sw, int sh) {
         CK(cudaMalloc(d, v.size() * sizeof(float)));
         CK(cudaMemcpy(*d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
     };
-    up_i(e.v.left, &e.d_vleft); up_i(e.v.ntaps, &e.d_vn); up_f(e.v.w, &e.d_vw);
-    up_i(e.h.left, &e.d_hleft); up_i(e.h.ntaps, &e.d_hn); up_f(e.h.w, &e.d_hw);
+    // device tables: zero-padded to a pitch that is a multiple of 4 floats (16-byte rows; the <= 4-tap fast path)
+    auto padded = [](const AxisTaps& a, int* pitch) {
+        *pitch = (a.max_taps + 3) / 4 * 4;
+        std::vector<float> w((size_t)a.dst_len * *pitch, 0.f);
+        for (int o = 0; o < a.dst_len; ++o)
+            for (int i = 0; i < a.max_taps; ++i) w[(size_t)o * *pitch + i] = a.w[(size_t)o * a.max_taps + i];
+        return w;
+    };
+    int vpitch = 0, hpitch = 0;
+    up_i(e.v.left, &e.d_vleft); up_i(e.v.ntaps, &e.d_vn); up_f(padded(e.v, &vpitch), &e.d_vw);
+    up_i(e.h.left, &e.d_hleft); up_i(e.h.ntaps, &e.d_hn); up_f(padded(e.h, &hpitch), &e.d_hw);
     // CTA tile: 64 x 8 destination pixels unless the source span would not fit in shared memory
     int tw = 64, th = 8;
     int cols = max_tile_span(e.h, tw);
@@ -549,7 +571,7 @@ static TapsEntry& get_taps(uf_model& m, int sw, int sh) {
     if ((size_t)th * cols * 3 * sizeof(float) > 200 * 1024)
         throw ArgError(UF_ERR_UNSUPPORTED, "resize ratio too large for the shared-memory tile (source " +
                                                std::to_string(sw) + "x" + std::to_string(sh) + ")");
-    e.dev = ResizeTapsDev{e.d_vleft, e.d_vn, e.d_vw, e.v.max_taps, e.d_hleft, e.d_hn, e.d_hw, e.h.max_taps, tw, th, cols};
+    e.dev = ResizeTapsDev{e.d_vleft, e.d_vn, e.d_vw, vpitch, e.d_hleft, e.d_hn, e.d_hw, hpitch, tw, th, cols};
     return m.taps.emplace(key, std::move(e)).first->second;
 }
 
@@ -581,8 +603,9 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                 break;
             case Impl::PointwiseTC: {
                 const TcWeights& tw = m.tc_weights[st.tc];
-                launch_pointwise_tc(s.tm_a[si], tw.tm_hi, tw.tm_lo, s.tm_o_ok[si] ? &s.tm_o[si] : nullptr, in, out,
-                                    op.in2 >= 0 ? &res : nullptr, op.b.data(), op.relu, frames, s.stream);
+                launch_pointwise_tc(s.tm_a[si], tw.tm_hi, tw.tm_lo, s.tm_o_ok[si] ? &s.tm_o[si] : nullptr,
+                                    s.tm_r_ok[si] ? &s.tm_r[si] : nullptr, in, out, op.in2 >= 0 ? &res : nullptr, op.b.data(),
+                                    op.relu, frames, s.stream);
                 break;
             }
             case Impl::FusedDwPw: {

@@ -70,6 +70,7 @@ resize_triangle_kernel(const uint8_t* __restrict__ src, long long src_frame_stri
 // u8 tile is staged in shared memory so the global stores are 4-byte words of contiguous rows.
 constexpr int RF_TW = 64, RF_TH = 8;
 
+template <bool TAPS4>  // TAPS4: every output has <= 4 taps per axis and the tables have a pitch of 4 (ratio <= 2)
 __global__ void __launch_bounds__(32 * RF_TH)
 resize_triangle_fast_kernel(const uint8_t* __restrict__ src, long long src_frame_stride, int sw, int sh,
                             uint8_t* __restrict__ dst, long long dst_frame_stride, int dw, int dh,
@@ -90,6 +91,30 @@ resize_triangle_fast_kernel(const uint8_t* __restrict__ src, long long src_frame
         const int l = t.vleft[oy], n = t.vn[oy];
         const float* w = t.vw + (size_t)oy * t.vmax;
         const uint8_t* sp = src + (size_t)blockIdx.z * src_frame_stride + (size_t)l * row_bytes + (size_t)col0 * 3;
+        if (TAPS4) {
+            // four taps, unrolled: zero-weight padding taps add +0.0 (exact), their row index is clamped into the frame
+            const float4 wq = *reinterpret_cast<const float4*>(w);
+            const int last = sh - 1 - l;
+            const unsigned* r0 = reinterpret_cast<const unsigned*>(sp);
+            const unsigned* r1 = reinterpret_cast<const unsigned*>(sp + (size_t)min(1, last) * row_bytes);
+            const unsigned* r2 = reinterpret_cast<const unsigned*>(sp + (size_t)min(2, last) * row_bytes);
+            const unsigned* r3 = reinterpret_cast<const unsigned*>(sp + (size_t)min(3, last) * row_bytes);
+            for (int wd = tx; wd < nwords; wd += 32) {
+                const unsigned u0 = __ldg(r0 + wd), u1 = __ldg(r1 + wd), u2 = __ldg(r2 + wd), u3 = __ldg(r3 + wd);
+                float a[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sh8 = 8 * j;
+                    float acc = __fmul_rn((float)((u0 >> sh8) & 0xffu), wq.x);
+                    acc = __fadd_rn(acc, __fmul_rn((float)((u1 >> sh8) & 0xffu), wq.y));
+                    acc = __fadd_rn(acc, __fmul_rn((float)((u2 >> sh8) & 0xffu), wq.z));
+                    acc = __fadd_rn(acc, __fmul_rn((float)((u3 >> sh8) & 0xffu), wq.w));
+                    if (round_intermediate) acc = roundf(fminf(fmaxf(acc, 0.f), 255.f));
+                    a[j] = acc;
+                }
+                *reinterpret_cast<float4*>(tmp_s + r * pitch + wd * 4) = make_float4(a[0], a[1], a[2], a[3]);
+            }
+        } else
         for (int wd = tx; wd < nwords; wd += 32) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             for (int i = 0; i < n; ++i) {
@@ -115,6 +140,14 @@ resize_triangle_fast_kernel(const uint8_t* __restrict__ src, long long src_frame
             const float* w = t.hw + (size_t)ox * t.hmax;
             const float* tp = tmp_s + r * pitch + l * 3;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            if (TAPS4) {
+                const float4 wq = *reinterpret_cast<const float4*>(w);
+                const int lastc = (col1 - col0 - 1 - l) * 3;  // padding taps (weight 0) re-read the last valid column
+                const float* t1 = tp + min(3, lastc), * t2 = tp + min(6, lastc), * t3 = tp + min(9, lastc);
+                a0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tp[0], wq.x), __fmul_rn(t1[0], wq.y)), __fmul_rn(t2[0], wq.z)), __fmul_rn(t3[0], wq.w));
+                a1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tp[1], wq.x), __fmul_rn(t1[1], wq.y)), __fmul_rn(t2[1], wq.z)), __fmul_rn(t3[1], wq.w));
+                a2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tp[2], wq.x), __fmul_rn(t1[2], wq.y)), __fmul_rn(t2[2], wq.z)), __fmul_rn(t3[2], wq.w));
+            } else
             for (int i = 0; i < n; ++i) {
                 const float wi = w[i];
                 a0 = __fadd_rn(a0, __fmul_rn(tp[i * 3 + 0], wi));
@@ -153,13 +186,19 @@ void launch_resize(const uint8_t* src, long long src_frame_stride, int sw, int s
             int dev = 0;
             cudaGetDevice(&dev);
             if (!configured[dev & 63]) {
-                cudaFuncSetAttribute(resize_triangle_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                cudaFuncSetAttribute(resize_triangle_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                cudaFuncSetAttribute(resize_triangle_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
                 configured[dev & 63] = true;
             }
             dim3 grid((dw + RF_TW - 1) / RF_TW, (dh + RF_TH - 1) / RF_TH, frames);
-            resize_triangle_fast_kernel<<<grid, dim3(32, RF_TH), smem, s>>>(src, src_frame_stride, sw, sh, dst,
-                                                                            dst_frame_stride, dw, dh, t, pitch,
-                                                                            round_intermediate);
+            if (t.vmax == 4 && t.hmax == 4)  // tables are padded to a pitch of 4 by the engine
+                resize_triangle_fast_kernel<true><<<grid, dim3(32, RF_TH), smem, s>>>(src, src_frame_stride, sw, sh, dst,
+                                                                                      dst_frame_stride, dw, dh, t, pitch,
+                                                                                      round_intermediate);
+            else
+                resize_triangle_fast_kernel<false><<<grid, dim3(32, RF_TH), smem, s>>>(src, src_frame_stride, sw, sh, dst,
+                                                                                       dst_frame_stride, dw, dh, t, pitch,
+                                                                                       round_intermediate);
             return;
         }
     }

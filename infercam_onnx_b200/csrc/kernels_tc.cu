@@ -149,7 +149,7 @@ struct TcParams {
 __global__ void __launch_bounds__(320, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
              const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_out,
-             const __grid_constant__ TcParams p) {
+             const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -161,7 +161,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     uint64_t* empty = conv + p.stages;       // [stages] MMAs that read the stage are done
     uint64_t* acc_full = empty + p.stages;   // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* res_bar = acc_empty + 2;       // [4] residual tile landed (one per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (p.M + TC_BM - 1) / TC_BM;
@@ -177,6 +178,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], 4);
         }
+        for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -289,6 +291,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             // fast path: +bias (constant bank) / ReLU in registers -> 128B-swizzled 32x32 tile per warp -> TMA store
             // (rows past M and columns past N are clipped by the tensor map): no address arithmetic at all.
             uint8_t* st = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) + q * 4096;
+            uint8_t* rs = st + 4 * 4096;  // residual tile of this warp (same 32 x 32, 128B-swizzled geometry)
+            uint32_t rph = 0;
             TC_T0();
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -298,6 +302,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_umma);
                 for (int c0 = 0; c0 < p.n_umma; c0 += 32) {
+                    if (p.has_res && lane == 0) {  // residual tile by TMA (rows past M read as zero)
+                        mbar_expect_tx(&res_bar[q], 4096);
+                        tma_load_2d(rs, &tm_res, &res_bar[q], c0, tile * TC_BM + q * 32);
+                    }
                     float v[32];
                     tmem_ld16(taddr + c0, v);
                     if (c0 + 16 < p.n_umma) {
@@ -305,6 +313,15 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     } else {
 #pragma unroll
                         for (int j = 16; j < 32; ++j) v[j] = 0.f;
+                    }
+                    if (p.has_res) {
+                        mbar_wait(&res_bar[q], rph);
+                        rph ^= 1;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rs + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4));
+                            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+                        }
                     }
                     if (lane == 0) bulk_wait_read0();  // this warp's previous store has left the staging tile
                     __syncwarp();
@@ -657,8 +674,9 @@ bool make_tmap_f32_2d_store(TmaMap* out, const float* base, uint64_t rows, uint6
 }
 
 // host_bias: N floats in HOST memory (copied into the kernel parameter space); tm_out may be null (legacy epilogue)
-void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TmaMap* tm_out, const TView& in,
-                         const TView& out, const TView* res, const float* host_bias, int relu, int frames, cudaStream_t s) {
+void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TmaMap* tm_out,
+                         const TmaMap* tm_res, const TView& in, const TView& out, const TView* res, const float* host_bias,
+                         int relu, int frames, cudaStream_t s) {
     TcParams p;
     p.out = out;
     p.res = res ? *res : TView{};
@@ -668,10 +686,10 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
     p.K = in.C;
     p.N = out.C;
     p.n_umma = pointwise_tc_n_umma(p.N);
-    p.tma_store = (tm_out != nullptr && res == nullptr) ? 1 : 0;
+    p.tma_store = (tm_out != nullptr && (res == nullptr || tm_res != nullptr)) ? 1 : 0;
     for (int i = 0; i < 256; ++i) p.bias[i] = i < p.N ? host_bias[i] : 0.f;
     const int stage_bytes = 2 * TC_A_BYTES + 2 * p.n_umma * TC_BK * 4;
-    int stages = (198 * 1024) / stage_bytes;
+    int stages = (188 * 1024) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
     p.stages = stages;
@@ -679,7 +697,7 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
     while (cols < 2 * p.n_umma) cols <<= 1;
     p.tmem_cols = cols;
     // stages | barriers + tmem slot | (pad to 1 KB) | 4 per-warp staging tiles of 4.6 KB (legacy) / 4 KB (TMA store)
-    const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 4) * sizeof(uint64_t) + 16 + 1024 + 4 * 32 * 36 * sizeof(float) + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 8) * sizeof(uint64_t) + 16 + 1024 + 8 * 4096 + 1024;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -690,8 +708,10 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
     const int tiles = (p.M + TC_BM - 1) / TC_BM;
     const int grid = tiles < 148 ? tiles : 148;
     const TmaMap& to = tm_out ? *tm_out : tm_a;  // unused when tma_store == 0
+    const TmaMap& tr = tm_res ? *tm_res : tm_a;  // unused without a residual
     pw_tc_kernel<<<grid, 320, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tm_a), *reinterpret_cast<const CUtensorMap*>(&tm_whi),
-                                         *reinterpret_cast<const CUtensorMap*>(&tm_wlo), *reinterpret_cast<const CUtensorMap*>(&to), p);
+                                         *reinterpret_cast<const CUtensorMap*>(&tm_wlo), *reinterpret_cast<const CUtensorMap*>(&to),
+                                         *reinterpret_cast<const CUtensorMap*>(&tr), p);
 }
 
 }  // namespace uf

@@ -20,9 +20,9 @@ int main(int argc, char** argv) {
     TView in{a, (long long)H * W * K, K, K, H, W}, out{o, (long long)H * W * N, N, N, H, W};
     std::vector<float> bias(N, 0.f);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) launch_pointwise_tc(ta, th, tl, &to, in, out, nullptr, bias.data(), 1, frames, 0);
+    for (int i = 0; i < 3; ++i) launch_pointwise_tc(ta, th, tl, &to, nullptr, in, out, nullptr, bias.data(), 1, frames, 0);
     cudaEventRecord(e0);
-    launch_pointwise_tc(ta, th, tl, &to, in, out, nullptr, bias.data(), 1, frames, 0);
+    launch_pointwise_tc(ta, th, tl, &to, nullptr, in, out, nullptr, bias.data(), 1, frames, 0);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
