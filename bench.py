@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -310,10 +310,10 @@ def main():
     l0 = model.launch_count()
     sampler.start()
     t_dev, wall_dev, out_dev = timed(step_device, args.steps, max(args.warmup, 3))
-    clocks = sampler.stop()
     launches = (model.launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))
     t_e2e_sync, wall_e2e_sync, out_e2e = timed(step_host, args.steps, max(args.warmup, 3))
     t_e2e, wall_e2e, _ = timed(step_host, args.steps, max(args.warmup, 3), threads=max(1, args.in_flight))
+    clocks = sampler.stop()  # sampled across the three timed regions (value, e2e one-at-a-time, e2e in flight)
     dets, counts = out_dev
     assert counts == out_e2e[1], "device-resident and host-fed runs disagree"
 
