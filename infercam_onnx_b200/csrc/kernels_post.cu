@@ -60,7 +60,9 @@ void launch_tail(const float* conf, const float* loc, long long conf_frame_strid
 //      all boxes selected so far, (B) survivors are resolved against each other with a
 //      PT x PT bit matrix built by warp ballots and swept by one warp.
 // ---------------------------------------------------------------------------------------------
-constexpr int PT = 256;      // threads per CTA == NMS chunk
+constexpr int PT = 256;      // NMS chunk (candidates resolved together)
+constexpr int PG = 4;        // thread groups: group g tests the chunk against the selected boxes s == g (mod PG)
+constexpr int PTHR = PT * PG;  // threads per CTA
 constexpr int PW = PT / 32;  // mask words per row
 constexpr int POST_SMEM_KEYS = 8192;
 
@@ -83,7 +85,18 @@ __device__ __forceinline__ float iou(const float4 a, const float4 b) {
     return __fdiv_rn(o, d);
 }
 
-__global__ void __launch_bounds__(PT)
+// `iou(a, b) > max_iou` with the reference's exact arithmetic, skipping the division when the overlap is empty:
+// then iou = 0 / (positive) = 0, which cannot exceed a non-negative threshold (exact is false: max_iou < 0).
+__device__ __forceinline__ bool iou_exceeds(const float4 a, const float4 b, float max_iou, bool exact) {
+    if (!exact) {
+        const float w = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+        const float h = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+        if (w < 0.0f || h < 0.0f || __fmul_rn(w, h) == 0.0f) return false;
+    }
+    return iou(a, b) > max_iou;
+}
+
+__global__ void __launch_bounds__(PTHR)
 post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, int K, float min_conf,
             float max_iou, PostBuffers pb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -94,7 +107,9 @@ post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, i
     int* kept = reinterpret_cast<int*>(alive_w + PW);                             // PT
     float* cscore = reinterpret_cast<float*>(kept + PT);                          // PT
     int* cidx = reinterpret_cast<int*>(cscore + PT);                              // PT
+    unsigned* dead = reinterpret_cast<unsigned*>(cidx + PT);                      // PT flags (phase A, OR over groups)
     __shared__ int s_cnt, s_nk;
+    const bool exact = !(max_iou >= 0.0f);  // negative / NaN threshold: no shortcut
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x;
@@ -104,7 +119,7 @@ post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, i
     __syncthreads();
     // 1. count (strict >, NaN compares false: nn.rs:127)
     int local = 0;
-    for (int k = tid; k < K; k += PT) local += sc[2 * (size_t)k + 1] > min_conf ? 1 : 0;
+    for (int k = tid; k < K; k += PTHR) local += sc[2 * (size_t)k + 1] > min_conf ? 1 : 0;
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if (lane == 0 && local) atomicAdd(&s_cnt, local);
     __syncthreads();
@@ -116,7 +131,7 @@ post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, i
     if (tid == 0) s_cnt = 0;
     __syncthreads();
     // 2. fill (order irrelevant: keys are unique, the sort fixes the order)
-    for (int k0 = 0; k0 < K; k0 += PT) {
+    for (int k0 = 0; k0 < K; k0 += PTHR) {
         const int k = k0 + tid;
         float v = 0.f;
         bool c = false;
@@ -127,12 +142,12 @@ post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, i
         basepos = __shfl_sync(0xffffffffu, basepos, 0);
         if (c) keys[basepos + __popc(bal & ((1u << lane) - 1))] = ((unsigned long long)f2ord(v) << 32) | (unsigned)k;
     }
-    for (int i = n + tid; i < n_pad; i += PT) keys[i] = 0ull;
+    for (int i = n + tid; i < n_pad; i += PTHR) keys[i] = 0ull;
     __syncthreads();
     // 3. bitonic sort, descending
     for (int k2 = 2; k2 <= n_pad; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n_pad; i += PT) {
+            for (int i = tid; i < n_pad; i += PTHR) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
                     const unsigned long long a = keys[i], b = keys[ixj];
@@ -148,35 +163,49 @@ post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, i
     float* dets = pb.dets + (size_t)f * K * 5;
     int* didx = pb.det_idx ? pb.det_idx + (size_t)f * K : nullptr;
     int n_sel = 0;
+    const int grp = tid / PT, ct = tid % PT;  // group, candidate slot within the chunk
     for (int base = 0; base < n; base += PT) {
         const int cnt = min(PT, n - base);
-        const bool valid = tid < cnt;
+        const bool valid = ct < cnt;
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
-            const unsigned k = (unsigned)(keys[base + tid] & 0xffffffffull);
+            const unsigned k = (unsigned)(keys[base + ct] & 0xffffffffull);
             b = bx[k];
-            cscore[tid] = sc[2 * (size_t)k + 1];
-            cidx[tid] = (int)k;
-        }
-        bool alive = valid;
-        // (A) against everything selected so far (uniform loop, broadcast loads)
-        for (int s = 0; s < n_sel; ++s) {
-            const float4 sb = sel[s];
-            if (alive && iou(b, sb) > max_iou) alive = false;
-        }
-        cbox[tid] = b;
-        const unsigned bal = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) alive_w[warp] = bal;
-        __syncthreads();
-        // (B) bit matrix: row j, bit i  <=>  j alive, i alive, i after j, iou(i, j) > max_iou
-        for (int j = 0; j < cnt; ++j) {
-            const bool aj = (alive_w[j >> 5] >> (j & 31)) & 1u;  // CTA-uniform
-            unsigned word = 0;
-            if (aj) {
-                const bool pred = alive && tid > j && iou(b, cbox[j]) > max_iou;
-                word = __ballot_sync(0xffffffffu, pred);
+            if (grp == 0) {
+                cscore[ct] = sc[2 * (size_t)k + 1];
+                cidx[ct] = (int)k;
+                cbox[ct] = b;
             }
-            if (lane == 0) mask[j * PW + warp] = word;
+        }
+        if (grp == 0) dead[ct] = 0u;
+        __syncthreads();
+        // (A) against everything selected so far: PG groups split the selected list, flags are OR-ed in smem
+        bool hit = false;
+        if (valid) {
+            for (int s = grp; s < n_sel && !hit; s += PG) hit = iou_exceeds(b, sel[s], max_iou, exact);
+        }
+        if (hit) dead[ct] = 1u;
+        __syncthreads();
+        bool alive = false;
+        if (grp == 0) {
+            alive = valid && dead[ct] == 0u;
+            const unsigned bal = __ballot_sync(0xffffffffu, alive);
+            if (lane == 0) alive_w[warp] = bal;
+        }
+        __syncthreads();
+        // (B) bit matrix: row j, bit i  <=>  j alive, i alive, i after j, iou(i, j) > max_iou; rows split over groups
+        if (true) {
+            const bool my_alive = valid && ((alive_w[ct >> 5] >> (ct & 31)) & 1u);
+            const int cw = ct >> 5;  // mask word this warp contributes to
+            for (int j = grp; j < cnt; j += PG) {
+                const bool aj = (alive_w[j >> 5] >> (j & 31)) & 1u;  // warp-uniform
+                unsigned word = 0;
+                if (aj) {
+                    const bool pred = my_alive && ct > j && iou_exceeds(b, cbox[j], max_iou, exact);
+                    word = __ballot_sync(0xffffffffu, pred);
+                }
+                if (lane == 0) mask[j * PW + cw] = word;
+            }
         }
         __syncthreads();
         if (warp == 0) {
@@ -209,7 +238,7 @@ post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, i
 
 static size_t post_smem_bytes() {
     return POST_SMEM_KEYS * sizeof(unsigned long long) + PT * sizeof(float4) + PT * PW * sizeof(unsigned) +
-           PW * sizeof(unsigned) + PT * sizeof(int) + PT * sizeof(float) + PT * sizeof(int);
+           PW * sizeof(unsigned) + PT * sizeof(int) + PT * sizeof(float) + PT * sizeof(int) + PT * sizeof(unsigned);
 }
 
 int post_configure() {
@@ -224,7 +253,7 @@ size_t post_sort_scratch_elems(int K) {
 
 void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
                  const PostBuffers& pb, int frames, cudaStream_t s) {
-    post_kernel<<<frames, PT, post_smem_bytes(), s>>>(scores, boxes, K, min_conf, max_iou, pb);
+    post_kernel<<<frames, PTHR, post_smem_bytes(), s>>>(scores, boxes, K, min_conf, max_iou, pb);
 }
 
 }  // namespace uf
