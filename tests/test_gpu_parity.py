@@ -99,6 +99,14 @@ def test_resize_bit_exact_synthetic_and_odd_sizes(model320, shape):
     np.testing.assert_array_equal(model320.preproc_u8(extreme), hotpath.resize_triangle(extreme, 320, 240))
 
 
+@pytest.mark.parametrize("shape", [(2160, 3840), (16, 4000), (3000, 24), (1200, 1600)])
+def test_resize_bit_exact_large_and_extreme_aspect(model320, shape):
+    """Maximum sizes: 4K frames (ratio 12 x 9: 20+ taps per axis) and extreme aspect ratios (stretch, nn.rs:74-80)."""
+    rng = np.random.default_rng(shape[0] + shape[1])
+    im = rng.integers(0, 256, (*shape, 3), dtype=np.uint8)
+    np.testing.assert_array_equal(model320.preproc_u8(im), hotpath.resize_triangle(im, 320, 240))
+
+
 def test_resize_pre024_switch(make_onnx):
     m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240),
                               resize_round_intermediate=True)
@@ -217,6 +225,23 @@ def test_postproc_exact_on_adversarial_inputs(model320, K, seed, spread):
     ref, ridx = hotpath.postproc(scores, boxes, 0.5, 0.5)
     np.testing.assert_array_equal(idx, ridx)
     np.testing.assert_array_equal(dets, ref)
+
+
+@pytest.mark.parametrize("min_conf,max_iou", [(0.3, 0.3), (0.9, 0.7), (0.5, 0.0), (0.5, -1.0), (-1.0, 0.5), (0.5, 1.0)])
+def test_postproc_other_thresholds(make_onnx, min_conf, max_iou):
+    """Thresholds other than the reference's 0.5/0.5 (nn.rs:55 takes them as arguments): max_iou = 0 and < 0
+    exercise the exact-division path, min_conf < 0 makes every prior a candidate (17 640 keys: the sort spills
+    from shared memory to the global scratch)."""
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, max_iou, min_conf, onnx_path=make_onnx(320, 240))
+    try:
+        for K, seed, spread in [(4420, 11, 0.1), (17640, 12, 0.05)]:
+            scores, boxes = _random_raw(K, seed, spread=spread)
+            dets, idx = m.postproc(scores, boxes)
+            ref, ridx = hotpath.postproc(scores, boxes, min_conf, max_iou)
+            np.testing.assert_array_equal(idx, ridx)
+            np.testing.assert_array_equal(dets, ref)
+    finally:
+        m.close()
 
 
 def test_postproc_edge_cases(model320):
