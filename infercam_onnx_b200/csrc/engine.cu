@@ -51,7 +51,7 @@ struct ArgError : public std::exception {
 
 static thread_local std::string g_last_error;
 
-enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwPw, FusedPix, FusedTma, SmallDense, Conv3x3Warp, Add, Relu, Copy };
+enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwTC, FusedDwPw, FusedPix, FusedTma, SmallDense, Conv3x3Warp, Add, Relu, Copy };
 
 static const char* impl_name(Impl i) {
     switch (i) {
@@ -60,6 +60,7 @@ static const char* impl_name(Impl i) {
         case Impl::Depthwise: return "depthwise3x3";
         case Impl::Pointwise: return "pointwise1x1";
         case Impl::PointwiseTC: return "pointwise1x1_tcgen05";
+        case Impl::FusedDwTC: return "fused_dw3x3_pw1x1_tcgen05";
         case Impl::FusedDwPw: return "fused_dw3x3_pw1x1";
         case Impl::FusedPix: return "fused_dw3x3_pw1x1_pix";
         case Impl::FusedTma: return "fused_dw3x3_pw1x1_tma";
@@ -339,8 +340,13 @@ static void build_steps(uf_model& m) {
                                      o2.pix_stride == o2.C && o2.base_off % 4 == 0 && !o2.in_concat;
                     // wide pairs: depthwise kernel + tensor-core GEMM beats the SIMT fusion (those maps are L2-resident)
                     const bool split_tc = nx_pw && !tma && tc_ok(nx) && (op.cout >= 128 || (op.cout == 64 && nx.cout >= 32));
-                    if (fusable && !split_tc) {
-                        st.impl = tma ? Impl::FusedTma : pix ? Impl::FusedPix : Impl::FusedDwPw;
+                    // depthwise computed inside the tensor-core kernel's converter warps: correct, but measured ~10 %
+                    // slower than depthwise kernel + GEMM (8 converter warps cannot hide the L2 latency of the taps),
+                    // so it is opt-in (UF_FLAG_FUSE_DW_TC) until the taps arrive by TMA
+                    const bool dw_tc = split_tc && uses[op.out] == 1 && !out.in_concat && op.cout % 32 == 0 &&
+                                       (m.cfg.flags & UF_FLAG_FUSE_DW_TC) && !(m.cfg.flags & UF_FLAG_NO_FUSION);
+                    if ((fusable && !split_tc) || dw_tc) {
+                        st.impl = dw_tc ? Impl::FusedDwTC : tma ? Impl::FusedTma : pix ? Impl::FusedPix : Impl::FusedDwPw;
                         st.op2 = (int)i + 1;
                         st.alg_bytes += bytes_of(nx.in) + bytes_of(nx.out);
                         st.min_bytes = bytes_of(op.in) + bytes_of(nx.out);
@@ -367,8 +373,8 @@ static void build_steps(uf_model& m) {
 
 static void build_tc_weights(uf_model& m) {
     for (Step& st : m.steps) {
-        if (st.impl != Impl::PointwiseTC) continue;
-        const Op& op = m.plan.ops[st.op];
+        if (st.impl != Impl::PointwiseTC && st.impl != Impl::FusedDwTC) continue;
+        const Op& op = m.plan.ops[st.impl == Impl::FusedDwTC ? st.op2 : st.op];
         const int N = op.cout, K = op.cin;
         std::vector<float> hi((size_t)N * K), lo((size_t)N * K);
         for (size_t i = 0; i < hi.size(); ++i) {  // op.w is [cout][cin][1][1] = [N][K], K contiguous
@@ -505,11 +511,14 @@ static void alloc_lane(uf_model& m, Lane& ln) {
                     throw CudaError("cuTensorMapEncodeTiled failed for fused layer '" + m.plan.tensors[pw.out].name + "'");
                 continue;
             }
-            if (m.steps[i].impl != Impl::PointwiseTC) continue;
-            const Op& op = m.plan.ops[m.steps[i].op];
-            TView v = make_view(m, s, op.in);
-            if (!make_tmap_f32_2d(&s.tm_a[i], v.p, (uint64_t)m.chunk * v.H * v.W, (uint64_t)v.C, (uint64_t)v.pix_stride * 4, 128))
-                throw CudaError("cuTensorMapEncodeTiled failed for the activations of '" + m.plan.tensors[op.out].name + "'");
+            if (m.steps[i].impl != Impl::PointwiseTC && m.steps[i].impl != Impl::FusedDwTC) continue;
+            const bool dwtc = m.steps[i].impl == Impl::FusedDwTC;
+            const Op& op = m.plan.ops[dwtc ? m.steps[i].op2 : m.steps[i].op];
+            if (!dwtc) {
+                TView v = make_view(m, s, op.in);
+                if (!make_tmap_f32_2d(&s.tm_a[i], v.p, (uint64_t)m.chunk * v.H * v.W, (uint64_t)v.C, (uint64_t)v.pix_stride * 4, 128))
+                    throw CudaError("cuTensorMapEncodeTiled failed for the activations of '" + m.plan.tensors[op.out].name + "'");
+            }
             // TMA-store epilogue when the output rows are 16-byte aligned and frames are densely packed
             TView o = make_view(m, s, op.out);
             const TensorDesc& od = m.plan.tensors[op.out];
@@ -606,6 +615,17 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                 launch_pointwise_tc(s.tm_a[si], tw.tm_hi, tw.tm_lo, s.tm_o_ok[si] ? &s.tm_o[si] : nullptr,
                                     s.tm_r_ok[si] ? &s.tm_r[si] : nullptr, in, out, op.in2 >= 0 ? &res : nullptr, op.b.data(),
                                     op.relu, frames, s.stream);
+                break;
+            }
+            case Impl::FusedDwTC: {
+                const Op& pw = p.ops[st.op2];
+                const TcWeights& tw = m.tc_weights[st.tc];
+                TView o2 = make_view(m, s, pw.out);
+                TView dummy = o2;
+                dummy.C = pw.cin;
+                TcDepthwise dwp{in, w, b, op.stride, op.relu ? 1 : 0};
+                launch_pointwise_tc(tw.tm_hi, tw.tm_hi, tw.tm_lo, s.tm_o_ok[si] ? &s.tm_o[si] : nullptr, nullptr, dummy, o2, nullptr,
+                                    pw.b.data(), pw.relu, frames, s.stream, &dwp);
                 break;
             }
             case Impl::FusedDwPw: {

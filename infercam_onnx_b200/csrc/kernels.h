@@ -81,10 +81,20 @@ int pointwise_tc_n_umma(int N);
 // tm_a: activations [frames*H*W][K] (row pitch pix_stride), box 128 rows; tm_whi/tm_wlo: weights [N][K], box n_umma rows
 bool make_tmap_f32_2d_store(TmaMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes);
 // tm_out (nullable): output [frames*H*W][N] for the TMA-store epilogue; host_bias: N floats in HOST memory
-// tm_res (nullable): residual tensor, same geometry as tm_out (TMA-loaded in the epilogue)
+// Depthwise mode: the A operand of the GEMM is computed on the fly, A = relu(dw3x3(in, stride) + b): `in` is the
+// depthwise INPUT, `w` [9][C] / `b` [C] its DEVICE weights; the depthwise result never reaches memory.
+struct TcDepthwise {
+    TView in;
+    const float* w;
+    const float* b;
+    int stride, relu;
+};
+// tm_res (nullable): residual tensor, same geometry as tm_out (TMA-loaded in the epilogue); dw (nullable): depthwise
+// mode (tm_a is then unused and `in` only provides K)
 void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TmaMap* tm_out,
                          const TmaMap* tm_res, const TView& in, const TView& out, const TView* res,
-                         const float* host_bias, int relu, int frames, cudaStream_t s);
+                         const float* host_bias, int relu, int frames, cudaStream_t s,
+                         const TcDepthwise* dw = nullptr);
 // K4+K5 fused, TMA-pipelined persistent form (C in {16,32,64}, N in {32,64}); tm_in: 4-D map of the input view
 // with box (16, in_w, in_h, 1) and 64B swizzle; tm_out: 4-D map of the output view with box (32, out_w, out_h, 1), 128B swizzle
 bool make_tmap_nhwc(TmaMap* out, const TView& v, int frames, uint32_t box_c, uint32_t box_w, uint32_t box_h, int swizzle_bytes);

@@ -143,10 +143,17 @@ struct TcParams {
     int has_res, relu;
     int M, K, N, n_umma, stages, tmem_cols;
     int tma_store;      // epilogue leaves through TMA (dense, 16-byte aligned rows, no residual)
+    // depthwise mode: the A operand is not loaded but COMPUTED by the converter warps, A = relu(dw3x3(in) + b)
+    int dw_mode, dw_stride, dw_relu;
+    TView dw_in;
+    const float* dw_w;  // [9][K]
+    const float* dw_b;  // [K]
     float bias[256];    // constant-bank operands of the epilogue
 };
 
-__global__ void __launch_bounds__(320, 1)
+constexpr int TC_THREADS = 448;  // warps 0-7 converters (0-3 in plain mode), 8-11 epilogue, 12 TMA producer, 13 MMA issuer
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
              const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_out,
              const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ TcParams p) {
@@ -171,7 +178,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&conv[s], 4);
+            mbar_init(&conv[s], p.dw_mode ? 8 : 4);
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -181,7 +188,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {
+    if (warp == 13) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -191,19 +198,19 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == 12) {
         // ===== TMA producer =====
         if (lane == 0) {
             TC_T0();
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t tx_bytes = (uint32_t)(TC_A_BYTES + 2 * b_bytes);
+            const uint32_t tx_bytes = (uint32_t)((p.dw_mode ? 0 : TC_A_BYTES) + 2 * b_bytes);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < kblocks; ++kb) {
                     TC_WAIT(mbar_wait(&empty[s], ph ^ 1));
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full[s], tx_bytes);
-                    tma_load_2d(st, &tm_a, &full[s], kb * TC_BK, tile * TC_BM);
+                    if (!p.dw_mode) tma_load_2d(st, &tm_a, &full[s], kb * TC_BK, tile * TC_BM);
                     tma_load_2d(st + 2 * TC_A_BYTES, &tm_whi, &full[s], kb * TC_BK, 0);
                     tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &tm_wlo, &full[s], kb * TC_BK, 0);
                     if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -211,7 +218,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             }
             TC_DONE(0);
         }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
         // ===== MMA issuer =====
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
@@ -250,7 +257,87 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             }
             TC_DONE(1);
         }
-    } else if (warp < 4) {
+    } else if (warp < 8 && p.dw_mode) {
+        // ===== converters, depthwise mode: A[row][k] = relu(dw3x3(in)[pixel row][channel k] + b) is computed here
+        // (the depthwise result never exists in memory) and written as (raw = tf32 hi, lo) in the 128B-swizzled
+        // K-major layout the UMMA descriptors expect: 16-byte chunk q of row r lives at r*128 + ((q ^ (r & 7)) << 4).
+        TC_T0();
+        const int ctid = threadIdx.x;          // 0..255
+        const int q = ctid & 7;                // 4-channel chunk of the 32-channel K block
+        const int r0 = ctid >> 3;              // rows r0 + 32*j, j = 0..3
+        const TView in = p.dw_in;
+        const int S = p.dw_stride, Wo = p.out.W, HWo = p.out.H * p.out.W;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            long long base[4];
+            int iy0[4], ix0[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = tile * TC_BM + r0 + 32 * j;
+                if (m < p.M) {
+                    const int f = m / HWo, pix = m - f * HWo;
+                    const int y = pix / Wo, x = pix - y * Wo;
+                    base[j] = (long long)f * in.frame_stride;
+                    iy0[j] = y * S - 1; ix0[j] = x * S - 1;
+                } else {
+                    base[j] = -1; iy0[j] = 0; ix0[j] = 0;
+                }
+            }
+            for (int kb = 0; kb < kblocks; ++kb) {
+                TC_WAIT(mbar_wait(&empty[s], ph ^ 1));  // the MMAs that read this stage have finished
+                const int c = kb * TC_BK + q * 4;
+                float4 wv[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)t * p.K + c));
+                const float4 bias4 = __ldg(reinterpret_cast<const float4*>(p.dw_b + c));
+                uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+                uint8_t* a_lo = a_hi + TC_A_BYTES;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {  // not unrolled: keeps 9 weights + one item's taps live, nothing more
+                    const int r = r0 + 32 * j;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (base[j] >= 0) {
+                        acc = bias4;
+                        const float* ip = in.p + base[j] + c;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {  // one input row at a time: 3 loads in flight, few live registers
+                            const int iy = iy0[j] + ky;
+                            const bool rok = iy >= 0 && iy < in.H;
+                            float4 v[3];
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int ix = ix0[j] + kx;
+                                v[kx] = (rok && ix >= 0 && ix < in.W)
+                                            ? *reinterpret_cast<const float4*>(ip + ((size_t)iy * in.W + ix) * in.pix_stride)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float4 ww = wv[ky * 3 + kx];
+                                acc.x = fmaf(v[kx].x, ww.x, acc.x); acc.y = fmaf(v[kx].y, ww.y, acc.y);
+                                acc.z = fmaf(v[kx].z, ww.z, acc.z); acc.w = fmaf(v[kx].w, ww.w, acc.w);
+                            }
+                        }
+                        if (p.dw_relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+                    }
+                    float4 l;
+                    l.x = acc.x - __uint_as_float(__float_as_uint(acc.x) & 0xffffe000u);
+                    l.y = acc.y - __uint_as_float(__float_as_uint(acc.y) & 0xffffe000u);
+                    l.z = acc.z - __uint_as_float(__float_as_uint(acc.z) & 0xffffe000u);
+                    l.w = acc.w - __uint_as_float(__float_as_uint(acc.w) & 0xffffe000u);
+                    const int off = r * 128 + ((q ^ (r & 7)) << 4);
+                    *reinterpret_cast<float4*>(a_hi + off) = acc;  // kind::tf32 ignores the low 13 mantissa bits: raw = hi
+                    *reinterpret_cast<float4*>(a_lo + off) = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+        if (threadIdx.x == 0) TC_DONE(2);
+    } else if (warp < 4 && !p.dw_mode) {
         // ===== converters: fp32 -> (tf32 hi, tf32 lo), element-wise so the swizzled layout is preserved =====
         TC_T0();
         int s = 0;
@@ -280,8 +367,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             }
         }
         if (threadIdx.x == 0) TC_DONE(2);
+    } else if (warp < 8) {
+        // idle converter warps in plain mode
     } else {
-        // ===== epilogue warps 4..7: TMEM -> registers -> per-warp smem transpose -> coalesced global =====
+        // ===== epilogue warps 8..11: TMEM -> registers -> per-warp smem transpose -> coalesced global =====
         // A TMEM lane is an output row, so a lane owns a whole row; writing rows straight from the
         // lanes would touch 32 different cache lines per store. Each warp stages 32 rows x 32 columns
         // in its own padded smem tile and writes them back 4 rows per instruction (8 lanes x 16 B =
@@ -345,7 +434,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
             }
             if (lane == 0) bulk_wait0();
-            if (threadIdx.x == 128) TC_DONE(3);
+            if (threadIdx.x == 256) TC_DONE(3);
         } else {
                 float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15)) + q * (32 * 36);
         const int HW = p.out.H * p.out.W;
@@ -415,7 +504,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 13) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
@@ -676,7 +765,7 @@ bool make_tmap_f32_2d_store(TmaMap* out, const float* base, uint64_t rows, uint6
 // host_bias: N floats in HOST memory (copied into the kernel parameter space); tm_out may be null (legacy epilogue)
 void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TmaMap* tm_out,
                          const TmaMap* tm_res, const TView& in, const TView& out, const TView* res, const float* host_bias,
-                         int relu, int frames, cudaStream_t s) {
+                         int relu, int frames, cudaStream_t s, const TcDepthwise* dw) {
     TcParams p;
     p.out = out;
     p.res = res ? *res : TView{};
@@ -687,6 +776,14 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
     p.N = out.C;
     p.n_umma = pointwise_tc_n_umma(p.N);
     p.tma_store = (tm_out != nullptr && (res == nullptr || tm_res != nullptr)) ? 1 : 0;
+    p.dw_mode = dw ? 1 : 0;
+    if (dw) {
+        p.dw_stride = dw->stride; p.dw_relu = dw->relu; p.dw_in = dw->in; p.dw_w = dw->w; p.dw_b = dw->b;
+        p.M = frames * out.H * out.W;  // the 1x1 conv runs on the depthwise OUTPUT pixels
+        p.K = dw->in.C;
+    } else {
+        p.dw_stride = 1; p.dw_relu = 0; p.dw_in = TView{}; p.dw_w = nullptr; p.dw_b = nullptr;
+    }
     for (int i = 0; i < 256; ++i) p.bias[i] = i < p.N ? host_bias[i] : 0.f;
     const int stage_bytes = 2 * TC_A_BYTES + 2 * p.n_umma * TC_BK * 4;
     int stages = (188 * 1024) / stage_bytes;
@@ -709,7 +806,7 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
     const int grid = tiles < 148 ? tiles : 148;
     const TmaMap& to = tm_out ? *tm_out : tm_a;  // unused when tma_store == 0
     const TmaMap& tr = tm_res ? *tm_res : tm_a;  // unused without a residual
-    pw_tc_kernel<<<grid, 320, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tm_a), *reinterpret_cast<const CUtensorMap*>(&tm_whi),
+    pw_tc_kernel<<<grid, TC_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tm_a), *reinterpret_cast<const CUtensorMap*>(&tm_whi),
                                          *reinterpret_cast<const CUtensorMap*>(&tm_wlo), *reinterpret_cast<const CUtensorMap*>(&to),
                                          *reinterpret_cast<const CUtensorMap*>(&tr), p);
 }

@@ -148,14 +148,15 @@ def _layer_report(m, oracle, frame):
     return rep
 
 
-@pytest.mark.parametrize("flags", [_capi.UF_FLAG_FORCE_GENERIC, _capi.UF_FLAG_NO_FUSION, 0])
+@pytest.mark.parametrize("flags", [_capi.UF_FLAG_FORCE_GENERIC, _capi.UF_FLAG_NO_FUSION, _capi.UF_FLAG_NO_TC,
+                                   _capi.UF_FLAG_FUSE_DW_TC, 0])
 def test_every_materialised_layer_matches_oracle(make_onnx, oracle320, flags):
     m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240), flags=flags)
     try:
         frame = _smooth(1, seed=3)[0]
         m.run(frame)
         rep = _layer_report(m, oracle320, frame)
-        assert len(rep) >= (40 if flags else 25)
+        assert len(rep) >= (40 if flags in (_capi.UF_FLAG_FORCE_GENERIC, _capi.UF_FLAG_NO_FUSION) else 25)
         bad = [r for r in rep if not r[2] <= 1e-4 * max(1.0, r[3])]
         assert not bad, f"layers off (name, chw, max_abs_diff, ref_max): {bad[:8]}"
     finally:
