@@ -229,6 +229,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
+    from infercam_onnx_b200 import streams
+    numa_bound = streams.bind_host_thread_near_gpu(local) if world > 1 else False  # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -387,6 +389,7 @@ def main():
                            "weights": "random-init seed 0 (He-normal, BN folded), cls_bias %.2f" % (CLS_BIAS if args.cls_bias is None else args.cls_bias),
                            "thresholds": [0.5, 0.5], "chunk": int(info.chunk), "slots": int(info.slots),
                            "l2": "inputs (236 MB/step/GPU) exceed the 126 MB L2; no flush needed",
+                           "host_affinity": "NVML-local cores" if numa_bound else "default",
                            "mean_detections_per_frame": float(np.mean(counts)),
                            "algorithmic_bytes_per_frame": int(info.algorithmic_bytes_per_frame),
                            "macs_per_frame": int(info.macs_per_frame)},
