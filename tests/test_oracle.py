@@ -208,3 +208,24 @@ def test_oracle_graph_shapes(make_onnx):
     m = UltrafaceOracle(make_onnx(640, 480, variant="slim"), 640, 480)
     s, b = m.raw([img])
     assert s.shape == (1, 17640, 2)
+
+
+@pytest.mark.parametrize("cfg", [dict(width=320, height=240), dict(width=320, height=240, variant="slim"),
+                                 dict(width=320, height=240, with_bn=True, seed=3), dict(width=640, height=480)])
+def test_oracle_cnn_agrees_with_opencv_dnn(make_onnx, cfg):
+    """Second opinion from an independent, third-party ONNX runtime (OpenCV's dnn module): it accepts
+    the fixture file as a regular ONNX model and its outputs agree with the oracle's interpreter. tract itself
+    cannot run here; this pins the operator semantics (Conv/BN/Relu/Concat/Transpose/Reshape/Softmax/Slice/...)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle.ultraface_ref import UltrafaceOracle
+    w, h = cfg["width"], cfg["height"]
+    path = make_onnx(w, h, variant=cfg.get("variant", "RFB"), with_bn=cfg.get("with_bn", False), seed=cfg.get("seed", 0))
+    net = cv2.dnn.readNetFromONNX(path)
+    m = UltrafaceOracle(path, w, h)
+    x = m.preproc(np.random.default_rng(0).integers(0, 256, (480, 640, 3), dtype=np.uint8))
+    net.setInput(x)
+    names = net.getUnconnectedOutLayersNames()
+    outs = dict(zip(names, net.forward(names)))
+    s, b = m.raw_from_tensor(x)
+    assert np.abs(outs["scores"].reshape(s.shape) - s).max() < 2e-5
+    assert np.abs(outs["boxes"].reshape(b.shape) - b).max() < 2e-5
