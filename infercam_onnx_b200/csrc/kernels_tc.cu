@@ -128,6 +128,30 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// 32 (or 16) accumulator columns of this thread's TMEM lane, one wait for both loads
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v, bool second) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    if (second) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr + 16));
+    } else {
+#pragma unroll
+        for (int i = 16; i < 32; ++i) r[i] = 0u;
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 // K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows at a
 // 128-byte pitch, 8-row groups 1024 bytes apart (SBO), version 1 (Blackwell), layout SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -151,7 +175,8 @@ struct TcParams {
     float bias[256];    // constant-bank operands of the epilogue
 };
 
-constexpr int TC_THREADS = 448;  // warps 0-7 converters (0-3 in plain mode), 8-11 epilogue, 12 TMA producer, 13 MMA issuer
+constexpr int TC_THREADS = 448;  // warps 0-3 converters, 4-7 converters (depthwise mode) or extra epilogue warps, 8-11 epilogue,
+                                 // 12 TMA producer, 13 MMA issuer
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
@@ -168,8 +193,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     uint64_t* empty = conv + p.stages;       // [stages] MMAs that read the stage are done
     uint64_t* acc_full = empty + p.stages;   // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
-    uint64_t* res_bar = acc_empty + 2;       // [4] residual tile landed (one per epilogue warp)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+    uint64_t* res_bar = acc_empty + 2;       // [8] residual tile landed (one per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (p.M + TC_BM - 1) / TC_BM;
@@ -183,9 +208,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 4);
+            mbar_init(&acc_empty[a], (!p.dw_mode && p.tma_store) ? 8 : 4);
         }
-        for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
+        for (int w = 0; w < 8; ++w) mbar_init(&res_bar[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 13) {
@@ -367,8 +392,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             }
         }
         if (threadIdx.x == 0) TC_DONE(2);
-    } else if (warp < 8) {
-        // idle converter warps in plain mode
+    } else if (warp < 8 && !(!p.dw_mode && p.tma_store)) {
+        // idle: these warps are converters in depthwise mode and extra epilogue warps with the TMA-store epilogue
     } else {
         // ===== epilogue warps 8..11: TMEM -> registers -> per-warp smem transpose -> coalesced global =====
         // A TMEM lane is an output row, so a lane owns a whole row; writing rows straight from the
@@ -377,10 +402,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         // one 128-byte line per row), with bias / residual / ReLU applied in the coalesced phase.
         const int q = warp & 3;
         if (p.tma_store) {
-            // fast path: +bias (constant bank) / ReLU in registers -> 128B-swizzled 32x32 tile per warp -> TMA store
-            // (rows past M and columns past N are clipped by the tensor map): no address arithmetic at all.
-            uint8_t* st = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) + q * 4096;
-            uint8_t* rs = st + 4 * 4096;  // residual tile of this warp (same 32 x 32, 128B-swizzled geometry)
+            // fast path: +bias (constant bank) / residual / ReLU in registers -> 128B-swizzled 32x32 tile per warp ->
+            // TMA store (rows past M and columns past N are clipped by the tensor map): no address arithmetic at all.
+            // In plain mode warps 4-7 join as a second epilogue group: a TMEM lane quarter (32 rows) is then shared by
+            // two warps that take alternate 32-column chunks.
+            const int ngrp = p.dw_mode ? 1 : 2;
+            const int grp = p.dw_mode ? 0 : (warp >= 8 ? 1 : 0);
+            const int ew = grp * 4 + q;  // epilogue warp index 0..7
+            uint8_t* st = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023)) + ew * 4096;
             uint32_t rph = 0;
             TC_T0();
             int it = 0;
@@ -390,30 +419,32 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 TC_WAIT(mbar_wait(&acc_full[a], aph));
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_umma);
-                for (int c0 = 0; c0 < p.n_umma; c0 += 32) {
-                    if (p.has_res && lane == 0) {  // residual tile by TMA (rows past M read as zero)
-                        mbar_expect_tx(&res_bar[q], 4096);
-                        tma_load_2d(rs, &tm_res, &res_bar[q], c0, tile * TC_BM + q * 32);
+                bool released = false;
+                for (int c0 = 32 * grp; c0 < p.n_umma; c0 += 32 * ngrp) {
+                    if (lane == 0) bulk_wait_read0();  // this warp's previous store has left its staging tile
+                    __syncwarp();
+                    if (p.has_res && lane == 0) {  // residual tile by TMA into the staging tile (rows past M read as zero)
+                        mbar_expect_tx(&res_bar[ew], 4096);
+                        tma_load_2d(st, &tm_res, &res_bar[ew], c0, tile * TC_BM + q * 32);
                     }
                     float v[32];
-                    tmem_ld16(taddr + c0, v);
-                    if (c0 + 16 < p.n_umma) {
-                        tmem_ld16(taddr + c0 + 16, v + 16);
-                    } else {
-#pragma unroll
-                        for (int j = 16; j < 32; ++j) v[j] = 0.f;
+                    tmem_ld32(taddr + c0, v, c0 + 16 < p.n_umma);
+                    if (c0 + 32 * ngrp >= p.n_umma) {  // last read of this accumulator: hand it back to the MMA warp now
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[a]);
+                        released = true;
                     }
                     if (p.has_res) {
-                        mbar_wait(&res_bar[q], rph);
+                        mbar_wait(&res_bar[ew], rph);
                         rph ^= 1;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(rs + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4));
+                            const float4 r4 = *reinterpret_cast<const float4*>(st + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4));
                             v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
                         }
+                        __syncwarp();  // every lane has read its residual row before the tile is overwritten
                     }
-                    if (lane == 0) bulk_wait_read0();  // this warp's previous store has left the staging tile
-                    __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 x;
@@ -429,9 +460,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                         bulk_commit();
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[a]);
+                if (!released) {  // this warp had no column chunk in this tile (N <= 32): still release the accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[a]);
+                }
             }
             if (lane == 0) bulk_wait0();
             if (threadIdx.x == 256) TC_DONE(3);
@@ -794,7 +827,7 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
     while (cols < 2 * p.n_umma) cols <<= 1;
     p.tmem_cols = cols;
     // stages | barriers + tmem slot | (pad to 1 KB) | 4 per-warp staging tiles of 4.6 KB (legacy) / 4 KB (TMA store)
-    const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 8) * sizeof(uint64_t) + 16 + 1024 + 8 * 4096 + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 12) * sizeof(uint64_t) + 16 + 1024 + 8 * 4096 + 1024;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
