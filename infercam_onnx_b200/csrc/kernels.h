@@ -111,6 +111,10 @@ void launch_copy(const TView& a, const TView& out, int frames, cudaStream_t s);
 // NHWC view -> dense NCHW (uf_tensor_read)
 void launch_nhwc_to_nchw(const TView& a, int frame, float* out, cudaStream_t s);
 
+// programmatic dependent launch for the kernel chain (pdl.cuh); process-wide switch, default off
+bool pdl_enabled();
+void pdl_set_enabled(bool on);
+
 // ---- K8: softmax over 2 classes + prior-box decode; conf [F,K,2], loc [F,K,4] raw head outputs
 void launch_tail(const float* conf, const float* loc, long long conf_frame_stride,
                  long long loc_frame_stride, const float* priors, int K, float center_var,

@@ -3,6 +3,7 @@
 // (BASELINE.json north_star: raw tensors within 1e-4 abs of the reference => no tf32/bf16 here).
 // Bias, folded BatchNorm, residual add and ReLU live in the epilogue of the producing conv.
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace uf {
 
@@ -93,8 +94,10 @@ __global__ void __launch_bounds__(STEM_T * STEM_T)
 stem_kernel(U8View in, const float* __restrict__ lut, TView out, const __grid_constant__ StemWeights wts, int relu) {
     __shared__ float s_in[STEM_IN * STEM_IN * 3];
     __shared__ float s_lut[768];
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
-    for (int i = tid; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+    for (int i = tid; i < 768; i += blockDim.x) s_lut[i] = lut[i];  // static table: may be read before the wait
+    pdl_wait();
     __syncthreads();
     const int ox0 = blockIdx.x * STEM_T, oy0 = blockIdx.y * STEM_T, n = blockIdx.z;
     const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
@@ -139,7 +142,7 @@ stem_kernel(U8View in, const float* __restrict__ lut, TView out, const __grid_co
 void launch_stem(const U8View& in, const float* lut, const TView& out, const float* host_w, int relu, int frames,
                  cudaStream_t s) {
     dim3 grid((out.W + STEM_T - 1) / STEM_T, (out.H + STEM_T - 1) / STEM_T, frames);
-    stem_kernel<<<grid, STEM_T * STEM_T, 0, s>>>(in, lut, out, *reinterpret_cast<const StemWeights*>(host_w), relu);
+    launch_pdl(stem_kernel, grid, dim3(STEM_T * STEM_T), 0, s, in, lut, out, *reinterpret_cast<const StemWeights*>(host_w), relu);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -154,6 +157,8 @@ __global__ void __launch_bounds__(128)
 depthwise3x3_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int relu,
                     int strips, long long total) {
     constexpr int NR = (R - 1) * S + 3;
+    pdl_launch_dependents();
+    pdl_wait();
     const int C4 = out.C >> 2;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -207,11 +212,11 @@ void launch_depthwise(const TView& in, const TView& out, const float* w_tc, cons
     if (stride == 1) {
         const int strips = (out.H + 3) / 4;
         const long long total = (long long)frames * strips * out.W * (out.C / 4);
-        depthwise3x3_kernel<1, 4><<<grid_for(total, 128, 64), 128, 0, s>>>(in, out, w_tc, b, relu, strips, total);
+        launch_pdl(depthwise3x3_kernel<1, 4>, dim3(grid_for(total, 128, 64)), dim3(128), 0, s, in, out, w_tc, b, relu, strips, total);
     } else {
         const int strips = (out.H + 1) / 2;
         const long long total = (long long)frames * strips * out.W * (out.C / 4);
-        depthwise3x3_kernel<2, 2><<<grid_for(total, 128, 64), 128, 0, s>>>(in, out, w_tc, b, relu, strips, total);
+        launch_pdl(depthwise3x3_kernel<2, 2>, dim3(grid_for(total, 128, 64)), dim3(128), 0, s, in, out, w_tc, b, relu, strips, total);
     }
 }
 
@@ -520,6 +525,8 @@ template <int N>
 __global__ void __launch_bounds__(256)
 conv3x3_warp_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int dil, int relu,
                     int total_pix) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= total_pix) return;
@@ -584,7 +591,7 @@ void launch_conv3x3_warp(const TView& in, const TView& out, const float* w_kkio,
                          int frames, cudaStream_t s) {
     const int total = frames * out.H * out.W;
     const int grid = (total * 32 + 255) / 256;
-#define UF_W(NN) conv3x3_warp_kernel<NN><<<grid, 256, 0, s>>>(in, out, w_kkio, b, dil, relu, total)
+#define UF_W(NN) launch_pdl(conv3x3_warp_kernel<NN>, dim3(grid), dim3(256), 0, s, in, out, w_kkio, b, dil, relu, total)
     switch (out.C) {
         case 4: UF_W(4); break;
         case 6: UF_W(6); break;
@@ -622,6 +629,15 @@ fused_dwpw_pix_kernel(TView in, TView out, const float* __restrict__ dw_w, const
     const int f = bid / tiles_y;
     const int x0 = txi * TX, y0 = tyi * TY;
     const int gx0 = x0 * S - 1, gy0 = y0 * S - 1;
+    pdl_launch_dependents();
+    for (int i = tid; i < 9 * C; i += NTHR) s_dw[i] = dw_w[i];
+    for (int i = tid; i < C; i += NTHR) s_dw[9 * C + i] = dw_b[i];
+    for (int i = tid; i < C * n_pad; i += NTHR) {
+        const int ci = i / n_pad, n = i - ci * n_pad;
+        s_pw[i] = n < N ? pw_w[(size_t)ci * N + n] : 0.f;
+    }
+    for (int i = tid; i < n_pad; i += NTHR) s_pb[i] = i < N ? pw_b[i] : 0.f;
+    pdl_wait();  // weights above are static; the input tile below is the predecessor's output
     const float* ip = in.p + (size_t)f * in.frame_stride;
     for (int i = tid; i < IH * IW * C4; i += NTHR) {
         const int pix = i / C4, q = i - pix * C4;   // constants: shifts
@@ -631,13 +647,6 @@ fused_dwpw_pix_kernel(TView in, TView out, const float* __restrict__ dw_w, const
         if (gy >= 0 && gy < in.H && gx >= 0 && gx < in.W) v = ld4(ip + ((size_t)gy * in.W + gx) * in.pix_stride + q * 4);
         st4(s_in + pix * P + q * 4, v);
     }
-    for (int i = tid; i < 9 * C; i += NTHR) s_dw[i] = dw_w[i];
-    for (int i = tid; i < C; i += NTHR) s_dw[9 * C + i] = dw_b[i];
-    for (int i = tid; i < C * n_pad; i += NTHR) {
-        const int ci = i / n_pad, n = i - ci * n_pad;
-        s_pw[i] = n < N ? pw_w[(size_t)ci * N + n] : 0.f;
-    }
-    for (int i = tid; i < n_pad; i += NTHR) s_pb[i] = i < N ? pw_b[i] : 0.f;
     __syncthreads();
     const int tx = tid % TX, ty = tid / TX;
     const int ox = x0 + tx, oy = y0 + ty;
@@ -711,8 +720,8 @@ static void launch_pix_t(const TView& in, const TView& out, const float* dw_w, c
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         configured[dev & 63] = true;
     }
-    kern<<<tiles_x * tiles_y * frames, TX * TY, smem, s>>>(in, out, dw_w, dw_b, dw_relu, pw_w, pw_b, pw_relu, tiles_x,
-                                                          tiles_y, n_pad);
+    launch_pdl(kern, dim3(tiles_x * tiles_y * frames), dim3(TX * TY), smem, s, in, out, dw_w, dw_b, dw_relu, pw_w, pw_b, pw_relu,
+               tiles_x, tiles_y, n_pad);
 }
 
 void launch_fused_dwpw_pix(const TView& in, const TView& out, const float* dw_w_tc, const float* dw_b, int stride,
@@ -748,6 +757,8 @@ small_dense3x3_kernel(TView in, TView out, const __grid_constant__ SmallDenseWei
                       int tiles_x, int tiles_y) {
     constexpr int P = CIN + 4, C4 = CIN / 4, NTHR = SD_TX * SD_TY;
     extern __shared__ __align__(16) float s_in[];  // (SD_TY+2d) x (SD_TX+2d) x P
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
     const int txi = bid % tiles_x; bid /= tiles_x;
@@ -812,8 +823,8 @@ static void launch_sd_t(const TView& in, const TView& out, const float* host_w, 
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         configured[dev & 63] = true;
     }
-    kern<<<tiles_x * tiles_y * frames, SD_TX * SD_TY, smem, s>>>(in, out, *reinterpret_cast<const SmallDenseWeights<CIN, COUT>*>(host_w),
-                                                                dil, relu, tiles_x, tiles_y);
+    launch_pdl(kern, dim3(tiles_x * tiles_y * frames), dim3(SD_TX * SD_TY), smem, s, in, out,
+               *reinterpret_cast<const SmallDenseWeights<CIN, COUT>*>(host_w), dil, relu, tiles_x, tiles_y);
 }
 
 // host_w: 9*CIN*COUT weights [ky][kx][ci][co] followed by COUT biases, in HOST memory; dil <= 8

@@ -12,6 +12,7 @@
 // from the back), suppression on strict `iou > max_iou`, EPS = 1e-7 inside the denominator,
 // every f32 operation rounded separately (no FMA) in the reference's left-to-right order.
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace uf {
 
@@ -19,6 +20,8 @@ __global__ void __launch_bounds__(256)
 tail_kernel(const float* __restrict__ conf, const float* __restrict__ loc, long long conf_fs, long long loc_fs,
             const float* __restrict__ priors, int K, float cv, float sv, float* __restrict__ scores,
             float* __restrict__ boxes, long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long f = idx / K;
@@ -47,8 +50,8 @@ void launch_tail(const float* conf, const float* loc, long long conf_frame_strid
     long long g = (total + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
     if (g < 1) g = 1;
-    tail_kernel<<<(int)g, 256, 0, s>>>(conf, loc, conf_frame_stride, loc_frame_stride, priors, K, center_var,
-                                       size_var, scores, boxes, total);
+    launch_pdl(tail_kernel, dim3((unsigned)g), dim3(256), 0, s, conf, loc, conf_frame_stride, loc_frame_stride, priors, K, center_var,
+               size_var, scores, boxes, total);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -111,6 +114,8 @@ post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, i
     __shared__ int s_cnt, s_nk;
     const bool exact = !(max_iou >= 0.0f);  // negative / NaN threshold: no shortcut
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x;
     const float* sc = scores + (size_t)f * K * 2;
@@ -253,7 +258,7 @@ size_t post_sort_scratch_elems(int K) {
 
 void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
                  const PostBuffers& pb, int frames, cudaStream_t s) {
-    post_kernel<<<frames, PTHR, post_smem_bytes(), s>>>(scores, boxes, K, min_conf, max_iou, pb);
+    launch_pdl(post_kernel, dim3(frames), dim3(PTHR), post_smem_bytes(), s, scores, boxes, K, min_conf, max_iou, pb);
 }
 
 }  // namespace uf

@@ -25,6 +25,7 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace uf {
 
@@ -183,6 +184,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
              const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_out,
              const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_launch_dependents();
+#ifdef UF_TC_TIMING
+    const long long t_entry = clock64();
+#endif
     // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = p.n_umma * TC_BK * 4;
@@ -222,6 +227,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#ifdef UF_TC_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_timing[8] = clock64() - t_entry;
+#endif
+    pdl_wait();  // barriers, TMEM and the tensor-map fetch above overlap the predecessor; its results are needed from here
 
     if (warp == 12) {
         // ===== TMA producer =====
@@ -264,17 +273,15 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     TC_WAIT(mbar_wait(&conv[s], ph));
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, w_hi = st + 2 * TC_A_BYTES, w_lo = w_hi + b_bytes;
+                    // descriptors once per stage; advancing K by 8 tf32 = 32 bytes is +2 in the 16-byte address field
+                    const uint64_t d_ahi = umma_desc_sw128(st), d_alo = umma_desc_sw128(st + TC_A_BYTES);
+                    const uint64_t d_whi = umma_desc_sw128(st + 2 * TC_A_BYTES), d_wlo = umma_desc_sw128(st + 2 * TC_A_BYTES + b_bytes);
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {  // small terms first, a_hi*w_hi last
-                        const uint32_t ab = term == 0 ? a_lo : a_hi;
-                        const uint32_t wb = term == 1 ? w_lo : w_hi;
+                    for (int k = 0; k < TC_BK / 8; ++k) { umma_tf32(d, d_alo + 2 * k, d_whi + 2 * k, idesc, accumulate); accumulate = 1; }
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes
-                            umma_tf32(d, umma_desc_sw128(ab + k * 32), umma_desc_sw128(wb + k * 32), idesc, accumulate);
-                            accumulate = 1;
-                        }
-                    }
+                    for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(d, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(d, d_ahi + 2 * k, d_whi + 2 * k, idesc, 1);
                     umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
@@ -537,6 +544,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
+#ifdef UF_TC_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_timing[9] = clock64() - t_entry;
+#endif
     if (warp == 13) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -633,11 +643,13 @@ fused_dwpw_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         tma_load_4d(in_buf + (u & 1) * SLICE_ALLOC, &tm_in, bar, (u % NSL) * 16, x0 * S - 1, y0 * S - 1, f);
     };
 
+    pdl_launch_dependents();
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();
     __syncthreads();
     if (tid == 0 && n_units > 0) {
         issue(0);
@@ -754,8 +766,9 @@ static void launch_tma_t(const TmaMap& tm_in, const TmaMap& tm_out, const TView&
     }
     int grid = 148 * ctas_per_sm[dev & 63];
     if (grid > total) grid = total;
-    kern<<<grid, TX * TY, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tm_in), *reinterpret_cast<const CUtensorMap*>(&tm_out),
-                                     *reinterpret_cast<const FusedWeights<C, N>*>(host_w), dw_relu, pw_relu, tiles_x, tiles_y, total);
+    launch_pdl(kern, dim3(grid), dim3(TX * TY), smem, s, *reinterpret_cast<const CUtensorMap*>(&tm_in),
+               *reinterpret_cast<const CUtensorMap*>(&tm_out), *reinterpret_cast<const FusedWeights<C, N>*>(host_w), dw_relu, pw_relu,
+               tiles_x, tiles_y, total);
 }
 
 size_t fused_dwpw_tma_weight_floats(int C, int N) { return (size_t)10 * C + (size_t)C * N + N; }
@@ -776,6 +789,10 @@ void launch_fused_dwpw_tma(const TmaMap& tm_in, const TmaMap& tm_out, const TVie
 #ifdef UF_TC_TIMING
 void tc_timing_read(long long* out16) { cudaMemcpyFromSymbol(out16, g_tc_timing, sizeof(long long) * 16); }
 #endif
+
+static bool g_pdl = false;  // measured: no gain once the chain is replayed as a CUDA graph, so opt-in (UF_FLAG_PDL)
+bool pdl_enabled() { return g_pdl; }
+void pdl_set_enabled(bool on) { g_pdl = on; }
 
 bool pointwise_tc_supported(int K, int N) { return K >= 32 && K % 4 == 0 && N >= 1 && N <= 256; }
 
@@ -839,9 +856,9 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
     const int grid = tiles < 148 ? tiles : 148;
     const TmaMap& to = tm_out ? *tm_out : tm_a;  // unused when tma_store == 0
     const TmaMap& tr = tm_res ? *tm_res : tm_a;  // unused without a residual
-    pw_tc_kernel<<<grid, TC_THREADS, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tm_a), *reinterpret_cast<const CUtensorMap*>(&tm_whi),
-                                         *reinterpret_cast<const CUtensorMap*>(&tm_wlo), *reinterpret_cast<const CUtensorMap*>(&to),
-                                         *reinterpret_cast<const CUtensorMap*>(&tr), p);
+    launch_pdl(pw_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, s, *reinterpret_cast<const CUtensorMap*>(&tm_a),
+               *reinterpret_cast<const CUtensorMap*>(&tm_whi), *reinterpret_cast<const CUtensorMap*>(&tm_wlo),
+               *reinterpret_cast<const CUtensorMap*>(&to), *reinterpret_cast<const CUtensorMap*>(&tr), p);
 }
 
 }  // namespace uf

@@ -322,6 +322,25 @@ def test_device_resident_input_equals_host_input(make_onnx):
         m.close()
 
 
+def test_programmatic_dependent_launch_gives_identical_results(make_onnx):
+    """UF_FLAG_PDL: kernels start before their predecessor has finished and wait with griddepcontrol.wait."""
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    frames = list(_noise(40, seed=77))
+    a = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=40)
+    ref = [a.run_batch(frames, cap=128) for _ in range(3)][-1]
+    sa, ba = a.raw_outputs(0, 40)
+    a.close()
+    b = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=40, flags=_capi.UF_FLAG_PDL)
+    try:
+        got = [b.run_batch(frames, cap=128) for _ in range(3)][-1]  # third call replays the captured graph
+        sb, bb = b.raw_outputs(0, 40)
+        np.testing.assert_array_equal(sa, sb)
+        np.testing.assert_array_equal(ba, bb)
+        assert got[1] == ref[1]
+    finally:
+        b.close()
+
+
 def test_concurrent_calls_on_one_handle(make_onnx):
     """`UltrafaceModel` is Send + Sync (inferer.rs:29-50): calls from several host threads on one handle run on
     separate lanes and must give exactly the single-threaded results."""

@@ -30,5 +30,6 @@ int main(int argc, char** argv) {
     const char* names[4] = {"producer", "mma", "converter", "epilogue"};
     printf("%dx%d K=%d N=%d M=%lld tiles=%lld: %.1f us (%s)\n", H, W, K, N, M, (M + 127) / 128, ms * 1e3, cudaGetErrorString(e));
     for (int r = 0; r < 4; ++r) printf("  %-9s total %8lld cycles, waiting %8lld (%.0f%%)\n", names[r], t[r * 2], t[r * 2 + 1], 100.0 * t[r * 2 + 1] / (t[r * 2] + 1));
+    printf("  prologue %lld cycles, entry->teardown barrier %lld cycles (block 0)\n", t[8], t[9]);
     return 0;
 }
