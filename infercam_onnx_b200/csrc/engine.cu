@@ -718,6 +718,7 @@ static void run_body(uf_model& m, Lane& ln, Slot& s, const U8View& input, uint32
     if (!use_graph) {
         run_cnn(m, s, input, frames);
         run_tail_post(m, ln, s, first, frames);
+        CK(cudaGetLastError());  // launch-configuration errors are not sticky: ask for them here
         return;
     }
     const auto key = std::make_tuple(first, frames, stem_inside ? 1 : 0);
@@ -727,6 +728,7 @@ static void run_body(uf_model& m, Lane& ln, Slot& s, const U8View& input, uint32
         if (s.graph_seen[key]++ == 0) {
             run_cnn(m, s, input, frames);
             run_tail_post(m, ln, s, first, frames);
+            CK(cudaGetLastError());
             return;
         }
         if (!stem_inside) run_cnn(m, s, input, frames, 0, 1);
@@ -742,6 +744,7 @@ static void run_body(uf_model& m, Lane& ln, Slot& s, const U8View& input, uint32
             throw;
         }
         CK(cudaStreamEndCapture(s.stream, &g));
+        CK(cudaGetLastError());
         cudaGraphExec_t ge = nullptr;
         cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
         cudaGraphDestroy(g);

@@ -320,6 +320,7 @@ struct Lowerer {
                                    "') is outside the UltraFace graph family");
         }
         finish_heads();
+        merge_sibling_pointwise();
         finalize_buffers();
     }
 
@@ -410,6 +411,58 @@ struct Lowerer {
             plan.size_variance = scal[1];
         } else if (!scal.empty()) {
             plan.warnings += "unexpected number of scalar Mul constants in the decode tail; using variances 0.1/0.2; ";
+        }
+    }
+
+    // Sibling 1x1 convs that read the same tensor (the three 64->8 branch heads of BasicRFB) become ONE conv with
+    // concatenated output channels: the input is read once and two launches disappear. The original outputs stay
+    // addressable as channel slices (strided views) of the merged tensor, so their consumers are unchanged.
+    void merge_sibling_pointwise() {
+        for (size_t i = 0; i < plan.ops.size(); ++i) {
+            Op& a = plan.ops[i];
+            auto mergeable = [&](const Op& o) {
+                if (o.kind != OpKind::Conv || o.k != 1 || o.groups != 1 || o.stride != 1 || o.pad != 0 || o.in2 >= 0) return false;
+                const TensorDesc& t = plan.tensors[o.out];
+                return !t.in_concat && !t.is_input && t.base_off == 0 && t.pix_stride == t.C && t.C % 4 == 0;
+            };
+            if (!mergeable(a)) continue;
+            std::vector<size_t> sib;
+            for (size_t j = i + 1; j < plan.ops.size(); ++j) {
+                const Op& b = plan.ops[j];
+                if (mergeable(b) && b.in == a.in && b.relu == a.relu && b.cin == a.cin) sib.push_back(j);
+            }
+            if (sib.empty()) continue;
+            const TensorDesc first = plan.tensors[a.out];
+            int ctot = a.cout;
+            for (size_t j : sib) ctot += plan.ops[j].cout;
+            // merged tensor + buffer
+            TensorDesc mt;
+            mt.name = first.name + "#merged";
+            mt.C = ctot; mt.H = first.H; mt.W = first.W;
+            mt.buf = (int)plan.buffers.size();
+            mt.pix_stride = ctot;
+            BufferDesc mb;
+            mb.frame_floats = (int64_t)ctot * first.H * first.W;
+            plan.buffers.push_back(mb);
+            plan.tensors.push_back(mt);
+            const int merged_id = (int)plan.tensors.size() - 1;
+            int off = 0;
+            auto retarget = [&](int tid_) {
+                TensorDesc& t = plan.tensors[tid_];
+                plan.buffers[t.buf].frame_floats = 0;
+                t.buf = mt.buf; t.base_off = off; t.pix_stride = ctot; t.in_concat = true;
+                off += t.C;
+            };
+            retarget(a.out);
+            for (size_t j : sib) {
+                const Op& b = plan.ops[j];
+                a.w.insert(a.w.end(), b.w.begin(), b.w.end());  // [cout][cin] rows simply concatenate
+                a.b.insert(a.b.end(), b.b.begin(), b.b.end());
+                retarget(b.out);
+            }
+            a.cout = ctot;
+            a.out = merged_id;
+            for (size_t k = sib.size(); k-- > 0;) plan.ops.erase(plan.ops.begin() + (long)sib[k]);
         }
     }
 
