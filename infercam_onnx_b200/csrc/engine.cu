@@ -51,7 +51,7 @@ struct ArgError : public std::exception {
 
 static thread_local std::string g_last_error;
 
-enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwTC, FusedDwPw, FusedPix, FusedTma, SmallDense, Conv3x3Warp, Add, Relu, Copy };
+enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwTC, FusedDwPw, FusedPix, FusedHead, FusedTma, SmallDense, Conv3x3Warp, Add, Relu, Copy };
 
 static const char* impl_name(Impl i) {
     switch (i) {
@@ -63,6 +63,7 @@ static const char* impl_name(Impl i) {
         case Impl::FusedDwTC: return "fused_dw3x3_pw1x1_tcgen05";
         case Impl::FusedDwPw: return "fused_dw3x3_pw1x1";
         case Impl::FusedPix: return "fused_dw3x3_pw1x1_pix";
+        case Impl::FusedHead: return "fused_dw3x3_pw1x1_head";
         case Impl::FusedTma: return "fused_dw3x3_pw1x1_tma";
         case Impl::Conv3x3Warp: return "conv3x3_warp";
         case Impl::SmallDense: return "small_dense3x3";
@@ -346,7 +347,8 @@ static void build_steps(uf_model& m) {
                     const bool dw_tc = split_tc && uses[op.out] == 1 && !out.in_concat && op.cout % 32 == 0 &&
                                        (m.cfg.flags & UF_FLAG_FUSE_DW_TC) && !(m.cfg.flags & UF_FLAG_NO_FUSION);
                     if ((fusable && !split_tc) || dw_tc) {
-                        st.impl = dw_tc ? Impl::FusedDwTC : tma ? Impl::FusedTma : pix ? Impl::FusedPix : Impl::FusedDwPw;
+                        const bool head = pix && !no_tc && head_dwpw_supported(op.cout, nx.cout, op.stride);
+                        st.impl = dw_tc ? Impl::FusedDwTC : tma ? Impl::FusedTma : head ? Impl::FusedHead : pix ? Impl::FusedPix : Impl::FusedDwPw;
                         st.op2 = (int)i + 1;
                         st.alg_bytes += bytes_of(nx.in) + bytes_of(nx.out);
                         st.min_bytes = bytes_of(op.in) + bytes_of(nx.out);
@@ -417,10 +419,11 @@ static void build_param_weights(uf_model& m) {
             for (int co = 0; co < co_n; ++co) st.host_w[(size_t)k * k * ci_n * co_n + co] = op.b[co];
             continue;
         }
-        if (st.impl != Impl::FusedTma) continue;
+        if (st.impl != Impl::FusedTma && st.impl != Impl::FusedHead) continue;
         const Op& dw = m.plan.ops[st.op];
         const Op& pw = m.plan.ops[st.op2];
-        const int C = dw.cout, N = pw.cout;
+        const int C = dw.cout, Nreal = pw.cout;
+        const int N = st.impl == Impl::FusedHead ? (Nreal <= 8 ? 8 : 16) : Nreal;  // heads: outputs zero-padded to 8 / 16
         st.host_w.assign(fused_dwpw_tma_weight_floats(C, N), 0.f);
         float* p = st.host_w.data();
         for (int t = 0; t < 9; ++t)
@@ -428,8 +431,8 @@ static void build_param_weights(uf_model& m) {
         for (int c = 0; c < C; ++c) p[9 * C + c] = dw.b[c];
         float* q = p + 10 * C;
         for (int ci = 0; ci < C; ++ci)
-            for (int n = 0; n < N; ++n) q[ci * N + n] = pw.w[(size_t)n * C + ci];  // ONNX [n][ci][1][1]
-        for (int n = 0; n < N; ++n) q[C * N + n] = pw.b[n];
+            for (int n = 0; n < Nreal; ++n) q[ci * N + n] = pw.w[(size_t)n * C + ci];  // ONNX [n][ci][1][1]
+        for (int n = 0; n < Nreal; ++n) q[C * N + n] = pw.b[n];
     }
 }
 
@@ -640,6 +643,12 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                 TView o2 = make_view(m, s, pw.out);
                 launch_fused_dwpw_pix(in, o2, w, b, op.stride, op.relu, m.d_weights + m.w_off[st.op2],
                                       m.d_weights + m.b_off[st.op2], pw.relu, frames, s.stream);
+                break;
+            }
+            case Impl::FusedHead: {
+                const Op& pw = p.ops[st.op2];
+                TView o2 = make_view(m, s, pw.out);
+                launch_head_dwpw(in, o2, st.host_w.data(), op.relu, pw.relu, frames, s.stream);
                 break;
             }
             case Impl::FusedTma: {

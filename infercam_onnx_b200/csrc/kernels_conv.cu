@@ -698,6 +698,104 @@ fused_dwpw_pix_kernel(TView in, TView out, const float* __restrict__ dw_w, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SSD `sep` heads on the 64-channel map (dw3x3 + ReLU -> 1x1 64 -> 6 / 12): same tile scheme as above, but the
+// depthwise and pointwise weights are kernel-parameter constants (6.8 KB), so the arithmetic is pure FFMA with
+// constant-bank operands and shared memory only serves the input tile.
+// ---------------------------------------------------------------------------------------------
+template <int NP>
+struct HeadWeights {
+    float dw[9 * 64];
+    float dwb[64];
+    float pw[64 * NP];  // [ci][n], zero padded to NP outputs
+    float pwb[NP];
+};
+
+template <int NP>
+__global__ void __launch_bounds__(256)
+head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<NP> wts, int dw_relu, int pw_relu, int tiles_x,
+                 int tiles_y) {
+    constexpr int C = 64, TX = 8, TY = 32, IW = TX + 2, IH = TY + 2, P = C + 4, NTHR = TX * TY, C4 = C / 4;
+    extern __shared__ __align__(16) float s_in[];  // IH*IW*P
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int txi = bid % tiles_x; bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int f = bid / tiles_y;
+    const int x0 = txi * TX, y0 = tyi * TY;
+    const float* ip = in.p + (size_t)f * in.frame_stride;
+    for (int i = tid; i < IH * IW * C4; i += NTHR) {
+        const int pix = i / C4, q = i - pix * C4;
+        const int py = pix / IW, px = pix - py * IW;
+        const int gy = y0 - 1 + py, gx = x0 - 1 + px;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < in.H && gx >= 0 && gx < in.W) v = ld4(ip + ((size_t)gy * in.W + gx) * in.pix_stride + q * 4);
+        st4(s_in + pix * P + q * 4, v);
+    }
+    __syncthreads();
+    const int tx = tid % TX, ty = tid / TX;
+    const int ox = x0 + tx, oy = y0 + ty;
+    if (ox >= out.W || oy >= out.H) return;
+    float o[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) o[j] = wts.pwb[j];
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+        float a0 = wts.dwb[c], a1 = wts.dwb[c + 1], a2 = wts.dwb[c + 2], a3 = wts.dwb[c + 3];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 v = ld4(s_in + ((ty + ky) * IW + tx + kx) * P + c);
+                const int wo = (ky * 3 + kx) * C + c;
+                a0 = fmaf(v.x, wts.dw[wo], a0); a1 = fmaf(v.y, wts.dw[wo + 1], a1);
+                a2 = fmaf(v.z, wts.dw[wo + 2], a2); a3 = fmaf(v.w, wts.dw[wo + 3], a3);
+            }
+        if (dw_relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {  // the depthwise result is consumed at once: no C-long register array
+            o[j] = fmaf(a0, wts.pw[c * NP + j], o[j]);
+            o[j] = fmaf(a1, wts.pw[(c + 1) * NP + j], o[j]);
+            o[j] = fmaf(a2, wts.pw[(c + 2) * NP + j], o[j]);
+            o[j] = fmaf(a3, wts.pw[(c + 3) * NP + j], o[j]);
+        }
+    }
+    float* op = out.p + (size_t)f * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
+    const int N = out.C;
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+        if (j < N) op[j] = pw_relu ? fmaxf(o[j], 0.f) : o[j];
+}
+
+bool head_dwpw_supported(int C, int N, int stride) { return C == 64 && stride == 1 && N >= 1 && N <= 16; }
+size_t head_dwpw_weight_floats(int N) { const int np = N <= 8 ? 8 : 16; return 10 * 64 + 64 * (size_t)np + np; }
+
+template <int NP>
+static void launch_head_t(const TView& in, const TView& out, const float* host_w, int dw_relu, int pw_relu, int frames,
+                          cudaStream_t s) {
+    const int tiles_x = (out.W + 7) / 8, tiles_y = (out.H + 31) / 32;
+    const size_t smem = (size_t)34 * 10 * 68 * sizeof(float);
+    auto kern = head_dwpw_kernel<NP>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        configured[dev & 63] = true;
+    }
+    launch_pdl(kern, dim3(tiles_x * tiles_y * frames), dim3(256), smem, s, in, out, *reinterpret_cast<const HeadWeights<NP>*>(host_w),
+               dw_relu, pw_relu, tiles_x, tiles_y);
+}
+
+// host_w: [dw 9*64][dw bias 64][pw 64*NP (ci major, zero padded)][pw bias NP] with NP = 8 (N <= 8) or 16, HOST memory
+void launch_head_dwpw(const TView& in, const TView& out, const float* host_w, int dw_relu, int pw_relu, int frames,
+                      cudaStream_t s) {
+    if (out.C <= 8) launch_head_t<8>(in, out, host_w, dw_relu, pw_relu, frames, s);
+    else launch_head_t<16>(in, out, host_w, dw_relu, pw_relu, frames, s);
+}
+
 bool fused_dwpw_pix_supported(int C, int N, int stride) {
     if (N > 64) return false;
     if (C == 16 || C == 32) return stride == 1 || stride == 2;
