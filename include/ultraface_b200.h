@@ -73,11 +73,12 @@ typedef struct uf_config {
     int32_t device;          /* CUDA device ordinal */
     uint32_t max_batch;      /* largest n accepted by uf_infer_batch* (>=1) */
     uint32_t norm_preset;    /* UF_NORM_* */
-    uint32_t chunk;          /* frames per pipeline stage; 0 = auto */
+    uint32_t chunk;          /* frames per launch for device-resident input; 0 = auto */
     uint32_t slots;          /* pipeline depth (streams); 0 = auto */
     uint32_t resize_round_intermediate; /* 0 = image 0.24.x (f32 between passes); 1 = pre-0.24 */
     uint32_t flags;          /* UF_FLAG_* */
     uint32_t lanes;          /* concurrent calls served in parallel on one handle; 0 = auto (2) */
+    uint32_t host_chunk;     /* frames per pipeline stage for HOST input (H2D overlap); 0 = auto */
 } uf_config;
 
 #define UF_FLAG_FORCE_GENERIC 1u /* debug: run every conv through the generic direct kernel */

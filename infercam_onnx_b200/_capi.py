@@ -22,7 +22,7 @@ class uf_config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("onnx_path", C.c_char_p), ("net_w", C.c_uint32), ("net_h", C.c_uint32),
                 ("max_iou", C.c_float), ("min_confidence", C.c_float), ("device", C.c_int32),
                 ("max_batch", C.c_uint32), ("norm_preset", C.c_uint32), ("chunk", C.c_uint32), ("slots", C.c_uint32),
-                ("resize_round_intermediate", C.c_uint32), ("flags", C.c_uint32), ("lanes", C.c_uint32)]
+                ("resize_round_intermediate", C.c_uint32), ("flags", C.c_uint32), ("lanes", C.c_uint32), ("host_chunk", C.c_uint32)]
 
 
 class uf_info(C.Structure):

@@ -101,7 +101,6 @@ constexpr int DET_FAST = 128;  // detections per frame copied back with the coun
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
     uint8_t* d_in = nullptr;
     size_t d_in_cap = 0;
     uint8_t* d_resized = nullptr;
@@ -479,7 +478,6 @@ static void alloc_lane(uf_model& m, Lane& ln) {
     uint64_t ws = 0;
     for (auto& s : ln.slots) {
         CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         s.d_in_cap = (size_t)m.chunk * 640 * 480 * 3;
         CK(cudaMalloc(&s.d_in, s.d_in_cap));
         CK(cudaMalloc(&s.d_resized, (size_t)m.chunk * H * W * 3));
@@ -732,6 +730,12 @@ static void run_body(uf_model& m, Lane& ln, Slot& s, const U8View& input, uint32
     }
     const auto key = std::make_tuple(first, frames, stem_inside ? 1 : 0);
     auto it = s.graphs.find(key);
+    if (it == s.graphs.end() && s.graphs.size() >= 64) {  // a caller with ever-changing batch shapes: stop caching
+        run_cnn(m, s, input, frames);
+        run_tail_post(m, ln, s, first, frames);
+        CK(cudaGetLastError());
+        return;
+    }
     if (it == s.graphs.end()) {
         // first sighting: run eagerly (kernels set their function attributes on first use); capture on the second
         if (s.graph_seen[key]++ == 0) {
@@ -817,8 +821,7 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
         i = j;
     }
     U8View input{s.d_resized, (long long)out_frame, H, W};
-    static const bool copy_only = getenv("UF_DEBUG_COPY_ONLY") != nullptr;  // experiment: H2D pipeline alone
-    if (!copy_only) run_body(m, ln, s, input, first, (int)n);
+    run_body(m, ln, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
 }
 
@@ -924,7 +927,7 @@ static uf_model* load_model(const uf_config& cfg_in) {
     chunk = std::min(chunk, cfg.max_batch);
     m->chunk = chunk;
     m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 64 : 16));
-    if (const char* e = getenv("UF_HOST_CHUNK")) m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint32_t)atoi(e)));
+    if (cfg.host_chunk) m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, cfg.host_chunk));
     uint32_t nslots = cfg.slots ? cfg.slots : 4;
     const uint32_t nchunks = (cfg.max_batch + m->host_chunk - 1) / m->host_chunk;
     m->nslots = std::max<uint32_t>(1, std::min(nslots, nchunks));
@@ -959,7 +962,6 @@ uf_model::~uf_model() {
         cudaFree(s.d_in); cudaFree(s.d_resized); cudaFree(s.d_arena); cudaFree(s.d_dets); cudaFree(s.d_sel);
         cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_dets);
-        if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (auto& kv : taps) {

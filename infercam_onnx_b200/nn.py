@@ -76,7 +76,7 @@ class UltrafaceModel(InferModel):
     @classmethod
     def new(cls, variant: UltrafaceVariant, max_iou: float, min_confidence: float, *, onnx_path: Optional[str] = None,
             device: int = 0, max_batch: int = 1, norm_preset: int = _capi.UF_NORM_REFERENCE, chunk: int = 0,
-            slots: int = 0, flags: int = 0, resize_round_intermediate: bool = False, lanes: int = 0,
+            slots: int = 0, flags: int = 0, resize_round_intermediate: bool = False, lanes: int = 0, host_chunk: int = 0,
             size: Optional[Tuple[int, int]] = None) -> "UltrafaceModel":
         """`UltrafaceModel::new` (nn.rs:55). The keyword arguments are extra knobs the reference
         hard-codes (cache path, nn.rs:149-157) or does not have (device, batch); `size` overrides the
@@ -93,6 +93,7 @@ class UltrafaceModel(InferModel):
         cfg.chunk, cfg.slots, cfg.flags = chunk, slots, flags
         cfg.resize_round_intermediate = int(resize_round_intermediate)
         cfg.lanes = lanes
+        cfg.host_chunk = host_chunk
         h = C.c_void_p()
         _check(lib.uf_model_load_ex(C.byref(cfg), C.byref(h)))
         return cls(h.value, wh, max_iou, min_confidence)
