@@ -701,15 +701,20 @@ static void run_tail_post(uf_model& m, Lane& ln, Slot& s, uint32_t first, int fr
     }
     float* scores = ln.d_scores + (size_t)first * K * 2;
     float* boxes = ln.d_boxes + (size_t)first * K * 4;
-    {
-        ProfScope ps(m, s, "tail_softmax_decode", (uint64_t)frames * K * 6 * 4 * 2, (uint64_t)frames * K * 6 * 4 * 2, 0);
-        launch_tail(conf.p, loc.p, conf.frame_stride, loc.frame_stride, m.d_priors, K, m.plan.center_variance,
-                    m.plan.size_variance, scores, boxes, frames, s.stream);
-    }
-    {
+    PostBuffers pb{s.d_sort, (int)post_sort_scratch_elems(K), s.d_sel, s.d_dets, s.d_det_idx, s.d_counts};
+    if (m.cfg.flags & UF_FLAG_NO_FUSION) {
+        {
+            ProfScope ps(m, s, "tail_softmax_decode", (uint64_t)frames * K * 6 * 4 * 2, (uint64_t)frames * K * 6 * 4 * 2, 0);
+            launch_tail(conf.p, loc.p, conf.frame_stride, loc.frame_stride, m.d_priors, K, m.plan.center_variance,
+                        m.plan.size_variance, scores, boxes, frames, s.stream);
+        }
         ProfScope ps(m, s, "post_threshold_sort_nms", (uint64_t)frames * K * 6 * 4, (uint64_t)frames * K * 6 * 4, 0);
-        PostBuffers pb{s.d_sort, (int)post_sort_scratch_elems(K), s.d_sel, s.d_dets, s.d_det_idx, s.d_counts};
         launch_post(scores, boxes, K, m.cfg.min_confidence, m.cfg.max_iou, pb, frames, s.stream);
+    } else {
+        // one launch: each frame's CTA decodes its own priors, then thresholds / sorts / suppresses them
+        ProfScope ps(m, s, "tail_post_softmax_decode_nms", (uint64_t)frames * K * 6 * 4 * 2, (uint64_t)frames * K * 6 * 4 * 2, 0);
+        launch_tail_post(conf.p, loc.p, conf.frame_stride, loc.frame_stride, m.d_priors, m.plan.center_variance,
+                         m.plan.size_variance, scores, boxes, K, m.cfg.min_confidence, m.cfg.max_iou, pb, frames, s.stream);
     }
     CK(cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)frames * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaMemcpy2DAsync(s.h_dets, (size_t)DET_FAST * 5 * sizeof(float), s.d_dets, (size_t)K * 5 * sizeof(float),

@@ -136,6 +136,9 @@ struct PostBuffers {
 };
 void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
                  const PostBuffers& pb, int frames, cudaStream_t s);
+void launch_tail_post(const float* conf, const float* loc, long long conf_frame_stride, long long loc_frame_stride,
+                      const float* priors, float center_var, float size_var, float* scores, float* boxes, int K,
+                      float min_conf, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s);
 size_t post_sort_scratch_elems(int K);  // sort_cap for a given K
 int post_configure();                   // opt in to large dynamic smem; returns cudaError_t
 

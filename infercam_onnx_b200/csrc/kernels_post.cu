@@ -16,6 +16,20 @@
 
 namespace uf {
 
+__device__ __forceinline__ void tail_one(const float2 c, const float4 l, const float4 p, float cv, float sv,
+                                         float2& score, float4& box) {
+    const float m = fmaxf(c.x, c.y);
+    const float e0 = expf(c.x - m), e1 = expf(c.y - m);
+    const float s = e0 + e1;
+    score = make_float2(e0 / s, e1 / s);
+    const float cx = __fadd_rn(__fmul_rn(__fmul_rn(l.x, cv), p.z), p.x);
+    const float cy = __fadd_rn(__fmul_rn(__fmul_rn(l.y, cv), p.w), p.y);
+    const float w = __fmul_rn(expf(__fmul_rn(l.z, sv)), p.z);
+    const float h = __fmul_rn(expf(__fmul_rn(l.w, sv)), p.w);
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    box = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+}
+
 __global__ void __launch_bounds__(256)
 tail_kernel(const float* __restrict__ conf, const float* __restrict__ loc, long long conf_fs, long long loc_fs,
             const float* __restrict__ priors, int K, float cv, float sv, float* __restrict__ scores,
@@ -29,17 +43,11 @@ tail_kernel(const float* __restrict__ conf, const float* __restrict__ loc, long 
         const float2 c = *reinterpret_cast<const float2*>(conf + f * conf_fs + 2 * (size_t)k);
         const float4 l = *reinterpret_cast<const float4*>(loc + f * loc_fs + 4 * (size_t)k);
         const float4 p = __ldg(reinterpret_cast<const float4*>(priors) + k);
-        const float m = fmaxf(c.x, c.y);
-        const float e0 = expf(c.x - m), e1 = expf(c.y - m);
-        const float s = e0 + e1;
-        *reinterpret_cast<float2*>(scores + (size_t)idx * 2) = make_float2(e0 / s, e1 / s);
-        const float cx = __fadd_rn(__fmul_rn(__fmul_rn(l.x, cv), p.z), p.x);
-        const float cy = __fadd_rn(__fmul_rn(__fmul_rn(l.y, cv), p.w), p.y);
-        const float w = __fmul_rn(expf(__fmul_rn(l.z, sv)), p.z);
-        const float h = __fmul_rn(expf(__fmul_rn(l.w, sv)), p.w);
-        const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
-        *reinterpret_cast<float4*>(boxes + (size_t)idx * 4) =
-            make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+        float2 so;
+        float4 bo;
+        tail_one(c, l, p, cv, sv, so, bo);
+        *reinterpret_cast<float2*>(scores + (size_t)idx * 2) = so;
+        *reinterpret_cast<float4*>(boxes + (size_t)idx * 4) = bo;
     }
 }
 
@@ -99,9 +107,20 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, const float4 b, floa
     return iou(a, b) > max_iou;
 }
 
+// Raw head outputs for the fused tail (TAIL = true): the CTA first turns its frame's conf / loc rows into
+// scores / boxes (same arithmetic as tail_kernel), counting candidates on the way, then carries on with them.
+struct TailIn {
+    const float* conf;
+    const float* loc;
+    long long conf_fs, loc_fs;
+    const float* priors;
+    float cv, sv;
+};
+
+template <bool TAIL>
 __global__ void __launch_bounds__(PTHR)
-post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, int K, float min_conf,
-            float max_iou, PostBuffers pb) {
+post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float min_conf,
+            float max_iou, PostBuffers pb, TailIn tin) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // POST_SMEM_KEYS
     float4* cbox = reinterpret_cast<float4*>(skeys + POST_SMEM_KEYS);             // PT
@@ -118,13 +137,29 @@ post_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, i
     pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.x;
-    const float* sc = scores + (size_t)f * K * 2;
-    const float4* bx = reinterpret_cast<const float4*>(boxes + (size_t)f * K * 4);
+    float* sc = scores + (size_t)f * K * 2;
+    float4* bx = reinterpret_cast<float4*>(boxes + (size_t)f * K * 4);
     if (tid == 0) s_cnt = 0;
     __syncthreads();
     // 1. count (strict >, NaN compares false: nn.rs:127)
     int local = 0;
-    for (int k = tid; k < K; k += PTHR) local += sc[2 * (size_t)k + 1] > min_conf ? 1 : 0;
+    if (TAIL) {
+        const float* cf = tin.conf + (size_t)f * tin.conf_fs;
+        const float* lf = tin.loc + (size_t)f * tin.loc_fs;
+        for (int k = tid; k < K; k += PTHR) {
+            const float2 c = *reinterpret_cast<const float2*>(cf + 2 * (size_t)k);
+            const float4 l = *reinterpret_cast<const float4*>(lf + 4 * (size_t)k);
+            const float4 p = __ldg(reinterpret_cast<const float4*>(tin.priors) + k);
+            float2 so;
+            float4 bo;
+            tail_one(c, l, p, tin.cv, tin.sv, so, bo);
+            *reinterpret_cast<float2*>(sc + 2 * (size_t)k) = so;
+            bx[k] = bo;
+            local += so.y > min_conf ? 1 : 0;
+        }
+    } else {
+        for (int k = tid; k < K; k += PTHR) local += sc[2 * (size_t)k + 1] > min_conf ? 1 : 0;
+    }
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if (lane == 0 && local) atomicAdd(&s_cnt, local);
     __syncthreads();
@@ -247,7 +282,9 @@ static size_t post_smem_bytes() {
 }
 
 int post_configure() {
-    return (int)cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem_bytes());
+    int e = (int)cudaFuncSetAttribute(post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem_bytes());
+    if (e) return e;
+    return (int)cudaFuncSetAttribute(post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem_bytes());
 }
 
 size_t post_sort_scratch_elems(int K) {
@@ -258,7 +295,17 @@ size_t post_sort_scratch_elems(int K) {
 
 void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
                  const PostBuffers& pb, int frames, cudaStream_t s) {
-    launch_pdl(post_kernel, dim3(frames), dim3(PTHR), post_smem_bytes(), s, scores, boxes, K, min_conf, max_iou, pb);
+    launch_pdl(post_kernel<false>, dim3(frames), dim3(PTHR), post_smem_bytes(), s, const_cast<float*>(scores),
+               const_cast<float*>(boxes), K, min_conf, max_iou, pb, TailIn{});
+}
+
+// tail + post in one launch: scores / boxes are OUTPUTS here (kept for uf_raw_outputs and the hooks)
+void launch_tail_post(const float* conf, const float* loc, long long conf_frame_stride, long long loc_frame_stride,
+                      const float* priors, float center_var, float size_var, float* scores, float* boxes, int K,
+                      float min_conf, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s) {
+    TailIn tin{conf, loc, conf_frame_stride, loc_frame_stride, priors, center_var, size_var};
+    launch_pdl(post_kernel<true>, dim3(frames), dim3(PTHR), post_smem_bytes(), s, scores, boxes, K, min_conf, max_iou, pb,
+               tin);
 }
 
 }  // namespace uf

@@ -406,6 +406,6 @@ def test_profile_counters(model320):
     model320.profile_enable(False)
     assert model320.launch_count() - n0 == sum(s["launches"] for s in stats)
     names = {s["name"].split("[")[0] for s in stats}
-    assert {"resize_triangle", "stem_3x3s2_u8", "tail_softmax_decode", "post_threshold_sort_nms"} <= names
+    assert {"resize_triangle", "stem_3x3s2_u8", "tail_post_softmax_decode_nms"} <= names
     assert any(n.startswith("fused_dw3x3_pw1x1") for n in names) and "pointwise1x1_tcgen05" in names
     assert all(s["device_ms"] > 0 for s in stats)
