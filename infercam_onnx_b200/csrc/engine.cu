@@ -311,7 +311,8 @@ static void build_steps(uf_model& m) {
         st.flops = 2 * macs_of(op);
         st.impl = Impl::Generic;
         const bool dw = op.k == 3 && op.groups == op.cin && op.cin == op.cout && op.pad == 1 && op.dil == 1 &&
-                        (op.stride == 1 || op.stride == 2) && op.in2 < 0 && !in.is_input && view_vec_ok(in) && view_vec_ok(out);
+                        (op.stride == 1 || op.stride == 2) && op.in2 < 0 && !in.is_input && view_vec_ok(in) && view_vec_ok(out) &&
+                        op.cout <= 512;  // depthwise3x3_kernel: one CTA row of 128 threads x 4 channels
         const bool pw = op.k == 1 && op.groups == 1 && op.stride == 1 && op.pad == 0 && !in.is_input && view_vec_ok(in);
         const bool no_tc = m.cfg.flags & UF_FLAG_NO_TC;
         // the TMA view of the activations is 2-D [frames*H*W][K]: frames must be densely packed
@@ -571,17 +572,23 @@ static TapsEntry& get_taps(uf_model& m, int sw, int sh) {
     int vpitch = 0, hpitch = 0;
     up_i(e.v.left, &e.d_vleft); up_i(e.v.ntaps, &e.d_vn); up_f(padded(e.v, &vpitch), &e.d_vw);
     up_i(e.h.left, &e.d_hleft); up_i(e.h.ntaps, &e.d_hn); up_f(padded(e.h, &hpitch), &e.d_hw);
-    // CTA tile: 64 x 8 destination pixels unless the source span would not fit in shared memory
-    int tw = 64, th = 8;
+    // CTA tile: up to 320 x 8 destination pixels (a whole row of the 320-wide net: the source span is then the
+    // whole source row, every 32-lane trip of the vertical pass is full and nothing is read twice horizontally),
+    // narrowed until the f32 intermediate fits ~64 KB of shared memory (3 CTAs per SM)
+    int tw = std::min(m.plan.net_w, 320), th = 8;
+    while (tw % 4) ++tw;
     int cols = max_tile_span(e.h, tw);
-    while ((size_t)th * cols * 3 * sizeof(float) > 96 * 1024 && (tw > 8 || th > 1)) {
-        if (th > 1) th /= 2; else tw /= 2;
+    while ((size_t)th * cols * 3 * sizeof(float) > 64 * 1024 && (tw > 8 || th > 1)) {
+        if (tw > 64) tw = (tw / 2 + 3) / 4 * 4;  // keep th = 8 (the fast kernel's row count) as long as possible
+        else if (th > 1) th /= 2;
+        else tw /= 2;
         cols = max_tile_span(e.h, tw);
     }
     if ((size_t)th * cols * 3 * sizeof(float) > 200 * 1024)
         throw ArgError(UF_ERR_UNSUPPORTED, "resize ratio too large for the shared-memory tile (source " +
                                                std::to_string(sw) + "x" + std::to_string(sh) + ")");
-    e.dev = ResizeTapsDev{e.d_vleft, e.d_vn, e.d_vw, vpitch, e.d_hleft, e.d_hn, e.d_hw, hpitch, tw, th, cols};
+    e.dev = ResizeTapsDev{e.d_vleft, e.d_vn, e.d_vw, vpitch, e.d_hleft, e.d_hn, e.d_hw, hpitch, tw, th, cols,
+                          tw > 64 ? 64 : 0, tw > 64 ? max_tile_span(e.h, 64) : 0};
     return m.taps.emplace(key, std::move(e)).first->second;
 }
 

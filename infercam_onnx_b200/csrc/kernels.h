@@ -30,6 +30,7 @@ struct ResizeTapsDev {
     const int* vleft; const int* vn; const float* vw; int vmax;
     const int* hleft; const int* hn; const float* hw; int hmax;
     int tile_w, tile_h, max_cols;  // CTA tile of the destination and widest source span of a tile
+    int small_w, small_cols;       // narrower tile for launches too small to fill the GPU with wide ones (0: none)
 };
 
 // ---- K1: bit-exact triangle resize (nn.rs:74-80), frames HWC u8 -> HWC u8

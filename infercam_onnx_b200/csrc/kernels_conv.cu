@@ -152,71 +152,67 @@ void launch_stem(const U8View& in, const float* lut, const TView& out, const flo
 // thread = 4 channels x one column x a strip of R vertically adjacent outputs: the 9 weights (per channel, so
 // they cannot be warp-uniform constants) are loaded once, all (R-1)*S+3 input rows are fetched up front
 // (independent 16-byte loads in flight) and reused across the strip, halving the loads per output.
+// Grid: x = column tile, y = strip, z = frame; thread = (4-channel group, column) with the channel group fastest, so a
+// warp's 16-byte accesses are contiguous along C. No index division beyond one 32-bit tid / C4.
 template <int S, int R>
 __global__ void __launch_bounds__(128)
-depthwise3x3_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int relu,
-                    int strips, long long total) {
+depthwise3x3_kernel(TView in, TView out, const float* __restrict__ w, const float* __restrict__ b, int relu, int xt) {
     constexpr int NR = (R - 1) * S + 3;
     pdl_launch_dependents();
     pdl_wait();
     const int C4 = out.C >> 2;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C4) * 4;
-        long long t = idx / C4;
-        const int x = (int)(t % out.W);
-        t /= out.W;
-        const int ys = (int)(t % strips);
-        const int n = (int)(t / strips);
-        const int oy0 = ys * R;
-        const int iy0 = oy0 * S - 1, ix0 = x * S - 1;
-        float4 wv[9];
+    const int xl = (int)threadIdx.x / C4;
+    const int c = ((int)threadIdx.x - xl * C4) * 4;
+    const int x = (int)blockIdx.x * xt + xl;
+    if (xl >= xt || x >= out.W) return;
+    const int n = blockIdx.z;
+    const int oy0 = (int)blockIdx.y * R;
+    const int iy0 = oy0 * S - 1, ix0 = x * S - 1;
+    float4 wv[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) wv[k] = ldg4(w + k * out.C + c);
-        const float4 bias = ldg4(b + c);
-        const float* ip = in.p + (size_t)n * in.frame_stride + c;
-        float4 v[NR][3];
+    for (int k = 0; k < 9; ++k) wv[k] = ldg4(w + k * out.C + c);
+    const float4 bias = ldg4(b + c);
+    const float* ip = in.p + (size_t)n * in.frame_stride + c;
+    const bool cok[3] = {ix0 >= 0, true, ix0 + 2 < in.W};
+    float4 v[NR][3];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int iy = iy0 + r;
-            const bool rok = iy >= 0 && iy < in.H;
+    for (int r = 0; r < NR; ++r) {
+        const int iy = iy0 + r;
+        const bool rok = iy >= 0 && iy < in.H;
+        const float* rp = ip + ((long long)iy * in.W + ix0) * in.pix_stride;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+            v[r][kx] = (rok && cok[kx]) ? ld4(rp + kx * in.pix_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float* op = out.p + (size_t)n * out.frame_stride + ((size_t)oy0 * out.W + x) * out.pix_stride + c;
+#pragma unroll
+    for (int o = 0; o < R; ++o) {
+        if (oy0 + o >= out.H) break;
+        float4 acc = bias;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ix0 + kx;
-                v[r][kx] = (rok && ix >= 0 && ix < in.W) ? ld4(ip + ((size_t)iy * in.W + ix) * in.pix_stride)
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 a = v[o * S + ky][kx];
+                const float4 ww = wv[ky * 3 + kx];
+                acc.x = fmaf(a.x, ww.x, acc.x); acc.y = fmaf(a.y, ww.y, acc.y);
+                acc.z = fmaf(a.z, ww.z, acc.z); acc.w = fmaf(a.w, ww.w, acc.w);
             }
-        }
-#pragma unroll
-        for (int o = 0; o < R; ++o) {
-            const int oy = oy0 + o;
-            if (oy >= out.H) break;
-            float4 acc = bias;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float4 a = v[o * S + ky][kx];
-                    const float4 ww = wv[ky * 3 + kx];
-                    acc.x = fmaf(a.x, ww.x, acc.x); acc.y = fmaf(a.y, ww.y, acc.y);
-                    acc.z = fmaf(a.z, ww.z, acc.z); acc.w = fmaf(a.w, ww.w, acc.w);
-                }
-            if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-            st4(out.p + (size_t)n * out.frame_stride + ((size_t)oy * out.W + x) * out.pix_stride + c, acc);
-        }
+        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        st4(op + (size_t)o * out.W * out.pix_stride, acc);
     }
 }
 
 void launch_depthwise(const TView& in, const TView& out, const float* w_tc, const float* b, int stride, int relu,
                       int frames, cudaStream_t s) {
+    const int C4 = out.C / 4;
+    const int xt = 128 / C4;  // columns per CTA (the engine only routes C <= 512 here)
     if (stride == 1) {
-        const int strips = (out.H + 3) / 4;
-        const long long total = (long long)frames * strips * out.W * (out.C / 4);
-        launch_pdl(depthwise3x3_kernel<1, 4>, dim3(grid_for(total, 128, 64)), dim3(128), 0, s, in, out, w_tc, b, relu, strips, total);
+        dim3 grid((out.W + xt - 1) / xt, (out.H + 3) / 4, frames);
+        launch_pdl(depthwise3x3_kernel<1, 4>, grid, dim3(128), 0, s, in, out, w_tc, b, relu, xt);
     } else {
-        const int strips = (out.H + 1) / 2;
-        const long long total = (long long)frames * strips * out.W * (out.C / 4);
-        launch_pdl(depthwise3x3_kernel<2, 2>, dim3(grid_for(total, 128, 64)), dim3(128), 0, s, in, out, w_tc, b, relu, strips, total);
+        dim3 grid((out.W + xt - 1) / xt, (out.H + 1) / 2, frames);
+        launch_pdl(depthwise3x3_kernel<2, 2>, grid, dim3(128), 0, s, in, out, w_tc, b, relu, xt);
     }
 }
 

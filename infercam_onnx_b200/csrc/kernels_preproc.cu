@@ -68,7 +68,17 @@ resize_triangle_kernel(const uint8_t* __restrict__ src, long long src_frame_stri
 // same arithmetic, same order, but 4 source bytes per load in the vertical pass, no integer
 // divisions (block = 32 x tile_h threads: y indexes the tile row, x strides the columns) and the
 // u8 tile is staged in shared memory so the global stores are 4-byte words of contiguous rows.
-constexpr int RF_TW = 64, RF_TH = 8;
+constexpr int RF_TH = 8;  // tile rows; the tile width comes with the tap tables (ResizeTapsDev::tile_w, multiple of 4)
+
+// u8 -> f32, two ways, both exact: bytes 0/1 through I2F.U8 (conversion pipe, quarter rate), bytes 2/3 as
+// PRMT (build the float 2^23 + b) + FADD (remove 2^23) on the integer / FMA pipes. Splitting the work keeps either
+// pipe from being the limiter (measured: all-I2F 121 us, all-PRMT 132 us per 128 VGA frames).
+__device__ __forceinline__ void bytes_to_f32(unsigned u, float (&f)[4]) {
+    f[0] = (float)(u & 0xffu);
+    f[1] = (float)((u >> 8) & 0xffu);
+    f[2] = __fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7442)), -8388608.0f);
+    f[3] = __fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)), -8388608.0f);
+}
 
 template <bool TAPS4>  // TAPS4: every output has <= 4 taps per axis and the tables have a pitch of 4 (ratio <= 2)
 __global__ void __launch_bounds__(32 * RF_TH)
@@ -76,10 +86,11 @@ resize_triangle_fast_kernel(const uint8_t* __restrict__ src, long long src_frame
                             uint8_t* __restrict__ dst, long long dst_frame_stride, int dw, int dh,
                             ResizeTapsDev t, int pitch /* floats per tmp row, multiple of 4 */, int round_intermediate) {
     extern __shared__ __align__(16) float tmp_s[];                       // RF_TH x pitch
-    uint8_t* out_s = reinterpret_cast<uint8_t*>(tmp_s + RF_TH * pitch);  // RF_TH x RF_TW*3
+    uint8_t* out_s = reinterpret_cast<uint8_t*>(tmp_s + RF_TH * pitch);  // RF_TH x tile_w*3
     const int tx = threadIdx.x, r = threadIdx.y;
-    const int ox0 = blockIdx.x * RF_TW, oy0 = blockIdx.y * RF_TH;
-    const int ox1 = min(ox0 + RF_TW, dw);
+    const int TW = t.tile_w, opitch = TW * 3;
+    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * RF_TH;
+    const int ox1 = min(ox0 + TW, dw);
     const int tw = ox1 - ox0;
     const int oy = oy0 + r;
     const bool row_ok = oy < dh;
@@ -99,20 +110,31 @@ resize_triangle_fast_kernel(const uint8_t* __restrict__ src, long long src_frame
             const unsigned* r1 = reinterpret_cast<const unsigned*>(sp + (size_t)min(1, last) * row_bytes);
             const unsigned* r2 = reinterpret_cast<const unsigned*>(sp + (size_t)min(2, last) * row_bytes);
             const unsigned* r3 = reinterpret_cast<const unsigned*>(sp + (size_t)min(3, last) * row_bytes);
-            for (int wd = tx; wd < nwords; wd += 32) {
-                const unsigned u0 = __ldg(r0 + wd), u1 = __ldg(r1 + wd), u2 = __ldg(r2 + wd), u3 = __ldg(r3 + wd);
-                float a[4];
+            // 4 x 32 words per trip: the 16 loads go out before the first conversion, addresses are base + immediate
+            for (int wd0 = tx; wd0 < nwords; wd0 += 128) {
+                unsigned u[4][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sh8 = 8 * j;
-                    float acc = __fmul_rn((float)((u0 >> sh8) & 0xffu), wq.x);
-                    acc = __fadd_rn(acc, __fmul_rn((float)((u1 >> sh8) & 0xffu), wq.y));
-                    acc = __fadd_rn(acc, __fmul_rn((float)((u2 >> sh8) & 0xffu), wq.z));
-                    acc = __fadd_rn(acc, __fmul_rn((float)((u3 >> sh8) & 0xffu), wq.w));
-                    if (round_intermediate) acc = roundf(fminf(fmaxf(acc, 0.f), 255.f));
-                    a[j] = acc;
+                for (int k = 0; k < 4; ++k) {
+                    const int wd = min(wd0 + 32 * k, nwords - 1);  // clamped: always a valid address
+                    u[k][0] = __ldg(r0 + wd); u[k][1] = __ldg(r1 + wd); u[k][2] = __ldg(r2 + wd); u[k][3] = __ldg(r3 + wd);
                 }
-                *reinterpret_cast<float4*>(tmp_s + r * pitch + wd * 4) = make_float4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int wd = wd0 + 32 * k;
+                    if (wd >= nwords) break;
+                    float f0[4], f1[4], f2[4], f3[4], a[4];
+                    bytes_to_f32(u[k][0], f0); bytes_to_f32(u[k][1], f1); bytes_to_f32(u[k][2], f2); bytes_to_f32(u[k][3], f3);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float acc = __fmul_rn(f0[j], wq.x);
+                        acc = __fadd_rn(acc, __fmul_rn(f1[j], wq.y));
+                        acc = __fadd_rn(acc, __fmul_rn(f2[j], wq.z));
+                        acc = __fadd_rn(acc, __fmul_rn(f3[j], wq.w));
+                        if (round_intermediate) acc = roundf(fminf(fmaxf(acc, 0.f), 255.f));
+                        a[j] = acc;
+                    }
+                    *reinterpret_cast<float4*>(tmp_s + r * pitch + wd * 4) = make_float4(a[0], a[1], a[2], a[3]);
+                }
             }
         } else
         for (int wd = tx; wd < nwords; wd += 32) {
@@ -157,30 +179,36 @@ resize_triangle_fast_kernel(const uint8_t* __restrict__ src, long long src_frame
             a0 = a0 < 0.f ? 0.f : (a0 > 255.f ? 255.f : a0);
             a1 = a1 < 0.f ? 0.f : (a1 > 255.f ? 255.f : a1);
             a2 = a2 < 0.f ? 0.f : (a2 > 255.f ? 255.f : a2);
-            uint8_t* op = out_s + r * (RF_TW * 3) + oxl * 3;
+            uint8_t* op = out_s + r * opitch + oxl * 3;
             op[0] = (uint8_t)roundf(a0); op[1] = (uint8_t)roundf(a1); op[2] = (uint8_t)roundf(a2);
         }
     }
     __syncthreads();
     if (row_ok) {
         uint8_t* d = dst + (size_t)blockIdx.z * dst_frame_stride + ((size_t)oy * dw + ox0) * 3;
-        if (tw == RF_TW && ((reinterpret_cast<size_t>(d) & 3) == 0)) {
-            const unsigned* o4 = reinterpret_cast<const unsigned*>(out_s + r * (RF_TW * 3));
-            for (int i = tx; i < RF_TW * 3 / 4; i += 32) reinterpret_cast<unsigned*>(d)[i] = o4[i];
+        if ((tw & 3) == 0 && ((reinterpret_cast<size_t>(d) & 3) == 0)) {
+            const unsigned* o4 = reinterpret_cast<const unsigned*>(out_s + r * opitch);
+            for (int i = tx; i < tw * 3 / 4; i += 32) reinterpret_cast<unsigned*>(d)[i] = o4[i];
         } else {
-            for (int i = tx; i < tw * 3; i += 32) d[i] = out_s[r * (RF_TW * 3) + i];
+            for (int i = tx; i < tw * 3; i += 32) d[i] = out_s[r * opitch + i];
         }
     }
 }
 
 void launch_resize(const uint8_t* src, long long src_frame_stride, int sw, int sh, uint8_t* dst,
-                   long long dst_frame_stride, int dw, int dh, int frames, const ResizeTapsDev& t,
+                   long long dst_frame_stride, int dw, int dh, int frames, const ResizeTapsDev& t_in,
                    int round_intermediate, cudaStream_t s) {
+    ResizeTapsDev t = t_in;
+    // a handful of frames: wide tiles would leave most SMs idle, use the narrow ones
+    if (t.small_w > 0 && (long long)frames * ((dw + t.tile_w - 1) / t.tile_w) * ((dh + t.tile_h - 1) / t.tile_h) < 2 * 148) {
+        t.tile_w = t.small_w;
+        t.max_cols = t.small_cols;
+    }
     // fast path: rows and frames 4-byte aligned, CTA tile 64 x 8 as built by the engine
     const bool aligned = (sw % 4 == 0) && ((reinterpret_cast<size_t>(src) & 3) == 0) && (src_frame_stride % 4 == 0);
-    if (aligned && t.tile_w == RF_TW && t.tile_h == RF_TH) {
+    if (aligned && t.tile_w % 4 == 0 && t.tile_h == RF_TH) {
         const int pitch = ((t.max_cols + 4) * 3 + 3) / 4 * 4;  // +4: col0 is aligned down by up to 3 pixels
-        const size_t smem = (size_t)RF_TH * pitch * sizeof(float) + (size_t)RF_TH * RF_TW * 3;
+        const size_t smem = (size_t)RF_TH * pitch * sizeof(float) + (size_t)RF_TH * t.tile_w * 3;
         if (smem <= 200 * 1024) {
             static bool configured[64] = {};
             int dev = 0;
@@ -190,7 +218,7 @@ void launch_resize(const uint8_t* src, long long src_frame_stride, int sw, int s
                 cudaFuncSetAttribute(resize_triangle_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
                 configured[dev & 63] = true;
             }
-            dim3 grid((dw + RF_TW - 1) / RF_TW, (dh + RF_TH - 1) / RF_TH, frames);
+            dim3 grid((dw + t.tile_w - 1) / t.tile_w, (dh + RF_TH - 1) / RF_TH, frames);
             if (t.vmax == 4 && t.hmax == 4)  // tables are padded to a pitch of 4 by the engine
                 resize_triangle_fast_kernel<true><<<grid, dim3(32, RF_TH), smem, s>>>(src, src_frame_stride, sw, sh, dst,
                                                                                       dst_frame_stride, dw, dh, t, pitch,
