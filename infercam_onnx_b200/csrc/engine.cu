@@ -346,9 +346,13 @@ static void build_steps(uf_model& m) {
                     // so it is opt-in (UF_FLAG_FUSE_DW_TC) until the taps arrive by TMA
                     const bool dw_tc = split_tc && uses[op.out] == 1 && !out.in_concat && op.cout % 32 == 0 &&
                                        (m.cfg.flags & UF_FLAG_FUSE_DW_TC) && !(m.cfg.flags & UF_FLAG_NO_FUSION);
-                    if ((fusable && !split_tc) || dw_tc) {
-                        const bool head = pix && !no_tc && head_dwpw_supported(op.cout, nx.cout, op.stride);
-                        st.impl = dw_tc ? Impl::FusedDwTC : tma ? Impl::FusedTma : head ? Impl::FusedHead : pix ? Impl::FusedPix : Impl::FusedDwPw;
+                    // SSD heads on the wide, tiny maps (128 / 256 channels -> <= 16): one constant-weight SIMT kernel instead
+                    // of depthwise + GEMM, whose two launches are all fixed cost at that size
+                    const bool head_wide = nx_pw && uses[op.out] == 1 && !out.in_concat && !no_tc && op.cout > 64 &&
+                                           head_dwpw_supported(op.cout, nx.cout, op.stride) && !(m.cfg.flags & UF_FLAG_FUSE_DW_TC);
+                    if ((fusable && !split_tc) || dw_tc || head_wide) {
+                        const bool head = head_wide || (pix && !no_tc && head_dwpw_supported(op.cout, nx.cout, op.stride));
+                        st.impl = dw_tc ? Impl::FusedDwTC : head_wide ? Impl::FusedHead : tma ? Impl::FusedTma : head ? Impl::FusedHead : pix ? Impl::FusedPix : Impl::FusedDwPw;
                         st.op2 = (int)i + 1;
                         st.alg_bytes += bytes_of(nx.in) + bytes_of(nx.out);
                         st.min_bytes = bytes_of(op.in) + bytes_of(nx.out);

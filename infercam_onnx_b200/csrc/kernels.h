@@ -66,7 +66,7 @@ void launch_fused_dwpw_pix(const TView& in, const TView& out, const float* dw_w_
                            int frames, cudaStream_t s);
 // SSD heads on the 64-channel map: dw3x3 -> 1x1 (N <= 16) with all weights as kernel-parameter constants
 bool head_dwpw_supported(int C, int N, int stride);
-size_t head_dwpw_weight_floats(int N);
+size_t head_dwpw_weight_floats(int C, int N);
 void launch_head_dwpw(const TView& in, const TView& out, const float* host_w, int dw_relu, int pw_relu, int frames,
                       cudaStream_t s);
 // K6b warp-per-pixel 3x3 (stride 1, pad = dil) for many input channels and <= 16 outputs (last SSD heads)

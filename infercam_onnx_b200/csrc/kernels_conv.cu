@@ -617,6 +617,36 @@ void launch_conv3x3_warp(const TView& in, const TView& out, const float* w_kkio,
 #undef UF_W
 }
 
+// Stage an IH x IW pixel tile (C4 float4 channel groups per pixel, top-left map coordinate (gy0, gx0)) into shared
+// memory at a pixel pitch of P floats, zeros outside the map. U independent loads are issued before the first
+// store: with one load per trip the loop is a chain of L2 latencies (measured 11 us per CTA on the 128-channel
+// heads), which is what bounds these small-tile kernels.
+template <int U>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ ip, const TView& in, float* __restrict__ s_in, int gy0,
+                                           int gx0, int IH, int IW, int C4, int P, int tid, int nthr) {
+    const int total = IH * IW * C4;
+    for (int i0 = tid; i0 < total; i0 += U * nthr) {
+        float4 v[U];
+        int so[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * nthr;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            so[u] = -1;
+            if (i < total) {
+                const int pix = i / C4, q = i - pix * C4;
+                const int py = pix / IW, px = pix - py * IW;
+                const int gy = gy0 + py, gx = gx0 + px;
+                so[u] = pix * P + q * 4;
+                if (gy >= 0 && gy < in.H && gx >= 0 && gx < in.W) v[u] = ld4(ip + ((size_t)gy * in.W + gx) * in.pix_stride + q * 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (so[u] >= 0) st4(s_in + so[u], v[u]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4+K5 fused, pixel-per-thread form for C <= 64: CTA = 8 x TY output pixels of one frame. The
 // input tile (+1 halo, stride-scaled) is staged in shared memory with coalesced float4 loads and a
@@ -654,14 +684,7 @@ fused_dwpw_pix_kernel(TView in, TView out, const float* __restrict__ dw_w, const
     for (int i = tid; i < n_pad; i += NTHR) s_pb[i] = i < N ? pw_b[i] : 0.f;
     pdl_wait();  // weights above are static; the input tile below is the predecessor's output
     const float* ip = in.p + (size_t)f * in.frame_stride;
-    for (int i = tid; i < IH * IW * C4; i += NTHR) {
-        const int pix = i / C4, q = i - pix * C4;   // constants: shifts
-        const int py = pix / IW, px = pix - py * IW;
-        const int gy = gy0 + py, gx = gx0 + px;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < in.H && gx >= 0 && gx < in.W) v = ld4(ip + ((size_t)gy * in.W + gx) * in.pix_stride + q * 4);
-        st4(s_in + pix * P + q * 4, v);
-    }
+    stage_tile<4>(ip, in, s_in, gy0, gx0, IH, IW, C4, P, tid, NTHR);
     __syncthreads();
     const int tx = tid % TX, ty = tid / TX;
     const int ox = x0 + tx, oy = y0 + ty;
@@ -714,56 +737,32 @@ fused_dwpw_pix_kernel(TView in, TView out, const float* __restrict__ dw_w, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// SSD `sep` heads on the 64-channel map (dw3x3 + ReLU -> 1x1 64 -> 6 / 12): same tile scheme as above, but the
-// depthwise and pointwise weights are kernel-parameter constants (6.8 KB), so the arithmetic is pure FFMA with
-// constant-bank operands and shared memory only serves the input tile.
+// SSD `sep` heads (dw3x3 + ReLU -> 1x1 C -> 4..16) on the 64 / 128 / 256-channel maps: same tile scheme as above, but
+// the depthwise and pointwise weights are kernel-parameter constants (6.8 - 27 KB), so the arithmetic is pure FFMA
+// with constant-bank operands and shared memory only serves the input tile. For C > 64 the channels are split over
+// SPLIT thread groups (each with compile-time channel indices, hence the PART template recursion) whose partial
+// sums meet in shared memory: the wide heads sit on tiny maps, and a pixel-per-thread CTA alone would leave the SM
+// almost empty. Replaces depthwise kernel + tensor-core GEMM (2 launches, ~36 us) for those layers.
 // ---------------------------------------------------------------------------------------------
-template <int NP>
+template <int C, int NP>
 struct HeadWeights {
-    float dw[9 * 64];
-    float dwb[64];
-    float pw[64 * NP];  // [ci][n], zero padded to NP outputs
+    float dw[9 * C];
+    float dwb[C];
+    float pw[C * NP];  // [ci][n], zero padded to NP outputs
     float pwb[NP];
 };
 
-template <int NP>
-__global__ void __launch_bounds__(256)
-head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<NP> wts, int dw_relu, int pw_relu, int tiles_x,
-                 int tiles_y) {
-    constexpr int C = 64, TX = 8, TY = 32, IW = TX + 2, IH = TY + 2, P = C + 4, NTHR = TX * TY, C4 = C / 4;
-    extern __shared__ __align__(16) float s_in[];  // IH*IW*P
-    pdl_launch_dependents();
-    pdl_wait();
-    const int tid = threadIdx.x;
-    int bid = blockIdx.x;
-    const int txi = bid % tiles_x; bid /= tiles_x;
-    const int tyi = bid % tiles_y;
-    const int f = bid / tiles_y;
-    const int x0 = txi * TX, y0 = tyi * TY;
-    const float* ip = in.p + (size_t)f * in.frame_stride;
-    for (int i = tid; i < IH * IW * C4; i += NTHR) {
-        const int pix = i / C4, q = i - pix * C4;
-        const int py = pix / IW, px = pix - py * IW;
-        const int gy = y0 - 1 + py, gx = x0 - 1 + px;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < in.H && gx >= 0 && gx < in.W) v = ld4(ip + ((size_t)gy * in.W + gx) * in.pix_stride + q * 4);
-        st4(s_in + pix * P + q * 4, v);
-    }
-    __syncthreads();
-    const int tx = tid % TX, ty = tid / TX;
-    const int ox = x0 + tx, oy = y0 + ty;
-    if (ox >= out.W || oy >= out.H) return;
-    float o[NP];
+template <int C, int NP, int IW, int SPLIT, int PART>
+__device__ __forceinline__ void head_part(const float* __restrict__ s_px, const HeadWeights<C, NP>& wts, int dw_relu, float (&o)[NP]) {
+    constexpr int P = C + 4, C0 = PART * (C / SPLIT), C1 = C0 + C / SPLIT;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) o[j] = wts.pwb[j];
-#pragma unroll
-    for (int c = 0; c < C; c += 4) {
+    for (int c = C0; c < C1; c += 4) {
         float a0 = wts.dwb[c], a1 = wts.dwb[c + 1], a2 = wts.dwb[c + 2], a3 = wts.dwb[c + 3];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const float4 v = ld4(s_in + ((ty + ky) * IW + tx + kx) * P + c);
+                const float4 v = ld4(s_px + (ky * IW + kx) * P + c);
                 const int wo = (ky * 3 + kx) * C + c;
                 a0 = fmaf(v.x, wts.dw[wo], a0); a1 = fmaf(v.y, wts.dw[wo + 1], a1);
                 a2 = fmaf(v.z, wts.dw[wo + 2], a2); a3 = fmaf(v.w, wts.dw[wo + 3], a3);
@@ -777,6 +776,58 @@ head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<NP> wt
             o[j] = fmaf(a3, wts.pw[(c + 3) * NP + j], o[j]);
         }
     }
+}
+
+template <int C, int NP, int TX, int TY, int SPLIT>
+__global__ void __launch_bounds__(((TX * TY + 31) / 32 * 32) * SPLIT)
+head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<C, NP> wts, int dw_relu, int pw_relu, int tiles_x,
+                 int tiles_y) {
+    constexpr int IW = TX + 2, IH = TY + 2, P = C + 4, GT = (TX * TY + 31) / 32 * 32, NTHR = GT * SPLIT, C4 = C / 4;
+    extern __shared__ __align__(16) float s_in[];  // IH*IW*P, then (SPLIT-1) * TX*TY * NP partial sums
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int txi = bid % tiles_x; bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int f = bid / tiles_y;
+    const int x0 = txi * TX, y0 = tyi * TY;
+    const float* ip = in.p + (size_t)f * in.frame_stride;
+    stage_tile<8>(ip, in, s_in, y0 - 1, x0 - 1, IH, IW, C4, P, tid, NTHR);
+    __syncthreads();
+    const int part = tid / GT, lt = tid - part * GT;  // part is warp-uniform: GT is a multiple of 32
+    const int tx = lt % TX, ty = lt / TX;
+    const int ox = x0 + tx, oy = y0 + ty;
+    const bool active = lt < TX * TY && ox < out.W && oy < out.H;
+    float o[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) o[j] = 0.f;
+    if (active) {
+        const float* s_px = s_in + (ty * IW + tx) * P;
+        if (part == 0) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) o[j] = wts.pwb[j];
+            head_part<C, NP, IW, SPLIT, 0>(s_px, wts, dw_relu, o);
+        }
+        if (SPLIT > 1 && part == 1) head_part<C, NP, IW, SPLIT, (SPLIT > 1 ? 1 : 0)>(s_px, wts, dw_relu, o);
+        if (SPLIT > 2 && part == 2) head_part<C, NP, IW, SPLIT, (SPLIT > 2 ? 2 : 0)>(s_px, wts, dw_relu, o);
+        if (SPLIT > 3 && part == 3) head_part<C, NP, IW, SPLIT, (SPLIT > 3 ? 3 : 0)>(s_px, wts, dw_relu, o);
+    }
+    if (SPLIT > 1) {
+        float* s_part = s_in + IH * IW * P;  // [SPLIT-1][TX*TY][NP]
+        if (active && part > 0) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) s_part[((part - 1) * TX * TY + lt) * NP + j] = o[j];
+        }
+        __syncthreads();
+        if (active && part == 0) {
+#pragma unroll
+            for (int sp = 0; sp < SPLIT - 1; ++sp)
+#pragma unroll
+                for (int j = 0; j < NP; ++j) o[j] += s_part[(sp * TX * TY + lt) * NP + j];
+        }
+    }
+    if (!active || part != 0) return;
     float* op = out.p + (size_t)f * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
     const int N = out.C;
 #pragma unroll
@@ -784,31 +835,40 @@ head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<NP> wt
         if (j < N) op[j] = pw_relu ? fmaxf(o[j], 0.f) : o[j];
 }
 
-bool head_dwpw_supported(int C, int N, int stride) { return C == 64 && stride == 1 && N >= 1 && N <= 16; }
-size_t head_dwpw_weight_floats(int N) { const int np = N <= 8 ? 8 : 16; return 10 * 64 + 64 * (size_t)np + np; }
+bool head_dwpw_supported(int C, int N, int stride) { return (C == 64 || C == 128 || C == 256) && stride == 1 && N >= 1 && N <= 16; }
+size_t head_dwpw_weight_floats(int C, int N) { const int np = N <= 8 ? 8 : 16; return 10 * (size_t)C + (size_t)C * np + np; }
 
-template <int NP>
+template <int C, int NP, int TX, int TY, int SPLIT>
 static void launch_head_t(const TView& in, const TView& out, const float* host_w, int dw_relu, int pw_relu, int frames,
                           cudaStream_t s) {
-    const int tiles_x = (out.W + 7) / 8, tiles_y = (out.H + 31) / 32;
-    const size_t smem = (size_t)34 * 10 * 68 * sizeof(float);
-    auto kern = head_dwpw_kernel<NP>;
+    static_assert(sizeof(HeadWeights<C, NP>) + 2 * sizeof(TView) + 64 <= 32764, "kernel parameter space exceeded");
+    constexpr int GT = (TX * TY + 31) / 32 * 32;
+    const int tiles_x = (out.W + TX - 1) / TX, tiles_y = (out.H + TY - 1) / TY;
+    const size_t smem = ((size_t)(TY + 2) * (TX + 2) * (C + 4) + (size_t)(SPLIT - 1) * TX * TY * NP) * sizeof(float);
+    auto kern = head_dwpw_kernel<C, NP, TX, TY, SPLIT>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         configured[dev & 63] = true;
     }
-    launch_pdl(kern, dim3(tiles_x * tiles_y * frames), dim3(256), smem, s, in, out, *reinterpret_cast<const HeadWeights<NP>*>(host_w),
-               dw_relu, pw_relu, tiles_x, tiles_y);
+    launch_pdl(kern, dim3(tiles_x * tiles_y * frames), dim3(GT * SPLIT), smem, s, in, out,
+               *reinterpret_cast<const HeadWeights<C, NP>*>(host_w), dw_relu, pw_relu, tiles_x, tiles_y);
 }
 
-// host_w: [dw 9*64][dw bias 64][pw 64*NP (ci major, zero padded)][pw bias NP] with NP = 8 (N <= 8) or 16, HOST memory
+// host_w: [dw 9*C][dw bias C][pw C*NP (ci major, zero padded)][pw bias NP] with NP = 8 (N <= 8) or 16, HOST memory
 void launch_head_dwpw(const TView& in, const TView& out, const float* host_w, int dw_relu, int pw_relu, int frames,
                       cudaStream_t s) {
-    if (out.C <= 8) launch_head_t<8>(in, out, host_w, dw_relu, pw_relu, frames, s);
-    else launch_head_t<16>(in, out, host_w, dw_relu, pw_relu, frames, s);
+#define UF_H(CC, TXX, TYY, SS)                                                                          \
+    do {                                                                                                \
+        if (out.C <= 8) launch_head_t<CC, 8, TXX, TYY, SS>(in, out, host_w, dw_relu, pw_relu, frames, s); \
+        else launch_head_t<CC, 16, TXX, TYY, SS>(in, out, host_w, dw_relu, pw_relu, frames, s);           \
+    } while (0)
+    if (in.C == 64) UF_H(64, 8, 32, 1);
+    else if (in.C == 128) UF_H(128, 20, 5, 2);   // 20x15 map: three tiles of 100 pixels, two channel halves
+    else if (in.C == 256) UF_H(256, 10, 8, 4);   // 10x8 map: one tile, four channel quarters
+#undef UF_H
 }
 
 bool fused_dwpw_pix_supported(int C, int N, int stride) {
@@ -880,14 +940,7 @@ small_dense3x3_kernel(TView in, TView out, const __grid_constant__ SmallDenseWei
     const int x0 = txi * SD_TX, y0 = tyi * SD_TY;
     const int IW = SD_TX + 2 * dil, IH = SD_TY + 2 * dil;
     const float* ip = in.p + (size_t)f * in.frame_stride;
-    for (int i = tid; i < IH * IW * C4; i += NTHR) {
-        const int pix = i / C4, q = i - pix * C4;
-        const int py = pix / IW, px = pix - py * IW;
-        const int gy = y0 - dil + py, gx = x0 - dil + px;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < in.H && gx >= 0 && gx < in.W) v = ld4(ip + ((size_t)gy * in.W + gx) * in.pix_stride + q * 4);
-        st4(s_in + pix * P + q * 4, v);
-    }
+    stage_tile<4>(ip, in, s_in, y0 - dil, x0 - dil, IH, IW, C4, P, tid, NTHR);
     __syncthreads();
     const int tx = tid % SD_TX, ty = tid / SD_TX;
     const int ox = x0 + tx, oy = y0 + ty;
