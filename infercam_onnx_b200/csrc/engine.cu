@@ -51,7 +51,7 @@ struct ArgError : public std::exception {
 
 static thread_local std::string g_last_error;
 
-enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwTC, FusedDwPw, FusedPix, FusedHead, FusedTma, SmallDense, Conv3x3Warp, Add, Relu, Copy };
+enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwTC, FusedDwPw, FusedPix, FusedHead, FusedHead2, FusedTma, SmallDense, Conv3x3Warp, Add, Relu, Copy };
 
 static const char* impl_name(Impl i) {
     switch (i) {
@@ -64,6 +64,7 @@ static const char* impl_name(Impl i) {
         case Impl::FusedDwPw: return "fused_dw3x3_pw1x1";
         case Impl::FusedPix: return "fused_dw3x3_pw1x1_pix";
         case Impl::FusedHead: return "fused_dw3x3_pw1x1_head";
+        case Impl::FusedHead2: return "fused_dw3x3_pw1x1_head_pair";
         case Impl::FusedTma: return "fused_dw3x3_pw1x1_tma";
         case Impl::Conv3x3Warp: return "conv3x3_warp";
         case Impl::SmallDense: return "small_dense3x3";
@@ -77,6 +78,7 @@ static const char* impl_name(Impl i) {
 struct Step {
     Impl impl = Impl::Generic;
     int op = -1, op2 = -1;  // plan op indices (op2: the pointwise of a fused pair)
+    int op3 = -1, op4 = -1;  // FusedHead2: depthwise / pointwise of the second head on the same input
     uint64_t alg_bytes = 0;  // SURVEY.md §8(d) convention: sum over Conv nodes of (in+out)*4, per frame
     uint64_t min_bytes = 0;  // compulsory traffic of this launch (fusion removes the intermediate), per frame
     uint64_t flops = 0;      // per frame
@@ -358,6 +360,24 @@ static void build_steps(uf_model& m) {
                         st.min_bytes = bytes_of(op.in) + bytes_of(nx.out);
                         st.flops += 2 * macs_of(nx);
                         m.tensor_readable[op.out] = 0;
+                        // class + box heads of one map (same input, <= 8 and <= 16 outputs): one launch, one staged tile
+                        if (st.impl == Impl::FusedHead && !m.steps.empty() && m.steps.back().impl == Impl::FusedHead) {
+                            Step& pv = m.steps.back();
+                            const Op& pdw = p.ops[pv.op];
+                            const Op& ppw = p.ops[pv.op2];
+                            if (pdw.in == op.in && head2_dwpw_supported(op.cout, std::min(ppw.cout, nx.cout), std::max(ppw.cout, nx.cout)) &&
+                                std::min(ppw.cout, nx.cout) <= 8) {
+                                pv.impl = Impl::FusedHead2;
+                                pv.op3 = (int)i;
+                                pv.op4 = (int)i + 1;
+                                if (nx.cout < ppw.cout) { std::swap(pv.op, pv.op3); std::swap(pv.op2, pv.op4); }  // head A = the narrow one
+                                pv.alg_bytes += st.alg_bytes;
+                                pv.min_bytes += bytes_of(nx.out);
+                                pv.flops += st.flops;
+                                ++i;
+                                continue;
+                            }
+                        }
                         m.steps.push_back(st);
                         ++i;
                         continue;
@@ -423,13 +443,16 @@ static void build_param_weights(uf_model& m) {
             for (int co = 0; co < co_n; ++co) st.host_w[(size_t)k * k * ci_n * co_n + co] = op.b[co];
             continue;
         }
-        if (st.impl != Impl::FusedTma && st.impl != Impl::FusedHead) continue;
-        const Op& dw = m.plan.ops[st.op];
-        const Op& pw = m.plan.ops[st.op2];
+        if (st.impl != Impl::FusedTma && st.impl != Impl::FusedHead && st.impl != Impl::FusedHead2) continue;
+        for (int half = 0; half < (st.impl == Impl::FusedHead2 ? 2 : 1); ++half) {
+        const Op& dw = m.plan.ops[half ? st.op3 : st.op];
+        const Op& pw = m.plan.ops[half ? st.op4 : st.op2];
         const int C = dw.cout, Nreal = pw.cout;
-        const int N = st.impl == Impl::FusedHead ? (Nreal <= 8 ? 8 : 16) : Nreal;  // heads: outputs zero-padded to 8 / 16
-        st.host_w.assign(fused_dwpw_tma_weight_floats(C, N), 0.f);
-        float* p = st.host_w.data();
+        // heads: outputs zero-padded to 8 / 16 (a pair: 8 for the first head, 16 for the second)
+        const int N = st.impl == Impl::FusedHead2 ? (half ? 16 : 8) : st.impl == Impl::FusedHead ? (Nreal <= 8 ? 8 : 16) : Nreal;
+        const size_t base = st.host_w.size();
+        st.host_w.resize(base + fused_dwpw_tma_weight_floats(C, N), 0.f);
+        float* p = st.host_w.data() + base;
         for (int t = 0; t < 9; ++t)
             for (int c = 0; c < C; ++c) p[t * C + c] = dw.w[(size_t)c * 9 + t];  // ONNX [c][1][ky][kx]
         for (int c = 0; c < C; ++c) p[9 * C + c] = dw.b[c];
@@ -437,6 +460,7 @@ static void build_param_weights(uf_model& m) {
         for (int ci = 0; ci < C; ++ci)
             for (int n = 0; n < Nreal; ++n) q[ci * N + n] = pw.w[(size_t)n * C + ci];  // ONNX [n][ci][1][1]
         for (int n = 0; n < Nreal; ++n) q[C * N + n] = pw.b[n];
+        }
     }
 }
 
@@ -658,6 +682,14 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                 const Op& pw = p.ops[st.op2];
                 TView o2 = make_view(m, s, pw.out);
                 launch_head_dwpw(in, o2, st.host_w.data(), op.relu, pw.relu, frames, s.stream);
+                break;
+            }
+            case Impl::FusedHead2: {
+                const Op& pwa = p.ops[st.op2];
+                const Op& dwb = p.ops[st.op3];
+                const Op& pwb = p.ops[st.op4];
+                const int relu_bits = (op.relu ? 1 : 0) | (pwa.relu ? 2 : 0) | (dwb.relu ? 4 : 0) | (pwb.relu ? 8 : 0);
+                launch_head2_dwpw(in, make_view(m, s, pwa.out), make_view(m, s, pwb.out), st.host_w.data(), relu_bits, frames, s.stream);
                 break;
             }
             case Impl::FusedTma: {

@@ -67,6 +67,10 @@ void launch_fused_dwpw_pix(const TView& in, const TView& out, const float* dw_w_
 // SSD heads on the 64-channel map: dw3x3 -> 1x1 (N <= 16) with all weights as kernel-parameter constants
 bool head_dwpw_supported(int C, int N, int stride);
 size_t head_dwpw_weight_floats(int C, int N);
+// two heads (<= 8 and <= 16 outputs) of the same input in one launch, C = 64 / 128
+bool head2_dwpw_supported(int C, int Na, int Nb);
+void launch_head2_dwpw(const TView& in, const TView& out_a, const TView& out_b, const float* host_w, int relu_bits, int frames,
+                       cudaStream_t s);
 void launch_head_dwpw(const TView& in, const TView& out, const float* host_w, int dw_relu, int pw_relu, int frames,
                       cudaStream_t s);
 // K6b warp-per-pixel 3x3 (stride 1, pad = dil) for many input channels and <= 16 outputs (last SSD heads)

@@ -778,23 +778,13 @@ __device__ __forceinline__ void head_part(const float* __restrict__ s_px, const 
     }
 }
 
+// one head on the staged tile: every thread of the CTA must call this (it contains a barrier when SPLIT > 1)
 template <int C, int NP, int TX, int TY, int SPLIT>
-__global__ void __launch_bounds__(((TX * TY + 31) / 32 * 32) * SPLIT)
-head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<C, NP> wts, int dw_relu, int pw_relu, int tiles_x,
-                 int tiles_y) {
-    constexpr int IW = TX + 2, IH = TY + 2, P = C + 4, GT = (TX * TY + 31) / 32 * 32, NTHR = GT * SPLIT, C4 = C / 4;
-    extern __shared__ __align__(16) float s_in[];  // IH*IW*P, then (SPLIT-1) * TX*TY * NP partial sums
-    pdl_launch_dependents();
-    pdl_wait();
+__device__ __forceinline__ void head_compute(const float* __restrict__ s_in, float* __restrict__ s_part,
+                                             const HeadWeights<C, NP>& wts, int dw_relu, int pw_relu, const TView& out, int f,
+                                             int x0, int y0) {
+    constexpr int IW = TX + 2, P = C + 4, GT = (TX * TY + 31) / 32 * 32;
     const int tid = threadIdx.x;
-    int bid = blockIdx.x;
-    const int txi = bid % tiles_x; bid /= tiles_x;
-    const int tyi = bid % tiles_y;
-    const int f = bid / tiles_y;
-    const int x0 = txi * TX, y0 = tyi * TY;
-    const float* ip = in.p + (size_t)f * in.frame_stride;
-    stage_tile<8>(ip, in, s_in, y0 - 1, x0 - 1, IH, IW, C4, P, tid, NTHR);
-    __syncthreads();
     const int part = tid / GT, lt = tid - part * GT;  // part is warp-uniform: GT is a multiple of 32
     const int tx = lt % TX, ty = lt / TX;
     const int ox = x0 + tx, oy = y0 + ty;
@@ -813,8 +803,7 @@ head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<C, NP>
         if (SPLIT > 2 && part == 2) head_part<C, NP, IW, SPLIT, (SPLIT > 2 ? 2 : 0)>(s_px, wts, dw_relu, o);
         if (SPLIT > 3 && part == 3) head_part<C, NP, IW, SPLIT, (SPLIT > 3 ? 3 : 0)>(s_px, wts, dw_relu, o);
     }
-    if (SPLIT > 1) {
-        float* s_part = s_in + IH * IW * P;  // [SPLIT-1][TX*TY][NP]
+    if (SPLIT > 1) {  // s_part: [SPLIT-1][TX*TY][NP]
         if (active && part > 0) {
 #pragma unroll
             for (int j = 0; j < NP; ++j) s_part[((part - 1) * TX * TY + lt) * NP + j] = o[j];
@@ -833,6 +822,52 @@ head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<C, NP>
 #pragma unroll
     for (int j = 0; j < NP; ++j)
         if (j < N) op[j] = pw_relu ? fmaxf(o[j], 0.f) : o[j];
+}
+
+template <int C, int NP, int TX, int TY, int SPLIT>
+__global__ void __launch_bounds__(((TX * TY + 31) / 32 * 32) * SPLIT)
+head_dwpw_kernel(TView in, TView out, const __grid_constant__ HeadWeights<C, NP> wts, int dw_relu, int pw_relu, int tiles_x,
+                 int tiles_y) {
+    constexpr int IW = TX + 2, IH = TY + 2, P = C + 4, NTHR = ((TX * TY + 31) / 32 * 32) * SPLIT, C4 = C / 4;
+    extern __shared__ __align__(16) float s_in[];  // IH*IW*P, then (SPLIT-1) * TX*TY * NP partial sums
+    pdl_launch_dependents();
+    pdl_wait();
+    int bid = blockIdx.x;
+    const int txi = bid % tiles_x; bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int f = bid / tiles_y;
+    const int x0 = txi * TX, y0 = tyi * TY;
+    stage_tile<8>(in.p + (size_t)f * in.frame_stride, in, s_in, y0 - 1, x0 - 1, IH, IW, C4, P, threadIdx.x, NTHR);
+    __syncthreads();
+    head_compute<C, NP, TX, TY, SPLIT>(s_in, s_in + IH * IW * P, wts, dw_relu, pw_relu, out, f, x0, y0);
+}
+
+// The class and box heads of one map read the same input: one staged tile serves both (NPA = 8, NPB = 16 outputs).
+template <int C>
+struct Head2Weights {
+    HeadWeights<C, 8> a;
+    HeadWeights<C, 16> b;
+};
+
+template <int C, int TX, int TY, int SPLIT>
+__global__ void __launch_bounds__(((TX * TY + 31) / 32 * 32) * SPLIT)
+head2_dwpw_kernel(TView in, TView out_a, TView out_b, const __grid_constant__ Head2Weights<C> wts, int relu_bits, int tiles_x,
+                  int tiles_y) {
+    constexpr int IW = TX + 2, IH = TY + 2, P = C + 4, NTHR = ((TX * TY + 31) / 32 * 32) * SPLIT, C4 = C / 4;
+    extern __shared__ __align__(16) float s_in[];  // IH*IW*P, then (SPLIT-1) * TX*TY * 16 partial sums
+    pdl_launch_dependents();
+    pdl_wait();
+    int bid = blockIdx.x;
+    const int txi = bid % tiles_x; bid /= tiles_x;
+    const int tyi = bid % tiles_y;
+    const int f = bid / tiles_y;
+    const int x0 = txi * TX, y0 = tyi * TY;
+    stage_tile<8>(in.p + (size_t)f * in.frame_stride, in, s_in, y0 - 1, x0 - 1, IH, IW, C4, P, threadIdx.x, NTHR);
+    __syncthreads();
+    float* s_part = s_in + IH * IW * P;
+    head_compute<C, 8, TX, TY, SPLIT>(s_in, s_part, wts.a, relu_bits & 1, relu_bits & 2, out_a, f, x0, y0);
+    if (SPLIT > 1) __syncthreads();  // the partial-sum buffer is reused
+    head_compute<C, 16, TX, TY, SPLIT>(s_in, s_part, wts.b, relu_bits & 4, relu_bits & 8, out_b, f, x0, y0);
 }
 
 bool head_dwpw_supported(int C, int N, int stride) { return (C == 64 || C == 128 || C == 256) && stride == 1 && N >= 1 && N <= 16; }
@@ -869,6 +904,35 @@ void launch_head_dwpw(const TView& in, const TView& out, const float* host_w, in
     else if (in.C == 128) UF_H(128, 20, 5, 2);   // 20x15 map: three tiles of 100 pixels, two channel halves
     else if (in.C == 256) UF_H(256, 10, 8, 4);   // 10x8 map: one tile, four channel quarters
 #undef UF_H
+}
+
+bool head2_dwpw_supported(int C, int Na, int Nb) { return (C == 64 || C == 128) && Na >= 1 && Na <= 8 && Nb >= 1 && Nb <= 16; }
+
+template <int C, int TX, int TY, int SPLIT>
+static void launch_head2_t(const TView& in, const TView& out_a, const TView& out_b, const float* host_w, int relu_bits, int frames,
+                           cudaStream_t s) {
+    static_assert(sizeof(Head2Weights<C>) + 3 * sizeof(TView) + 64 <= 32764, "kernel parameter space exceeded");
+    constexpr int GT = (TX * TY + 31) / 32 * 32;
+    const int tiles_x = (out_a.W + TX - 1) / TX, tiles_y = (out_a.H + TY - 1) / TY;
+    const size_t smem = ((size_t)(TY + 2) * (TX + 2) * (C + 4) + (size_t)(SPLIT - 1) * TX * TY * 16) * sizeof(float);
+    auto kern = head2_dwpw_kernel<C, TX, TY, SPLIT>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        configured[dev & 63] = true;
+    }
+    launch_pdl(kern, dim3(tiles_x * tiles_y * frames), dim3(GT * SPLIT), smem, s, in, out_a, out_b,
+               *reinterpret_cast<const Head2Weights<C>*>(host_w), relu_bits, tiles_x, tiles_y);
+}
+
+// host_w: HeadWeights<C, 8> of head A followed by HeadWeights<C, 16> of head B (HOST memory);
+// relu_bits: 1 = A depthwise, 2 = A pointwise, 4 = B depthwise, 8 = B pointwise
+void launch_head2_dwpw(const TView& in, const TView& out_a, const TView& out_b, const float* host_w, int relu_bits, int frames,
+                       cudaStream_t s) {
+    if (in.C == 64) launch_head2_t<64, 8, 32, 1>(in, out_a, out_b, host_w, relu_bits, frames, s);
+    else if (in.C == 128) launch_head2_t<128, 20, 5, 2>(in, out_a, out_b, host_w, relu_bits, frames, s);
 }
 
 bool fused_dwpw_pix_supported(int C, int N, int stride) {
