@@ -900,6 +900,8 @@ void launch_head_dwpw(const TView& in, const TView& out, const float* host_w, in
         if (out.C <= 8) launch_head_t<CC, 8, TXX, TYY, SS>(in, out, host_w, dw_relu, pw_relu, frames, s); \
         else launch_head_t<CC, 16, TXX, TYY, SS>(in, out, host_w, dw_relu, pw_relu, frames, s);           \
     } while (0)
+    // (smaller tiles / more channel slices for occupancy were measured: no gain - ncu shows these kernels limited by
+    // the constant-load stream, one LDCU.128 per 4 FFMA, not by latency hiding)
     if (in.C == 64) UF_H(64, 8, 32, 1);
     else if (in.C == 128) UF_H(128, 20, 5, 2);   // 20x15 map: three tiles of 100 pixels, two channel halves
     else if (in.C == 256) UF_H(256, 10, 8, 4);   // 10x8 map: one tile, four channel quarters
