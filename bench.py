@@ -186,6 +186,25 @@ class CpuPort:
             self.pool.join()
 
 
+_REAL_STDOUT_FD = None
+
+
+def capture_stdout():
+    """Point fd 1 at stderr for the whole run: libraries (NCCL prints its version banner on stdout) must not add
+    lines next to the one JSON line the driver parses. emit_json_line() writes to the saved, real stdout."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT_FD if _REAL_STDOUT_FD is not None else 1, data)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -214,11 +233,12 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} frames per step x {args.steps} steps of the batch-{args.batch} workload"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def main():
     args = parse_args()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -401,7 +421,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "latency_batch1_ms": ({"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)], "iters": len(lat)} if lat else None),
                 "wall_check": {"value_wall_s": wall_dev, "value_event_s": t_dev, "e2e_wall_s": wall_e2e}}
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     model.close()
     if dist is not None:
         dist.barrier()
