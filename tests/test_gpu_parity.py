@@ -164,7 +164,9 @@ def test_every_materialised_layer_matches_oracle(make_onnx, oracle320, flags):
 
 
 @pytest.mark.parametrize("cfg", [dict(wh=(320, 240), variant="RFB"), dict(wh=(320, 240), variant="slim"),
-                                 dict(wh=(640, 480), variant="RFB"), dict(wh=(320, 240), variant="RFB", with_bn=True, seed=3)])
+                                 dict(wh=(640, 480), variant="RFB"), dict(wh=(320, 240), variant="RFB", with_bn=True, seed=3),
+                                 # maps 44x36 / 22x18 / 11x9 / 6x5: no kernel tile divides them (partial tiles everywhere)
+                                 dict(wh=(352, 288), variant="RFB", seed=5), dict(wh=(352, 288), variant="slim", seed=6)])
 def test_raw_outputs_within_1e4_and_detections_match(make_onnx, test_pics, cfg):
     wh = cfg["wh"]
     path = make_onnx(*wh, variant=cfg["variant"], with_bn=cfg.get("with_bn", False), seed=cfg.get("seed", 0), cls_bias=-0.75)
