@@ -129,6 +129,9 @@ UF_API int uf_infer_batch_device(uf_model* m, const uint8_t* d_rgb, uint32_t w, 
 UF_API int uf_raw_outputs(uf_model* m, uint32_t first, uint32_t n, float* scores, float* boxes);
 /* nn.rs:74-80 alone: out_u8 = net_h x net_w x 3. */
 UF_API int uf_preproc_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t* out_u8);
+/* Same for n <= chunk frames of identical size, resized by ONE launch (the batch path's kernel selection, e.g. the
+ * exact-integer 2:1 kernel, differs from the single-frame one): out_u8 = n x net_h x net_w x 3. */
+UF_API int uf_preproc_u8_batch(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t n, uint8_t* out_u8);
 /* nn.rs:70-94: out = 1 x 3 x net_h x net_w f32 (NCHW). */
 UF_API int uf_preproc_f32(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, float* out);
 /* nn.rs:109-140 + 198-260 alone on caller-supplied raw tensors (scores K x 2, boxes K x 4). */

@@ -52,6 +52,7 @@ SIGNATURES = {
                                         C.c_uint32, _p(C.c_uint32)]),
     "uf_raw_outputs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(C.c_float), _p(C.c_float)]),
     "uf_preproc_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "uf_preproc_u8_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "uf_preproc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _p(C.c_float)]),
     "uf_postproc": (C.c_int, [C.c_void_p, _p(C.c_float), _p(C.c_float), C.c_uint32, _p(uf_det), C.c_uint32,
                               _p(C.c_uint32), _p(C.c_int32)]),

@@ -1167,6 +1167,37 @@ int uf_preproc_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint8
     });
 }
 
+int uf_preproc_u8_batch(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t n, uint8_t* out_u8) {
+    return guarded([&] {
+        REQUIRE(m && rgb && out_u8 && w > 0 && h > 0 && n > 0, "bad argument");
+        if (n > m->chunk) throw ArgError(UF_ERR_CAPACITY, "uf_preproc_u8_batch: n exceeds the stage size (uf_config.chunk)");
+        LaneLock ll(*m, true);
+        Slot& s = ll.lane->slots[0];
+        CK(cudaSetDevice(m->cfg.device));
+        const int W = m->plan.net_w, H = m->plan.net_h;
+        const size_t fb = (size_t)w * h * 3, ob = (size_t)W * H * 3;
+        if ((int)w == W && (int)h == H) {
+            CK(cudaMemcpyAsync(s.d_resized, rgb, fb * n, cudaMemcpyHostToDevice, s.stream));
+        } else {
+            if (fb * n > s.d_in_cap) {
+                CK(cudaStreamSynchronize(s.stream));
+                CK(cudaFree(s.d_in));
+                s.d_in = nullptr;
+                CK(cudaMalloc(&s.d_in, fb * n));
+                s.d_in_cap = fb * n;
+            }
+            CK(cudaMemcpyAsync(s.d_in, rgb, fb * n, cudaMemcpyHostToDevice, s.stream));
+            TapsEntry& t = get_taps(*m, w, h);
+            m->launches++;
+            launch_resize(s.d_in, (long long)fb, w, h, s.d_resized, (long long)ob, W, H, (int)n, t.dev,
+                          m->cfg.resize_round_intermediate, s.stream);
+        }
+        CK(cudaMemcpyAsync(out_u8, s.d_resized, ob * n, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+    });
+}
+
 int uf_preproc_f32(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, float* out) {
     return guarded([&] {
         REQUIRE(m && rgb && out && w > 0 && h > 0, "bad argument");

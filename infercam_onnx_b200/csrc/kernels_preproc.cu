@@ -195,6 +195,121 @@ resize_triangle_fast_kernel(const uint8_t* __restrict__ src, long long src_frame
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Exact 2:1 reduction on both axes (the 640x480 camera frame onto the 320x240 net, 1280x960 onto 640x480): away
+// from the border every output has the four taps 2o-1 .. 2o+2 with weights {1,3,3,1}/8 — exact binary fractions — so
+// every product and partial sum of the reference's f32 arithmetic is exact (values are multiples of 1/64 below 2^8)
+// and the result is the integer  (sum_ij w_i w_j p_ij + 32) >> 6  (clamp is a no-op, round-half-away = +32 >> 6).
+// The kernel does that in packed 16-bit integer lanes: ~20 integer ops per 4 source bytes instead of 16 conversions
+// and 28 f32 operations. The first / last output row and column have clamped, renormalised taps (weights /1.75, not
+// exact): those 1.5 % of the outputs are recomputed in f32 from the tap tables, same operation order as the
+// generic kernel. round_intermediate (u8 between the passes): (v + 4) >> 3 per pass, also exact.
+// ---------------------------------------------------------------------------------------------
+constexpr int RH_TH = 8, RH_THREADS = 256;
+
+__device__ __forceinline__ uint8_t resize_px_f32(const uint8_t* __restrict__ sf, int sw, const ResizeTapsDev& t, int oy, int ox,
+                                                 int ch, int round_intermediate) {
+    const int vl = t.vleft[oy], vn = t.vn[oy], hl = t.hleft[ox], hn = t.hn[ox];
+    const float* vw = t.vw + (size_t)oy * t.vmax;
+    const float* hw = t.hw + (size_t)ox * t.hmax;
+    float acc = 0.f;
+    for (int j = 0; j < hn; ++j) {
+        float v = 0.f;
+        for (int i = 0; i < vn; ++i)
+            v = __fadd_rn(v, __fmul_rn((float)sf[((size_t)(vl + i) * sw + hl + j) * 3 + ch], vw[i]));
+        if (round_intermediate) v = roundf(fminf(fmaxf(v, 0.f), 255.f));
+        acc = __fadd_rn(acc, __fmul_rn(v, hw[j]));
+    }
+    acc = acc < 0.f ? 0.f : (acc > 255.f ? 255.f : acc);
+    return (uint8_t)roundf(acc);
+}
+
+__global__ void __launch_bounds__(RH_THREADS)
+resize_half_exact_kernel(const uint8_t* __restrict__ src, long long src_frame_stride, int sw, int sh,
+                         uint8_t* __restrict__ dst, long long dst_frame_stride, int dw, int dh, ResizeTapsDev t,
+                         int round_intermediate) {
+    extern __shared__ __align__(16) uint8_t rh_smem[];
+    const int sb = sw * 3;                                         // source bytes per row
+    uint16_t* vt = reinterpret_cast<uint16_t*>(rh_smem);           // RH_TH x sb: vertical sums (a + 3b + 3c + d)
+    uint8_t* out_s = rh_smem + (size_t)RH_TH * sb * 2;             // RH_TH x dw*3
+    const int tid = threadIdx.x, lane = tid & 31, r = tid >> 5;    // warp r owns tile row r in both passes
+    const int oy0 = blockIdx.x * RH_TH;
+    const int rows = min(RH_TH, dh - oy0);
+    const uint8_t* sf = src + (size_t)blockIdx.y * src_frame_stride;
+    const int row_words = sb >> 2;
+    if (r < rows) {
+        const int oy = oy0 + r;
+        const int y0 = 2 * oy - 1;  // rows are clamped into the frame: only border outputs see the difference
+        const unsigned* p0 = reinterpret_cast<const unsigned*>(sf + (size_t)max(y0, 0) * sb);
+        const unsigned* p1 = reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 1) * sb);
+        const unsigned* p2 = reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 2) * sb);
+        const unsigned* p3 = reinterpret_cast<const unsigned*>(sf + (size_t)min(y0 + 3, sh - 1) * sb);
+        uint2* vrow = reinterpret_cast<uint2*>(vt + (size_t)r * sb);
+        for (int wd0 = lane; wd0 < row_words; wd0 += 128) {
+            unsigned a[4], b[4], c[4], d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int wd = min(wd0 + 32 * k, row_words - 1);
+                a[k] = __ldg(p0 + wd); b[k] = __ldg(p1 + wd); c[k] = __ldg(p2 + wd); d[k] = __ldg(p3 + wd);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int wd = wd0 + 32 * k;
+                if (wd >= row_words) break;
+                // bytes 0,2 and bytes 1,3 as packed 16-bit lanes; sums stay below 2^11 (2^8 after the optional rounding)
+                unsigned e = (a[k] & 0x00ff00ffu) + (d[k] & 0x00ff00ffu) + 3u * ((b[k] & 0x00ff00ffu) + (c[k] & 0x00ff00ffu));
+                unsigned o = ((a[k] >> 8) & 0x00ff00ffu) + ((d[k] >> 8) & 0x00ff00ffu) +
+                             3u * (((b[k] >> 8) & 0x00ff00ffu) + ((c[k] >> 8) & 0x00ff00ffu));
+                if (round_intermediate) {
+                    e = ((e + 0x00040004u) >> 3) & 0x00ff00ffu;
+                    o = ((o + 0x00040004u) >> 3) & 0x00ff00ffu;
+                }
+                vrow[wd] = make_uint2(__byte_perm(e, o, 0x5410), __byte_perm(e, o, 0x7632));  // u16 order: byte 0,1,2,3
+            }
+        }
+    }
+    __syncthreads();
+    if (r < rows) {
+        const uint16_t* vrow = vt + (size_t)r * sb;
+        uint8_t* orow = out_s + (size_t)r * dw * 3;
+        const int sh6 = round_intermediate ? 3 : 6;
+        const int half = round_intermediate ? 4 : 32;
+        for (int ox = lane; ox < dw; ox += 32) {
+            const int base = min(max(6 * ox - 3, 0), sb - 12);  // clamped: only the border columns see it
+            const uint16_t* x = vrow + base;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int s4 = (int)x[ch] + (int)x[9 + ch] + 3 * ((int)x[3 + ch] + (int)x[6 + ch]);
+                orow[ox * 3 + ch] = (uint8_t)((s4 + half) >> sh6);
+            }
+        }
+    }
+    __syncthreads();
+    // border outputs in f32 from the tap tables (clamped, renormalised taps are not binary fractions)
+    for (int rr = 0; rr < rows; ++rr) {
+        const int oy = oy0 + rr;
+        if (oy == 0 || oy == dh - 1) {
+            for (int e = tid; e < dw * 3; e += RH_THREADS)
+                out_s[(size_t)rr * dw * 3 + e] = resize_px_f32(sf, sw, t, oy, e / 3, e % 3, round_intermediate);
+        }
+    }
+    for (int e = tid; e < rows * 6; e += RH_THREADS) {
+        const int rr = e / 6, q = e - rr * 6;
+        const int ox = q >= 3 ? dw - 1 : 0, ch = q >= 3 ? q - 3 : q;
+        out_s[(size_t)rr * dw * 3 + ox * 3 + ch] = resize_px_f32(sf, sw, t, oy0 + rr, ox, ch, round_intermediate);
+    }
+    __syncthreads();
+    if (r < rows) {
+        uint8_t* d = dst + (size_t)blockIdx.y * dst_frame_stride + (size_t)(oy0 + r) * dw * 3;
+        if ((reinterpret_cast<size_t>(d) & 3) == 0) {
+            const unsigned* o4 = reinterpret_cast<const unsigned*>(out_s + (size_t)r * dw * 3);
+            for (int i = lane; i < dw * 3 / 4; i += 32) reinterpret_cast<unsigned*>(d)[i] = o4[i];
+        } else {
+            for (int i = lane; i < dw * 3; i += 32) d[i] = out_s[(size_t)r * dw * 3 + i];
+        }
+    }
+}
+
 void launch_resize(const uint8_t* src, long long src_frame_stride, int sw, int sh, uint8_t* dst,
                    long long dst_frame_stride, int dw, int dh, int frames, const ResizeTapsDev& t_in,
                    int round_intermediate, cudaStream_t s) {
@@ -204,8 +319,25 @@ void launch_resize(const uint8_t* src, long long src_frame_stride, int sw, int s
         t.tile_w = t.small_w;
         t.max_cols = t.small_cols;
     }
-    // fast path: rows and frames 4-byte aligned, CTA tile 64 x 8 as built by the engine
     const bool aligned = (sw % 4 == 0) && ((reinterpret_cast<size_t>(src) & 3) == 0) && (src_frame_stride % 4 == 0);
+    // exact 2:1 on both axes: integer kernel (whole rows per CTA)
+    if (aligned && sw == 2 * dw && sh == 2 * dh && dw % 4 == 0 && dh >= 2 && dw >= 4 && t.vmax == 4 && t.hmax == 4 && frames <= 65535 &&
+        (long long)frames * ((dh + RH_TH - 1) / RH_TH) >= 148) {  // whole-row CTAs: a few frames would leave the GPU empty
+        const size_t smem = (size_t)RH_TH * sw * 3 * 2 + (size_t)RH_TH * dw * 3;
+        if (smem <= 96 * 1024) {
+            static bool configured_h[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!configured_h[dev & 63]) {
+                cudaFuncSetAttribute(resize_half_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                configured_h[dev & 63] = true;
+            }
+            resize_half_exact_kernel<<<dim3((dh + RH_TH - 1) / RH_TH, frames), RH_THREADS, smem, s>>>(
+                src, src_frame_stride, sw, sh, dst, dst_frame_stride, dw, dh, t, round_intermediate);
+            return;
+        }
+    }
+    // fast f32 path: rows and frames 4-byte aligned, CTA tile (multiple of 4) x 8 as built by the engine
     if (aligned && t.tile_w % 4 == 0 && t.tile_h == RF_TH) {
         const int pitch = ((t.max_cols + 4) * 3 + 3) / 4 * 4;  // +4: col0 is aligned down by up to 3 pixels
         const size_t smem = (size_t)RF_TH * pitch * sizeof(float) + (size_t)RF_TH * t.tile_w * 3;

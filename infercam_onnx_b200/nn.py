@@ -164,6 +164,17 @@ class UltrafaceModel(InferModel):
                                           out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def preproc_u8_batch(self, frames: np.ndarray) -> np.ndarray:
+        """nn.rs:74-80 for n same-size frames [n,h,w,3] in ONE launch (n <= the stage size) -> u8 [n,H,W,3]."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        if frames.ndim != 4 or frames.shape[3] != 3:
+            raise ValueError("frames must be [n, h, w, 3] uint8")
+        n, h, w = frames.shape[:3]
+        out = np.empty((n, self.height, self.width, 3), np.uint8)
+        _check(_capi.load().uf_preproc_u8_batch(self._h, frames.ctypes.data_as(C.c_void_p), w, h, n,
+                                                out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def preproc(self, input: np.ndarray) -> np.ndarray:  # noqa: A002
         """nn.rs:70-94 -> f32 [1,3,H,W]"""
         img = _as_rgb(input)

@@ -109,12 +109,38 @@ def test_resize_bit_exact_large_and_extreme_aspect(model320, shape):
 
 def test_resize_pre024_switch(make_onnx):
     m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240),
-                              resize_round_intermediate=True)
+                              resize_round_intermediate=True, max_batch=8)
     try:
         im = _noise(1, 427, 640, seed=5)[0]
         np.testing.assert_array_equal(m.preproc_u8(im), hotpath.resize_triangle(im, 320, 240, True))
+        ims = _noise(8, 480, 640, seed=6)  # exact 2:1 batch: the integer kernel's (v + 4) >> 3 per pass
+        got = m.preproc_u8_batch(ims)
+        for i in range(len(ims)):
+            np.testing.assert_array_equal(got[i], hotpath.resize_triangle(ims[i], 320, 240, True))
     finally:
         m.close()
+
+
+def test_resize_exact_half_integer_kernel(make_onnx):
+    """Exact 2:1 on both axes runs in packed integer arithmetic (interior) + f32 tap tables (border row / column):
+    must equal the oracle's f32 restatement bit for bit, including saturated and constant images, on both nets."""
+    for net, shape in (((320, 240), (480, 640)), ((640, 480), (960, 1280))):
+        m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(*net), size=net, max_batch=16)
+        try:
+            rng = np.random.default_rng(net[0])
+            ims = [rng.integers(0, 256, (*shape, 3), dtype=np.uint8),
+                   np.where(rng.random((*shape, 3)) < 0.5, 0, 255).astype(np.uint8),
+                   np.full((*shape, 3), 255, np.uint8), np.zeros((*shape, 3), np.uint8),
+                   _smooth(1, *shape, seed=2)[0]]
+            for im in ims:  # single frame: f32 kernel (too few whole-row CTAs to fill the GPU)
+                np.testing.assert_array_equal(m.preproc_u8(im), hotpath.resize_triangle(im, *net))
+            # batch of 10: the integer kernel (whole-row CTAs need >= 148 of them)
+            batch = np.stack(ims + ims)
+            got = m.preproc_u8_batch(batch)
+            for i, im in enumerate(batch):
+                np.testing.assert_array_equal(got[i], hotpath.resize_triangle(im, *net), err_msg=str(i))
+        finally:
+            m.close()
 
 
 # ---------------------------------------------------------------------------------------------
