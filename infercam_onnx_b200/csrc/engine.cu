@@ -399,8 +399,8 @@ static void build_steps(uf_model& m) {
 
 static void build_tc_weights(uf_model& m) {
     for (Step& st : m.steps) {
-        if (st.impl != Impl::PointwiseTC && st.impl != Impl::FusedDwTC) continue;
-        const Op& op = m.plan.ops[st.impl == Impl::FusedDwTC ? st.op2 : st.op];
+        if (st.impl != Impl::PointwiseTC && st.impl != Impl::FusedDwTC && st.impl != Impl::FusedTma) continue;
+        const Op& op = m.plan.ops[st.impl == Impl::PointwiseTC ? st.op : st.op2];
         const int N = op.cout, K = op.cin;
         std::vector<float> hi((size_t)N * K), lo((size_t)N * K);
         for (size_t i = 0; i < hi.size(); ++i) {  // op.w is [cout][cin][1][1] = [N][K], K contiguous
@@ -418,8 +418,11 @@ static void build_tc_weights(uf_model& m) {
         CK(cudaMemcpy(t.d_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(t.d_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
         const uint32_t box = (uint32_t)pointwise_tc_n_umma(N);
-        if (!make_tmap_f32_2d(&t.tm_hi, t.d_hi, N, K, (uint64_t)K * 4, box) ||
-            !make_tmap_f32_2d(&t.tm_lo, t.d_lo, N, K, (uint64_t)K * 4, box))
+        const bool fused = st.impl == Impl::FusedTma;  // whole [N][K] matrix as one box, swizzle span = K * 4 (64 / 128 B)
+        if (fused ? (!make_tmap_f32_2d_sw(&t.tm_hi, t.d_hi, N, K, (uint64_t)K * 4, (uint32_t)K, (uint32_t)N) ||
+                     !make_tmap_f32_2d_sw(&t.tm_lo, t.d_lo, N, K, (uint64_t)K * 4, (uint32_t)K, (uint32_t)N))
+                  : (!make_tmap_f32_2d(&t.tm_hi, t.d_hi, N, K, (uint64_t)K * 4, box) ||
+                     !make_tmap_f32_2d(&t.tm_lo, t.d_lo, N, K, (uint64_t)K * 4, box)))
             throw CudaError("cuTensorMapEncodeTiled failed for 1x1 weights of '" + m.plan.tensors[op.out].name + "'");
         st.tc = (int)m.tc_weights.size();
         m.tc_weights.push_back(t);
@@ -535,8 +538,10 @@ static void alloc_lane(uf_model& m, Lane& ln) {
                 const Op& dw = m.plan.ops[m.steps[i].op];
                 const Op& pw = m.plan.ops[m.steps[i].op2];
                 int iw, ih, ow, oh;
-                fused_dwpw_tma_boxes(dw.stride, &iw, &ih, &ow, &oh);
-                if (!make_tmap_nhwc(&s.tm_a[i], make_view(m, s, dw.in), (int)m.chunk, 16, iw, ih, 64) ||
+                if (m.cfg.flags & UF_FLAG_TMA_SIMT_PW) fused_dwpw_tma_boxes(dw.stride, &iw, &ih, &ow, &oh);
+                else fused_dwpw_tc_boxes(dw.stride, &iw, &ih, &ow, &oh);
+                const int sc = (m.cfg.flags & UF_FLAG_TMA_SIMT_PW) ? 16 : fused_dwpw_tc_slice_channels(dw.cout);
+                if (!make_tmap_nhwc(&s.tm_a[i], make_view(m, s, dw.in), (int)m.chunk, sc, iw, ih, sc * 4) ||
                     !make_tmap_nhwc(&s.tm_o[i], make_view(m, s, pw.out), (int)m.chunk, 32, ow, oh, 128))
                     throw CudaError("cuTensorMapEncodeTiled failed for fused layer '" + m.plan.tensors[pw.out].name + "'");
                 continue;
@@ -695,7 +700,13 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
             case Impl::FusedTma: {
                 const Op& pw = p.ops[st.op2];
                 TView o2 = make_view(m, s, pw.out);
-                launch_fused_dwpw_tma(s.tm_a[si], s.tm_o[si], in, o2, st.host_w.data(), op.stride, op.relu, pw.relu, frames, s.stream);
+                if (m.cfg.flags & UF_FLAG_TMA_SIMT_PW) {
+                    launch_fused_dwpw_tma(s.tm_a[si], s.tm_o[si], in, o2, st.host_w.data(), op.stride, op.relu, pw.relu, frames, s.stream);
+                } else {
+                    const TcWeights& tw = m.tc_weights[st.tc];
+                    launch_fused_dwpw_tc(s.tm_a[si], s.tm_o[si], tw.tm_hi, tw.tm_lo, in, o2, st.host_w.data(), op.stride, op.relu,
+                                         pw.relu, frames, s.stream);
+                }
                 break;
             }
             case Impl::SmallDense: launch_small_dense(in, out, st.host_w.data(), op.dil, op.relu, frames, s.stream); break;

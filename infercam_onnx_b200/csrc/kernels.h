@@ -111,6 +111,14 @@ bool make_tmap_nhwc(TmaMap* out, const TView& v, int frames, uint32_t box_c, uin
 bool fused_dwpw_tma_supported(int C, int N, int stride);
 void fused_dwpw_tma_boxes(int stride, int* in_w, int* in_h, int* out_w, int* out_h);
 size_t fused_dwpw_tma_weight_floats(int C, int N);
+// tensor-core form (1x1 conv on tcgen05, 3xTF32): CTA tile 8 x 16, weights [N][C] as tf32 hi / lo tensor maps
+void fused_dwpw_tc_boxes(int stride, int* in_w, int* in_h, int* out_w, int* out_h);
+int fused_dwpw_tc_slice_channels(int C);  // channels per input TMA box (its swizzle span is 4x that in bytes)
+bool make_tmap_f32_2d_sw(TmaMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                         uint32_t box_cols, uint32_t box_rows);
+void launch_fused_dwpw_tc(const TmaMap& tm_in, const TmaMap& tm_out, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TView& in,
+                          const TView& out, const float* host_w, int stride, int dw_relu, int pw_relu, int frames,
+                          cudaStream_t s);
 // host_w: [dw 9*C][dw bias C][pw C*N][pw bias N] in HOST memory (passed by value as a __grid_constant__ parameter)
 void launch_fused_dwpw_tma(const TmaMap& tm_in, const TmaMap& tm_out, const TView& in, const TView& out,
                            const float* host_w, int stride, int dw_relu, int pw_relu, int frames, cudaStream_t s);

@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "kernels.h"
 #include "pdl.cuh"
@@ -157,6 +159,14 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 // 128-byte pitch, 8-row groups 1024 bytes apart (SBO), version 1 (Blackwell), layout SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// Same for a swizzle span of row_bytes = 64 or 128 (= the K extent of the tile): 8-row groups 8 * row_bytes apart,
+// layout 4 (SWIZZLE_64B) / 2 (SWIZZLE_128B) of cute::UMMA::LayoutType.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)((8u * row_bytes) >> 4) << 32) | (1ull << 46) |
+           (layout << 61);
 }
 
 constexpr int TC_BM = 128;        // rows per tile = UMMA M
@@ -717,6 +727,211 @@ fused_dwpw_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     if (tid == 0) bulk_wait0();  // smem must outlive the last store
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core form of the kernel above: same TMA-fed depthwise front half (thread = output pixel, 16-channel slices,
+// depthwise weights as constant operands), but the 1x1 conv — 78 % of the kernel's FFMAs — leaves the SIMT pipes:
+// every thread writes its pixel's C depthwise results as one K-major row of the A operand (raw fp32 = tf32 hi, and
+// the lo remainder) in the canonical swizzled layout, one thread issues the 3xTF32 tcgen05.mma sequence
+// (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi) against the CTA-resident W_hi / W_lo tiles into a TMEM accumulator, and the
+// same threads read their row back (tcgen05.ld: warp w owns TMEM lanes 32w..32w+31 = its own pixels), add the bias,
+// apply ReLU and stage it for the TMA store. CTA = 8 x 16 pixels = one UMMA M tile of 128 rows; the output staging
+// tile aliases the A tiles (dead once the MMAs have committed), ~70 KB of shared memory, three CTAs per SM cover
+// each other's MMA / TMA latencies.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+struct DwWeights {
+    float dw[9 * C];  // [tap][c]
+    float dwb[C];
+    float pwb[64];    // bias of the 1x1 conv (N <= 64)
+};
+
+// A kernel that allocates tensor memory runs ONE CTA per SM (cudaOccupancyMaxActiveBlocksPerMultiprocessor = 1
+// whatever its footprint: the CTA owns the SM's TMEM), and a single 128-thread tile pipeline leaves the SM idle during
+// every barrier, MMA round trip and TMA wait (measured: 1.9-2.7 us per tile, slower than the SIMT 1x1). So the CTA holds
+// G independent GROUPS of 128 threads, each a complete tile pipeline of its own — input slices, A / staging buffer,
+// mbarriers, accumulator columns, a named barrier (bar.sync 1+g, 128) — sharing only the resident W tiles: what
+// three or four co-resident CTAs would have been.
+template <int C, int N, int S, int G, int NB>
+__global__ void __launch_bounds__(128 * G, 1)
+fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                     const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                     const __grid_constant__ DwWeights<C> wts, int dw_relu, int pw_relu, int tiles_x, int tiles_y,
+                     int total_tiles) {
+    constexpr int TX = 8, TY = 16, IW = (TX - 1) * S + 3, IH = (TY - 1) * S + 3;
+    constexpr int SC = 16;                   // channels per input slice (64-byte box rows; 32-channel / 128-byte slices were
+    constexpr int NSL = C / SC;              // measured: no faster per tile, and they cost a group of shared memory)
+    constexpr int SROW = SC * 4, SQ = SC / 4;
+    constexpr int SLICE_BYTES = IH * IW * SROW;
+    constexpr int SLICE_ALLOC = (SLICE_BYTES + 1023) / 1024 * 1024;
+    constexpr int ROWB = C * 4;              // bytes per A / W row = swizzle span (64 or 128)
+    constexpr int A_BYTES = 128 * ROWB;      // 8 or 16 KB
+    constexpr int A_REGION = 2 * A_BYTES < 16384 ? 16384 : 2 * A_BYTES;  // A_hi | A_lo, and at least the 16 KB staging tile
+    constexpr int GROUP_BYTES = NB * SLICE_ALLOC + A_REGION;  // NB input slices in flight per group (memory latency)
+    constexpr int W_BYTES = N * ROWB;
+    constexpr int NCOL = N <= 32 ? 32 : 64;  // accumulator columns per group
+    constexpr uint32_t TMEM_COLS = G * NCOL <= 32 ? 32 : (G * NCOL <= 64 ? 64 : (G * NCOL <= 128 ? 128 : 256));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, g = tid >> 7, lt = tid & 127, lwarp = lt >> 5;
+    uint8_t* in_buf = smem + g * GROUP_BYTES;                 // NB x SLICE_ALLOC
+    uint8_t* a_hi = in_buf + NB * SLICE_ALLOC;                 // A_hi | A_lo; the staging tile (128 x 128 B) aliases them
+    uint8_t* a_lo = a_hi + A_BYTES;
+    uint8_t* out_stage = a_hi;
+    uint8_t* w_hi = smem + G * GROUP_BYTES;
+    uint8_t* w_lo = w_hi + W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + W_BYTES);
+    uint64_t* w_bar = bars;
+    uint64_t* full = bars + 1 + g * (NB + 1);                 // [NB] input slices of this group
+    uint64_t* mma_bar = full + NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + G * (NB + 1));
+    const int vcta = blockIdx.x * G + g, vgrid = gridDim.x * G;  // this group's place among all tile pipelines
+    const int my_tiles = vcta < total_tiles ? (total_tiles - vcta + vgrid - 1) / vgrid : 0;
+    const int n_units = my_tiles * NSL;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+
+    auto tile_coords = [&](int t, int& f, int& y0, int& x0) {
+        int b = vcta + t * vgrid;
+        const int txi = b % tiles_x; b /= tiles_x;
+        const int tyi = b % tiles_y;
+        f = b / tiles_y;
+        x0 = txi * TX; y0 = tyi * TY;
+    };
+    auto issue = [&](int u) {  // group leader only
+        int f, y0, x0;
+        tile_coords(u / NSL, f, y0, x0);
+        uint64_t* bar = &full[u % NB];
+        mbar_expect_tx(bar, SLICE_BYTES);
+        tma_load_4d(in_buf + (u % NB) * SLICE_ALLOC, &tm_in, bar, (u % NSL) * SC, x0 * S - 1, y0 * S - 1, f);
+    };
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        mbar_init(w_bar, 1);
+        for (int i = 0; i < G * (NB + 1); ++i) mbar_init(bars + 1 + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {  // the weights are static: fetched before the predecessor kernel is waited for
+        mbar_expect_tx(w_bar, 2 * W_BYTES);
+        tma_load_2d(w_hi, &tm_whi, w_bar, 0, 0);
+        tma_load_2d(w_lo, &tm_wlo, w_bar, 0, 0);
+    }
+    pdl_wait();
+    if (lt == 0) {
+        for (int i = 0; i < NB && i < n_units; ++i) issue(i);
+    }
+    const int tx = lt % TX, ty = lt / TX;
+    // instruction descriptor: D=F32, A=B=TF32, K-major both, N>>3, M>>4 (M = 128)
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // this thread's row of the A tiles: 16-byte chunk q lives at q ^ (row & 7) (128B swizzle) or q ^ ((row >> 1) & 3) (64B)
+    const int a_row = lt * ROWB;
+    const int a_swz = ROWB == 128 ? (lt & 7) : ((lt >> 1) & 3);
+    const uint32_t acc = tmem_base + (uint32_t)(g * NCOL);                 // this group's accumulator columns
+    const uint32_t taddr = acc + ((uint32_t)(lwarp * 32) << 16);          // warp w of a group owns TMEM lanes 32w..32w+31
+    int u = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl, ++u) {
+            mbar_wait(&full[u % NB], (uint32_t)((u / NB) & 1));
+            const uint8_t* buf = in_buf + (u % NB) * SLICE_ALLOC;
+            float4 dq[SQ];
+#pragma unroll
+            for (int q = 0; q < SQ; ++q) {
+                const int c = sl * SC + q * 4;
+                float a0 = wts.dwb[c], a1 = wts.dwb[c + 1], a2 = wts.dwb[c + 2], a3 = wts.dwb[c + 3];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int r = (ty * S + ky) * IW + tx * S + kx;  // row of the box (one pixel's SC channels)
+                        const int sw = SROW == 128 ? (r & 7) : ((r >> 1) & 3);
+                        const float4 v = *reinterpret_cast<const float4*>(buf + r * SROW + ((q ^ sw) << 4));
+                        const int wo = (ky * 3 + kx) * C + c;
+                        a0 = fmaf(v.x, wts.dw[wo], a0); a1 = fmaf(v.y, wts.dw[wo + 1], a1);
+                        a2 = fmaf(v.z, wts.dw[wo + 2], a2); a3 = fmaf(v.w, wts.dw[wo + 3], a3);
+                    }
+                if (dw_relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                dq[q] = make_float4(a0, a1, a2, a3);
+            }
+            if (sl == 0) {  // first write into the A buffer: the previous tile's store (staged there) must have read it
+                if (lt == 0) bulk_wait_read0();
+                group_sync();
+            }
+#pragma unroll
+            for (int q = 0; q < SQ; ++q) {
+                const int off = a_row + (((sl * SQ + q) ^ a_swz) << 4);
+                float4 l;
+                l.x = dq[q].x - __uint_as_float(__float_as_uint(dq[q].x) & 0xffffe000u);
+                l.y = dq[q].y - __uint_as_float(__float_as_uint(dq[q].y) & 0xffffe000u);
+                l.z = dq[q].z - __uint_as_float(__float_as_uint(dq[q].z) & 0xffffe000u);
+                l.w = dq[q].w - __uint_as_float(__float_as_uint(dq[q].w) & 0xffffe000u);
+                *reinterpret_cast<float4*>(a_hi + off) = dq[q];  // kind::tf32 ignores the low 13 mantissa bits: raw = hi
+                *reinterpret_cast<float4*>(a_lo + off) = l;
+            }
+            if (sl == NSL - 1) fence_proxy_async();  // A rows (generic proxy) -> visible to the tensor core
+            group_sync();                            // the group is done with this slice buffer (and, last slice, with A)
+            if (lt == 0 && u + NB < n_units) issue(u + NB);
+        }
+        if (lt == 0) {
+            if (t == 0) mbar_wait(w_bar, 0);
+            tc_fence_after();
+            const uint64_t d_ahi = umma_desc_kmajor(smem_u32(a_hi), ROWB), d_alo = umma_desc_kmajor(smem_u32(a_lo), ROWB);
+            const uint64_t d_whi = umma_desc_kmajor(smem_u32(w_hi), ROWB), d_wlo = umma_desc_kmajor(smem_u32(w_lo), ROWB);
+#pragma unroll
+            for (int k = 0; k < C / 8; ++k) umma_tf32(acc, d_alo + 2 * k, d_whi + 2 * k, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < C / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1);
+#pragma unroll
+            for (int k = 0; k < C / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_whi + 2 * k, idesc, 1);
+            umma_commit(mma_bar);
+        }
+        __syncwarp();
+        mbar_wait(mma_bar, (uint32_t)(t & 1));
+        tc_fence_after();
+        int f, y0, x0;
+        tile_coords(t, f, y0, x0);
+#pragma unroll
+        for (int n0 = 0; n0 < N; n0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + n0, v, true);
+            if (n0 > 0) {  // second pass of a 64-output layer: wait until the first pass' store has read the staging tile
+                if (lt == 0) bulk_wait_read0();
+                group_sync();
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 x = make_float4(v[q * 4] + wts.pwb[n0 + q * 4], v[q * 4 + 1] + wts.pwb[n0 + q * 4 + 1],
+                                       v[q * 4 + 2] + wts.pwb[n0 + q * 4 + 2], v[q * 4 + 3] + wts.pwb[n0 + q * 4 + 3]);
+                if (pw_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                *reinterpret_cast<float4*>(out_stage + lt * 128 + ((q ^ (lt & 7)) << 4)) = x;  // 128B swizzle
+            }
+            fence_proxy_async();
+            tc_fence_before();  // this thread's tcgen05.ld are complete: the next tile's MMAs may overwrite the accumulator
+            group_sync();
+            if (lt == 0) {
+                tma_store_4d(&tm_out, out_stage, n0, x0, y0, f);
+                bulk_commit();
+            }
+        }
+    }
+    if (lt == 0) bulk_wait0();  // smem must outlive the last store
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // NHWC fp32 view as a 4-D tensor map (C, W, H, frames); box = (box_c, box_w, box_h, 1)
 bool make_tmap_nhwc(TmaMap* out, const TView& v, int frames, uint32_t box_c, uint32_t box_w, uint32_t box_h, int swizzle_bytes) {
     EncodeTiledFn fn = encode_fn();
@@ -783,6 +998,74 @@ void launch_fused_dwpw_tma(const TmaMap& tm_in, const TmaMap& tm_out, const TVie
     else if (C == 32 && N == 32 && stride == 2) UF_T(32, 32, 2, 16);
     else if (C == 32 && N == 64 && stride == 2) UF_T(32, 64, 2, 16);
     else if (C == 32 && N == 64 && stride == 1) UF_T(32, 64, 1, 32);
+#undef UF_T
+}
+
+// fp32 matrix [rows][cols], box = box_rows x box_cols floats, swizzle span = box_cols * 4 bytes (64 or 128)
+bool make_tmap_f32_2d_sw(TmaMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                         uint32_t box_cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = box_cols * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim,
+                    gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+int fused_dwpw_tc_slice_channels(int) { return 16; }
+
+void fused_dwpw_tc_boxes(int stride, int* in_w, int* in_h, int* out_w, int* out_h) {
+    const int TX = 8, TY = 16;
+    *in_w = (TX - 1) * stride + 3; *in_h = (TY - 1) * stride + 3; *out_w = TX; *out_h = TY;
+}
+
+template <int C, int N, int S, int G, int NB>
+static void launch_fused_tc_t(const TmaMap& tm_in, const TmaMap& tm_out, const TmaMap& tm_whi, const TmaMap& tm_wlo,
+                              const TView& out, const float* host_w, int dw_relu, int pw_relu, int frames, cudaStream_t s) {
+    constexpr int TX = 8, TY = 16, IW = (TX - 1) * S + 3, IH = (TY - 1) * S + 3;
+    constexpr int SLICE_ALLOC = (IH * IW * 64 + 1023) / 1024 * 1024;
+    constexpr int A_REGION = 2 * 128 * C * 4 < 16384 ? 16384 : 2 * 128 * C * 4;
+    constexpr size_t SMEM = (size_t)G * (NB * SLICE_ALLOC + A_REGION) + 2 * N * C * 4 + (2 + (NB + 1) * G) * 8 + 16 + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
+    static_assert(sizeof(DwWeights<C>) + 4 * sizeof(CUtensorMap) + 64 <= 32764, "kernel parameter space exceeded");
+    DwWeights<C> w;
+    memcpy(w.dw, host_w, sizeof(float) * 10 * C);  // dw taps followed by the dw bias
+    for (int i = 0; i < 64; ++i) w.pwb[i] = i < N ? host_w[10 * C + C * N + i] : 0.f;
+    const int tiles_x = (out.W + TX - 1) / TX, tiles_y = (out.H + TY - 1) / TY;
+    const int total = tiles_x * tiles_y * frames;
+    auto kern = fused_dwpw_tc_kernel<C, N, S, G, NB>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured[dev & 63] = true;
+    }
+    int grid = 148;  // one CTA per SM (tensor memory), G tile pipelines each
+    if (grid > (total + G - 1) / G) grid = (total + G - 1) / G;
+    launch_pdl(kern, dim3(grid), dim3(128 * G), SMEM, s, *reinterpret_cast<const CUtensorMap*>(&tm_in),
+               *reinterpret_cast<const CUtensorMap*>(&tm_out), *reinterpret_cast<const CUtensorMap*>(&tm_whi),
+               *reinterpret_cast<const CUtensorMap*>(&tm_wlo), w, dw_relu, pw_relu, tiles_x, tiles_y, total);
+}
+
+// host_w as for launch_fused_dwpw_tma; tm_whi / tm_wlo: the 1x1 weights [N][C] split into tf32 hi / lo, box C x N
+void launch_fused_dwpw_tc(const TmaMap& tm_in, const TmaMap& tm_out, const TmaMap& tm_whi, const TmaMap& tm_wlo, const TView& in,
+                          const TView& out, const float* host_w, int stride, int dw_relu, int pw_relu, int frames,
+                          cudaStream_t s) {
+#define UF_T(CC, NN, SS, GG, BB) launch_fused_tc_t<CC, NN, SS, GG, BB>(tm_in, tm_out, tm_whi, tm_wlo, out, host_w, dw_relu, pw_relu, frames, s)
+    const int C = in.C, N = out.C;
+    // groups per CTA: as many tile pipelines as fit the SM's 227 KB (stride 2: the input slices alone take 74 KB each)
+    // (groups, slice buffers) per shape, measured on B200: the group count matters most, a third slice buffer a little
+    if (C == 16 && N == 32 && stride == 1) UF_T(16, 32, 1, 5, 2);
+    else if (C == 32 && N == 32 && stride == 1) UF_T(32, 32, 1, 3, 3);
+    else if (C == 32 && N == 32 && stride == 2) UF_T(32, 32, 2, 2, 2);
+    else if (C == 32 && N == 64 && stride == 2) UF_T(32, 64, 2, 1, 2);
+    else if (C == 32 && N == 64 && stride == 1) UF_T(32, 64, 1, 2, 4);
 #undef UF_T
 }
 
