@@ -339,7 +339,10 @@ static void build_steps(uf_model& m) {
                     const TensorDesc& o2 = p.tensors[nx.out];
                     const bool fusable = nx_pw && uses[op.out] == 1 && !out.in_concat && fused_dwpw_supported(op.cout, nx.cout);
                     // 16/32-channel pairs on the big maps: TMA-pipelined fused kernel (memory-bound)
-                    const bool tma = fusable && !no_tc && fused_dwpw_tma_supported(op.cout, nx.cout, op.stride) &&
+                    const bool simt_pw = m.cfg.flags & UF_FLAG_TMA_SIMT_PW;
+                    const bool tma = fusable && !no_tc &&
+                                     (simt_pw ? fused_dwpw_tma_supported(op.cout, nx.cout, op.stride)
+                                              : fused_dwpw_tc_supported(op.cout, nx.cout, op.stride)) &&
                                      o2.pix_stride == o2.C && o2.base_off % 4 == 0 && !o2.in_concat;
                     // wide pairs: depthwise kernel + tensor-core GEMM beats the SIMT fusion (those maps are L2-resident)
                     const bool split_tc = nx_pw && !tma && tc_ok(nx) && (op.cout >= 128 || (op.cout == 64 && nx.cout >= 32));
@@ -418,9 +421,10 @@ static void build_tc_weights(uf_model& m) {
         CK(cudaMemcpy(t.d_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(t.d_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
         const uint32_t box = (uint32_t)pointwise_tc_n_umma(N);
-        const bool fused = st.impl == Impl::FusedTma;  // whole [N][K] matrix as one box, swizzle span = K * 4 (64 / 128 B)
-        if (fused ? (!make_tmap_f32_2d_sw(&t.tm_hi, t.d_hi, N, K, (uint64_t)K * 4, (uint32_t)K, (uint32_t)N) ||
-                     !make_tmap_f32_2d_sw(&t.tm_lo, t.d_lo, N, K, (uint64_t)K * 4, (uint32_t)K, (uint32_t)N))
+        const bool fused = st.impl == Impl::FusedTma;  // [N][<= 32] boxes, swizzle span = box width (64 / 128 B)
+        const uint32_t kc = (uint32_t)std::min(K, 32);  // one K block = one swizzle span (64 / 128 B) per box
+        if (fused ? (!make_tmap_f32_2d_sw(&t.tm_hi, t.d_hi, N, K, (uint64_t)K * 4, kc, (uint32_t)N) ||
+                     !make_tmap_f32_2d_sw(&t.tm_lo, t.d_lo, N, K, (uint64_t)K * 4, kc, (uint32_t)N))
                   : (!make_tmap_f32_2d(&t.tm_hi, t.d_hi, N, K, (uint64_t)K * 4, box) ||
                      !make_tmap_f32_2d(&t.tm_lo, t.d_lo, N, K, (uint64_t)K * 4, box)))
             throw CudaError("cuTensorMapEncodeTiled failed for 1x1 weights of '" + m.plan.tensors[op.out].name + "'");

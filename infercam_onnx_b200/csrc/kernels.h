@@ -109,6 +109,7 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
 // with box (16, in_w, in_h, 1) and 64B swizzle; tm_out: 4-D map of the output view with box (32, out_w, out_h, 1), 128B swizzle
 bool make_tmap_nhwc(TmaMap* out, const TView& v, int frames, uint32_t box_c, uint32_t box_w, uint32_t box_h, int swizzle_bytes);
 bool fused_dwpw_tma_supported(int C, int N, int stride);
+bool fused_dwpw_tc_supported(int C, int N, int stride);
 void fused_dwpw_tma_boxes(int stride, int* in_w, int* in_h, int* out_w, int* out_h);
 size_t fused_dwpw_tma_weight_floats(int C, int N);
 // tensor-core form (1x1 conv on tcgen05, 3xTF32): CTA tile 8 x 16, weights [N][C] as tf32 hi / lo tensor maps

@@ -763,11 +763,15 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     constexpr int SROW = SC * 4, SQ = SC / 4;
     constexpr int SLICE_BYTES = IH * IW * SROW;
     constexpr int SLICE_ALLOC = (SLICE_BYTES + 1023) / 1024 * 1024;
-    constexpr int ROWB = C * 4;              // bytes per A / W row = swizzle span (64 or 128)
-    constexpr int A_BYTES = 128 * ROWB;      // 8 or 16 KB
+    constexpr int KBLK = C > 32 ? C / 32 : 1;  // K blocks of the operand tiles: one swizzle span (<= 32 channels) each
+    constexpr int KC = C / KBLK;             // channels per K block (16 or 32)
+    constexpr int ROWB = KC * 4;             // bytes per A / W row within a K block = swizzle span (64 or 128)
+    constexpr int AKB = 128 * ROWB;          // one K block of an A tile (8 or 16 KB)
+    constexpr int WKB = N * ROWB;            // one K block of a W tile
+    constexpr int A_BYTES = KBLK * AKB;
     constexpr int A_REGION = 2 * A_BYTES < 16384 ? 16384 : 2 * A_BYTES;  // A_hi | A_lo, and at least the 16 KB staging tile
     constexpr int GROUP_BYTES = NB * SLICE_ALLOC + A_REGION;  // NB input slices in flight per group (memory latency)
-    constexpr int W_BYTES = N * ROWB;
+    constexpr int W_BYTES = KBLK * WKB;
     constexpr int NCOL = N <= 32 ? 32 : 64;  // accumulator columns per group
     constexpr uint32_t TMEM_COLS = G * NCOL <= 32 ? 32 : (G * NCOL <= 64 ? 64 : (G * NCOL <= 128 ? 128 : 256));
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -822,8 +826,10 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     if (tid == 0) {  // the weights are static: fetched before the predecessor kernel is waited for
         mbar_expect_tx(w_bar, 2 * W_BYTES);
-        tma_load_2d(w_hi, &tm_whi, w_bar, 0, 0);
-        tma_load_2d(w_lo, &tm_wlo, w_bar, 0, 0);
+        for (int kb = 0; kb < KBLK; ++kb) {
+            tma_load_2d(w_hi + kb * WKB, &tm_whi, w_bar, kb * KC, 0);
+            tma_load_2d(w_lo + kb * WKB, &tm_wlo, w_bar, kb * KC, 0);
+        }
     }
     pdl_wait();
     if (lt == 0) {
@@ -868,7 +874,8 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             }
 #pragma unroll
             for (int q = 0; q < SQ; ++q) {
-                const int off = a_row + (((sl * SQ + q) ^ a_swz) << 4);
+                const int ch = sl * SQ + q;                 // 16-byte chunk of the pixel's C channels
+                const int off = (ch / (KC / 4)) * AKB + a_row + (((ch % (KC / 4)) ^ a_swz) << 4);
                 float4 l;
                 l.x = dq[q].x - __uint_as_float(__float_as_uint(dq[q].x) & 0xffffe000u);
                 l.y = dq[q].y - __uint_as_float(__float_as_uint(dq[q].y) & 0xffffe000u);
@@ -884,14 +891,17 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         if (lt == 0) {
             if (t == 0) mbar_wait(w_bar, 0);
             tc_fence_after();
-            const uint64_t d_ahi = umma_desc_kmajor(smem_u32(a_hi), ROWB), d_alo = umma_desc_kmajor(smem_u32(a_lo), ROWB);
-            const uint64_t d_whi = umma_desc_kmajor(smem_u32(w_hi), ROWB), d_wlo = umma_desc_kmajor(smem_u32(w_lo), ROWB);
 #pragma unroll
-            for (int k = 0; k < C / 8; ++k) umma_tf32(acc, d_alo + 2 * k, d_whi + 2 * k, idesc, k > 0 ? 1u : 0u);
+            for (int kb = 0; kb < KBLK; ++kb) {
+                const uint64_t d_ahi = umma_desc_kmajor(smem_u32(a_hi + kb * AKB), ROWB), d_alo = umma_desc_kmajor(smem_u32(a_lo + kb * AKB), ROWB);
+                const uint64_t d_whi = umma_desc_kmajor(smem_u32(w_hi + kb * WKB), ROWB), d_wlo = umma_desc_kmajor(smem_u32(w_lo + kb * WKB), ROWB);
 #pragma unroll
-            for (int k = 0; k < C / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1);
+                for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_alo + 2 * k, d_whi + 2 * k, idesc, (kb | k) > 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < C / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_whi + 2 * k, idesc, 1);
+                for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1);
+#pragma unroll
+                for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_whi + 2 * k, idesc, 1);
+            }
             umma_commit(mma_bar);
         }
         __syncwarp();
@@ -951,6 +961,11 @@ bool make_tmap_nhwc(TmaMap* out, const TView& v, int frames, uint32_t box_c, uin
 bool fused_dwpw_tma_supported(int C, int N, int stride) {
     if (C == 16) return N == 32 && stride == 1;
     return C == 32 && (N == 32 || N == 64) && (stride == 1 || stride == 2);
+}
+
+// the tcgen05 form also takes the 64-channel pairs of the 40x30 map (two K blocks per operand tile)
+bool fused_dwpw_tc_supported(int C, int N, int stride) {
+    return fused_dwpw_tma_supported(C, N, stride) || (C == 64 && N == 64 && stride == 1);
 }
 
 void fused_dwpw_tma_boxes(int stride, int* in_w, int* in_h, int* out_w, int* out_h) {
@@ -1066,6 +1081,7 @@ void launch_fused_dwpw_tc(const TmaMap& tm_in, const TmaMap& tm_out, const TmaMa
     else if (C == 32 && N == 32 && stride == 2) UF_T(32, 32, 2, 2, 2);
     else if (C == 32 && N == 64 && stride == 2) UF_T(32, 64, 2, 2, 2);
     else if (C == 32 && N == 64 && stride == 1) UF_T(32, 64, 1, 2, 4);
+    else if (C == 64 && N == 64 && stride == 1) UF_T(64, 64, 1, 2, 2);
 #undef UF_T
 }
 
