@@ -760,7 +760,11 @@ static void run_tail_post(uf_model& m, Lane& ln, Slot& s, uint32_t first, int fr
     float* scores = ln.d_scores + (size_t)first * K * 2;
     float* boxes = ln.d_boxes + (size_t)first * K * 4;
     PostBuffers pb{s.d_sort, (int)post_sort_scratch_elems(K), s.d_sel, s.d_dets, s.d_det_idx, s.d_counts};
-    if (m.cfg.flags & UF_FLAG_NO_FUSION) {
+    // one CTA per frame decodes its own priors before the NMS: worth a launch when there are enough frames to fill the
+    // GPU (or just one or two: batch-1 latency); a 32-frame stage of the 640x480 net (K = 17 640) decodes faster spread
+    // over all SMs by the separate kernel
+    const bool fuse_tail = !(m.cfg.flags & UF_FLAG_NO_FUSION) && (frames >= 96 || frames <= 2);
+    if (!fuse_tail) {
         {
             ProfScope ps(m, s, "tail_softmax_decode", (uint64_t)frames * K * 6 * 4 * 2, (uint64_t)frames * K * 6 * 4 * 2, 0);
             launch_tail(conf.p, loc.p, conf.frame_stride, loc.frame_stride, m.d_priors, K, m.plan.center_variance,
