@@ -87,6 +87,7 @@ typedef struct uf_config {
 #define UF_FLAG_NO_TC 8u         /* keep the 1x1 convs on the fp32 SIMT kernels (no tcgen05 3xTF32 path) */
 #define UF_FLAG_PDL 32u          /* launch the kernel chain with programmatic dependent launch (process-wide; measured neutral) */
 #define UF_FLAG_TMA_SIMT_PW 64u  /* fused dw+1x1 layers of the big maps: keep the 1x1 on the SIMT pipes (the pre-tcgen05 kernel) */
+#define UF_FLAG_DENSE3_TC 128u   /* dense 3x3 convs of the RFB branches as a tcgen05 implicit GEMM (zero-copy im2col; measured slower) */
 #define UF_FLAG_FUSE_DW_TC 16u   /* compute depthwise 3x3 inside the tensor-core GEMM's converter warps (C >= 64) */
 
 typedef struct uf_info {

@@ -13,6 +13,7 @@ STATUS = {0: "UF_OK", 1: "UF_ERR_INVALID_ARG", 2: "UF_ERR_IO", 3: "UF_ERR_ONNX",
 UF_NORM_REFERENCE, UF_NORM_127_128 = 0, 1
 UF_FLAG_FORCE_GENERIC, UF_FLAG_NO_GRAPH, UF_FLAG_NO_FUSION, UF_FLAG_NO_TC, UF_FLAG_FUSE_DW_TC, UF_FLAG_PDL = 1, 2, 4, 8, 16, 32
 UF_FLAG_TMA_SIMT_PW = 64
+UF_FLAG_DENSE3_TC = 128
 
 
 class uf_det(C.Structure):

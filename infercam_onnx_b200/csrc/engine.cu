@@ -51,7 +51,7 @@ struct ArgError : public std::exception {
 
 static thread_local std::string g_last_error;
 
-enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwTC, FusedDwPw, FusedPix, FusedHead, FusedHead2, FusedTma, SmallDense, Conv3x3Warp, Add, Relu, Copy };
+enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwTC, FusedDwPw, FusedPix, FusedHead, FusedHead2, FusedTma, SmallDense, SmallDenseTC, Conv3x3Warp, Add, Relu, Copy };
 
 static const char* impl_name(Impl i) {
     switch (i) {
@@ -68,6 +68,7 @@ static const char* impl_name(Impl i) {
         case Impl::FusedTma: return "fused_dw3x3_pw1x1_tma";
         case Impl::Conv3x3Warp: return "conv3x3_warp";
         case Impl::SmallDense: return "small_dense3x3";
+        case Impl::SmallDenseTC: return "dense3x3_tcgen05";
         case Impl::Add: return "eltwise_add";
         case Impl::Relu: return "eltwise_relu";
         case Impl::Copy: return "eltwise_copy";
@@ -388,6 +389,9 @@ static void build_steps(uf_model& m) {
                 }
             } else if (pw) {
                 st.impl = tc_ok(op) ? Impl::PointwiseTC : Impl::Pointwise;
+            } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.groups == 1 && op.in2 < 0 && !no_tc &&
+                       (m.cfg.flags & UF_FLAG_DENSE3_TC) && dense3x3_tc_supported(op.cin, op.cout, op.dil) && view_vec_ok(in)) {
+                st.impl = Impl::SmallDenseTC;  // zero-copy im2col on the tensor cores: correct, measured 20 % slower, opt-in
             } else if (op.k == 3 && op.stride == 1 && op.pad == op.dil && op.dil <= 8 && op.groups == 1 && op.in2 < 0 &&
                        small_dense_supported(op.cin, op.cout) && view_vec_ok(in) && view_vec_ok(out)) {
                 st.impl = Impl::SmallDense;
@@ -428,6 +432,37 @@ static void build_tc_weights(uf_model& m) {
                   : (!make_tmap_f32_2d(&t.tm_hi, t.d_hi, N, K, (uint64_t)K * 4, box) ||
                      !make_tmap_f32_2d(&t.tm_lo, t.d_lo, N, K, (uint64_t)K * 4, box)))
             throw CudaError("cuTensorMapEncodeTiled failed for 1x1 weights of '" + m.plan.tensors[op.out].name + "'");
+        st.tc = (int)m.tc_weights.size();
+        m.tc_weights.push_back(t);
+        m.weight_bytes += 2 * hi.size() * sizeof(float);
+    }
+}
+
+// SmallDenseTC: W[n][c][tap] as [tap][chunk q][n (16)][4 floats] (the no-swizzle K-major operand layout), tf32 hi / lo
+static void build_dense3_weights(uf_model& m) {
+    for (Step& st : m.steps) {
+        if (st.impl != Impl::SmallDenseTC) continue;
+        const Op& op = m.plan.ops[st.op];
+        const int CQ = ((op.cin + 7) / 8 * 8) / 4;
+        std::vector<float> hi(dense3x3_tc_weight_floats(op.cin), 0.f), lo(hi.size(), 0.f);
+        for (int n = 0; n < op.cout; ++n)
+            for (int c = 0; c < op.cin; ++c)
+                for (int tap = 0; tap < 9; ++tap) {
+                    const float w = op.w[((size_t)n * op.cin + c) * 9 + tap];  // ONNX [n][c][ky][kx]
+                    uint32_t u;
+                    memcpy(&u, &w, 4);
+                    u &= 0xffffe000u;
+                    float h;
+                    memcpy(&h, &u, 4);
+                    const size_t i = (((size_t)tap * CQ + c / 4) * 16 + n) * 4 + c % 4;
+                    hi[i] = h;
+                    lo[i] = w - h;
+                }
+        TcWeights t;
+        CK(cudaMalloc(&t.d_hi, hi.size() * sizeof(float)));
+        CK(cudaMalloc(&t.d_lo, lo.size() * sizeof(float)));
+        CK(cudaMemcpy(t.d_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(t.d_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
         st.tc = (int)m.tc_weights.size();
         m.tc_weights.push_back(t);
         m.weight_bytes += 2 * hi.size() * sizeof(float);
@@ -711,6 +746,11 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                     launch_fused_dwpw_tc(s.tm_a[si], s.tm_o[si], tw.tm_hi, tw.tm_lo, in, o2, st.host_w.data(), op.stride, op.relu,
                                          pw.relu, frames, s.stream);
                 }
+                break;
+            }
+            case Impl::SmallDenseTC: {
+                const TcWeights& tw = m.tc_weights[st.tc];
+                launch_dense3x3_tc(in, out, tw.d_hi, tw.d_lo, op.b.data(), op.dil, op.relu, frames, s.stream);
                 break;
             }
             case Impl::SmallDense: launch_small_dense(in, out, st.host_w.data(), op.dil, op.relu, frames, s.stream); break;
@@ -1001,6 +1041,7 @@ static uf_model* load_model(const uf_config& cfg_in) {
     pack_weights(*m);
     build_steps(*m);
     build_tc_weights(*m);
+    build_dense3_weights(*m);
     build_param_weights(*m);
     label_steps(*m);
     build_lut(*m);

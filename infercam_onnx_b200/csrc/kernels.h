@@ -77,6 +77,11 @@ void launch_head_dwpw(const TView& in, const TView& out, const float* host_w, in
 bool conv3x3_warp_supported(int cin, int cout);
 void launch_conv3x3_warp(const TView& in, const TView& out, const float* w_kkio, const float* b, int dil,
                          int relu, int frames, cudaStream_t s);
+// K6 on tcgen05 (kernels_tc.cu): dense 3x3, stride 1, pad = dil, Cin / Cout <= 16; zero-copy im2col from one staged tile
+bool dense3x3_tc_supported(int cin, int cout, int dil);
+size_t dense3x3_tc_weight_floats(int cin);
+void launch_dense3x3_tc(const TView& in, const TView& out, const float* w_hi, const float* w_lo, const float* host_bias, int dil,
+                        int relu, int frames, cudaStream_t s);
 // K6 small dense 3x3 (stride 1, pad = dil), Cin,Cout in {8,12,16}, weights [3][3][Cin][Cout]
 bool small_dense_supported(int cin, int cout);
 // host_w: 9*Cin*Cout weights [ky][kx][ci][co] + Cout biases in HOST memory (kernel-parameter constants); dil <= 8

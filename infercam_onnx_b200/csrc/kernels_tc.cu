@@ -1085,6 +1085,231 @@ void launch_fused_dwpw_tc(const TmaMap& tm_in, const TmaMap& tm_out, const TmaMa
 #undef UF_T
 }
 
+// ---------------------------------------------------------------------------------------------
+// K6 on the tensor cores: dense 3x3 convolution (stride 1, pad = dilation, Cin <= 16, Cout <= 16: the RFB branches) as
+// an implicit GEMM whose im2col costs nothing. A group stages the input tile (+ dilation halo) ONCE in shared memory
+// in the canonical NO-SWIZZLE K-major operand layout, channel-chunk major: T[q][pixel][4 floats] (q = 4-channel chunk).
+// In that layout 8 consecutive pixels of a tile row are one 8 x 16 B core matrix, the next 8-row group of the M tile
+// (the next output row) is IW * 16 B further (SBO) and the next 16 bytes of K (the next chunk) NPIX * 16 B further (LBO)
+// — and the operand of tap (ky, kx) is the SAME tile read from a start address shifted by ((ky*IW + kx) * dil) * 16 B.
+// Nine taps x Cin/8 k-steps x 3 (3xTF32) MMAs of 128 x 16 x 8 per 8 x 16 pixel tile replace 9*Cin*Cout FFMAs per pixel;
+// the SIMT work left is the tile staging (with the hi / lo split) and the 16-output epilogue. Same grouped layout as
+// the fused kernel above: one CTA per SM, G independent tile pipelines.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+struct Dense3Params {
+    TView in, out;
+    const float* w_hi;  // [9][CQ][16][4] floats: W[n][4q + j][tap], zero padded (n >= Cout, c >= Cin)
+    const float* w_lo;
+    int CQ;             // 4-channel chunks of K per tap, even (Cin padded to a multiple of 8)
+    int dil, relu;
+    int tiles_x, tiles_y, total_tiles;
+    int group_bytes;    // 2 * CQ * NPIX * 16 rounded up to 128
+    float bias[16];
+};
+
+template <int G, int U>  // G tile pipelines per CTA, U staging loads in flight per thread
+__global__ void __launch_bounds__(128 * G, 1)
+dense3x3_tc_kernel(const __grid_constant__ Dense3Params p) {
+    constexpr int TX = 8, TY = 16;
+    extern __shared__ __align__(128) uint8_t smem_d3[];
+    const int tid = threadIdx.x, g = tid >> 7, lt = tid & 127, lwarp = lt >> 5;
+    const int d = p.dil, IW = TX + 2 * d, IH = TY + 2 * d, NPIX = IH * IW, CQ = p.CQ;
+    const int w_bytes = 9 * CQ * 256;
+    uint8_t* w_hi = smem_d3;
+    uint8_t* w_lo = w_hi + w_bytes;
+    uint8_t* t_hi = w_lo + w_bytes + g * p.group_bytes;   // [CQ][NPIX][16 B]
+    uint8_t* t_lo = t_hi + CQ * NPIX * 16;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + w_bytes + G * p.group_bytes);
+    uint64_t* mma_bar = bars + g;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G);
+    constexpr int NACC = 4;  // independent accumulators per group: consecutive MMAs into ONE accumulator serialise on its
+                             // read-modify-write latency (~150 cycles each for these tiny N = 16 MMAs); the epilogue adds them up
+    constexpr uint32_t TMEM_COLS = G * NACC * 16 <= 256 ? 256 : 512;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int i = 0; i < G; ++i) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // weights: static, staged before the predecessor kernel is waited for
+    for (int i = tid; i < w_bytes / 16; i += 128 * G) {
+        reinterpret_cast<float4*>(w_hi)[i] = __ldg(reinterpret_cast<const float4*>(p.w_hi) + i);
+        reinterpret_cast<float4*>(w_lo)[i] = __ldg(reinterpret_cast<const float4*>(p.w_lo) + i);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    const int vcta = blockIdx.x * G + g, vgrid = gridDim.x * G;
+    const uint32_t acc = tmem_base + (uint32_t)(g * NACC * 16);
+    const uint32_t taddr = acc + ((uint32_t)(lwarp * 32) << 16);
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const bool vec = ((p.out.C & 3) == 0) && ((p.out.pix_stride & 3) == 0) && ((reinterpret_cast<size_t>(p.out.p) & 15) == 0) &&
+                     ((p.out.frame_stride & 3) == 0);
+    const int C4 = p.in.C >> 2;  // real 4-channel chunks (<= CQ)
+    int it = 0;
+    for (int tile = vcta; tile < p.total_tiles; tile += vgrid, ++it) {
+        int b = tile;
+        const int txi = b % p.tiles_x; b /= p.tiles_x;
+        const int tyi = b % p.tiles_y;
+        const int f = b / p.tiles_y;
+        const int x0 = txi * TX, y0 = tyi * TY;
+        // stage the tile: T[q][pix] = in[y0 - d + py][x0 - d + px][4q..4q+3] (zero outside the map / past Cin), hi and lo
+        const float* ip = p.in.p + (size_t)f * p.in.frame_stride;
+        const int items = NPIX * CQ;
+        for (int i0 = lt; i0 < items; i0 += U * 128) {
+            float4 v[U];
+            int so[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * 128;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                so[u] = -1;
+                if (i < items) {
+                    const int pix = i / CQ, q = i - pix * CQ;  // q fastest: a warp reads whole pixels (contiguous channels)
+                    const int py = pix / IW, px = pix - py * IW;
+                    const int gy = y0 - d + py, gx = x0 - d + px;
+                    so[u] = (q * NPIX + pix) * 16;
+                    if (q < C4 && gy >= 0 && gy < p.in.H && gx >= 0 && gx < p.in.W)
+                        v[u] = *reinterpret_cast<const float4*>(ip + ((size_t)gy * p.in.W + gx) * p.in.pix_stride + q * 4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (so[u] >= 0) {
+                    float4 l;
+                    l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xffffe000u);
+                    l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xffffe000u);
+                    l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xffffe000u);
+                    l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xffffe000u);
+                    *reinterpret_cast<float4*>(t_hi + so[u]) = v[u];  // kind::tf32 ignores the low 13 mantissa bits: raw = hi
+                    *reinterpret_cast<float4*>(t_lo + so[u]) = l;
+                }
+            }
+        }
+        fence_proxy_async();
+        group_sync();
+        if (lt == 0) {
+            tc_fence_after();
+            const uint32_t lbo_a = (uint32_t)NPIX * 16u, sbo_a = (uint32_t)IW * 16u;
+            int nmma = 0;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const uint32_t shift = (uint32_t)((ky * d * IW + kx * d) * 16);
+                for (int ks = 0; ks < CQ / 2; ++ks) {
+                    const uint32_t a_off = (uint32_t)(2 * ks) * lbo_a + shift;
+                    const uint64_t d_ahi = umma_desc_nosw(smem_u32(t_hi) + a_off, lbo_a, sbo_a);
+                    const uint64_t d_alo = umma_desc_nosw(smem_u32(t_lo) + a_off, lbo_a, sbo_a);
+                    const uint32_t w_off = (uint32_t)((tap * CQ + 2 * ks) * 256);
+                    const uint64_t d_whi = umma_desc_nosw(smem_u32(w_hi) + w_off, 256u, 128u);
+                    const uint64_t d_wlo = umma_desc_nosw(smem_u32(w_lo) + w_off, 256u, 128u);
+                    umma_tf32(acc + 16 * (nmma % NACC), d_alo, d_whi, idesc, nmma >= NACC ? 1u : 0u); ++nmma;
+                    umma_tf32(acc + 16 * (nmma % NACC), d_ahi, d_wlo, idesc, nmma >= NACC ? 1u : 0u); ++nmma;
+                    umma_tf32(acc + 16 * (nmma % NACC), d_ahi, d_whi, idesc, nmma >= NACC ? 1u : 0u); ++nmma;
+                }
+            }
+            umma_commit(mma_bar);
+        }
+        __syncwarp();
+        mbar_wait(mma_bar, (uint32_t)(it & 1));
+        tc_fence_after();
+        float v[16];
+        {
+            float part[32];
+            tmem_ld32(taddr, part, true);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = part[j] + part[16 + j];
+            tmem_ld32(taddr + 32, part, true);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += part[j] + part[16 + j];
+        }
+        tc_fence_before();
+        const int ox = x0 + (lt & 7), oy = y0 + (lt >> 3);  // M row = ty * 8 + tx
+        if (ox < p.out.W && oy < p.out.H) {
+            float* op = p.out.p + (size_t)f * p.out.frame_stride + ((size_t)oy * p.out.W + ox) * p.out.pix_stride;
+            if (vec) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    if (j < p.out.C) {
+                        float4 x = make_float4(v[j] + p.bias[j], v[j + 1] + p.bias[j + 1], v[j + 2] + p.bias[j + 2], v[j + 3] + p.bias[j + 3]);
+                        if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        *reinterpret_cast<float4*>(op + j) = x;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j < p.out.C) {
+                        const float x = v[j] + p.bias[j];
+                        op[j] = p.relu ? fmaxf(x, 0.f) : x;
+                    }
+                }
+            }
+        }
+        group_sync();  // every thread has read its accumulator row and the MMAs are done with the tile: both may be overwritten
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+bool dense3x3_tc_supported(int cin, int cout, int dil) {
+    return cin % 4 == 0 && cin >= 4 && cin <= 16 && cout >= 1 && cout <= 16 && dil >= 1 && dil <= 8;
+}
+
+size_t dense3x3_tc_weight_floats(int cin) { return (size_t)9 * (((cin + 7) / 8 * 8) / 4) * 16 * 4; }
+
+// w_hi / w_lo: DEVICE arrays in the layout of Dense3Params; host_bias: Cout floats (HOST)
+void launch_dense3x3_tc(const TView& in, const TView& out, const float* w_hi, const float* w_lo, const float* host_bias, int dil,
+                        int relu, int frames, cudaStream_t s) {
+    Dense3Params p;
+    p.in = in; p.out = out; p.w_hi = w_hi; p.w_lo = w_lo;
+    p.CQ = ((in.C + 7) / 8 * 8) / 4;
+    p.dil = dil; p.relu = relu;
+    p.tiles_x = (out.W + 7) / 8; p.tiles_y = (out.H + 15) / 16;
+    p.total_tiles = p.tiles_x * p.tiles_y * frames;
+    const int npix = (16 + 2 * dil) * (8 + 2 * dil);
+    p.group_bytes = (2 * p.CQ * npix * 16 + 127) / 128 * 128;
+    for (int i = 0; i < 16; ++i) p.bias[i] = i < out.C ? host_bias[i] : 0.f;
+    // as many tile pipelines as fit ~200 KB next to the weights (a TMEM kernel gets one CTA per SM)
+    const size_t fixed = (size_t)2 * 9 * p.CQ * 256 + 8 * 8 + 16 + 128;
+    const int fit = (int)((200 * 1024 - fixed) / p.group_bytes);
+    const int G = fit >= 6 ? 6 : (fit >= 4 ? 4 : 3);
+    const size_t smem = fixed + (size_t)G * p.group_bytes;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(dense3x3_tc_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(dense3x3_tc_kernel<4, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(dense3x3_tc_kernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured[dev & 63] = true;
+    }
+    int grid = 148;
+    if (grid > (p.total_tiles + G - 1) / G) grid = (p.total_tiles + G - 1) / G;
+    if (G == 6) launch_pdl(dense3x3_tc_kernel<6, 8>, dim3(grid), dim3(128 * 6), smem, s, p);
+    else if (G == 4) launch_pdl(dense3x3_tc_kernel<4, 12>, dim3(grid), dim3(128 * 4), smem, s, p);
+    else launch_pdl(dense3x3_tc_kernel<3, 16>, dim3(grid), dim3(128 * 3), smem, s, p);
+}
+
 #ifdef UF_TC_TIMING
 void tc_timing_read(long long* out16) { cudaMemcpyFromSymbol(out16, g_tc_timing, sizeof(long long) * 16); }
 #endif

@@ -175,7 +175,7 @@ def _layer_report(m, oracle, frame):
 
 
 @pytest.mark.parametrize("flags", [_capi.UF_FLAG_FORCE_GENERIC, _capi.UF_FLAG_NO_FUSION, _capi.UF_FLAG_NO_TC,
-                                   _capi.UF_FLAG_FUSE_DW_TC, _capi.UF_FLAG_TMA_SIMT_PW, 0])
+                                   _capi.UF_FLAG_FUSE_DW_TC, _capi.UF_FLAG_TMA_SIMT_PW, _capi.UF_FLAG_DENSE3_TC, 0])
 def test_every_materialised_layer_matches_oracle(make_onnx, oracle320, flags):
     m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240), flags=flags)
     try:
