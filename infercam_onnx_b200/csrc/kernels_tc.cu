@@ -772,8 +772,13 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     constexpr int A_REGION = 2 * A_BYTES < 16384 ? 16384 : 2 * A_BYTES;  // A_hi | A_lo, and at least the 16 KB staging tile
     constexpr int GROUP_BYTES = NB * SLICE_ALLOC + A_REGION;  // NB input slices in flight per group (memory latency)
     constexpr int W_BYTES = KBLK * WKB;
-    constexpr int NCOL = N <= 32 ? 32 : 64;  // accumulator columns per group
-    constexpr uint32_t TMEM_COLS = G * NCOL <= 32 ? 32 : (G * NCOL <= 64 ? 64 : (G * NCOL <= 128 ? 128 : 256));
+    constexpr int NPAD = N <= 32 ? 32 : 64;  // N as the MMA sees it
+    // One K block: W_hi and W_lo sit back to back in shared memory = ONE B operand of 2N rows, so a_hi * [w_hi | w_lo]
+    // is a single MMA into 2N accumulator columns (these small MMAs cost the same whatever their N) and a_lo * w_hi a
+    // second one into the first N: two MMAs per k-step instead of three, the epilogue adds the two halves.
+    constexpr bool WIDE = KBLK == 1 && N == NPAD;
+    constexpr int NCOL = WIDE ? 2 * NPAD : NPAD;  // accumulator columns per group
+    constexpr uint32_t TMEM_COLS = G * NCOL <= 32 ? 32 : (G * NCOL <= 64 ? 64 : (G * NCOL <= 128 ? 128 : (G * NCOL <= 256 ? 256 : 512)));
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, g = tid >> 7, lt = tid & 127, lwarp = lt >> 5;
@@ -837,7 +842,8 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     }
     const int tx = lt % TX, ty = lt / TX;
     // instruction descriptor: D=F32, A=B=TF32, K-major both, N>>3, M>>4 (M = 128)
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * NPAD) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // this thread's row of the A tiles: 16-byte chunk q lives at q ^ (row & 7) (128B swizzle) or q ^ ((row >> 1) & 3) (64B)
     const int a_row = lt * ROWB;
     const int a_swz = ROWB == 128 ? (lt & 7) : ((lt >> 1) & 3);
@@ -895,12 +901,19 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             for (int kb = 0; kb < KBLK; ++kb) {
                 const uint64_t d_ahi = umma_desc_kmajor(smem_u32(a_hi + kb * AKB), ROWB), d_alo = umma_desc_kmajor(smem_u32(a_lo + kb * AKB), ROWB);
                 const uint64_t d_whi = umma_desc_kmajor(smem_u32(w_hi + kb * WKB), ROWB), d_wlo = umma_desc_kmajor(smem_u32(w_lo + kb * WKB), ROWB);
+                if (WIDE) {
 #pragma unroll
-                for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_alo + 2 * k, d_whi + 2 * k, idesc, (kb | k) > 0 ? 1u : 0u);
+                    for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_whi + 2 * k, idesc2, k > 0 ? 1u : 0u);  // [w_hi | w_lo]
 #pragma unroll
-                for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1);
+                    for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_alo + 2 * k, d_whi + 2 * k, idesc, 1);
+                } else {
 #pragma unroll
-                for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_whi + 2 * k, idesc, 1);
+                    for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_alo + 2 * k, d_whi + 2 * k, idesc, (kb | k) > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < KC / 8; ++k) umma_tf32(acc, d_ahi + 2 * k, d_whi + 2 * k, idesc, 1);
+                }
             }
             umma_commit(mma_bar);
         }
@@ -913,6 +926,12 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         for (int n0 = 0; n0 < N; n0 += 32) {
             float v[32];
             tmem_ld32(taddr + n0, v, true);
+            if (WIDE) {  // + the a_hi * w_lo half
+                float v2[32];
+                tmem_ld32(taddr + NPAD + n0, v2, true);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += v2[j];
+            }
             if (n0 > 0) {  // second pass of a 64-output layer: wait until the first pass' store has read the staging tile
                 if (lt == 0) bulk_wait_read0();
                 group_sync();
