@@ -1098,7 +1098,7 @@ void launch_fused_dwpw_tc(const TmaMap& tm_in, const TmaMap& tm_out, const TmaMa
     if (C == 16 && N == 32 && stride == 1) UF_T(16, 32, 1, 5, 2);
     else if (C == 32 && N == 32 && stride == 1) UF_T(32, 32, 1, 3, 3);
     else if (C == 32 && N == 32 && stride == 2) UF_T(32, 32, 2, 2, 2);
-    else if (C == 32 && N == 64 && stride == 2) UF_T(32, 64, 2, 2, 2);
+    else if (C == 32 && N == 64 && stride == 2) UF_T(32, 64, 2, 3, 1);
     else if (C == 32 && N == 64 && stride == 1) UF_T(32, 64, 1, 2, 4);
     else if (C == 64 && N == 64 && stride == 1) UF_T(64, 64, 1, 2, 2);
 #undef UF_T
