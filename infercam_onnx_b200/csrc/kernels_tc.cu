@@ -26,6 +26,10 @@
 #include <cstdlib>
 #include <cstring>
 
+// dense3x3_tc_kernel operand layout: 1 = pixel-major rows with the 32B / 64B swizzle (keyed on absolute shared-memory
+// address bits, which is what makes a shifted descriptor start address legal), 0 = no-swizzle chunk-major planes.
+// Both are parity-green and equally fast; see the kernel's header comment.
+#define UF_D3_SWZ 1
 #include "kernels.h"
 #include "pdl.cuh"
 
@@ -1114,6 +1118,10 @@ void launch_fused_dwpw_tc(const TmaMap& tm_in, const TmaMap& tm_out, const TmaMa
 // Nine taps x Cin/8 k-steps x 3 (3xTF32) MMAs of 128 x 16 x 8 per 8 x 16 pixel tile replace 9*Cin*Cout FFMAs per pixel;
 // the SIMT work left is the tile staging (with the hi / lo split) and the 16-output epilogue. Same grouped layout as
 // the fused kernel above: one CTA per SM, G independent tile pipelines.
+// The swizzled form (UF_D3_SWZ, default) keeps the tile pixel-major, T[pixel][Cin floats] with the 32B / 64B swizzle
+// applied from ABSOLUTE shared-memory address bits, SBO = one tile row; measured on B200: a descriptor whose start
+// address is shifted by an arbitrary number of rows (not a multiple of the 8-row swizzle atom) reads such a tile
+// correctly with base_offset = 0, i.e. the tensor core derives the swizzle phase from the address, not from the row index.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
@@ -1141,9 +1149,19 @@ dense3x3_tc_kernel(const __grid_constant__ Dense3Params p) {
     const int w_bytes = 9 * CQ * 256;
     uint8_t* w_hi = smem_d3;
     uint8_t* w_lo = w_hi + w_bytes;
+#if UF_D3_SWZ
+    // experiment: pixel-major tile [pix][CQ * 16 B] with the 32B / 64B swizzle keyed on ABSOLUTE address bits; group regions 1 KB aligned
+    uint8_t* t_hi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w_lo + w_bytes) + 1023) & ~uintptr_t(1023)) + g * p.group_bytes;
+    uint8_t* t_lo = t_hi + p.group_bytes / 2;
+#else
     uint8_t* t_hi = w_lo + w_bytes + g * p.group_bytes;   // [CQ][NPIX][16 B]
     uint8_t* t_lo = t_hi + CQ * NPIX * 16;
+#endif
+#if UF_D3_SWZ
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(w_lo + w_bytes) + 1023) & ~uintptr_t(1023)) + G * p.group_bytes);
+#else
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + w_bytes + G * p.group_bytes);
+#endif
     uint64_t* mma_bar = bars + g;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G);
     constexpr int NACC = 4;  // independent accumulators per group: consecutive MMAs into ONE accumulator serialise on its
@@ -1203,7 +1221,15 @@ dense3x3_tc_kernel(const __grid_constant__ Dense3Params p) {
                     const int pix = i / CQ, q = i - pix * CQ;  // q fastest: a warp reads whole pixels (contiguous channels)
                     const int py = pix / IW, px = pix - py * IW;
                     const int gy = y0 - d + py, gx = x0 - d + px;
+#if UF_D3_SWZ
+                    {
+                        const uint32_t rowa = smem_u32(t_hi) + (uint32_t)pix * (uint32_t)(CQ * 16);
+                        const int sw = CQ == 4 ? (int)((rowa >> 7) & 3u) : (int)((rowa >> 7) & 1u);
+                        so[u] = pix * (CQ * 16) + ((q ^ sw) << 4);
+                    }
+#else
                     so[u] = (q * NPIX + pix) * 16;
+#endif
                     if (q < C4 && gy >= 0 && gy < p.in.H && gx >= 0 && gx < p.in.W)
                         v[u] = *reinterpret_cast<const float4*>(ip + ((size_t)gy * p.in.W + gx) * p.in.pix_stride + q * 4);
                 }
@@ -1231,9 +1257,18 @@ dense3x3_tc_kernel(const __grid_constant__ Dense3Params p) {
                 const int ky = tap / 3, kx = tap - ky * 3;
                 const uint32_t shift = (uint32_t)((ky * d * IW + kx * d) * 16);
                 for (int ks = 0; ks < CQ / 2; ++ks) {
+#if UF_D3_SWZ
+                    const uint32_t rowb = (uint32_t)CQ * 16u;
+                    const uint32_t a_off = (uint32_t)((ky * d * IW + kx * d)) * rowb + (uint32_t)ks * 32u;
+                    const uint64_t lay = CQ == 4 ? 4ull : 6ull;  // SWIZZLE_64B / SWIZZLE_32B
+                    const uint32_t a_hi_addr = smem_u32(t_hi) + a_off, a_lo_addr = smem_u32(t_lo) + a_off;
+                    const uint64_t d_ahi = (uint64_t)((a_hi_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(((uint32_t)IW * rowb) >> 4) << 32) | (1ull << 46) | (lay << 61);
+                    const uint64_t d_alo = (uint64_t)((a_lo_addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(((uint32_t)IW * rowb) >> 4) << 32) | (1ull << 46) | (lay << 61);
+#else
                     const uint32_t a_off = (uint32_t)(2 * ks) * lbo_a + shift;
                     const uint64_t d_ahi = umma_desc_nosw(smem_u32(t_hi) + a_off, lbo_a, sbo_a);
                     const uint64_t d_alo = umma_desc_nosw(smem_u32(t_lo) + a_off, lbo_a, sbo_a);
+#endif
                     const uint32_t w_off = (uint32_t)((tap * CQ + 2 * ks) * 256);
                     const uint64_t d_whi = umma_desc_nosw(smem_u32(w_hi) + w_off, 256u, 128u);
                     const uint64_t d_wlo = umma_desc_nosw(smem_u32(w_lo) + w_off, 256u, 128u);
@@ -1306,10 +1341,14 @@ void launch_dense3x3_tc(const TView& in, const TView& out, const float* w_hi, co
     p.tiles_x = (out.W + 7) / 8; p.tiles_y = (out.H + 15) / 16;
     p.total_tiles = p.tiles_x * p.tiles_y * frames;
     const int npix = (16 + 2 * dil) * (8 + 2 * dil);
+#if UF_D3_SWZ
+    p.group_bytes = (2 * p.CQ * npix * 16 + 2047) / 2048 * 2048;
+#else
     p.group_bytes = (2 * p.CQ * npix * 16 + 127) / 128 * 128;
+#endif
     for (int i = 0; i < 16; ++i) p.bias[i] = i < out.C ? host_bias[i] : 0.f;
     // as many tile pipelines as fit ~200 KB next to the weights (a TMEM kernel gets one CTA per SM)
-    const size_t fixed = (size_t)2 * 9 * p.CQ * 256 + 8 * 8 + 16 + 128;
+    const size_t fixed = (size_t)2 * 9 * p.CQ * 256 + 8 * 8 + 16 + 128 + 1024;
     const int fit = (int)((200 * 1024 - fixed) / p.group_bytes);
     const int G = fit >= 6 ? 6 : (fit >= 4 ? 4 : 3);
     const size_t smem = fixed + (size_t)G * p.group_bytes;
