@@ -182,6 +182,8 @@ struct TcParams {
     int has_res, relu;
     int M, K, N, n_umma, stages, tmem_cols;
     int tma_store;      // epilogue leaves through TMA (dense, 16-byte aligned rows, no residual)
+    int wide;           // a_hi x [w_hi | w_lo] as ONE MMA into 2 * n_umma columns (the tensor pipe's time goes with the A
+                        // operand read, M x K, not with N): 8 MMAs per K block instead of 12, the epilogue adds the halves
     // depthwise mode: the A operand is not loaded but COMPUTED by the converter warps, A = relu(dw3x3(in) + b)
     int dw_mode, dw_stride, dw_relu;
     TView dw_in;
@@ -218,6 +220,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = (p.M + TC_BM - 1) / TC_BM;
     const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+    const int acc_stride = p.wide ? 2 * p.n_umma : p.n_umma;  // TMEM columns per accumulator buffer
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -271,6 +274,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_umma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * p.n_umma) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             TC_T0();
             int s = 0;
             uint32_t ph = 0;
@@ -280,7 +284,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 const uint32_t aph = (uint32_t)((it >> 1) & 1);
                 TC_WAIT(mbar_wait(&acc_empty[a], aph ^ 1));
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(a * p.n_umma);
+                const uint32_t d = tmem_base + (uint32_t)(a * acc_stride);
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     TC_WAIT(mbar_wait(&full[s], ph));
@@ -290,12 +294,19 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     // descriptors once per stage; advancing K by 8 tf32 = 32 bytes is +2 in the 16-byte address field
                     const uint64_t d_ahi = umma_desc_sw128(st), d_alo = umma_desc_sw128(st + TC_A_BYTES);
                     const uint64_t d_whi = umma_desc_sw128(st + 2 * TC_A_BYTES), d_wlo = umma_desc_sw128(st + 2 * TC_A_BYTES + b_bytes);
+                    if (p.wide) {  // W_hi and W_lo are adjacent in the stage: one B operand of 2 * n_umma rows
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) { umma_tf32(d, d_alo + 2 * k, d_whi + 2 * k, idesc, accumulate); accumulate = 1; }
+                        for (int k = 0; k < TC_BK / 8; ++k) { umma_tf32(d, d_ahi + 2 * k, d_whi + 2 * k, idesc2, accumulate); accumulate = 1; }
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(d, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1);
+                        for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(d, d_alo + 2 * k, d_whi + 2 * k, idesc, 1);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(d, d_ahi + 2 * k, d_whi + 2 * k, idesc, 1);
+                        for (int k = 0; k < TC_BK / 8; ++k) { umma_tf32(d, d_alo + 2 * k, d_whi + 2 * k, idesc, accumulate); accumulate = 1; }
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(d, d_ahi + 2 * k, d_wlo + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(d, d_ahi + 2 * k, d_whi + 2 * k, idesc, 1);
+                    }
                     umma_commit(&empty[s]);  // implies tcgen05.fence::before_thread_sync
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
@@ -439,7 +450,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 const uint32_t aph = (uint32_t)((it >> 1) & 1);
                 TC_WAIT(mbar_wait(&acc_full[a], aph));
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_umma);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_stride);
                 bool released = false;
                 for (int c0 = 32 * grp; c0 < p.n_umma; c0 += 32 * ngrp) {
                     if (lane == 0) bulk_wait_read0();  // this warp's previous store has left its staging tile
@@ -450,6 +461,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     }
                     float v[32];
                     tmem_ld32(taddr + c0, v, c0 + 16 < p.n_umma);
+                    if (p.wide) {  // + the a_hi * w_lo half
+                        float v2[32];
+                        tmem_ld32(taddr + p.n_umma + c0, v2, c0 + 16 < p.n_umma);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+                    }
                     if (c0 + 32 * ngrp >= p.n_umma) {  // last read of this accumulator: hand it back to the MMA warp now
                         tc_fence_before();
                         __syncwarp();
@@ -505,11 +522,17 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             mbar_wait(&acc_full[a], aph);
             tc_fence_after();
             const int m_base = tile * TC_BM + q * 32;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_umma);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_stride);
             for (int c0 = 0; c0 < p.n_umma; c0 += 32) {
                 float v[32];
                 tmem_ld16(taddr + c0, v);  // warp-collective: executed by every lane
                 if (c0 + 16 < p.n_umma) tmem_ld16(taddr + c0 + 16, v + 16);
+                if (p.wide) {
+                    float v2[32];
+                    tmem_ld32(taddr + p.n_umma + c0, v2, c0 + 16 < p.n_umma);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += (j < 16 || c0 + 16 < p.n_umma) ? v2[j] : 0.f;
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
@@ -1422,8 +1445,9 @@ void launch_pointwise_tc(const TmaMap& tm_a, const TmaMap& tm_whi, const TmaMap&
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
     p.stages = stages;
+    p.wide = p.n_umma <= 128 ? 1 : 0;  // 2 * n_umma <= 256 (the MMA's N limit) and two such accumulators fit 512 columns
     int cols = 32;
-    while (cols < 2 * p.n_umma) cols <<= 1;
+    while (cols < 2 * (p.wide ? 2 * p.n_umma : p.n_umma)) cols <<= 1;
     p.tmem_cols = cols;
     // stages | barriers + tmem slot | (pad to 1 KB) | 4 per-warp staging tiles of 4.6 KB (legacy) / 4 KB (TMA store)
     const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 12) * sizeof(uint64_t) + 16 + 1024 + 8 * 4096 + 1024;
