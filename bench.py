@@ -65,7 +65,7 @@ def workload_name(args):
 
 
 def make_model_file(tmpdir, args):
-    from infercam_onnx_b200.onnx_fixture import write_ultraface_onnx
+    from tools.onnx_fixture import write_ultraface_onnx
     w, h = (int(v) for v in args.net.split("x"))
     path = os.path.join(tmpdir, f"ultraface-{args.variant}-{w}.onnx")
     write_ultraface_onnx(path, width=w, height=h, variant=args.variant, seed=0,

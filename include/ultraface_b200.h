@@ -165,6 +165,10 @@ UF_API int uf_profile_read(uf_model* m, uf_kernel_stat* out, uint32_t cap, uint3
 /* number of kernel launches issued by this handle since load (the library's own kernels only) */
 UF_API int uf_launch_count(const uf_model* m, uint64_t* n);
 
+/* fault injection for the error-path tests: every following uf_infer_batch* call on this handle fails with UF_ERR_CUDA
+ * after `stages` pipeline stages have been submitted (stages < 0: off). A failed call leaves the handle usable. */
+UF_API int uf_debug_fail_after(uf_model* m, int32_t stages);
+
 /* ---- host-only entry points (no GPU needed): loader / lowering / tap tables ---- */
 /* Parses + lowers the ONNX file and writes a JSON description (ops after folding with weight
  * checksums, heads, prior count, MACs, bytes) into out[cap]; *needed = bytes incl. NUL. */

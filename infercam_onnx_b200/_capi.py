@@ -67,6 +67,7 @@ SIGNATURES = {
     "uf_profile_reset": (C.c_int, [C.c_void_p]),
     "uf_profile_read": (C.c_int, [C.c_void_p, _p(uf_kernel_stat), C.c_uint32, _p(C.c_uint32)]),
     "uf_launch_count": (C.c_int, [C.c_void_p, _p(C.c_uint64)]),
+    "uf_debug_fail_after": (C.c_int, [C.c_void_p, C.c_int32]),
     "uf_onnx_inspect": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t, _p(C.c_size_t)]),
     "uf_resize_taps": (C.c_int, [C.c_uint32, C.c_uint32, _p(C.c_int32), _p(C.c_int32), _p(C.c_float), C.c_uint32,
                                  _p(C.c_uint32)]),

@@ -98,7 +98,15 @@ struct TapsEntry {
     int *d_vleft = nullptr, *d_vn = nullptr, *d_hleft = nullptr, *d_hn = nullptr;
     float *d_vw = nullptr, *d_hw = nullptr;
     ResizeTapsDev dev{};
+    uint64_t last_use = 0;
+    TapsEntry() = default;
+    TapsEntry(const TapsEntry&) = delete;
+    TapsEntry& operator=(const TapsEntry&) = delete;
+    // cudaFree waits for the device, so kernels already queued with these tables finish first
+    ~TapsEntry() { cudaFree(d_vleft); cudaFree(d_vn); cudaFree(d_vw); cudaFree(d_hleft); cudaFree(d_hn); cudaFree(d_hw); }
 };
+using TapsRef = std::shared_ptr<TapsEntry>;
+constexpr size_t TAPS_CACHE_MAX = 32;  // distinct source sizes kept on the device (sizes come from network peers)
 
 constexpr int DET_FAST = 128;  // detections per frame copied back with the counts in one D2H
 
@@ -109,8 +117,9 @@ struct Slot {
     uint8_t* d_resized = nullptr;
     float* d_arena = nullptr;
     float *d_dets = nullptr, *d_sel = nullptr;
-    int *d_counts = nullptr, *d_det_idx = nullptr;
+    int *d_counts = nullptr, *d_det_idx = nullptr, *d_big_n = nullptr;
     unsigned long long* d_sort = nullptr;
+    unsigned* d_mask = nullptr;  // NMS suppression bit matrix [chunk][K][pitch] (frames with many candidates)
     int* h_counts = nullptr;   // pinned [chunk]
     float* h_dets = nullptr;   // pinned [chunk][DET_FAST][5]
     // pending work description
@@ -167,9 +176,11 @@ struct uf_model {
     float* d_priors = nullptr;
     std::vector<std::unique_ptr<Lane>> lanes;
     std::atomic<uint32_t> lane_rr{0};
-    std::map<std::pair<int, int>, TapsEntry> taps;
+    std::map<std::pair<int, int>, TapsRef> taps;
+    uint64_t taps_clock = 0;
     std::atomic<uint64_t> launches{0};
-    bool profiling = false;
+    std::atomic<bool> profiling{false};
+    std::atomic<int> fail_after_stages{-1};  // fault injection (uf_debug_fail_after): throw after that many submits
     std::vector<KernelStat> stats;
     std::map<std::string, int> stat_index;
     // hook scratch (uf_postproc / uf_preproc_*), grown on demand
@@ -213,13 +224,13 @@ struct ProfScope {
     uf_model& m;
     Slot& s;
     bool on;
-    ProfScope(uf_model& mm, Slot& ss, const std::string& name, uint64_t alg, uint64_t minb, uint64_t flops)
+    ProfScope(uf_model& mm, Slot& ss, const std::string& name, uint64_t alg, uint64_t minb, uint64_t flops, int n_launches = 1)
         : m(mm), s(ss), on(mm.profiling) {
-        m.launches++;
+        m.launches += (uint64_t)n_launches;
         if (!on) return;
         std::lock_guard<std::mutex> lk(m.aux_mu);
         int id = stat_id(m, name);
-        m.stats[id].launches++;
+        m.stats[id].launches += (uint64_t)n_launches;
         m.stats[id].alg_bytes += alg;
         m.stats[id].min_bytes += minb;
         m.stats[id].flops += flops;
@@ -560,6 +571,13 @@ static void alloc_lane(uf_model& m, Lane& ln) {
         CK(cudaMalloc(&s.d_det_idx, (size_t)m.chunk * K * sizeof(int)));
         CK(cudaMalloc(&s.d_counts, (size_t)m.chunk * sizeof(int)));
         CK(cudaMalloc(&s.d_sort, (size_t)m.chunk * sort_cap * sizeof(unsigned long long)));
+        CK(cudaMalloc(&s.d_big_n, (size_t)m.chunk * sizeof(int)));
+        CK(cudaMemsetAsync(s.d_big_n, 0, (size_t)m.chunk * sizeof(int), s.stream));
+        if (post_mask_supported(K)) {
+            const size_t mb = (size_t)m.chunk * K * post_mask_pitch(K) * sizeof(unsigned);
+            CK(cudaMalloc(&s.d_mask, mb));
+            ws += mb;
+        }
         CK(cudaMallocHost(&s.h_counts, (size_t)m.chunk * sizeof(int)));
         CK(cudaMallocHost(&s.h_dets, (size_t)m.chunk * DET_FAST * 5 * sizeof(float)));
         ws += s.d_in_cap + (size_t)m.chunk * H * W * 3 + arena + (size_t)m.chunk * K * (5 + 4 + 1) * 4 +
@@ -617,12 +635,13 @@ static void alloc_lane(uf_model& m, Lane& ln) {
     m.workspace_bytes += ws;
 }
 
-static TapsEntry& get_taps(uf_model& m, int sw, int sh) {
-    std::lock_guard<std::mutex> lk(m.aux_mu);  // std::map nodes are stable: the reference outlives the lock
+static TapsRef get_taps(uf_model& m, int sw, int sh) {
+    std::lock_guard<std::mutex> lk(m.aux_mu);
     auto key = std::make_pair(sw, sh);
     auto it = m.taps.find(key);
-    if (it != m.taps.end()) return it->second;
-    TapsEntry e;
+    if (it != m.taps.end()) { it->second->last_use = ++m.taps_clock; return it->second; }
+    TapsRef ep = std::make_shared<TapsEntry>();  // a CK throw below frees what was already allocated
+    TapsEntry& e = *ep;
     e.v = build_axis_taps(sh, m.plan.net_h);
     e.h = build_axis_taps(sw, m.plan.net_w);
     auto up_i = [](const std::vector<int32_t>& v, int** d) {
@@ -661,7 +680,15 @@ static TapsEntry& get_taps(uf_model& m, int sw, int sh) {
                                                std::to_string(sw) + "x" + std::to_string(sh) + ")");
     e.dev = ResizeTapsDev{e.d_vleft, e.d_vn, e.d_vw, vpitch, e.d_hleft, e.d_hn, e.d_hw, hpitch, tw, th, cols,
                           tw > 64 ? 64 : 0, tw > 64 ? max_tile_span(e.h, 64) : 0};
-    return m.taps.emplace(key, std::move(e)).first->second;
+    if (m.taps.size() >= TAPS_CACHE_MAX) {  // evict the least recently used size (callers still using it hold a reference)
+        auto old = m.taps.begin();
+        for (auto jt = m.taps.begin(); jt != m.taps.end(); ++jt)
+            if (jt->second->last_use < old->second->last_use) old = jt;
+        m.taps.erase(old);
+    }
+    e.last_use = ++m.taps_clock;
+    m.taps.emplace(key, ep);
+    return ep;
 }
 
 // ---- execution -----------------------------------------------------------------------------
@@ -773,17 +800,23 @@ static void harvest(uf_model& m, Slot& s, uf_det* out, uint32_t cap, uint32_t* n
     wait_slot(m, s);
     s.pending = false;
     const int K = m.K;
+    uint32_t max_take = 0;
     for (uint32_t i = 0; i < s.n; ++i) {
         const uint32_t cnt = (uint32_t)s.h_counts[i];
         const uint32_t g = s.first + i;
         if (n_out) n_out[g] = cnt;
         if (!out || cap == 0) continue;
         const uint32_t take = std::min(cnt, cap);
-        const uint32_t fast = std::min<uint32_t>(take, DET_FAST);
-        memcpy(out + (size_t)g * cap, s.h_dets + (size_t)i * DET_FAST * 5, (size_t)fast * sizeof(uf_det));
-        if (take > fast)  // rare: more than DET_FAST faces in one frame
-            CK(cudaMemcpy(out + (size_t)g * cap + fast, s.d_dets + ((size_t)i * K + fast) * 5,
-                          (size_t)(take - fast) * sizeof(uf_det), cudaMemcpyDeviceToHost));
+        max_take = std::max(max_take, take);
+        memcpy(out + (size_t)g * cap, s.h_dets + (size_t)i * DET_FAST * 5, (size_t)std::min<uint32_t>(take, DET_FAST) * sizeof(uf_det));
+    }
+    // frames with more than DET_FAST faces (the NMS-heavy configuration): ONE strided copy for the whole stage,
+    // sized from the largest count, straight into the caller's rows (entries past n_out[i] are unspecified)
+    if (max_take > DET_FAST) {
+        CK(cudaMemcpy2DAsync(out + (size_t)s.first * cap + DET_FAST, (size_t)cap * sizeof(uf_det), s.d_dets + (size_t)DET_FAST * 5,
+                             (size_t)K * sizeof(uf_det), (size_t)(max_take - DET_FAST) * sizeof(uf_det), s.n,
+                             cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
     }
 }
 
@@ -799,7 +832,8 @@ static void run_tail_post(uf_model& m, Lane& ln, Slot& s, uint32_t first, int fr
     }
     float* scores = ln.d_scores + (size_t)first * K * 2;
     float* boxes = ln.d_boxes + (size_t)first * K * 4;
-    PostBuffers pb{s.d_sort, (int)post_sort_scratch_elems(K), s.d_sel, s.d_dets, s.d_det_idx, s.d_counts};
+    PostBuffers pb{s.d_sort, (int)post_sort_scratch_elems(K), s.d_sel, s.d_dets, s.d_det_idx, s.d_counts,
+                   s.d_mask, post_mask_pitch(K), s.d_big_n};
     // one CTA per frame decodes its own priors before the NMS: worth a launch when there are enough frames to fill the
     // GPU (or just one or two: batch-1 latency); a 32-frame stage of the 640x480 net (K = 17 640) decodes faster spread
     // over all SMs by the separate kernel
@@ -817,6 +851,10 @@ static void run_tail_post(uf_model& m, Lane& ln, Slot& s, uint32_t first, int fr
         ProfScope ps(m, s, "tail_post_softmax_decode_nms", (uint64_t)frames * K * 6 * 4 * 2, (uint64_t)frames * K * 6 * 4 * 2, 0);
         launch_tail_post(conf.p, loc.p, conf.frame_stride, loc.frame_stride, m.d_priors, m.plan.center_variance,
                          m.plan.size_variance, scores, boxes, K, m.cfg.min_confidence, m.cfg.max_iou, pb, frames, s.stream);
+    }
+    if (pb.mask) {  // frames with more than a few hundred candidates: suppression bit matrix + ordered sweep (2 launches)
+        ProfScope ps(m, s, "nms_bitmatrix_sweep", 0, 0, 0, 2);
+        launch_nms_big(scores, K, m.cfg.max_iou, pb, frames, s.stream);
     }
     CK(cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)frames * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaMemcpy2DAsync(s.h_dets, (size_t)DET_FAST * 5 * sizeof(float), s.d_dets, (size_t)K * 5 * sizeof(float),
@@ -886,6 +924,17 @@ struct FrameSrc {
     uint32_t w, h;
 };
 
+// staging buffer for frames that need a resize; a failed re-allocation leaves the slot empty, not broken
+static void grow_input(Slot& s, size_t need) {
+    if (need <= s.d_in_cap) return;
+    CK(cudaStreamSynchronize(s.stream));
+    cudaFree(s.d_in);
+    s.d_in = nullptr;
+    s.d_in_cap = 0;
+    CK(cudaMalloc(&s.d_in, need));
+    s.d_in_cap = need;
+}
+
 // One chunk of host frames on slot s.
 static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, uint32_t first, uint32_t n) {
     const int W = m.plan.net_w, H = m.plan.net_h;
@@ -894,13 +943,7 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
     size_t need = 0;
     for (uint32_t i = 0; i < n; ++i)
         if ((int)fr[i].w != W || (int)fr[i].h != H) need += (size_t)fr[i].w * fr[i].h * 3 + 16;
-    if (need > s.d_in_cap) {
-        CK(cudaStreamSynchronize(s.stream));
-        CK(cudaFree(s.d_in));
-        s.d_in = nullptr;
-        CK(cudaMalloc(&s.d_in, need));
-        s.d_in_cap = need;
-    }
+    grow_input(s, need);
     size_t off = 0;
     uint32_t i = 0;
     while (i < n) {
@@ -919,10 +962,10 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
             a = b;
         }
         if (!ident) {
-            TapsEntry& t = get_taps(m, fr[i].w, fr[i].h);
+            TapsRef t = get_taps(m, fr[i].w, fr[i].h);
             ProfScope ps(m, s, "resize_triangle", (uint64_t)(j - i) * (fb + out_frame), (uint64_t)(j - i) * (fb + out_frame), 0);
             launch_resize(s.d_in + off, (long long)fb, fr[i].w, fr[i].h, s.d_resized + (size_t)i * out_frame,
-                          (long long)out_frame, W, H, (int)(j - i), t.dev, m.cfg.resize_round_intermediate, s.stream);
+                          (long long)out_frame, W, H, (int)(j - i), t->dev, m.cfg.resize_round_intermediate, s.stream);
             off += (size_t)(j - i) * fb;
         }
         i = j;
@@ -941,9 +984,9 @@ static void run_chunk_device(uf_model& m, Lane& ln, Slot& s, const uint8_t* d_rg
         input.p = d_rgb;  // identity resize (sample.rs early return): the stem reads the caller's frames
         input.frame_stride = (long long)fb;
     } else {
-        TapsEntry& t = get_taps(m, w, h);
+        TapsRef t = get_taps(m, w, h);
         ProfScope ps(m, s, "resize_triangle", (uint64_t)n * (fb + out_frame), (uint64_t)n * (fb + out_frame), 0);
-        launch_resize(d_rgb, (long long)fb, w, h, s.d_resized, (long long)out_frame, W, H, (int)n, t.dev,
+        launch_resize(d_rgb, (long long)fb, w, h, s.d_resized, (long long)out_frame, W, H, (int)n, t->dev,
                       m.cfg.resize_round_intermediate, s.stream);
     }
     run_body(m, ln, s, input, first, (int)n);
@@ -952,6 +995,25 @@ static void run_chunk_device(uf_model& m, Lane& ln, Slot& s, const uint8_t* d_rg
 
 // `taper`: shrink the last pipeline stages (host input). The copy of stage i+1 hides behind the kernels of stage
 // i, but nothing hides the kernels of the LAST stage, so the tail of the batch is cut into smaller stages.
+// after a failed call: nothing of it may survive into the next one (a stale `pending` slot would make the next
+// call's harvest write the failed call's results into the new caller's, possibly much smaller, arrays)
+static void abandon_lane(uf_model& m, Lane& ln) {
+    for (auto& s : ln.slots) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s.stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(s.stream, &g);
+            if (g) cudaGraphDestroy(g);
+        }
+        cudaStreamSynchronize(s.stream);
+        s.pending = false;
+        s.ev_used = 0;
+        s.n = 0;
+    }
+    ln.last_n = 0;
+    cudaGetLastError();
+}
+
 template <typename F>
 static void run_pipeline(uf_model& m, Lane& ln, uint32_t n, uint32_t step, bool taper, uf_det* out, uint32_t cap,
                          uint32_t* n_out, F&& submit) {
@@ -960,19 +1022,26 @@ static void run_pipeline(uf_model& m, Lane& ln, uint32_t n, uint32_t step, bool 
     const uint32_t nslots = m.profiling ? 1 : m.nslots;  // profiling: one stream, so event pairs time kernels alone
     uint32_t c = 0;
     ++ln.batch_id;
-    for (uint32_t first = 0; first < n; ++c) {
-        uint32_t cnt = std::min(step, n - first);
-        if (taper && !m.profiling) {
-            const uint32_t rem = n - first;
-            if (rem <= step && rem > 16) cnt = std::max<uint32_t>(16, (rem / 2 + 7) / 8 * 8);
+    try {
+        for (uint32_t first = 0; first < n; ++c) {
+            uint32_t cnt = std::min(step, n - first);
+            if (taper && !m.profiling) {
+                const uint32_t rem = n - first;
+                if (rem <= step && rem > 16) cnt = std::max<uint32_t>(16, (rem / 2 + 7) / 8 * 8);
+            }
+            Slot& s = ln.slots[c % nslots];
+            harvest(m, s, out, cap, n_out);
+            if (m.fail_after_stages.load() >= 0 && (int)c >= m.fail_after_stages.load())
+                throw CudaError("injected fault after " + std::to_string(c) + " pipeline stages (uf_debug_fail_after)");
+            submit(s, first, cnt);
+            s.batch_id = ln.batch_id;
+            first += cnt;
         }
-        Slot& s = ln.slots[c % nslots];
-        harvest(m, s, out, cap, n_out);
-        submit(s, first, cnt);
-        s.batch_id = ln.batch_id;
-        first += cnt;
+        for (uint32_t k = 0; k < nslots; ++k) harvest(m, ln.slots[(c + k) % nslots], out, cap, n_out);
+    } catch (...) {
+        abandon_lane(m, ln);
+        throw;
     }
-    for (uint32_t k = 0; k < nslots; ++k) harvest(m, ln.slots[(c + k) % nslots], out, cap, n_out);
     ln.last_n = n;
 }
 
@@ -1068,14 +1137,11 @@ uf_model::~uf_model() {
         for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         for (auto& g : s.graphs) cudaGraphExecDestroy(g.second);
         cudaFree(s.d_in); cudaFree(s.d_resized); cudaFree(s.d_arena); cudaFree(s.d_dets); cudaFree(s.d_sel);
-        cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort);
+        cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort); cudaFree(s.d_big_n); cudaFree(s.d_mask);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_dets);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    for (auto& kv : taps) {
-        TapsEntry& t = kv.second;
-        cudaFree(t.d_vleft); cudaFree(t.d_vn); cudaFree(t.d_vw); cudaFree(t.d_hleft); cudaFree(t.d_hn); cudaFree(t.d_hw);
-    }
+    taps.clear();
     for (auto& t : tc_weights) { cudaFree(t.d_hi); cudaFree(t.d_lo); }
     for (auto& lane : lanes) { cudaFree(lane->d_scores); cudaFree(lane->d_boxes); }
     cudaFree(d_weights); cudaFree(d_lut); cudaFree(d_priors); cudaFree(d_hook);
@@ -1198,17 +1264,11 @@ static void preproc_to_slot0(uf_model* m, Lane& ln, const uint8_t* rgb, uint32_t
     if ((int)w == W && (int)h == H) {
         CK(cudaMemcpyAsync(s.d_resized, rgb, fb, cudaMemcpyHostToDevice, s.stream));
     } else {
-        if (fb > s.d_in_cap) {
-            CK(cudaStreamSynchronize(s.stream));
-            CK(cudaFree(s.d_in));
-            s.d_in = nullptr;
-            CK(cudaMalloc(&s.d_in, fb));
-            s.d_in_cap = fb;
-        }
+        grow_input(s, fb);
         CK(cudaMemcpyAsync(s.d_in, rgb, fb, cudaMemcpyHostToDevice, s.stream));
-        TapsEntry& t = get_taps(*m, w, h);
+        TapsRef t = get_taps(*m, w, h);
         m->launches++;
-        launch_resize(s.d_in, (long long)fb, w, h, s.d_resized, (long long)W * H * 3, W, H, 1, t.dev,
+        launch_resize(s.d_in, (long long)fb, w, h, s.d_resized, (long long)W * H * 3, W, H, 1, t->dev,
                       m->cfg.resize_round_intermediate, s.stream);
     }
 }
@@ -1239,17 +1299,11 @@ int uf_preproc_u8_batch(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h,
         if ((int)w == W && (int)h == H) {
             CK(cudaMemcpyAsync(s.d_resized, rgb, fb * n, cudaMemcpyHostToDevice, s.stream));
         } else {
-            if (fb * n > s.d_in_cap) {
-                CK(cudaStreamSynchronize(s.stream));
-                CK(cudaFree(s.d_in));
-                s.d_in = nullptr;
-                CK(cudaMalloc(&s.d_in, fb * n));
-                s.d_in_cap = fb * n;
-            }
+            grow_input(s, fb * n);
             CK(cudaMemcpyAsync(s.d_in, rgb, fb * n, cudaMemcpyHostToDevice, s.stream));
-            TapsEntry& t = get_taps(*m, w, h);
+            TapsRef t = get_taps(*m, w, h);
             m->launches++;
-            launch_resize(s.d_in, (long long)fb, w, h, s.d_resized, (long long)ob, W, H, (int)n, t.dev,
+            launch_resize(s.d_in, (long long)fb, w, h, s.d_resized, (long long)ob, W, H, (int)n, t->dev,
                           m->cfg.resize_round_intermediate, s.stream);
         }
         CK(cudaMemcpyAsync(out_u8, s.d_resized, ob * n, cudaMemcpyDeviceToHost, s.stream));
@@ -1293,15 +1347,19 @@ int uf_postproc(uf_model* m, const float* scores, const float* boxes, uint32_t K
         auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
         const size_t o_scores = 0, o_boxes = a16(o_scores + (size_t)K * 2 * 4), o_sel = a16(o_boxes + (size_t)K * 4 * 4),
                      o_dets = a16(o_sel + (size_t)K * 4 * 4), o_idx = a16(o_dets + (size_t)K * 5 * 4),
-                     o_cnt = a16(o_idx + (size_t)K * 4), o_sort = a16(o_cnt + 4), total = o_sort + sort_cap * 8;
+                     o_cnt = a16(o_idx + (size_t)K * 4), o_big = a16(o_cnt + 4), o_sort = a16(o_big + 4),
+                     o_mask = a16(o_sort + sort_cap * 8),
+                     total = o_mask + (post_mask_supported((int)K) ? (size_t)K * post_mask_pitch((int)K) * 4 : 0);
         char* d = (char*)hook_scratch(*m, total);
         CK(cudaMemcpyAsync(d + o_scores, scores, (size_t)K * 2 * 4, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(d + o_boxes, boxes, (size_t)K * 4 * 4, cudaMemcpyHostToDevice, s.stream));
         PostBuffers pb{(unsigned long long*)(d + o_sort), (int)sort_cap, (float*)(d + o_sel), (float*)(d + o_dets),
-                       (int*)(d + o_idx), (int*)(d + o_cnt)};
-        m->launches++;
+                       (int*)(d + o_idx), (int*)(d + o_cnt),
+                       post_mask_supported((int)K) ? (unsigned*)(d + o_mask) : nullptr, post_mask_pitch((int)K), (int*)(d + o_big)};
+        m->launches += pb.mask ? 3 : 1;
         launch_post((const float*)(d + o_scores), (const float*)(d + o_boxes), (int)K, m->cfg.min_confidence,
                     m->cfg.max_iou, pb, 1, s.stream);
+        launch_nms_big((const float*)(d + o_scores), (int)K, m->cfg.max_iou, pb, 1, s.stream);
         int cnt = 0;
         CK(cudaMemcpyAsync(&cnt, d + o_cnt, 4, cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
@@ -1398,6 +1456,13 @@ int uf_profile_read(uf_model* m, uf_kernel_stat* out, uint32_t cap, uint32_t* n_
             out[i].compulsory_bytes = m->stats[i].min_bytes;
             out[i].flops = m->stats[i].flops;
         }
+    });
+}
+
+int uf_debug_fail_after(uf_model* m, int32_t stages) {
+    return guarded([&] {
+        REQUIRE(m, "null model");
+        m->fail_after_stages = stages;
     });
 }
 

@@ -152,6 +152,10 @@ struct PostBuffers {
     float* dets;                       // [frames][K][5]
     int* det_idx;                      // [frames][K] prior index of each detection (nullable)
     int* counts;                       // [frames]
+    // bit-matrix NMS for frames with many candidates (nullable: then every frame is resolved inside post_kernel)
+    unsigned* mask;                    // [frames][K][mask_pitch] suppression bits, rows / columns in processing order
+    int mask_pitch;                    // words per row (post_mask_pitch(K))
+    int* big_n;                        // [frames] candidates of a frame left to the bit-matrix kernels (0: done already)
 };
 void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
                  const PostBuffers& pb, int frames, cudaStream_t s);
@@ -160,5 +164,9 @@ void launch_tail_post(const float* conf, const float* loc, long long conf_frame_
                       float min_conf, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s);
 size_t post_sort_scratch_elems(int K);  // sort_cap for a given K
 int post_configure();                   // opt in to large dynamic smem; returns cudaError_t
+// second half of the post step for the frames post_kernel left to the bit-matrix path (two launches; no-op without pb.mask)
+void launch_nms_big(const float* scores, int K, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s);
+int post_mask_pitch(int K);
+bool post_mask_supported(int K);
 
 }  // namespace uf

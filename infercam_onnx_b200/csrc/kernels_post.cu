@@ -67,18 +67,30 @@ void launch_tail(const float* conf, const float* loc, long long conf_frame_strid
 //   1. count candidates (score > min_conf), pick the key array (shared memory if it fits)
 //   2. fill keys = (orderable(score) << 32 | prior index), pad to a power of two with 0
 //   3. bitonic sort, descending  => position order == the reference's pop() order
-//   4. greedy NMS in chunks of PT candidates: (A) every candidate of the chunk is tested against
-//      all boxes selected so far, (B) survivors are resolved against each other with a
-//      PT x PT bit matrix built by warp ballots and swept by one warp.
+//   4. greedy NMS. Few candidates (n <= NMS_SMALL, a real scene): in this CTA, in chunks of PT candidates —
+//      (A) every candidate of the chunk is tested against all boxes selected so far, (B) survivors are
+//      resolved against each other with a PT x PT bit matrix built by warp ballots and swept by one warp.
+//      Many candidates (the NMS-heavy configuration, thousands per frame): the CTA only publishes the sorted
+//      candidates; nms_mask_kernel builds the upper-triangular suppression bit matrix of every such frame with
+//      the whole GPU (all pairs are independent), nms_sweep_kernel then walks it in order, one CTA per frame,
+//      32 candidates per step (the 32x32 diagonal block is resolved in registers with shuffles, the rows of
+//      the survivors are OR-ed into the frame's `removed` bitset with all loads in flight at once).
+//      Both produce exactly the reference's greedy selection.
 // ---------------------------------------------------------------------------------------------
 constexpr int PT = 256;      // NMS chunk (candidates resolved together)
 constexpr int PG = 4;        // thread groups: group g tests the chunk against the selected boxes s == g (mod PG)
 constexpr int PTHR = PT * PG;  // threads per CTA
 constexpr int PW = PT / 32;  // mask words per row
-constexpr int POST_SMEM_KEYS = 8192;
+constexpr int POST_SMEM_KEYS = 8192;   // sort keys held in shared memory (K <= 8192) ...
+constexpr int POST_SMEM_KEYS_BIG = 16384;  // ... or 16384 (larger K: 128 KB of the 227 KB an sm_100 CTA may use)
+constexpr int NMS_SMALL = 512;       // more candidates than this: bit-matrix path (needs PostBuffers::mask)
+constexpr int MROWS = 64;            // nms_mask_kernel: rows staged per work unit
+constexpr int MCOLS = 256;           // ... columns per pass (one per thread; 8 mask words)
 
+// order-preserving map f32 -> u32; -0.0 and +0.0 map to the same key (Rust's partial_cmp calls them equal, so the
+// prior index decides, nn.rs:134)
 __device__ __forceinline__ unsigned f2ord(float f) {
-    const unsigned u = __float_as_uint(f);
+    const unsigned u = f == 0.0f ? 0u : __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
@@ -120,10 +132,10 @@ struct TailIn {
 template <bool TAIL>
 __global__ void __launch_bounds__(PTHR)
 post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float min_conf,
-            float max_iou, PostBuffers pb, TailIn tin) {
+            float max_iou, PostBuffers pb, TailIn tin, int smem_keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // POST_SMEM_KEYS
-    float4* cbox = reinterpret_cast<float4*>(skeys + POST_SMEM_KEYS);             // PT
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // smem_keys
+    float4* cbox = reinterpret_cast<float4*>(skeys + smem_keys);                  // PT
     unsigned* mask = reinterpret_cast<unsigned*>(cbox + PT);                      // PT * PW
     unsigned* alive_w = mask + PT * PW;                                           // PW
     int* kept = reinterpret_cast<int*>(alive_w + PW);                             // PT
@@ -166,7 +178,7 @@ post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float 
     const int n = s_cnt;
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
-    unsigned long long* keys = (n_pad <= POST_SMEM_KEYS) ? skeys : pb.sort_scratch + (size_t)f * pb.sort_cap;
+    unsigned long long* keys = (n_pad <= smem_keys) ? skeys : pb.sort_scratch + (size_t)f * pb.sort_cap;
     __syncthreads();
     if (tid == 0) s_cnt = 0;
     __syncthreads();
@@ -202,6 +214,19 @@ post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float 
     float4* sel = reinterpret_cast<float4*>(pb.sel_boxes) + (size_t)f * K;
     float* dets = pb.dets + (size_t)f * K * 5;
     int* didx = pb.det_idx ? pb.det_idx + (size_t)f * K : nullptr;
+    if (pb.mask != nullptr) {
+        const bool big = n > NMS_SMALL;
+        if (tid == 0) pb.big_n[f] = big ? n : 0;
+        if (big) {  // publish the sorted candidates (boxes in processing order, keys = score | prior) and leave
+            unsigned long long* gkeys = pb.sort_scratch + (size_t)f * pb.sort_cap;
+            for (int i = tid; i < n; i += PTHR) {
+                const unsigned long long key = keys[i];
+                if (keys != gkeys) gkeys[i] = key;
+                sel[i] = bx[(unsigned)(key & 0xffffffffull)];
+            }
+            return;
+        }
+    }
     int n_sel = 0;
     const int grp = tid / PT, ct = tid % PT;  // group, candidate slot within the chunk
     for (int base = 0; base < n; base += PT) {
@@ -276,15 +301,133 @@ post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float 
     if (tid == 0) pb.counts[f] = n_sel;
 }
 
-static size_t post_smem_bytes() {
-    return POST_SMEM_KEYS * sizeof(unsigned long long) + PT * sizeof(float4) + PT * PW * sizeof(unsigned) +
+// ---------------------------------------------------------------------------------------------
+// nms_mask_kernel: bit (i, j), j > i, of frame f  <=>  iou(cand_j, cand_i) > max_iou  (candidates in processing
+// order). Work unit = (frame, MROWS rows): the rows are staged in shared memory once and every thread walks them for
+// its own column, MCOLS columns per pass, starting at the diagonal; one ballot per row and warp is one mask word.
+// Persistent grid: units are dealt round-robin, so frames with few or no candidates cost nothing.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MCOLS)
+nms_mask_kernel(PostBuffers pb, int K, int frames, float max_iou) {
+    __shared__ float4 rows[MROWS];
+    const bool exact = !(max_iou >= 0.0f);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = pb.mask_pitch;
+    long long unit0 = 0;  // global index of the frame's first unit
+    for (int f = 0; f < frames; ++f) {
+        const int n = pb.big_n[f];
+        if (n == 0) continue;
+        const int RT = (n + MROWS - 1) / MROWS;
+        const float4* sel = reinterpret_cast<const float4*>(pb.sel_boxes) + (size_t)f * K;
+        unsigned* mask = pb.mask + (size_t)f * K * W;
+        // first unit of this frame that is mine: u == blockIdx.x (mod gridDim.x)
+        int r = (int)(((long long)blockIdx.x - unit0 % gridDim.x + gridDim.x) % gridDim.x);
+        for (; r < RT; r += gridDim.x) {
+            const int row0 = r * MROWS;
+            const int nrows = min(MROWS, n - row0);
+            __syncthreads();
+            if (tid < nrows) rows[tid] = sel[row0 + tid];
+            __syncthreads();
+            for (int col0 = row0 / MCOLS * MCOLS; col0 < n; col0 += MCOLS) {
+                const int j = col0 + tid;
+                const bool valid = j < n;
+                const float4 b = valid ? sel[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int word = (col0 >> 5) + warp;
+                if (word * 32 < n) {  // warp-uniform
+#pragma unroll 4
+                    for (int i = 0; i < nrows; ++i) {
+                        const bool pred = valid && j > row0 + i && iou_exceeds(b, rows[i], max_iou, exact);
+                        const unsigned bal = __ballot_sync(0xffffffffu, pred);
+                        if (lane == 0) mask[(size_t)(row0 + i) * W + word] = bal;
+                    }
+                }
+            }
+        }
+        unit0 += RT;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// nms_sweep_kernel: one CTA per frame with a published candidate list. `removed` bitset in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int SWEEP_THR = 128;
+
+__global__ void __launch_bounds__(SWEEP_THR)
+nms_sweep_kernel(const float* __restrict__ scores, PostBuffers pb, int K) {
+    extern __shared__ unsigned removed[];  // mask_pitch words
+    __shared__ unsigned s_kept;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int f = blockIdx.x;
+    const int n = pb.big_n[f];
+    if (n == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = pb.mask_pitch;
+    const int nw = (n + 31) >> 5;
+    const unsigned* mask = pb.mask + (size_t)f * K * W;
+    const float4* sel = reinterpret_cast<const float4*>(pb.sel_boxes) + (size_t)f * K;
+    const unsigned long long* keys = pb.sort_scratch + (size_t)f * pb.sort_cap;
+    const float* sc = scores + (size_t)f * K * 2;
+    float* dets = pb.dets + (size_t)f * K * 5;
+    int* didx = pb.det_idx ? pb.det_idx + (size_t)f * K : nullptr;
+    for (int w = tid; w < nw; w += SWEEP_THR) removed[w] = 0u;
+    __syncthreads();
+    int n_sel = 0;
+    for (int c = 0; c < nw; ++c) {
+        const int row = 32 * c + lane;
+        if (warp == 0) {
+            // diagonal block: lane l holds the suppression word of candidate 32c + l against candidates 32c ..
+            const unsigned diag = row < n ? mask[(size_t)row * W + c] : 0u;
+            unsigned rem = removed[c];
+            if (32 * c + 32 > n) rem |= 0xffffffffu << (n - 32 * c);  // past the end: never kept
+            unsigned kept = 0u;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const unsigned d = __shfl_sync(0xffffffffu, diag, b);
+                if (!((rem >> b) & 1u)) { kept |= 1u << b; rem |= d; }
+            }
+            if (lane == 0) s_kept = kept;
+            if ((kept >> lane) & 1u) {
+                const int pos = n_sel + __popc(kept & ((1u << lane) - 1u));
+                const unsigned k = (unsigned)(keys[row] & 0xffffffffull);
+                const float4 kb = sel[row];
+                float* d = dets + (size_t)pos * 5;
+                d[0] = kb.x; d[1] = kb.y; d[2] = kb.z; d[3] = kb.w; d[4] = sc[2 * (size_t)k + 1];
+                if (didx) didx[pos] = (int)k;
+            }
+        }
+        __syncthreads();
+        const unsigned kept = s_kept;
+        n_sel += __popc(kept);
+        // rows of the survivors suppress later words: all (predicated) loads of a word are independent
+        for (int w = c + 1 + tid; w < nw; w += SWEEP_THR) {
+            const unsigned* col = mask + (size_t)(32 * c) * W + w;
+            unsigned acc = 0u;
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+                if ((kept >> b) & 1u) acc |= col[(size_t)b * W];
+            if (acc) removed[w] |= acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) pb.counts[f] = n_sel;
+}
+
+static int smem_keys_for(int K) { return K <= POST_SMEM_KEYS ? POST_SMEM_KEYS : POST_SMEM_KEYS_BIG; }
+
+static size_t post_smem_bytes(int smem_keys) {
+    return (size_t)smem_keys * sizeof(unsigned long long) + PT * sizeof(float4) + PT * PW * sizeof(unsigned) +
            PW * sizeof(unsigned) + PT * sizeof(int) + PT * sizeof(float) + PT * sizeof(int) + PT * sizeof(unsigned);
 }
 
 int post_configure() {
-    int e = (int)cudaFuncSetAttribute(post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem_bytes());
+    int e = (int)cudaFuncSetAttribute(post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem_bytes(POST_SMEM_KEYS_BIG));
     if (e) return e;
-    return (int)cudaFuncSetAttribute(post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem_bytes());
+    e = (int)cudaFuncSetAttribute(post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem_bytes(POST_SMEM_KEYS_BIG));
+    if (e) return e;
+    return (int)cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
 size_t post_sort_scratch_elems(int K) {
@@ -293,10 +436,21 @@ size_t post_sort_scratch_elems(int K) {
     return c;
 }
 
+int post_mask_pitch(int K) { return ((K + 31) / 32 + 3) / 4 * 4; }  // words per row, 16-byte multiple
+bool post_mask_supported(int K) { return K <= 32768; }             // sweep bitset <= 4 KB words, matrix <= 128 MB per frame
+
+void launch_nms_big(const float* scores, int K, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s) {
+    if (!pb.mask) return;
+    // the whole GPU, several CTAs per SM (the kernel is latency-bound on its shared-memory broadcasts)
+    launch_pdl(nms_mask_kernel, dim3(148 * 8), dim3(MCOLS), 0, s, pb, K, frames, max_iou);
+    launch_pdl(nms_sweep_kernel, dim3(frames), dim3(SWEEP_THR), (size_t)pb.mask_pitch * sizeof(unsigned), s, scores, pb, K);
+}
+
 void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
                  const PostBuffers& pb, int frames, cudaStream_t s) {
-    launch_pdl(post_kernel<false>, dim3(frames), dim3(PTHR), post_smem_bytes(), s, const_cast<float*>(scores),
-               const_cast<float*>(boxes), K, min_conf, max_iou, pb, TailIn{});
+    const int sk = smem_keys_for(K);
+    launch_pdl(post_kernel<false>, dim3(frames), dim3(PTHR), post_smem_bytes(sk), s, const_cast<float*>(scores),
+               const_cast<float*>(boxes), K, min_conf, max_iou, pb, TailIn{}, sk);
 }
 
 // tail + post in one launch: scores / boxes are OUTPUTS here (kept for uf_raw_outputs and the hooks)
@@ -304,8 +458,9 @@ void launch_tail_post(const float* conf, const float* loc, long long conf_frame_
                       const float* priors, float center_var, float size_var, float* scores, float* boxes, int K,
                       float min_conf, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s) {
     TailIn tin{conf, loc, conf_frame_stride, loc_frame_stride, priors, center_var, size_var};
-    launch_pdl(post_kernel<true>, dim3(frames), dim3(PTHR), post_smem_bytes(), s, scores, boxes, K, min_conf, max_iou, pb,
-               tin);
+    const int sk = smem_keys_for(K);
+    launch_pdl(post_kernel<true>, dim3(frames), dim3(PTHR), post_smem_bytes(sk), s, scores, boxes, K, min_conf, max_iou, pb,
+               tin, sk);
 }
 
 }  // namespace uf

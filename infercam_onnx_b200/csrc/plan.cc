@@ -8,6 +8,7 @@
 #include <stdexcept>
 
 namespace uf {
+void verify_decode_tail(const OnnxModel& m, const std::string& loc_value, const std::string& boxes_value, const Plan& plan);  // tail_check.cc
 namespace {
 
 struct HeadRef {
@@ -30,6 +31,7 @@ struct Lowerer {
     std::set<std::string> tail;                         // values of the decode tail (not materialised)
     std::vector<bool> consumed;
     std::vector<HeadRef> cls_list, reg_list;
+    std::string reg_value, scores_value;  // ONNX names: concatenated regression heads; Softmax output
 
     explicit Lowerer(const OnnxModel& mm) : m(mm) {}
 
@@ -84,13 +86,17 @@ struct Lowerer {
         if (!is_const(n.inputs[1])) throw UnsupportedError("Conv weights of '" + n.outputs[0] + "' are not an initialiser");
         const OnnxTensor& wt = cst(n.inputs[1]);
         if (wt.dtype != 1 || wt.dims.size() != 4) throw UnsupportedError("Conv weights must be 4-D float32");
+        for (int64_t d : wt.dims)
+            if (d < 1 || d > 65536) throw std::runtime_error("onnx: Conv '" + n.outputs[0] + "' weight dimension out of range");
         const TensorDesc in = plan.tensors[tid.at(n.inputs[0])];
         Op op;
         op.kind = OpKind::Conv;
         op.in = tid.at(n.inputs[0]);
         op.onnx_node = n.outputs[0];
         op.cout = (int)wt.dims[0];
-        op.groups = (int)n.attr_i("group", 1);
+        const int64_t grp = n.attr_i("group", 1);
+        if (grp < 1 || grp > 65536) throw std::runtime_error("onnx: Conv '" + n.outputs[0] + "' has a bad group count");
+        op.groups = (int)grp;
         op.cin = (int)wt.dims[1] * op.groups;
         if (op.cin != in.C) throw std::runtime_error("onnx: Conv '" + n.outputs[0] + "' channel mismatch");
         if (wt.dims[2] != wt.dims[3]) throw UnsupportedError("non-square Conv kernel");
@@ -100,6 +106,8 @@ struct Lowerer {
         auto st = n.attr_ints("strides", {1, 1});
         auto dl = n.attr_ints("dilations", {1, 1});
         auto pd = n.attr_ints("pads", {0, 0, 0, 0});
+        if (st.size() != 2 || dl.size() != 2 || st[0] < 1 || dl[0] < 1 || st[0] > 64 || dl[0] > 64 || pd.size() != 4 || pd[0] < 0 || pd[0] > 1024)
+            throw UnsupportedError("strides / dilations / pads of Conv '" + n.outputs[0] + "' are malformed");
         if (st[0] != st[1] || dl[0] != dl[1] || pd.size() != 4 || pd[0] != pd[1] || pd[0] != pd[2] || pd[0] != pd[3])
             throw UnsupportedError("anisotropic stride/dilation/pad in Conv '" + n.outputs[0] + "'");
         auto ap = n.attrs.find("auto_pad");
@@ -128,6 +136,8 @@ struct Lowerer {
             int ci = sole_consumer(cur);
             if (ci < 0 || consumed[ci]) break;
             const OnnxNode& c = m.nodes[ci];
+            // once the skip connection is fused, (conv + res) * v is no longer conv * v + res: only Relu may follow
+            if (op.in2 >= 0 && c.op != "Relu") break;
             if (c.op == "BatchNormalization" && c.inputs.size() == 5 && c.inputs[0] == cur) {
                 std::vector<float> g, be, mu, var;
                 if (!channel_const(c.inputs[1], op.cout, g) || !channel_const(c.inputs[2], op.cout, be) ||
@@ -236,6 +246,8 @@ struct Lowerer {
         for (size_t idx = 0; idx < m.nodes.size(); ++idx) {
             if (consumed[idx]) continue;
             const OnnxNode& n = m.nodes[idx];
+            if (n.op != "Constant" && (n.inputs.empty() || n.outputs.empty()))
+                throw std::runtime_error("onnx: node '" + n.op + "' without inputs or outputs");
             auto feat = [&](const std::string& s) { return tid.count(s) > 0; };
             auto tailish = [&](const std::string& s) {
                 return s.empty() || is_const(s) || tail.count(s) || headref.count(s) || headlist.count(s);
@@ -290,6 +302,7 @@ struct Lowerer {
                 if (axis != 2 && axis != -1) throw UnsupportedError("Softmax axis must be the class axis");
                 if (!cls_list.empty()) throw UnsupportedError("more than one Softmax over head outputs");
                 cls_list = headlist.at(n.inputs[0]);
+                scores_value = n.outputs[0];
                 tail.insert(n.outputs[0]);
                 continue;
             }
@@ -301,7 +314,8 @@ struct Lowerer {
             if (kTailOps.count(n.op) && touches_headlist) {
                 for (auto& i : n.inputs)
                     if (headlist.count(i)) {
-                        if (reg_list.empty()) reg_list = headlist.at(i);
+                        if (reg_list.empty()) { reg_list = headlist.at(i); reg_value = i; }
+                        else if (i != reg_value) throw UnsupportedError("more than one head list feeds the decode tail");
                     }
                 for (auto& o : n.outputs) tail.insert(o);
                 continue;
@@ -360,6 +374,17 @@ struct Lowerer {
             }
         }
         resolve_priors();
+        // outputs[0] must be the Softmax itself (nn.rs:111 reads face probabilities from it), outputs[1] the decoded
+        // boxes: verified by running the tail on the host against the formula the post kernel implements
+        std::string boxes_value;
+        bool scores_ok = false;
+        for (auto& o : m.outputs) {
+            if (o.name == scores_value) scores_ok = true;
+            else boxes_value = o.name;
+        }
+        if (!scores_ok || boxes_value.empty()) throw UnsupportedError("graph outputs are not (Softmax scores, decoded boxes)");
+        if (m.outputs[0].name != scores_value) throw UnsupportedError("graph output 0 is not the Softmax scores (nn.rs:111 expects scores first)");
+        verify_decode_tail(m, reg_value, boxes_value, plan);
     }
 
     void resolve_priors() {

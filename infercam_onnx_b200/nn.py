@@ -241,6 +241,10 @@ class UltrafaceModel(InferModel):
                 f[key] += s[key]
         return list(fam.values())
 
+    def debug_fail_after(self, stages: int) -> None:
+        """Fault injection: following batched calls fail after `stages` pipeline stages (negative: off)."""
+        _check(_capi.load().uf_debug_fail_after(self._h, stages))
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         _check(_capi.load().uf_launch_count(self._h, C.byref(n)))

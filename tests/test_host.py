@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from infercam_onnx_b200 import _capi, nn
-from infercam_onnx_b200.onnx_fixture import generate_priors
+from tools.onnx_fixture import generate_priors
 from oracle import hotpath
 from oracle.onnx_reader import load_onnx
 
@@ -139,3 +139,110 @@ def test_variant_mirror():
     assert nn.UltrafaceVariant.W640H480.width_height() == (640, 480)  # nn.rs:36-41
     assert nn.UltrafaceVariant.W320H240.width_height() == (320, 240)
     assert nn.default_model_path(nn.UltrafaceVariant.W320H240).endswith("infercam_onnx/ultraface-RFB-320.onnx")
+
+
+def test_upstream_shaped_export_lowers_to_the_same_plan(make_onnx):
+    """nn.rs:165-172 loads `version-RFB-*.onnx`, an un-simplified opset-9 export: Shape/Gather/Unsqueeze/Concat reshape
+    targets, Constant-node priors sliced in the graph, attribute-form Slice, explicit BatchNormalization. The lowering
+    must produce the plan of the simplified file with the same weights, with the priors taken from the graph."""
+    for wh in ((320, 240), (640, 480)):
+        for with_bn in (False, True):
+            a = nn.onnx_inspect(make_onnx(*wh, seed=4, with_bn=with_bn), *wh)
+            b = nn.onnx_inspect(make_onnx(*wh, seed=4, with_bn=with_bn, style="upstream"), *wh)
+            assert b["priors_from_graph"] and b["warnings"] == ""
+            assert (a["num_priors"], a["priors_sum"], a["center_variance"], a["size_variance"]) == \
+                   (b["num_priors"], b["priors_sum"], b["center_variance"], b["size_variance"])
+            assert len(a["ops"]) == len(b["ops"])
+            for x, y in zip(a["ops"], b["ops"]):
+                for k in ("kind", "cin", "cout", "k", "stride", "pad", "dil", "groups", "relu", "residual", "h", "w",
+                          "pix_stride", "base_off", "w_sum", "w_abs", "b_sum"):
+                    assert x[k] == y[k], (k, x["out"], y["out"])
+
+
+@pytest.mark.parametrize("style", ["simplified", "upstream"])
+@pytest.mark.parametrize("tail", ["no_exp", "corner_only"])
+def test_decode_tail_is_verified_by_evaluation(make_onnx, style, tail):
+    """The post kernel hard-codes the UltraFace decode; a graph whose tail computes anything else must be refused at load
+    (tail_check.cc runs the tail sub-graph on the host against the formula), not run with silently wrong boxes."""
+    with pytest.raises(nn.UltrafaceError) as e:
+        nn.onnx_inspect(make_onnx(320, 240, style=style, tail=tail), 320, 240)
+    assert e.value.code == 4 and "decode" in str(e.value)
+
+
+def _patched_onnx(tmp_path, name, mutate):
+    """Writes a small fixture graph after `mutate(builder_module)` has monkey-patched the writer."""
+    import tools.onnx_fixture as fx
+    path = str(tmp_path / name)
+    undo = mutate(fx)
+    try:
+        fx.write_ultraface_onnx(path, width=320, height=240, seed=1)
+    finally:
+        undo()
+    return path
+
+
+def test_hostile_conv_attributes_do_not_crash(tmp_path):
+    """Entry points never abort (header contract): malformed strides / dilations / group are errors, not SIGFPE / OOB."""
+    import tools.onnx_fixture as fx
+    orig = fx.node_proto
+    for bad in (dict(strides=[2]), dict(dilations=[]), dict(group=0), dict(strides=[0, 0]), dict(pads=[1, 1])):
+        def patched(op, inputs, outputs, name="", **attrs):
+            if op == "Conv":
+                attrs.update(bad)
+            return orig(op, inputs, outputs, name, **attrs)
+
+        def mutate(mod):
+            mod.node_proto = patched
+            return lambda: setattr(mod, "node_proto", orig)
+        path = _patched_onnx(tmp_path, "hostile.onnx", mutate)
+        with pytest.raises(nn.UltrafaceError) as e:
+            nn.onnx_inspect(path, 320, 240)
+        assert e.value.code in (3, 4), bad
+
+
+def test_scale_after_residual_add_is_not_folded(tmp_path):
+    """conv -> Add(skip) -> Mul(v): folding v into the conv alone would compute conv*v + skip. The lowering must refuse
+    (or keep the Mul), never fold."""
+    import tools.onnx_fixture as fx
+    orig = fx.node_proto
+    state = {"after_add": None}
+
+    def patched(op, inputs, outputs, name="", **attrs):
+        if op == "Relu" and state["after_add"] == inputs[0]:
+            # insert a per-tensor scale between the residual Add and its Relu
+            scale = orig("Constant", [], ["rfb_scale"], value=np.asarray(2.0, np.float32))
+            mul = orig("Mul", [inputs[0], "rfb_scale"], ["rfb_scaled"])
+            state["extra"] = [scale, mul]
+            return orig(op, ["rfb_scaled"], outputs, name, **attrs)
+        if op == "Add" and len(inputs) == 2 and inputs[0].startswith(("mul", "conv")) and inputs[1].startswith("conv"):
+            state["after_add"] = outputs[0]
+        return orig(op, inputs, outputs, name, **attrs)
+
+    class ListProxy(list):
+        def append(self, item):
+            extra = state.pop("extra", None)
+            if extra:
+                for x in extra:
+                    super().append(x)
+            super().append(item)
+
+    orig_builder_init = fx._Builder.__init__
+
+    def builder_init(self, seed, with_bn):
+        orig_builder_init(self, seed, with_bn)
+        self.nodes = ListProxy()
+
+    def mutate(mod):
+        mod.node_proto = patched
+        mod._Builder.__init__ = builder_init
+
+        def undo():
+            mod.node_proto = orig
+            mod._Builder.__init__ = orig_builder_init
+        return undo
+    path = _patched_onnx(tmp_path, "scaled_residual.onnx", mutate)
+    g = load_onnx(path)
+    assert any(n.op == "Mul" and "rfb_scale" in n.inputs for n in g.nodes), "fixture patch did not take"
+    with pytest.raises(nn.UltrafaceError) as e:
+        nn.onnx_inspect(path, 320, 240)
+    assert e.value.code == 4

@@ -229,3 +229,27 @@ def test_oracle_cnn_agrees_with_opencv_dnn(make_onnx, cfg):
     s, b = m.raw_from_tensor(x)
     assert np.abs(outs["scores"].reshape(s.shape) - s).max() < 2e-5
     assert np.abs(outs["boxes"].reshape(b.shape) - b).max() < 2e-5
+
+
+def test_oracle_runs_upstream_shaped_export_identically(make_onnx):
+    """The interpreter handles the un-simplified export shape (Shape/Gather/Unsqueeze/Constant, attribute-form Slice,
+    explicit BN) and gives exactly what the simplified file with the same weights gives."""
+    from oracle.ultraface_ref import UltrafaceOracle
+    frame = np.random.default_rng(3).integers(0, 256, (427, 640, 3), dtype=np.uint8)
+    a = UltrafaceOracle(make_onnx(320, 240, seed=4, cls_bias=-0.75), 320, 240).raw([frame])
+    b = UltrafaceOracle(make_onnx(320, 240, seed=4, cls_bias=-0.75, style="upstream"), 320, 240).raw([frame])
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_reference_face_counts_through_the_oracle(real_rfb640_path, test_pics, reference_face_counts):
+    """integration_tests.rs:20-34 through the CPU restatement: this is the test that PINS the oracle the moment the weight
+    file the reference downloads is available (skipped until then: "parity unpinned")."""
+    from oracle.ultraface_ref import UltrafaceOracle
+    o = UltrafaceOracle(real_rfb640_path, 640, 480, 0.5, 0.5)
+    assert {k: len(o.run(im)) for k, im in test_pics.items()} == reference_face_counts
+
+
+def test_reference_photos_have_the_reference_geometry(test_pics, reference_face_counts):
+    assert set(test_pics) == set(reference_face_counts)
+    assert sorted(im.shape[:2] for im in test_pics.values()) == sorted([(427, 640)] * 5 + [(462, 640), (676, 640), (960, 640)])

@@ -2,7 +2,7 @@ import os, sys, time, tempfile
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from infercam_onnx_b200 import nn, _capi
-from infercam_onnx_b200.onnx_fixture import write_ultraface_onnx
+from tools.onnx_fixture import write_ultraface_onnx
 tmp = tempfile.mkdtemp()
 path = write_ultraface_onnx(os.path.join(tmp, "m.onnx"), width=320, height=240, seed=0, cls_bias=-0.75)
 frames = np.random.default_rng(0).integers(0, 256, (1, 480, 640, 3), dtype=np.uint8)

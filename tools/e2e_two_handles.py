@@ -3,7 +3,7 @@ import os, sys, time, tempfile, threading
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from infercam_onnx_b200 import nn
-from infercam_onnx_b200.onnx_fixture import write_ultraface_onnx
+from tools.onnx_fixture import write_ultraface_onnx
 tmp = tempfile.mkdtemp()
 path = write_ultraface_onnx(os.path.join(tmp, "m.onnx"), width=320, height=240, seed=0, cls_bias=-0.75)
 nh = int(sys.argv[1]) if len(sys.argv) > 1 else 2

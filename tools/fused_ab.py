@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from infercam_onnx_b200 import _capi, nn  # noqa: E402
-from infercam_onnx_b200.onnx_fixture import write_ultraface_onnx  # noqa: E402
+from tools.onnx_fixture import write_ultraface_onnx  # noqa: E402
 
 tmp = tempfile.mkdtemp()
 path = write_ultraface_onnx(os.path.join(tmp, "m.onnx"), width=320, height=240, seed=0, cls_bias=-0.75)

@@ -11,7 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from infercam_onnx_b200 import _capi, nn  # noqa: E402
-from infercam_onnx_b200.onnx_fixture import write_ultraface_onnx  # noqa: E402
+from tools.onnx_fixture import write_ultraface_onnx  # noqa: E402
 from oracle import hotpath  # noqa: E402
 from oracle.ultraface_ref import UltrafaceOracle  # noqa: E402
 

@@ -63,7 +63,8 @@ def _f_float(field: int, v: float) -> bytes:
 
 def tensor_proto(name: str, arr: np.ndarray) -> bytes:
     """TensorProto: dims=1, data_type=2, name=8, raw_data=9."""
-    arr = np.ascontiguousarray(arr)
+    arr = np.asarray(arr)
+    arr = arr if arr.ndim == 0 else np.ascontiguousarray(arr)  # (ascontiguousarray would turn a scalar into [1])
     dt = {np.dtype("float32"): 1, np.dtype("int64"): 7}[arr.dtype]
     out = b"".join(_f_varint(1, int(d)) for d in arr.shape)
     out += _f_varint(2, dt)
@@ -115,7 +116,7 @@ def model_proto(nodes: list[bytes], inits: list[bytes], inputs: list[bytes], out
     graph += b"".join(_f_bytes(11, i) for i in inputs)
     graph += b"".join(_f_bytes(12, o) for o in outputs)
     out = _f_varint(1, 4)  # ir_version
-    out += _f_str(2, "infercam_onnx_b200.onnx_fixture")
+    out += _f_str(2, "tools.onnx_fixture")
     out += _f_bytes(7, graph)
     out += _f_bytes(8, _f_str(1, "") + _f_varint(2, opset))
     return out
@@ -245,15 +246,36 @@ class _Builder:
 
 
 def build_ultraface_onnx(width: int = 320, height: int = 240, variant: str = "RFB", seed: int = 0,
-                         with_bn: bool = False, cls_bias: float = 0.0, head_gain: float = 1.0) -> bytes:
+                         with_bn: bool = False, cls_bias: float = 0.0, head_gain: float = 1.0,
+                         style: str = "simplified", tail: str = "standard") -> bytes:
     """Return the serialized ModelProto.
+
+    style="upstream" writes the graph the way the files the reference downloads
+    (`version-RFB-{320,640}.onnx`, nn.rs:21-22: a PyTorch-1.x opset-9 export, not simplified) are shaped:
+    every head reshape is fed by a computed shape (Shape -> Gather -> Unsqueeze -> Concat -> Reshape),
+    all constants are `Constant` NODES (priors as one [1,K,4] tensor that is sliced in the graph, the
+    variances, the reshape dims, the divisor 2), `Slice` carries starts/ends/axes as attributes, and
+    center_form_to_corner_form re-slices the concatenated centre-form boxes. Same seed => same weights
+    as style="simplified", so both files must produce identical tensors.
+    tail="swapped_variances" / "no_exp" / "corner_only": deliberately non-UltraFace decode tails the
+    loader must refuse (tail_check.cc).
 
     cls_bias shifts the face-class logit of every classification head: it sets
     the fraction of priors above min_confidence on synthetic frames (SURVEY.md
     §8d config 5). head_gain scales head weights (spread of logits / offsets).
     """
-    assert variant in ("RFB", "slim")
+    assert variant in ("RFB", "slim") and style in ("simplified", "upstream")
     b = _Builder(seed, with_bn)
+    upstream = style == "upstream"
+
+    def const(arr: np.ndarray, hint: str = "c") -> str:
+        """initialiser (simplified) or Constant node (upstream)"""
+        if not upstream:
+            return b.init(arr, hint)
+        y = b.fresh(hint)
+        b.nodes.append(node_proto("Constant", [], [y], value=np.asarray(arr)))
+        return y
+
     c = 16
     x = b.conv("input", 3, c, 3, 2, 1)                       # 0 conv_bn(3,16,2)
     x = b.dw_sep(x, c, 2 * c, 1)                              # 1
@@ -298,7 +320,21 @@ def build_ultraface_onnx(width: int = 320, height: int = 240, variant: str = "RF
             t = b.fresh("tr")
             b.nodes.append(node_proto("Transpose", [y], [t], perm=[0, 2, 3, 1]))
             r = b.fresh("rs")
-            b.nodes.append(node_proto("Reshape", [t, b.init(np.asarray([1, -1, per], np.int64), "shape")], [r]))
+            if upstream:  # x.view(x.size(0), -1, per): the batch dimension is read back from the tensor
+                shp = b.fresh("shape")
+                b.nodes.append(node_proto("Shape", [t], [shp]))
+                g = b.fresh("gather")
+                b.nodes.append(node_proto("Gather", [shp, const(np.asarray(0, np.int64), "idx")], [g], axis=0))
+                dims = []
+                for src_ in (g, const(np.asarray(-1, np.int64), "m1"), const(np.asarray(per, np.int64), "per")):
+                    u = b.fresh("unsq")
+                    b.nodes.append(node_proto("Unsqueeze", [src_], [u], axes=[0]))
+                    dims.append(u)
+                tgt = b.fresh("tgt")
+                b.nodes.append(node_proto("Concat", dims, [tgt], axis=0))
+                b.nodes.append(node_proto("Reshape", [t, tgt], [r]))
+            else:
+                b.nodes.append(node_proto("Reshape", [t, b.init(np.asarray([1, -1, per], np.int64), "shape")], [r]))
             parts.append(r)
 
     conf = b.fresh("conf")
@@ -309,28 +345,51 @@ def build_ultraface_onnx(width: int = 320, height: int = 240, variant: str = "RF
 
     pri = generate_priors(width, height)
     K = pri.shape[0]
-    p_xy = b.init(pri[None, :, :2].copy(), "prior_xy")
-    p_wh = b.init(pri[None, :, 2:].copy(), "prior_wh")
 
     def op(kind: str, ins: list[str], **attrs) -> str:
         y = b.fresh(kind.lower())
         b.nodes.append(node_proto(kind, ins, [y], **attrs))
         return y
 
+    def sl(x: str, lo: int, hi: int) -> str:
+        return op("Slice", [x], axes=[2], starts=[lo], ends=[hi])
+
+    if upstream:
+        p_all = const(pri[None].copy(), "priors")  # one [1,K,4] Constant, sliced in the graph
+        p_xy, p_wh = sl(p_all, 0, 2), sl(p_all, 2, 4)
+        p_wh2 = sl(p_all, 2, 4)
+    else:
+        p_xy = b.init(pri[None, :, :2].copy(), "prior_xy")
+        p_wh = p_wh2 = b.init(pri[None, :, 2:].copy(), "prior_wh")
+    cv, sv = CENTER_VARIANCE, SIZE_VARIANCE
+    if tail == "swapped_variances":
+        cv, sv = sv, cv
+
     # box_utils.convert_locations_to_boxes
-    l_xy = op("Slice", [loc], axes=[2], starts=[0], ends=[2])
-    l_wh = op("Slice", [loc], axes=[2], starts=[2], ends=[4])
-    cxy = op("Mul", [l_xy, b.init(np.asarray(CENTER_VARIANCE, np.float32), "cv")])
+    l_xy = sl(loc, 0, 2)
+    l_wh = sl(loc, 2, 4)
+    cxy = op("Mul", [l_xy, const(np.asarray(cv, np.float32), "cv")])
     cxy = op("Mul", [cxy, p_wh])
     cxy = op("Add", [cxy, p_xy])
-    wh = op("Mul", [l_wh, b.init(np.asarray(SIZE_VARIANCE, np.float32), "sv")])
-    wh = op("Exp", [wh])
-    wh = op("Mul", [wh, p_wh])
-    # box_utils.center_form_to_corner_form
-    half = op("Div", [wh, b.init(np.asarray(2.0, np.float32), "two")])
-    tl = op("Sub", [cxy, half])
-    br = op("Add", [cxy, half])
-    b.nodes.append(node_proto("Concat", [tl, br], ["boxes"], axis=2))
+    wh = op("Mul", [l_wh, const(np.asarray(sv, np.float32), "sv")])
+    if tail != "no_exp":
+        wh = op("Exp", [wh])
+    wh = op("Mul", [wh, p_wh2])
+    if upstream:  # torch.cat([...], dim=-1) then center_form_to_corner_form slices it again
+        centre = op("Concat", [cxy, wh], axis=2)
+        cxy, wh = sl(centre, 0, 2), sl(centre, 2, 4)
+        cxy2 = sl(centre, 0, 2)
+        wh2 = sl(centre, 2, 4)
+    else:
+        cxy2, wh2 = cxy, wh
+    if tail == "corner_only":  # a graph that outputs centre-form boxes
+        b.nodes.append(node_proto("Concat", [cxy, wh], ["boxes"], axis=2))
+    else:
+        # box_utils.center_form_to_corner_form
+        two = np.asarray(2.0, np.float32)
+        tl = op("Sub", [cxy, op("Div", [wh, const(two, "two")])])
+        br = op("Add", [cxy2, op("Div", [wh2, const(two, "two")])])
+        b.nodes.append(node_proto("Concat", [tl, br], ["boxes"], axis=2))
 
     return model_proto(
         b.nodes, b.inits,

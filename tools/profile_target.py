@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from infercam_onnx_b200 import nn  # noqa: E402
-from infercam_onnx_b200.onnx_fixture import write_ultraface_onnx  # noqa: E402
+from tools.onnx_fixture import write_ultraface_onnx  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 net = sys.argv[2] if len(sys.argv) > 2 else "320x240"
