@@ -88,6 +88,7 @@ typedef struct uf_config {
 #define UF_FLAG_PDL 32u          /* launch the kernel chain with programmatic dependent launch (process-wide; measured neutral) */
 #define UF_FLAG_TMA_SIMT_PW 64u  /* fused dw+1x1 layers of the big maps: keep the 1x1 on the SIMT pipes (the pre-tcgen05 kernel) */
 #define UF_FLAG_DENSE3_TC 128u   /* dense 3x3 convs of the RFB branches as a tcgen05 implicit GEMM (zero-copy im2col; measured slower) */
+#define UF_FLAG_NO_PRESTEM 256u  /* frames at exactly 2x the network size: keep resize and stem as two kernels (default: one fused kernel) */
 #define UF_FLAG_FUSE_DW_TC 16u   /* compute depthwise 3x3 inside the tensor-core GEMM's converter warps (C >= 64) */
 
 typedef struct uf_info {
@@ -134,6 +135,9 @@ UF_API int uf_preproc_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h
 /* Same for n <= chunk frames of identical size, resized by ONE launch (the batch path's kernel selection, e.g. the
  * exact-integer 2:1 kernel, differs from the single-frame one): out_u8 = n x net_h x net_w x 3. */
 UF_API int uf_preproc_u8_batch(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t n, uint8_t* out_u8);
+/* The resized u8 pixels as the FUSED resize + normalise + stem kernel (frames at exactly 2x the network size) computed and
+ * convolved them: n <= chunk frames of (2 net_w) x (2 net_h) -> out_u8 = n x net_h x net_w x 3. UF_ERR_UNSUPPORTED otherwise. */
+UF_API int uf_debug_prestem_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t n, uint8_t* out_u8);
 /* nn.rs:70-94: out = 1 x 3 x net_h x net_w f32 (NCHW). */
 UF_API int uf_preproc_f32(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, float* out);
 /* nn.rs:109-140 + 198-260 alone on caller-supplied raw tensors (scores K x 2, boxes K x 4). */
@@ -178,6 +182,80 @@ UF_API int uf_onnx_inspect(const char* onnx_path, uint32_t net_w, uint32_t net_h
  * left/ntaps/w are non-NULL fills left[dst_len], ntaps[dst_len], w[dst_len * w_pitch]. */
 UF_API int uf_resize_taps(uint32_t src_len, uint32_t dst_len, int32_t* left, int32_t* ntaps, float* w,
                           uint32_t w_pitch, uint32_t* max_taps);
+
+/* ==== stream batcher + stream -> GPU routing ==========================================
+ * Replaces the loop of `Inferer::run` (inferer.rs:29-50: recv_ref -> model.run -> send) and the bounded LOSSY queue in
+ * front of it (`INFER_IMAGES_CHANNEL`, capacity 10, lib.rs:32-37; the router fills it with `try_send_ref` and drops the
+ * frame when it is full, router.rs:64-72). One batcher owns one model handle per device; a frame of stream `s` (the
+ * `hashed(&id)` of router.rs:58, see uf_stream_hash) always goes to device `devices[s % n_devices]`, so streams shard
+ * over the GPUs with no cross-GPU traffic and the results of one stream stay in submission order. Per device, worker
+ * threads drain up to `max_batch` frames — or what has arrived when `max_delay_us` expires, so a lone webcam is not held
+ * back — call the batched path with several batches in flight (the handle's lanes), and queue the detections for
+ * uf_batcher_poll, batch by batch in formation order.
+ * Frames live in pinned host memory owned by the batcher, one pool per device: uf_batcher_acquire hands the ingest side a
+ * slot of the right pool to decode INTO (no extra host copy; N4), uf_batcher_commit queues it. uf_batcher_try_submit is
+ * acquire + memcpy + commit for callers that already hold the pixels. None of these block. */
+typedef struct uf_batcher uf_batcher;
+
+typedef struct uf_batcher_config {
+    uint32_t struct_size;        /* = sizeof(uf_batcher_config) */
+    uf_config model;             /* template for every device's handle (`device` is overridden; max_batch 0 = this max_batch) */
+    const int32_t* devices;      /* CUDA ordinals, one handle each (an ordinal may repeat); NULL = {0} */
+    uint32_t n_devices;
+    uint32_t max_batch;          /* frames per batch (0 = 64) */
+    uint32_t max_delay_us;       /* how long a worker waits for a batch to fill (0 = 2000) */
+    uint32_t capacity;           /* frames queued per device before new ones are dropped (0 = 2 * max_batch) */
+    uint32_t workers;            /* batches in flight per device (0 = 2) */
+    uint32_t det_cap;            /* detections returned per frame (0 = 64) */
+    uint32_t max_frame_bytes;    /* pinned slot size (0 = 1280 * 720 * 3) */
+} uf_batcher_config;
+
+typedef struct uf_result {
+    uint64_t stream;             /* as submitted */
+    uint64_t user_tag;           /* as submitted (e.g. a frame sequence number) */
+    int32_t device;              /* CUDA ordinal that ran the frame */
+    int32_t status;              /* UF_OK, or the status of the failed batch (the frame is skipped, inferer.rs:37) */
+    uint32_t n_dets;             /* faces selected (may exceed det_cap; only min(n_dets, det_cap) were returned) */
+    uint32_t batch_size;         /* frames in the batch this frame rode in */
+    uint64_t latency_us;         /* commit -> result queued */
+} uf_result;
+
+typedef struct uf_batcher_stats {
+    uint64_t submitted, dropped, completed, failed, batches;
+} uf_batcher_stats;
+
+UF_API int uf_batcher_create(const uf_batcher_config* cfg, uf_batcher** out);
+/* Same with the batched call injected (the seam `trait InferModel` is in the reference, nn.rs:24-26): `fn` receives what
+ * uf_infer_batch would, plus `user` and the device ordinal; no handle is loaded and CUDA is not touched. This is how the
+ * queueing / routing / ordering logic is tested without a GPU; a product batcher passes through uf_batcher_create. */
+typedef int (*uf_batch_fn)(void* user, int32_t device, const uint8_t* const* rgb, const uint32_t* w, const uint32_t* h,
+                           uint32_t n, uf_det* out, uint32_t cap, uint32_t* n_out);
+UF_API int uf_batcher_create_ex(const uf_batcher_config* cfg, uf_batch_fn fn, void* user, uf_batcher** out);
+UF_API void uf_batcher_destroy(uf_batcher* b); /* finishes what is queued, joins the workers, frees the handles */
+/* *buf = pinned slot of >= bytes in the owner device's pool, or NULL when the queue is full (frame dropped, counted). */
+UF_API int uf_batcher_acquire(uf_batcher* b, uint64_t stream, size_t bytes, uint8_t** buf, uint64_t* ticket);
+UF_API int uf_batcher_commit(uf_batcher* b, uint64_t ticket, uint32_t w, uint32_t h, uint64_t user_tag);
+UF_API int uf_batcher_abort(uf_batcher* b, uint64_t ticket);
+UF_API int uf_batcher_try_submit(uf_batcher* b, uint64_t stream, const uint8_t* rgb, uint32_t w, uint32_t h,
+                                 uint64_t user_tag, int32_t* accepted);
+/* Up to cap finished frames: res[i] + dets[i * det_cap ..]. Waits at most timeout_ms for the first one. */
+UF_API int uf_batcher_poll(uf_batcher* b, uf_result* res, uf_det* dets, uint32_t cap, uint32_t timeout_ms, uint32_t* n_out);
+UF_API int uf_batcher_flush(uf_batcher* b, uint32_t timeout_ms); /* returns when everything committed so far is pollable */
+UF_API int uf_batcher_stats_read(const uf_batcher* b, uf_batcher_stats* out);
+UF_API int uf_batcher_owner(const uf_batcher* b, uint64_t stream, int32_t* device);
+UF_API int uf_batcher_model(uf_batcher* b, uint32_t device_slot, uf_model** out); /* borrowed: parity hooks, profiling */
+
+/* ---- ingest helpers, host only (N4) ----
+ * `hashed(&id)` of infer_server/src/lib.rs:39-46: Rust's DefaultHasher (SipHash-1-3, zero keys) over the bytes of the
+ * stream name followed by the 0xff terminator `str::hash` appends. */
+UF_API int uf_stream_hash(const uint8_t* name, size_t len, uint64_t* out);
+/* One length-delimited frame of the data socket (data_socket.rs:34-47) = a bincode-1.3 `ProtoMsg`
+ * (common/src/protocol.rs:7-19): u32 LE variant (0 ConnectReq(String), 1 FrameMsg{id: String, data: Vec<u8>}),
+ * u64 LE lengths. Zero-copy: *id / *data point into msg. kind: 0 / 1. Malformed input = UF_ERR_INVALID_ARG. */
+UF_API int uf_protomsg_parse(const uint8_t* msg, size_t len, uint32_t* kind, const uint8_t** id, size_t* id_len,
+                             const uint8_t** data, size_t* data_len);
+/* test hook: SipHash-c-d with explicit keys (uf_stream_hash is c = 1, d = 3, zero keys; c = 2, d = 4 has published vectors) */
+UF_API int uf_debug_siphash(uint32_t c, uint32_t d, uint64_t k0, uint64_t k1, const uint8_t* in, size_t len, uint64_t* out);
 
 UF_API const char* uf_last_error(void);
 UF_API const char* uf_version(void);

@@ -14,6 +14,7 @@ UF_NORM_REFERENCE, UF_NORM_127_128 = 0, 1
 UF_FLAG_FORCE_GENERIC, UF_FLAG_NO_GRAPH, UF_FLAG_NO_FUSION, UF_FLAG_NO_TC, UF_FLAG_FUSE_DW_TC, UF_FLAG_PDL = 1, 2, 4, 8, 16, 32
 UF_FLAG_TMA_SIMT_PW = 64
 UF_FLAG_DENSE3_TC = 128
+UF_FLAG_NO_PRESTEM = 256
 
 
 class uf_det(C.Structure):
@@ -39,8 +40,26 @@ class uf_kernel_stat(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("compulsory_bytes", C.c_uint64), ("flops", C.c_uint64)]
 
 
+class uf_batcher_config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("model", uf_config), ("devices", C.POINTER(C.c_int32)), ("n_devices", C.c_uint32),
+                ("max_batch", C.c_uint32), ("max_delay_us", C.c_uint32), ("capacity", C.c_uint32), ("workers", C.c_uint32),
+                ("det_cap", C.c_uint32), ("max_frame_bytes", C.c_uint32)]
+
+
+class uf_result(C.Structure):
+    _fields_ = [("stream", C.c_uint64), ("user_tag", C.c_uint64), ("device", C.c_int32), ("status", C.c_int32),
+                ("n_dets", C.c_uint32), ("batch_size", C.c_uint32), ("latency_us", C.c_uint64)]
+
+
+class uf_batcher_stats(C.Structure):
+    _fields_ = [("submitted", C.c_uint64), ("dropped", C.c_uint64), ("completed", C.c_uint64), ("failed", C.c_uint64),
+                ("batches", C.c_uint64)]
+
+
 _p = C.POINTER
 _void_pp = _p(C.c_void_p)
+uf_batch_fn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, _p(C.c_void_p), _p(C.c_uint32), _p(C.c_uint32), C.c_uint32,
+                          _p(uf_det), C.c_uint32, _p(C.c_uint32))
 # name -> (restype, argtypes); every symbol include/ultraface_b200.h declares
 SIGNATURES = {
     "uf_model_load": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_int32, C.c_uint32, _void_pp]),
@@ -55,6 +74,7 @@ SIGNATURES = {
     "uf_raw_outputs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _p(C.c_float), _p(C.c_float)]),
     "uf_preproc_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "uf_preproc_u8_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "uf_debug_prestem_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "uf_preproc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _p(C.c_float)]),
     "uf_postproc": (C.c_int, [C.c_void_p, _p(C.c_float), _p(C.c_float), C.c_uint32, _p(uf_det), C.c_uint32,
                               _p(C.c_uint32), _p(C.c_int32)]),
@@ -71,6 +91,21 @@ SIGNATURES = {
     "uf_onnx_inspect": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t, _p(C.c_size_t)]),
     "uf_resize_taps": (C.c_int, [C.c_uint32, C.c_uint32, _p(C.c_int32), _p(C.c_int32), _p(C.c_float), C.c_uint32,
                                  _p(C.c_uint32)]),
+    "uf_batcher_create": (C.c_int, [_p(uf_batcher_config), _void_pp]),
+    "uf_batcher_create_ex": (C.c_int, [_p(uf_batcher_config), uf_batch_fn, C.c_void_p, _void_pp]),
+    "uf_batcher_destroy": (None, [C.c_void_p]),
+    "uf_batcher_acquire": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, _void_pp, _p(C.c_uint64)]),
+    "uf_batcher_commit": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]),
+    "uf_batcher_abort": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "uf_batcher_try_submit": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, _p(C.c_int32)]),
+    "uf_batcher_poll": (C.c_int, [C.c_void_p, _p(uf_result), _p(uf_det), C.c_uint32, C.c_uint32, _p(C.c_uint32)]),
+    "uf_batcher_flush": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "uf_batcher_stats_read": (C.c_int, [C.c_void_p, _p(uf_batcher_stats)]),
+    "uf_batcher_owner": (C.c_int, [C.c_void_p, C.c_uint64, _p(C.c_int32)]),
+    "uf_batcher_model": (C.c_int, [C.c_void_p, C.c_uint32, _void_pp]),
+    "uf_stream_hash": (C.c_int, [C.c_char_p, C.c_size_t, _p(C.c_uint64)]),
+    "uf_protomsg_parse": (C.c_int, [C.c_char_p, C.c_size_t, _p(C.c_uint32), _void_pp, _p(C.c_size_t), _void_pp, _p(C.c_size_t)]),
+    "uf_debug_siphash": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_char_p, C.c_size_t, _p(C.c_uint64)]),
     "uf_last_error": (C.c_char_p, []),
     "uf_version": (C.c_char_p, []),
     "uf_device_count": (C.c_int, [_p(C.c_int32)]),

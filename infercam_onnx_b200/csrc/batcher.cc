@@ -1,0 +1,478 @@
+// batcher.cc — stream batcher and stream -> GPU router behind the C ABI (uf_batcher_*), plus the ingest helpers
+// uf_stream_hash / uf_protomsg_parse. SURVEY.md §8f rows N1 and N4.
+//
+// What it replaces in the reference (/root/reference/infer_server/src): the single inference task that handles one
+// frame at a time (`Inferer::run`, inferer.rs:29-50), the bounded lossy queue in front of it (`INFER_IMAGES_CHANNEL`,
+// lib.rs:32-37, filled with `try_send_ref` in router.rs:64-72) and the `hashed(&id)` stream key (lib.rs:39-46,
+// router.rs:58) — which here also picks the GPU. Host plumbing only: no arithmetic on pixels happens in this file; the
+// batches go through the same entry point an external caller would use (uf_infer_batch).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ultraface_b200.h"
+
+namespace uf {
+void set_last_error(const std::string& msg);  // engine.cu (thread-local message behind uf_last_error)
+}
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+
+struct Ticket {            // one pinned slot
+    uint8_t* buf = nullptr;
+    uint64_t stream = 0, tag = 0;
+    uint32_t w = 0, h = 0;
+    Clock::time_point t_commit;
+    int state = 0;         // 0 free, 1 acquired, 2 queued, 3 in a batch
+};
+
+struct Done {
+    uf_result res;
+    std::vector<uf_det> dets;
+};
+
+struct Device {
+    int32_t ordinal = 0;
+    uf_model* model = nullptr;
+    bool pinned = true;
+    uint8_t* pool = nullptr;           // pinned, nslots * slot_bytes
+    std::vector<Ticket> slots;
+    std::vector<uint32_t> free_slots;
+    std::deque<uint32_t> queue;        // committed slots, submission order
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t next_batch = 0;           // sequence number of the next batch formed
+    uint64_t next_deliver = 0;         // sequence number allowed to publish its results
+    std::condition_variable deliver_cv;
+    std::vector<std::thread> workers;
+};
+
+}  // namespace
+
+struct uf_batcher {
+    uf_batcher_config cfg{};
+    uf_batch_fn backend = nullptr;  // NULL: uf_infer_batch on the device's own handle
+    void* backend_user = nullptr;
+    std::string onnx_path;
+    std::vector<std::unique_ptr<Device>> devs;
+    size_t slot_bytes = 0;
+    uint32_t nslots = 0;
+    std::atomic<bool> closing{false};
+    // results
+    std::mutex done_mu;
+    std::condition_variable done_cv;
+    std::deque<Done> done;
+    std::atomic<uint64_t> submitted{0}, dropped{0}, completed{0}, failed{0}, batches{0}, inflight{0};
+};
+
+namespace {
+
+inline uint64_t ticket_of(uint32_t dev, uint32_t slot) { return ((uint64_t)dev << 32) | slot; }
+
+void worker_loop(uf_batcher* b, Device* d) {
+    const uint32_t max_batch = b->cfg.max_batch, det_cap = b->cfg.det_cap;
+    std::vector<uint32_t> take;
+    std::vector<const uint8_t*> ptrs;
+    std::vector<uint32_t> ws, hs, counts;
+    std::vector<uf_det> dets;
+    if (!b->backend) cudaSetDevice(d->ordinal);
+    for (;;) {
+        uint64_t seq;
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->cv.wait(lk, [&] { return !d->queue.empty() || b->closing.load(); });
+            if (d->queue.empty()) return;  // closing and drained
+            // a batch is worth waiting for, but not for long: a lone stream must not be held back
+            const auto deadline = Clock::now() + std::chrono::microseconds(b->cfg.max_delay_us);
+            while (d->queue.size() < max_batch && !b->closing.load())
+                if (d->cv.wait_until(lk, deadline) == std::cv_status::timeout) break;
+            take.clear();
+            while (!d->queue.empty() && take.size() < max_batch) {
+                take.push_back(d->queue.front());
+                d->queue.pop_front();
+                d->slots[take.back()].state = 3;
+            }
+            seq = d->next_batch++;
+        }
+        const uint32_t n = (uint32_t)take.size();
+        ptrs.resize(n); ws.resize(n); hs.resize(n); counts.assign(n, 0);
+        dets.resize((size_t)n * det_cap);
+        for (uint32_t i = 0; i < n; ++i) {
+            const Ticket& t = d->slots[take[i]];
+            ptrs[i] = t.buf; ws[i] = t.w; hs[i] = t.h;
+        }
+        const int rc = b->backend
+                           ? b->backend(b->backend_user, d->ordinal, ptrs.data(), ws.data(), hs.data(), n, dets.data(), det_cap, counts.data())
+                           : uf_infer_batch(d->model, ptrs.data(), ws.data(), hs.data(), n, dets.data(), det_cap, counts.data());
+        const auto now = Clock::now();
+        std::vector<Done> out(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const Ticket& t = d->slots[take[i]];
+            Done& o = out[i];
+            o.res.stream = t.stream; o.res.user_tag = t.tag; o.res.device = d->ordinal; o.res.status = rc;
+            o.res.n_dets = rc == UF_OK ? counts[i] : 0; o.res.batch_size = n;
+            o.res.latency_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(now - t.t_commit).count();
+            if (rc == UF_OK) {
+                const uint32_t k = counts[i] < det_cap ? counts[i] : det_cap;
+                o.dets.assign(dets.begin() + (size_t)i * det_cap, dets.begin() + (size_t)i * det_cap + k);
+            }
+        }
+        {
+            // publish batches in the order they were formed: a stream lives on one device, so this keeps every
+            // stream's results in submission order even with several batches in flight
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->deliver_cv.wait(lk, [&] { return d->next_deliver == seq; });
+            {
+                std::lock_guard<std::mutex> dl(b->done_mu);
+                for (auto& o : out) b->done.push_back(std::move(o));
+            }
+            for (uint32_t s : take) {
+                d->slots[s].state = 0;
+                d->free_slots.push_back(s);
+            }
+            d->next_deliver++;
+            d->deliver_cv.notify_all();
+        }
+        b->batches++;
+        (rc == UF_OK ? b->completed : b->failed) += n;
+        b->inflight -= n;
+        b->done_cv.notify_all();
+    }
+}
+
+struct Fail {
+    int code;
+    std::string msg;
+};
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return UF_OK;
+    } catch (const Fail& e) {
+        uf::set_last_error(e.msg);
+        return e.code;
+    } catch (const std::exception& e) {
+        uf::set_last_error(e.what());
+        return UF_ERR_INVALID_ARG;
+    }
+}
+
+#define NEED(cond, msg) do { if (!(cond)) throw Fail{UF_ERR_INVALID_ARG, msg}; } while (0)
+
+// SipHash-c-d (Aumasson & Bernstein), streaming over one buffer plus a trailing byte; Rust's DefaultHasher is c=1, d=3
+inline uint64_t rotl(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
+
+uint64_t siphash(int c_rounds, int d_rounds, uint64_t k0, uint64_t k1, const uint8_t* in, size_t len) {
+    uint64_t v0 = k0 ^ 0x736f6d6570736575ull, v1 = k1 ^ 0x646f72616e646f6dull, v2 = k0 ^ 0x6c7967656e657261ull,
+             v3 = k1 ^ 0x7465646279746573ull;
+    auto round = [&] {
+        v0 += v1; v1 = rotl(v1, 13); v1 ^= v0; v0 = rotl(v0, 32);
+        v2 += v3; v3 = rotl(v3, 16); v3 ^= v2;
+        v0 += v3; v3 = rotl(v3, 21); v3 ^= v0;
+        v2 += v1; v1 = rotl(v1, 17); v1 ^= v2; v2 = rotl(v2, 32);
+    };
+    const size_t full = len / 8 * 8;
+    for (size_t i = 0; i < full; i += 8) {
+        uint64_t m = 0;
+        for (int k = 0; k < 8; ++k) m |= (uint64_t)in[i + k] << (8 * k);
+        v3 ^= m;
+        for (int r = 0; r < c_rounds; ++r) round();
+        v0 ^= m;
+    }
+    uint64_t last = (uint64_t)(len & 0xff) << 56;
+    for (size_t k = 0; k < len - full; ++k) last |= (uint64_t)in[full + k] << (8 * k);
+    v3 ^= last;
+    for (int r = 0; r < c_rounds; ++r) round();
+    v0 ^= last;
+    v2 ^= 0xff;
+    for (int r = 0; r < d_rounds; ++r) round();
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+
+}  // namespace
+
+extern "C" {
+
+static void free_device(Device& d) {
+    if (d.model) uf_model_free(d.model);
+    if (d.pinned) uf_host_free(d.pool); else free(d.pool);
+}
+
+int uf_batcher_create(const uf_batcher_config* cfg, uf_batcher** out) { return uf_batcher_create_ex(cfg, nullptr, nullptr, out); }
+
+int uf_batcher_create_ex(const uf_batcher_config* cfg, uf_batch_fn backend, void* user, uf_batcher** out) {
+    return guarded([&] {
+        NEED(cfg && out, "null argument");
+        NEED(cfg->struct_size == sizeof(uf_batcher_config), "uf_batcher_config.struct_size mismatch");
+        NEED(backend || (cfg->model.struct_size == sizeof(uf_config) && cfg->model.onnx_path), "uf_batcher_config.model is not a filled uf_config");
+        *out = nullptr;
+        std::unique_ptr<uf_batcher> b(new uf_batcher());
+        b->cfg = *cfg;
+        b->backend = backend;
+        b->backend_user = user;
+        b->onnx_path = cfg->model.onnx_path ? cfg->model.onnx_path : "";
+        b->cfg.model.onnx_path = b->onnx_path.c_str();
+        uf_batcher_config& c = b->cfg;
+        if (c.max_batch == 0) c.max_batch = 64;
+        if (c.max_delay_us == 0) c.max_delay_us = 2000;
+        if (c.capacity == 0) c.capacity = 2 * c.max_batch;
+        if (c.workers == 0) c.workers = 2;
+        if (c.det_cap == 0) c.det_cap = 64;
+        if (c.max_frame_bytes == 0) c.max_frame_bytes = 1280 * 720 * 3;
+        NEED(c.workers <= 8 && c.max_batch <= 4096 && c.capacity <= (1u << 20), "workers / max_batch / capacity out of range");
+        std::vector<int32_t> ords(cfg->devices ? cfg->devices : nullptr, cfg->devices ? cfg->devices + cfg->n_devices : nullptr);
+        if (ords.empty()) ords.push_back(0);
+        NEED(ords.size() <= 64, "too many devices");
+        b->slot_bytes = ((size_t)c.max_frame_bytes + 255) / 256 * 256;
+        b->nslots = c.capacity + c.workers * c.max_batch;  // queued + riding in a batch
+        for (size_t i = 0; i < ords.size(); ++i) {
+            std::unique_ptr<Device> d(new Device());
+            d->ordinal = ords[i];
+            void* p = nullptr;
+            if (backend) {  // injected backend (tests): no handle, no CUDA, pageable pool
+                d->pinned = false;
+                p = malloc(b->slot_bytes * b->nslots);
+                if (!p) {
+                    for (auto& e : b->devs) free_device(*e);
+                    throw Fail{UF_ERR_INVALID_ARG, "out of host memory for the frame pool"};
+                }
+            } else {
+                uf_config mc = c.model;
+                mc.device = ords[i];
+                if (mc.max_batch < c.max_batch) mc.max_batch = c.max_batch;
+                if (mc.lanes == 0) mc.lanes = c.workers;
+                int rc = uf_model_load_ex(&mc, &d->model);
+                if (rc != UF_OK) {
+                    for (auto& e : b->devs) free_device(*e);
+                    throw Fail{rc, std::string("device ") + std::to_string(ords[i]) + ": " + uf_last_error()};
+                }
+                cudaSetDevice(ords[i]);
+                rc = uf_host_alloc(b->slot_bytes * b->nslots, &p);
+                if (rc != UF_OK) {
+                    uf_model_free(d->model);
+                    for (auto& e : b->devs) free_device(*e);
+                    throw Fail{rc, std::string("pinned frame pool: ") + uf_last_error()};
+                }
+            }
+            d->pool = (uint8_t*)p;
+            d->slots.resize(b->nslots);
+            for (uint32_t s = 0; s < b->nslots; ++s) {
+                d->slots[s].buf = d->pool + (size_t)s * b->slot_bytes;
+                d->free_slots.push_back(b->nslots - 1 - s);
+            }
+            b->devs.push_back(std::move(d));
+        }
+        for (auto& d : b->devs)
+            for (uint32_t w = 0; w < c.workers; ++w) d->workers.emplace_back(worker_loop, b.get(), d.get());
+        *out = b.release();
+    });
+}
+
+void uf_batcher_destroy(uf_batcher* b) {
+    if (!b) return;
+    b->closing = true;
+    for (auto& d : b->devs) {
+        { std::lock_guard<std::mutex> lk(d->mu); }
+        d->cv.notify_all();
+    }
+    for (auto& d : b->devs)
+        for (auto& t : d->workers) t.join();
+    for (auto& d : b->devs) free_device(*d);
+    delete b;
+}
+
+int uf_batcher_acquire(uf_batcher* b, uint64_t stream, size_t bytes, uint8_t** buf, uint64_t* ticket) {
+    return guarded([&] {
+        NEED(b && buf && ticket, "null argument");
+        *buf = nullptr;
+        *ticket = 0;
+        NEED(!b->closing.load(), "batcher is closing");
+        if (bytes > b->slot_bytes) throw Fail{UF_ERR_CAPACITY, "frame larger than uf_batcher_config.max_frame_bytes"};
+        const uint32_t di = (uint32_t)(stream % b->devs.size());
+        Device& d = *b->devs[di];
+        std::lock_guard<std::mutex> lk(d.mu);
+        // lossy, like try_send_ref on a full INFER_IMAGES_CHANNEL (router.rs:64-72): the frame is dropped, the caller goes on
+        if (d.queue.size() >= b->cfg.capacity || d.free_slots.empty()) {
+            b->dropped++;
+            return;
+        }
+        const uint32_t s = d.free_slots.back();
+        d.free_slots.pop_back();
+        Ticket& t = d.slots[s];
+        t.state = 1;
+        t.stream = stream;
+        *buf = t.buf;
+        *ticket = ticket_of(di, s);
+    });
+}
+
+static Ticket& ticket_ref(uf_batcher* b, uint64_t ticket, Device** dev) {
+    const uint32_t di = (uint32_t)(ticket >> 32), s = (uint32_t)ticket;
+    if (di >= b->devs.size() || s >= b->nslots) throw Fail{UF_ERR_INVALID_ARG, "bad ticket"};
+    *dev = b->devs[di].get();
+    return (*dev)->slots[s];
+}
+
+int uf_batcher_commit(uf_batcher* b, uint64_t ticket, uint32_t w, uint32_t h, uint64_t user_tag) {
+    return guarded([&] {
+        NEED(b, "null argument");
+        Device* d = nullptr;
+        Ticket& t = ticket_ref(b, ticket, &d);
+        NEED(w > 0 && h > 0 && (size_t)w * h * 3 <= b->slot_bytes, "frame size does not fit the slot");
+        {
+            std::lock_guard<std::mutex> lk(d->mu);
+            NEED(t.state == 1, "ticket is not in the acquired state");
+            t.w = w; t.h = h; t.tag = user_tag; t.t_commit = Clock::now(); t.state = 2;
+            d->queue.push_back((uint32_t)ticket);
+            b->submitted++;
+            b->inflight++;
+        }
+        d->cv.notify_one();
+    });
+}
+
+int uf_batcher_abort(uf_batcher* b, uint64_t ticket) {
+    return guarded([&] {
+        NEED(b, "null argument");
+        Device* d = nullptr;
+        Ticket& t = ticket_ref(b, ticket, &d);
+        std::lock_guard<std::mutex> lk(d->mu);
+        NEED(t.state == 1, "ticket is not in the acquired state");
+        t.state = 0;
+        d->free_slots.push_back((uint32_t)ticket);
+    });
+}
+
+int uf_batcher_try_submit(uf_batcher* b, uint64_t stream, const uint8_t* rgb, uint32_t w, uint32_t h, uint64_t user_tag,
+                          int32_t* accepted) {
+    if (accepted) *accepted = 0;
+    if (!b || !rgb || !accepted || w == 0 || h == 0) {
+        uf::set_last_error("bad argument");
+        return UF_ERR_INVALID_ARG;
+    }
+    uint8_t* buf = nullptr;
+    uint64_t ticket = 0;
+    int rc = uf_batcher_acquire(b, stream, (size_t)w * h * 3, &buf, &ticket);
+    if (rc != UF_OK || !buf) return rc;
+    memcpy(buf, rgb, (size_t)w * h * 3);
+    rc = uf_batcher_commit(b, ticket, w, h, user_tag);
+    if (rc == UF_OK) *accepted = 1;
+    else uf_batcher_abort(b, ticket);
+    return rc;
+}
+
+int uf_batcher_poll(uf_batcher* b, uf_result* res, uf_det* dets, uint32_t cap, uint32_t timeout_ms, uint32_t* n_out) {
+    return guarded([&] {
+        NEED(b && n_out && (cap == 0 || (res && dets)), "null argument");
+        *n_out = 0;
+        std::unique_lock<std::mutex> lk(b->done_mu);
+        if (b->done.empty() && timeout_ms)
+            b->done_cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return !b->done.empty(); });
+        uint32_t n = 0;
+        while (n < cap && !b->done.empty()) {
+            Done& o = b->done.front();
+            res[n] = o.res;
+            if (!o.dets.empty()) memcpy(dets + (size_t)n * b->cfg.det_cap, o.dets.data(), o.dets.size() * sizeof(uf_det));
+            b->done.pop_front();
+            ++n;
+        }
+        *n_out = n;
+    });
+}
+
+int uf_batcher_flush(uf_batcher* b, uint32_t timeout_ms) {
+    return guarded([&] {
+        NEED(b, "null argument");
+        std::unique_lock<std::mutex> lk(b->done_mu);
+        const bool ok = b->done_cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return b->inflight.load() == 0; });
+        if (!ok) throw Fail{UF_ERR_CAPACITY, "uf_batcher_flush timed out with frames still in flight"};
+    });
+}
+
+int uf_batcher_stats_read(const uf_batcher* b, uf_batcher_stats* out) {
+    return guarded([&] {
+        NEED(b && out, "null argument");
+        out->submitted = b->submitted.load(); out->dropped = b->dropped.load(); out->completed = b->completed.load();
+        out->failed = b->failed.load(); out->batches = b->batches.load();
+    });
+}
+
+int uf_batcher_owner(const uf_batcher* b, uint64_t stream, int32_t* device) {
+    return guarded([&] {
+        NEED(b && device, "null argument");
+        *device = b->devs[stream % b->devs.size()]->ordinal;
+    });
+}
+
+int uf_batcher_model(uf_batcher* b, uint32_t device_slot, uf_model** out) {
+    return guarded([&] {
+        NEED(b && out && device_slot < b->devs.size(), "bad argument");
+        NEED(b->devs[device_slot]->model, "this batcher runs an injected backend, it owns no model handle");
+        *out = b->devs[device_slot]->model;
+    });
+}
+
+int uf_stream_hash(const uint8_t* name, size_t len, uint64_t* out) {
+    return guarded([&] {
+        NEED(out && (name || len == 0), "null argument");
+        // `impl Hash for str`: state.write(bytes); state.write_u8(0xff)  — SipHash is a byte-stream hash, so this is the
+        // hash of name || 0xff
+        std::vector<uint8_t> buf(name, name + len);
+        buf.push_back(0xff);
+        *out = siphash(1, 3, 0, 0, buf.data(), buf.size());
+    });
+}
+
+// test hook: the generic SipHash-c-d with explicit keys (checked against the published SipHash-2-4 vectors)
+int uf_debug_siphash(uint32_t c, uint32_t d, uint64_t k0, uint64_t k1, const uint8_t* in, size_t len, uint64_t* out) {
+    return guarded([&] {
+        NEED(out && (in || len == 0) && c >= 1 && c <= 8 && d >= 1 && d <= 8, "bad argument");
+        *out = siphash((int)c, (int)d, k0, k1, in, len);
+    });
+}
+
+int uf_protomsg_parse(const uint8_t* msg, size_t len, uint32_t* kind, const uint8_t** id, size_t* id_len,
+                      const uint8_t** data, size_t* data_len) {
+    return guarded([&] {
+        NEED(msg && kind && id && id_len && data && data_len, "null argument");
+        *id = *data = nullptr;
+        *id_len = *data_len = 0;
+        size_t pos = 0;
+        auto u = [&](int bytes) -> uint64_t {
+            if (len - pos < (size_t)bytes) throw Fail{UF_ERR_INVALID_ARG, "ProtoMsg: truncated"};
+            uint64_t v = 0;
+            for (int k = 0; k < bytes; ++k) v |= (uint64_t)msg[pos + k] << (8 * k);
+            pos += bytes;
+            return v;
+        };
+        auto blob = [&](const uint8_t** p, size_t* n) {
+            const uint64_t l = u(8);
+            if (l > len - pos) throw Fail{UF_ERR_INVALID_ARG, "ProtoMsg: length prefix exceeds the message"};
+            *p = msg + pos;
+            *n = (size_t)l;
+            pos += (size_t)l;
+        };
+        const uint64_t variant = u(4);
+        if (variant > 1) throw Fail{UF_ERR_INVALID_ARG, "ProtoMsg: unknown enum variant"};
+        *kind = (uint32_t)variant;
+        blob(id, id_len);
+        if (variant == 1) blob(data, data_len);
+        if (pos != len) throw Fail{UF_ERR_INVALID_ARG, "ProtoMsg: trailing bytes"};  // bincode::deserialize tolerates them; a frame never has any
+    });
+}
+
+}  // extern "C"

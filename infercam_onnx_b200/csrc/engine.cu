@@ -50,6 +50,7 @@ struct ArgError : public std::exception {
     } while (0)
 
 static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }  // batcher.cc
 
 enum class Impl { Generic, Stem, Depthwise, Pointwise, PointwiseTC, FusedDwTC, FusedDwPw, FusedPix, FusedHead, FusedHead2, FusedTma, SmallDense, SmallDenseTC, Conv3x3Warp, Add, Relu, Copy };
 
@@ -188,6 +189,8 @@ struct uf_model {
     size_t d_hook_cap = 0;
     std::vector<uint8_t> tensor_readable;  // per plan tensor: materialised in the arena
     std::vector<TcWeights> tc_weights;
+    bool prestem_ok = false;     // first step is the 3 -> 16 stem kernel and UF_FLAG_NO_PRESTEM is not set
+    std::string prestem_label;
 
     ~uf_model();
 };
@@ -195,6 +198,15 @@ struct uf_model {
 namespace uf {
 
 static inline int64_t align4(int64_t v) { return (v + 3) / 4 * 4; }
+
+// low part of a 3xTF32 weight split, rounded to nearest tf32 (the tensor core would truncate it: a bias, see tf32_lo)
+static inline float tf32_round(float v) {
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    u = (u + 0x1000u) & 0xffffe000u;
+    memcpy(&v, &u, 4);
+    return v;
+}
 
 static TView make_view(const uf_model& m, const Slot& s, int t) {
     const TensorDesc& td = m.plan.tensors[t];
@@ -428,7 +440,7 @@ static void build_tc_weights(uf_model& m) {
             float h;
             memcpy(&h, &u, 4);
             hi[i] = h;
-            lo[i] = op.w[i] - h;
+            lo[i] = tf32_round(op.w[i] - h);
         }
         TcWeights t;
         CK(cudaMalloc(&t.d_hi, hi.size() * sizeof(float)));
@@ -467,7 +479,7 @@ static void build_dense3_weights(uf_model& m) {
                     memcpy(&h, &u, 4);
                     const size_t i = (((size_t)tap * CQ + c / 4) * 16 + n) * 4 + c % 4;
                     hi[i] = h;
-                    lo[i] = w - h;
+                    lo[i] = tf32_round(w - h);
                 }
         TcWeights t;
         CK(cudaMalloc(&t.d_hi, hi.size() * sizeof(float)));
@@ -571,10 +583,10 @@ static void alloc_lane(uf_model& m, Lane& ln) {
         CK(cudaMalloc(&s.d_det_idx, (size_t)m.chunk * K * sizeof(int)));
         CK(cudaMalloc(&s.d_counts, (size_t)m.chunk * sizeof(int)));
         CK(cudaMalloc(&s.d_sort, (size_t)m.chunk * sort_cap * sizeof(unsigned long long)));
-        CK(cudaMalloc(&s.d_big_n, (size_t)m.chunk * sizeof(int)));
-        CK(cudaMemsetAsync(s.d_big_n, 0, (size_t)m.chunk * sizeof(int), s.stream));
+        CK(cudaMalloc(&s.d_big_n, ((size_t)m.chunk + 1) * sizeof(int)));  // [chunk] + the stage's any_big flag
+        CK(cudaMemsetAsync(s.d_big_n, 0, ((size_t)m.chunk + 1) * sizeof(int), s.stream));
         if (post_mask_supported(K)) {
-            const size_t mb = (size_t)m.chunk * K * post_mask_pitch(K) * sizeof(unsigned);
+            const size_t mb = (size_t)m.chunk * post_mask_words(K) * sizeof(unsigned);
             CK(cudaMalloc(&s.d_mask, mb));
             ws += mb;
         }
@@ -698,7 +710,12 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
     for (size_t si = first_step; si < m.steps.size() && si < last_step; ++si) {
         const Step& st = m.steps[si];
         const Op& op = p.ops[st.op];
-        ProfScope ps(m, s, st.label, st.alg_bytes * frames, st.min_bytes * frames, st.flops * frames);
+        const bool fused_pre = st.impl == Impl::Stem && input.W == 2 * p.net_w && input.H == 2 * p.net_h;
+        // fused resize + normalise + stem: SURVEY.md 8(d) preproc bytes (u8 source in, f32 NCHW out) on top of the conv's
+        const uint64_t pre_alg = fused_pre ? (uint64_t)input.W * input.H * 3 + 12ull * p.net_w * p.net_h : 0;
+        const uint64_t pre_min = fused_pre ? (uint64_t)input.W * input.H * 3 - 3ull * p.net_w * p.net_h : 0;
+        ProfScope ps(m, s, fused_pre ? m.prestem_label : st.label, (st.alg_bytes + pre_alg) * frames, (st.min_bytes + pre_min) * frames,
+                     st.flops * frames);
         const float* w = m.d_weights + m.w_off[st.op];
         const float* b = m.d_weights + m.b_off[st.op];
         TView out = make_view(m, s, op.out);
@@ -712,7 +729,15 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
                                     op.in2 >= 0 ? &res : nullptr, w, b, cp, frames, s.stream);
                 break;
             }
-            case Impl::Stem: launch_stem(input, m.d_lut, out, st.host_w.data(), op.relu, frames, s.stream); break;
+            case Impl::Stem:
+                if (input.W == 2 * p.net_w && input.H == 2 * p.net_h) {  // the frames themselves: resize + normalise + stem in one kernel
+                    TapsRef t = get_taps(m, input.W, input.H);
+                    launch_prestem(input, m.d_lut, t->dev, out, st.host_w.data(), op.relu, (int)m.cfg.resize_round_intermediate, frames,
+                                   nullptr, s.stream);
+                } else {
+                    launch_stem(input, m.d_lut, out, st.host_w.data(), op.relu, frames, s.stream);
+                }
+                break;
             case Impl::Depthwise: launch_depthwise(in, out, w, b, op.stride, op.relu, frames, s.stream); break;
             case Impl::Pointwise:
                 launch_pointwise(in, out, op.in2 >= 0 ? &res : nullptr, w, b, op.relu, frames, s.stream);
@@ -833,7 +858,7 @@ static void run_tail_post(uf_model& m, Lane& ln, Slot& s, uint32_t first, int fr
     float* scores = ln.d_scores + (size_t)first * K * 2;
     float* boxes = ln.d_boxes + (size_t)first * K * 4;
     PostBuffers pb{s.d_sort, (int)post_sort_scratch_elems(K), s.d_sel, s.d_dets, s.d_det_idx, s.d_counts,
-                   s.d_mask, post_mask_pitch(K), s.d_big_n};
+                   s.d_mask, post_mask_pitch(K), s.d_big_n, s.d_big_n + m.chunk};
     // one CTA per frame decodes its own priors before the NMS: worth a launch when there are enough frames to fill the
     // GPU (or just one or two: batch-1 latency); a 32-frame stage of the 640x480 net (K = 17 640) decodes faster spread
     // over all SMs by the separate kernel
@@ -852,9 +877,13 @@ static void run_tail_post(uf_model& m, Lane& ln, Slot& s, uint32_t first, int fr
         launch_tail_post(conf.p, loc.p, conf.frame_stride, loc.frame_stride, m.d_priors, m.plan.center_variance,
                          m.plan.size_variance, scores, boxes, K, m.cfg.min_confidence, m.cfg.max_iou, pb, frames, s.stream);
     }
-    if (pb.mask) {  // frames with more than a few hundred candidates: suppression bit matrix + ordered sweep (2 launches)
-        ProfScope ps(m, s, "nms_bitmatrix_sweep", 0, 0, 0, 2);
-        launch_nms_big(scores, K, m.cfg.max_iou, pb, frames, s.stream);
+    if (pb.mask) {  // frames with more than a few hundred candidates: suppression bit matrix, then the ordered sweep
+        {
+            ProfScope ps(m, s, "nms_bitmatrix", 0, 0, 0);
+            launch_nms_mask(K, m.cfg.max_iou, pb, frames, s.stream);
+        }
+        ProfScope ps(m, s, "nms_sweep", 0, 0, 0);
+        launch_nms_sweep(scores, K, pb, frames, s.stream);
     }
     CK(cudaMemcpyAsync(s.h_counts, s.d_counts, (size_t)frames * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaMemcpy2DAsync(s.h_dets, (size_t)DET_FAST * 5 * sizeof(float), s.d_dets, (size_t)K * 5 * sizeof(float),
@@ -944,6 +973,14 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
     for (uint32_t i = 0; i < n; ++i)
         if ((int)fr[i].w != W || (int)fr[i].h != H) need += (size_t)fr[i].w * fr[i].h * 3 + 16;
     grow_input(s, need);
+    // every frame of the stage at exactly twice the network size (the benchmark's 640x480 webcam frames into RFB-320): they
+    // are only copied; the first kernel of the chain resamples, normalises and convolves them
+    bool all_double = m.prestem_ok && n > 0 && (int)fr[0].w == 2 * W && (int)fr[0].h == 2 * H;
+    for (uint32_t k = 1; k < n && all_double; ++k) all_double = fr[k].w == fr[0].w && fr[k].h == fr[0].h;
+    if (all_double) {
+        TapsRef t = get_taps(m, fr[0].w, fr[0].h);
+        all_double = prestem_supported(s.d_in, (long long)fr[0].w * fr[0].h * 3, fr[0].w, fr[0].h, W, H, t->dev);
+    }
     size_t off = 0;
     uint32_t i = 0;
     while (i < n) {
@@ -961,7 +998,7 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
             CK(cudaMemcpyAsync(dst + (size_t)(a - i) * fb, fr[a].p, (size_t)(b - a) * fb, cudaMemcpyHostToDevice, s.stream));
             a = b;
         }
-        if (!ident) {
+        if (!ident && !all_double) {
             TapsRef t = get_taps(m, fr[i].w, fr[i].h);
             ProfScope ps(m, s, "resize_triangle", (uint64_t)(j - i) * (fb + out_frame), (uint64_t)(j - i) * (fb + out_frame), 0);
             launch_resize(s.d_in + off, (long long)fb, fr[i].w, fr[i].h, s.d_resized + (size_t)i * out_frame,
@@ -971,6 +1008,7 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
         i = j;
     }
     U8View input{s.d_resized, (long long)out_frame, H, W};
+    if (all_double) input = U8View{s.d_in, (long long)fr[0].w * fr[0].h * 3, (int)fr[0].h, (int)fr[0].w};
     run_body(m, ln, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
 }
@@ -985,9 +1023,13 @@ static void run_chunk_device(uf_model& m, Lane& ln, Slot& s, const uint8_t* d_rg
         input.frame_stride = (long long)fb;
     } else {
         TapsRef t = get_taps(m, w, h);
-        ProfScope ps(m, s, "resize_triangle", (uint64_t)n * (fb + out_frame), (uint64_t)n * (fb + out_frame), 0);
-        launch_resize(d_rgb, (long long)fb, w, h, s.d_resized, (long long)out_frame, W, H, (int)n, t->dev,
-                      m.cfg.resize_round_intermediate, s.stream);
+        if (m.prestem_ok && prestem_supported(d_rgb, (long long)fb, w, h, W, H, t->dev)) {
+            input = U8View{d_rgb, (long long)fb, (int)h, (int)w};  // resampled inside the first kernel of the chain
+        } else {
+            ProfScope ps(m, s, "resize_triangle", (uint64_t)n * (fb + out_frame), (uint64_t)n * (fb + out_frame), 0);
+            launch_resize(d_rgb, (long long)fb, w, h, s.d_resized, (long long)out_frame, W, H, (int)n, t->dev,
+                          m.cfg.resize_round_intermediate, s.stream);
+        }
     }
     run_body(m, ln, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
@@ -1113,6 +1155,11 @@ static uf_model* load_model(const uf_config& cfg_in) {
     build_dense3_weights(*m);
     build_param_weights(*m);
     label_steps(*m);
+    m->prestem_ok = !m->steps.empty() && m->steps[0].impl == Impl::Stem && !(cfg.flags & UF_FLAG_NO_PRESTEM);
+    if (m->prestem_ok) {
+        const std::string& l = m->steps[0].label;
+        m->prestem_label = "resize2x_norm_stem_u8" + l.substr(l.find('['));
+    }
     build_lut(*m);
     CK(cudaMalloc(&m->d_priors, (size_t)m->K * 4 * sizeof(float)));
     CK(cudaMemcpy(m->d_priors, m->plan.priors.data(), (size_t)m->K * 4 * sizeof(float), cudaMemcpyHostToDevice));
@@ -1312,6 +1359,33 @@ int uf_preproc_u8_batch(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h,
     });
 }
 
+int uf_debug_prestem_u8(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t n, uint8_t* out_u8) {
+    return guarded([&] {
+        REQUIRE(m && rgb && out_u8 && w > 0 && h > 0 && n > 0, "bad argument");
+        if (n > m->chunk) throw ArgError(UF_ERR_CAPACITY, "uf_debug_prestem_u8: n exceeds the stage size (uf_config.chunk)");
+        LaneLock ll(*m, true);
+        Slot& s = ll.lane->slots[0];
+        CK(cudaSetDevice(m->cfg.device));
+        const int W = m->plan.net_w, H = m->plan.net_h;
+        const size_t fb = (size_t)w * h * 3, ob = (size_t)W * H * 3;
+        if (!m->prestem_ok) throw ArgError(UF_ERR_UNSUPPORTED, "this model's first layer does not run the fused resize + stem kernel");
+        grow_input(s, fb * n);
+        TapsRef t = get_taps(*m, w, h);
+        if (!prestem_supported(s.d_in, (long long)fb, w, h, W, H, t->dev))
+            throw ArgError(UF_ERR_UNSUPPORTED, "frames are not at exactly twice the network size");
+        CK(cudaMemcpyAsync(s.d_in, rgb, fb * n, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemsetAsync(s.d_resized, 0xA5, ob * n, s.stream));
+        const Step& st = m->steps[0];
+        const Op& op = m->plan.ops[st.op];
+        m->launches++;
+        launch_prestem(U8View{s.d_in, (long long)fb, (int)h, (int)w}, m->d_lut, t->dev, make_view(*m, s, op.out), st.host_w.data(), op.relu,
+                       (int)m->cfg.resize_round_intermediate, (int)n, s.d_resized, s.stream);
+        CK(cudaMemcpyAsync(out_u8, s.d_resized, ob * n, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+    });
+}
+
 int uf_preproc_f32(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, float* out) {
     return guarded([&] {
         REQUIRE(m && rgb && out && w > 0 && h > 0, "bad argument");
@@ -1347,19 +1421,24 @@ int uf_postproc(uf_model* m, const float* scores, const float* boxes, uint32_t K
         auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
         const size_t o_scores = 0, o_boxes = a16(o_scores + (size_t)K * 2 * 4), o_sel = a16(o_boxes + (size_t)K * 4 * 4),
                      o_dets = a16(o_sel + (size_t)K * 4 * 4), o_idx = a16(o_dets + (size_t)K * 5 * 4),
-                     o_cnt = a16(o_idx + (size_t)K * 4), o_big = a16(o_cnt + 4), o_sort = a16(o_big + 4),
+                     o_cnt = a16(o_idx + (size_t)K * 4), o_big = a16(o_cnt + 4), o_sort = a16(o_big + 8),
                      o_mask = a16(o_sort + sort_cap * 8),
-                     total = o_mask + (post_mask_supported((int)K) ? (size_t)K * post_mask_pitch((int)K) * 4 : 0);
+                     total = o_mask + (post_mask_supported((int)K) ? post_mask_words((int)K) * 4 : 0);
         char* d = (char*)hook_scratch(*m, total);
         CK(cudaMemcpyAsync(d + o_scores, scores, (size_t)K * 2 * 4, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(d + o_boxes, boxes, (size_t)K * 4 * 4, cudaMemcpyHostToDevice, s.stream));
         PostBuffers pb{(unsigned long long*)(d + o_sort), (int)sort_cap, (float*)(d + o_sel), (float*)(d + o_dets),
                        (int*)(d + o_idx), (int*)(d + o_cnt),
-                       post_mask_supported((int)K) ? (unsigned*)(d + o_mask) : nullptr, post_mask_pitch((int)K), (int*)(d + o_big)};
+                       post_mask_supported((int)K) ? (unsigned*)(d + o_mask) : nullptr, post_mask_pitch((int)K), (int*)(d + o_big),
+                       (int*)(d + o_big) + 1};
         m->launches += pb.mask ? 3 : 1;
+        CK(cudaMemsetAsync(d + o_big, 0, 8, s.stream));
         launch_post((const float*)(d + o_scores), (const float*)(d + o_boxes), (int)K, m->cfg.min_confidence,
                     m->cfg.max_iou, pb, 1, s.stream);
-        launch_nms_big((const float*)(d + o_scores), (int)K, m->cfg.max_iou, pb, 1, s.stream);
+        if (pb.mask) {
+            launch_nms_mask((int)K, m->cfg.max_iou, pb, 1, s.stream);
+            launch_nms_sweep((const float*)(d + o_scores), (int)K, pb, 1, s.stream);
+        }
         int cnt = 0;
         CK(cudaMemcpyAsync(&cnt, d + o_cnt, 4, cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));

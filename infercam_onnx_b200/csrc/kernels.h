@@ -48,6 +48,10 @@ void launch_conv_generic(const TView& in, const U8View* in_u8, const float* lut,
 // host_w: 27*16 weights [ky][kx][ci][co] + 16 biases in HOST memory (passed as a __grid_constant__ parameter)
 void launch_stem(const U8View& in, const float* lut, const TView& out, const float* host_w, int relu, int frames,
                  cudaStream_t s);
+// K1 + K2 + K3 fused for frames at exactly twice the network size (kernels_prestem.cu): src = the u8 frames themselves
+bool prestem_supported(const uint8_t* src, long long src_frame_stride, int sw, int sh, int net_w, int net_h, const ResizeTapsDev& t);
+void launch_prestem(const U8View& src, const float* lut, const ResizeTapsDev& t, const TView& out, const float* host_w, int relu,
+                    int round_intermediate, int frames, uint8_t* dbg_resized, cudaStream_t s);
 // K4 depthwise 3x3 (pad 1, stride 1|2), weights [9][C]
 void launch_depthwise(const TView& in, const TView& out, const float* w_tc, const float* b, int stride,
                       int relu, int frames, cudaStream_t s);
@@ -156,6 +160,7 @@ struct PostBuffers {
     unsigned* mask;                    // [frames][K][mask_pitch] suppression bits, rows / columns in processing order
     int mask_pitch;                    // words per row (post_mask_pitch(K))
     int* big_n;                        // [frames] candidates of a frame left to the bit-matrix kernels (0: done already)
+    int* any_big;                      // [1] some frame of the stage published a candidate list (reset by the sweep)
 };
 void launch_post(const float* scores, const float* boxes, int K, float min_conf, float max_iou,
                  const PostBuffers& pb, int frames, cudaStream_t s);
@@ -164,9 +169,11 @@ void launch_tail_post(const float* conf, const float* loc, long long conf_frame_
                       float min_conf, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s);
 size_t post_sort_scratch_elems(int K);  // sort_cap for a given K
 int post_configure();                   // opt in to large dynamic smem; returns cudaError_t
-// second half of the post step for the frames post_kernel left to the bit-matrix path (two launches; no-op without pb.mask)
-void launch_nms_big(const float* scores, int K, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s);
+// second half of the post step for the frames post_kernel left to the bit-matrix path (requires pb.mask)
+void launch_nms_mask(int K, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s);
+void launch_nms_sweep(const float* scores, int K, const PostBuffers& pb, int frames, cudaStream_t s);
 int post_mask_pitch(int K);
+size_t post_mask_words(int K);  // per frame
 bool post_mask_supported(int K);
 
 }  // namespace uf

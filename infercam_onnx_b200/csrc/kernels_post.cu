@@ -119,6 +119,22 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, const float4 b, floa
     return iou(a, b) > max_iou;
 }
 
+// The same decision for the bit-matrix kernel, where both areas are known beforehand (area_a = bbox_area of the candidate,
+// area_b of the earlier box) and max_iou >= 0: the division is replaced by a comparison against max_iou * denominator
+// with a guard band of 1e-6 (8 ulp) on either side — inside the band (one pair in millions) the reference's division decides,
+// so the result is the reference's, bit for bit. thr_hi / thr_lo = max_iou * (1 +- 1e-6).
+__device__ __forceinline__ bool iou_exceeds_fast(const float4 a, float area_a, const float4 b, float area_b, float max_iou,
+                                                 float thr_hi, float thr_lo) {
+    const float w = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    const float h = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float o = (w < 0.0f || h < 0.0f) ? 0.0f : __fmul_rn(w, h);
+    if (o == 0.0f) return false;  // 0 / positive = 0 cannot exceed a non-negative threshold
+    const float d = __fadd_rn(__fsub_rn(__fadd_rn(area_a, area_b), o), 1.0e-7f);
+    if (o > __fmul_rn(thr_hi, d)) return true;
+    if (o < __fmul_rn(thr_lo, d)) return false;
+    return __fdiv_rn(o, d) > max_iou;
+}
+
 // Raw head outputs for the fused tail (TAIL = true): the CTA first turns its frame's conf / loc rows into
 // scores / boxes (same arithmetic as tail_kernel), counting candidates on the way, then carries on with them.
 struct TailIn {
@@ -216,7 +232,10 @@ post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float 
     int* didx = pb.det_idx ? pb.det_idx + (size_t)f * K : nullptr;
     if (pb.mask != nullptr) {
         const bool big = n > NMS_SMALL;
-        if (tid == 0) pb.big_n[f] = big ? n : 0;
+        if (tid == 0) {
+            pb.big_n[f] = big ? n : 0;
+            if (big) atomicOr(pb.any_big, 1);
+        }
         if (big) {  // publish the sorted candidates (boxes in processing order, keys = score | prior) and leave
             unsigned long long* gkeys = pb.sort_scratch + (size_t)f * pb.sort_cap;
             for (int i = tid; i < n; i += PTHR) {
@@ -303,114 +322,182 @@ post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float 
 
 // ---------------------------------------------------------------------------------------------
 // nms_mask_kernel: bit (i, j), j > i, of frame f  <=>  iou(cand_j, cand_i) > max_iou  (candidates in processing
-// order). Work unit = (frame, MROWS rows): the rows are staged in shared memory once and every thread walks them for
-// its own column, MCOLS columns per pass, starting at the diagonal; one ballot per row and warp is one mask word.
-// Persistent grid: units are dealt round-robin, so frames with few or no candidates cost nothing.
+// order). Layout: [frame][row block i/32][word j/32][i%32] — the 32 rows of a block are adjacent for one word, so this
+// kernel stores, and the sweep loads, whole 128-byte lines. Work unit = (frame, MROWS rows): the rows (and their areas)
+// are staged in shared memory once and every thread walks them for its own column, MCOLS columns per pass, starting at
+// the diagonal; one ballot per row and warp is one mask word, lane i%32 keeps the word of row i. Persistent grid: units
+// are dealt round-robin, frames without a published candidate list cost one shared-memory read.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MCOLS)
 nms_mask_kernel(PostBuffers pb, int K, int frames, float max_iou) {
     __shared__ float4 rows[MROWS];
+    __shared__ float rarea[MROWS];
+    __shared__ int s_n[MCOLS];
     const bool exact = !(max_iou >= 0.0f);
+    const float thr_hi = max_iou * 1.000001f, thr_lo = max_iou * 0.999999f;
     pdl_launch_dependents();
     pdl_wait();
+    if (*pb.any_big == 0) return;  // the usual case: no frame of this stage has that many candidates
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int W = pb.mask_pitch;
+    const int W = pb.mask_pitch, K32 = (K + 31) >> 5;
     long long unit0 = 0;  // global index of the frame's first unit
-    for (int f = 0; f < frames; ++f) {
-        const int n = pb.big_n[f];
-        if (n == 0) continue;
-        const int RT = (n + MROWS - 1) / MROWS;
-        const float4* sel = reinterpret_cast<const float4*>(pb.sel_boxes) + (size_t)f * K;
-        unsigned* mask = pb.mask + (size_t)f * K * W;
-        // first unit of this frame that is mine: u == blockIdx.x (mod gridDim.x)
-        int r = (int)(((long long)blockIdx.x - unit0 % gridDim.x + gridDim.x) % gridDim.x);
-        for (; r < RT; r += gridDim.x) {
-            const int row0 = r * MROWS;
-            const int nrows = min(MROWS, n - row0);
-            __syncthreads();
-            if (tid < nrows) rows[tid] = sel[row0 + tid];
-            __syncthreads();
-            for (int col0 = row0 / MCOLS * MCOLS; col0 < n; col0 += MCOLS) {
-                const int j = col0 + tid;
-                const bool valid = j < n;
-                const float4 b = valid ? sel[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const int word = (col0 >> 5) + warp;
-                if (word * 32 < n) {  // warp-uniform
-#pragma unroll 4
-                    for (int i = 0; i < nrows; ++i) {
-                        const bool pred = valid && j > row0 + i && iou_exceeds(b, rows[i], max_iou, exact);
-                        const unsigned bal = __ballot_sync(0xffffffffu, pred);
-                        if (lane == 0) mask[(size_t)(row0 + i) * W + word] = bal;
+    for (int f0 = 0; f0 < frames; f0 += MCOLS) {
+        __syncthreads();
+        s_n[tid] = f0 + tid < frames ? pb.big_n[f0 + tid] : 0;
+        __syncthreads();
+        for (int ff = 0; ff < MCOLS && f0 + ff < frames; ++ff) {
+            const int n = s_n[ff];
+            if (n == 0) continue;
+            const int f = f0 + ff;
+            const int RT = (n + MROWS - 1) / MROWS;
+            const float4* sel = reinterpret_cast<const float4*>(pb.sel_boxes) + (size_t)f * K;
+            unsigned* mask = pb.mask + (size_t)f * K32 * W * 32;
+            // first unit of this frame that is mine: unit0 + r == blockIdx.x (mod gridDim.x)
+            int r = (int)(((long long)blockIdx.x - unit0 % gridDim.x + gridDim.x) % gridDim.x);
+            for (; r < RT; r += gridDim.x) {
+                const int row0 = r * MROWS;
+                const int nrows = min(MROWS, n - row0);
+                __syncthreads();
+                if (tid < MROWS) {
+                    const float4 rb4 = tid < nrows ? sel[row0 + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rows[tid] = rb4;
+                    rarea[tid] = bbox_area(rb4.x, rb4.y, rb4.z, rb4.w);
+                }
+                __syncthreads();
+                for (int col0 = row0 / MCOLS * MCOLS; col0 < n; col0 += MCOLS) {
+                    const int j = col0 + tid;
+                    const bool valid = j < n;
+                    const float4 b = valid ? sel[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float barea = bbox_area(b.x, b.y, b.z, b.w);
+                    const int word = (col0 >> 5) + warp;
+                    if (word * 32 >= n) continue;  // warp-uniform
+#pragma unroll
+                    for (int h = 0; h < MROWS / 32; ++h) {
+                        const int rb = (row0 >> 5) + h;
+                        if (rb * 32 >= n || word < rb) continue;  // past the end / below the diagonal: never read
+                        unsigned keep = 0u;
+#pragma unroll 8
+                        for (int i = 0; i < 32; ++i) {
+                            const int ri = 32 * h + i;
+                            const bool hit = exact ? iou_exceeds(b, rows[ri], max_iou, true)
+                                                   : iou_exceeds_fast(b, barea, rows[ri], rarea[ri], max_iou, thr_hi, thr_lo);
+                            const bool pred = valid && j > row0 + ri && ri < nrows && hit;
+                            const unsigned bal = __ballot_sync(0xffffffffu, pred);
+                            if (lane == i) keep = bal;
+                        }
+                        mask[((size_t)rb * W + word) * 32 + lane] = keep;
                     }
                 }
             }
+            unit0 += RT;
         }
-        unit0 += RT;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// nms_sweep_kernel: one CTA per frame with a published candidate list. `removed` bitset in shared memory.
+// nms_sweep_kernel: one CTA per frame with a published candidate list; `removed` bitset in shared memory.
+// Two levels: a super-chunk of 256 candidates (8 words) is resolved by one warp from its 8x8-word diagonal block held
+// in shared memory — 32 candidates per step in registers (shuffles), survivors' rows folded into the super-chunk's
+// remaining words with a warp OR-reduction — then all warps push the survivors' rows into the words beyond the
+// super-chunk (whole lines, sixteen loads in flight per lane), so the serial chain per 256 candidates is one block
+// load, eight register-resident steps and one parallel push.
 // ---------------------------------------------------------------------------------------------
-constexpr int SWEEP_THR = 128;
+constexpr int SWEEP_THR = 512;
+constexpr int SWEEP_WARPS = SWEEP_THR / 32;
 
 __global__ void __launch_bounds__(SWEEP_THR)
 nms_sweep_kernel(const float* __restrict__ scores, PostBuffers pb, int K) {
     extern __shared__ unsigned removed[];  // mask_pitch words
-    __shared__ unsigned s_kept;
+    __shared__ unsigned blk[8][8][32];     // [row block q][word k][row in block]
+    __shared__ unsigned s_kept[8];
     pdl_launch_dependents();
     pdl_wait();
     const int f = blockIdx.x;
     const int n = pb.big_n[f];
+    if (f == 0 && threadIdx.x == 0) *pb.any_big = 0;  // consumed (nms_mask_kernel ran before this kernel)
     if (n == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int W = pb.mask_pitch;
+    const int W = pb.mask_pitch, K32 = (K + 31) >> 5;
     const int nw = (n + 31) >> 5;
-    const unsigned* mask = pb.mask + (size_t)f * K * W;
+    const unsigned* __restrict__ mask = pb.mask + (size_t)f * K32 * W * 32;
     const float4* sel = reinterpret_cast<const float4*>(pb.sel_boxes) + (size_t)f * K;
     const unsigned long long* keys = pb.sort_scratch + (size_t)f * pb.sort_cap;
     const float* sc = scores + (size_t)f * K * 2;
     float* dets = pb.dets + (size_t)f * K * 5;
     int* didx = pb.det_idx ? pb.det_idx + (size_t)f * K : nullptr;
     for (int w = tid; w < nw; w += SWEEP_THR) removed[w] = 0u;
-    __syncthreads();
-    int n_sel = 0;
-    for (int c = 0; c < nw; ++c) {
-        const int row = 32 * c + lane;
+    int n_sel = 0;  // tracked by warp 0
+    for (int word0 = 0; word0 < nw; word0 += 8) {
+        const int nq = min(8, nw - word0);  // row blocks (= words) of this super-chunk
+        __syncthreads();
+        // 1. diagonal super-block (upper triangle: word k >= row block q)
+        for (int p = warp; p < 64; p += SWEEP_WARPS) {
+            const int q = p >> 3, k = p & 7;
+            if (q < nq && k < nq && k >= q) blk[q][k][lane] = mask[((size_t)(word0 + q) * W + word0 + k) * 32 + lane];
+        }
+        __syncthreads();
+        // 2. eight serial steps of 32 candidates, warp 0
         if (warp == 0) {
-            // diagonal block: lane l holds the suppression word of candidate 32c + l against candidates 32c ..
-            const unsigned diag = row < n ? mask[(size_t)row * W + c] : 0u;
-            unsigned rem = removed[c];
-            if (32 * c + 32 > n) rem |= 0xffffffffu << (n - 32 * c);  // past the end: never kept
-            unsigned kept = 0u;
+            for (int q = 0; q < 8; ++q) {
+                unsigned kept = 0u;
+                if (q < nq) {
+                    const int row = 32 * (word0 + q) + lane;
+                    const bool in = row < n;
+                    // prefetch what the survivors will write (independent of the resolution below)
+                    const unsigned long long key = in ? keys[row] : 0ull;
+                    const float4 kb = in ? sel[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const unsigned diag = blk[q][q][lane];
+                    unsigned rem = removed[word0 + q];
+                    if (32 * (word0 + q) + 32 > n) rem |= 0xffffffffu << (n - 32 * (word0 + q));  // past the end: never kept
 #pragma unroll
-            for (int b = 0; b < 32; ++b) {
-                const unsigned d = __shfl_sync(0xffffffffu, diag, b);
-                if (!((rem >> b) & 1u)) { kept |= 1u << b; rem |= d; }
-            }
-            if (lane == 0) s_kept = kept;
-            if ((kept >> lane) & 1u) {
-                const int pos = n_sel + __popc(kept & ((1u << lane) - 1u));
-                const unsigned k = (unsigned)(keys[row] & 0xffffffffull);
-                const float4 kb = sel[row];
-                float* d = dets + (size_t)pos * 5;
-                d[0] = kb.x; d[1] = kb.y; d[2] = kb.z; d[3] = kb.w; d[4] = sc[2 * (size_t)k + 1];
-                if (didx) didx[pos] = (int)k;
+                    for (int b = 0; b < 32; ++b) {
+                        const unsigned d = __shfl_sync(0xffffffffu, diag, b);
+                        if (!((rem >> b) & 1u)) { kept |= 1u << b; rem |= d; }
+                    }
+                    const bool mine = (kept >> lane) & 1u;
+                    for (int k = q + 1; k < nq; ++k) {
+                        const unsigned r = __reduce_or_sync(0xffffffffu, mine ? blk[q][k][lane] : 0u);
+                        if (lane == 0) removed[word0 + k] |= r;
+                    }
+                    __syncwarp();
+                    if (mine) {
+                        const int pos = n_sel + __popc(kept & ((1u << lane) - 1u));
+                        const unsigned k = (unsigned)(key & 0xffffffffull);
+                        float* d = dets + (size_t)pos * 5;
+                        d[0] = kb.x; d[1] = kb.y; d[2] = kb.z; d[3] = kb.w; d[4] = sc[2 * (size_t)k + 1];
+                        if (didx) didx[pos] = (int)k;
+                    }
+                    n_sel += __popc(kept);
+                }
+                if (lane == 0) s_kept[q] = kept;
             }
         }
         __syncthreads();
-        const unsigned kept = s_kept;
-        n_sel += __popc(kept);
-        // rows of the survivors suppress later words: all (predicated) loads of a word are independent
-        for (int w = c + 1 + tid; w < nw; w += SWEEP_THR) {
-            const unsigned* col = mask + (size_t)(32 * c) * W + w;
-            unsigned acc = 0u;
+        // 3. push the survivors' rows into every word beyond the super-chunk: a warp owns a word, loads the line of each of
+        //    the 8 row blocks (two words per trip: sixteen loads in flight), ORs them per lane, reduces across the lanes
+        const int wfar = word0 + 8;
+        unsigned km[8];
 #pragma unroll
-            for (int b = 0; b < 32; ++b)
-                if ((kept >> b) & 1u) acc |= col[(size_t)b * W];
-            if (acc) removed[w] |= acc;
+        for (int q = 0; q < 8; ++q) km[q] = ((s_kept[q] >> lane) & 1u) ? 0xffffffffu : 0u;
+        for (int w = wfar + warp; w < nw; w += 2 * SWEEP_WARPS) {
+            const int w2 = w + SWEEP_WARPS;
+            const bool two = w2 < nw;
+            unsigned v[8], u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                v[q] = q < nq ? mask[((size_t)(word0 + q) * W + w) * 32 + lane] : 0u;
+                u[q] = (two && q < nq) ? mask[((size_t)(word0 + q) * W + w2) * 32 + lane] : 0u;
+            }
+            unsigned a = 0u, b2 = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { a |= v[q] & km[q]; b2 |= u[q] & km[q]; }
+            a = __reduce_or_sync(0xffffffffu, a);
+            b2 = __reduce_or_sync(0xffffffffu, b2);
+            if (lane == 0) {
+                if (a) removed[w] |= a;
+                if (two && b2) removed[w2] |= b2;
+            }
         }
-        __syncthreads();
     }
     if (tid == 0) pb.counts[f] = n_sel;
 }
@@ -437,12 +524,15 @@ size_t post_sort_scratch_elems(int K) {
 }
 
 int post_mask_pitch(int K) { return ((K + 31) / 32 + 3) / 4 * 4; }  // words per row, 16-byte multiple
-bool post_mask_supported(int K) { return K <= 32768; }             // sweep bitset <= 4 KB words, matrix <= 128 MB per frame
+size_t post_mask_words(int K) { return (size_t)((K + 31) / 32) * post_mask_pitch(K) * 32; }  // per frame
+bool post_mask_supported(int K) { return K <= 32768; }             // sweep bitset <= 4 KB, matrix <= 128 MB per frame
 
-void launch_nms_big(const float* scores, int K, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s) {
-    if (!pb.mask) return;
-    // the whole GPU, several CTAs per SM (the kernel is latency-bound on its shared-memory broadcasts)
-    launch_pdl(nms_mask_kernel, dim3(148 * 8), dim3(MCOLS), 0, s, pb, K, frames, max_iou);
+void launch_nms_mask(int K, float max_iou, const PostBuffers& pb, int frames, cudaStream_t s) {
+    // the whole GPU, as many CTAs as fit (the kernel is bound by issue and shared-memory broadcast latency)
+    launch_pdl(nms_mask_kernel, dim3(148 * 4), dim3(MCOLS), 0, s, pb, K, frames, max_iou);
+}
+
+void launch_nms_sweep(const float* scores, int K, const PostBuffers& pb, int frames, cudaStream_t s) {
     launch_pdl(nms_sweep_kernel, dim3(frames), dim3(SWEEP_THR), (size_t)pb.mask_pitch * sizeof(unsigned), s, scores, pb, K);
 }
 

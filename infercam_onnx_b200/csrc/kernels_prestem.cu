@@ -1,0 +1,172 @@
+// kernels_prestem.cu — K1 + K2 + K3 in one kernel for frames at exactly twice the network size (640x480 -> RFB-320,
+// 1280x960 -> RFB-640): `image::imageops::resize(.., Triangle)` (/root/reference/infer_server/src/nn.rs:74-80), the
+// normalisation + HWC->NCHW of nn.rs:82-91 and the first Conv of the graph (3x3 stride 2, 3 -> 16, + BN + ReLU;
+// nn.rs:181). The resized u8 frame and the normalised f32 tensor never exist in memory: a CTA reads the u8 source
+// tile, resamples it in packed integer arithmetic, normalises through the 3x256 LUT into shared memory and convolves.
+//
+// Bit-exactness of the resize (the u8 values the convolution sees are the ones the reference would have produced):
+// at exactly 2:1 every interior output has the taps 2o-1 .. 2o+2 with weights {1,3,3,1}/8, exact binary fractions, so
+// every product and partial sum of the reference's f32 arithmetic is exact and the result is the integer
+// (sum_ij w_i w_j p_ij + 32) >> 6 (see resize_half_exact_kernel in kernels_preproc.cu, which this kernel restates on
+// 2-D tiles). First / last output row and column have clamped, renormalised taps (not binary fractions): they are
+// recomputed in f32 from the tap tables in the reference's operation order. `dbg_resized` (parity hook) receives the
+// u8 values the kernel convolved.
+#include "kernels.h"
+#include "pdl.cuh"
+
+namespace uf {
+
+constexpr int PS_TX = 32, PS_TY = 8;                  // stem outputs per CTA (thread = one output pixel, 16 channels)
+constexpr int PS_RW = 2 * PS_TX + 1, PS_RH = 2 * PS_TY + 1;  // resized pixels under the tile (3x3 stride 2, pad 1)
+constexpr int PS_SCOLS = 4 * PS_TX + 8;               // source columns staged per row, aligned down to a multiple of 4
+constexpr int PS_SB = PS_SCOLS * 3;                   // bytes per staged source row (multiple of 4)
+constexpr int PS_WORDS = PS_SB / 4;
+constexpr int PS_HALF = PS_TX + 1;                    // resized columns per parity
+
+struct PrestemWeights {
+    float w[27 * 16];  // [ky][kx][ci][co]
+    float b[16];
+};
+
+__device__ __forceinline__ uint8_t prestem_px_f32(const uint8_t* __restrict__ sf, int sw, const ResizeTapsDev& t, int oy, int ox,
+                                                  int ch, int round_intermediate) {
+    const int vl = t.vleft[oy], vn = t.vn[oy], hl = t.hleft[ox], hn = t.hn[ox];
+    const float* vw = t.vw + (size_t)oy * t.vmax;
+    const float* hw = t.hw + (size_t)ox * t.hmax;
+    float acc = 0.f;
+    for (int j = 0; j < hn; ++j) {
+        float v = 0.f;
+        for (int i = 0; i < vn; ++i)
+            v = __fadd_rn(v, __fmul_rn((float)sf[((size_t)(vl + i) * sw + hl + j) * 3 + ch], vw[i]));
+        if (round_intermediate) v = roundf(fminf(fmaxf(v, 0.f), 255.f));
+        acc = __fadd_rn(acc, __fmul_rn(v, hw[j]));
+    }
+    acc = acc < 0.f ? 0.f : (acc > 255.f ? 255.f : acc);
+    return (uint8_t)roundf(acc);
+}
+
+__global__ void __launch_bounds__(PS_TX * PS_TY)
+resize2_stem_kernel(U8View src, const float* __restrict__ lut, ResizeTapsDev t, TView out, const __grid_constant__ PrestemWeights wts,
+                    int relu, int round_intermediate, uint8_t* __restrict__ dbg_resized) {
+    __shared__ __align__(16) uint16_t vt[PS_RH][PS_SB];          // vertical sums a + 3b + 3c + d per source byte column
+    __shared__ float s_in[3][PS_RH][2][PS_HALF];                 // normalised resized tile: [channel][row][column parity][column / 2]
+    __shared__ float s_lut[768];
+    pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 768; i += PS_TX * PS_TY) s_lut[i] = lut[i];  // static table: may be read before the wait
+    pdl_wait();
+    const int sw = src.W, sh = src.H, dw = sw >> 1, dh = sh >> 1;
+    const int ox0 = blockIdx.x * PS_TX, oy0 = blockIdx.y * PS_TY, n = blockIdx.z;
+    const int rx0 = 2 * ox0 - 1, ry0 = 2 * oy0 - 1;  // first resized column / row under the tile (may be -1: padding)
+    const int sx0 = 4 * ox0 - 4;                     // first staged source column (16-byte aligned in the row)
+    const uint8_t* sf = src.p + (size_t)n * src.frame_stride;
+    const int row_words = (sw * 3) >> 2;
+    const int word0 = (sx0 * 3) >> 2;                // may be negative at the left edge: clamped below
+
+    // 1. vertical pass, packed 16-bit lanes: item = (resized row, source word)
+    for (int it0 = tid; it0 < PS_RH * PS_WORDS; it0 += 4 * PS_TX * PS_TY) {
+        unsigned a[4], b[4], c[4], d[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int it = min(it0 + k * PS_TX * PS_TY, PS_RH * PS_WORDS - 1);
+            const int rl = it / PS_WORDS, wl = it - rl * PS_WORDS;
+            const int ry = min(max(ry0 + rl, 0), dh - 1);  // padding rows: any value, zeroed in pass 2
+            const int y0 = 2 * ry - 1;                       // clamped into the frame: only border outputs see the difference
+            const int wd = min(max(word0 + wl, 0), row_words - 1);
+            a[k] = __ldg(reinterpret_cast<const unsigned*>(sf + (size_t)max(y0, 0) * sw * 3) + wd);
+            b[k] = __ldg(reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 1) * sw * 3) + wd);
+            c[k] = __ldg(reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 2) * sw * 3) + wd);
+            d[k] = __ldg(reinterpret_cast<const unsigned*>(sf + (size_t)min(y0 + 3, sh - 1) * sw * 3) + wd);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int it = it0 + k * PS_TX * PS_TY;
+            if (it >= PS_RH * PS_WORDS) break;
+            const int rl = it / PS_WORDS, wl = it - rl * PS_WORDS;
+            // bytes 0,2 and bytes 1,3 as packed 16-bit lanes; sums stay below 2^11 (2^8 after the optional rounding)
+            unsigned e = (a[k] & 0x00ff00ffu) + (d[k] & 0x00ff00ffu) + 3u * ((b[k] & 0x00ff00ffu) + (c[k] & 0x00ff00ffu));
+            unsigned o = ((a[k] >> 8) & 0x00ff00ffu) + ((d[k] >> 8) & 0x00ff00ffu) +
+                         3u * (((b[k] >> 8) & 0x00ff00ffu) + ((c[k] >> 8) & 0x00ff00ffu));
+            if (round_intermediate) {
+                e = ((e + 0x00040004u) >> 3) & 0x00ff00ffu;
+                o = ((o + 0x00040004u) >> 3) & 0x00ff00ffu;
+            }
+            *reinterpret_cast<uint2*>(&vt[rl][4 * wl]) = make_uint2(__byte_perm(e, o, 0x5410), __byte_perm(e, o, 0x7632));
+        }
+    }
+    __syncthreads();
+
+    // 2. horizontal pass + normalise: item = (resized row, resized column); padding (outside the resized frame) = 0 in
+    //    normalised space, as in the ONNX Conv
+    const int sh6 = round_intermediate ? 3 : 6, half = round_intermediate ? 4 : 32;
+    uint8_t* dbg = dbg_resized ? dbg_resized + (size_t)n * dw * dh * 3 : nullptr;
+    for (int it = tid; it < PS_RH * PS_RW; it += PS_TX * PS_TY) {
+        const int rl = it / PS_RW, cl = it - rl * PS_RW;
+        const int rx = rx0 + cl, ry = ry0 + rl;
+        const bool inside = rx >= 0 && rx < dw && ry >= 0 && ry < dh;
+        const uint16_t* x = &vt[rl][6 * cl + 3];  // source column 2*rx - 1, relative to sx0
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const int s4 = (int)x[ch] + (int)x[9 + ch] + 3 * ((int)x[3 + ch] + (int)x[6 + ch]);
+            const int u = (s4 + half) >> sh6;
+            s_in[ch][rl][cl & 1][cl >> 1] = inside ? s_lut[ch * 256 + u] : 0.0f;
+            if (dbg && inside && cl >= 1 && rl >= 1) dbg[((size_t)ry * dw + rx) * 3 + ch] = (uint8_t)u;
+        }
+    }
+    // 3. border outputs of the resize in f32 from the tap tables (clamped, renormalised taps are not binary fractions)
+    const bool edge = ry0 <= 0 || ry0 + PS_RH >= dh || rx0 <= 0 || rx0 + PS_RW >= dw;  // CTA-uniform
+    if (edge) {
+        __syncthreads();
+        for (int it = tid; it < PS_RH * PS_RW * 3; it += PS_TX * PS_TY) {
+            const int ch = it % 3, p = it / 3;
+            const int rl = p / PS_RW, cl = p - rl * PS_RW;
+            const int rx = rx0 + cl, ry = ry0 + rl;
+            if (rx < 0 || rx >= dw || ry < 0 || ry >= dh) continue;
+            if (ry != 0 && ry != dh - 1 && rx != 0 && rx != dw - 1) continue;
+            const uint8_t u = prestem_px_f32(sf, sw, t, ry, rx, ch, round_intermediate);
+            s_in[ch][rl][cl & 1][cl >> 1] = s_lut[ch * 256 + u];
+            if (dbg && cl >= 1 && rl >= 1) dbg[((size_t)ry * dw + rx) * 3 + ch] = u;
+        }
+    }
+    __syncthreads();
+
+    // 4. the convolution: thread = output pixel, weights as constant-bank operands
+    const int tx = tid % PS_TX, ty = tid / PS_TX;
+    const int ox = ox0 + tx, oy = oy0 + ty;
+    if (ox >= out.W || oy >= out.H) return;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = wts.b[c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float v = s_in[ci][2 * ty + ky][kx & 1][tx + (kx >> 1)];
+#pragma unroll
+                for (int co = 0; co < 16; ++co) acc[co] = fmaf(v, wts.w[((ky * 3 + kx) * 3 + ci) * 16 + co], acc[co]);
+            }
+    float* op = out.p + (size_t)n * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 v = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        *reinterpret_cast<float4*>(op + q * 4) = v;
+    }
+}
+
+bool prestem_supported(const uint8_t* src, long long src_frame_stride, int sw, int sh, int net_w, int net_h, const ResizeTapsDev& t) {
+    return sw == 2 * net_w && sh == 2 * net_h && sw % 4 == 0 && net_w >= 4 && net_h >= 2 && (reinterpret_cast<size_t>(src) & 3) == 0 &&
+           src_frame_stride % 4 == 0 && t.vmax == 4 && t.hmax == 4;
+}
+
+// host_w: 27*16 weights [ky][kx][ci][co] followed by 16 biases, in HOST memory; src = frames at twice the network size
+void launch_prestem(const U8View& src, const float* lut, const ResizeTapsDev& t, const TView& out, const float* host_w, int relu,
+                    int round_intermediate, int frames, uint8_t* dbg_resized, cudaStream_t s) {
+    dim3 grid((out.W + PS_TX - 1) / PS_TX, (out.H + PS_TY - 1) / PS_TY, frames);
+    launch_pdl(resize2_stem_kernel, grid, dim3(PS_TX * PS_TY), 0, s, src, lut, t, out, *reinterpret_cast<const PrestemWeights*>(host_w),
+               relu, round_intermediate, dbg_resized);
+}
+
+}  // namespace uf

@@ -35,6 +35,17 @@
 
 namespace uf {
 
+// 3xTF32 split of an fp32 operand: hi = the value with its low 13 mantissa bits cut (what kind::tf32 reads from the raw
+// fp32 word, so hi is never materialised), lo = v - hi (exact, 13 significant bits) ROUNDED to tf32 precision: adding
+// half a tf32 ulp to the bit pattern turns the tensor core's truncation of lo into round-to-nearest. Truncating lo
+// instead loses up to 2^-20 |v| always towards zero — a bias that adds up linearly over K and through the layers
+// (measured: 10x the error of the fp32 SIMT path; with the rounding, ~2x).
+__device__ __forceinline__ float tf32_lo(float v) {
+    const float l = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    return __uint_as_float(__float_as_uint(l) + 0x1000u);
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
 // ---------------------------------------------------------------------------------------------
@@ -379,10 +390,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                         if (p.dw_relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
                     }
                     float4 l;
-                    l.x = acc.x - __uint_as_float(__float_as_uint(acc.x) & 0xffffe000u);
-                    l.y = acc.y - __uint_as_float(__float_as_uint(acc.y) & 0xffffe000u);
-                    l.z = acc.z - __uint_as_float(__float_as_uint(acc.z) & 0xffffe000u);
-                    l.w = acc.w - __uint_as_float(__float_as_uint(acc.w) & 0xffffe000u);
+                    l.x = tf32_lo(acc.x);
+                    l.y = tf32_lo(acc.y);
+                    l.z = tf32_lo(acc.z);
+                    l.w = tf32_lo(acc.w);
                     const int off = r * 128 + ((q ^ (r & 7)) << 4);
                     *reinterpret_cast<float4*>(a_hi + off) = acc;  // kind::tf32 ignores the low 13 mantissa bits: raw = hi
                     *reinterpret_cast<float4*>(a_lo + off) = l;
@@ -408,11 +419,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 for (int j = 0; j < TC_A_BYTES / 16 / 128; ++j) {
                     const int i = threadIdx.x + j * 128;
                     const float4 v = hi[i];
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                    float4 l;
+                    l.x = tf32_lo(v.x);
+                    l.y = tf32_lo(v.y);
+                    l.z = tf32_lo(v.z);
+                    l.w = tf32_lo(v.w);
                     // hi is not written back: kind::tf32 ignores the low 13 mantissa bits of its operands, i.e. the
                     // raw fp32 tile already *is* a_hi (checked by the 1e-4 layer-parity tests)
                     lo[i] = l;
@@ -910,10 +921,10 @@ fused_dwpw_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                 const int ch = sl * SQ + q;                 // 16-byte chunk of the pixel's C channels
                 const int off = (ch / (KC / 4)) * AKB + a_row + (((ch % (KC / 4)) ^ a_swz) << 4);
                 float4 l;
-                l.x = dq[q].x - __uint_as_float(__float_as_uint(dq[q].x) & 0xffffe000u);
-                l.y = dq[q].y - __uint_as_float(__float_as_uint(dq[q].y) & 0xffffe000u);
-                l.z = dq[q].z - __uint_as_float(__float_as_uint(dq[q].z) & 0xffffe000u);
-                l.w = dq[q].w - __uint_as_float(__float_as_uint(dq[q].w) & 0xffffe000u);
+                l.x = tf32_lo(dq[q].x);
+                l.y = tf32_lo(dq[q].y);
+                l.z = tf32_lo(dq[q].z);
+                l.w = tf32_lo(dq[q].w);
                 *reinterpret_cast<float4*>(a_hi + off) = dq[q];  // kind::tf32 ignores the low 13 mantissa bits: raw = hi
                 *reinterpret_cast<float4*>(a_lo + off) = l;
             }
@@ -1261,10 +1272,10 @@ dense3x3_tc_kernel(const __grid_constant__ Dense3Params p) {
             for (int u = 0; u < U; ++u) {
                 if (so[u] >= 0) {
                     float4 l;
-                    l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xffffe000u);
-                    l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xffffe000u);
-                    l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xffffe000u);
-                    l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xffffe000u);
+                    l.x = tf32_lo(v[u].x);
+                    l.y = tf32_lo(v[u].y);
+                    l.z = tf32_lo(v[u].z);
+                    l.w = tf32_lo(v[u].w);
                     *reinterpret_cast<float4*>(t_hi + so[u]) = v[u];  // kind::tf32 ignores the low 13 mantissa bits: raw = hi
                     *reinterpret_cast<float4*>(t_lo + so[u]) = l;
                 }

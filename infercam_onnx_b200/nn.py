@@ -175,6 +175,14 @@ class UltrafaceModel(InferModel):
                                                 out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def prestem_u8(self, frames: np.ndarray) -> np.ndarray:
+        """The resized u8 pixels as seen by the fused resize+normalise+stem kernel ([n, 2H, 2W, 3] -> [n, H, W, 3])."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape[:3]
+        out = np.empty((n, self.height, self.width, 3), np.uint8)
+        _check(_capi.load().uf_debug_prestem_u8(self._h, frames.ctypes.data_as(C.c_void_p), w, h, n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def preproc(self, input: np.ndarray) -> np.ndarray:  # noqa: A002
         """nn.rs:70-94 -> f32 [1,3,H,W]"""
         img = _as_rgb(input)

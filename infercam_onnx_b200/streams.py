@@ -7,14 +7,14 @@ repo is the benchmark's timing barrier / max-reduce (torch.distributed: NCCL on 
 """
 from __future__ import annotations
 
-import hashlib
 from typing import List, Sequence
 
 
 def stream_id(name: str) -> int:
-    """Stable 64-bit id of a stream name (the reference uses Rust's DefaultHasher, which is not stable across
-    builds; any fixed hash gives the same partitioning property)."""
-    return int.from_bytes(hashlib.blake2b(name.encode(), digest_size=8).digest(), "little")
+    """The reference's stream key `hashed(&id)` (lib.rs:39-46: DefaultHasher = SipHash-1-3 with zero keys), computed by
+    the library (uf_stream_hash) so that the Rust server, the Python mirror and the batcher's routing agree."""
+    from .batcher import stream_hash
+    return stream_hash(name)
 
 
 def owner(stream: int, world_size: int) -> int:

@@ -1,105 +1,212 @@
-"""Host logic of the stream batcher with a fake model — no GPU; plus one GPU test."""
+"""Stream batcher + stream -> GPU router behind the C ABI (csrc/batcher.cc).
+
+CPU tests drive the real C++ queueing / routing / ordering code with an injected backend (uf_batcher_create_ex, the
+seam `trait InferModel` is in the reference, nn.rs:24-26); the GPU tests run the product batcher (one handle per
+device) and check its results against the ORACLE."""
 import threading
 import time
 
 import numpy as np
 import pytest
 
-from infercam_onnx_b200.batcher import StreamBatcher
+from infercam_onnx_b200 import nn
+from infercam_onnx_b200.batcher import StreamBatcher, stream_hash
 
 
-class FakeModel:
-    """run_batch returns one detection per frame whose confidence encodes the frame's value."""
+def _frame(value, h=4, w=4):
+    f = np.zeros((h, w, 3), np.uint8)
+    f[0, 0, 0], f[0, 0, 1], f[0, 0, 2] = value & 255, (value >> 8) & 255, (value >> 16) & 255
+    return f
 
-    def __init__(self, delay=0.0):
-        self.batches = []
-        self.delay = delay
-        self.lock = threading.Lock()
 
-    def run_batch(self, frames, cap):
+def _value(f):
+    return int(f[0, 0, 0]) | int(f[0, 0, 1]) << 8 | int(f[0, 0, 2]) << 16
+
+
+class FakeBackend:
+    """One detection per frame whose confidence encodes the frame's value; uneven latency so batches finish out of order."""
+
+    def __init__(self, delay=0.0, gate=None):
+        self.batches, self.devices, self.delay, self.gate, self.lock = [], [], delay, gate, threading.Lock()
+
+    def __call__(self, device, frames):
+        if self.gate is not None:
+            self.gate.wait()
         with self.lock:
             self.batches.append(len(frames))
-        time.sleep(self.delay * (1 + (len(self.batches) % 2)))  # uneven latency: batches finish out of order
-        dets = [np.float32([[0, 0, 1, 1, float(f)]]) for f in frames]
-        return dets, [1] * len(frames)
+            self.devices.append(device)
+            k = len(self.batches)
+        time.sleep(self.delay * (1 + k % 2))
+        return [np.float32([[0, 0, 1, 1, float(_value(f))]]) for f in frames]
 
 
 def test_batches_respect_max_batch_and_keep_per_stream_order():
-    model = FakeModel(delay=0.002)
-    got = {}
-    lock = threading.Lock()
+    be = FakeBackend(delay=0.002)
+    got, lock = {}, threading.Lock()
 
     def on_result(stream, dets):
         with lock:
             got.setdefault(stream, []).append(dets[0][1])
-    b = StreamBatcher(model, max_batch=16, max_delay=0.001, capacity=10_000, workers=3)
+    b = StreamBatcher(backend=be, max_batch=16, max_delay=0.001, capacity=10_000, workers=3, max_frame_bytes=64)
     for i in range(400):
-        assert b.try_submit(i % 8, i, on_result)
+        assert b.try_submit(i % 8, _frame(i), on_result)
     b.close()
-    assert max(model.batches) <= 16 and sum(model.batches) == 400 and b.frames == 400
+    st = b.stats()
+    assert max(be.batches) <= 16 and sum(be.batches) == 400
+    assert st["submitted"] == st["completed"] == 400 and st["dropped"] == 0 and st["batches"] == len(be.batches)
     for s in range(8):
         assert got[s] == [float(i) for i in range(400) if i % 8 == s]  # submission order per stream
 
 
 def test_deadline_flushes_a_partial_batch():
-    model = FakeModel()
-    done = threading.Event()
-    b = StreamBatcher(model, max_batch=256, max_delay=0.01, workers=1)
+    be = FakeBackend()
+    b = StreamBatcher(backend=be, max_batch=256, max_delay=0.01, workers=1, max_frame_bytes=64)
     t0 = time.monotonic()
-    b.try_submit("cam", 7, lambda s, d: done.set())
-    assert done.wait(2.0) and time.monotonic() - t0 < 1.0  # a lone frame is not held back for a full batch
+    assert b.try_submit(7, _frame(7), tag=42)
+    res = b.poll(4, timeout=2.0)
+    assert time.monotonic() - t0 < 1.0  # a lone frame is not held back for a full batch
+    assert [(r["stream"], r["tag"], r["n_dets"], r["batch_size"]) for r in res] == [(7, 42, 1, 1)]
+    assert res[0]["dets"][0, 4] == 7.0
     b.close()
-    assert model.batches == [1]
+    assert be.batches == [1]
 
 
 def test_lossy_when_full_like_the_reference_channel():
     """router.rs:64-72: try_send_ref drops the frame when INFER_IMAGES_CHANNEL (capacity 10, lib.rs:37) is full."""
     gate = threading.Event()
-
-    class Blocked(FakeModel):
-        def run_batch(self, frames, cap):
-            gate.wait(5.0)
-            return super().run_batch(frames, cap)
-    model = Blocked()
-    b = StreamBatcher(model, max_batch=4, max_delay=0.0, capacity=10, workers=1)
-    accepted = sum(b.try_submit("cam", i, lambda s, d: None) for i in range(100))
-    assert accepted < 100 and b.dropped == 100 - accepted and accepted <= 10 + 4
+    be = FakeBackend(gate=gate)
+    b = StreamBatcher(backend=be, max_batch=4, max_delay=0.0005, capacity=10, workers=1, max_frame_bytes=64)
+    accepted = 0
+    for i in range(100):  # the worker takes one batch of <= 4 and blocks; 10 more queue up; the rest is dropped
+        accepted += b.try_submit(0, _frame(i))
+        time.sleep(0.0002)
+    assert 10 <= accepted <= 14
+    assert b.stats()["dropped"] == 100 - accepted
     gate.set()
+    b.flush()
+    vals = [int(r["dets"][0, 4]) for r in b.poll(256)]
+    assert len(vals) == accepted and vals == sorted(vals)  # what was accepted comes out, in order
     b.close()
-    assert b.frames == accepted
-    with pytest.raises(RuntimeError):
-        b.try_submit("cam", 0, lambda s, d: None)
 
 
-def test_failed_batch_skips_its_frames():
-    class Failing(FakeModel):
-        def run_batch(self, frames, cap):
-            if any(f < 0 for f in frames):
-                raise RuntimeError("bad frame")
-            return super().run_batch(frames, cap)
-    seen = []
-    b = StreamBatcher(Failing(), max_batch=1, max_delay=0.0, workers=1)
-    for v in (1, -1, 2):
-        b.try_submit("cam", v, lambda s, d: seen.append(d[0][1]))
+def test_streams_route_to_their_owner_device():
+    """device = devices[stream % n] (lib.rs:39-46 `hashed` is the stream key): a stream never changes device."""
+    be = FakeBackend()
+    b = StreamBatcher(backend=be, devices=(0, 1, 2), max_batch=8, max_delay=0.001, capacity=4096, workers=2, max_frame_bytes=64)
+    keys = [stream_hash("cam%d" % i) for i in range(32)]
+    for rep in range(4):
+        for k in keys:
+            assert b.try_submit(k, _frame(rep))
+    b.flush()
+    res = b.poll(1024)
+    assert len(res) == 128
+    for r in res:
+        assert r["device"] == r["stream"] % 3 == b.owner(r["stream"])
+    assert {r["device"] for r in res} == {0, 1, 2}
+    per_stream = {}
+    for r in res:
+        per_stream.setdefault(r["stream"], []).append(int(r["dets"][0, 4]))
+    assert all(v == [0, 1, 2, 3] for v in per_stream.values())
     b.close()
-    assert seen == [1.0, 2.0]  # inferer.rs:37 `if let Ok(..)`: the failed frame is skipped, the loop goes on
+
+
+def test_acquire_commit_abort_zero_copy_path():
+    be = FakeBackend()
+    b = StreamBatcher(backend=be, max_batch=4, max_delay=0.001, capacity=2, workers=1, max_frame_bytes=4 * 4 * 3)
+    view, t = b.acquire(5, 4, 4)
+    view[:] = _frame(1234)
+    b.commit(t, 4, 4, tag=9)
+    view2, t2 = b.acquire(5, 4, 4)
+    b.abort(t2)
+    with pytest.raises(nn.UltrafaceError):
+        b.commit(t2, 4, 4)  # not acquired any more
+    with pytest.raises(nn.UltrafaceError) as e:
+        b.acquire(5, 100, 100)  # larger than a slot
+    assert e.value.code == 7
+    b.flush()
+    (r,) = b.poll(8)
+    assert (r["tag"], int(r["dets"][0, 4])) == (9, 1234)
+    b.close()
+
+
+def test_failed_batches_skip_their_frames():
+    """inferer.rs:37 `if let Ok(..)`: a failing inference skips the frame, the loop goes on."""
+    calls = []
+
+    def flaky(device, frames):
+        calls.append(len(frames))
+        if len(calls) == 1:
+            raise RuntimeError("boom")
+        return [np.float32([[0, 0, 1, 1, 1.0]]) for _ in frames]
+    b = StreamBatcher(backend=flaky, max_batch=2, max_delay=0.02, capacity=64, workers=1, max_frame_bytes=64)
+    for i in range(6):
+        b.try_submit(0, _frame(i), tag=i)
+    b.flush()
+    res = b.poll(16)
+    assert [r["status"] for r in res] == [5, 5, 0, 0, 0, 0] and [r["tag"] for r in res] == list(range(6))
+    assert b.stats()["failed"] == 2
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_batcher_matches_oracle(make_onnx, test_pics):
+    """The product batcher (its own handle, pinned pool, batches in flight) against the ORACLE end to end."""
+    from oracle import hotpath
+    from oracle.ultraface_ref import UltrafaceOracle
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    oracle = UltrafaceOracle(path, 320, 240, 0.5, 0.5)
+    rng = np.random.default_rng(5)
+    frames = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(40)] + list(test_pics.values())
+    b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=16, max_delay=0.002, capacity=1024,
+                      workers=3, cap=256)
+    try:
+        for i, f in enumerate(frames):
+            assert b.try_submit(stream_hash("cam%d" % (i % 5)), f, tag=i)
+        b.flush()
+        res = {r["tag"]: r for r in b.poll(1024)}
+        assert len(res) == len(frames)
+        s_ref, b_ref = oracle.raw(frames)
+        flips = 0
+        for i in range(len(frames)):
+            ref, _ = hotpath.postproc(s_ref[i], b_ref[i], 0.5, 0.5)
+            got = res[i]["dets"]
+            assert res[i]["status"] == 0
+            if len(got) == len(ref):
+                np.testing.assert_allclose(got, ref, atol=1e-4)
+            else:
+                flips += 1  # a candidate within tolerance of a threshold (checked prior by prior in test_gpu_parity)
+        assert flips <= 2
+        st = b.stats()
+        assert st["completed"] == len(frames) and st["batches"] >= 3
+    finally:
+        b.close()
 
 
 @pytest.mark.gpu
-def test_batcher_with_the_real_model(make_onnx):
-    from infercam_onnx_b200 import nn
+def test_gpu_batcher_two_handles_route_by_stream(make_onnx):
+    """Two handles (here on the same device) owned by one batcher: frames go to devices[stream % 2]; identical frames give
+    identical results whichever handle ran them, and every stream stays in order."""
     path = make_onnx(320, 240, cls_bias=-0.75)
-    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=32, lanes=2)
+    rng = np.random.default_rng(6)
+    base = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(4)]
+    b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, devices=(0, 0), max_batch=8, max_delay=0.001,
+                      capacity=512, workers=2, cap=128)
     try:
-        rng = np.random.default_rng(5)
-        frames = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(6)]
-        expect = [m.run(f, cap=256) for f in frames]
-        got = {}
-        b = StreamBatcher(m, max_batch=32, max_delay=0.002, workers=2)
-        for i in range(120):
-            assert b.try_submit(i % 6, frames[i % 6], lambda s, d: got.setdefault(s, []).append(d))
-        b.close()
-        for s in range(6):
-            assert len(got[s]) == 20 and all(d == expect[s] for d in got[s])
+        n = 0
+        for rep in range(6):
+            for s in range(8):
+                assert b.try_submit(s, base[s % 4], tag=rep)
+                n += 1
+        b.flush()
+        res = b.poll(1024)
+        assert len(res) == n
+        seen = {}
+        for r in res:
+            seen.setdefault(r["stream"], []).append(r)
+        for s, rs in seen.items():
+            assert [r["tag"] for r in rs] == list(range(6))
+            for r in rs:
+                np.testing.assert_array_equal(r["dets"], seen[s % 4][0]["dets"])
     finally:
-        m.close()
+        b.close()

@@ -155,6 +155,53 @@ def test_resize_exact_half_integer_kernel(make_onnx):
             m.close()
 
 
+@pytest.mark.parametrize("net,round_intermediate", [((320, 240), False), ((640, 480), False), ((320, 240), True)])
+def test_fused_resize_stem_kernel_sees_the_reference_pixels(make_onnx, net, round_intermediate):
+    """Frames at exactly twice the network size never exist resized in memory: one kernel resamples (packed integer
+    arithmetic for the interior, f32 tap tables for the border row / column), normalises and convolves. Its debug output —
+    the u8 pixels it convolved — must equal the oracle's resize bit for bit, and the whole network must give exactly what
+    the two-kernel path (UF_FLAG_NO_PRESTEM) gives."""
+    w, h = net
+    path = make_onnx(w, h, cls_bias=-0.75)
+    kw = dict(onnx_path=path, size=net, max_batch=16, resize_round_intermediate=round_intermediate)
+    fused = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, **kw)
+    plain = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, flags=_capi.UF_FLAG_NO_PRESTEM, **kw)
+    try:
+        rng = np.random.default_rng(w)
+        shape = (2 * h, 2 * w)
+        ims = np.stack([rng.integers(0, 256, (*shape, 3), dtype=np.uint8),
+                        np.where(rng.random((*shape, 3)) < 0.5, 0, 255).astype(np.uint8),
+                        np.full((*shape, 3), 255, np.uint8), np.zeros((*shape, 3), np.uint8),
+                        _smooth(1, *shape, seed=2)[0], rng.integers(0, 256, (*shape, 3), dtype=np.uint8)])
+        got = fused.prestem_u8(ims)
+        for i, im in enumerate(ims):
+            np.testing.assert_array_equal(got[i], hotpath.resize_triangle(im, w, h, round_intermediate), err_msg=str(i))
+        for n in (1, len(ims)):  # single frame (latency path) and a batch
+            da, ca = fused.run_batch(list(ims[:n]), cap=512)
+            sa, ba = fused.raw_outputs(0, n)
+            db, cb = plain.run_batch(list(ims[:n]), cap=512)
+            sb, bb = plain.raw_outputs(0, n)
+            np.testing.assert_array_equal(sa, sb)
+            np.testing.assert_array_equal(ba, bb)
+            assert ca == cb
+        names = {s_["name"].split("[")[0] for s_ in _profile_one(fused, ims[0])}
+        assert "resize2x_norm_stem_u8" in names and "resize_triangle" not in names
+        names = {s_["name"].split("[")[0] for s_ in _profile_one(plain, ims[0])}
+        assert "resize_triangle" in names and "stem_3x3s2_u8" in names
+    finally:
+        fused.close()
+        plain.close()
+
+
+def _profile_one(m, frame):
+    m.profile_enable(True)
+    m.profile_reset()
+    m.run(frame)
+    stats = m.profile_read()
+    m.profile_enable(False)
+    return stats
+
+
 # ---------------------------------------------------------------------------------------------
 # R2: normalise + HWC->NCHW, bit-exact (both presets)
 # ---------------------------------------------------------------------------------------------
@@ -466,7 +513,7 @@ def test_postproc_edge_cases(model320):
 def test_batch_chunking_and_mixed_sizes_equal_single_frame(make_onnx, test_pics):
     path = make_onnx(320, 240, cls_bias=-0.75)
     single = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path)
-    batched = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=16, chunk=3, slots=2)
+    batched = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=24, chunk=3, slots=2)
     try:
         pics = [test_pics[k] for k in sorted(test_pics)]
         frames = [_noise(1, seed=i)[0] for i in range(5)] + pics + [_noise(1, 240, 320, seed=9)[0]] + pics[:2] + \
@@ -505,7 +552,7 @@ def test_failed_call_leaves_no_stale_results(make_onnx):
             f = np.ascontiguousarray(frames[5])
             rc = _capi.load().uf_infer(m._h, f.ctypes.data_as(_capi.C.c_void_p), 640, 480,
                                        out[1].ctypes.data_as(_capi.C.POINTER(_capi.uf_det)), 4,
-                                       _capi.C.byref(cnt, 4))
+                                       _capi.C.cast(_capi.C.addressof(cnt) + 4, _capi.C.POINTER(_capi.C.c_uint32)))
             assert rc == 0
             assert cnt[0] == 99 and cnt[2] == 99 and cnt[1] == gc[5]
             assert (out[0] == 7.0).all() and (out[2] == 7.0).all()
@@ -649,6 +696,6 @@ def test_profile_counters(model320):
     model320.profile_enable(False)
     assert model320.launch_count() - n0 == sum(s["launches"] for s in stats)
     names = {s["name"].split("[")[0] for s in stats}
-    assert {"resize_triangle", "stem_3x3s2_u8", "tail_post_softmax_decode_nms"} <= names
+    assert {"resize2x_norm_stem_u8", "tail_post_softmax_decode_nms"} <= names
     assert any(n.startswith("fused_dw3x3_pw1x1") for n in names) and "pointwise1x1_tcgen05" in names
     assert all(s["device_ms"] > 0 for s in stats)

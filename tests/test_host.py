@@ -246,3 +246,17 @@ def test_scale_after_residual_add_is_not_folded(tmp_path):
     with pytest.raises(nn.UltrafaceError) as e:
         nn.onnx_inspect(path, 320, 240)
     assert e.value.code == 4
+
+
+def test_rust_sys_crate_declares_every_header_symbol():
+    """rust/ultraface-sys cannot be compiled here (no cargo), so at least keep it complete against the header."""
+    header = open(os.path.join(ROOT, "include", "ultraface_b200.h")).read()
+    declared = set(re.findall(r"UF_API\s+[\w\s\*]+?\b(uf_\w+)\s*\(", header))
+    rust = open(os.path.join(ROOT, "rust", "ultraface-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (uf_\w+)\s*\(", rust))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    # struct field lists follow the header order
+    for struct, cls in (("uf_config", _capi.uf_config), ("uf_info", _capi.uf_info), ("uf_result", _capi.uf_result),
+                        ("uf_batcher_config", _capi.uf_batcher_config), ("uf_batcher_stats", _capi.uf_batcher_stats)):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % struct, rust, re.S).group(1)
+        assert re.findall(r"pub (\w+):", body) == [f for f, _ in cls._fields_], struct

@@ -33,6 +33,19 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mine = streams.shard_streams(1024, rank, world)
+    # every rank drives ITS streams through its own batcher (the C++ queue / router with an injected backend: no GPU here)
+    import numpy as np
+    from infercam_onnx_b200.batcher import StreamBatcher
+    b = StreamBatcher(backend=lambda dev, frames: [np.float32([[0, 0, 1, 1, float(f[0, 0, 0])]]) for f in frames],
+                      max_batch=64, max_delay=0.001, capacity=4096, workers=2, max_frame_bytes=64)
+    for s in mine:
+        f = np.zeros((2, 2, 3), np.uint8)
+        f[0, 0, 0] = s % 251
+        assert b.try_submit(s, f, tag=s)
+    b.flush()
+    res = b.poll(2048)
+    assert sorted(r["tag"] for r in res) == mine and all(r["dets"][0, 4] == r["stream"] % 251 for r in res)
+    b.close()
     seconds = 1.0 + rank  # rank 1 is the slow one
     fps = streams.aggregate_throughput(dist, len(mine), seconds)
     gathered = [None] * world
