@@ -183,6 +183,33 @@ UF_API int uf_onnx_inspect(const char* onnx_path, uint32_t net_w, uint32_t net_h
 UF_API int uf_resize_taps(uint32_t src_len, uint32_t dst_len, int32_t* left, int32_t* ntaps, float* w,
                           uint32_t w_pitch, uint32_t* max_taps);
 
+/* ==== JPEG in front of the path ================================================================
+ * Replaces `turbojpeg::decompress_image` (inferer.rs:35): frames arrive as baseline JPEG (what a V4L2 MJPG webcam sends,
+ * cam_sender/src/sensors.rs); Huffman decoding runs on host threads, dequantisation + inverse DCT + chroma upsampling +
+ * YCbCr->RGB on the GPU, bit-exact with libjpeg-turbo's default decoder (ISLOW IDCT, fancy upsampling), and the decoded
+ * frame goes straight into the resize. What crosses PCIe is the list of nonzero coefficients (4 bytes each + 4 bytes per
+ * 8x8 block), not 3 bytes per pixel. Baseline / extended-sequential Huffman, 8 bit, one interleaved scan, grey or YCbCr
+ * 4:4:4 / 4:2:2 / 4:2:0; anything else (progressive, arithmetic, CMYK ...) is UF_ERR_UNSUPPORTED. */
+typedef struct uf_jpeg_info {
+    uint32_t w, h, ncomp;
+    uint32_t hs[3], vs[3];      /* sampling factors */
+    uint32_t nblocks;           /* 8x8 blocks in decode (MCU-interleaved) order */
+    uint32_t nonzero;           /* nonzero coefficients (uf_jpeg_coefficients only) */
+    uint16_t quant[3][64];      /* per component, natural (row-major) order (uf_jpeg_coefficients only) */
+} uf_jpeg_info;
+/* jpeg[i] / len[i]: one JPEG file per frame. Otherwise as uf_infer_batch. */
+UF_API int uf_infer_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, uf_det* out, uint32_t cap,
+                               uint32_t* n_out);
+/* parity hook: the decoded RGB8 pixels of one frame, as the GPU kernels produce them (out_rgb: w * h * 3 bytes, cap_bytes
+ * its capacity; *w / *h are set even when the capacity is too small: UF_ERR_CAPACITY). */
+UF_API int uf_jpeg_decode_rgb(uf_model* m, const uint8_t* jpeg, size_t len, uint8_t* out_rgb, size_t cap_bytes, uint32_t* w,
+                              uint32_t* h);
+/* host only: headers. */
+UF_API int uf_jpeg_info_read(const uint8_t* jpeg, size_t len, uf_jpeg_info* out);
+/* host only: Huffman decoding alone. coefs (nullable) = nblocks x 64 quantised coefficients, blocks in decode order, natural
+ * order inside a block; cap_blocks = its capacity in blocks. */
+UF_API int uf_jpeg_coefficients(const uint8_t* jpeg, size_t len, uf_jpeg_info* info, int16_t* coefs, size_t cap_blocks);
+
 /* ==== stream batcher + stream -> GPU routing ==========================================
  * Replaces the loop of `Inferer::run` (inferer.rs:29-50: recv_ref -> model.run -> send) and the bounded LOSSY queue in
  * front of it (`INFER_IMAGES_CHANNEL`, capacity 10, lib.rs:32-37; the router fills it with `try_send_ref` and drops the

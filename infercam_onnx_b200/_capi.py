@@ -40,6 +40,11 @@ class uf_kernel_stat(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("compulsory_bytes", C.c_uint64), ("flops", C.c_uint64)]
 
 
+class uf_jpeg_info(C.Structure):
+    _fields_ = [("w", C.c_uint32), ("h", C.c_uint32), ("ncomp", C.c_uint32), ("hs", C.c_uint32 * 3), ("vs", C.c_uint32 * 3),
+                ("nblocks", C.c_uint32), ("nonzero", C.c_uint32), ("quant", (C.c_uint16 * 64) * 3)]
+
+
 class uf_batcher_config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("model", uf_config), ("devices", C.POINTER(C.c_int32)), ("n_devices", C.c_uint32),
                 ("max_batch", C.c_uint32), ("max_delay_us", C.c_uint32), ("capacity", C.c_uint32), ("workers", C.c_uint32),
@@ -91,6 +96,10 @@ SIGNATURES = {
     "uf_onnx_inspect": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t, _p(C.c_size_t)]),
     "uf_resize_taps": (C.c_int, [C.c_uint32, C.c_uint32, _p(C.c_int32), _p(C.c_int32), _p(C.c_float), C.c_uint32,
                                  _p(C.c_uint32)]),
+    "uf_infer_batch_jpeg": (C.c_int, [C.c_void_p, _p(C.c_void_p), _p(C.c_size_t), C.c_uint32, _p(uf_det), C.c_uint32, _p(C.c_uint32)]),
+    "uf_jpeg_decode_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _p(C.c_uint32), _p(C.c_uint32)]),
+    "uf_jpeg_info_read": (C.c_int, [C.c_void_p, C.c_size_t, _p(uf_jpeg_info)]),
+    "uf_jpeg_coefficients": (C.c_int, [C.c_void_p, C.c_size_t, _p(uf_jpeg_info), C.c_void_p, C.c_size_t]),
     "uf_batcher_create": (C.c_int, [_p(uf_batcher_config), _void_pp]),
     "uf_batcher_create_ex": (C.c_int, [_p(uf_batcher_config), uf_batch_fn, C.c_void_p, _void_pp]),
     "uf_batcher_destroy": (None, [C.c_void_p]),

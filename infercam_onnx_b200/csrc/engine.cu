@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +25,7 @@
 #include <vector>
 
 #include "../../include/ultraface_b200.h"
+#include "jpeg_decode.h"
 #include "kernels.h"
 #include "onnx_graph.h"
 #include "plan.h"
@@ -123,6 +127,12 @@ struct Slot {
     unsigned* d_mask = nullptr;  // NMS suppression bit matrix [chunk][K][pitch] (frames with many candidates)
     int* h_counts = nullptr;   // pinned [chunk]
     float* h_dets = nullptr;   // pinned [chunk][DET_FAST][5]
+    // N2: per-stage JPEG staging (pinned host side, device side), grown on demand
+    uint8_t* h_jpeg = nullptr;
+    uint8_t* d_jpeg = nullptr;
+    size_t jpeg_cap = 0;
+    uint8_t* d_planes = nullptr;
+    size_t planes_cap = 0;
     // pending work description
     bool pending = false;
     uint32_t first = 0, n = 0;
@@ -149,6 +159,74 @@ struct Lane {
     float *d_scores = nullptr, *d_boxes = nullptr;  // raw outputs of the lane's last batch [max_batch][K][2|4]
     uint32_t last_n = 0;
     uint64_t batch_id = 0;
+};
+
+// A few host threads for the per-frame serial work in front of the GPU (Huffman decoding): one job at a time, the
+// caller works too.
+class HostPool {
+public:
+    HostPool() {
+        unsigned n = std::thread::hardware_concurrency();
+        n = std::max(1u, std::min(n ? n - 1 : 1u, 31u));
+        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void parallel_for(uint32_t n, const std::function<void(uint32_t)>& fn) {
+        if (n == 0) return;
+        std::unique_lock<std::mutex> job(job_mu_);  // one parallel_for at a time
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; next_ = 0; done_ = 0; ++epoch_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return done_ == n_; });
+        fn_ = nullptr;
+    }
+
+private:
+    void work() {
+        for (;;) {
+            uint32_t i;
+            const std::function<void(uint32_t)>* fn;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= n_) return;
+                i = next_++;
+                fn = fn_;
+            }
+            (*fn)(i);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (++done_ == n_) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+                if (stop_) return;
+                seen = epoch_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, job_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(uint32_t)>* fn_ = nullptr;
+    uint32_t n_ = 0, next_ = 0, done_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
 };
 
 struct KernelStat {
@@ -189,6 +267,12 @@ struct uf_model {
     size_t d_hook_cap = 0;
     std::vector<uint8_t> tensor_readable;  // per plan tensor: materialised in the arena
     std::vector<TcWeights> tc_weights;
+    std::unique_ptr<HostPool> host_pool;  // Huffman decoding workers, created on first use
+    HostPool& pool() {
+        std::lock_guard<std::mutex> lk(aux_mu);
+        if (!host_pool) host_pool.reset(new HostPool());
+        return *host_pool;
+    }
     bool prestem_ok = false;     // first step is the 3 -> 16 stem kernel and UF_FLAG_NO_PRESTEM is not set
     std::string prestem_label;
 
@@ -949,8 +1033,9 @@ static void run_body(uf_model& m, Lane& ln, Slot& s, const U8View& input, uint32
 }
 
 struct FrameSrc {
-    const uint8_t* p;
+    const uint8_t* p;            // RGB8 pixels in host memory, or NULL when the frame arrives as JPEG coefficients
     uint32_t w, h;
+    const JpegCoefs* jc = nullptr;
 };
 
 // staging buffer for frames that need a resize; a failed re-allocation leaves the slot empty, not broken
@@ -962,6 +1047,75 @@ static void grow_input(Slot& s, size_t need) {
     s.d_in_cap = 0;
     CK(cudaMalloc(&s.d_in, need));
     s.d_in_cap = need;
+}
+
+// ---- N2: JPEG frames. Layout of a run in the stage's staging buffer (host pinned = device image):
+//   [JpegPlan x frames][block offsets of every frame][entries of every frame], each part 16-byte aligned
+static size_t jpeg_stage_bytes(const JpegCoefs& jc) {
+    return sizeof(JpegPlan) + (jc.block_off.size() + jc.entries.size()) * sizeof(uint32_t) + 64;
+}
+
+static void grow_jpeg(Slot& s, size_t need, size_t planes_need) {
+    if (need > s.jpeg_cap) {
+        CK(cudaStreamSynchronize(s.stream));
+        cudaFreeHost(s.h_jpeg); cudaFree(s.d_jpeg);
+        s.h_jpeg = s.d_jpeg = nullptr;
+        s.jpeg_cap = 0;
+        const size_t cap = need + need / 4;
+        CK(cudaMallocHost(&s.h_jpeg, cap));
+        CK(cudaMalloc(&s.d_jpeg, cap));
+        s.jpeg_cap = cap;
+    }
+    if (planes_need > s.planes_cap) {
+        CK(cudaStreamSynchronize(s.stream));
+        cudaFree(s.d_planes);
+        s.d_planes = nullptr;
+        s.planes_cap = 0;
+        CK(cudaMalloc(&s.d_planes, planes_need + planes_need / 4));
+        s.planes_cap = planes_need + planes_need / 4;
+    }
+}
+
+// `cnt` same-size JPEG frames -> RGB8 at dst (frame k at dst + k * w * h * 3): one H2D of plans + nonzero coefficients, then
+// dequantise + IDCT + upsample + colour on the device
+static void decode_jpeg_run(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t cnt, uint8_t* dst, size_t& jpeg_used, size_t& planes_used) {
+    auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+    size_t n_offs = 0, n_ent = 0;
+    for (uint32_t k = 0; k < cnt; ++k) { n_offs += fr[k].jc->block_off.size(); n_ent += fr[k].jc->entries.size(); }
+    const size_t base = a16(jpeg_used);
+    const size_t o_plans = base, o_offs = a16(o_plans + cnt * sizeof(JpegPlan)), o_ent = a16(o_offs + n_offs * 4), end = o_ent + n_ent * 4;
+    if (end > s.jpeg_cap) throw CudaError("internal: JPEG staging buffer undersized");
+    JpegPlan* plans = reinterpret_cast<JpegPlan*>(s.h_jpeg + o_plans);
+    uint32_t* offs = reinterpret_cast<uint32_t*>(s.h_jpeg + o_offs);
+    uint32_t* ent = reinterpret_cast<uint32_t*>(s.h_jpeg + o_ent);
+    size_t io = 0, ie = 0;
+    uint32_t max_blocks = 0;
+    const size_t fb = (size_t)fr[0].w * fr[0].h * 3;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const JpegCoefs& jc = *fr[k].jc;
+        JpegPlan p = jc.plan;
+        p.offs_base = (uint32_t)io;
+        p.entries_base = (uint32_t)ie;
+        const size_t ro = (size_t)k * fb, po = planes_used;
+        p.rgb_off_lo = (uint32_t)ro; p.rgb_off_hi = (uint32_t)(ro >> 32);
+        p.planes_off_lo = (uint32_t)po; p.planes_off_hi = (uint32_t)(po >> 32);
+        planes_used += p.plane_bytes;
+        plans[k] = p;
+        memcpy(offs + io, jc.block_off.data(), jc.block_off.size() * 4);
+        memcpy(ent + ie, jc.entries.data(), jc.entries.size() * 4);
+        io += jc.block_off.size();
+        ie += jc.entries.size();
+        max_blocks = std::max(max_blocks, p.nblocks);
+    }
+    if (planes_used > s.planes_cap) throw CudaError("internal: JPEG plane buffer undersized");
+    CK(cudaMemcpyAsync(s.d_jpeg + base, s.h_jpeg + base, end - base, cudaMemcpyHostToDevice, s.stream));
+    jpeg_used = end;
+    JpegBatchDev b{reinterpret_cast<const JpegPlan*>(s.d_jpeg + o_plans), reinterpret_cast<const uint32_t*>(s.d_jpeg + o_offs),
+                   reinterpret_cast<const uint32_t*>(s.d_jpeg + o_ent), s.d_planes, dst};
+    // SURVEY.md 8(d)-style accounting: coefficients in, planes written + read, RGB out
+    const uint64_t bytes = (uint64_t)(end - base) + 2ull * (planes_used) + (uint64_t)cnt * fb;
+    ProfScope ps(m, s, "jpeg_idct_upsample_rgb", bytes, (uint64_t)(end - base) + (uint64_t)cnt * fb, 0, 2);
+    launch_jpeg_decode(b, (int)cnt, max_blocks, fr[0].w, fr[0].h, s.stream);
 }
 
 // One chunk of host frames on slot s.
@@ -976,22 +1130,35 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
     // every frame of the stage at exactly twice the network size (the benchmark's 640x480 webcam frames into RFB-320): they
     // are only copied; the first kernel of the chain resamples, normalises and convolves them
     bool all_double = m.prestem_ok && n > 0 && (int)fr[0].w == 2 * W && (int)fr[0].h == 2 * H;
-    for (uint32_t k = 1; k < n && all_double; ++k) all_double = fr[k].w == fr[0].w && fr[k].h == fr[0].h;
+    for (uint32_t k = 1; k < n && all_double; ++k)
+        all_double = fr[k].w == fr[0].w && fr[k].h == fr[0].h && (fr[k].jc != nullptr) == (fr[0].jc != nullptr);
     if (all_double) {
         TapsRef t = get_taps(m, fr[0].w, fr[0].h);
         all_double = prestem_supported(s.d_in, (long long)fr[0].w * fr[0].h * 3, fr[0].w, fr[0].h, W, H, t->dev);
     }
+    // JPEG frames of the stage: size the staging buffers once (growing them mid-stage would strand copies in flight)
+    size_t jpeg_need = 0, planes_need = 0, jpeg_used = 0, planes_used = 0;
+    for (uint32_t k = 0; k < n; ++k)
+        if (fr[k].jc) {
+            jpeg_need += jpeg_stage_bytes(*fr[k].jc);
+            planes_need += fr[k].jc->plan.plane_bytes;
+        }
+    if (jpeg_need) grow_jpeg(s, jpeg_need, planes_need);
     size_t off = 0;
     uint32_t i = 0;
     while (i < n) {
         // run of frames with identical size (and, for the copy, contiguous host addresses)
         uint32_t j = i + 1;
         const size_t fb = (size_t)fr[i].w * fr[i].h * 3;
-        while (j < n && fr[j].w == fr[i].w && fr[j].h == fr[i].h) ++j;
+        while (j < n && fr[j].w == fr[i].w && fr[j].h == fr[i].h && (fr[j].jc != nullptr) == (fr[i].jc != nullptr)) ++j;
         const bool ident = (int)fr[i].w == W && (int)fr[i].h == H;
         if (!ident) off = (off + 15) / 16 * 16;  // keep every run 16-byte aligned for the fast resize path
         uint8_t* dst = ident ? s.d_resized + (size_t)i * out_frame : s.d_in + off;
         uint32_t a = i;
+        if (fr[i].jc) {  // JPEG: coefficients up, pixels made on the device (the runs of a stage share the staging buffer)
+            decode_jpeg_run(m, s, fr + i, j - i, dst, jpeg_used, planes_used);
+            a = j;
+        }
         while (a < j) {  // merge host-contiguous frames into one cudaMemcpyAsync
             uint32_t b = a + 1;
             while (b < j && fr[b].p == fr[b - 1].p + fb) ++b;
@@ -1185,6 +1352,7 @@ uf_model::~uf_model() {
         for (auto& g : s.graphs) cudaGraphExecDestroy(g.second);
         cudaFree(s.d_in); cudaFree(s.d_resized); cudaFree(s.d_arena); cudaFree(s.d_dets); cudaFree(s.d_sel);
         cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort); cudaFree(s.d_big_n); cudaFree(s.d_mask);
+        cudaFreeHost(s.h_jpeg); cudaFree(s.d_jpeg); cudaFree(s.d_planes);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_dets);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -1203,6 +1371,7 @@ static int guarded(F&& f) {
     } catch (const ArgError& e) { g_last_error = e.msg; return e.code;
     } catch (const IoError& e) { g_last_error = e.msg; return UF_ERR_IO;
     } catch (const UnsupportedError& e) { g_last_error = e.msg; return UF_ERR_UNSUPPORTED;
+    } catch (const JpegError& e) { g_last_error = e.msg; return e.code;
     } catch (const CudaError& e) { g_last_error = e.msg; cudaGetLastError(); return UF_ERR_CUDA;
     } catch (const std::bad_alloc&) { g_last_error = "out of host memory"; return UF_ERR_INVALID_ARG;
     } catch (const std::exception& e) { g_last_error = e.what(); return UF_ERR_ONNX; }
@@ -1270,6 +1439,65 @@ int uf_infer_batch(uf_model* m, const uint8_t* const* rgb, const uint32_t* w, co
         run_pipeline(*m, ln, n, m->host_chunk, true, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
             run_chunk_host(*m, ln, s, fr.data() + first, first, cnt);
         });
+    });
+}
+
+// Huffman decoding of n frames on the library's host worker threads (the only serial part of JPEG decoding)
+static void entropy_decode_all(uf_model& m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, std::vector<JpegCoefs>& out) {
+    out.resize(n);
+    std::vector<JpegError> errs(n, JpegError{UF_OK, ""});
+    m.pool().parallel_for(n, [&](uint32_t i) {
+        try {
+            jpeg_entropy_decode(jpeg[i], len[i], out[i]);
+        } catch (const JpegError& e) {
+            errs[i] = e;
+        } catch (const std::exception& e) {
+            errs[i] = JpegError{UF_ERR_INVALID_ARG, e.what()};
+        }
+    });
+    for (uint32_t i = 0; i < n; ++i)
+        if (errs[i].code != UF_OK) throw JpegError{errs[i].code, "frame " + std::to_string(i) + ": " + errs[i].msg};
+}
+
+int uf_infer_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, uf_det* out, uint32_t cap,
+                        uint32_t* n_out) {
+    return guarded([&] {
+        REQUIRE(m && (n == 0 || (jpeg && len)) && n_out, "null argument");
+        REQUIRE(cap == 0 || out, "out is NULL with cap > 0");
+        for (uint32_t i = 0; i < n; ++i) REQUIRE(jpeg[i] && len[i] >= 4, "bad frame " + std::to_string(i));
+        if (n > m->cfg.max_batch) throw ArgError(UF_ERR_CAPACITY, "batch of " + std::to_string(n) + " exceeds max_batch " + std::to_string(m->cfg.max_batch));
+        std::vector<JpegCoefs> coefs;
+        entropy_decode_all(*m, jpeg, len, n, coefs);
+        std::vector<FrameSrc> fr(n);
+        for (uint32_t i = 0; i < n; ++i) fr[i] = FrameSrc{nullptr, coefs[i].plan.w, coefs[i].plan.h, &coefs[i]};
+        LaneLock ll(*m, false);
+        Lane& ln = *ll.lane;
+        run_pipeline(*m, ln, n, m->host_chunk, true, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
+            run_chunk_host(*m, ln, s, fr.data() + first, first, cnt);
+        });
+    });
+}
+
+int uf_jpeg_decode_rgb(uf_model* m, const uint8_t* jpeg, size_t len, uint8_t* out_rgb, size_t cap_bytes, uint32_t* w, uint32_t* h) {
+    return guarded([&] {
+        REQUIRE(m && jpeg && w && h, "null argument");
+        JpegCoefs jc;
+        jpeg_entropy_decode(jpeg, len, jc);
+        *w = jc.plan.w;
+        *h = jc.plan.h;
+        const size_t fb = (size_t)jc.plan.w * jc.plan.h * 3;
+        if (!out_rgb || cap_bytes < fb) throw ArgError(UF_ERR_CAPACITY, "output buffer smaller than w * h * 3");
+        LaneLock ll(*m, true);
+        Slot& s = ll.lane->slots[0];
+        CK(cudaSetDevice(m->cfg.device));
+        grow_input(s, fb);
+        grow_jpeg(s, jpeg_stage_bytes(jc), jc.plan.plane_bytes);
+        FrameSrc fr{nullptr, jc.plan.w, jc.plan.h, &jc};
+        size_t ju = 0, pu = 0;
+        decode_jpeg_run(*m, s, &fr, 1, s.d_in, ju, pu);
+        CK(cudaMemcpyAsync(out_rgb, s.d_in, fb, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
     });
 }
 
@@ -1603,6 +1831,36 @@ int uf_onnx_inspect(const char* onnx_path, uint32_t net_w, uint32_t net_h, char*
             memcpy(out, j.data(), n);
             out[n] = 0;
         }
+    });
+}
+
+static void fill_jpeg_info(const JpegPlan& p, uf_jpeg_info* o) {
+    memset(o, 0, sizeof(*o));
+    o->w = p.w; o->h = p.h; o->ncomp = p.ncomp; o->nblocks = p.nblocks;
+    for (uint32_t c = 0; c < p.ncomp; ++c) { o->hs[c] = p.hs[c]; o->vs[c] = p.vs[c]; }
+}
+
+int uf_jpeg_info_read(const uint8_t* jpeg, size_t len, uf_jpeg_info* out) {
+    return guarded([&] {
+        REQUIRE(jpeg && out, "null argument");
+        fill_jpeg_info(jpeg_parse_header(jpeg, len), out);
+    });
+}
+
+int uf_jpeg_coefficients(const uint8_t* jpeg, size_t len, uf_jpeg_info* info, int16_t* coefs, size_t cap_blocks) {
+    return guarded([&] {
+        REQUIRE(jpeg && info, "null argument");
+        JpegCoefs jc;
+        jpeg_entropy_decode(jpeg, len, jc);
+        fill_jpeg_info(jc.plan, info);
+        info->nonzero = (uint32_t)jc.entries.size();
+        memcpy(info->quant, jc.plan.quant, sizeof(info->quant));
+        if (!coefs) return;
+        if (cap_blocks < jc.plan.nblocks) throw ArgError(UF_ERR_CAPACITY, "coefficient buffer smaller than nblocks");
+        memset(coefs, 0, (size_t)jc.plan.nblocks * 64 * sizeof(int16_t));
+        for (uint32_t b = 0; b < jc.plan.nblocks; ++b)
+            for (uint32_t e = jc.block_off[b]; e < jc.block_off[b + 1]; ++e)
+                coefs[(size_t)b * 64 + (jc.entries[e] >> 16)] = (int16_t)(jc.entries[e] & 0xffffu);
     });
 }
 

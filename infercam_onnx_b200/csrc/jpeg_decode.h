@@ -1,0 +1,64 @@
+// jpeg_decode.h — N2: JPEG in front of the hot path.
+//
+// The reference decodes every frame on the CPU with libjpeg-turbo before the path starts
+// (`turbojpeg::decompress_image`, /root/reference/infer_server/src/inferer.rs:35; README.md:62-64: ~15 ms per frame for
+// decode + encode). Here only the inherently serial part — Huffman decoding of the entropy-coded segment — stays on the
+// host (jpeg_entropy.cc, one frame per worker thread); it emits the quantised coefficients as a compact list of nonzeros,
+// which is what crosses PCIe (typically a third of the RGB bytes). Dequantisation, the inverse DCT, chroma upsampling and
+// YCbCr -> RGB run on the GPU (kernels_jpeg.cu) and restate libjpeg-turbo's DEFAULT decoder bit for bit: `jpeg_idct_islow`
+// (jidctint.c), `h2v1_fancy_upsample` / `h2v2_fancy_upsample` (jdsample.c) and `ycc_rgb_convert` (jdcolor.c), the
+// algorithms tjDecompress2 runs with flags = 0. Scope: baseline sequential JPEG (SOF0 / SOF1 Huffman, 8 bit), one
+// interleaved scan, 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 — what a V4L2 MJPG webcam sends (cam_sender/src/sensors.rs).
+// Progressive files are refused with UF_ERR_UNSUPPORTED.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace uf {
+
+constexpr int JPEG_MAX_SLOTS = 10;  // blocks per MCU (JPEG limit)
+
+// Geometry + tables of one frame: plain data, copied to the device as is.
+struct JpegPlan {
+    uint32_t w, h;                 // image size
+    uint32_t ncomp;                // 1 or 3
+    uint32_t hmax, vmax;           // largest sampling factors
+    uint32_t mcus_x, mcus_y;       // MCUs per row / column
+    uint32_t blocks_per_mcu;
+    uint32_t nblocks;              // mcus_x * mcus_y * blocks_per_mcu (decode order)
+    uint32_t hs[3], vs[3];         // sampling factors
+    uint32_t plane_w[3], plane_h[3];   // component planes padded to whole MCUs (samples)
+    uint32_t real_w[3], real_h[3];     // downsampled_width / height: ceil(w * hs / hmax) ...
+    uint32_t plane_off[3];         // byte offset of the plane inside the frame's plane buffer
+    uint32_t plane_bytes;          // all planes
+    uint32_t offs_base;            // index of this frame's first block offset in the batch's offset array
+    uint32_t entries_base;         // index of this frame's first entry in the batch's entry array
+    uint32_t rgb_off_lo, rgb_off_hi;   // byte offset of the decoded RGB frame in the destination buffer (64 bit)
+    uint32_t planes_off_lo, planes_off_hi;  // byte offset of the frame's planes in the batch's plane buffer
+    uint8_t slot_comp[JPEG_MAX_SLOTS], slot_h[JPEG_MAX_SLOTS], slot_v[JPEG_MAX_SLOTS];  // block slot in the MCU -> component, offsets
+    uint8_t pad_[2];
+    uint16_t quant[3][64];         // per component, NATURAL (row-major) order
+};
+
+// One frame after Huffman decoding. entry = (natural index << 16) | (uint16) quantised value.
+struct JpegCoefs {
+    JpegPlan plan{};
+    std::vector<uint32_t> block_off;  // nblocks + 1, offsets into `entries` (decode order)
+    std::vector<uint32_t> entries;
+};
+
+struct JpegError {
+    int code;  // uf_status
+    std::string msg;
+};
+
+// Parses the headers only. Throws JpegError.
+JpegPlan jpeg_parse_header(const uint8_t* data, size_t len);
+// Parses and Huffman-decodes. Throws JpegError (UF_ERR_UNSUPPORTED: progressive / arithmetic / 12 bit / multi-scan ...;
+// UF_ERR_INVALID_ARG: not a JPEG / truncated headers). A truncated or corrupt entropy segment decodes like libjpeg does:
+// missing data reads as zero bits.
+void jpeg_entropy_decode(const uint8_t* data, size_t len, JpegCoefs& out);
+
+}  // namespace uf

@@ -148,6 +148,17 @@ void launch_tail(const float* conf, const float* loc, long long conf_frame_strid
                  long long loc_frame_stride, const float* priors, int K, float center_var,
                  float size_var, float* scores, float* boxes, int frames, cudaStream_t s);
 
+// ---- N2: JPEG sample-domain decode (kernels_jpeg.cu): planes = scratch for the component planes, rgb = destination
+struct JpegPlan;
+struct JpegBatchDev {
+    const JpegPlan* plans;     // [frames]
+    const uint32_t* offs;      // block offsets of all frames (JpegPlan::offs_base)
+    const uint32_t* entries;   // (natural index << 16 | value) of all frames (JpegPlan::entries_base)
+    uint8_t* planes;           // JpegPlan::planes_off
+    uint8_t* rgb;              // JpegPlan::rgb_off
+};
+void launch_jpeg_decode(const JpegBatchDev& b, int frames, uint32_t max_nblocks, uint32_t max_w, uint32_t max_h, cudaStream_t s);
+
 // ---- K9-K11: threshold + sort + greedy NMS, one CTA per frame (nn.rs:109-140,198-260)
 struct PostBuffers {
     unsigned long long* sort_scratch;  // [frames][sort_cap] keys, used when candidates exceed smem

@@ -45,15 +45,18 @@ __device__ __forceinline__ uint8_t prestem_px_f32(const uint8_t* __restrict__ sf
     return (uint8_t)roundf(acc);
 }
 
-__global__ void __launch_bounds__(PS_TX * PS_TY)
+constexpr int PS_THREADS = 128;   // thread = output column x 2 output rows (ty, ty + PS_TY / 2): every weight fetched feeds 2 FFMAs
+constexpr int PS_WARPS = PS_THREADS / 32;
+
+__global__ void __launch_bounds__(PS_THREADS)
 resize2_stem_kernel(U8View src, const float* __restrict__ lut, ResizeTapsDev t, TView out, const __grid_constant__ PrestemWeights wts,
                     int relu, int round_intermediate, uint8_t* __restrict__ dbg_resized) {
     __shared__ __align__(16) uint16_t vt[PS_RH][PS_SB];          // vertical sums a + 3b + 3c + d per source byte column
     __shared__ float s_in[3][PS_RH][2][PS_HALF];                 // normalised resized tile: [channel][row][column parity][column / 2]
     __shared__ float s_lut[768];
     pdl_launch_dependents();
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 768; i += PS_TX * PS_TY) s_lut[i] = lut[i];  // static table: may be read before the wait
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 768; i += PS_THREADS) s_lut[i] = lut[i];  // static table: may be read before the wait
     pdl_wait();
     const int sw = src.W, sh = src.H, dw = sw >> 1, dh = sh >> 1;
     const int ox0 = blockIdx.x * PS_TX, oy0 = blockIdx.y * PS_TY, n = blockIdx.z;
@@ -62,27 +65,28 @@ resize2_stem_kernel(U8View src, const float* __restrict__ lut, ResizeTapsDev t, 
     const uint8_t* sf = src.p + (size_t)n * src.frame_stride;
     const int row_words = (sw * 3) >> 2;
     const int word0 = (sx0 * 3) >> 2;                // may be negative at the left edge: clamped below
+    const int row_bytes = sw * 3;
 
-    // 1. vertical pass, packed 16-bit lanes: item = (resized row, source word)
-    for (int it0 = tid; it0 < PS_RH * PS_WORDS; it0 += 4 * PS_TX * PS_TY) {
+    // 1. vertical pass, packed 16-bit lanes: warp = resized row (4 source row pointers set up once), lane = source word
+    int wofs[4];                                     // this lane's 4 word offsets in a source row, clamped into the row
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wofs[k] = min(max(word0 + lane + 32 * k, 0), row_words - 1);
+    for (int rl = warp; rl < PS_RH; rl += PS_WARPS) {
+        const int ry = min(max(ry0 + rl, 0), dh - 1);  // padding rows: any value, zeroed in pass 2
+        const int y0 = 2 * ry - 1;                       // clamped into the frame: only border outputs see the difference
+        const unsigned* p0 = reinterpret_cast<const unsigned*>(sf + (size_t)max(y0, 0) * row_bytes);
+        const unsigned* p1 = reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 1) * row_bytes);
+        const unsigned* p2 = reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 2) * row_bytes);
+        const unsigned* p3 = reinterpret_cast<const unsigned*>(sf + (size_t)min(y0 + 3, sh - 1) * row_bytes);
         unsigned a[4], b[4], c[4], d[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int it = min(it0 + k * PS_TX * PS_TY, PS_RH * PS_WORDS - 1);
-            const int rl = it / PS_WORDS, wl = it - rl * PS_WORDS;
-            const int ry = min(max(ry0 + rl, 0), dh - 1);  // padding rows: any value, zeroed in pass 2
-            const int y0 = 2 * ry - 1;                       // clamped into the frame: only border outputs see the difference
-            const int wd = min(max(word0 + wl, 0), row_words - 1);
-            a[k] = __ldg(reinterpret_cast<const unsigned*>(sf + (size_t)max(y0, 0) * sw * 3) + wd);
-            b[k] = __ldg(reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 1) * sw * 3) + wd);
-            c[k] = __ldg(reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 2) * sw * 3) + wd);
-            d[k] = __ldg(reinterpret_cast<const unsigned*>(sf + (size_t)min(y0 + 3, sh - 1) * sw * 3) + wd);
+            a[k] = __ldg(p0 + wofs[k]); b[k] = __ldg(p1 + wofs[k]); c[k] = __ldg(p2 + wofs[k]); d[k] = __ldg(p3 + wofs[k]);
         }
+        uint2* vrow = reinterpret_cast<uint2*>(&vt[rl][0]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int it = it0 + k * PS_TX * PS_TY;
-            if (it >= PS_RH * PS_WORDS) break;
-            const int rl = it / PS_WORDS, wl = it - rl * PS_WORDS;
+            if (lane + 32 * k >= PS_WORDS) break;
             // bytes 0,2 and bytes 1,3 as packed 16-bit lanes; sums stay below 2^11 (2^8 after the optional rounding)
             unsigned e = (a[k] & 0x00ff00ffu) + (d[k] & 0x00ff00ffu) + 3u * ((b[k] & 0x00ff00ffu) + (c[k] & 0x00ff00ffu));
             unsigned o = ((a[k] >> 8) & 0x00ff00ffu) + ((d[k] >> 8) & 0x00ff00ffu) +
@@ -91,38 +95,59 @@ resize2_stem_kernel(U8View src, const float* __restrict__ lut, ResizeTapsDev t, 
                 e = ((e + 0x00040004u) >> 3) & 0x00ff00ffu;
                 o = ((o + 0x00040004u) >> 3) & 0x00ff00ffu;
             }
-            *reinterpret_cast<uint2*>(&vt[rl][4 * wl]) = make_uint2(__byte_perm(e, o, 0x5410), __byte_perm(e, o, 0x7632));
+            vrow[lane + 32 * k] = make_uint2(__byte_perm(e, o, 0x5410), __byte_perm(e, o, 0x7632));  // u16 order: byte 0,1,2,3
         }
     }
     __syncthreads();
 
-    // 2. horizontal pass + normalise: item = (resized row, resized column); padding (outside the resized frame) = 0 in
-    //    normalised space, as in the ONNX Conv
+    // 2. horizontal pass + normalise: warp = resized row, lane = resized column (3 trips for the 65 columns); the 12 sums
+    //    of a pixel sit in 7 consecutive 32-bit words. Padding (outside the resized frame) = 0 in normalised space, as in
+    //    the ONNX Conv.
     const int sh6 = round_intermediate ? 3 : 6, half = round_intermediate ? 4 : 32;
     uint8_t* dbg = dbg_resized ? dbg_resized + (size_t)n * dw * dh * 3 : nullptr;
-    for (int it = tid; it < PS_RH * PS_RW; it += PS_TX * PS_TY) {
-        const int rl = it / PS_RW, cl = it - rl * PS_RW;
-        const int rx = rx0 + cl, ry = ry0 + rl;
-        const bool inside = rx >= 0 && rx < dw && ry >= 0 && ry < dh;
-        const uint16_t* x = &vt[rl][6 * cl + 3];  // source column 2*rx - 1, relative to sx0
+    for (int rl = warp; rl < PS_RH; rl += PS_WARPS) {
+        const int ry = ry0 + rl;
+        const bool row_in = ry >= 0 && ry < dh;
+        const unsigned* vw = reinterpret_cast<const unsigned*>(&vt[rl][0]);
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const int s4 = (int)x[ch] + (int)x[9 + ch] + 3 * ((int)x[3 + ch] + (int)x[6 + ch]);
-            const int u = (s4 + half) >> sh6;
-            s_in[ch][rl][cl & 1][cl >> 1] = inside ? s_lut[ch * 256 + u] : 0.0f;
-            if (dbg && inside && cl >= 1 && rl >= 1) dbg[((size_t)ry * dw + rx) * 3 + ch] = (uint8_t)u;
+        for (int trip = 0; trip < 3; ++trip) {
+            const int cl = lane + 32 * trip;
+            if (cl >= PS_RW) break;
+            const int rx = rx0 + cl;
+            const bool inside = row_in && rx >= 0 && rx < dw;
+            // u16 index 6 cl + 3 .. 6 cl + 14 (source columns 2 rx - 1 .. 2 rx + 2, three channels each)
+            const unsigned* x = vw + 3 * cl + 1;
+            const unsigned w0 = x[0], w1 = x[1], w2 = x[2], w3 = x[3], w4 = x[4], w5 = x[5], w6 = x[6];
+            const int r4 = (int)(w0 >> 16) + (int)(w5 & 0xffffu) + 3 * ((int)(w2 & 0xffffu) + (int)(w3 >> 16));
+            const int g4 = (int)(w1 & 0xffffu) + (int)(w5 >> 16) + 3 * ((int)(w2 >> 16) + (int)(w4 & 0xffffu));
+            const int b4 = (int)(w1 >> 16) + (int)(w6 & 0xffffu) + 3 * ((int)(w3 & 0xffffu) + (int)(w4 >> 16));
+            const int ur = (r4 + half) >> sh6, ug = (g4 + half) >> sh6, ub = (b4 + half) >> sh6;
+            float* dst = &s_in[0][rl][cl & 1][cl >> 1];
+            dst[0] = inside ? s_lut[ur] : 0.0f;
+            dst[PS_RH * 2 * PS_HALF] = inside ? s_lut[256 + ug] : 0.0f;
+            dst[2 * PS_RH * 2 * PS_HALF] = inside ? s_lut[512 + ub] : 0.0f;
+            if (dbg && inside && cl >= 1 && rl >= 1) {
+                uint8_t* q = dbg + ((size_t)ry * dw + rx) * 3;
+                q[0] = (uint8_t)ur; q[1] = (uint8_t)ug; q[2] = (uint8_t)ub;
+            }
         }
     }
-    // 3. border outputs of the resize in f32 from the tap tables (clamped, renormalised taps are not binary fractions)
+    // 3. border outputs of the resize in f32 from the tap tables (clamped, renormalised taps are not binary fractions):
+    //    resized rows 0 / dh - 1 and columns 0 / dw - 1 where the tile holds them
     const bool edge = ry0 <= 0 || ry0 + PS_RH >= dh || rx0 <= 0 || rx0 + PS_RW >= dw;  // CTA-uniform
     if (edge) {
         __syncthreads();
-        for (int it = tid; it < PS_RH * PS_RW * 3; it += PS_TX * PS_TY) {
-            const int ch = it % 3, p = it / 3;
-            const int rl = p / PS_RW, cl = p - rl * PS_RW;
+        const int br0 = 0 - ry0, br1 = dh - 1 - ry0;  // local rows of the two border rows (maybe outside the tile)
+        const int bc0 = 0 - rx0, bc1 = dw - 1 - rx0;
+        // items: [2 border rows x PS_RW columns] then [2 border columns x PS_RH rows], 3 channels each
+        for (int it = tid; it < (2 * PS_RW + 2 * PS_RH) * 3; it += PS_THREADS) {
+            const int ch = it % 3, q = it / 3;
+            int rl, cl;
+            if (q < 2 * PS_RW) { rl = q < PS_RW ? br0 : br1; cl = q < PS_RW ? q : q - PS_RW; }
+            else { const int q2 = q - 2 * PS_RW; cl = q2 < PS_RH ? bc0 : bc1; rl = q2 < PS_RH ? q2 : q2 - PS_RH; }
+            if (rl < 0 || rl >= PS_RH || cl < 0 || cl >= PS_RW) continue;
             const int rx = rx0 + cl, ry = ry0 + rl;
             if (rx < 0 || rx >= dw || ry < 0 || ry >= dh) continue;
-            if (ry != 0 && ry != dh - 1 && rx != 0 && rx != dw - 1) continue;
             const uint8_t u = prestem_px_f32(sf, sw, t, ry, rx, ch, round_intermediate);
             s_in[ch][rl][cl & 1][cl >> 1] = s_lut[ch * 256 + u];
             if (dbg && cl >= 1 && rl >= 1) dbg[((size_t)ry * dw + rx) * 3 + ch] = u;
@@ -130,29 +155,40 @@ resize2_stem_kernel(U8View src, const float* __restrict__ lut, ResizeTapsDev t, 
     }
     __syncthreads();
 
-    // 4. the convolution: thread = output pixel, weights as constant-bank operands
-    const int tx = tid % PS_TX, ty = tid / PS_TX;
-    const int ox = ox0 + tx, oy = oy0 + ty;
-    if (ox >= out.W || oy >= out.H) return;
-    float acc[16];
+    // 4. the convolution: thread = output column x rows (ty, ty + 4), weights as constant-bank operands shared by both
+    const int tx = lane, ty = warp;
+    const int ox = ox0 + tx;
+    if (ox >= out.W) return;
+    float acc0[16], acc1[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = wts.b[c];
+    for (int c = 0; c < 16; ++c) acc0[c] = acc1[c] = wts.b[c];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-                const float v = s_in[ci][2 * ty + ky][kx & 1][tx + (kx >> 1)];
+                const float v0 = s_in[ci][2 * ty + ky][kx & 1][tx + (kx >> 1)];
+                const float v1 = s_in[ci][2 * (ty + PS_TY / 2) + ky][kx & 1][tx + (kx >> 1)];
 #pragma unroll
-                for (int co = 0; co < 16; ++co) acc[co] = fmaf(v, wts.w[((ky * 3 + kx) * 3 + ci) * 16 + co], acc[co]);
+                for (int co = 0; co < 16; ++co) {
+                    const float wv = wts.w[((ky * 3 + kx) * 3 + ci) * 16 + co];
+                    acc0[co] = fmaf(v0, wv, acc0[co]);
+                    acc1[co] = fmaf(v1, wv, acc1[co]);
+                }
             }
-    float* op = out.p + (size_t)n * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float4 v = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        *reinterpret_cast<float4*>(op + q * 4) = v;
+    for (int half_i = 0; half_i < 2; ++half_i) {
+        const int oy = oy0 + ty + half_i * (PS_TY / 2);
+        if (oy >= out.H) continue;
+        const float* acc = half_i ? acc1 : acc0;
+        float* op = out.p + (size_t)n * out.frame_stride + ((size_t)oy * out.W + ox) * out.pix_stride;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4*>(op + q * 4) = v;
+        }
     }
 }
 
@@ -165,7 +201,7 @@ bool prestem_supported(const uint8_t* src, long long src_frame_stride, int sw, i
 void launch_prestem(const U8View& src, const float* lut, const ResizeTapsDev& t, const TView& out, const float* host_w, int relu,
                     int round_intermediate, int frames, uint8_t* dbg_resized, cudaStream_t s) {
     dim3 grid((out.W + PS_TX - 1) / PS_TX, (out.H + PS_TY - 1) / PS_TY, frames);
-    launch_pdl(resize2_stem_kernel, grid, dim3(PS_TX * PS_TY), 0, s, src, lut, t, out, *reinterpret_cast<const PrestemWeights*>(host_w),
+    launch_pdl(resize2_stem_kernel, grid, dim3(PS_THREADS), 0, s, src, lut, t, out, *reinterpret_cast<const PrestemWeights*>(host_w),
                relu, round_intermediate, dbg_resized);
 }
 

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import threading
 import json
 import os
 from typing import List, Optional, Sequence, Tuple
@@ -72,6 +73,7 @@ class UltrafaceModel(InferModel):
         self.info = info
         self.num_priors = int(info.num_priors)
         self.max_batch = int(info.max_batch)
+        self._tls = threading.local()
 
     @classmethod
     def new(cls, variant: UltrafaceVariant, max_iou: float, min_confidence: float, *, onnx_path: Optional[str] = None,
@@ -100,6 +102,9 @@ class UltrafaceModel(InferModel):
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
+            for buf in getattr(self._tls, "out", {}).values():  # this thread's pinned result arrays
+                buf.free()
+            self._tls = threading.local()
             _capi.load().uf_model_free(self._h)
             self._h = C.c_void_p()
 
@@ -143,11 +148,40 @@ class UltrafaceModel(InferModel):
         return self._run_batch_raw(
             lambda out, cnt: _capi.load().uf_infer_batch_device(self._h, C.c_void_p(device_ptr), w, h, n, out, cap, cnt), n, cap)
 
+    def run_batch_jpeg(self, jpegs: Sequence[bytes], cap: int = 256) -> List[np.ndarray]:
+        """N2: frames as baseline JPEG files (bytes); Huffman decoding on host threads, the rest on the GPU."""
+        n = len(jpegs)
+        bufs = [C.create_string_buffer(bytes(j), len(j)) for j in jpegs]
+        ptrs = (C.c_void_p * max(n, 1))(*[C.addressof(b) for b in bufs])
+        lens = (C.c_size_t * max(n, 1))(*[len(j) for j in jpegs])
+        return self._run_batch_raw(lambda out, cnt: _capi.load().uf_infer_batch_jpeg(self._h, ptrs, lens, n, out, cap, cnt), n, cap)
+
+    def jpeg_decode_rgb(self, jpeg: bytes) -> np.ndarray:
+        """Parity hook: the RGB8 pixels the GPU decode kernels produce for one JPEG file."""
+        info = jpeg_info(jpeg)
+        out = np.empty((info["h"], info["w"], 3), np.uint8)
+        w, h = C.c_uint32(), C.c_uint32()
+        buf = C.create_string_buffer(bytes(jpeg), len(jpeg))
+        _check(_capi.load().uf_jpeg_decode_rgb(self._h, buf, len(jpeg), out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(w), C.byref(h)))
+        return out
+
     def _run_batch_raw(self, call, n: int, cap: int) -> List[np.ndarray]:
-        out = np.zeros((max(n, 1), cap, 5), np.float32)
-        cnt = (C.c_uint32 * max(n, 1))()
-        _check(call(out.ctypes.data_as(C.POINTER(_capi.uf_det)), cnt))
-        return [out[i, : min(cnt[i], cap)].copy() for i in range(n)], [int(cnt[i]) for i in range(n)]
+        # result arrays live in pinned host memory, one set per calling thread and (n, cap), reused from call to call:
+        # the library writes detections beyond the first 128 of a frame with an asynchronous strided copy, which is only
+        # asynchronous (and fast) into pinned memory, and a 40 MB np.zeros per call would dominate an NMS-heavy batch
+        tl = self._tls
+        cache = getattr(tl, "out", None)
+        if cache is None:
+            cache = tl.out = {}
+        key = (max(n, 1), cap)
+        if key not in cache:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache))).free()
+            cache[key] = _PinnedResults(*key)
+        buf = cache[key]
+        _check(call(buf.dets.ctypes.data_as(C.POINTER(_capi.uf_det)), buf.counts_p))
+        cnt = buf.counts
+        return [buf.dets[i, : min(int(cnt[i]), cap)].copy() for i in range(n)], [int(cnt[i]) for i in range(n)]
 
     # ---- parity hooks
     def raw_outputs(self, first: int, n: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -277,6 +311,28 @@ def onnx_inspect(path: str, width: int, height: int) -> dict:
     return json.loads(buf.value.decode())
 
 
+def jpeg_info(jpeg: bytes) -> dict:
+    """Host-only: size / components / sampling factors from the JPEG headers."""
+    info = _capi.uf_jpeg_info()
+    buf = C.create_string_buffer(bytes(jpeg), len(jpeg))
+    _check(_capi.load().uf_jpeg_info_read(buf, len(jpeg), C.byref(info)))
+    nc = int(info.ncomp)
+    return dict(w=int(info.w), h=int(info.h), ncomp=nc, hs=list(info.hs)[:nc], vs=list(info.vs)[:nc], nblocks=int(info.nblocks))
+
+
+def jpeg_coefficients(jpeg: bytes):
+    """Host-only: Huffman decoding alone -> (info dict incl. quant [ncomp,64] and the nonzero count, coefs [nblocks,64] int16;
+    blocks in decode (MCU-interleaved) order, natural order inside a block)."""
+    d = jpeg_info(jpeg)
+    info = _capi.uf_jpeg_info()
+    coefs = np.zeros((d["nblocks"], 64), np.int16)
+    buf = C.create_string_buffer(bytes(jpeg), len(jpeg))
+    _check(_capi.load().uf_jpeg_coefficients(buf, len(jpeg), C.byref(info), coefs.ctypes.data_as(C.c_void_p), d["nblocks"]))
+    d["nonzero"] = int(info.nonzero)
+    d["quant"] = np.ctypeslib.as_array(info.quant).reshape(3, 64)[: d["ncomp"]].copy()
+    return d, coefs
+
+
 def resize_taps(src_len: int, dst_len: int):
     """Host-only: (left, ntaps, w[dst, max_taps]) of one resize axis as the GPU kernel will use them."""
     lib = _capi.load()
@@ -295,6 +351,25 @@ def device_count() -> int:
     n = C.c_int32()
     _check(_capi.load().uf_device_count(C.byref(n)))
     return int(n.value)
+
+
+class _PinnedResults:
+    """[n, cap, 5] f32 detections + [n] u32 counts in pinned host memory."""
+
+    def __init__(self, n: int, cap: int):
+        self.nbytes = n * cap * 20 + n * 4
+        p = C.c_void_p()
+        _check(_capi.load().uf_host_alloc(self.nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.dets = np.ctypeslib.as_array((C.c_float * (n * cap * 5)).from_address(self.ptr)).reshape(n, cap, 5)
+        self.counts = np.ctypeslib.as_array((C.c_uint32 * n).from_address(self.ptr + n * cap * 20))
+        self.counts_p = C.cast(self.ptr + n * cap * 20, C.POINTER(C.c_uint32))
+
+    def free(self) -> None:
+        if self.ptr:
+            self.dets = self.counts = None
+            _capi.load().uf_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
 
 
 class PinnedFrames:

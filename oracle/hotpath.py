@@ -14,8 +14,8 @@ _LIB = None
 def build() -> str:
     """Compile liboracle.so with the committed Makefile (building the checker is not using it)."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "hotpath_oracle.c")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("hotpath_oracle.c", "jpeg_oracle.c", "Makefile")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 

@@ -86,6 +86,19 @@ pub struct uf_kernel_stat {
 
 #[repr(C)]
 #[derive(Clone, Copy)]
+pub struct uf_jpeg_info {
+    pub w: u32,
+    pub h: u32,
+    pub ncomp: u32,
+    pub hs: [u32; 3],
+    pub vs: [u32; 3],
+    pub nblocks: u32,
+    pub nonzero: u32,
+    pub quant: [[u16; 64]; 3],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
 pub struct uf_batcher_config {
     pub struct_size: u32,
     pub model: uf_config,
@@ -172,6 +185,13 @@ extern "C" {
     pub fn uf_onnx_inspect(onnx_path: *const c_char, net_w: u32, net_h: u32, out: *mut c_char, cap: usize, needed: *mut usize) -> c_int;
     pub fn uf_resize_taps(src_len: u32, dst_len: u32, left: *mut i32, ntaps: *mut i32, w: *mut f32, w_pitch: u32,
                           max_taps: *mut u32) -> c_int;
+    // JPEG in front of the path (N2)
+    pub fn uf_infer_batch_jpeg(m: *mut uf_model, jpeg: *const *const u8, len: *const usize, n: u32, out: *mut uf_det, cap: u32,
+                               n_out: *mut u32) -> c_int;
+    pub fn uf_jpeg_decode_rgb(m: *mut uf_model, jpeg: *const u8, len: usize, out_rgb: *mut u8, cap_bytes: usize, w: *mut u32,
+                              h: *mut u32) -> c_int;
+    pub fn uf_jpeg_info_read(jpeg: *const u8, len: usize, out: *mut uf_jpeg_info) -> c_int;
+    pub fn uf_jpeg_coefficients(jpeg: *const u8, len: usize, info: *mut uf_jpeg_info, coefs: *mut i16, cap_blocks: usize) -> c_int;
     // stream batcher + router
     pub fn uf_batcher_create(cfg: *const uf_batcher_config, out: *mut *mut uf_batcher) -> c_int;
     pub fn uf_batcher_create_ex(cfg: *const uf_batcher_config, f: uf_batch_fn, user: *mut c_void, out: *mut *mut uf_batcher) -> c_int;

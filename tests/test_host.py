@@ -257,6 +257,7 @@ def test_rust_sys_crate_declares_every_header_symbol():
     assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
     # struct field lists follow the header order
     for struct, cls in (("uf_config", _capi.uf_config), ("uf_info", _capi.uf_info), ("uf_result", _capi.uf_result),
-                        ("uf_batcher_config", _capi.uf_batcher_config), ("uf_batcher_stats", _capi.uf_batcher_stats)):
+                        ("uf_batcher_config", _capi.uf_batcher_config), ("uf_batcher_stats", _capi.uf_batcher_stats),
+                        ("uf_jpeg_info", _capi.uf_jpeg_info)):
         body = re.search(r"pub struct %s \{(.*?)\n\}" % struct, rust, re.S).group(1)
         assert re.findall(r"pub (\w+):", body) == [f for f, _ in cls._fields_], struct
