@@ -137,7 +137,7 @@ def smooth_frames(n, seed):
 
 def batcher_leg(nn, path, w, h, local, rank, world, frames, steps, barrier, max_over_ranks):
     """e2e through the C-ABI stream batcher (uf_batcher_*): this rank's shard of 1 024 logical streams
-    (streams.shard_streams: stream s -> rank s % world), frames copied into the batcher's pinned pool by 4 producer threads
+    (streams.shard_streams: stream s -> rank s % world), frames copied into the batcher's pinned pool by 8 producer threads
     (the ingest side's job), results polled by the main thread. Returns (frames/s, stats)."""
     import threading
     import torch
@@ -148,7 +148,7 @@ def batcher_leg(nn, path, w, h, local, rank, world, frames, steps, barrier, max_
     b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, size=(w, h), devices=(local,), max_batch=128,
                       max_delay=0.002, capacity=4 * B, workers=3, cap=64, max_frame_bytes=SRC_W * SRC_H * 3)
     total = B * steps
-    n_prod = 4
+    n_prod = 8
 
     def produce(k, count, base):
         i = 0
@@ -487,7 +487,7 @@ def main():
         done, dt_b, st = batcher_leg(nn, path, w, h, local, rank, world, frames, args.steps, barrier, max_over_ranks)
         extra["batcher"] = {"value": done * world / dt_b, "unit": "frames/s",
                             "api": "uf_batcher_try_submit / uf_batcher_poll (C ABI): 1024 logical streams sharded s % n_gpus "
-                                   "(streams.shard_streams), 4 producer threads copy frames into the owner GPU's pinned pool, "
+                                   "(streams.shard_streams), 8 producer threads copy frames into the owner GPU's pinned pool, "
                                    "batches of <= 128 formed on a 2 ms deadline, 3 in flight",
                             "batches": st["batches"], "mean_batch": st["completed"] / max(1, st["batches"]), "dropped_then_retried": st["dropped"]}
         dt_j, jpeg_b, coef_b, out_j = jpeg_leg(nn, model, args.steps, barrier, max_over_ranks, B, cap)

@@ -265,6 +265,15 @@ UF_API int uf_batcher_commit(uf_batcher* b, uint64_t ticket, uint32_t w, uint32_
 UF_API int uf_batcher_abort(uf_batcher* b, uint64_t ticket);
 UF_API int uf_batcher_try_submit(uf_batcher* b, uint64_t stream, const uint8_t* rgb, uint32_t w, uint32_t h,
                                  uint64_t user_tag, int32_t* accepted);
+/* The same for frames that arrive as JPEG files (N2; what `FrameMsg.data` holds, common/src/protocol.rs:15-19): the slot
+ * receives the file's bytes, the worker sends the batch through uf_infer_batch_jpeg. RGB and JPEG frames may be mixed. */
+UF_API int uf_batcher_commit_jpeg(uf_batcher* b, uint64_t ticket, size_t jpeg_len, uint64_t user_tag);
+UF_API int uf_batcher_try_submit_jpeg(uf_batcher* b, uint64_t stream, const uint8_t* jpeg, size_t len, uint64_t user_tag,
+                                      int32_t* accepted);
+/* The whole ingest step for one length-delimited data-socket frame (data_socket.rs:34-47 -> router.rs:56-72): parse the
+ * bincode ProtoMsg, key the stream with hashed(&id), and — for a FrameMsg — queue its JPEG payload on the GPU that owns the
+ * stream. *stream (nullable) receives the key; a ConnectReq is accepted = 0 with UF_OK. */
+UF_API int uf_batcher_ingest(uf_batcher* b, const uint8_t* msg, size_t len, uint64_t user_tag, int32_t* accepted, uint64_t* stream);
 /* Up to cap finished frames: res[i] + dets[i * det_cap ..]. Waits at most timeout_ms for the first one. */
 UF_API int uf_batcher_poll(uf_batcher* b, uf_result* res, uf_det* dets, uint32_t cap, uint32_t timeout_ms, uint32_t* n_out);
 UF_API int uf_batcher_flush(uf_batcher* b, uint32_t timeout_ms); /* returns when everything committed so far is pollable */

@@ -107,6 +107,9 @@ SIGNATURES = {
     "uf_batcher_commit": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]),
     "uf_batcher_abort": (C.c_int, [C.c_void_p, C.c_uint64]),
     "uf_batcher_try_submit": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, _p(C.c_int32)]),
+    "uf_batcher_commit_jpeg": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, C.c_uint64]),
+    "uf_batcher_try_submit_jpeg": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_uint64, _p(C.c_int32)]),
+    "uf_batcher_ingest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, _p(C.c_int32), _p(C.c_uint64)]),
     "uf_batcher_poll": (C.c_int, [C.c_void_p, _p(uf_result), _p(uf_det), C.c_uint32, C.c_uint32, _p(C.c_uint32)]),
     "uf_batcher_flush": (C.c_int, [C.c_void_p, C.c_uint32]),
     "uf_batcher_stats_read": (C.c_int, [C.c_void_p, _p(uf_batcher_stats)]),

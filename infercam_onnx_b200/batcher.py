@@ -114,6 +114,21 @@ class StreamBatcher:
                 self._callbacks.pop(tag, None)
         return bool(ok.value)
 
+    def try_submit_jpeg(self, stream: int, jpeg: bytes, tag: int = 0) -> bool:
+        """A frame as a baseline JPEG file (N2): decoded on the way (Huffman on the host, the rest on the GPU)."""
+        ok = C.c_int32()
+        buf = C.create_string_buffer(bytes(jpeg), len(jpeg))
+        _check(_capi.load().uf_batcher_try_submit_jpeg(self._h, stream, buf, len(jpeg), tag, C.byref(ok)))
+        return bool(ok.value)
+
+    def ingest(self, msg: bytes, tag: int = 0) -> Tuple[bool, int]:
+        """One length-delimited data-socket frame (bincode ProtoMsg): parse, key the stream with hashed(&id), queue the JPEG
+        payload on the owner GPU. Returns (accepted, stream key)."""
+        ok, key = C.c_int32(), C.c_uint64()
+        buf = C.create_string_buffer(bytes(msg), len(msg))
+        _check(_capi.load().uf_batcher_ingest(self._h, buf, len(msg), tag, C.byref(ok), C.byref(key)))
+        return bool(ok.value), int(key.value)
+
     def acquire(self, stream: int, h: int, w: int):
         """Zero-copy producer (N4): a [h,w,3] view of a pinned slot in the owner GPU's pool + its ticket, or (None, 0) if dropped."""
         buf, ticket = C.c_void_p(), C.c_uint64()

@@ -8,6 +8,7 @@
 // batches go through the same entry point an external caller would use (uf_infer_batch).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -34,6 +35,7 @@ struct Ticket {            // one pinned slot
     uint8_t* buf = nullptr;
     uint64_t stream = 0, tag = 0;
     uint32_t w = 0, h = 0;
+    size_t jpeg_len = 0;   // > 0: the slot holds a JPEG file of that many bytes, not RGB8 pixels (N2)
     Clock::time_point t_commit;
     int state = 0;         // 0 free, 1 acquired, 2 queued, 3 in a batch
 };
@@ -86,6 +88,7 @@ void worker_loop(uf_batcher* b, Device* d) {
     std::vector<uint32_t> take;
     std::vector<const uint8_t*> ptrs;
     std::vector<uint32_t> ws, hs, counts;
+    std::vector<size_t> lens;
     std::vector<uf_det> dets;
     if (!b->backend) cudaSetDevice(d->ordinal);
     for (;;) {
@@ -107,20 +110,33 @@ void worker_loop(uf_batcher* b, Device* d) {
             seq = d->next_batch++;
         }
         const uint32_t n = (uint32_t)take.size();
+        // RGB frames first, JPEG frames after them (stable), so that each kind goes through its own batched entry point;
+        // results are published per frame, so the order inside the batch does not matter
+        std::stable_partition(take.begin(), take.end(), [&](uint32_t s) { return d->slots[s].jpeg_len == 0; });
+        uint32_t n_rgb = 0;
+        while (n_rgb < n && d->slots[take[n_rgb]].jpeg_len == 0) ++n_rgb;
         ptrs.resize(n); ws.resize(n); hs.resize(n); counts.assign(n, 0);
+        lens.resize(n);
         dets.resize((size_t)n * det_cap);
         for (uint32_t i = 0; i < n; ++i) {
             const Ticket& t = d->slots[take[i]];
-            ptrs[i] = t.buf; ws[i] = t.w; hs[i] = t.h;
+            ptrs[i] = t.buf; ws[i] = t.w; hs[i] = t.h; lens[i] = t.jpeg_len;
         }
-        const int rc = b->backend
-                           ? b->backend(b->backend_user, d->ordinal, ptrs.data(), ws.data(), hs.data(), n, dets.data(), det_cap, counts.data())
-                           : uf_infer_batch(d->model, ptrs.data(), ws.data(), hs.data(), n, dets.data(), det_cap, counts.data());
+        int rc_rgb = UF_OK, rc_jpeg = UF_OK;
+        if (b->backend) {
+            rc_rgb = rc_jpeg = b->backend(b->backend_user, d->ordinal, ptrs.data(), ws.data(), hs.data(), n, dets.data(), det_cap, counts.data());
+        } else {
+            if (n_rgb) rc_rgb = uf_infer_batch(d->model, ptrs.data(), ws.data(), hs.data(), n_rgb, dets.data(), det_cap, counts.data());
+            if (n > n_rgb)
+                rc_jpeg = uf_infer_batch_jpeg(d->model, ptrs.data() + n_rgb, lens.data() + n_rgb, n - n_rgb,
+                                              dets.data() + (size_t)n_rgb * det_cap, det_cap, counts.data() + n_rgb);
+        }
         const auto now = Clock::now();
         std::vector<Done> out(n);
         for (uint32_t i = 0; i < n; ++i) {
             const Ticket& t = d->slots[take[i]];
             Done& o = out[i];
+            const int rc = i < n_rgb ? rc_rgb : rc_jpeg;
             o.res.stream = t.stream; o.res.user_tag = t.tag; o.res.device = d->ordinal; o.res.status = rc;
             o.res.n_dets = rc == UF_OK ? counts[i] : 0; o.res.batch_size = n;
             o.res.latency_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(now - t.t_commit).count();
@@ -146,7 +162,8 @@ void worker_loop(uf_batcher* b, Device* d) {
             d->deliver_cv.notify_all();
         }
         b->batches++;
-        (rc == UF_OK ? b->completed : b->failed) += n;
+        (rc_rgb == UF_OK ? b->completed : b->failed) += n_rgb;
+        (rc_jpeg == UF_OK ? b->completed : b->failed) += n - n_rgb;
         b->inflight -= n;
         b->done_cv.notify_all();
     }
@@ -336,7 +353,7 @@ int uf_batcher_commit(uf_batcher* b, uint64_t ticket, uint32_t w, uint32_t h, ui
         {
             std::lock_guard<std::mutex> lk(d->mu);
             NEED(t.state == 1, "ticket is not in the acquired state");
-            t.w = w; t.h = h; t.tag = user_tag; t.t_commit = Clock::now(); t.state = 2;
+            t.w = w; t.h = h; t.jpeg_len = 0; t.tag = user_tag; t.t_commit = Clock::now(); t.state = 2;
             d->queue.push_back((uint32_t)ticket);
             b->submitted++;
             b->inflight++;
@@ -373,6 +390,56 @@ int uf_batcher_try_submit(uf_batcher* b, uint64_t stream, const uint8_t* rgb, ui
     if (rc == UF_OK) *accepted = 1;
     else uf_batcher_abort(b, ticket);
     return rc;
+}
+
+int uf_batcher_commit_jpeg(uf_batcher* b, uint64_t ticket, size_t jpeg_len, uint64_t user_tag) {
+    return guarded([&] {
+        NEED(b, "null argument");
+        Device* d = nullptr;
+        Ticket& t = ticket_ref(b, ticket, &d);
+        NEED(jpeg_len >= 4 && jpeg_len <= b->slot_bytes, "JPEG length does not fit the slot");
+        {
+            std::lock_guard<std::mutex> lk(d->mu);
+            NEED(t.state == 1, "ticket is not in the acquired state");
+            t.w = t.h = 0; t.jpeg_len = jpeg_len; t.tag = user_tag; t.t_commit = Clock::now(); t.state = 2;
+            d->queue.push_back((uint32_t)ticket);
+            b->submitted++;
+            b->inflight++;
+        }
+        d->cv.notify_one();
+    });
+}
+
+int uf_batcher_try_submit_jpeg(uf_batcher* b, uint64_t stream, const uint8_t* jpeg, size_t len, uint64_t user_tag, int32_t* accepted) {
+    if (accepted) *accepted = 0;
+    if (!b || !jpeg || !accepted || len < 4) {
+        uf::set_last_error("bad argument");
+        return UF_ERR_INVALID_ARG;
+    }
+    uint8_t* buf = nullptr;
+    uint64_t ticket = 0;
+    int rc = uf_batcher_acquire(b, stream, len, &buf, &ticket);
+    if (rc != UF_OK || !buf) return rc;
+    memcpy(buf, jpeg, len);
+    rc = uf_batcher_commit_jpeg(b, ticket, len, user_tag);
+    if (rc == UF_OK) *accepted = 1;
+    else uf_batcher_abort(b, ticket);
+    return rc;
+}
+
+int uf_batcher_ingest(uf_batcher* b, const uint8_t* msg, size_t len, uint64_t user_tag, int32_t* accepted, uint64_t* stream) {
+    if (accepted) *accepted = 0;
+    uint32_t kind = 0;
+    const uint8_t *id = nullptr, *data = nullptr;
+    size_t id_len = 0, data_len = 0;
+    int rc = uf_protomsg_parse(msg, len, &kind, &id, &id_len, &data, &data_len);
+    if (rc != UF_OK) return rc;
+    uint64_t key = 0;
+    rc = uf_stream_hash(id, id_len, &key);
+    if (rc != UF_OK) return rc;
+    if (stream) *stream = key;
+    if (kind != 1) return UF_OK;  // ConnectReq: nothing to infer
+    return uf_batcher_try_submit_jpeg(b, key, data, data_len, user_tag, accepted);
 }
 
 int uf_batcher_poll(uf_batcher* b, uf_result* res, uf_det* dets, uint32_t cap, uint32_t timeout_ms, uint32_t* n_out) {

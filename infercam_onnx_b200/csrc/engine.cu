@@ -157,6 +157,7 @@ struct Lane {
     std::mutex mu;
     std::vector<Slot> slots;
     float *d_scores = nullptr, *d_boxes = nullptr;  // raw outputs of the lane's last batch [max_batch][K][2|4]
+    std::vector<JpegCoefs> jpeg_coefs;              // N2: Huffman-decoded frames of the call in progress (storage reused)
     uint32_t last_n = 0;
     uint64_t batch_id = 0;
 };
@@ -1444,7 +1445,7 @@ int uf_infer_batch(uf_model* m, const uint8_t* const* rgb, const uint32_t* w, co
 
 // Huffman decoding of n frames on the library's host worker threads (the only serial part of JPEG decoding)
 static void entropy_decode_all(uf_model& m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, std::vector<JpegCoefs>& out) {
-    out.resize(n);
+    if (out.size() < n) out.resize(n);
     std::vector<JpegError> errs(n, JpegError{UF_OK, ""});
     m.pool().parallel_for(n, [&](uint32_t i) {
         try {
@@ -1466,12 +1467,12 @@ int uf_infer_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* l
         REQUIRE(cap == 0 || out, "out is NULL with cap > 0");
         for (uint32_t i = 0; i < n; ++i) REQUIRE(jpeg[i] && len[i] >= 4, "bad frame " + std::to_string(i));
         if (n > m->cfg.max_batch) throw ArgError(UF_ERR_CAPACITY, "batch of " + std::to_string(n) + " exceeds max_batch " + std::to_string(m->cfg.max_batch));
-        std::vector<JpegCoefs> coefs;
+        LaneLock ll(*m, false);
+        Lane& ln = *ll.lane;
+        std::vector<JpegCoefs>& coefs = ln.jpeg_coefs;
         entropy_decode_all(*m, jpeg, len, n, coefs);
         std::vector<FrameSrc> fr(n);
         for (uint32_t i = 0; i < n; ++i) fr[i] = FrameSrc{nullptr, coefs[i].plan.w, coefs[i].plan.h, &coefs[i]};
-        LaneLock ll(*m, false);
-        Lane& ln = *ll.lane;
         run_pipeline(*m, ln, n, m->host_chunk, true, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
             run_chunk_host(*m, ln, s, fr.data() + first, first, cnt);
         });

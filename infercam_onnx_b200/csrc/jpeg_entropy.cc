@@ -48,6 +48,7 @@ struct HuffTable {
     uint8_t vals[256] = {};
     // derived
     uint16_t look[1 << LOOK];   // (length << 8) | symbol, 0 = longer than LOOK bits
+    int16_t fast_ac[1 << LOOK]; // AC tables: code AND value bits inside LOOK bits -> (value << 8) | (run << 4) | total bits; 0 = no
     int32_t maxcode[18];        // largest code of each length (-1: none), [17] = sentinel
     int32_t valoff[17];         // vals index = code + valoff[length]
 
@@ -66,6 +67,17 @@ struct HuffTable {
             code <<= 1;
         }
         maxcode[17] = 0x7fffffff;
+        // one lookup decodes a whole (run, value) pair when the code and its magnitude bits fit in LOOK bits and the value in a byte
+        for (int i = 0; i < (1 << LOOK); ++i) {
+            fast_ac[i] = 0;
+            const uint16_t e = look[i];
+            if (!e) continue;
+            const int len = e >> 8, rs = e & 0xff, run = rs >> 4, mag = rs & 15;
+            if (mag == 0 || len + mag > LOOK) continue;
+            int k = ((i << len) & ((1 << LOOK) - 1)) >> (LOOK - mag);
+            if (k < (1 << (mag - 1))) k -= (1 << mag) - 1;
+            if (k >= -128 && k <= 127) fast_ac[i] = (int16_t)((k * 256) + (run * 16) + (len + mag));
+        }
     }
     void set(const uint8_t* b, const uint8_t* v, int n) {
         memcpy(bits, b, 16);
@@ -320,7 +332,7 @@ void jpeg_entropy_decode(const uint8_t* data, size_t len, JpegCoefs& out) {
         if (!P.dc[P.td[c]].defined || !P.ac[P.ta[c]].defined) fail(UF_ERR_INVALID_ARG, "Huffman table not defined");
     out.plan = p;
     out.block_off.resize((size_t)p.nblocks + 1);
-    out.entries.clear();
+    out.entries.clear();  // (callers reuse JpegCoefs objects: the capacity survives from frame to frame)
     out.entries.reserve(std::min<size_t>((size_t)p.nblocks * 64, (len - P.scan_start) * 2 + 64));
     BitReader br{data + P.scan_start, data + len};
     int pred[3] = {0, 0, 0};
@@ -358,6 +370,15 @@ void jpeg_entropy_decode(const uint8_t* data, size_t len, JpegCoefs& out) {
             const int16_t dc = (int16_t)pred[c];  // JCOEF is a short
             if (dc) out.entries.push_back((uint32_t)(uint16_t)dc);  // natural index 0
             for (int k = 1; k < 64;) {
+                if (br.nbits < 32) br.refill();
+                const int16_t fa = act.fast_ac[br.peek(LOOK)];
+                if (fa) {  // code + magnitude bits resolved by one lookup
+                    k += (fa >> 4) & 15;
+                    br.skip(fa & 15);
+                    out.entries.push_back(((uint32_t)kZigzag[k] << 16) | (uint16_t)(int16_t)(fa >> 8));
+                    ++k;
+                    continue;
+                }
                 const int rs = decode_symbol(br, act);
                 const int r = rs >> 4;
                 s = rs & 15;

@@ -371,19 +371,40 @@ nms_mask_kernel(PostBuffers pb, int K, int frames, float max_iou) {
                     const float barea = bbox_area(b.x, b.y, b.z, b.w);
                     const int word = (col0 >> 5) + warp;
                     if (word * 32 >= n) continue;  // warp-uniform
+                    // rows this column has to be tested against: the earlier candidates (i < j) that exist (ri < nrows)
+                    const int lim = valid ? min(j - row0, nrows) : 0;
 #pragma unroll
                     for (int h = 0; h < MROWS / 32; ++h) {
                         const int rb = (row0 >> 5) + h;
                         if (rb * 32 >= n || word < rb) continue;  // past the end / below the diagonal: never read
                         unsigned keep = 0u;
+                        if (exact) {  // negative / NaN threshold: the reference's division, always
 #pragma unroll 8
-                        for (int i = 0; i < 32; ++i) {
-                            const int ri = 32 * h + i;
-                            const bool hit = exact ? iou_exceeds(b, rows[ri], max_iou, true)
-                                                   : iou_exceeds_fast(b, barea, rows[ri], rarea[ri], max_iou, thr_hi, thr_lo);
-                            const bool pred = valid && j > row0 + ri && ri < nrows && hit;
-                            const unsigned bal = __ballot_sync(0xffffffffu, pred);
-                            if (lane == i) keep = bal;
+                            for (int i = 0; i < 32; ++i) {
+                                const int ri = 32 * h + i;
+                                const unsigned bal = __ballot_sync(0xffffffffu, ri < lim && iou_exceeds(b, rows[ri], max_iou, true));
+                                if (lane == i) keep = bal;
+                            }
+                        } else {
+                            // branch-free form of iou_exceeds_fast: the decision is o > max_iou * d outside a guard band of
+                            // +-1e-6 around the threshold; a pair inside the band (one in millions) sends the warp through
+                            // the reference's division for that row
+#pragma unroll 16
+                            for (int i = 0; i < 32; ++i) {
+                                const int ri = 32 * h + i;
+                                const float4 r4 = rows[ri];
+                                const float ww = __fsub_rn(fminf(b.w, r4.w), fmaxf(b.y, r4.y));
+                                const float hh = __fsub_rn(fminf(b.z, r4.z), fmaxf(b.x, r4.x));
+                                const float o = __fmul_rn(ww, hh);
+                                const float d = __fadd_rn(__fsub_rn(__fadd_rn(barea, rarea[ri]), o), 1.0e-7f);
+                                const bool overlap = !(ww < 0.0f) && !(hh < 0.0f) && o != 0.0f && ri < lim;  // NaN sides count as overlap, as in the reference
+                                const bool sure = o > __fmul_rn(thr_hi, d);
+                                bool pred = overlap && sure;
+                                if (__any_sync(0xffffffffu, overlap && !sure && !(o < __fmul_rn(thr_lo, d))))
+                                    pred = overlap && __fdiv_rn(o, d) > max_iou;
+                                const unsigned bal = __ballot_sync(0xffffffffu, pred);
+                                if (lane == i) keep = bal;
+                            }
                         }
                         mask[((size_t)rb * W + word) * 32 + lane] = keep;
                     }

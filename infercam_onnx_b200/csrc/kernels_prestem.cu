@@ -67,69 +67,56 @@ resize2_stem_kernel(U8View src, const float* __restrict__ lut, ResizeTapsDev t, 
     const int word0 = (sx0 * 3) >> 2;                // may be negative at the left edge: clamped below
     const int row_bytes = sw * 3;
 
-    // 1. vertical pass, packed 16-bit lanes: warp = resized row (4 source row pointers set up once), lane = source word
-    int wofs[4];                                     // this lane's 4 word offsets in a source row, clamped into the row
+    // 1. vertical pass, packed 16-bit lanes: thread = one 4-byte column of the source tile, walking down its 2 * PS_RH + 2
+    //    source rows with a sliding window — every source word is loaded and unpacked once and feeds two resized rows
+    //    (rows 2r-1 .. 2r+2 for resized row r). Row indices are clamped into the frame one by one: only padding rows
+    //    (zeroed in pass 2) and border rows (recomputed in pass 3) see the difference.
+    if (tid < PS_WORDS) {
+        const int wd = min(max(word0 + tid, 0), row_words - 1);
+        const unsigned* col = reinterpret_cast<const unsigned*>(sf) + wd;
+        const int ys0 = 2 * ry0 - 1;  // source row of the first tap of the first resized row
+        auto ld = [&](int k) { return __ldg(col + (size_t)min(max(ys0 + k, 0), sh - 1) * row_words); };
+        unsigned v0 = ld(0), v1 = ld(1);
+        unsigned e0 = v0 & 0x00ff00ffu, o0 = (v0 >> 8) & 0x00ff00ffu, e1 = v1 & 0x00ff00ffu, o1 = (v1 >> 8) & 0x00ff00ffu;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) wofs[k] = min(max(word0 + lane + 32 * k, 0), row_words - 1);
-    for (int rl = warp; rl < PS_RH; rl += PS_WARPS) {
-        const int ry = min(max(ry0 + rl, 0), dh - 1);  // padding rows: any value, zeroed in pass 2
-        const int y0 = 2 * ry - 1;                       // clamped into the frame: only border outputs see the difference
-        const unsigned* p0 = reinterpret_cast<const unsigned*>(sf + (size_t)max(y0, 0) * row_bytes);
-        const unsigned* p1 = reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 1) * row_bytes);
-        const unsigned* p2 = reinterpret_cast<const unsigned*>(sf + (size_t)(y0 + 2) * row_bytes);
-        const unsigned* p3 = reinterpret_cast<const unsigned*>(sf + (size_t)min(y0 + 3, sh - 1) * row_bytes);
-        unsigned a[4], b[4], c[4], d[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            a[k] = __ldg(p0 + wofs[k]); b[k] = __ldg(p1 + wofs[k]); c[k] = __ldg(p2 + wofs[k]); d[k] = __ldg(p3 + wofs[k]);
-        }
-        uint2* vrow = reinterpret_cast<uint2*>(&vt[rl][0]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (lane + 32 * k >= PS_WORDS) break;
+        for (int rl = 0; rl < PS_RH; ++rl) {
+            const unsigned v2 = ld(2 * rl + 2), v3 = ld(2 * rl + 3);
+            const unsigned e2 = v2 & 0x00ff00ffu, o2 = (v2 >> 8) & 0x00ff00ffu, e3 = v3 & 0x00ff00ffu, o3 = (v3 >> 8) & 0x00ff00ffu;
             // bytes 0,2 and bytes 1,3 as packed 16-bit lanes; sums stay below 2^11 (2^8 after the optional rounding)
-            unsigned e = (a[k] & 0x00ff00ffu) + (d[k] & 0x00ff00ffu) + 3u * ((b[k] & 0x00ff00ffu) + (c[k] & 0x00ff00ffu));
-            unsigned o = ((a[k] >> 8) & 0x00ff00ffu) + ((d[k] >> 8) & 0x00ff00ffu) +
-                         3u * (((b[k] >> 8) & 0x00ff00ffu) + ((c[k] >> 8) & 0x00ff00ffu));
+            unsigned e = e0 + e3 + 3u * (e1 + e2);
+            unsigned o = o0 + o3 + 3u * (o1 + o2);
             if (round_intermediate) {
                 e = ((e + 0x00040004u) >> 3) & 0x00ff00ffu;
                 o = ((o + 0x00040004u) >> 3) & 0x00ff00ffu;
             }
-            vrow[lane + 32 * k] = make_uint2(__byte_perm(e, o, 0x5410), __byte_perm(e, o, 0x7632));  // u16 order: byte 0,1,2,3
+            *reinterpret_cast<uint2*>(&vt[rl][4 * tid]) = make_uint2(__byte_perm(e, o, 0x5410), __byte_perm(e, o, 0x7632));  // u16 order: byte 0,1,2,3
+            e0 = e2; o0 = o2; e1 = e3; o1 = o3;
         }
     }
     __syncthreads();
 
-    // 2. horizontal pass + normalise: warp = resized row, lane = resized column (3 trips for the 65 columns); the 12 sums
-    //    of a pixel sit in 7 consecutive 32-bit words. Padding (outside the resized frame) = 0 in normalised space, as in
-    //    the ONNX Conv.
+    // 2. horizontal pass + normalise: one resized pixel (3 channels) per item; the 12 sums of a pixel sit in 7 consecutive
+    //    32-bit words. Padding (outside the resized frame) = 0 in normalised space, as in the ONNX Conv.
     const int sh6 = round_intermediate ? 3 : 6, half = round_intermediate ? 4 : 32;
     uint8_t* dbg = dbg_resized ? dbg_resized + (size_t)n * dw * dh * 3 : nullptr;
-    for (int rl = warp; rl < PS_RH; rl += PS_WARPS) {
-        const int ry = ry0 + rl;
-        const bool row_in = ry >= 0 && ry < dh;
-        const unsigned* vw = reinterpret_cast<const unsigned*>(&vt[rl][0]);
-#pragma unroll
-        for (int trip = 0; trip < 3; ++trip) {
-            const int cl = lane + 32 * trip;
-            if (cl >= PS_RW) break;
-            const int rx = rx0 + cl;
-            const bool inside = row_in && rx >= 0 && rx < dw;
-            // u16 index 6 cl + 3 .. 6 cl + 14 (source columns 2 rx - 1 .. 2 rx + 2, three channels each)
-            const unsigned* x = vw + 3 * cl + 1;
-            const unsigned w0 = x[0], w1 = x[1], w2 = x[2], w3 = x[3], w4 = x[4], w5 = x[5], w6 = x[6];
-            const int r4 = (int)(w0 >> 16) + (int)(w5 & 0xffffu) + 3 * ((int)(w2 & 0xffffu) + (int)(w3 >> 16));
-            const int g4 = (int)(w1 & 0xffffu) + (int)(w5 >> 16) + 3 * ((int)(w2 >> 16) + (int)(w4 & 0xffffu));
-            const int b4 = (int)(w1 >> 16) + (int)(w6 & 0xffffu) + 3 * ((int)(w3 & 0xffffu) + (int)(w4 >> 16));
-            const int ur = (r4 + half) >> sh6, ug = (g4 + half) >> sh6, ub = (b4 + half) >> sh6;
-            float* dst = &s_in[0][rl][cl & 1][cl >> 1];
-            dst[0] = inside ? s_lut[ur] : 0.0f;
-            dst[PS_RH * 2 * PS_HALF] = inside ? s_lut[256 + ug] : 0.0f;
-            dst[2 * PS_RH * 2 * PS_HALF] = inside ? s_lut[512 + ub] : 0.0f;
-            if (dbg && inside && cl >= 1 && rl >= 1) {
-                uint8_t* q = dbg + ((size_t)ry * dw + rx) * 3;
-                q[0] = (uint8_t)ur; q[1] = (uint8_t)ug; q[2] = (uint8_t)ub;
-            }
+    for (int it = tid; it < PS_RH * PS_RW; it += PS_THREADS) {
+        const int rl = it / PS_RW, cl = it - rl * PS_RW;  // division by a constant
+        const int rx = rx0 + cl, ry = ry0 + rl;
+        const bool inside = ry >= 0 && ry < dh && rx >= 0 && rx < dw;
+        // u16 index 6 cl + 3 .. 6 cl + 14 (source columns 2 rx - 1 .. 2 rx + 2, three channels each)
+        const unsigned* x = reinterpret_cast<const unsigned*>(&vt[rl][0]) + 3 * cl + 1;
+        const unsigned w0 = x[0], w1 = x[1], w2 = x[2], w3 = x[3], w4 = x[4], w5 = x[5], w6 = x[6];
+        const int r4 = (int)(w0 >> 16) + (int)(w5 & 0xffffu) + 3 * ((int)(w2 & 0xffffu) + (int)(w3 >> 16));
+        const int g4 = (int)(w1 & 0xffffu) + (int)(w5 >> 16) + 3 * ((int)(w2 >> 16) + (int)(w4 & 0xffffu));
+        const int b4 = (int)(w1 >> 16) + (int)(w6 & 0xffffu) + 3 * ((int)(w3 & 0xffffu) + (int)(w4 >> 16));
+        const int ur = (r4 + half) >> sh6, ug = (g4 + half) >> sh6, ub = (b4 + half) >> sh6;
+        float* dst = &s_in[0][rl][cl & 1][cl >> 1];
+        dst[0] = inside ? s_lut[ur] : 0.0f;
+        dst[PS_RH * 2 * PS_HALF] = inside ? s_lut[256 + ug] : 0.0f;
+        dst[2 * PS_RH * 2 * PS_HALF] = inside ? s_lut[512 + ub] : 0.0f;
+        if (dbg && inside && cl >= 1 && rl >= 1) {
+            uint8_t* q = dbg + ((size_t)ry * dw + rx) * 3;
+            q[0] = (uint8_t)ur; q[1] = (uint8_t)ug; q[2] = (uint8_t)ub;
         }
     }
     // 3. border outputs of the resize in f32 from the tap tables (clamped, renormalised taps are not binary fractions):

@@ -201,6 +201,10 @@ extern "C" {
     pub fn uf_batcher_abort(b: *mut uf_batcher, ticket: u64) -> c_int;
     pub fn uf_batcher_try_submit(b: *mut uf_batcher, stream: u64, rgb: *const u8, w: u32, h: u32, user_tag: u64,
                                  accepted: *mut i32) -> c_int;
+    pub fn uf_batcher_commit_jpeg(b: *mut uf_batcher, ticket: u64, jpeg_len: usize, user_tag: u64) -> c_int;
+    pub fn uf_batcher_try_submit_jpeg(b: *mut uf_batcher, stream: u64, jpeg: *const u8, len: usize, user_tag: u64,
+                                      accepted: *mut i32) -> c_int;
+    pub fn uf_batcher_ingest(b: *mut uf_batcher, msg: *const u8, len: usize, user_tag: u64, accepted: *mut i32, stream: *mut u64) -> c_int;
     pub fn uf_batcher_poll(b: *mut uf_batcher, res: *mut uf_result, dets: *mut uf_det, cap: u32, timeout_ms: u32,
                            n_out: *mut u32) -> c_int;
     pub fn uf_batcher_flush(b: *mut uf_batcher, timeout_ms: u32) -> c_int;

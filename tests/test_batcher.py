@@ -210,3 +210,62 @@ def test_gpu_batcher_two_handles_route_by_stream(make_onnx):
                 np.testing.assert_array_equal(r["dets"], seen[s % 4][0]["dets"])
     finally:
         b.close()
+
+
+@pytest.mark.gpu
+def test_gpu_ingest_of_wire_messages_end_to_end(make_onnx, test_pics):
+    """The whole road of a frame in the reference — `ProtoMsg::FrameMsg{id, data: JPEG}` off the data socket
+    (data_socket.rs:34-47), `hashed(&id)` (router.rs:58), lossy queue (router.rs:64-72), decode (inferer.rs:35), inference
+    (inferer.rs:37) — through ONE C-ABI call per message (uf_batcher_ingest), checked against the oracle's restatement of
+    the wire format / stream key and against the plain RGB path on libjpeg-turbo's pixels."""
+    import io
+
+    from PIL import Image
+
+    from oracle import ingest
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    names = ["cam-%d" % i for i in range(6)]
+    rng = np.random.default_rng(9)
+    frames = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(6)] + list(test_pics.values())[:4]
+    jpegs = []
+    for f in frames:
+        b = io.BytesIO()
+        Image.fromarray(f).save(b, "JPEG", quality=88, subsampling=1)
+        jpegs.append(b.getvalue())
+    rgbs = [np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(j)).convert("RGB"))) for j in jpegs]
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=16)
+    exp, _ = m.run_batch(rgbs, cap=64)
+    m.close()
+    b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, devices=(0, 0), max_batch=8, max_delay=0.002,
+                      capacity=256, workers=2, cap=64)
+    try:
+        ok, key = b.ingest(ingest.protomsg_connect("cam-0"))
+        assert not ok and key == ingest.hashed("cam-0")  # ConnectReq: keyed, nothing queued
+        sent = {}
+        for rep in range(3):
+            for i, j in enumerate(jpegs):
+                name = names[i % len(names)]
+                tag = rep * 100 + i
+                ok, key = b.ingest(ingest.protomsg_frame(name, j), tag=tag)
+                assert ok and key == ingest.hashed(name) == stream_hash(name)
+                sent[tag] = (key, i)
+        b.flush()
+        res = b.poll(1024)
+        assert len(res) == len(sent)
+        order = {}
+        for r in res:
+            key, i = sent[r["tag"]]
+            assert r["status"] == 0 and r["stream"] == key and r["device"] == 0
+            np.testing.assert_array_equal(r["dets"], exp[i][:64])
+            order.setdefault(key, []).append(r["tag"])
+        assert all(v == sorted(v) for v in order.values())  # per-stream submission order
+        with pytest.raises(nn.UltrafaceError):
+            b.ingest(b"\x01\x00\x00\x00garbage")
+        # a frame that is not a decodable JPEG fails ITS batch only (status != 0), the batcher carries on
+        assert b.ingest(ingest.protomsg_frame("cam-0", b"\xff\xd8 not a jpeg"), tag=7777)[0]
+        assert b.ingest(ingest.protomsg_frame("cam-1", jpegs[0]), tag=7778)[0]
+        b.flush()
+        late = {r["tag"]: r for r in b.poll(16)}
+        assert late[7777]["status"] != 0
+    finally:
+        b.close()
