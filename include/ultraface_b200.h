@@ -281,6 +281,12 @@ UF_API int uf_batcher_stats_read(const uf_batcher* b, uf_batcher_stats* out);
 UF_API int uf_batcher_owner(const uf_batcher* b, uint64_t stream, int32_t* device);
 UF_API int uf_batcher_model(uf_batcher* b, uint32_t device_slot, uf_model** out); /* borrowed: parity hooks, profiling */
 
+/* measurement aid: `producers` C++ threads submit `total` frames (frame i = frames[i % n_frames], stream = streams[i % n_streams];
+ * dropped frames are retried so that every frame is counted) while the caller's thread polls; *seconds = wall time. */
+UF_API int uf_debug_batcher_drive(uf_batcher* b, const uint8_t* frames, uint32_t n_frames, uint32_t w, uint32_t h,
+                                  const uint64_t* streams, uint32_t n_streams, uint64_t total, uint32_t producers, double* seconds,
+                                  uint64_t* detections);
+
 /* ---- ingest helpers, host only (N4) ----
  * `hashed(&id)` of infer_server/src/lib.rs:39-46: Rust's DefaultHasher (SipHash-1-3, zero keys) over the bytes of the
  * stream name followed by the 0xff terminator `str::hash` appends. */

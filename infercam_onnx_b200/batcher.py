@@ -165,6 +165,14 @@ class StreamBatcher:
                 if cb is not None and r["status"] == 0:  # a failed batch skips its frames (`if let Ok(..)`, inferer.rs:37)
                     cb(r["stream"], [((float(d[0]), float(d[1]), float(d[2]), float(d[3])), float(d[4])) for d in r["dets"]])
 
+    def drive(self, frames_ptr: int, n_frames: int, w: int, h: int, streams: Sequence[int], total: int, producers: int = 4):
+        """Measurement aid (uf_debug_batcher_drive): C++ producer threads + C++ poll loop; returns (seconds, detections)."""
+        arr = (C.c_uint64 * len(streams))(*streams)
+        sec, det = C.c_double(), C.c_uint64()
+        _check(_capi.load().uf_debug_batcher_drive(self._h, C.c_void_p(frames_ptr), n_frames, w, h, arr, len(streams), total, producers,
+                                                   C.byref(sec), C.byref(det)))
+        return float(sec.value), int(det.value)
+
     def flush(self, timeout: float = 30.0) -> None:
         _check(_capi.load().uf_batcher_flush(self._h, int(timeout * 1e3)))
 

@@ -131,12 +131,20 @@ void worker_loop(uf_batcher* b, Device* d) {
                 rc_jpeg = uf_infer_batch_jpeg(d->model, ptrs.data() + n_rgb, lens.data() + n_rgb, n - n_rgb,
                                               dets.data() + (size_t)n_rgb * det_cap, det_cap, counts.data() + n_rgb);
         }
+        // one undecodable file fails the whole JPEG call: isolate it so that its batch-mates are not skipped with it
+        std::vector<int> rc_each;
+        if (!b->backend && rc_jpeg != UF_OK && n - n_rgb > 1) {
+            rc_each.assign(n, UF_OK);
+            for (uint32_t i = n_rgb; i < n; ++i)
+                rc_each[i] = uf_infer_batch_jpeg(d->model, ptrs.data() + i, lens.data() + i, 1, dets.data() + (size_t)i * det_cap, det_cap,
+                                                 counts.data() + i);
+        }
         const auto now = Clock::now();
         std::vector<Done> out(n);
         for (uint32_t i = 0; i < n; ++i) {
             const Ticket& t = d->slots[take[i]];
             Done& o = out[i];
-            const int rc = i < n_rgb ? rc_rgb : rc_jpeg;
+            const int rc = i < n_rgb ? rc_rgb : rc_each.empty() ? rc_jpeg : rc_each[i];
             o.res.stream = t.stream; o.res.user_tag = t.tag; o.res.device = d->ordinal; o.res.status = rc;
             o.res.n_dets = rc == UF_OK ? counts[i] : 0; o.res.batch_size = n;
             o.res.latency_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(now - t.t_commit).count();
@@ -163,7 +171,11 @@ void worker_loop(uf_batcher* b, Device* d) {
         }
         b->batches++;
         (rc_rgb == UF_OK ? b->completed : b->failed) += n_rgb;
-        (rc_jpeg == UF_OK ? b->completed : b->failed) += n - n_rgb;
+        if (rc_each.empty()) {
+            (rc_jpeg == UF_OK ? b->completed : b->failed) += n - n_rgb;
+        } else {
+            for (uint32_t i = n_rgb; i < n; ++i) (rc_each[i] == UF_OK ? b->completed : b->failed) += 1;
+        }
         b->inflight -= n;
         b->done_cv.notify_all();
     }
@@ -490,6 +502,46 @@ int uf_batcher_model(uf_batcher* b, uint32_t device_slot, uf_model** out) {
         NEED(b && out && device_slot < b->devs.size(), "bad argument");
         NEED(b->devs[device_slot]->model, "this batcher runs an injected backend, it owns no model handle");
         *out = b->devs[device_slot]->model;
+    });
+}
+
+// Measurement aid: drives the batcher from C++ — `producers` threads submit `total` frames (frame i = frames + (i % n_frames)
+// * w * h * 3, stream = streams[i % n_streams]) with the lossy try_submit, retrying dropped frames so that every frame is
+// counted, while the calling thread polls — and reports the wall time. What a Rust ingest task would do, minus Rust.
+int uf_debug_batcher_drive(uf_batcher* b, const uint8_t* frames, uint32_t n_frames, uint32_t w, uint32_t h, const uint64_t* streams,
+                           uint32_t n_streams, uint64_t total, uint32_t producers, double* seconds, uint64_t* detections) {
+    return guarded([&] {
+        NEED(b && frames && n_frames && w && h && streams && n_streams && producers && producers <= 64 && seconds, "bad argument");
+        const size_t fb = (size_t)w * h * 3;
+        std::atomic<uint64_t> next{0}, errors{0};
+        const auto t0 = Clock::now();
+        std::vector<std::thread> ts;
+        for (uint32_t p = 0; p < producers; ++p)
+            ts.emplace_back([&] {
+                for (;;) {
+                    const uint64_t i = next.fetch_add(1);
+                    if (i >= total) return;
+                    for (;;) {
+                        int32_t ok = 0;
+                        if (uf_batcher_try_submit(b, streams[i % n_streams], frames + (i % n_frames) * fb, w, h, i, &ok) != UF_OK) { errors++; break; }
+                        if (ok) break;
+                        std::this_thread::sleep_for(std::chrono::microseconds(50));
+                    }
+                }
+            });
+        std::vector<uf_result> res(1024);
+        std::vector<uf_det> dets((size_t)1024 * b->cfg.det_cap);
+        uint64_t got = 0, ndet = 0;
+        while (got + errors.load() < total) {
+            uint32_t n = 0;
+            if (uf_batcher_poll(b, res.data(), dets.data(), 1024, 20, &n) != UF_OK) break;
+            for (uint32_t k = 0; k < n; ++k) ndet += res[k].n_dets;
+            got += n;
+        }
+        for (auto& t : ts) t.join();
+        *seconds = std::chrono::duration<double>(Clock::now() - t0).count();
+        if (detections) *detections = ndet;
+        if (errors.load()) throw Fail{UF_ERR_INVALID_ARG, "uf_batcher_try_submit failed for " + std::to_string(errors.load()) + " frames"};
     });
 }
 

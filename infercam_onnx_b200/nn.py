@@ -74,6 +74,7 @@ class UltrafaceModel(InferModel):
         self.num_priors = int(info.num_priors)
         self.max_batch = int(info.max_batch)
         self._tls = threading.local()
+        self._ptr_args = {}
 
     @classmethod
     def new(cls, variant: UltrafaceVariant, max_iou: float, min_confidence: float, *, onnx_path: Optional[str] = None,
@@ -137,10 +138,14 @@ class UltrafaceModel(InferModel):
 
     def run_batch_ptr(self, host_ptr: int, w: int, h: int, n: int, cap: int = 256) -> List[np.ndarray]:
         """n frames of w x h contiguous in (pinned) HOST memory at host_ptr."""
-        fb = w * h * 3
-        ptrs = (C.c_void_p * n)(*[host_ptr + i * fb for i in range(n)])
-        ws = (C.c_uint32 * n)(*([w] * n))
-        hs = (C.c_uint32 * n)(*([h] * n))
+        key = (host_ptr, w, h, n)
+        args = self._ptr_args.get(key)
+        if args is None:  # the argument arrays of a repeated call (a ring of pinned frames) are built once
+            fb = w * h * 3
+            args = ((C.c_void_p * n)(*[host_ptr + i * fb for i in range(n)]), (C.c_uint32 * n)(*([w] * n)), (C.c_uint32 * n)(*([h] * n)))
+            if len(self._ptr_args) < 64:
+                self._ptr_args[key] = args
+        ptrs, ws, hs = args
         return self._run_batch_raw(lambda out, cnt: _capi.load().uf_infer_batch(self._h, ptrs, ws, hs, n, out, cap, cnt), n, cap)
 
     def run_batch_device(self, device_ptr: int, w: int, h: int, n: int, cap: int = 256) -> List[np.ndarray]:
@@ -179,9 +184,12 @@ class UltrafaceModel(InferModel):
                 cache.pop(next(iter(cache))).free()
             cache[key] = _PinnedResults(*key)
         buf = cache[key]
-        _check(call(buf.dets.ctypes.data_as(C.POINTER(_capi.uf_det)), buf.counts_p))
-        cnt = buf.counts
-        return [buf.dets[i, : min(int(cnt[i]), cap)].copy() for i in range(n)], [int(cnt[i]) for i in range(n)]
+        _check(call(buf.dets_p, buf.counts_p))
+        counts = buf.counts[:n].tolist()
+        # one copy out of the pinned array (only as deep as the fullest frame), per-frame results are views of it
+        deepest = min(max(counts, default=0), cap)
+        out = buf.dets[:n, :deepest].copy()
+        return [out[i, : min(c, cap)] for i, c in enumerate(counts)], counts
 
     # ---- parity hooks
     def raw_outputs(self, first: int, n: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -364,6 +372,7 @@ class _PinnedResults:
         self.dets = np.ctypeslib.as_array((C.c_float * (n * cap * 5)).from_address(self.ptr)).reshape(n, cap, 5)
         self.counts = np.ctypeslib.as_array((C.c_uint32 * n).from_address(self.ptr + n * cap * 20))
         self.counts_p = C.cast(self.ptr + n * cap * 20, C.POINTER(C.c_uint32))
+        self.dets_p = C.cast(self.ptr, C.POINTER(_capi.uf_det))
 
     def free(self) -> None:
         if self.ptr:

@@ -266,6 +266,7 @@ def test_gpu_ingest_of_wire_messages_end_to_end(make_onnx, test_pics):
         assert b.ingest(ingest.protomsg_frame("cam-1", jpegs[0]), tag=7778)[0]
         b.flush()
         late = {r["tag"]: r for r in b.poll(16)}
-        assert late[7777]["status"] != 0
+        assert late[7777]["status"] != 0 and late[7778]["status"] == 0
+        np.testing.assert_array_equal(late[7778]["dets"], exp[0][:64])
     finally:
         b.close()
