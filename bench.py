@@ -137,7 +137,7 @@ def smooth_frames(n, seed):
 
 def batcher_leg(nn, path, w, h, local, rank, world, pinned, B, steps, barrier, max_over_ranks):
     """e2e through the C-ABI stream batcher (uf_batcher_*): this rank's shard of 1 024 logical streams
-    (streams.shard_streams: stream s -> rank s % world) keyed by the reference's `hashed(name)`; 6 C++ producer threads
+    (streams.shard_streams: stream s -> rank s % world) keyed by the reference's `hashed(name)`; 10 C++ producer threads
     (uf_debug_batcher_drive: what the Rust ingest task would be) copy frames from pinned memory into the batcher's pinned
     pool with the lossy try_submit, the batcher forms batches of <= 128 on a 2 ms deadline with 3 in flight, the caller polls.
     Returns (frames, seconds, stats)."""
@@ -146,10 +146,10 @@ def batcher_leg(nn, path, w, h, local, rank, world, pinned, B, steps, barrier, m
     mine = [streams.stream_id("stream-%d" % s) for s in streams.shard_streams(1024, rank, world)]
     b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, size=(w, h), devices=(local,), max_batch=128,
                       max_delay=0.002, capacity=4 * B, workers=3, cap=64, max_frame_bytes=SRC_W * SRC_H * 3)
-    b.drive(pinned.ptr, B, SRC_W, SRC_H, mine, 3 * B, producers=6)  # warm-up: graphs of the batcher's own handle
+    b.drive(pinned.ptr, B, SRC_W, SRC_H, mine, 3 * B, producers=10)  # warm-up: graphs of the batcher's own handle
     barrier()
     total = B * steps
-    sec, _ = b.drive(pinned.ptr, B, SRC_W, SRC_H, mine, total, producers=6)
+    sec, _ = b.drive(pinned.ptr, B, SRC_W, SRC_H, mine, total, producers=10)
     barrier()
     dt = max_over_ranks(sec)
     st = b.stats()
@@ -461,7 +461,7 @@ def main():
         done, dt_b, st = batcher_leg(nn, path, w, h, local, rank, world, pinned, B, args.steps, barrier, max_over_ranks)
         extra["batcher"] = {"value": done * world / dt_b, "unit": "frames/s",
                             "api": "uf_batcher_try_submit / uf_batcher_poll (C ABI): 1024 logical streams keyed by hashed(name), sharded "
-                                   "s % n_gpus (streams.shard_streams), 6 C++ producer threads copy frames into the owner GPU's pinned "
+                                   "s % n_gpus (streams.shard_streams), 10 C++ producer threads copy frames into the owner GPU's pinned "
                                    "pool (wall-clock timed), batches of <= 128 formed on a 2 ms deadline, 3 in flight",
                             "batches": st["batches"], "mean_batch": st["completed"] / max(1, st["batches"]), "dropped_then_retried": st["dropped"]}
         dt_j, jpeg_b, coef_b, out_j = jpeg_leg(nn, model, args.steps, barrier, max_over_ranks, B, cap)
