@@ -56,24 +56,25 @@ fn env_u32(name: &str, default: u32) -> u32 {
     std::env::var(name).ok().and_then(|v| v.parse().ok()).unwrap_or(default)
 }
 
-/// Cache lookup + download exactly as the original `get_model` (nn.rs:143-163); only the load differs.
-pub(crate) async fn model_path(variant: &UltrafaceVariant) -> Result<std::path::PathBuf> {
-    let (model_name, download_link) = match variant {
+/// Where the weight file lives and where it comes from: the same cache directory, file names and URLs as the
+/// original `get_model` (nn.rs:143-163), so an existing cache keeps working. Only the load that follows differs.
+fn weight_file(variant: &UltrafaceVariant) -> (&'static str, &'static str) {
+    match variant {
         UltrafaceVariant::W640H480 => ("ultraface-RFB-640.onnx", ULTRAFACE_LINK_640),
         UltrafaceVariant::W320H240 => ("ultraface-RFB-320.onnx", ULTRAFACE_LINK_320),
-    };
-    let model_file_dir = dirs::cache_dir().expect("cache dir").join("infercam_onnx");
-    if !model_file_dir.is_dir() {
-        std::fs::create_dir_all(&model_file_dir)?;
     }
-    let model_file_path = model_file_dir.join(model_name);
-    if !model_file_path.is_file() {
-        let client = reqwest::Client::new();
-        println!("Downloading Ultraface model...");
-        download_file(&client, download_link, &model_file_path).await?;
-        println!("Download complete");
+}
+
+pub(crate) async fn model_path(variant: &UltrafaceVariant) -> Result<std::path::PathBuf> {
+    let (file_name, url) = weight_file(variant);
+    let cache = dirs::cache_dir().ok_or_else(|| anyhow!("no cache directory on this platform"))?.join("infercam_onnx");
+    std::fs::create_dir_all(&cache)?;
+    let path = cache.join(file_name);
+    if !path.is_file() {
+        // first run: fetch the weights once, as the reference does
+        download_file(&reqwest::Client::new(), url, &path).await?;
     }
-    Ok(model_file_path)
+    Ok(path)
 }
 
 pub(crate) fn model_config(path: &CString, variant: &UltrafaceVariant, max_iou: f32, min_confidence: f32) -> sys::uf_config {
