@@ -322,13 +322,14 @@ post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float 
 
 // ---------------------------------------------------------------------------------------------
 // nms_mask_kernel: bit (i, j), j > i, of frame f  <=>  iou(cand_j, cand_i) > max_iou  (candidates in processing
-// order). Layout: [frame][row block i/32][word j/32][i%32] — the 32 rows of a block are adjacent for one word, so this
-// kernel stores, and the sweep loads, whole 128-byte lines. Work unit = (frame, MROWS rows): the rows (and their areas)
-// are staged in shared memory once and every thread walks them for its own column, MCOLS columns per pass, starting at
-// the diagonal; one ballot per row and warp is one mask word, lane i%32 keeps the word of row i. Persistent grid: units
-// are dealt round-robin, frames without a published candidate list cost one shared-memory read.
+// order). Layout: [frame][row block i/32][column block j/32][j%32] -> u32 whose bit i%32 is (i, j): each COLUMN keeps its 32
+// decisions against a block of rows in one word (no transposition, no warp-wide operation in the producer), the 32
+// columns of a block are adjacent, so this kernel stores, and the sweep loads, whole 128-byte lines. Work unit = (frame,
+// MROWS rows): the rows (and their areas) are staged in shared memory once and every thread walks them for its own column,
+// MCOLS columns per pass, starting at the diagonal. Persistent grid: units are dealt round-robin, frames without a
+// published candidate list cost one shared-memory read.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MCOLS)
+__global__ void __launch_bounds__(MCOLS, 3)
 nms_mask_kernel(PostBuffers pb, int K, int frames, float max_iou) {
     __shared__ float4 rows[MROWS];
     __shared__ float rarea[MROWS];
@@ -377,19 +378,18 @@ nms_mask_kernel(PostBuffers pb, int K, int frames, float max_iou) {
                     for (int h = 0; h < MROWS / 32; ++h) {
                         const int rb = (row0 >> 5) + h;
                         if (rb * 32 >= n || word < rb) continue;  // past the end / below the diagonal: never read
-                        unsigned keep = 0u;
+                        // this column's 32 decisions against the rows of block rb, one bit per row — no warp-wide
+                        // operation in the loop: the word is stored column-major (see the layout note above)
+                        unsigned bits = 0u;
                         if (exact) {  // negative / NaN threshold: the reference's division, always
 #pragma unroll 8
-                            for (int i = 0; i < 32; ++i) {
-                                const int ri = 32 * h + i;
-                                const unsigned bal = __ballot_sync(0xffffffffu, ri < lim && iou_exceeds(b, rows[ri], max_iou, true));
-                                if (lane == i) keep = bal;
-                            }
+                            for (int i = 0; i < 32; ++i)
+                                if (iou_exceeds(b, rows[32 * h + i], max_iou, true)) bits |= 1u << i;
                         } else {
-                            // branch-free form of iou_exceeds_fast: the decision is o > max_iou * d outside a guard band of
-                            // +-1e-6 around the threshold; a pair inside the band (one in millions) sends the warp through
-                            // the reference's division for that row
-#pragma unroll 16
+                            // decision o > max_iou * d outside a guard band of +-1e-6 around the threshold; pairs inside the
+                            // band (one in millions) are collected in `amb` and settled by the reference's division below
+                            unsigned amb = 0u;
+#pragma unroll
                             for (int i = 0; i < 32; ++i) {
                                 const int ri = 32 * h + i;
                                 const float4 r4 = rows[ri];
@@ -397,16 +397,20 @@ nms_mask_kernel(PostBuffers pb, int K, int frames, float max_iou) {
                                 const float hh = __fsub_rn(fminf(b.z, r4.z), fmaxf(b.x, r4.x));
                                 const float o = __fmul_rn(ww, hh);
                                 const float d = __fadd_rn(__fsub_rn(__fadd_rn(barea, rarea[ri]), o), 1.0e-7f);
-                                const bool overlap = !(ww < 0.0f) && !(hh < 0.0f) && o != 0.0f && ri < lim;  // NaN sides count as overlap, as in the reference
+                                const bool overlap = !(ww < 0.0f) && !(hh < 0.0f) && o != 0.0f;  // NaN sides count as overlap, as in the reference
                                 const bool sure = o > __fmul_rn(thr_hi, d);
-                                bool pred = overlap && sure;
-                                if (__any_sync(0xffffffffu, overlap && !sure && !(o < __fmul_rn(thr_lo, d))))
-                                    pred = overlap && __fdiv_rn(o, d) > max_iou;
-                                const unsigned bal = __ballot_sync(0xffffffffu, pred);
-                                if (lane == i) keep = bal;
+                                if (overlap && sure) bits |= 1u << i;
+                                if (overlap && !sure && !(o < __fmul_rn(thr_lo, d))) amb |= 1u << i;
+                            }
+                            while (amb) {  // rare, per lane
+                                const int i = __ffs(amb) - 1;
+                                amb &= amb - 1;
+                                if (iou(b, rows[32 * h + i]) > max_iou) bits |= 1u << i;
                             }
                         }
-                        mask[((size_t)rb * W + word) * 32 + lane] = keep;
+                        const int nvalid = lim - 32 * h;  // rows of this block that exist and precede the column
+                        bits &= nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : (1u << nvalid) - 1u);
+                        mask[((size_t)rb * W + word) * 32 + lane] = bits;
                     }
                 }
             }
@@ -417,11 +421,11 @@ nms_mask_kernel(PostBuffers pb, int K, int frames, float max_iou) {
 
 // ---------------------------------------------------------------------------------------------
 // nms_sweep_kernel: one CTA per frame with a published candidate list; `removed` bitset in shared memory.
-// Two levels: a super-chunk of 256 candidates (8 words) is resolved by one warp from its 8x8-word diagonal block held
-// in shared memory — 32 candidates per step in registers (shuffles), survivors' rows folded into the super-chunk's
-// remaining words with a warp OR-reduction — then all warps push the survivors' rows into the words beyond the
-// super-chunk (whole lines, sixteen loads in flight per lane), so the serial chain per 256 candidates is one block
-// load, eight register-resident steps and one parallel push.
+// Two levels: a super-chunk of 256 candidates (8 blocks of 32) is resolved by one warp from its 8x8-block diagonal part of
+// the matrix held in shared memory — 32 candidates per step in registers (one shuffle each), the survivors' effect on the
+// super-chunk's later blocks by one ballot per block — then all warps push the survivors' effect on every candidate beyond
+// the super-chunk (whole lines, sixteen loads in flight per lane, one ballot per 32 candidates), so the serial chain per
+// 256 candidates is one block load, eight register-resident steps and one parallel push.
 // ---------------------------------------------------------------------------------------------
 constexpr int SWEEP_THR = 512;
 constexpr int SWEEP_WARPS = SWEEP_THR / 32;
@@ -429,7 +433,7 @@ constexpr int SWEEP_WARPS = SWEEP_THR / 32;
 __global__ void __launch_bounds__(SWEEP_THR)
 nms_sweep_kernel(const float* __restrict__ scores, PostBuffers pb, int K) {
     extern __shared__ unsigned removed[];  // mask_pitch words
-    __shared__ unsigned blk[8][8][32];     // [row block q][word k][row in block]
+    __shared__ unsigned blk[8][8][32];     // [row block q][column block k][column in block] -> bits over the rows of block q
     __shared__ unsigned s_kept[8];
     pdl_launch_dependents();
     pdl_wait();
@@ -457,7 +461,8 @@ nms_sweep_kernel(const float* __restrict__ scores, PostBuffers pb, int K) {
             if (q < nq && k < nq && k >= q) blk[q][k][lane] = mask[((size_t)(word0 + q) * W + word0 + k) * 32 + lane];
         }
         __syncthreads();
-        // 2. eight serial steps of 32 candidates, warp 0
+        // 2. eight serial steps of 32 candidates, warp 0. Lane = candidate j of the block; its word of the diagonal block
+        //    holds, bit by bit, which earlier candidates i of the same block would suppress it.
         if (warp == 0) {
             for (int q = 0; q < 8; ++q) {
                 unsigned kept = 0u;
@@ -467,21 +472,21 @@ nms_sweep_kernel(const float* __restrict__ scores, PostBuffers pb, int K) {
                     // prefetch what the survivors will write (independent of the resolution below)
                     const unsigned long long key = in ? keys[row] : 0ull;
                     const float4 kb = in ? sel[row] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const unsigned diag = blk[q][q][lane];
+                    const unsigned col = blk[q][q][lane];
                     unsigned rem = removed[word0 + q];
                     if (32 * (word0 + q) + 32 > n) rem |= 0xffffffffu << (n - 32 * (word0 + q));  // past the end: never kept
 #pragma unroll
                     for (int b = 0; b < 32; ++b) {
-                        const unsigned d = __shfl_sync(0xffffffffu, diag, b);
-                        if (!((rem >> b) & 1u)) { kept |= 1u << b; rem |= d; }
+                        const unsigned cb = __shfl_sync(0xffffffffu, col, b);  // who suppresses candidate b
+                        if (!((rem >> b) & 1u) && !(cb & kept)) kept |= 1u << b;
                     }
-                    const bool mine = (kept >> lane) & 1u;
+                    // survivors of this block suppress candidates of the super-chunk's later blocks
                     for (int k = q + 1; k < nq; ++k) {
-                        const unsigned r = __reduce_or_sync(0xffffffffu, mine ? blk[q][k][lane] : 0u);
+                        const unsigned r = __ballot_sync(0xffffffffu, (blk[q][k][lane] & kept) != 0u);
                         if (lane == 0) removed[word0 + k] |= r;
                     }
                     __syncwarp();
-                    if (mine) {
+                    if ((kept >> lane) & 1u) {
                         const int pos = n_sel + __popc(kept & ((1u << lane) - 1u));
                         const unsigned k = (unsigned)(key & 0xffffffffull);
                         float* d = dets + (size_t)pos * 5;
@@ -494,12 +499,12 @@ nms_sweep_kernel(const float* __restrict__ scores, PostBuffers pb, int K) {
             }
         }
         __syncthreads();
-        // 3. push the survivors' rows into every word beyond the super-chunk: a warp owns a word, loads the line of each of
-        //    the 8 row blocks (two words per trip: sixteen loads in flight), ORs them per lane, reduces across the lanes
+        // 3. push: a warp owns a word (32 candidates beyond the super-chunk), loads their words against each of the 8 row
+        //    blocks (two words per trip: sixteen loads in flight), masks them with the blocks' survivors, one ballot
         const int wfar = word0 + 8;
         unsigned km[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) km[q] = ((s_kept[q] >> lane) & 1u) ? 0xffffffffu : 0u;
+        for (int q = 0; q < 8; ++q) km[q] = s_kept[q];
         for (int w = wfar + warp; w < nw; w += 2 * SWEEP_WARPS) {
             const int w2 = w + SWEEP_WARPS;
             const bool two = w2 < nw;
@@ -512,8 +517,8 @@ nms_sweep_kernel(const float* __restrict__ scores, PostBuffers pb, int K) {
             unsigned a = 0u, b2 = 0u;
 #pragma unroll
             for (int q = 0; q < 8; ++q) { a |= v[q] & km[q]; b2 |= u[q] & km[q]; }
-            a = __reduce_or_sync(0xffffffffu, a);
-            b2 = __reduce_or_sync(0xffffffffu, b2);
+            a = __ballot_sync(0xffffffffu, a != 0u);
+            b2 = __ballot_sync(0xffffffffu, b2 != 0u);
             if (lane == 0) {
                 if (a) removed[w] |= a;
                 if (two && b2) removed[w2] |= b2;
