@@ -210,6 +210,30 @@ UF_API int uf_jpeg_info_read(const uint8_t* jpeg, size_t len, uf_jpeg_info* out)
  * order inside a block; cap_blocks = its capacity in blocks. */
 UF_API int uf_jpeg_coefficients(const uint8_t* jpeg, size_t len, uf_jpeg_info* info, int16_t* coefs, size_t cap_blocks);
 
+/* ==== after the path: overlay + JPEG encode (partial) ===========================================
+ * Replaces `draw_bboxes_on_image` + `turbojpeg::compress_image(&frame, 95, Subsamp::Sub2x2)` (inferer.rs:38-39, 58-92) for the
+ * RECTANGLES: every detection's outline is drawn as imageproc's `draw_hollow_rect` draws it — corners from the reference's
+ * casts (x_tl as i32, (x_br - x_tl) as u32 ... of bbox * (scale_w, scale_h); the reference passes 1280 x 720 whatever the
+ * frame, router.rs:66-67), four clipped 1-pixel segments in (0, 255, 0); a box whose width or height casts to 0 is skipped
+ * (the reference would panic in Rect::of_size). The confidence TEXT the reference prints with rusttype is not drawn.
+ * The frame is then encoded as baseline JPEG, YCbCr 4:2:0, Annex K Huffman tables, jpeg_set_quality(quality) tables: colour
+ * conversion, chroma downsampling, forward ISLOW DCT and quantisation on the GPU (the coefficients are libjpeg-turbo's, bit
+ * for bit), Huffman coding on the host. out / cap: destination buffer; *out_len = bytes needed (UF_ERR_CAPACITY if > cap). */
+UF_API int uf_annotate_encode_jpeg(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets,
+                                   float scale_w, float scale_h, uint32_t quality, uint8_t* out, size_t cap, size_t* out_len);
+/* Same with the frame given as the baseline JPEG it arrived as (decoded on the GPU, N2; never leaves the device as pixels). */
+UF_API int uf_annotate_reencode_jpeg(uf_model* m, const uint8_t* jpeg, size_t len, const uf_det* dets, uint32_t n_dets,
+                                     float scale_w, float scale_h, uint32_t quality, uint8_t* out, size_t cap, size_t* out_len);
+/* host only: the Huffman-coding / file-writing half alone. coefs = quantised blocks of a w x h YCbCr 4:2:0 frame, per
+ * component plane (Y, Cb, Cr; each padded to whole 16x16 MCUs) in raster order, natural order inside a block; tables =
+ * jpeg_set_quality(quality). uf_jpeg_quality_tables returns those tables (natural order). */
+UF_API int uf_jpeg_write_coefficients(uint32_t w, uint32_t h, uint32_t quality, const int16_t* coefs, size_t n_blocks, uint8_t* out,
+                                      size_t cap, size_t* out_len);
+UF_API int uf_jpeg_quality_tables(uint32_t quality, uint16_t* lum64, uint16_t* chr64);
+/* parity hook: the frame with the rectangles drawn (RGB8, w * h * 3 bytes). */
+UF_API int uf_draw_boxes_rgb(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets,
+                             float scale_w, float scale_h, uint8_t* out_rgb);
+
 /* ==== stream batcher + stream -> GPU routing ==========================================
  * Replaces the loop of `Inferer::run` (inferer.rs:29-50: recv_ref -> model.run -> send) and the bounded LOSSY queue in
  * front of it (`INFER_IMAGES_CHANNEL`, capacity 10, lib.rs:32-37; the router fills it with `try_send_ref` and drops the

@@ -100,6 +100,13 @@ SIGNATURES = {
     "uf_jpeg_decode_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _p(C.c_uint32), _p(C.c_uint32)]),
     "uf_jpeg_info_read": (C.c_int, [C.c_void_p, C.c_size_t, _p(uf_jpeg_info)]),
     "uf_jpeg_coefficients": (C.c_int, [C.c_void_p, C.c_size_t, _p(uf_jpeg_info), C.c_void_p, C.c_size_t]),
+    "uf_annotate_encode_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float,
+                                          C.c_uint32, C.c_void_p, C.c_size_t, _p(C.c_size_t)]),
+    "uf_annotate_reencode_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_uint32,
+                                            C.c_void_p, C.c_size_t, _p(C.c_size_t)]),
+    "uf_jpeg_write_coefficients": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _p(C.c_size_t)]),
+    "uf_jpeg_quality_tables": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p]),
+    "uf_draw_boxes_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]),
     "uf_batcher_create": (C.c_int, [_p(uf_batcher_config), _void_pp]),
     "uf_batcher_create_ex": (C.c_int, [_p(uf_batcher_config), uf_batch_fn, C.c_void_p, _void_pp]),
     "uf_batcher_destroy": (None, [C.c_void_p]),

@@ -1502,6 +1502,144 @@ int uf_jpeg_decode_rgb(uf_model* m, const uint8_t* jpeg, size_t len, uint8_t* ou
     });
 }
 
+// ---- N3: rectangles as the reference computes them (inferer.rs:66-75) and imageproc draws them ----
+static int32_t sat_i32(float v) {  // Rust `as i32`: saturating, NaN -> 0
+    if (!(v == v)) return 0;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)v;
+}
+static uint32_t sat_u32(float v) {  // Rust `as u32`
+    if (!(v == v) || v <= 0.0f) return 0;
+    if (v >= 4294967296.0f) return UINT32_MAX;
+    return (uint32_t)v;
+}
+
+static std::vector<int4> reference_rects(const uf_det* dets, uint32_t n, float width, float height) {
+    std::vector<int4> r;
+    for (uint32_t i = 0; i < n; ++i) {
+        // inferer.rs:69-75, f32 arithmetic, one rounding per operation
+        volatile float x_tl = dets[i].x0 * width, y_tl = dets[i].y0 * height;
+        volatile float x_br = dets[i].x1 * width, y_br = dets[i].y1 * height;
+        volatile float rect_width = x_br - x_tl, rect_height = y_br - y_tl;
+        const uint32_t rw = sat_u32(rect_width), rh = sat_u32(rect_height);
+        if (rw == 0 || rh == 0) continue;  // Rect::of_size asserts on these: the reference would panic, we skip the box
+        const int64_t left = sat_i32(x_tl), top = sat_i32(y_tl);
+        const int64_t right = left + (int64_t)rw - 1, bottom = top + (int64_t)rh - 1;  // imageproc Rect::right / bottom
+        auto cl = [](int64_t v) { return (int)std::max<int64_t>(-(1 << 30), std::min<int64_t>(1 << 30, v)); };  // clipping happens per pixel anyway
+        r.push_back(make_int4(cl(left), cl(top), cl(right), cl(bottom)));
+    }
+    return r;
+}
+
+// draws on the RGB frame at s.d_in (device) and, if `file` is given, encodes it; everything on slot 0 of the locked lane
+static void annotate_on_device(uf_model& m, Slot& s, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets, float scale_w, float scale_h,
+                               int quality, std::vector<uint8_t>* file) {
+    std::vector<int4> rects = reference_rects(dets, n_dets, scale_w, scale_h);
+    // clip rectangles that lie wholly outside early (a box far off-frame would otherwise be a long empty loop)
+    std::vector<int4> vis;
+    for (const int4& r : rects)
+        if (r.z >= 0 && r.w >= 0 && r.x < (int)w && r.y < (int)h)
+            vis.push_back(make_int4(std::max(r.x, -1), std::max(r.y, -1), std::min(r.z, (int)w), std::min(r.w, (int)h)));
+    if (!vis.empty()) {
+        int4* d_rects = (int4*)hook_scratch(m, vis.size() * sizeof(int4));
+        CK(cudaMemcpyAsync(d_rects, vis.data(), vis.size() * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
+        m.launches++;
+        launch_draw_rects(s.d_in, (int)w, (int)h, d_rects, (int)vis.size(), s.stream);
+        CK(cudaStreamSynchronize(s.stream));  // `vis` is pageable host memory
+    }
+    if (!file) return;
+    const JpegPlan plan = jpeg_encode_plan(w, h, quality);
+    const size_t coef_bytes = (size_t)plan.plane_bytes * sizeof(int16_t);
+    grow_jpeg(s, coef_bytes, plan.plane_bytes);
+    m.launches += 2;
+    launch_jpeg_encode(s.d_in, plan, s.d_planes, reinterpret_cast<int16_t*>(s.d_jpeg), s.stream);
+    CK(cudaMemcpyAsync(s.h_jpeg, s.d_jpeg, coef_bytes, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaGetLastError());
+    jpeg_write_file(plan, reinterpret_cast<const int16_t*>(s.h_jpeg), *file);
+}
+
+static void deliver_file(const std::vector<uint8_t>& file, uint8_t* out, size_t cap, size_t* out_len) {
+    *out_len = file.size();
+    if (file.size() > cap || !out) throw ArgError(UF_ERR_CAPACITY, "output buffer smaller than the encoded file (" + std::to_string(file.size()) + " bytes)");
+    memcpy(out, file.data(), file.size());
+}
+
+int uf_annotate_encode_jpeg(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets, float scale_w,
+                            float scale_h, uint32_t quality, uint8_t* out, size_t cap, size_t* out_len) {
+    return guarded([&] {
+        REQUIRE(m && rgb && out_len && w > 0 && h > 0 && w <= 16384 && h <= 16384 && (n_dets == 0 || dets), "bad argument");
+        LaneLock ll(*m, true);
+        Slot& s = ll.lane->slots[0];
+        CK(cudaSetDevice(m->cfg.device));
+        const size_t fb = (size_t)w * h * 3;
+        grow_input(s, fb);
+        CK(cudaMemcpyAsync(s.d_in, rgb, fb, cudaMemcpyHostToDevice, s.stream));
+        std::vector<uint8_t> file;
+        annotate_on_device(*m, s, w, h, dets, n_dets, scale_w, scale_h, (int)quality, &file);
+        deliver_file(file, out, cap, out_len);
+    });
+}
+
+int uf_annotate_reencode_jpeg(uf_model* m, const uint8_t* jpeg, size_t len, const uf_det* dets, uint32_t n_dets, float scale_w,
+                              float scale_h, uint32_t quality, uint8_t* out, size_t cap, size_t* out_len) {
+    return guarded([&] {
+        REQUIRE(m && jpeg && out_len && (n_dets == 0 || dets), "bad argument");
+        JpegCoefs jc;
+        jpeg_entropy_decode(jpeg, len, jc);
+        LaneLock ll(*m, true);
+        Slot& s = ll.lane->slots[0];
+        CK(cudaSetDevice(m->cfg.device));
+        const size_t fb = (size_t)jc.plan.w * jc.plan.h * 3;
+        grow_input(s, fb);
+        grow_jpeg(s, jpeg_stage_bytes(jc), jc.plan.plane_bytes);
+        FrameSrc fr{nullptr, jc.plan.w, jc.plan.h, &jc};
+        size_t ju = 0, pu = 0;
+        decode_jpeg_run(*m, s, &fr, 1, s.d_in, ju, pu);
+        std::vector<uint8_t> file;
+        annotate_on_device(*m, s, jc.plan.w, jc.plan.h, dets, n_dets, scale_w, scale_h, (int)quality, &file);
+        deliver_file(file, out, cap, out_len);
+    });
+}
+
+int uf_jpeg_write_coefficients(uint32_t w, uint32_t h, uint32_t quality, const int16_t* coefs, size_t n_blocks, uint8_t* out, size_t cap,
+                               size_t* out_len) {
+    return guarded([&] {
+        REQUIRE(coefs && out_len && w > 0 && h > 0 && w <= 16384 && h <= 16384, "bad argument");
+        const JpegPlan plan = jpeg_encode_plan(w, h, (int)quality);
+        const size_t need = ((size_t)plan.plane_w[0] * plan.plane_h[0] + 2 * (size_t)plan.plane_w[1] * plan.plane_h[1]) / 64;
+        REQUIRE(n_blocks == need, "n_blocks does not match the padded planes of a 4:2:0 frame of this size (" + std::to_string(need) + ")");
+        std::vector<uint8_t> file;
+        jpeg_write_file(plan, coefs, file);
+        deliver_file(file, out, cap, out_len);
+    });
+}
+
+int uf_jpeg_quality_tables(uint32_t quality, uint16_t* lum64, uint16_t* chr64) {
+    return guarded([&] {
+        REQUIRE(lum64 && chr64, "null argument");
+        jpeg_quality_tables((int)quality, lum64, chr64);
+    });
+}
+
+int uf_draw_boxes_rgb(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets, float scale_w,
+                      float scale_h, uint8_t* out_rgb) {
+    return guarded([&] {
+        REQUIRE(m && rgb && out_rgb && w > 0 && h > 0 && w <= 16384 && h <= 16384 && (n_dets == 0 || dets), "bad argument");
+        LaneLock ll(*m, true);
+        Slot& s = ll.lane->slots[0];
+        CK(cudaSetDevice(m->cfg.device));
+        const size_t fb = (size_t)w * h * 3;
+        grow_input(s, fb);
+        CK(cudaMemcpyAsync(s.d_in, rgb, fb, cudaMemcpyHostToDevice, s.stream));
+        annotate_on_device(*m, s, w, h, dets, n_dets, scale_w, scale_h, 0, nullptr);
+        CK(cudaMemcpyAsync(out_rgb, s.d_in, fb, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+    });
+}
+
 int uf_infer(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, uf_det* out, uint32_t cap, uint32_t* n_out) {
     const uint8_t* ptrs[1] = {rgb};
     return uf_infer_batch(m, ptrs, &w, &h, 1, out, cap, n_out);

@@ -54,6 +54,12 @@ struct JpegError {
     std::string msg;
 };
 
+// ---- encoder (N3), jpeg_encode.cc
+void jpeg_quality_tables(int quality, uint16_t lum[64], uint16_t chr[64]);   // jpeg_set_quality(q, force_baseline)
+JpegPlan jpeg_encode_plan(uint32_t w, uint32_t h, int quality);              // YCbCr 4:2:0 geometry + tables
+// coefs: quantised blocks per component plane in raster order (see jpeg_encode.cc); writes a complete JFIF file
+void jpeg_write_file(const JpegPlan& p, const int16_t* coefs, std::vector<uint8_t>& out);
+
 // Parses the headers only. Throws JpegError.
 JpegPlan jpeg_parse_header(const uint8_t* data, size_t len);
 // Parses and Huffman-decodes. Throws JpegError (UF_ERR_UNSUPPORTED: progressive / arithmetic / 12 bit / multi-scan ...;

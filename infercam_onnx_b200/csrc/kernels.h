@@ -159,6 +159,10 @@ struct JpegBatchDev {
 };
 void launch_jpeg_decode(const JpegBatchDev& b, int frames, uint32_t max_nblocks, uint32_t max_w, uint32_t max_h, cudaStream_t s);
 
+// ---- N3: rectangle overlay + JPEG encode front half (kernels_jpeg_enc.cu)
+void launch_draw_rects(uint8_t* rgb, int w, int h, const int4* d_rects, int n, cudaStream_t s);
+void launch_jpeg_encode(const uint8_t* d_rgb, const JpegPlan& plan, uint8_t* d_planes, int16_t* d_coefs, cudaStream_t s);
+
 // ---- K9-K11: threshold + sort + greedy NMS, one CTA per frame (nn.rs:109-140,198-260)
 struct PostBuffers {
     unsigned long long* sort_scratch;  // [frames][sort_cap] keys, used when candidates exceed smem

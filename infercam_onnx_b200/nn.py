@@ -170,6 +170,38 @@ class UltrafaceModel(InferModel):
         _check(_capi.load().uf_jpeg_decode_rgb(self._h, buf, len(jpeg), out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(w), C.byref(h)))
         return out
 
+    # ---- N3 (rectangles + JPEG encode; inferer.rs:38-39, 58-92)
+    @staticmethod
+    def _dets_array(dets):
+        d = np.ascontiguousarray(np.asarray(dets, np.float32).reshape(-1, 5))
+        return d, d.ctypes.data_as(C.c_void_p), len(d)
+
+    def draw_boxes(self, rgb: np.ndarray, dets, scale_w: float, scale_h: float) -> np.ndarray:
+        img = _as_rgb(rgb)
+        out = np.empty_like(img)
+        d, dp, n = self._dets_array(dets)
+        _check(_capi.load().uf_draw_boxes_rgb(self._h, img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], dp, n, scale_w, scale_h,
+                                              out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def annotate_encode_jpeg(self, frame, dets, scale_w: float, scale_h: float, quality: int = 95) -> bytes:
+        """frame: HxWx3 u8 RGB array, or the bytes of a baseline JPEG (decoded on the GPU). Returns a JPEG file."""
+        d, dp, n = self._dets_array(dets)
+        need = C.c_size_t()
+        if isinstance(frame, (bytes, bytearray)):
+            src = C.create_string_buffer(bytes(frame), len(frame))
+            info = jpeg_info(bytes(frame))
+            cap = info["w"] * info["h"] * 3 + 4096
+            out = C.create_string_buffer(cap)
+            _check(_capi.load().uf_annotate_reencode_jpeg(self._h, src, len(frame), dp, n, scale_w, scale_h, quality, out, cap, C.byref(need)))
+        else:
+            img = _as_rgb(frame)
+            cap = img.size + 4096
+            out = C.create_string_buffer(cap)
+            _check(_capi.load().uf_annotate_encode_jpeg(self._h, img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], dp, n, scale_w,
+                                                        scale_h, quality, out, cap, C.byref(need)))
+        return out.raw[: need.value]
+
     def _run_batch_raw(self, call, n: int, cap: int) -> List[np.ndarray]:
         # result arrays live in pinned host memory, one set per calling thread and (n, cap), reused from call to call:
         # the library writes detections beyond the first 128 of a frame with an asynchronous strided copy, which is only
@@ -339,6 +371,22 @@ def jpeg_coefficients(jpeg: bytes):
     d["nonzero"] = int(info.nonzero)
     d["quant"] = np.ctypeslib.as_array(info.quant).reshape(3, 64)[: d["ncomp"]].copy()
     return d, coefs
+
+
+def jpeg_write_coefficients(w: int, h: int, quality: int, coefs: np.ndarray) -> bytes:
+    """Host-only: Huffman coding + file writing of quantised 4:2:0 blocks given per padded component plane in raster order."""
+    coefs = np.ascontiguousarray(coefs, np.int16).reshape(-1, 64)
+    cap = w * h * 3 + 65536
+    out = C.create_string_buffer(cap)
+    need = C.c_size_t()
+    _check(_capi.load().uf_jpeg_write_coefficients(w, h, quality, coefs.ctypes.data_as(C.c_void_p), len(coefs), out, cap, C.byref(need)))
+    return out.raw[: need.value]
+
+
+def jpeg_quality_tables(quality: int):
+    lum, chr_ = np.zeros(64, np.uint16), np.zeros(64, np.uint16)
+    _check(_capi.load().uf_jpeg_quality_tables(quality, lum.ctypes.data_as(C.c_void_p), chr_.ctypes.data_as(C.c_void_p)))
+    return lum, chr_
 
 
 def resize_taps(src_len: int, dst_len: int):

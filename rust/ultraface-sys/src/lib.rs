@@ -192,6 +192,16 @@ extern "C" {
                               h: *mut u32) -> c_int;
     pub fn uf_jpeg_info_read(jpeg: *const u8, len: usize, out: *mut uf_jpeg_info) -> c_int;
     pub fn uf_jpeg_coefficients(jpeg: *const u8, len: usize, info: *mut uf_jpeg_info, coefs: *mut i16, cap_blocks: usize) -> c_int;
+    // overlay + JPEG encode (N3, rectangles only)
+    pub fn uf_annotate_encode_jpeg(m: *mut uf_model, rgb: *const u8, w: u32, h: u32, dets: *const uf_det, n_dets: u32, scale_w: f32,
+                                   scale_h: f32, quality: u32, out: *mut u8, cap: usize, out_len: *mut usize) -> c_int;
+    pub fn uf_annotate_reencode_jpeg(m: *mut uf_model, jpeg: *const u8, len: usize, dets: *const uf_det, n_dets: u32, scale_w: f32,
+                                     scale_h: f32, quality: u32, out: *mut u8, cap: usize, out_len: *mut usize) -> c_int;
+    pub fn uf_jpeg_write_coefficients(w: u32, h: u32, quality: u32, coefs: *const i16, n_blocks: usize, out: *mut u8, cap: usize,
+                                      out_len: *mut usize) -> c_int;
+    pub fn uf_jpeg_quality_tables(quality: u32, lum64: *mut u16, chr64: *mut u16) -> c_int;
+    pub fn uf_draw_boxes_rgb(m: *mut uf_model, rgb: *const u8, w: u32, h: u32, dets: *const uf_det, n_dets: u32, scale_w: f32,
+                             scale_h: f32, out_rgb: *mut u8) -> c_int;
     // stream batcher + router
     pub fn uf_batcher_create(cfg: *const uf_batcher_config, out: *mut *mut uf_batcher) -> c_int;
     pub fn uf_batcher_create_ex(cfg: *const uf_batcher_config, f: uf_batch_fn, user: *mut c_void, out: *mut *mut uf_batcher) -> c_int;

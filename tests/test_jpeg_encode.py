@@ -1,0 +1,120 @@
+"""N3, rectangles + JPEG encode after the path (inferer.rs:38-39, 58-92). The reference encodes with
+libjpeg-turbo (`turbojpeg::compress_image(&frame, 95, Sub2x2)`); libjpeg-turbo is in this image behind PIL, so it is the
+checker: the file PIL writes from the same pixels at the same quality must hold exactly the coefficients and tables ours
+holds. The rectangle overlay is checked against the oracle's restatement of imageproc's `draw_hollow_rect` (unpinned)."""
+import io
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from infercam_onnx_b200 import nn
+from oracle import draw as odraw
+
+
+def _pil_jpeg(arr, quality=95):
+    b = io.BytesIO()
+    Image.fromarray(arr).save(b, "JPEG", quality=quality, subsampling=2)
+    return b.getvalue()
+
+
+def _to_plane_raster(info, coefs):
+    """decode-order blocks (MCU-interleaved) -> per padded component plane, raster order (the encoder's layout)."""
+    w, h = info["w"], info["h"]
+    mx, my = (w + 15) // 16, (h + 15) // 16
+    planes = [np.zeros((my * 2, mx * 2, 64), np.int16), np.zeros((my, mx, 64), np.int16), np.zeros((my, mx, 64), np.int16)]
+    c = coefs.reshape(my, mx, 6, 64)
+    planes[0][0::2, 0::2] = c[:, :, 0]
+    planes[0][0::2, 1::2] = c[:, :, 1]
+    planes[0][1::2, 0::2] = c[:, :, 2]
+    planes[0][1::2, 1::2] = c[:, :, 3]
+    planes[1][:] = c[:, :, 4]
+    planes[2][:] = c[:, :, 5]
+    return np.concatenate([p.reshape(-1, 64) for p in planes])
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (462, 640), (301, 333), (9, 17), (16, 8), (720, 1280)])
+def test_huffman_writer_round_trips_libjpeg_turbo_files(test_pics, shape):
+    """Host half alone: decode a libjpeg-turbo file to coefficients, write them back with our Huffman coder / file writer,
+    and libjpeg-turbo must decode our file to exactly the pixels of its own (incl. frames whose last MCUs hold dummy blocks)."""
+    pic = np.ascontiguousarray(np.resize(test_pics["omar-lopez-T6zu4jFhVwg"], (*shape, 3)) if shape[0] > 462 or shape[1] > 640
+                               else test_pics["omar-lopez-T6zu4jFhVwg"][: shape[0], : shape[1]])
+    for q in (95, 60):
+        ref = _pil_jpeg(pic, q)
+        info, coefs = nn.jpeg_coefficients(ref)
+        lum, chr_ = nn.jpeg_quality_tables(q)
+        np.testing.assert_array_equal(info["quant"][0], lum)  # jpeg_set_quality scaling = libjpeg-turbo's
+        np.testing.assert_array_equal(info["quant"][1], chr_)
+        ours = nn.jpeg_write_coefficients(shape[1], shape[0], q, _to_plane_raster(info, coefs))
+        info2, coefs2 = nn.jpeg_coefficients(ours)
+        np.testing.assert_array_equal(coefs2, coefs)
+        np.testing.assert_array_equal(np.asarray(Image.open(io.BytesIO(ours)).convert("RGB")),
+                                      np.asarray(Image.open(io.BytesIO(ref)).convert("RGB")))
+        assert abs(len(ours) - len(ref)) <= 64  # same entropy-coded size, headers differ by a few bytes at most
+
+
+def _boxes():
+    return np.float32([[0.10, 0.20, 0.30, 0.60, 0.99], [0.5, 0.5, 0.5001, 0.9, 0.8],      # thin: width casts to 0 at small scales
+                       [-0.2, -0.1, 0.25, 0.3, 0.7], [0.8, 0.7, 1.4, 1.3, 0.6],              # partly outside
+                       [2.0, 2.0, 3.0, 3.0, 0.55], [0.3, 0.3, 0.2, 0.2, 0.5],                # wholly outside; inverted (skipped)
+                       [0.0, 0.0, 1.0, 1.0, 0.51]])                                          # the whole frame
+
+
+@pytest.mark.gpu
+def test_gpu_rectangles_match_the_oracle(make_onnx, test_pics):
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240))
+    try:
+        for pic, (sw, sh) in ((test_pics["omar-lopez-T6zu4jFhVwg"], (640.0, 462.0)), (test_pics["bruce-mars-ZXq7xoo98b0"], (1280.0, 720.0)),
+                              (test_pics["michael-dam-mEZ3PoFGs_k"][:100, :90], (90.0, 100.0))):
+            got = m.draw_boxes(pic, _boxes(), sw, sh)
+            np.testing.assert_array_equal(got, odraw.draw_boxes(pic, _boxes(), sw, sh))
+            assert (got != pic).any()
+        np.testing.assert_array_equal(m.draw_boxes(pic, np.zeros((0, 5), np.float32), 1.0, 1.0), pic)
+    finally:
+        m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(480, 640), (462, 640), (301, 333), (9, 17), (720, 1280)])
+def test_gpu_encoder_writes_libjpeg_turbos_coefficients(make_onnx, test_pics, shape):
+    """Colour conversion, 4:2:0 downsampling, forward DCT and quantisation on the GPU: for the same pixels and quality the
+    coefficients in our file equal the ones in libjpeg-turbo's file (PIL), so both decode to the same picture."""
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240))
+    try:
+        rng = np.random.default_rng(shape[0])
+        src = test_pics["omar-lopez-T6zu4jFhVwg"]
+        pic = np.ascontiguousarray(np.resize(src, (*shape, 3)) if shape[0] > 462 or shape[1] > 640 else src[: shape[0], : shape[1]])
+        for frame, q in ((pic, 95), (pic, 50), (rng.integers(0, 256, (*shape, 3), dtype=np.uint8), 95),
+                         (np.where(rng.random((*shape, 3)) < 0.5, 0, 255).astype(np.uint8), 100)):
+            ours = m.annotate_encode_jpeg(frame, np.zeros((0, 5), np.float32), 1.0, 1.0, quality=q)
+            ref = _pil_jpeg(frame, q)
+            ia, ca = nn.jpeg_coefficients(ours)
+            ib, cb = nn.jpeg_coefficients(ref)
+            np.testing.assert_array_equal(ia["quant"], ib["quant"])
+            np.testing.assert_array_equal(ca, cb)
+            np.testing.assert_array_equal(np.asarray(Image.open(io.BytesIO(ours)).convert("RGB")),
+                                          np.asarray(Image.open(io.BytesIO(ref)).convert("RGB")))
+    finally:
+        m.close()
+
+
+@pytest.mark.gpu
+def test_gpu_annotate_reencode_from_jpeg(make_onnx, test_pics):
+    """The production order of inferer.rs:35-39 in one call: JPEG in -> decode (GPU) -> rectangles -> encode -> JPEG out;
+    equals decoding with libjpeg-turbo, drawing with the oracle and encoding with libjpeg-turbo."""
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path)
+    try:
+        b = io.BytesIO()
+        Image.fromarray(test_pics["clarke-sanders-ybPJ47PMT_M"]).save(b, "JPEG", quality=90, subsampling=1)
+        jpeg_in = b.getvalue()
+        pixels = np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(jpeg_in)).convert("RGB")))
+        dets, counts = m.run_batch_jpeg([jpeg_in], cap=64)
+        boxes = dets[0] if len(dets[0]) else _boxes()
+        ours = m.annotate_encode_jpeg(jpeg_in, boxes, 640.0, 427.0, quality=95)
+        ref = _pil_jpeg(odraw.draw_boxes(pixels, boxes, 640.0, 427.0), 95)
+        np.testing.assert_array_equal(nn.jpeg_coefficients(ours)[1], nn.jpeg_coefficients(ref)[1])
+        np.testing.assert_array_equal(np.asarray(Image.open(io.BytesIO(ours)).convert("RGB")),
+                                      np.asarray(Image.open(io.BytesIO(ref)).convert("RGB")))
+    finally:
+        m.close()
