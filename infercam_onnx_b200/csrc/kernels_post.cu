@@ -329,7 +329,7 @@ post_kernel(float* __restrict__ scores, float* __restrict__ boxes, int K, float 
 // MCOLS columns per pass, starting at the diagonal. Persistent grid: units are dealt round-robin, frames without a
 // published candidate list cost one shared-memory read.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MCOLS, 3)
+__global__ void __launch_bounds__(MCOLS)
 nms_mask_kernel(PostBuffers pb, int K, int frames, float max_iou) {
     __shared__ float4 rows[MROWS];
     __shared__ float rarea[MROWS];
