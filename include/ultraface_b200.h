@@ -88,6 +88,7 @@ typedef struct uf_config {
 #define UF_FLAG_PDL 32u          /* launch the kernel chain with programmatic dependent launch (process-wide; measured neutral) */
 #define UF_FLAG_TMA_SIMT_PW 64u  /* fused dw+1x1 layers of the big maps: keep the 1x1 on the SIMT pipes (the pre-tcgen05 kernel) */
 #define UF_FLAG_DENSE3_TC 128u   /* dense 3x3 convs of the RFB branches as a tcgen05 implicit GEMM (zero-copy im2col; measured slower) */
+#define UF_FLAG_JPEG_HOST_HUFFMAN 512u /* uf_infer_batch_jpeg: Huffman-decode on host threads (default: on the GPU, host only for restart intervals / damaged streams) */
 #define UF_FLAG_NO_PRESTEM 256u  /* frames at exactly 2x the network size: keep resize and stem as two kernels (default: one fused kernel) */
 #define UF_FLAG_FUSE_DW_TC 16u   /* compute depthwise 3x3 inside the tensor-core GEMM's converter warps (C >= 64) */
 
@@ -200,6 +201,10 @@ typedef struct uf_jpeg_info {
 /* jpeg[i] / len[i]: one JPEG file per frame. Otherwise as uf_infer_batch. */
 UF_API int uf_infer_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, uf_det* out, uint32_t cap,
                                uint32_t* n_out);
+/* parity hook: the quantised coefficients as the DEVICE Huffman decoder produces them (same layout as uf_jpeg_coefficients);
+ * *on_device = 1 + the synchronisation rounds it took if the frame went through it, 0 if it was handed to the host decoder
+ * (restart intervals, damaged data). */
+UF_API int uf_jpeg_coefficients_gpu(uf_model* m, const uint8_t* jpeg, size_t len, int16_t* coefs, size_t cap_blocks, int32_t* on_device);
 /* parity hook: the decoded RGB8 pixels of one frame, as the GPU kernels produce them (out_rgb: w * h * 3 bytes, cap_bytes
  * its capacity; *w / *h are set even when the capacity is too small: UF_ERR_CAPACITY). */
 UF_API int uf_jpeg_decode_rgb(uf_model* m, const uint8_t* jpeg, size_t len, uint8_t* out_rgb, size_t cap_bytes, uint32_t* w,

@@ -15,6 +15,7 @@ UF_FLAG_FORCE_GENERIC, UF_FLAG_NO_GRAPH, UF_FLAG_NO_FUSION, UF_FLAG_NO_TC, UF_FL
 UF_FLAG_TMA_SIMT_PW = 64
 UF_FLAG_DENSE3_TC = 128
 UF_FLAG_NO_PRESTEM = 256
+UF_FLAG_JPEG_HOST_HUFFMAN = 512
 
 
 class uf_det(C.Structure):
@@ -97,6 +98,7 @@ SIGNATURES = {
     "uf_resize_taps": (C.c_int, [C.c_uint32, C.c_uint32, _p(C.c_int32), _p(C.c_int32), _p(C.c_float), C.c_uint32,
                                  _p(C.c_uint32)]),
     "uf_infer_batch_jpeg": (C.c_int, [C.c_void_p, _p(C.c_void_p), _p(C.c_size_t), C.c_uint32, _p(uf_det), C.c_uint32, _p(C.c_uint32)]),
+    "uf_jpeg_coefficients_gpu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _p(C.c_int32)]),
     "uf_jpeg_decode_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _p(C.c_uint32), _p(C.c_uint32)]),
     "uf_jpeg_info_read": (C.c_int, [C.c_void_p, C.c_size_t, _p(uf_jpeg_info)]),
     "uf_jpeg_coefficients": (C.c_int, [C.c_void_p, C.c_size_t, _p(uf_jpeg_info), C.c_void_p, C.c_size_t]),

@@ -133,6 +133,11 @@ struct Slot {
     size_t jpeg_cap = 0;
     uint8_t* d_planes = nullptr;
     size_t planes_cap = 0;
+    uint8_t* d_huff = nullptr;   // GPU Huffman scratch: subsequence states, block counts, dense coefficient blocks
+    size_t huff_cap = 0;
+    int* h_jstatus = nullptr;    // pinned [chunk + 1]: per frame of the stage 0 = decoded on the GPU, else redo on the host; [chunk] = round flag
+    uint32_t jstatus_n = 0;      // frames of the stage whose status is meaningful (GPU Huffman path used)
+    std::vector<uint32_t> redo;  // global frame indices the GPU Huffman path handed back (collected by harvest)
     // pending work description
     bool pending = false;
     uint32_t first = 0, n = 0;
@@ -158,6 +163,7 @@ struct Lane {
     std::vector<Slot> slots;
     float *d_scores = nullptr, *d_boxes = nullptr;  // raw outputs of the lane's last batch [max_batch][K][2|4]
     std::vector<JpegCoefs> jpeg_coefs;              // N2: Huffman-decoded frames of the call in progress (storage reused)
+    std::vector<JpegBitstream> jpeg_streams;        // N2: frames prepared for the device Huffman decoder (storage reused)
     uint32_t last_n = 0;
     uint64_t batch_id = 0;
 };
@@ -260,6 +266,7 @@ struct uf_model {
     uint64_t taps_clock = 0;
     std::atomic<uint64_t> launches{0};
     std::atomic<bool> profiling{false};
+    std::atomic<uint64_t> jpeg_redone{0};  // frames the device Huffman decoder handed back to the host decoder
     std::atomic<int> fail_after_stages{-1};  // fault injection (uf_debug_fail_after): throw after that many submits
     std::vector<KernelStat> stats;
     std::map<std::string, int> stat_index;
@@ -677,6 +684,7 @@ static void alloc_lane(uf_model& m, Lane& ln) {
         }
         CK(cudaMallocHost(&s.h_counts, (size_t)m.chunk * sizeof(int)));
         CK(cudaMallocHost(&s.h_dets, (size_t)m.chunk * DET_FAST * 5 * sizeof(float)));
+        CK(cudaMallocHost(&s.h_jstatus, ((size_t)m.chunk + 1) * sizeof(int)));
         ws += s.d_in_cap + (size_t)m.chunk * H * W * 3 + arena + (size_t)m.chunk * K * (5 + 4 + 1) * 4 +
               (size_t)m.chunk * sort_cap * 8;
         CK(cudaStreamSynchronize(s.stream));
@@ -911,6 +919,9 @@ static void harvest(uf_model& m, Slot& s, uf_det* out, uint32_t cap, uint32_t* n
     s.pending = false;
     const int K = m.K;
     uint32_t max_take = 0;
+    for (uint32_t i = 0; i < s.jstatus_n && i < s.n; ++i)
+        if (s.h_jstatus[i] != 0) s.redo.push_back(s.first + i);  // GPU Huffman declined this frame: its detections are void
+    s.jstatus_n = 0;
     for (uint32_t i = 0; i < s.n; ++i) {
         const uint32_t cnt = (uint32_t)s.h_counts[i];
         const uint32_t g = s.first + i;
@@ -1034,9 +1045,10 @@ static void run_body(uf_model& m, Lane& ln, Slot& s, const U8View& input, uint32
 }
 
 struct FrameSrc {
-    const uint8_t* p;            // RGB8 pixels in host memory, or NULL when the frame arrives as JPEG coefficients
+    const uint8_t* p;            // RGB8 pixels in host memory, or NULL when the frame arrives as JPEG
     uint32_t w, h;
-    const JpegCoefs* jc = nullptr;
+    const JpegCoefs* jc = nullptr;      // JPEG, Huffman-decoded on the host
+    const JpegBitstream* jb = nullptr;  // JPEG, to be Huffman-decoded on the GPU
 };
 
 // staging buffer for frames that need a resize; a failed re-allocation leaves the slot empty, not broken
@@ -1119,6 +1131,115 @@ static void decode_jpeg_run(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t c
     launch_jpeg_decode(b, (int)cnt, max_blocks, fr[0].w, fr[0].h, s.stream);
 }
 
+// ---- N2, Huffman decoding on the device too. Scratch per frame: 3 state arrays + 2 count arrays per subsequence, the dense blocks.
+static size_t huff_scratch_bytes(const JpegBitstream& jb) {  // (+ slack for the alignment of a run's sections)
+    return (size_t)jb.huff.nsub * (3 * 8 + 2 * 4) + (size_t)jb.plan.nblocks * 64 * sizeof(int16_t) + 512;
+}
+static size_t huff_stage_bytes(const JpegBitstream& jb) { return sizeof(JpegPlan) + sizeof(JpegHuffFrame) + jb.data.size() + 96; }
+static void grow_huff(Slot& s, size_t need) {
+    if (need <= s.huff_cap) return;
+    CK(cudaStreamSynchronize(s.stream));
+    cudaFree(s.d_huff);
+    s.d_huff = nullptr;
+    s.huff_cap = 0;
+    CK(cudaMalloc(&s.d_huff, need + need / 4));
+    s.huff_cap = need + need / 4;
+}
+
+
+struct HuffRun {
+    const JpegPlan* d_plans = nullptr;   // device: the run's plans (offs_base = first block of the frame in d_coefs)
+    const int16_t* d_coefs = nullptr;    // device: dense blocks, decode order, natural order inside a block
+    const int* d_status = nullptr;       // device: per frame, 0 = decoded to exactly its blocks
+    size_t n_blocks = 0;
+    uint32_t max_blocks = 0;
+    int rounds = 0;
+};
+
+// Entropy-decodes `cnt` prepared frames on the device, asynchronously on the slot's stream. rgb_frame_bytes: stride of the frames in the RGB destination of the later stages.
+static HuffRun huffman_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t cnt, size_t rgb_frame_bytes, size_t& jpeg_used,
+                               size_t& planes_used, size_t& huff_used) {
+    auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
+    HuffRun R;
+    size_t n_bytes = 0, n_sub = 0;
+    uint32_t max_nsub = 0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        n_bytes += a16(fr[k].jb->data.size());
+        n_sub += fr[k].jb->huff.nsub;
+        R.n_blocks += fr[k].jb->plan.nblocks;
+        max_nsub = std::max(max_nsub, fr[k].jb->huff.nsub);
+        R.max_blocks = std::max(R.max_blocks, fr[k].jb->plan.nblocks);
+    }
+    // staging (pinned = device image): [JpegPlan x cnt][JpegHuffFrame x cnt][bytes]
+    const size_t base = a16(jpeg_used);
+    const size_t o_plans = base, o_hf = a16(o_plans + cnt * sizeof(JpegPlan)), o_bytes = a16(o_hf + cnt * sizeof(JpegHuffFrame)),
+                 end = o_bytes + n_bytes;
+    if (end > s.jpeg_cap) throw CudaError("internal: JPEG staging buffer undersized");
+    // device scratch: [state A][state B][start_used][nblk][blk_base][changed + status][dense coefficient blocks]
+    const size_t hb = (huff_used + 255) / 256 * 256;
+    const size_t h_a = hb, h_b = h_a + n_sub * 8, h_su = h_b + n_sub * 8, h_nb = h_su + n_sub * 8, h_bb = h_nb + n_sub * 4,
+                 h_fl = a16(h_bb + n_sub * 4), h_co = a16(h_fl + ((size_t)cnt + 1) * 4), h_end = h_co + R.n_blocks * 64 * sizeof(int16_t);
+    if (h_end > s.huff_cap) throw CudaError("internal: GPU Huffman scratch undersized");
+    huff_used = h_end;
+    JpegPlan* plans = reinterpret_cast<JpegPlan*>(s.h_jpeg + o_plans);
+    JpegHuffFrame* hfs = reinterpret_cast<JpegHuffFrame*>(s.h_jpeg + o_hf);
+    size_t ib = 0, isub = 0, iblk = 0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const JpegBitstream& jb = *fr[k].jb;
+        JpegPlan p = jb.plan;
+        p.offs_base = (uint32_t)iblk;  // dense path: index of the frame's first block
+        p.entries_base = 0;
+        const size_t ro = (size_t)k * rgb_frame_bytes, po = planes_used;
+        p.rgb_off_lo = (uint32_t)ro; p.rgb_off_hi = (uint32_t)(ro >> 32);
+        p.planes_off_lo = (uint32_t)po; p.planes_off_hi = (uint32_t)(po >> 32);
+        planes_used += p.plane_bytes;
+        plans[k] = p;
+        JpegHuffFrame h = jb.huff;
+        h.data_off = (uint32_t)ib; h.sub_base = (uint32_t)isub; h.coef_base = (uint32_t)iblk;
+        hfs[k] = h;
+        memcpy(s.h_jpeg + o_bytes + ib, jb.data.data(), jb.data.size());
+        ib += a16(jb.data.size());
+        isub += jb.huff.nsub;
+        iblk += jb.plan.nblocks;
+    }
+    CK(cudaMemcpyAsync(s.d_jpeg + base, s.h_jpeg + base, end - base, cudaMemcpyHostToDevice, s.stream));
+    jpeg_used = end;
+    int* d_flags = reinterpret_cast<int*>(s.d_huff + h_fl);  // [1 + k] = status of frame k
+    JpegHuffBatch hbt{reinterpret_cast<const JpegHuffFrame*>(s.d_jpeg + o_hf), s.d_jpeg + o_bytes,
+                      reinterpret_cast<unsigned long long*>(s.d_huff + h_su), reinterpret_cast<uint32_t*>(s.d_huff + h_nb),
+                      reinterpret_cast<uint32_t*>(s.d_huff + h_bb), reinterpret_cast<int16_t*>(s.d_huff + h_co), d_flags + 1};
+    unsigned long long* st[2] = {reinterpret_cast<unsigned long long*>(s.d_huff + h_a), reinterpret_cast<unsigned long long*>(s.d_huff + h_b)};
+    R.d_plans = reinterpret_cast<const JpegPlan*>(s.d_jpeg + o_plans);
+    R.d_coefs = reinterpret_cast<const int16_t*>(s.d_huff + h_co);
+    R.d_status = d_flags + 1;
+    R.rounds = jhuff_rounds(max_nsub);  // after launch r the first r + 1 CTAs of a frame are exact: a fixed count, no read-back
+    ProfScope ps(m, s, "jpeg_huffman_gpu", (uint64_t)n_bytes + R.n_blocks * 128, (uint64_t)n_bytes + R.n_blocks * 128, 0, R.rounds + 3);
+    CK(cudaMemsetAsync(s.d_huff + h_fl, 0xff, ((size_t)cnt + 1) * 4, s.stream));  // status: not decoded yet
+    CK(cudaMemsetAsync(s.d_huff + h_co, 0, R.n_blocks * 64 * sizeof(int16_t), s.stream));
+    int cur = 1;
+    for (int r = 0; r < R.rounds; ++r) {
+        launch_jhuff_sync(hbt, (int)cnt, max_nsub, r == 0, st[cur], st[cur ^ 1], s.stream);
+        cur ^= 1;  // st[cur] holds the latest end states
+    }
+    launch_jhuff_finish(hbt, (int)cnt, max_nsub, st[cur], s.stream);
+    return R;
+}
+
+// `cnt` same-size JPEG frames (frames [first_in_stage, +cnt) of the stage) -> RGB8 at dst, entropy decoding included. A
+// frame that does not decode to exactly its blocks is flagged in s.h_jstatus and redone by the caller on the host decoder.
+static void decode_jpeg_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t first_in_stage, uint32_t cnt, uint8_t* dst,
+                                size_t& jpeg_used, size_t& planes_used, size_t& huff_used) {
+    const size_t fb = (size_t)fr[0].w * fr[0].h * 3;
+    const HuffRun R = huffman_run_gpu(m, s, fr, cnt, fb, jpeg_used, planes_used, huff_used);
+    if (planes_used > s.planes_cap) throw CudaError("internal: JPEG plane buffer undersized");
+    s.jstatus_n = std::max(s.jstatus_n, first_in_stage + cnt);
+    CK(cudaMemcpyAsync(s.h_jstatus + first_in_stage, R.d_status, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+    JpegBatchDev b{R.d_plans, nullptr, nullptr, s.d_planes, dst, R.d_coefs};
+    ProfScope ps(m, s, "jpeg_idct_upsample_rgb", (uint64_t)R.n_blocks * 128 + 2ull * planes_used + (uint64_t)cnt * fb,
+                 (uint64_t)R.n_blocks * 128 + (uint64_t)cnt * fb, 0, 2);
+    launch_jpeg_decode(b, (int)cnt, R.max_blocks, fr[0].w, fr[0].h, s.stream);
+}
+
 // One chunk of host frames on slot s.
 static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, uint32_t first, uint32_t n) {
     const int W = m.plan.net_w, H = m.plan.net_h;
@@ -1138,26 +1259,38 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
         all_double = prestem_supported(s.d_in, (long long)fr[0].w * fr[0].h * 3, fr[0].w, fr[0].h, W, H, t->dev);
     }
     // JPEG frames of the stage: size the staging buffers once (growing them mid-stage would strand copies in flight)
-    size_t jpeg_need = 0, planes_need = 0, jpeg_used = 0, planes_used = 0;
-    for (uint32_t k = 0; k < n; ++k)
+    size_t jpeg_need = 0, planes_need = 0, jpeg_used = 0, planes_used = 0, huff_need = 0, huff_used = 0;
+    s.jstatus_n = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        s.h_jstatus[k] = 0;
         if (fr[k].jc) {
             jpeg_need += jpeg_stage_bytes(*fr[k].jc);
             planes_need += fr[k].jc->plan.plane_bytes;
+        } else if (fr[k].jb) {
+            jpeg_need += huff_stage_bytes(*fr[k].jb);
+            planes_need += fr[k].jb->plan.plane_bytes;
+            huff_need += huff_scratch_bytes(*fr[k].jb);
         }
+    }
     if (jpeg_need) grow_jpeg(s, jpeg_need, planes_need);
+    grow_huff(s, huff_need);
     size_t off = 0;
     uint32_t i = 0;
     while (i < n) {
         // run of frames with identical size (and, for the copy, contiguous host addresses)
         uint32_t j = i + 1;
         const size_t fb = (size_t)fr[i].w * fr[i].h * 3;
-        while (j < n && fr[j].w == fr[i].w && fr[j].h == fr[i].h && (fr[j].jc != nullptr) == (fr[i].jc != nullptr)) ++j;
+        while (j < n && fr[j].w == fr[i].w && fr[j].h == fr[i].h && (fr[j].jc != nullptr) == (fr[i].jc != nullptr) &&
+               (fr[j].jb != nullptr) == (fr[i].jb != nullptr)) ++j;
         const bool ident = (int)fr[i].w == W && (int)fr[i].h == H;
         if (!ident) off = (off + 15) / 16 * 16;  // keep every run 16-byte aligned for the fast resize path
         uint8_t* dst = ident ? s.d_resized + (size_t)i * out_frame : s.d_in + off;
         uint32_t a = i;
         if (fr[i].jc) {  // JPEG: coefficients up, pixels made on the device (the runs of a stage share the staging buffer)
             decode_jpeg_run(m, s, fr + i, j - i, dst, jpeg_used, planes_used);
+            a = j;
+        } else if (fr[i].jb) {  // JPEG: the entropy-coded bytes up, Huffman decoding on the device too
+            decode_jpeg_run_gpu(m, s, fr + i, i, j - i, dst, jpeg_used, planes_used, huff_used);
             a = j;
         }
         while (a < j) {  // merge host-contiguous frames into one cudaMemcpyAsync
@@ -1219,6 +1352,8 @@ static void abandon_lane(uf_model& m, Lane& ln) {
         s.pending = false;
         s.ev_used = 0;
         s.n = 0;
+        s.jstatus_n = 0;
+        s.redo.clear();
     }
     ln.last_n = 0;
     cudaGetLastError();
@@ -1353,7 +1488,7 @@ uf_model::~uf_model() {
         for (auto& g : s.graphs) cudaGraphExecDestroy(g.second);
         cudaFree(s.d_in); cudaFree(s.d_resized); cudaFree(s.d_arena); cudaFree(s.d_dets); cudaFree(s.d_sel);
         cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort); cudaFree(s.d_big_n); cudaFree(s.d_mask);
-        cudaFreeHost(s.h_jpeg); cudaFree(s.d_jpeg); cudaFree(s.d_planes);
+        cudaFreeHost(s.h_jpeg); cudaFree(s.d_jpeg); cudaFree(s.d_planes); cudaFree(s.d_huff); cudaFreeHost(s.h_jstatus);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_dets);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -1469,19 +1604,86 @@ int uf_infer_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* l
         if (n > m->cfg.max_batch) throw ArgError(UF_ERR_CAPACITY, "batch of " + std::to_string(n) + " exceeds max_batch " + std::to_string(m->cfg.max_batch));
         LaneLock ll(*m, false);
         Lane& ln = *ll.lane;
-        std::vector<JpegCoefs>& coefs = ln.jpeg_coefs;
-        entropy_decode_all(*m, jpeg, len, n, coefs);
         std::vector<FrameSrc> fr(n);
-        for (uint32_t i = 0; i < n; ++i) fr[i] = FrameSrc{nullptr, coefs[i].plan.w, coefs[i].plan.h, &coefs[i]};
+        const bool gpu_huffman = !(m->cfg.flags & UF_FLAG_JPEG_HOST_HUFFMAN);
+        if (gpu_huffman) {
+            // host: headers, tables, byte unstuffing (a memchr pass); device: everything else
+            std::vector<JpegBitstream>& bs = ln.jpeg_streams;
+            if (bs.size() < n) bs.resize(n);
+            std::vector<JpegError> errs(n, JpegError{UF_OK, ""});
+            m->pool().parallel_for(n, [&](uint32_t i) {
+                try { jpeg_prepare_bitstream(jpeg[i], len[i], bs[i]); }
+                catch (const JpegError& e) { errs[i] = e; }
+                catch (const std::exception& e) { errs[i] = JpegError{UF_ERR_INVALID_ARG, e.what()}; }
+            });
+            for (uint32_t i = 0; i < n; ++i)
+                if (errs[i].code != UF_OK) throw JpegError{errs[i].code, "frame " + std::to_string(i) + ": " + errs[i].msg};
+            std::vector<JpegCoefs>& coefs = ln.jpeg_coefs;
+            if (coefs.size() < n) coefs.resize(n);
+            for (uint32_t i = 0; i < n; ++i) {
+                if (bs[i].gpu_ok) {
+                    fr[i] = FrameSrc{nullptr, bs[i].plan.w, bs[i].plan.h, nullptr, &bs[i]};
+                } else {  // restart intervals / markers inside the segment: the host decoder
+                    jpeg_entropy_decode(jpeg[i], len[i], coefs[i]);
+                    fr[i] = FrameSrc{nullptr, coefs[i].plan.w, coefs[i].plan.h, &coefs[i], nullptr};
+                }
+            }
+        } else {
+            std::vector<JpegCoefs>& coefs = ln.jpeg_coefs;
+            entropy_decode_all(*m, jpeg, len, n, coefs);
+            for (uint32_t i = 0; i < n; ++i) fr[i] = FrameSrc{nullptr, coefs[i].plan.w, coefs[i].plan.h, &coefs[i], nullptr};
+        }
         run_pipeline(*m, ln, n, m->host_chunk, true, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
             run_chunk_host(*m, ln, s, fr.data() + first, first, cnt);
         });
+        // frames the device decoder handed back (truncated / damaged streams): host decoder, one by one
+        std::vector<uint32_t> redo;
+        for (auto& s : ln.slots) {
+            redo.insert(redo.end(), s.redo.begin(), s.redo.end());
+            s.redo.clear();
+        }
+        for (uint32_t g : redo) {
+            JpegCoefs jc;
+            jpeg_entropy_decode(jpeg[g], len[g], jc);
+            FrameSrc one{nullptr, jc.plan.w, jc.plan.h, &jc, nullptr};
+            run_pipeline(*m, ln, 1, m->host_chunk, true, out ? out + (size_t)g * cap : nullptr, cap, n_out + g,
+                         [&](Slot& s, uint32_t first, uint32_t cnt) { run_chunk_host(*m, ln, s, &one, first, cnt); });
+        }
+        m->jpeg_redone += redo.size();
+        if (!redo.empty()) ln.last_n = 0;  // the raw-output hooks would mix two calls
     });
 }
 
 int uf_jpeg_decode_rgb(uf_model* m, const uint8_t* jpeg, size_t len, uint8_t* out_rgb, size_t cap_bytes, uint32_t* w, uint32_t* h) {
     return guarded([&] {
         REQUIRE(m && jpeg && w && h, "null argument");
+        JpegBitstream jb;
+        const bool gpu_huffman = !(m->cfg.flags & UF_FLAG_JPEG_HOST_HUFFMAN);
+        if (gpu_huffman) {
+            jpeg_prepare_bitstream(jpeg, len, jb);
+            *w = jb.plan.w;
+            *h = jb.plan.h;
+            const size_t fb = (size_t)jb.plan.w * jb.plan.h * 3;
+            if (!out_rgb || cap_bytes < fb) throw ArgError(UF_ERR_CAPACITY, "output buffer smaller than w * h * 3");
+            if (jb.gpu_ok) {
+                LaneLock ll(*m, true);
+                Slot& s = ll.lane->slots[0];
+                CK(cudaSetDevice(m->cfg.device));
+                grow_input(s, fb);
+                grow_jpeg(s, huff_stage_bytes(jb), jb.plan.plane_bytes);
+                grow_huff(s, huff_scratch_bytes(jb));
+                FrameSrc fr{nullptr, jb.plan.w, jb.plan.h, nullptr, &jb};
+                size_t ju = 0, pu = 0, hu = 0;
+                s.h_jstatus[0] = 0;
+                decode_jpeg_run_gpu(*m, s, &fr, 0, 1, s.d_in, ju, pu, hu);
+                CK(cudaMemcpyAsync(out_rgb, s.d_in, fb, cudaMemcpyDeviceToHost, s.stream));
+                CK(cudaStreamSynchronize(s.stream));
+                CK(cudaGetLastError());
+                s.jstatus_n = 0;
+                if (s.h_jstatus[0] == 0) return;
+                m->jpeg_redone++;  // damaged / truncated: the host decoder below
+            }
+        }
         JpegCoefs jc;
         jpeg_entropy_decode(jpeg, len, jc);
         *w = jc.plan.w;
@@ -1499,6 +1701,33 @@ int uf_jpeg_decode_rgb(uf_model* m, const uint8_t* jpeg, size_t len, uint8_t* ou
         CK(cudaMemcpyAsync(out_rgb, s.d_in, fb, cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaGetLastError());
+    });
+}
+
+int uf_jpeg_coefficients_gpu(uf_model* m, const uint8_t* jpeg, size_t len, int16_t* coefs, size_t cap_blocks, int32_t* on_device) {
+    return guarded([&] {
+        REQUIRE(m && jpeg && coefs && on_device, "null argument");
+        JpegBitstream jb;
+        jpeg_prepare_bitstream(jpeg, len, jb);
+        if (cap_blocks < jb.plan.nblocks) throw ArgError(UF_ERR_CAPACITY, "coefficient buffer smaller than nblocks");
+        *on_device = 0;
+        if (jb.gpu_ok) {
+            LaneLock ll(*m, true);
+            Slot& s = ll.lane->slots[0];
+            CK(cudaSetDevice(m->cfg.device));
+            grow_jpeg(s, huff_stage_bytes(jb), 0);
+            grow_huff(s, huff_scratch_bytes(jb));
+            FrameSrc fr{nullptr, jb.plan.w, jb.plan.h, nullptr, &jb};
+            size_t ju = 0, pu = 0, hu = 0;
+            const HuffRun R = huffman_run_gpu(*m, s, &fr, 1, 0, ju, pu, hu);
+            CK(cudaMemcpyAsync(coefs, R.d_coefs, (size_t)jb.plan.nblocks * 128, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(s.h_jstatus, R.d_status, 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            CK(cudaGetLastError());
+            if (s.h_jstatus[0] == 0) { *on_device = 1 + R.rounds; return; }
+        }
+        uf_jpeg_info info;
+        if (uf_jpeg_coefficients(jpeg, len, &info, coefs, cap_blocks) != UF_OK) throw ArgError(UF_ERR_INVALID_ARG, g_last_error);
     });
 }
 

@@ -54,6 +54,36 @@ struct JpegError {
     std::string msg;
 };
 
+// ---- Huffman decoding on the GPU (kernels_jpeg_huff.cu): what the host prepares per frame
+constexpr int JH_LOOK = 9;          // bits resolved by one table lookup (same as the host decoder)
+struct JpegHuffTab {                // one Huffman table in decoder form
+    uint16_t look[1 << JH_LOOK];    // (length << 8) | symbol, 0 = longer than JH_LOOK bits
+    int32_t maxcode[18];            // largest code of each length (-1: none), [17] = sentinel
+    int32_t valoff[17];             // vals index = code + valoff[length]
+    uint8_t vals[256];
+};
+struct JpegHuffFrame {              // plain data, copied to the device as is
+    JpegHuffTab dc[3], ac[3];       // per component
+    uint32_t data_off;              // byte offset of the frame's UNSTUFFED entropy-coded segment in the batch's byte buffer
+    uint32_t data_bits;             // its length in bits
+    uint32_t nsub;                  // subsequences of JH_SUBSEQ_BITS
+    uint32_t sub_base;              // index of the frame's first subsequence in the batch's state arrays
+    uint32_t coef_base;             // index of the frame's first block in the batch's dense coefficient buffer
+    uint32_t nblocks, blocks_per_mcu;
+    uint8_t slot_comp[JPEG_MAX_SLOTS];
+    uint8_t pad_[2];
+};
+constexpr uint32_t JH_SUBSEQ_BITS = 1024;  // 128 bytes per GPU thread
+constexpr uint32_t JH_MAX_SUBSEQ = 32768;   // 4 MB of entropy-coded data per frame (256 launches at most); beyond: host decoder
+struct JpegBitstream {              // one frame, host side
+    JpegPlan plan{};
+    JpegHuffFrame huff{};           // tables + geometry (offsets filled in when the batch is laid out)
+    std::vector<uint8_t> data;      // entropy-coded segment with the 0xFF00 stuffing removed, up to the first marker
+    bool gpu_ok = false;            // false: restart intervals / markers inside the segment / oversized -> host entropy decoder
+};
+// Parses the headers, derives the decoder tables, removes the byte stuffing. Throws JpegError like jpeg_entropy_decode.
+void jpeg_prepare_bitstream(const uint8_t* data, size_t len, JpegBitstream& out);
+
 // ---- encoder (N3), jpeg_encode.cc
 void jpeg_quality_tables(int quality, uint16_t lum[64], uint16_t chr[64]);   // jpeg_set_quality(q, force_baseline)
 JpegPlan jpeg_encode_plan(uint32_t w, uint32_t h, int quality);              // YCbCr 4:2:0 geometry + tables

@@ -313,6 +313,54 @@ void parse(const uint8_t* d, size_t len, Parsed& P, bool want_scan) {
 
 }  // namespace
 
+void jpeg_prepare_bitstream(const uint8_t* data, size_t len, JpegBitstream& out) {
+    Parsed P;
+    parse(data, len, P, true);
+    if (!P.dc[0].defined) P.dc[0].set(kStdDcLumBits, kStdDcVals, 12);
+    if (!P.dc[1].defined) P.dc[1].set(kStdDcChrBits, kStdDcVals, 12);
+    if (!P.ac[0].defined) P.ac[0].set(kStdAcLumBits, kStdAcLumVals, 162);
+    if (!P.ac[1].defined) P.ac[1].set(kStdAcChrBits, kStdAcChrVals, 162);
+    const JpegPlan& p = P.plan;
+    out.plan = p;
+    JpegHuffFrame& h = out.huff;
+    memset(&h, 0, sizeof(h));
+    for (uint32_t c = 0; c < p.ncomp; ++c) {
+        const HuffTable* src[2] = {&P.dc[P.td[c]], &P.ac[P.ta[c]]};
+        if (!src[0]->defined || !src[1]->defined) fail(UF_ERR_INVALID_ARG, "Huffman table not defined");
+        JpegHuffTab* dst[2] = {&h.dc[c], &h.ac[c]};
+        for (int k = 0; k < 2; ++k) {
+            static_assert(sizeof(dst[k]->look) == sizeof(src[k]->look) && JH_LOOK == LOOK, "table formats agree");
+            memcpy(dst[k]->look, src[k]->look, sizeof(dst[k]->look));
+            memcpy(dst[k]->maxcode, src[k]->maxcode, sizeof(dst[k]->maxcode));
+            memcpy(dst[k]->valoff, src[k]->valoff, sizeof(dst[k]->valoff));
+            memcpy(dst[k]->vals, src[k]->vals, sizeof(dst[k]->vals));
+        }
+    }
+    h.nblocks = p.nblocks;
+    h.blocks_per_mcu = p.blocks_per_mcu;
+    memcpy(h.slot_comp, p.slot_comp, sizeof(h.slot_comp));
+    // remove the byte stuffing; the segment ends at the first real marker
+    out.data.clear();
+    out.data.reserve(len - P.scan_start + 8);
+    const uint8_t* q = data + P.scan_start;
+    const uint8_t* end = data + len;
+    bool marker_inside = false;
+    while (q < end) {
+        const uint8_t* f = (const uint8_t*)memchr(q, 0xff, (size_t)(end - q));
+        if (!f) { out.data.insert(out.data.end(), q, end); break; }
+        out.data.insert(out.data.end(), q, f);
+        if (f + 1 >= end) break;
+        if (f[1] == 0x00) { out.data.push_back(0xff); q = f + 2; continue; }
+        if (f[1] == 0xff) { q = f + 1; continue; }  // fill byte
+        marker_inside = f[1] != 0xd9;               // EOI ends the segment; anything else (RSTn, DNL ...) is for the host decoder
+        break;
+    }
+    h.data_bits = (uint32_t)out.data.size() * 8;
+    h.nsub = (h.data_bits + JH_SUBSEQ_BITS - 1) / JH_SUBSEQ_BITS;
+    out.data.resize((out.data.size() + 15) / 16 * 16 + 16, 0);  // zero tail: the reader may look a few bytes past the end
+    out.gpu_ok = P.restart_interval == 0 && !marker_inside && h.nsub > 0 && h.nsub <= JH_MAX_SUBSEQ;
+}
+
 JpegPlan jpeg_parse_header(const uint8_t* data, size_t len) {
     Parsed P;
     parse(data, len, P, false);

@@ -156,7 +156,23 @@ struct JpegBatchDev {
     const uint32_t* entries;   // (natural index << 16 | value) of all frames (JpegPlan::entries_base)
     uint8_t* planes;           // JpegPlan::planes_off
     uint8_t* rgb;              // JpegPlan::rgb_off
+    const int16_t* dense;      // non-NULL: dense quantised blocks [JpegPlan::offs_base + block][64] (GPU Huffman path) instead of the lists
 };
+// Huffman decoding on the GPU (kernels_jpeg_huff.cu)
+struct JpegHuffFrame;
+struct JpegHuffBatch {
+    const JpegHuffFrame* frames;        // [frames]
+    const uint8_t* bytes;               // unstuffed entropy-coded segments (JpegHuffFrame::data_off)
+    unsigned long long* start_used;     // [subsequences] start state of the last decode of each subsequence
+    uint32_t* nblk;                     // [subsequences] blocks started in it
+    uint32_t* blk_base;                 // [subsequences] exclusive prefix of nblk inside the frame
+    int16_t* coefs;                     // dense blocks (JpegHuffFrame::coef_base), zeroed by the caller
+    int* status;                        // [frames] 0 = decoded to exactly its blocks
+};
+void launch_jhuff_sync(const JpegHuffBatch& b, int frames, uint32_t max_nsub, int first, const unsigned long long* in,
+                       unsigned long long* out, cudaStream_t s);
+int jhuff_rounds(uint32_t max_nsub);  // launches of launch_jhuff_sync that make every frame of the run exact
+void launch_jhuff_finish(const JpegHuffBatch& b, int frames, uint32_t max_nsub, const unsigned long long* fin, cudaStream_t s);
 void launch_jpeg_decode(const JpegBatchDev& b, int frames, uint32_t max_nblocks, uint32_t max_w, uint32_t max_h, cudaStream_t s);
 
 // ---- N3: rectangle overlay + JPEG encode front half (kernels_jpeg_enc.cu)

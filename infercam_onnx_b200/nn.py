@@ -170,6 +170,16 @@ class UltrafaceModel(InferModel):
         _check(_capi.load().uf_jpeg_decode_rgb(self._h, buf, len(jpeg), out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(w), C.byref(h)))
         return out
 
+    def jpeg_coefficients_gpu(self, jpeg: bytes):
+        """Parity hook: (coefficients [nblocks, 64] int16 as the DEVICE Huffman decoder produces them, launches): launches = 0
+        if the frame was handed to the host decoder (restart intervals, damaged data), else the synchronisation launches."""
+        info = jpeg_info(jpeg)
+        out = np.zeros((info["nblocks"], 64), np.int16)
+        on_dev = C.c_int32()
+        buf = C.create_string_buffer(bytes(jpeg), len(jpeg))
+        _check(_capi.load().uf_jpeg_coefficients_gpu(self._h, buf, len(jpeg), out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(on_dev)))
+        return out, max(on_dev.value - 1, 0) if on_dev.value else 0
+
     # ---- N3 (rectangles + JPEG encode; inferer.rs:38-39, 58-92)
     @staticmethod
     def _dets_array(dets):

@@ -188,6 +188,7 @@ extern "C" {
     // JPEG in front of the path (N2)
     pub fn uf_infer_batch_jpeg(m: *mut uf_model, jpeg: *const *const u8, len: *const usize, n: u32, out: *mut uf_det, cap: u32,
                                n_out: *mut u32) -> c_int;
+    pub fn uf_jpeg_coefficients_gpu(m: *mut uf_model, jpeg: *const u8, len: usize, coefs: *mut i16, cap_blocks: usize, on_device: *mut i32) -> c_int;
     pub fn uf_jpeg_decode_rgb(m: *mut uf_model, jpeg: *const u8, len: usize, out_rgb: *mut u8, cap_bytes: usize, w: *mut u32,
                               h: *mut u32) -> c_int;
     pub fn uf_jpeg_info_read(jpeg: *const u8, len: usize, out: *mut uf_jpeg_info) -> c_int;

@@ -1,0 +1,105 @@
+// huff_sim.cc — CPU-only test helper (never part of the library): steps the synchronisation rounds of the device Huffman
+// decoder (infercam_onnx_b200/csrc/kernels_jpeg_huff.cu) serially on the host, running the SAME symbol-level decoder
+// (jpeg_huff_core.h), so that the round logic — guessed states, fixed point, block prefix, write pass, DC scan, status —
+// can be checked against the sequential decoder without a GPU. Mirrors the kernels one to one; "thread t" is a loop index.
+#include <cstring>
+#include <vector>
+
+#include "../../infercam_onnx_b200/csrc/jpeg_decode.h"
+#include "../../infercam_onnx_b200/csrc/jpeg_huff_core.h"
+
+using namespace uf;
+using namespace uf::jh;
+
+extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t cap_blocks, int* rounds, int* status, int max_rounds) {
+    JpegBitstream jb;
+    try {
+        jpeg_prepare_bitstream(jpeg, len, jb);
+    } catch (const JpegError& e) {
+        return -e.code;
+    }
+    if (!jb.gpu_ok) return 1;
+    if (cap_blocks < jb.plan.nblocks) return 2;
+    const JpegHuffFrame& fr = jb.huff;
+    Tabs* tabs = new Tabs;
+    memcpy(tabs, &fr.dc[0], sizeof(Tabs));
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(jb.data.data());
+    const uint32_t n = fr.nsub;
+    std::vector<unsigned long long> in(n), out(n), start_used(n);
+    std::vector<uint32_t> nblk(n), base(n);
+    constexpr uint32_t JHT = 128;  // as the kernel
+    int iters_max = 0;
+    auto launch = [&](bool first) {  // one jhuff_sync_kernel launch: CTAs in any order, they only read `in` of the launch before
+        for (uint32_t t0 = 0; t0 < n; t0 += JHT) {
+            const uint32_t lanes = std::min(JHT, n - t0);
+            const unsigned long long cta_start = t0 == 0 ? 0ull : (first ? pack_state(t0 * JH_SUBSEQ_BITS, 0, 0) : in[t0 - 1]);
+            if (!first && cta_start == start_used[t0]) {
+                for (uint32_t i = 0; i < lanes; ++i) out[t0 + i] = in[t0 + i];
+                continue;
+            }
+            unsigned long long my_start[JHT], my_end[JHT], s_end[JHT];
+            uint32_t my_n[JHT];
+            bool dirty[JHT];
+            for (uint32_t i = 0; i < JHT; ++i) {
+                my_start[i] = ~0ull; my_end[i] = 0; my_n[i] = 0; dirty[i] = false;
+                if (first) my_end[i] = pack_state((t0 + i + 1) * JH_SUBSEQ_BITS, 0, 0);
+                else if (i < lanes) { my_start[i] = start_used[t0 + i]; my_end[i] = in[t0 + i]; }
+                s_end[i] = my_end[i];
+            }
+            for (int iter = 0; iter <= (int)JHT; ++iter) {
+                bool any = false, ch[JHT];
+                for (uint32_t i = 0; i < JHT; ++i) {  // "threads", all reading the state of before this iteration
+                    ch[i] = false;
+                    const unsigned long long ns = i == 0 ? cta_start : s_end[i - 1];
+                    if (i < lanes && ns != my_start[i]) {
+                        uint32_t p = (uint32_t)(ns >> 32), slot = (uint32_t)(ns >> 8) & 0xff, k = (uint32_t)ns & 0xff;
+                        if (slot >= fr.blocks_per_mcu) slot = 0;
+                        const uint32_t p_end = std::min((t0 + i + 1) * JH_SUBSEQ_BITS, fr.data_bits);
+                        my_n[i] = huff_run<false>(*tabs, fr, d, p, slot, k, p_end, nullptr, 0);
+                        my_end[i] = pack_state(p, slot, k);
+                        my_start[i] = ns;
+                        ch[i] = dirty[i] = true;
+                        any = true;
+                    }
+                }
+                // (the loop above read s_end[i - 1] after iteration-local writes would have happened on a GPU only past the barrier:
+                //  here ch[] delays the writes)
+                for (uint32_t i = 0; i < JHT; ++i)
+                    if (ch[i]) s_end[i] = my_end[i];
+                iters_max = std::max(iters_max, iter + 1);
+                if (!any) break;
+            }
+            for (uint32_t i = 0; i < lanes; ++i) {
+                out[t0 + i] = my_end[i];
+                if (dirty[i]) { start_used[t0 + i] = my_start[i]; nblk[t0 + i] = my_n[i]; }
+            }
+        }
+        in.swap(out);
+    };
+    *rounds = (int)((n + JHT - 1) / JHT);
+    for (int r = 0; r < *rounds; ++r) launch(r == 0);
+    (void)max_rounds;
+    *rounds = *rounds * 1000 + iters_max;  // launches * 1000 + the most in-CTA iterations any CTA took
+    const bool settled = true;
+    *status = 1;
+    if (settled) {
+        uint32_t acc = 0;
+        for (uint32_t t = 0; t < n; ++t) { base[t] = acc; acc += nblk[t]; }
+        memset(coefs, 0, (size_t)jb.plan.nblocks * 128);
+        for (uint32_t t = 0; t < n; ++t) {
+            const unsigned long long start = t == 0 ? 0ull : in[t - 1];
+            uint32_t p = (uint32_t)(start >> 32), slot = (uint32_t)(start >> 8) & 0xff, k = (uint32_t)start & 0xff;
+            const uint32_t p_end = std::min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits);
+            const uint32_t c = huff_run<true>(*tabs, fr, d, p, slot, k, p_end, coefs, base[t]);
+            if (t == n - 1) *status = (base[t] + c == fr.nblocks && k == 0) ? 0 : 1;
+        }
+        int pred[3] = {0, 0, 0};
+        for (uint32_t b = 0; b < fr.nblocks; ++b) {
+            const int c = fr.slot_comp[b % fr.blocks_per_mcu];
+            pred[c] += coefs[(size_t)b * 64];
+            coefs[(size_t)b * 64] = (int16_t)pred[c];
+        }
+    }
+    delete tabs;
+    return 0;
+}

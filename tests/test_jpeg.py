@@ -150,3 +150,129 @@ def test_gpu_jpeg_batch_equals_rgb_batch_of_the_same_pixels(make_onnx, test_pics
         assert ca == cj[:5]
     finally:
         m.close()
+
+
+# ---- Huffman decoding on the device (kernels_jpeg_huff.cu) ----
+def _damaged(data, rng, n):
+    """n variants of one file: a flipped bit, a cut with EOI appended, three overwritten bytes — all inside the scan."""
+    sos = data.index(b"\xff\xda") + 14
+    out = []
+    for t in range(n):
+        e = bytearray(data)
+        pos = int(rng.integers(sos, len(e) - 4))
+        if t % 3 == 0:
+            e[pos] ^= 1 << int(rng.integers(0, 8))
+        elif t % 3 == 1:
+            e = e[:pos] + b"\xff\xd9"
+        else:
+            e[pos:pos + 3] = bytes(rng.integers(0, 256, 3).tolist())
+        out.append(bytes(e))
+    return out
+
+
+def test_huffman_synchronisation_rounds_on_the_host(test_pics, tmp_path):
+    """The device decoder's round logic (guessed start states, in-CTA fixed point, one CTA of progress per launch, block
+    prefix, write pass, DC scan, the status that sends a frame back to the host decoder), stepped serially on the CPU by
+    tests/helpers/huff_sim.cc over the SAME symbol decoder the kernels compile (csrc/jpeg_huff_core.h), must reproduce the
+    sequential decoder on intact files, and on damaged ones either reproduce it or decline (status != 0)."""
+    import ctypes as C
+    import pathlib
+    import subprocess
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    so = tmp_path / "huff_sim.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", f"-I{root / 'include'}", "-o", str(so),
+                    str(root / "tests/helpers/huff_sim.cc"), str(root / "infercam_onnx_b200/csrc/jpeg_entropy.cc")], check=True)
+    lib = C.CDLL(str(so))
+    lib.huff_sim.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+
+    def sim(data):
+        info, ref = nn.jpeg_coefficients(data)
+        out = np.zeros_like(ref)
+        r, st = C.c_int(), C.c_int()
+        rc = lib.huff_sim(data, len(data), out.ctypes.data, out.shape[0], C.byref(r), C.byref(st), 0)
+        return rc, st.value, np.array_equal(out, ref), r.value
+
+    for name, data in _cases(test_pics):
+        rc, st, eq, r = sim(data)
+        if name.startswith("restart"):
+            assert rc == 1, name  # not for the device decoder
+        else:
+            assert (rc, st, eq) == (0, 0, True), (name, rc, st, eq, r)
+    rng = np.random.default_rng(5)
+    pic = test_pics["omar-lopez-T6zu4jFhVwg"][:240, :320]
+    declined = 0
+    for ss in (0, 1, 2):
+        for e in _damaged(_enc(pic, 75, ss), rng, 60):
+            rc, st, eq, _ = sim(e)
+            assert rc in (0, 1)
+            if rc == 0 and st == 0:
+                assert eq
+            else:
+                declined += 1
+    assert declined > 30  # every truncated file at least
+
+
+@pytest.mark.gpu
+def test_gpu_huffman_coefficients_equal_the_sequential_decoder(make_onnx, test_pics):
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240))
+    try:
+        rng = np.random.default_rng(2)
+        cases = _cases(test_pics)
+        big = np.asarray(Image.fromarray(test_pics["omar-lopez-T6zu4jFhVwg"]).resize((1920, 1080), Image.BICUBIC)).astype(np.int16)
+        big = (big + rng.integers(-10, 10, big.shape)).clip(0, 255).astype(np.uint8)
+        cases.append(("1080p 4:2:0", _enc(big, 90, 2)))
+        cases.append(("1080p 4:2:2 q100", _enc(big, 100, 1)))
+        for name, data in cases:
+            _, ref = nn.jpeg_coefficients(data)
+            got, launches = m.jpeg_coefficients_gpu(data)
+            np.testing.assert_array_equal(got, ref, err_msg=name)
+            assert (launches == 0) == name.startswith("restart"), (name, launches)
+        pic = test_pics["omar-lopez-T6zu4jFhVwg"][:240, :320]
+        on_device = 0
+        for ss in (0, 1, 2):
+            for e in _damaged(_enc(pic, 75, ss), rng, 30):
+                _, ref = nn.jpeg_coefficients(e)
+                got, launches = m.jpeg_coefficients_gpu(e)
+                np.testing.assert_array_equal(got, ref)
+                on_device += launches > 0
+                np.testing.assert_array_equal(m.jpeg_decode_rgb(e), _turbo_lenient(e, m))
+        assert on_device > 10  # flipped bits usually still decode to whole blocks: those stay on the device
+    finally:
+        m.close()
+
+
+def _turbo_lenient(data, m):
+    """Pixels for a damaged file: PIL refuses some of them, so the checker is the host-Huffman path of the same library
+    (itself pinned to libjpeg-turbo on intact and truncated files above)."""
+    info, coefs = nn.jpeg_coefficients(data)
+    return ojpeg.reconstruct(coefs, info["w"], info["h"], info["hs"], info["vs"], info["quant"])
+
+
+@pytest.mark.gpu
+def test_gpu_huffman_batch_equals_host_huffman_batch(make_onnx, test_pics):
+    """A mixed batch — sizes, samplings, a restart-interval frame, truncated and bit-flipped frames in the middle — gives the
+    same detections whether the entropy decoding runs on the device (default) or on host threads (UF_FLAG_JPEG_HOST_HUFFMAN)."""
+    from infercam_onnx_b200 import _capi
+
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    rng = np.random.default_rng(8)
+    pics = list(test_pics.values())
+    jpegs = [_enc(rng.integers(0, 256, (480, 640, 3), dtype=np.uint8), 92, 1) for _ in range(9)]
+    jpegs += [_enc(p, 88, 2) for p in pics] + [_enc(pics[1][:301, :333], 70, 1)]
+    jpegs[4:4] = _damaged(jpegs[0], rng, 3)          # same size as their neighbours: inside a run
+    jpegs += _damaged(_enc(pics[2], 80, 2), rng, 3)
+    jpegs += [d for n, d in _cases(test_pics) if n.startswith("restart")]
+    res = []
+    for flags in (0, _capi.UF_FLAG_JPEG_HOST_HUFFMAN):
+        m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=48, host_chunk=8, flags=flags)
+        try:
+            res.append(m.run_batch_jpeg(jpegs, cap=256))
+            again = m.run_batch_jpeg(jpegs[:6], cap=256)   # storage reuse across calls
+            assert again[1] == res[-1][1][:6]
+        finally:
+            m.close()
+    assert res[0][1] == res[1][1]
+    assert sum(res[0][1]) > 0
+    for a, b in zip(res[0][0], res[1][0]):
+        np.testing.assert_array_equal(a, b)
