@@ -253,7 +253,7 @@ struct uf_model {
     std::string onnx_path;
     Plan plan;
     int K = 0;
-    uint32_t chunk = 0, host_chunk = 0, nslots = 0;
+    uint32_t chunk = 0, host_chunk = 0, jpeg_chunk = 0, nslots = 0;
     std::vector<Step> steps;
     std::vector<size_t> w_off, b_off;  // per plan op, floats into d_weights
     float* d_weights = nullptr;
@@ -1135,7 +1135,10 @@ static void decode_jpeg_run(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t c
 static size_t huff_scratch_bytes(const JpegBitstream& jb) {  // (+ slack for the alignment of a run's sections)
     return (size_t)jb.huff.nsub * (3 * 8 + 2 * 4) + (size_t)jb.plan.nblocks * 64 * sizeof(int16_t) + 512;
 }
-static size_t huff_stage_bytes(const JpegBitstream& jb) { return sizeof(JpegPlan) + sizeof(JpegHuffFrame) + jb.data.size() + 96; }
+// (staging: a frame may bring its own table set — frames of one camera share one, but the bound cannot assume it)
+static size_t huff_stage_bytes(const JpegBitstream& jb) {
+    return sizeof(JpegPlan) + sizeof(JpegHuffFrame) + sizeof(JpegHuffTabSet) + jb.data.size() + 96;
+}
 static void grow_huff(Slot& s, size_t need) {
     if (need <= s.huff_cap) return;
     CK(cudaStreamSynchronize(s.stream));
@@ -1170,20 +1173,31 @@ static HuffRun huffman_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_
         max_nsub = std::max(max_nsub, fr[k].jb->huff.nsub);
         R.max_blocks = std::max(R.max_blocks, fr[k].jb->plan.nblocks);
     }
-    // staging (pinned = device image): [JpegPlan x cnt][JpegHuffFrame x cnt][bytes]
+    // the run's distinct table sets (normally one: every frame of a camera carries the same DHT, or none)
+    std::vector<uint32_t> set_of(cnt);
+    std::vector<const JpegHuffKey*> keys;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        uint32_t u = 0;
+        while (u < keys.size() && !(*keys[u] == fr[k].jb->key)) ++u;
+        if (u == keys.size()) keys.push_back(&fr[k].jb->key);
+        set_of[k] = u;
+    }
+    // staging (pinned = device image): [JpegPlan x cnt][JpegHuffFrame x cnt][JpegHuffTabSet x distinct][bytes]
     const size_t base = a16(jpeg_used);
-    const size_t o_plans = base, o_hf = a16(o_plans + cnt * sizeof(JpegPlan)), o_bytes = a16(o_hf + cnt * sizeof(JpegHuffFrame)),
-                 end = o_bytes + n_bytes;
+    const size_t o_plans = base, o_hf = a16(o_plans + cnt * sizeof(JpegPlan)), o_ts = a16(o_hf + cnt * sizeof(JpegHuffFrame)),
+                 o_bytes = a16(o_ts + keys.size() * sizeof(JpegHuffTabSet)), end = o_bytes + n_bytes;
     if (end > s.jpeg_cap) throw CudaError("internal: JPEG staging buffer undersized");
-    // device scratch: [state A][state B][start_used][nblk][blk_base][changed + status][dense coefficient blocks]
+    // device scratch: [state A][state B][start_used][nblk][status][dense coefficient blocks]
     const size_t hb = (huff_used + 255) / 256 * 256;
-    const size_t h_a = hb, h_b = h_a + n_sub * 8, h_su = h_b + n_sub * 8, h_nb = h_su + n_sub * 8, h_bb = h_nb + n_sub * 4,
-                 h_fl = a16(h_bb + n_sub * 4), h_co = a16(h_fl + ((size_t)cnt + 1) * 4), h_end = h_co + R.n_blocks * 64 * sizeof(int16_t);
+    const size_t h_a = hb, h_b = h_a + n_sub * 8, h_su = h_b + n_sub * 8, h_nb = h_su + n_sub * 8,
+                 h_fl = a16(h_nb + n_sub * 4), h_co = a16(h_fl + ((size_t)cnt + 1) * 4), h_end = h_co + R.n_blocks * 64 * sizeof(int16_t);
     if (h_end > s.huff_cap) throw CudaError("internal: GPU Huffman scratch undersized");
     huff_used = h_end;
     JpegPlan* plans = reinterpret_cast<JpegPlan*>(s.h_jpeg + o_plans);
     JpegHuffFrame* hfs = reinterpret_cast<JpegHuffFrame*>(s.h_jpeg + o_hf);
+    for (size_t u = 0; u < keys.size(); ++u) jpeg_build_tabset(*keys[u], reinterpret_cast<JpegHuffTabSet*>(s.h_jpeg + o_ts)[u]);
     size_t ib = 0, isub = 0, iblk = 0;
+    std::vector<size_t> byte_off(cnt);
     for (uint32_t k = 0; k < cnt; ++k) {
         const JpegBitstream& jb = *fr[k].jb;
         JpegPlan p = jb.plan;
@@ -1195,26 +1209,28 @@ static HuffRun huffman_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_
         planes_used += p.plane_bytes;
         plans[k] = p;
         JpegHuffFrame h = jb.huff;
-        h.data_off = (uint32_t)ib; h.sub_base = (uint32_t)isub; h.coef_base = (uint32_t)iblk;
+        h.tabset = set_of[k]; h.data_off = (uint32_t)ib; h.sub_base = (uint32_t)isub; h.coef_base = (uint32_t)iblk;
         hfs[k] = h;
-        memcpy(s.h_jpeg + o_bytes + ib, jb.data.data(), jb.data.size());
+        byte_off[k] = o_bytes + ib;
         ib += a16(jb.data.size());
         isub += jb.huff.nsub;
         iblk += jb.plan.nblocks;
     }
+    m.pool().parallel_for(cnt, [&](uint32_t k) { memcpy(s.h_jpeg + byte_off[k], fr[k].jb->data.data(), fr[k].jb->data.size()); });
     CK(cudaMemcpyAsync(s.d_jpeg + base, s.h_jpeg + base, end - base, cudaMemcpyHostToDevice, s.stream));
     jpeg_used = end;
     int* d_flags = reinterpret_cast<int*>(s.d_huff + h_fl);  // [1 + k] = status of frame k
-    JpegHuffBatch hbt{reinterpret_cast<const JpegHuffFrame*>(s.d_jpeg + o_hf), s.d_jpeg + o_bytes,
+    JpegHuffBatch hbt{reinterpret_cast<const JpegHuffFrame*>(s.d_jpeg + o_hf), reinterpret_cast<const JpegHuffTabSet*>(s.d_jpeg + o_ts),
+                      s.d_jpeg + o_bytes,
                       reinterpret_cast<unsigned long long*>(s.d_huff + h_su), reinterpret_cast<uint32_t*>(s.d_huff + h_nb),
-                      reinterpret_cast<uint32_t*>(s.d_huff + h_bb), reinterpret_cast<int16_t*>(s.d_huff + h_co), d_flags + 1};
+                      reinterpret_cast<int16_t*>(s.d_huff + h_co), d_flags + 1};
     unsigned long long* st[2] = {reinterpret_cast<unsigned long long*>(s.d_huff + h_a), reinterpret_cast<unsigned long long*>(s.d_huff + h_b)};
     R.d_plans = reinterpret_cast<const JpegPlan*>(s.d_jpeg + o_plans);
     R.d_coefs = reinterpret_cast<const int16_t*>(s.d_huff + h_co);
     R.d_status = d_flags + 1;
-    R.rounds = jhuff_rounds(max_nsub);  // after launch r the first r + 1 CTAs of a frame are exact: a fixed count, no read-back
-    ProfScope ps(m, s, "jpeg_huffman_gpu", (uint64_t)n_bytes + R.n_blocks * 128, (uint64_t)n_bytes + R.n_blocks * 128, 0, R.rounds + 3);
-    CK(cudaMemsetAsync(s.d_huff + h_fl, 0xff, ((size_t)cnt + 1) * 4, s.stream));  // status: not decoded yet
+    R.rounds = jhuff_rounds(max_nsub);  // a fixed count, no read-back: the write pass verifies the result
+    ProfScope ps(m, s, "jpeg_huffman_gpu", (uint64_t)n_bytes + R.n_blocks * 128, (uint64_t)n_bytes + R.n_blocks * 128, 0, R.rounds + 2);
+    CK(cudaMemsetAsync(s.d_huff + h_fl, 0, ((size_t)cnt + 1) * 4, s.stream));  // status
     CK(cudaMemsetAsync(s.d_huff + h_co, 0, R.n_blocks * 64 * sizeof(int16_t), s.stream));
     int cur = 1;
     for (int r = 0; r < R.rounds; ++r) {
@@ -1449,6 +1465,8 @@ static uf_model* load_model(const uf_config& cfg_in) {
     m->chunk = chunk;
     m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint64_t)cfg.net_w * cfg.net_h <= 320 * 240 ? 64 : 16));
     if (cfg.host_chunk) m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, cfg.host_chunk));
+    m->jpeg_chunk = std::max(m->host_chunk, std::min<uint32_t>(chunk, 128));
+    if (const char* e = getenv("UF_JPEG_CHUNK")) m->jpeg_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint32_t)atoi(e)));  // tuning knob
     uint32_t nslots = cfg.slots ? cfg.slots : 4;
     const uint32_t nchunks = (cfg.max_batch + m->host_chunk - 1) / m->host_chunk;
     m->nslots = std::max<uint32_t>(1, std::min(nslots, nchunks));
@@ -1633,7 +1651,8 @@ int uf_infer_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* l
             entropy_decode_all(*m, jpeg, len, n, coefs);
             for (uint32_t i = 0; i < n; ++i) fr[i] = FrameSrc{nullptr, coefs[i].plan.w, coefs[i].plan.h, &coefs[i], nullptr};
         }
-        run_pipeline(*m, ln, n, m->host_chunk, true, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
+        // (compressed frames are small: the stage can be as large as one for device-resident input, which fills the GPU better)
+        run_pipeline(*m, ln, n, gpu_huffman ? m->jpeg_chunk : m->host_chunk, true, out, cap, n_out, [&](Slot& s, uint32_t first, uint32_t cnt) {
             run_chunk_host(*m, ln, s, fr.data() + first, first, cnt);
         });
         // frames the device decoder handed back (truncated / damaged streams): host decoder, one by one

@@ -54,33 +54,48 @@ struct JpegError {
     std::string msg;
 };
 
-// ---- Huffman decoding on the GPU (kernels_jpeg_huff.cu): what the host prepares per frame
-constexpr int JH_LOOK = 9;          // bits resolved by one table lookup (same as the host decoder)
-struct JpegHuffTab {                // one Huffman table in decoder form
-    uint16_t look[1 << JH_LOOK];    // (length << 8) | symbol, 0 = longer than JH_LOOK bits
-    int32_t maxcode[18];            // largest code of each length (-1: none), [17] = sentinel
+// ---- Huffman decoding on the GPU (kernels_jpeg_huff.cu): what the host prepares
+constexpr int JH_LOOK = 10;         // bits resolved by one table lookup on the device
+// One Huffman table in the device decoder's form. A look entry says everything the decoder's loop needs about a symbol:
+//   bits 0-4   bits to consume: code length + magnitude bits
+//   bits 5-11  how far the coefficient index moves: run + 1 for a coefficient, 16 for ZRL, 64 for EOB (= block done), 1 for DC
+//   bits 12-15 magnitude bits (0: no value follows — EOB, ZRL, or a zero DC difference)
+// 0 = the code is longer than JH_LOOK bits (lim / valoff / vals resolve it).
+struct JpegHuffTab {
+    uint16_t look[1 << JH_LOOK];
+    uint32_t lim[17];               // [l]: 16-bit left-aligned windows below it hold a code of <= l bits (lengths without codes repeat)
     int32_t valoff[17];             // vals index = code + valoff[length]
     uint8_t vals[256];
 };
+struct JpegHuffTabSet {             // the tables of a frame, per component; frames with the same DHT content share one
+    JpegHuffTab dc[3], ac[3];
+};
+struct JpegHuffKey {                // what a table set is built from (and compared by): the DHT content as the frame uses it
+    uint8_t bits[6][16];            // dc of component 0..2, ac of component 0..2
+    uint8_t vals[6][256];
+    bool operator==(const JpegHuffKey& o) const;
+};
 struct JpegHuffFrame {              // plain data, copied to the device as is
-    JpegHuffTab dc[3], ac[3];       // per component
+    uint32_t tabset;                // index of the frame's table set in the batch
     uint32_t data_off;              // byte offset of the frame's UNSTUFFED entropy-coded segment in the batch's byte buffer
     uint32_t data_bits;             // its length in bits
     uint32_t nsub;                  // subsequences of JH_SUBSEQ_BITS
     uint32_t sub_base;              // index of the frame's first subsequence in the batch's state arrays
     uint32_t coef_base;             // index of the frame's first block in the batch's dense coefficient buffer
     uint32_t nblocks, blocks_per_mcu;
-    uint8_t slot_comp[JPEG_MAX_SLOTS];
-    uint8_t pad_[2];
+    uint32_t slotmap;               // 2 bits per block slot of the MCU: its component
+    uint32_t pad_[3];
 };
-constexpr uint32_t JH_SUBSEQ_BITS = 1024;  // 128 bytes per GPU thread
-constexpr uint32_t JH_MAX_SUBSEQ = 32768;   // 4 MB of entropy-coded data per frame (256 launches at most); beyond: host decoder
+constexpr uint32_t JH_SUBSEQ_BITS = 256;    // bits per GPU thread: short, so that a frame is thousands of threads and a pass is brief
+constexpr uint32_t JH_MAX_SUBSEQ = 1u << 17;  // beyond (4 MB of entropy-coded data): host decoder
 struct JpegBitstream {              // one frame, host side
     JpegPlan plan{};
-    JpegHuffFrame huff{};           // tables + geometry (offsets filled in when the batch is laid out)
+    JpegHuffFrame huff{};           // geometry (offsets and the table set index are filled in when the batch is laid out)
+    JpegHuffKey key{};
     std::vector<uint8_t> data;      // entropy-coded segment with the 0xFF00 stuffing removed, up to the first marker
     bool gpu_ok = false;            // false: restart intervals / markers inside the segment / oversized -> host entropy decoder
 };
+void jpeg_build_tabset(const JpegHuffKey& key, JpegHuffTabSet& out);
 // Parses the headers, derives the decoder tables, removes the byte stuffing. Throws JpegError like jpeg_entropy_decode.
 void jpeg_prepare_bitstream(const uint8_t* data, size_t len, JpegBitstream& out);
 

@@ -313,6 +313,39 @@ void parse(const uint8_t* d, size_t len, Parsed& P, bool want_scan) {
 
 }  // namespace
 
+bool JpegHuffKey::operator==(const JpegHuffKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+
+// The device decoder's tables (jpeg_decode.h: JpegHuffTab) from the DHT content. `dc`: the symbol is a size category.
+static void build_device_table(const uint8_t bits[16], const uint8_t vals[256], bool dc, JpegHuffTab& T) {
+    memset(&T, 0, sizeof(T));
+    memcpy(T.vals, vals, 256);
+    auto entry = [&](int len, int sym) -> uint16_t {
+        const int s = sym & 15, r = sym >> 4;
+        const int kadv = dc ? 1 : (s ? r + 1 : (r == 15 ? 16 : 64));
+        return (uint16_t)((len + s) | (kadv << 5) | (s << 12));
+    };
+    int code = 0, k = 0;
+    T.lim[0] = 0;
+    for (int l = 1; l <= 16; ++l) {
+        T.valoff[l] = k - code;
+        for (int i = 0; i < bits[l - 1]; ++i, ++k, ++code) {
+            if (l <= JH_LOOK && k < 256) {
+                const int first = code << (JH_LOOK - l);
+                for (int f = 0; f < (1 << (JH_LOOK - l)) && first + f < (1 << JH_LOOK); ++f) T.look[first + f] = entry(l, vals[k]);
+            }
+        }
+        T.lim[l] = bits[l - 1] ? (uint32_t)code << (16 - l) : T.lim[l - 1];
+        code <<= 1;
+    }
+}
+
+void jpeg_build_tabset(const JpegHuffKey& key, JpegHuffTabSet& out) {
+    for (int c = 0; c < 3; ++c) {
+        build_device_table(key.bits[c], key.vals[c], true, out.dc[c]);
+        build_device_table(key.bits[3 + c], key.vals[3 + c], false, out.ac[c]);
+    }
+}
+
 void jpeg_prepare_bitstream(const uint8_t* data, size_t len, JpegBitstream& out) {
     Parsed P;
     parse(data, len, P, true);
@@ -324,21 +357,18 @@ void jpeg_prepare_bitstream(const uint8_t* data, size_t len, JpegBitstream& out)
     out.plan = p;
     JpegHuffFrame& h = out.huff;
     memset(&h, 0, sizeof(h));
+    memset(&out.key, 0, sizeof(out.key));
     for (uint32_t c = 0; c < p.ncomp; ++c) {
         const HuffTable* src[2] = {&P.dc[P.td[c]], &P.ac[P.ta[c]]};
         if (!src[0]->defined || !src[1]->defined) fail(UF_ERR_INVALID_ARG, "Huffman table not defined");
-        JpegHuffTab* dst[2] = {&h.dc[c], &h.ac[c]};
         for (int k = 0; k < 2; ++k) {
-            static_assert(sizeof(dst[k]->look) == sizeof(src[k]->look) && JH_LOOK == LOOK, "table formats agree");
-            memcpy(dst[k]->look, src[k]->look, sizeof(dst[k]->look));
-            memcpy(dst[k]->maxcode, src[k]->maxcode, sizeof(dst[k]->maxcode));
-            memcpy(dst[k]->valoff, src[k]->valoff, sizeof(dst[k]->valoff));
-            memcpy(dst[k]->vals, src[k]->vals, sizeof(dst[k]->vals));
+            memcpy(out.key.bits[3 * k + c], src[k]->bits, 16);
+            memcpy(out.key.vals[3 * k + c], src[k]->vals, 256);
         }
     }
     h.nblocks = p.nblocks;
     h.blocks_per_mcu = p.blocks_per_mcu;
-    memcpy(h.slot_comp, p.slot_comp, sizeof(h.slot_comp));
+    for (uint32_t sl = 0; sl < (uint32_t)JPEG_MAX_SLOTS; ++sl) h.slotmap |= (uint32_t)(p.slot_comp[sl] & 3u) << (2 * sl);
     // remove the byte stuffing; the segment ends at the first real marker
     out.data.clear();
     out.data.reserve(len - P.scan_start + 8);
@@ -357,7 +387,7 @@ void jpeg_prepare_bitstream(const uint8_t* data, size_t len, JpegBitstream& out)
     }
     h.data_bits = (uint32_t)out.data.size() * 8;
     h.nsub = (h.data_bits + JH_SUBSEQ_BITS - 1) / JH_SUBSEQ_BITS;
-    out.data.resize((out.data.size() + 15) / 16 * 16 + 16, 0);  // zero tail: the reader may look a few bytes past the end
+    out.data.resize((out.data.size() + 15) / 16 * 16 + 32, 0);  // zero tail: the reader fetches up to 5 words past the end
     out.gpu_ok = P.restart_interval == 0 && !marker_inside && h.nsub > 0 && h.nsub <= JH_MAX_SUBSEQ;
 }
 

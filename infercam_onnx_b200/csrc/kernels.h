@@ -160,14 +160,15 @@ struct JpegBatchDev {
 };
 // Huffman decoding on the GPU (kernels_jpeg_huff.cu)
 struct JpegHuffFrame;
+struct JpegHuffTabSet;
 struct JpegHuffBatch {
     const JpegHuffFrame* frames;        // [frames]
+    const JpegHuffTabSet* tabsets;      // the batch's distinct table sets (JpegHuffFrame::tabset)
     const uint8_t* bytes;               // unstuffed entropy-coded segments (JpegHuffFrame::data_off)
     unsigned long long* start_used;     // [subsequences] start state of the last decode of each subsequence
     uint32_t* nblk;                     // [subsequences] blocks started in it
-    uint32_t* blk_base;                 // [subsequences] exclusive prefix of nblk inside the frame
     int16_t* coefs;                     // dense blocks (JpegHuffFrame::coef_base), zeroed by the caller
-    int* status;                        // [frames] 0 = decoded to exactly its blocks
+    int* status;                        // [frames] zeroed by the caller; stays 0 = settled and decoded to exactly its blocks
 };
 void launch_jhuff_sync(const JpegHuffBatch& b, int frames, uint32_t max_nsub, int first, const unsigned long long* in,
                        unsigned long long* out, cudaStream_t s);

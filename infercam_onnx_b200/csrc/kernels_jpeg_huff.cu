@@ -24,12 +24,32 @@ using namespace jh;
 
 namespace {
 
-constexpr int JHT = 128;  // threads per CTA (one subsequence each)
+constexpr int JHT = 256;         // threads per CTA (one subsequence each): a CTA spans 8 KB of the stream
+constexpr int JH_MAX_ROUNDS = 3;  // launches of the synchronisation kernel (see jhuff_sync_kernel)
 
-__device__ __forceinline__ void load_tabs(Tabs& tabs, const JpegHuffFrame& fr) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&fr.dc[0]);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&tabs);
-    for (int i = threadIdx.x; i < (int)(sizeof(Tabs) / 4); i += JHT) dst[i] = src[i];
+__constant__ uint8_t c_zigzag[80] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
+                                     6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31,
+                                     39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+
+__device__ __forceinline__ void load_tabs(Tabs& tabs, const JpegHuffTabSet& set) {
+    static_assert(sizeof(JpegHuffTabSet) % 16 == 0, "copied as uint4");
+    const uint4* src = reinterpret_cast<const uint4*>(&set);
+    uint4* dst = reinterpret_cast<uint4*>(&tabs.set);
+    for (int i = threadIdx.x; i < (int)(sizeof(JpegHuffTabSet) / 16); i += JHT) dst[i] = src[i];
+    if (threadIdx.x < 80) tabs.zz[threadIdx.x] = c_zigzag[threadIdx.x];
+}
+
+// sum over the CTA, the same value in every thread (blockDim.x = JHT)
+__device__ __forceinline__ uint32_t cta_sum(uint32_t v, uint32_t* s_part) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < JHT / 32; ++w) t += s_part[w];
+    __syncthreads();
+    return t;
 }
 
 }  // namespace
@@ -38,18 +58,21 @@ __device__ __forceinline__ void load_tabs(Tabs& tabs, const JpegHuffFrame& fr) {
 // one another: thread i restarts from the end state thread i-1 reached, until no start state changes (<= JHT iterations;
 // in practice a handful, a decoder started in a wrong state falls into step with the true one within a few dozen symbols).
 // What a CTA cannot know is the end state of the CTA before it: that comes from the previous launch (`in`), so after launch
-// r the first r+1 CTAs of every frame are exact, and ceil(nsub / JHT) launches make the whole frame the sequential decode —
-// a fixed number, no flag to read back, nothing for the host to wait on. A CTA whose incoming state did not change since
-// its last run copies its end states and leaves.
+// r the first r+1 CTAs of every frame are exact, and ceil(nsub / JHT) launches would make any frame the sequential decode.
+// In practice launch 1 already hands every CTA the true state (the CTA before it fell into step long before its end), so
+// min(ceil(nsub / JHT), JH_MAX_ROUNDS) launches are made — a fixed number, no flag to read back, nothing for the host to
+// wait on — and the write pass CHECKS the fixed point (every thread's start state is its predecessor's end state); a frame
+// that fails the check is handed to the host decoder like any other the device declines. A CTA whose incoming state did
+// not change since its last run copies its end states and leaves.
 __global__ void __launch_bounds__(JHT)
 jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out) {
-    __shared__ Tabs tabs;
+    __shared__ __align__(16) Tabs tabs;
     __shared__ unsigned long long s_end[JHT];
     const JpegHuffFrame& fr = b.frames[blockIdx.y];
-    const uint32_t t0 = blockIdx.x * JHT;
-    if (t0 >= fr.nsub) return;
+    const uint32_t nsub = fr.nsub, t0 = blockIdx.x * JHT;
+    if (t0 >= nsub) return;
     const uint32_t t = t0 + threadIdx.x;
-    const bool active = t < fr.nsub;
+    const bool active = t < nsub;
     const size_t gi = (size_t)fr.sub_base + t;
     const unsigned long long cta_start =
         blockIdx.x == 0 ? 0ull : (first ? pack_state(t0 * JH_SUBSEQ_BITS, 0, 0) : in[(size_t)fr.sub_base + t0 - 1]);
@@ -57,7 +80,7 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
         if (active) out[gi] = in[gi];
         return;
     }
-    load_tabs(tabs, fr);
+    load_tabs(tabs, b.tabsets[fr.tabset]);
     unsigned long long my_start = ~0ull, my_end = 0;
     uint32_t my_n = 0;
     bool dirty = false;
@@ -70,14 +93,14 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
     s_end[threadIdx.x] = my_end;
     __syncthreads();
     const uint32_t* data = reinterpret_cast<const uint32_t*>(b.bytes + fr.data_off);
-    const uint32_t p_end = min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits);
+    const uint32_t p_end = min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits), bpm = fr.blocks_per_mcu, slotmap = fr.slotmap;
     for (int iter = 0; iter <= JHT; ++iter) {
         const unsigned long long ns = threadIdx.x == 0 ? cta_start : s_end[threadIdx.x - 1];
         bool ch = false;
         if (active && ns != my_start) {
             uint32_t p = (uint32_t)(ns >> 32), slot = (uint32_t)(ns >> 8) & 0xff, k = (uint32_t)ns & 0xff;
-            if (slot >= fr.blocks_per_mcu) slot = 0;
-            my_n = huff_run<false>(tabs, fr, data, p, slot, k, p_end, nullptr, 0);
+            if (slot >= bpm) slot = 0;
+            my_n = huff_run<false>(tabs, slotmap, bpm, 0, data, p, slot, k, p_end, nullptr, 0);
             my_end = pack_state(p, slot, k);
             my_start = ns;
             ch = dirty = true;
@@ -95,91 +118,95 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
     }
 }
 
-// exclusive prefix sum of the blocks started per subsequence, one CTA per frame
-__global__ void __launch_bounds__(256)
-jhuff_scan_kernel(JpegHuffBatch b) {
-    __shared__ uint32_t part[256];
-    const JpegHuffFrame& fr = b.frames[blockIdx.x];
-    const uint32_t n = fr.nsub, per = (n + 255) / 256, t0 = threadIdx.x * per, t1 = min(t0 + per, n);
-    uint32_t s = 0;
-    for (uint32_t t = t0; t < t1; ++t) s += b.nblk[fr.sub_base + t];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int i = 0; i < 256; ++i) { const uint32_t v = part[i]; part[i] = acc; acc += v; }
-    }
-    __syncthreads();
-    uint32_t acc = part[threadIdx.x];
-    for (uint32_t t = t0; t < t1; ++t) {
-        b.blk_base[fr.sub_base + t] = acc;
-        acc += b.nblk[fr.sub_base + t];
-    }
-}
-
-// second pass: every subsequence again, from its settled start state, writing the coefficients
+// Second pass: every subsequence again, from its settled start state, writing the coefficients. The index of a thread's
+// first block = the blocks started by every subsequence before it: summed over the CTAs before this one, scanned inside.
 __global__ void __launch_bounds__(JHT)
 jhuff_write_kernel(JpegHuffBatch b, const unsigned long long* __restrict__ fin) {
-    __shared__ Tabs tabs;
+    __shared__ __align__(16) Tabs tabs;
+    __shared__ uint32_t s_part[JHT / 32], s_warp[JHT / 32];
     const JpegHuffFrame& fr = b.frames[blockIdx.y];
-    if (blockIdx.x * JHT >= fr.nsub) return;
-    load_tabs(tabs, fr);
+    const uint32_t nsub = fr.nsub, t0 = blockIdx.x * JHT;
+    if (t0 >= nsub) return;
+    load_tabs(tabs, b.tabsets[fr.tabset]);
+    const uint32_t* nblk = b.nblk + fr.sub_base;
+    uint32_t before = 0;
+    for (uint32_t u = threadIdx.x; u < t0; u += JHT) before += nblk[u];
+    before = cta_sum(before, s_part);  // (also the barrier after load_tabs)
+    const uint32_t t = t0 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool active = t < nsub;
+    const uint32_t mine = active ? nblk[t] : 0;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    const uint32_t t = blockIdx.x * JHT + threadIdx.x;
-    if (t >= fr.nsub) return;
+    uint32_t base = before + incl - mine;
+    for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+    if (!active) return;
     const size_t gi = (size_t)fr.sub_base + t;
     const unsigned long long start = t == 0 ? 0ull : fin[gi - 1];
+    if (start != b.start_used[gi]) atomicOr(b.status + blockIdx.y, 2);  // not the fixed point: the frame is not settled
     uint32_t p = (uint32_t)(start >> 32), slot = (uint32_t)(start >> 8) & 0xff, k = (uint32_t)start & 0xff;
-    const uint32_t p_end = min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits);
-    const uint32_t base = b.blk_base[gi];
-    const uint32_t n = huff_run<true>(tabs, fr, reinterpret_cast<const uint32_t*>(b.bytes + fr.data_off), p, slot, k, p_end,
-                                      b.coefs + (size_t)fr.coef_base * 64, base);
-    if (t == fr.nsub - 1)  // the frame decoded to exactly its blocks, ending on a block boundary: else the host decoder takes it
-        b.status[blockIdx.y] = (base + n == fr.nblocks && k == 0) ? 0 : 1;
+    if (slot >= fr.blocks_per_mcu) slot = 0;
+    const uint32_t p_end = min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits), nblocks = fr.nblocks;
+    const uint32_t n = huff_run<true>(tabs, fr.slotmap, fr.blocks_per_mcu, nblocks, reinterpret_cast<const uint32_t*>(b.bytes + fr.data_off),
+                                      p, slot, k, p_end, b.coefs + (size_t)fr.coef_base * 64, base);
+    if (t == nsub - 1 && !(base + n == nblocks && k == 0))  // not exactly the frame's blocks, ending on a block boundary
+        atomicOr(b.status + blockIdx.y, 1);
 }
 
-// DC differences -> DC values: per component a running sum over its blocks in decode order (JCOEF wraps at 16 bits)
-__global__ void __launch_bounds__(96)
+// DC differences -> DC values: per component a running sum over its blocks in decode order (the predictor is an int, the
+// stored JCOEF its low 16 bits). One CTA per (frame, component): a contiguous piece per thread, summed, scanned, re-walked.
+__global__ void __launch_bounds__(JHT)
 jhuff_dc_kernel(JpegHuffBatch b) {
+    __shared__ uint32_t s_slots[JPEG_MAX_SLOTS], s_cnt;
+    __shared__ int s_warp[JHT / 32];
     const JpegHuffFrame& fr = b.frames[blockIdx.x];
-    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t slots[JPEG_MAX_SLOTS], cnt = 0;
-    for (uint32_t s = 0; s < fr.blocks_per_mcu; ++s)
-        if (fr.slot_comp[s] == c) slots[cnt++] = s;
+    const uint32_t c = blockIdx.y, bpm = fr.blocks_per_mcu;
+    if (threadIdx.x == 0) {
+        uint32_t cnt = 0;
+        for (uint32_t s = 0; s < bpm; ++s)
+            if (((fr.slotmap >> (2 * s)) & 3u) == c) s_slots[cnt++] = s;
+        s_cnt = cnt;
+    }
+    __syncthreads();
+    const uint32_t cnt = s_cnt;
     if (cnt == 0) return;
-    const uint32_t total = fr.nblocks / fr.blocks_per_mcu * cnt;
+    const uint32_t total = fr.nblocks / bpm * cnt, per = (total + JHT - 1) / JHT;
+    const uint32_t i0 = min(threadIdx.x * per, total), i1 = min(i0 + per, total);
     int16_t* coefs = b.coefs + (size_t)fr.coef_base * 64;
-    int carry = 0;
-    constexpr int U = 4;  // chunks of 32 blocks whose loads are issued together (only the carry is serial)
-    for (uint32_t i0 = 0; i0 < total; i0 += 32 * U) {
-        size_t idx[U];
-        int v[U];
+    auto at = [&](uint32_t i) -> size_t {
+        const uint32_t mcu = i / cnt;
+        return ((size_t)mcu * bpm + s_slots[i - mcu * cnt]) * 64;
+    };
+    int sum = 0;
+    for (uint32_t i = i0; i < i1; ++i) sum += coefs[at(i)];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t i = i0 + u * 32 + lane;
-            idx[u] = 0;
-            v[u] = 0;
-            if (i < total) {
-                const uint32_t mcu = i / cnt, j = i - mcu * cnt;
-                uint32_t sl = slots[0];
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int run = incl - sum;
+    for (uint32_t w = 0; w < warp; ++w) run += s_warp[w];
+    for (uint32_t i = i0; i < i1; i += 8) {  // loads of a group first: a store in between would order them
+        size_t idx[8];
+        int v[8];
 #pragma unroll
-                for (int q = 1; q < JPEG_MAX_SLOTS; ++q)
-                    if ((uint32_t)q == j) sl = slots[q];
-                idx[u] = ((size_t)mcu * fr.blocks_per_mcu + sl) * 64;
-                v[u] = coefs[idx[u]];
-            }
+        for (int u = 0; u < 8; ++u) {
+            idx[u] = i + u < i1 ? at(i + u) : 0;
+            v[u] = i + u < i1 ? coefs[idx[u]] : 0;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            int x = v[u];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            x += carry;
-            if (i0 + u * 32 + lane < total) coefs[idx[u]] = (int16_t)x;
-            carry = __shfl_sync(0xffffffffu, x, 31);
+        for (int u = 0; u < 8; ++u) {
+            run += v[u];
+            if (i + u < i1) coefs[idx[u]] = (int16_t)run;
         }
     }
 }
@@ -189,12 +216,11 @@ void launch_jhuff_sync(const JpegHuffBatch& b, int frames, uint32_t max_nsub, in
     jhuff_sync_kernel<<<dim3((max_nsub + JHT - 1) / JHT, frames), JHT, 0, s>>>(b, first, in, out);
 }
 
-int jhuff_rounds(uint32_t max_nsub) { return (int)((max_nsub + JHT - 1) / JHT); }
+int jhuff_rounds(uint32_t max_nsub) { return (int)min((max_nsub + JHT - 1) / JHT, (uint32_t)JH_MAX_ROUNDS); }
 
 void launch_jhuff_finish(const JpegHuffBatch& b, int frames, uint32_t max_nsub, const unsigned long long* fin, cudaStream_t s) {
-    jhuff_scan_kernel<<<frames, 256, 0, s>>>(b);
     jhuff_write_kernel<<<dim3((max_nsub + JHT - 1) / JHT, frames), JHT, 0, s>>>(b, fin);
-    jhuff_dc_kernel<<<frames, 96, 0, s>>>(b);
+    jhuff_dc_kernel<<<dim3(frames, 3), JHT, 0, s>>>(b);
 }
 
 }  // namespace uf

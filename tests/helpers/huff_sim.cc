@@ -22,12 +22,14 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
     if (cap_blocks < jb.plan.nblocks) return 2;
     const JpegHuffFrame& fr = jb.huff;
     Tabs* tabs = new Tabs;
-    memcpy(tabs, &fr.dc[0], sizeof(Tabs));
+    jpeg_build_tabset(jb.key, tabs->set);
+    for (int i = 0; i < 80; ++i) tabs->zz[i] = zigzag_natural(i);
+    const uint32_t slotmap = fr.slotmap, bpm = fr.blocks_per_mcu;
     const uint32_t* d = reinterpret_cast<const uint32_t*>(jb.data.data());
     const uint32_t n = fr.nsub;
     std::vector<unsigned long long> in(n), out(n), start_used(n);
     std::vector<uint32_t> nblk(n), base(n);
-    constexpr uint32_t JHT = 128;  // as the kernel
+    constexpr uint32_t JHT = 256;  // as the kernel
     int iters_max = 0;
     auto launch = [&](bool first) {  // one jhuff_sync_kernel launch: CTAs in any order, they only read `in` of the launch before
         for (uint32_t t0 = 0; t0 < n; t0 += JHT) {
@@ -55,7 +57,7 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
                         uint32_t p = (uint32_t)(ns >> 32), slot = (uint32_t)(ns >> 8) & 0xff, k = (uint32_t)ns & 0xff;
                         if (slot >= fr.blocks_per_mcu) slot = 0;
                         const uint32_t p_end = std::min((t0 + i + 1) * JH_SUBSEQ_BITS, fr.data_bits);
-                        my_n[i] = huff_run<false>(*tabs, fr, d, p, slot, k, p_end, nullptr, 0);
+                        my_n[i] = huff_run<false>(*tabs, slotmap, bpm, 0, d, p, slot, k, p_end, nullptr, 0);
                         my_end[i] = pack_state(p, slot, k);
                         my_start[i] = ns;
                         ch[i] = dirty[i] = true;
@@ -76,26 +78,27 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
         }
         in.swap(out);
     };
-    *rounds = (int)((n + JHT - 1) / JHT);
+    *rounds = (int)std::min<uint32_t>((n + JHT - 1) / JHT, max_rounds > 0 ? (uint32_t)max_rounds : 3u);  // JH_MAX_ROUNDS
     for (int r = 0; r < *rounds; ++r) launch(r == 0);
-    (void)max_rounds;
     *rounds = *rounds * 1000 + iters_max;  // launches * 1000 + the most in-CTA iterations any CTA took
     const bool settled = true;
-    *status = 1;
+    *status = 0;
     if (settled) {
         uint32_t acc = 0;
         for (uint32_t t = 0; t < n; ++t) { base[t] = acc; acc += nblk[t]; }
         memset(coefs, 0, (size_t)jb.plan.nblocks * 128);
         for (uint32_t t = 0; t < n; ++t) {
             const unsigned long long start = t == 0 ? 0ull : in[t - 1];
+            if (start != start_used[t]) *status |= 2;
             uint32_t p = (uint32_t)(start >> 32), slot = (uint32_t)(start >> 8) & 0xff, k = (uint32_t)start & 0xff;
+            if (slot >= bpm) slot = 0;
             const uint32_t p_end = std::min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits);
-            const uint32_t c = huff_run<true>(*tabs, fr, d, p, slot, k, p_end, coefs, base[t]);
-            if (t == n - 1) *status = (base[t] + c == fr.nblocks && k == 0) ? 0 : 1;
+            const uint32_t c = huff_run<true>(*tabs, slotmap, bpm, fr.nblocks, d, p, slot, k, p_end, coefs, base[t]);
+            if (t == n - 1 && !(base[t] + c == fr.nblocks && k == 0)) *status |= 1;
         }
         int pred[3] = {0, 0, 0};
         for (uint32_t b = 0; b < fr.nblocks; ++b) {
-            const int c = fr.slot_comp[b % fr.blocks_per_mcu];
+            const int c = (int)((fr.slotmap >> (2 * (b % fr.blocks_per_mcu))) & 3u);
             pred[c] += coefs[(size_t)b * 64];
             coefs[(size_t)b * 64] = (int16_t)pred[c];
         }
