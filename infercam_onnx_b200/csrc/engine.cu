@@ -1132,8 +1132,9 @@ static void decode_jpeg_run(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t c
 }
 
 // ---- N2, Huffman decoding on the device too. Scratch per frame: 3 state arrays + 2 count arrays per subsequence, the dense blocks.
+static size_t huff_ent_cap(const JpegBitstream& jb) { return (size_t)jb.huff.data_bits / 2 + 16; }
 static size_t huff_scratch_bytes(const JpegBitstream& jb) {  // (+ slack for the alignment of a run's sections)
-    return (size_t)jb.huff.nsub * (3 * 8 + 2 * 4) + (size_t)jb.plan.nblocks * 64 * sizeof(int16_t) + 512;
+    return (size_t)jb.huff.nsub * (3 * 8 + 4) + ((size_t)jb.plan.nblocks + 1) * (4 + 2) + huff_ent_cap(jb) * 4 + 1024;
 }
 // (staging: a frame may bring its own table set — frames of one camera share one, but the bound cannot assume it)
 static size_t huff_stage_bytes(const JpegBitstream& jb) {
@@ -1152,7 +1153,9 @@ static void grow_huff(Slot& s, size_t need) {
 
 struct HuffRun {
     const JpegPlan* d_plans = nullptr;   // device: the run's plans (offs_base = first block of the frame in d_coefs)
-    const int16_t* d_coefs = nullptr;    // device: dense blocks, decode order, natural order inside a block
+    const uint32_t* d_offs = nullptr;    // device: per frame nblocks + 1 block offsets into its AC entries
+    const uint32_t* d_entries = nullptr; // device: AC entries (natural index << 16 | value)
+    const int16_t* d_dcv = nullptr;      // device: DC values
     const int* d_status = nullptr;       // device: per frame, 0 = decoded to exactly its blocks
     size_t n_blocks = 0;
     uint32_t max_blocks = 0;
@@ -1164,11 +1167,12 @@ static HuffRun huffman_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_
                                size_t& planes_used, size_t& huff_used) {
     auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
     HuffRun R;
-    size_t n_bytes = 0, n_sub = 0;
+    size_t n_bytes = 0, n_sub = 0, n_ent = 0;
     uint32_t max_nsub = 0;
     for (uint32_t k = 0; k < cnt; ++k) {
         n_bytes += a16(fr[k].jb->data.size());
         n_sub += fr[k].jb->huff.nsub;
+        n_ent += huff_ent_cap(*fr[k].jb);
         R.n_blocks += fr[k].jb->plan.nblocks;
         max_nsub = std::max(max_nsub, fr[k].jb->huff.nsub);
         R.max_blocks = std::max(R.max_blocks, fr[k].jb->plan.nblocks);
@@ -1187,34 +1191,38 @@ static HuffRun huffman_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_
     const size_t o_plans = base, o_hf = a16(o_plans + cnt * sizeof(JpegPlan)), o_ts = a16(o_hf + cnt * sizeof(JpegHuffFrame)),
                  o_bytes = a16(o_ts + keys.size() * sizeof(JpegHuffTabSet)), end = o_bytes + n_bytes;
     if (end > s.jpeg_cap) throw CudaError("internal: JPEG staging buffer undersized");
-    // device scratch: [state A][state B][start_used][nblk][status][dense coefficient blocks]
+    // device scratch: [state A][state B][start_used][counts][status][block offsets][DC][AC entries]
     const size_t hb = (huff_used + 255) / 256 * 256;
-    const size_t h_a = hb, h_b = h_a + n_sub * 8, h_su = h_b + n_sub * 8, h_nb = h_su + n_sub * 8,
-                 h_fl = a16(h_nb + n_sub * 4), h_co = a16(h_fl + ((size_t)cnt + 1) * 4), h_end = h_co + R.n_blocks * 64 * sizeof(int16_t);
+    const size_t h_a = hb, h_b = h_a + n_sub * 8, h_su = h_b + n_sub * 8, h_nb = h_su + n_sub * 8, h_fl = a16(h_nb + n_sub * 4),
+                 h_of = a16(h_fl + ((size_t)cnt + 1) * 4), h_dc = a16(h_of + (R.n_blocks + cnt) * 4), h_en = a16(h_dc + (R.n_blocks + cnt) * 2),
+                 h_end = h_en + n_ent * 4;
     if (h_end > s.huff_cap) throw CudaError("internal: GPU Huffman scratch undersized");
+    if (n_ent >= (1ull << 32) || R.n_blocks + cnt >= (1ull << 32)) throw CudaError("internal: JPEG run too large for 32-bit indices");
     huff_used = h_end;
     JpegPlan* plans = reinterpret_cast<JpegPlan*>(s.h_jpeg + o_plans);
     JpegHuffFrame* hfs = reinterpret_cast<JpegHuffFrame*>(s.h_jpeg + o_hf);
     for (size_t u = 0; u < keys.size(); ++u) jpeg_build_tabset(*keys[u], reinterpret_cast<JpegHuffTabSet*>(s.h_jpeg + o_ts)[u]);
-    size_t ib = 0, isub = 0, iblk = 0;
+    size_t ib = 0, isub = 0, iblk = 0, ient = 0;
     std::vector<size_t> byte_off(cnt);
     for (uint32_t k = 0; k < cnt; ++k) {
         const JpegBitstream& jb = *fr[k].jb;
         JpegPlan p = jb.plan;
-        p.offs_base = (uint32_t)iblk;  // dense path: index of the frame's first block
-        p.entries_base = 0;
+        p.offs_base = (uint32_t)(iblk + k);  // (nblocks + 1 offsets per frame)
+        p.entries_base = (uint32_t)ient;
         const size_t ro = (size_t)k * rgb_frame_bytes, po = planes_used;
         p.rgb_off_lo = (uint32_t)ro; p.rgb_off_hi = (uint32_t)(ro >> 32);
         p.planes_off_lo = (uint32_t)po; p.planes_off_hi = (uint32_t)(po >> 32);
         planes_used += p.plane_bytes;
         plans[k] = p;
         JpegHuffFrame h = jb.huff;
-        h.tabset = set_of[k]; h.data_off = (uint32_t)ib; h.sub_base = (uint32_t)isub; h.coef_base = (uint32_t)iblk;
+        h.tabset = set_of[k]; h.data_off = (uint32_t)ib; h.sub_base = (uint32_t)isub;
+        h.offs_base = (uint32_t)(iblk + k); h.ent_base = (uint32_t)ient; h.ent_cap = (uint32_t)huff_ent_cap(jb);
         hfs[k] = h;
         byte_off[k] = o_bytes + ib;
         ib += a16(jb.data.size());
         isub += jb.huff.nsub;
         iblk += jb.plan.nblocks;
+        ient += huff_ent_cap(jb);
     }
     m.pool().parallel_for(cnt, [&](uint32_t k) { memcpy(s.h_jpeg + byte_off[k], fr[k].jb->data.data(), fr[k].jb->data.size()); });
     CK(cudaMemcpyAsync(s.d_jpeg + base, s.h_jpeg + base, end - base, cudaMemcpyHostToDevice, s.stream));
@@ -1223,15 +1231,17 @@ static HuffRun huffman_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_
     JpegHuffBatch hbt{reinterpret_cast<const JpegHuffFrame*>(s.d_jpeg + o_hf), reinterpret_cast<const JpegHuffTabSet*>(s.d_jpeg + o_ts),
                       s.d_jpeg + o_bytes,
                       reinterpret_cast<unsigned long long*>(s.d_huff + h_su), reinterpret_cast<uint32_t*>(s.d_huff + h_nb),
-                      reinterpret_cast<int16_t*>(s.d_huff + h_co), d_flags + 1};
+                      reinterpret_cast<uint32_t*>(s.d_huff + h_of), reinterpret_cast<uint32_t*>(s.d_huff + h_en),
+                      reinterpret_cast<int16_t*>(s.d_huff + h_dc), d_flags + 1};
     unsigned long long* st[2] = {reinterpret_cast<unsigned long long*>(s.d_huff + h_a), reinterpret_cast<unsigned long long*>(s.d_huff + h_b)};
     R.d_plans = reinterpret_cast<const JpegPlan*>(s.d_jpeg + o_plans);
-    R.d_coefs = reinterpret_cast<const int16_t*>(s.d_huff + h_co);
+    R.d_offs = reinterpret_cast<const uint32_t*>(s.d_huff + h_of);
+    R.d_entries = reinterpret_cast<const uint32_t*>(s.d_huff + h_en);
+    R.d_dcv = reinterpret_cast<const int16_t*>(s.d_huff + h_dc);
     R.d_status = d_flags + 1;
     R.rounds = jhuff_rounds(max_nsub);  // a fixed count, no read-back: the write pass verifies the result
-    ProfScope ps(m, s, "jpeg_huffman_gpu", (uint64_t)n_bytes + R.n_blocks * 128, (uint64_t)n_bytes + R.n_blocks * 128, 0, R.rounds + 2);
+    ProfScope ps(m, s, "jpeg_huffman_gpu", 2 * (uint64_t)n_bytes + R.n_blocks * 8, (uint64_t)n_bytes + R.n_blocks * 6, 0, R.rounds + 2);
     CK(cudaMemsetAsync(s.d_huff + h_fl, 0, ((size_t)cnt + 1) * 4, s.stream));  // status
-    CK(cudaMemsetAsync(s.d_huff + h_co, 0, R.n_blocks * 64 * sizeof(int16_t), s.stream));
     int cur = 1;
     for (int r = 0; r < R.rounds; ++r) {
         launch_jhuff_sync(hbt, (int)cnt, max_nsub, r == 0, st[cur], st[cur ^ 1], s.stream);
@@ -1250,9 +1260,9 @@ static void decode_jpeg_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32
     if (planes_used > s.planes_cap) throw CudaError("internal: JPEG plane buffer undersized");
     s.jstatus_n = std::max(s.jstatus_n, first_in_stage + cnt);
     CK(cudaMemcpyAsync(s.h_jstatus + first_in_stage, R.d_status, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s.stream));
-    JpegBatchDev b{R.d_plans, nullptr, nullptr, s.d_planes, dst, R.d_coefs};
-    ProfScope ps(m, s, "jpeg_idct_upsample_rgb", (uint64_t)R.n_blocks * 128 + 2ull * planes_used + (uint64_t)cnt * fb,
-                 (uint64_t)R.n_blocks * 128 + (uint64_t)cnt * fb, 0, 2);
+    JpegBatchDev b{R.d_plans, R.d_offs, R.d_entries, s.d_planes, dst, R.d_dcv, R.d_status};
+    ProfScope ps(m, s, "jpeg_idct_upsample_rgb", (uint64_t)R.n_blocks * 16 + 2ull * planes_used + (uint64_t)cnt * fb,
+                 (uint64_t)R.n_blocks * 16 + (uint64_t)cnt * fb, 0, 2);
     launch_jpeg_decode(b, (int)cnt, R.max_blocks, fr[0].w, fr[0].h, s.stream);
 }
 
@@ -1739,11 +1749,27 @@ int uf_jpeg_coefficients_gpu(uf_model* m, const uint8_t* jpeg, size_t len, int16
             FrameSrc fr{nullptr, jb.plan.w, jb.plan.h, nullptr, &jb};
             size_t ju = 0, pu = 0, hu = 0;
             const HuffRun R = huffman_run_gpu(*m, s, &fr, 1, 0, ju, pu, hu);
-            CK(cudaMemcpyAsync(coefs, R.d_coefs, (size_t)jb.plan.nblocks * 128, cudaMemcpyDeviceToHost, s.stream));
+            const uint32_t nb = jb.plan.nblocks;
+            std::vector<uint32_t> offs((size_t)nb + 1);
+            std::vector<int16_t> dcv(nb);
+            CK(cudaMemcpyAsync(offs.data(), R.d_offs, offs.size() * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(dcv.data(), R.d_dcv, dcv.size() * 2, cudaMemcpyDeviceToHost, s.stream));
             CK(cudaMemcpyAsync(s.h_jstatus, R.d_status, 4, cudaMemcpyDeviceToHost, s.stream));
             CK(cudaStreamSynchronize(s.stream));
             CK(cudaGetLastError());
-            if (s.h_jstatus[0] == 0) { *on_device = 1 + R.rounds; return; }
+            if (s.h_jstatus[0] == 0) {
+                if (offs[nb] > huff_ent_cap(jb)) throw CudaError("internal: device Huffman entry count out of range");
+                std::vector<uint32_t> ent(offs[nb]);
+                CK(cudaMemcpy(ent.data(), R.d_entries, ent.size() * 4, cudaMemcpyDeviceToHost));
+                memset(coefs, 0, (size_t)nb * 128);
+                for (uint32_t bk = 0; bk < nb; ++bk) {
+                    coefs[(size_t)bk * 64] = dcv[bk];
+                    for (uint32_t e = offs[bk]; e < offs[bk + 1] && e < ent.size(); ++e)
+                        coefs[(size_t)bk * 64 + ((ent[e] >> 16) & 63)] = (int16_t)(ent[e] & 0xffffu);
+                }
+                *on_device = 1 + R.rounds;
+                return;
+            }
         }
         uf_jpeg_info info;
         if (uf_jpeg_coefficients(jpeg, len, &info, coefs, cap_blocks) != UF_OK) throw ArgError(UF_ERR_INVALID_ARG, g_last_error);

@@ -81,10 +81,12 @@ struct JpegHuffFrame {              // plain data, copied to the device as is
     uint32_t data_bits;             // its length in bits
     uint32_t nsub;                  // subsequences of JH_SUBSEQ_BITS
     uint32_t sub_base;              // index of the frame's first subsequence in the batch's state arrays
-    uint32_t coef_base;             // index of the frame's first block in the batch's dense coefficient buffer
+    uint32_t offs_base;             // index of the frame's first block in the batch's block-offset and DC arrays (nblocks + 1 each)
+    uint32_t ent_base;              // index of the frame's first entry in the batch's entry array
+    uint32_t ent_cap;               // entries reserved for the frame: data_bits / 2 + 16 (an AC entry takes at least 2 bits)
     uint32_t nblocks, blocks_per_mcu;
     uint32_t slotmap;               // 2 bits per block slot of the MCU: its component
-    uint32_t pad_[3];
+    uint32_t pad_[1];
 };
 constexpr uint32_t JH_SUBSEQ_BITS = 256;    // bits per GPU thread: short, so that a frame is thousands of threads and a pass is brief
 constexpr uint32_t JH_MAX_SUBSEQ = 1u << 17;  // beyond (4 MB of entropy-coded data): host decoder

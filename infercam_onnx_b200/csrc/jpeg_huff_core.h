@@ -67,15 +67,23 @@ JH_FN uint32_t long_symbol(const JpegHuffTab& T, uint32_t x, bool dc) {
     return (len + s) | (kadv << 5) | (s << 12);
 }
 
-// Decodes from state (p, slot, k) while p < p_end. WRITE: coefficients go to `coefs` (dense blocks of the frame; DC as the
-// difference), `next_block` = index of the next block to start, and decoding stops for good once `nblocks` blocks are done
-// (the bits after the last block are padding). slotmap: 2 bits per block slot of the MCU = its component. Returns the
-// number of blocks started.
+// What the write pass produces, per frame (the layout the IDCT kernel reads, kernels_jpeg.cu):
+struct HuffOut {
+    uint32_t* offs;     // [nblocks + 1] index of each block's first AC entry
+    uint32_t* entries;  // (natural index << 16) | (uint16) value of the nonzero AC coefficients, in decode order
+    int16_t* dcv;       // [nblocks] DC difference of each block (summed into DC values by jhuff_dc_kernel)
+    uint32_t ent_cap;   // entries the frame's list can hold (an unsettled frame must not write past it)
+};
+
+// Decodes from state (p, slot, k) while p < p_end, counting the blocks started (low 16 bits of the result) and the nonzero
+// AC coefficients (high 16 bits). WRITE: those go to `out`; next_block / next_entry = where this subsequence's first block
+// start / first entry land, and decoding stops for good once `nblocks` blocks are done (the bits after the last block are
+// padding). slotmap: 2 bits per block slot of the MCU = its component.
 template <bool WRITE>
 JH_FN uint32_t huff_run(const Tabs& tabs, uint32_t slotmap, uint32_t bpm, uint32_t nblocks, const uint32_t* __restrict__ d, uint32_t& p_io,
-                        uint32_t& slot_io, uint32_t& k_io, uint32_t p_end, int16_t* __restrict__ coefs, uint32_t next_block) {
-    uint32_t p = p_io, slot = slot_io, k = k_io, started = 0;
-    int16_t* blk = WRITE && k > 0 && next_block > 0 && next_block - 1 < nblocks ? coefs + (size_t)(next_block - 1) * 64 : nullptr;
+                        uint32_t& slot_io, uint32_t& k_io, uint32_t p_end, const HuffOut& out, uint32_t next_block, uint32_t next_entry) {
+    uint32_t p = p_io, slot = slot_io, k = k_io, counts = 0;
+    bool in_block = WRITE && k > 0 && next_block > 0 && next_block - 1 < nblocks;  // the block in progress is one of the frame's
     // acc: the next nb bits of the stream, left-aligned; `ahead` = word wi - 1, already fetched
     uint32_t wi = p >> 5;
     unsigned long long acc = (((unsigned long long)be32(d, wi) << 32) | be32(d, wi + 1)) << (p & 31);
@@ -98,20 +106,21 @@ JH_FN uint32_t huff_run(const Tabs& tabs, uint32_t slotmap, uint32_t bpm, uint32
         const uint32_t hi = (uint32_t)(acc >> 32);
         uint32_t e = T.look[hi >> (32 - JH_LOOK)];
         if (e == 0) e = long_symbol(T, hi >> 16, dc);
-        const uint32_t total = e & 31u, kadv = (e >> 5) & 127u;
+        const uint32_t total = e & 31u, kadv = (e >> 5) & 127u, s = e >> 12;
         if (WRITE) {
-            const uint32_t s = e >> 12;
+            const int v = s ? extend((uint32_t)((acc << (total - s)) >> (64 - s)), s) : 0;
             if (dc) {
-                blk = coefs + (size_t)next_block * 64;
+                out.offs[next_block] = next_entry;
+                out.dcv[next_block] = (int16_t)v;
                 ++next_block;
-            }
-            if ((s != 0 || dc) && blk) {
-                const int v = s ? extend((uint32_t)((acc << (total - s)) >> (64 - s)), s) : 0;
+                in_block = true;
+            } else if (s != 0) {
                 const uint32_t at = k + kadv - 1;
-                blk[tabs.zz[at < 80 ? at : 79]] = (int16_t)v;
+                if (in_block && next_entry < out.ent_cap) out.entries[next_entry] = ((uint32_t)tabs.zz[at < 80 ? at : 79] << 16) | (uint32_t)(uint16_t)(int16_t)v;
+                ++next_entry;
             }
         }
-        started += dc;
+        counts += dc ? 1u : (s != 0 ? 0x10000u : 0u);
         acc <<= total;
         nb -= (int)total;
         p += total;
@@ -127,7 +136,7 @@ JH_FN uint32_t huff_run(const Tabs& tabs, uint32_t slotmap, uint32_t bpm, uint32
     p_io = p;
     slot_io = slot;
     k_io = k;
-    return started;
+    return counts;
 }
 
 }  // namespace jh

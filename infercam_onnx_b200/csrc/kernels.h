@@ -156,7 +156,8 @@ struct JpegBatchDev {
     const uint32_t* entries;   // (natural index << 16 | value) of all frames (JpegPlan::entries_base)
     uint8_t* planes;           // JpegPlan::planes_off
     uint8_t* rgb;              // JpegPlan::rgb_off
-    const int16_t* dense;      // non-NULL: dense quantised blocks [JpegPlan::offs_base + block][64] (GPU Huffman path) instead of the lists
+    const int16_t* dcv;        // non-NULL (GPU Huffman path): DC values [JpegPlan::offs_base + block]; the lists then hold the AC part only
+    const int* status;         // non-NULL (GPU Huffman path): frames with a nonzero status are skipped (their lists are not valid)
 };
 // Huffman decoding on the GPU (kernels_jpeg_huff.cu)
 struct JpegHuffFrame;
@@ -166,8 +167,10 @@ struct JpegHuffBatch {
     const JpegHuffTabSet* tabsets;      // the batch's distinct table sets (JpegHuffFrame::tabset)
     const uint8_t* bytes;               // unstuffed entropy-coded segments (JpegHuffFrame::data_off)
     unsigned long long* start_used;     // [subsequences] start state of the last decode of each subsequence
-    uint32_t* nblk;                     // [subsequences] blocks started in it
-    int16_t* coefs;                     // dense blocks (JpegHuffFrame::coef_base), zeroed by the caller
+    uint32_t* counts;                   // [subsequences] blocks started in it | nonzero AC coefficients in it << 16
+    uint32_t* offs;                     // [blocks + frames] first AC entry of each block, per frame nblocks + 1 (JpegHuffFrame::offs_base)
+    uint32_t* entries;                  // AC entries of all frames (JpegHuffFrame::ent_base)
+    int16_t* dcv;                       // [blocks + frames] DC differences, then DC values
     int* status;                        // [frames] zeroed by the caller; stays 0 = settled and decoded to exactly its blocks
 };
 void launch_jhuff_sync(const JpegHuffBatch& b, int frames, uint32_t max_nsub, int first, const unsigned long long* in,

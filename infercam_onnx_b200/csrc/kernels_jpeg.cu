@@ -73,6 +73,7 @@ jpeg_idct_kernel(JpegBatchDev b) {
     __syncthreads();
     const uint32_t blk = blockIdx.x * JB_PER_CTA + (tid >> 3);
     if (blk >= plan.nblocks) return;  // whole 8-thread groups leave together; no block-wide barrier follows
+    if (b.status && b.status[blockIdx.y] != 0) return;  // the device Huffman decoder declined the frame: its lists are not valid
     const int t = tid & 7;
     const unsigned gmask = 0xffu << ((tid & 31) & ~7);  // the 8 lanes working on this block
     int* cf = coef + (tid >> 3) * JB_STRIDE;
@@ -81,26 +82,20 @@ jpeg_idct_kernel(JpegBatchDev b) {
     const uint32_t my = mcu / plan.mcus_x, mx = mcu - my * plan.mcus_x;
     const uint32_t bx = mx * plan.hs[c] + plan.slot_h[sl], by = my * plan.vs[c] + plan.slot_v[sl];
     // 1. the block's coefficients, dequantised (DEQUANTIZE: coefficient * quantval)
-    if (b.dense) {  // GPU Huffman path: dense blocks; thread t takes row t
-        const uint4 raw = *reinterpret_cast<const uint4*>(b.dense + ((size_t)plan.offs_base + blk) * 64 + t * 8);
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    // zero, then scatter the list of nonzeros (host Huffman path: DC included; device path: AC only, DC from its own array)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            cf[t * 8 + 2 * i] = (int)(short)(w[i] & 0xffffu) * (int)plan.quant[c][t * 8 + 2 * i];
-            cf[t * 8 + 2 * i + 1] = (int)(short)(w[i] >> 16) * (int)plan.quant[c][t * 8 + 2 * i + 1];
-        }
-    } else {  // host Huffman path: zero, then scatter the list of nonzeros
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cf[i * 8 + t] = 0;
-        __syncwarp(gmask);
+    for (int i = 0; i < 8; ++i) cf[i * 8 + t] = 0;
+    __syncwarp(gmask);
+    {
         const uint32_t* offs = b.offs + plan.offs_base + blk;
-        const uint32_t e0 = offs[0], e1 = offs[1];
+        const uint32_t e0 = offs[0], e1 = min(offs[1], e0 + 64u);
         const uint32_t* ent = b.entries + plan.entries_base;
         for (uint32_t e = e0 + t; e < e1; e += 8) {
             const uint32_t v = ent[e];
             const int idx = (v >> 16) & 63;
             cf[idx] = (int)(short)(v & 0xffffu) * (int)plan.quant[c][idx];
         }
+        if (b.dcv && t == 0) cf[0] = (int)b.dcv[plan.offs_base + blk] * (int)plan.quant[c][0];
     }
     __syncwarp(gmask);
     // 2. columns: thread t = column t; results stored transposed (index column * 8 + row) so that pass 2 reads conflict-free

@@ -11,9 +11,9 @@
 // and usually by many, because a decoder started in a wrong state falls into step with the true one after a few dozen
 // symbols. The fixed point (no end state changes) IS the sequential decode: end[t] = decode(end[t-1]) for all t, end[-1] true.
 // The rounds run inside a CTA over its 128 subsequences, and once per launch across CTAs (jhuff_sync_kernel).
-// Then a prefix sum of the blocks started per subsequence gives every thread its output position, a second pass writes the
-// coefficients (DC as differences), a per-component scan turns DC differences into values, and the dense blocks go to the
-// IDCT kernel. The coefficients are the host decoder's, hence libjpeg-turbo's, bit for bit (tests/test_jpeg.py).
+// Then a prefix sum of the blocks started and nonzero coefficients met per subsequence gives every thread its output
+// position, a second pass writes the coefficients as the compact per-block lists the IDCT kernel reads (DC differences
+// apart), and a per-component scan turns DC differences into values. The coefficients are the host decoder's, hence libjpeg-turbo's, bit for bit (tests/test_jpeg.py).
 #include "jpeg_decode.h"
 #include "jpeg_huff_core.h"
 #include "kernels.h"
@@ -39,13 +39,16 @@ __device__ __forceinline__ void load_tabs(Tabs& tabs, const JpegHuffTabSet& set)
     if (threadIdx.x < 80) tabs.zz[threadIdx.x] = c_zigzag[threadIdx.x];
 }
 
+// blocks | entries << 32 of a packed per-subsequence count
+__device__ __forceinline__ unsigned long long widen(uint32_t c) { return (unsigned long long)(c & 0xffffu) | ((unsigned long long)(c >> 16) << 32); }
+
 // sum over the CTA, the same value in every thread (blockDim.x = JHT)
-__device__ __forceinline__ uint32_t cta_sum(uint32_t v, uint32_t* s_part) {
+__device__ __forceinline__ unsigned long long cta_sum(unsigned long long v, unsigned long long* s_part) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
     __syncthreads();
-    uint32_t t = 0;
+    unsigned long long t = 0;
 #pragma unroll
     for (int w = 0; w < JHT / 32; ++w) t += s_part[w];
     __syncthreads();
@@ -100,7 +103,7 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
         if (active && ns != my_start) {
             uint32_t p = (uint32_t)(ns >> 32), slot = (uint32_t)(ns >> 8) & 0xff, k = (uint32_t)ns & 0xff;
             if (slot >= bpm) slot = 0;
-            my_n = huff_run<false>(tabs, slotmap, bpm, 0, data, p, slot, k, p_end, nullptr, 0);
+            my_n = huff_run<false>(tabs, slotmap, bpm, 0, data, p, slot, k, p_end, HuffOut{}, 0, 0);
             my_end = pack_state(p, slot, k);
             my_start = ns;
             ch = dirty = true;
@@ -113,49 +116,55 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
         out[gi] = my_end;
         if (dirty) {
             b.start_used[gi] = my_start;
-            b.nblk[gi] = my_n;
+            b.counts[gi] = my_n;
         }
     }
 }
 
-// Second pass: every subsequence again, from its settled start state, writing the coefficients. The index of a thread's
-// first block = the blocks started by every subsequence before it: summed over the CTAs before this one, scanned inside.
+// Second pass: every subsequence again, from its settled start state, writing the block offsets, the AC entries and the DC
+// differences. Where a thread's first block start and first entry land = the blocks and entries counted by every
+// subsequence before it: summed over the CTAs before this one, scanned inside.
 __global__ void __launch_bounds__(JHT)
 jhuff_write_kernel(JpegHuffBatch b, const unsigned long long* __restrict__ fin) {
     __shared__ __align__(16) Tabs tabs;
-    __shared__ uint32_t s_part[JHT / 32], s_warp[JHT / 32];
+    __shared__ unsigned long long s_part[JHT / 32], s_warp[JHT / 32];
     const JpegHuffFrame& fr = b.frames[blockIdx.y];
     const uint32_t nsub = fr.nsub, t0 = blockIdx.x * JHT;
     if (t0 >= nsub) return;
     load_tabs(tabs, b.tabsets[fr.tabset]);
-    const uint32_t* nblk = b.nblk + fr.sub_base;
-    uint32_t before = 0;
-    for (uint32_t u = threadIdx.x; u < t0; u += JHT) before += nblk[u];
+    const uint32_t* counts = b.counts + fr.sub_base;
+    unsigned long long before = 0;
+    for (uint32_t u = threadIdx.x; u < t0; u += JHT) before += widen(counts[u]);
     before = cta_sum(before, s_part);  // (also the barrier after load_tabs)
     const uint32_t t = t0 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool active = t < nsub;
-    const uint32_t mine = active ? nblk[t] : 0;
-    uint32_t incl = mine;
+    const unsigned long long mine = active ? widen(counts[t]) : 0;
+    unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= (uint32_t)o) incl += y;
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    uint32_t base = before + incl - mine;
+    unsigned long long base = before + incl - mine;
     for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
     if (!active) return;
+    const uint32_t base_blk = (uint32_t)base, base_ent = (uint32_t)(base >> 32);
     const size_t gi = (size_t)fr.sub_base + t;
     const unsigned long long start = t == 0 ? 0ull : fin[gi - 1];
     if (start != b.start_used[gi]) atomicOr(b.status + blockIdx.y, 2);  // not the fixed point: the frame is not settled
     uint32_t p = (uint32_t)(start >> 32), slot = (uint32_t)(start >> 8) & 0xff, k = (uint32_t)start & 0xff;
     if (slot >= fr.blocks_per_mcu) slot = 0;
     const uint32_t p_end = min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits), nblocks = fr.nblocks;
+    const HuffOut out{b.offs + fr.offs_base, b.entries + fr.ent_base, b.dcv + fr.offs_base, fr.ent_cap};
     const uint32_t n = huff_run<true>(tabs, fr.slotmap, fr.blocks_per_mcu, nblocks, reinterpret_cast<const uint32_t*>(b.bytes + fr.data_off),
-                                      p, slot, k, p_end, b.coefs + (size_t)fr.coef_base * 64, base);
-    if (t == nsub - 1 && !(base + n == nblocks && k == 0))  // not exactly the frame's blocks, ending on a block boundary
-        atomicOr(b.status + blockIdx.y, 1);
+                                      p, slot, k, p_end, out, base_blk, base_ent);
+    if (t == nsub - 1) {
+        out.offs[nblocks] = base_ent + (n >> 16);  // end of the last block's entries
+        if (!(base_blk + (n & 0xffffu) == nblocks && k == 0))  // not exactly the frame's blocks, ending on a block boundary
+            atomicOr(b.status + blockIdx.y, 1);
+    }
 }
 
 // DC differences -> DC values: per component a running sum over its blocks in decode order (the predictor is an int, the
@@ -165,6 +174,7 @@ jhuff_dc_kernel(JpegHuffBatch b) {
     __shared__ uint32_t s_slots[JPEG_MAX_SLOTS], s_cnt;
     __shared__ int s_warp[JHT / 32];
     const JpegHuffFrame& fr = b.frames[blockIdx.x];
+    if (b.status[blockIdx.x] != 0) return;  // not every block has a DC difference: the host decoder redoes the frame
     const uint32_t c = blockIdx.y, bpm = fr.blocks_per_mcu;
     if (threadIdx.x == 0) {
         uint32_t cnt = 0;
@@ -177,13 +187,13 @@ jhuff_dc_kernel(JpegHuffBatch b) {
     if (cnt == 0) return;
     const uint32_t total = fr.nblocks / bpm * cnt, per = (total + JHT - 1) / JHT;
     const uint32_t i0 = min(threadIdx.x * per, total), i1 = min(i0 + per, total);
-    int16_t* coefs = b.coefs + (size_t)fr.coef_base * 64;
-    auto at = [&](uint32_t i) -> size_t {
+    int16_t* dcv = b.dcv + fr.offs_base;
+    auto at = [&](uint32_t i) -> uint32_t {
         const uint32_t mcu = i / cnt;
-        return ((size_t)mcu * bpm + s_slots[i - mcu * cnt]) * 64;
+        return mcu * bpm + s_slots[i - mcu * cnt];
     };
     int sum = 0;
-    for (uint32_t i = i0; i < i1; ++i) sum += coefs[at(i)];
+    for (uint32_t i = i0; i < i1; ++i) sum += dcv[at(i)];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = sum;
 #pragma unroll
@@ -196,17 +206,17 @@ jhuff_dc_kernel(JpegHuffBatch b) {
     int run = incl - sum;
     for (uint32_t w = 0; w < warp; ++w) run += s_warp[w];
     for (uint32_t i = i0; i < i1; i += 8) {  // loads of a group first: a store in between would order them
-        size_t idx[8];
+        uint32_t idx[8];
         int v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             idx[u] = i + u < i1 ? at(i + u) : 0;
-            v[u] = i + u < i1 ? coefs[idx[u]] : 0;
+            v[u] = i + u < i1 ? dcv[idx[u]] : 0;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             run += v[u];
-            if (i + u < i1) coefs[idx[u]] = (int16_t)run;
+            if (i + u < i1) dcv[idx[u]] = (int16_t)run;
         }
     }
 }

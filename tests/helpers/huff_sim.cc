@@ -57,7 +57,7 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
                         uint32_t p = (uint32_t)(ns >> 32), slot = (uint32_t)(ns >> 8) & 0xff, k = (uint32_t)ns & 0xff;
                         if (slot >= fr.blocks_per_mcu) slot = 0;
                         const uint32_t p_end = std::min((t0 + i + 1) * JH_SUBSEQ_BITS, fr.data_bits);
-                        my_n[i] = huff_run<false>(*tabs, slotmap, bpm, 0, d, p, slot, k, p_end, nullptr, 0);
+                        my_n[i] = huff_run<false>(*tabs, slotmap, bpm, 0, d, p, slot, k, p_end, HuffOut{}, 0, 0);
                         my_end[i] = pack_state(p, slot, k);
                         my_start[i] = ns;
                         ch[i] = dirty[i] = true;
@@ -81,26 +81,37 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
     *rounds = (int)std::min<uint32_t>((n + JHT - 1) / JHT, max_rounds > 0 ? (uint32_t)max_rounds : 3u);  // JH_MAX_ROUNDS
     for (int r = 0; r < *rounds; ++r) launch(r == 0);
     *rounds = *rounds * 1000 + iters_max;  // launches * 1000 + the most in-CTA iterations any CTA took
-    const bool settled = true;
     *status = 0;
-    if (settled) {
-        uint32_t acc = 0;
-        for (uint32_t t = 0; t < n; ++t) { base[t] = acc; acc += nblk[t]; }
-        memset(coefs, 0, (size_t)jb.plan.nblocks * 128);
+    {
+        const uint32_t nb = fr.nblocks, cap = fr.data_bits / 2 + 16;
+        std::vector<uint32_t> offs((size_t)nb + 1, 0), ent(cap, 0);
+        std::vector<int16_t> dcv(nb, 0);
+        const HuffOut ho{offs.data(), ent.data(), dcv.data(), cap};
+        unsigned long long acc = 0;  // blocks | entries << 32
         for (uint32_t t = 0; t < n; ++t) {
+            base[t] = (uint32_t)acc;
+            const uint32_t base_ent = (uint32_t)(acc >> 32);
+            acc += (unsigned long long)(nblk[t] & 0xffffu) | ((unsigned long long)(nblk[t] >> 16) << 32);
             const unsigned long long start = t == 0 ? 0ull : in[t - 1];
             if (start != start_used[t]) *status |= 2;
             uint32_t p = (uint32_t)(start >> 32), slot = (uint32_t)(start >> 8) & 0xff, k = (uint32_t)start & 0xff;
             if (slot >= bpm) slot = 0;
             const uint32_t p_end = std::min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits);
-            const uint32_t c = huff_run<true>(*tabs, slotmap, bpm, fr.nblocks, d, p, slot, k, p_end, coefs, base[t]);
-            if (t == n - 1 && !(base[t] + c == fr.nblocks && k == 0)) *status |= 1;
+            const uint32_t c = huff_run<true>(*tabs, slotmap, bpm, nb, d, p, slot, k, p_end, ho, base[t], base_ent);
+            if (t == n - 1) {
+                offs[nb] = base_ent + (c >> 16);
+                if (!(base[t] + (c & 0xffffu) == nb && k == 0)) *status |= 1;
+            }
         }
-        int pred[3] = {0, 0, 0};
-        for (uint32_t b = 0; b < fr.nblocks; ++b) {
-            const int c = (int)((fr.slotmap >> (2 * (b % fr.blocks_per_mcu))) & 3u);
-            pred[c] += coefs[(size_t)b * 64];
-            coefs[(size_t)b * 64] = (int16_t)pred[c];
+        memset(coefs, 0, (size_t)nb * 128);
+        if (*status == 0) {
+            int pred[3] = {0, 0, 0};
+            for (uint32_t b = 0; b < nb; ++b) {
+                const int c = (int)((fr.slotmap >> (2 * (b % fr.blocks_per_mcu))) & 3u);
+                pred[c] += dcv[b];
+                coefs[(size_t)b * 64] = (int16_t)pred[c];
+                for (uint32_t e = offs[b]; e < offs[b + 1] && e < cap; ++e) coefs[(size_t)b * 64 + ((ent[e] >> 16) & 63)] = (int16_t)(ent[e] & 0xffffu);
+            }
         }
     }
     delete tabs;
