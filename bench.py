@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--cls-bias", type=float, default=None,
                     help="face-logit bias of the random-init heads (default %.2f: ~1%% of priors pass; 0: ~28%%, the NMS-heavy config)" % CLS_BIAS)
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the batcher and JPEG end-to-end legs")
-    ap.add_argument("--in-flight", type=int, default=3,
+    ap.add_argument("--in-flight", type=int, default=4,
                     help="host threads calling uf_infer_batch concurrently on the one handle in the e2e leg (a stream "
                          "batcher keeps several batches in flight so the copies of one overlap the kernels of another)")
     return ap.parse_args()

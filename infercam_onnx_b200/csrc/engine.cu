@@ -254,6 +254,7 @@ struct uf_model {
     Plan plan;
     int K = 0;
     uint32_t chunk = 0, host_chunk = 0, jpeg_chunk = 0, nslots = 0;
+    uint32_t jh_threads = 150000, jh_bits = 0;  // device Huffman: threads a run should have / forced bits per thread (tuning knobs)
     std::vector<Step> steps;
     std::vector<size_t> w_off, b_off;  // per plan op, floats into d_weights
     float* d_weights = nullptr;
@@ -1134,7 +1135,8 @@ static void decode_jpeg_run(uf_model& m, Slot& s, const FrameSrc* fr, uint32_t c
 // ---- N2, Huffman decoding on the device too. Scratch per frame: 3 state arrays + 2 count arrays per subsequence, the dense blocks.
 static size_t huff_ent_cap(const JpegBitstream& jb) { return (size_t)jb.huff.data_bits / 2 + 16; }
 static size_t huff_scratch_bytes(const JpegBitstream& jb) {  // (+ slack for the alignment of a run's sections)
-    return (size_t)jb.huff.nsub * (3 * 8 + 4) + ((size_t)jb.plan.nblocks + 1) * (4 + 2) + huff_ent_cap(jb) * 4 + 1024;
+    const size_t nsub_max = (jb.huff.data_bits + JH_MIN_SUBSEQ_BITS - 1) / JH_MIN_SUBSEQ_BITS;  // (whatever length the run picks)
+    return nsub_max * (3 * 8 + 4) + ((size_t)jb.plan.nblocks + 1) * (4 + 2) + huff_ent_cap(jb) * 4 + 1024;
 }
 // (staging: a frame may bring its own table set — frames of one camera share one, but the bound cannot assume it)
 static size_t huff_stage_bytes(const JpegBitstream& jb) {
@@ -1167,14 +1169,22 @@ static HuffRun huffman_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_
                                size_t& planes_used, size_t& huff_used) {
     auto a16 = [](size_t v) { return (v + 15) / 16 * 16; };
     HuffRun R;
-    size_t n_bytes = 0, n_sub = 0, n_ent = 0;
+    size_t n_bytes = 0, n_sub = 0, n_ent = 0, n_bits = 0;
     uint32_t max_nsub = 0;
+    for (uint32_t k = 0; k < cnt; ++k) n_bits += fr[k].jb->huff.data_bits;
+    // Bits per thread: as long as the run still gives the GPU ~150 k threads (a thread that starts from a guess needs a few
+    // thousand bits to fall into step, so the work is about 1 + that / sub_bits passes over the data: long is cheap, but a
+    // small run needs short subsequences to have threads at all).
+    uint32_t sub_bits = JH_MAX_SUBSEQ_BITS;
+    while (sub_bits > 256 && n_bits / sub_bits < m.jh_threads) sub_bits /= 2;  // (measured: 256 for 16 frames of 75 KB, 512-1024 for 128)
+    if (m.jh_bits) sub_bits = m.jh_bits;
+    auto nsub_of = [&](const JpegBitstream& jb) { return (jb.huff.data_bits + sub_bits - 1) / sub_bits; };
     for (uint32_t k = 0; k < cnt; ++k) {
         n_bytes += a16(fr[k].jb->data.size());
-        n_sub += fr[k].jb->huff.nsub;
+        n_sub += nsub_of(*fr[k].jb);
         n_ent += huff_ent_cap(*fr[k].jb);
         R.n_blocks += fr[k].jb->plan.nblocks;
-        max_nsub = std::max(max_nsub, fr[k].jb->huff.nsub);
+        max_nsub = std::max(max_nsub, nsub_of(*fr[k].jb));
         R.max_blocks = std::max(R.max_blocks, fr[k].jb->plan.nblocks);
     }
     // the run's distinct table sets (normally one: every frame of a camera carries the same DHT, or none)
@@ -1215,12 +1225,13 @@ static HuffRun huffman_run_gpu(uf_model& m, Slot& s, const FrameSrc* fr, uint32_
         planes_used += p.plane_bytes;
         plans[k] = p;
         JpegHuffFrame h = jb.huff;
+        h.sub_bits = sub_bits; h.nsub = nsub_of(jb);
         h.tabset = set_of[k]; h.data_off = (uint32_t)ib; h.sub_base = (uint32_t)isub;
         h.offs_base = (uint32_t)(iblk + k); h.ent_base = (uint32_t)ient; h.ent_cap = (uint32_t)huff_ent_cap(jb);
         hfs[k] = h;
         byte_off[k] = o_bytes + ib;
         ib += a16(jb.data.size());
-        isub += jb.huff.nsub;
+        isub += h.nsub;
         iblk += jb.plan.nblocks;
         ient += huff_ent_cap(jb);
     }
@@ -1477,6 +1488,8 @@ static uf_model* load_model(const uf_config& cfg_in) {
     if (cfg.host_chunk) m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, cfg.host_chunk));
     m->jpeg_chunk = std::max(m->host_chunk, std::min<uint32_t>(chunk, 128));
     if (const char* e = getenv("UF_JPEG_CHUNK")) m->jpeg_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint32_t)atoi(e)));  // tuning knob
+    if (const char* e = getenv("UF_JH_THREADS")) m->jh_threads = (uint32_t)std::max(1, atoi(e));
+    if (const char* e = getenv("UF_JH_BITS"); e && atoi(e) > 0) m->jh_bits = std::max(JH_MIN_SUBSEQ_BITS, std::min(JH_MAX_SUBSEQ_BITS, (uint32_t)atoi(e) / 32 * 32));
     uint32_t nslots = cfg.slots ? cfg.slots : 4;
     const uint32_t nchunks = (cfg.max_batch + m->host_chunk - 1) / m->host_chunk;
     m->nslots = std::max<uint32_t>(1, std::min(nslots, nchunks));

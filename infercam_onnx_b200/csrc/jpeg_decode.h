@@ -79,17 +79,21 @@ struct JpegHuffFrame {              // plain data, copied to the device as is
     uint32_t tabset;                // index of the frame's table set in the batch
     uint32_t data_off;              // byte offset of the frame's UNSTUFFED entropy-coded segment in the batch's byte buffer
     uint32_t data_bits;             // its length in bits
-    uint32_t nsub;                  // subsequences of JH_SUBSEQ_BITS
+    uint32_t sub_bits;              // bits per subsequence (= per GPU thread), chosen when the batch is laid out
+    uint32_t nsub;                  // subsequences: ceil(data_bits / sub_bits)
     uint32_t sub_base;              // index of the frame's first subsequence in the batch's state arrays
     uint32_t offs_base;             // index of the frame's first block in the batch's block-offset and DC arrays (nblocks + 1 each)
     uint32_t ent_base;              // index of the frame's first entry in the batch's entry array
     uint32_t ent_cap;               // entries reserved for the frame: data_bits / 2 + 16 (an AC entry takes at least 2 bits)
     uint32_t nblocks, blocks_per_mcu;
     uint32_t slotmap;               // 2 bits per block slot of the MCU: its component
-    uint32_t pad_[1];
 };
-constexpr uint32_t JH_SUBSEQ_BITS = 256;    // bits per GPU thread: short, so that a frame is thousands of threads and a pass is brief
-constexpr uint32_t JH_MAX_SUBSEQ = 1u << 17;  // beyond (4 MB of entropy-coded data): host decoder
+// Bits per GPU thread. Short subsequences give more threads and shorter passes, long ones fewer passes over the data (a
+// decoder started in a guessed state needs a few thousand bits to fall into step, whatever the subsequence length: every
+// thread decodes about 1 + that distance / sub_bits subsequences' worth of bits). The engine picks per run from how many
+// bits the run holds (engine.cu: huffman_run_gpu).
+constexpr uint32_t JH_MIN_SUBSEQ_BITS = 128, JH_MAX_SUBSEQ_BITS = 2048, JH_DEFAULT_SUBSEQ_BITS = 512;
+constexpr uint32_t JH_MAX_DATA_BITS = 1u << 25;  // beyond (4 MB of entropy-coded data): host decoder
 struct JpegBitstream {              // one frame, host side
     JpegPlan plan{};
     JpegHuffFrame huff{};           // geometry (offsets and the table set index are filled in when the batch is laid out)

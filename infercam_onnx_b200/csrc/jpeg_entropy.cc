@@ -386,9 +386,10 @@ void jpeg_prepare_bitstream(const uint8_t* data, size_t len, JpegBitstream& out)
         break;
     }
     h.data_bits = (uint32_t)out.data.size() * 8;
-    h.nsub = (h.data_bits + JH_SUBSEQ_BITS - 1) / JH_SUBSEQ_BITS;
+    h.sub_bits = JH_DEFAULT_SUBSEQ_BITS;
+    h.nsub = (h.data_bits + h.sub_bits - 1) / h.sub_bits;
     out.data.resize((out.data.size() + 15) / 16 * 16 + 32, 0);  // zero tail: the reader fetches up to 5 words past the end
-    out.gpu_ok = P.restart_interval == 0 && !marker_inside && h.nsub > 0 && h.nsub <= JH_MAX_SUBSEQ;
+    out.gpu_ok = P.restart_interval == 0 && !marker_inside && h.nsub > 0 && h.data_bits <= JH_MAX_DATA_BITS;
 }
 
 JpegPlan jpeg_parse_header(const uint8_t* data, size_t len) {

@@ -25,7 +25,7 @@ using namespace jh;
 namespace {
 
 constexpr int JHT = 256;         // threads per CTA (one subsequence each): a CTA spans 8 KB of the stream
-constexpr int JH_MAX_ROUNDS = 3;  // launches of the synchronisation kernel (see jhuff_sync_kernel)
+constexpr int JH_MAX_ROUNDS = 4;  // launches of the synchronisation kernel (see jhuff_sync_kernel)
 
 __constant__ uint8_t c_zigzag[80] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
                                      6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31,
@@ -72,13 +72,13 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
     __shared__ __align__(16) Tabs tabs;
     __shared__ unsigned long long s_end[JHT];
     const JpegHuffFrame& fr = b.frames[blockIdx.y];
-    const uint32_t nsub = fr.nsub, t0 = blockIdx.x * JHT;
+    const uint32_t nsub = fr.nsub, t0 = blockIdx.x * JHT, sub_bits = fr.sub_bits;
     if (t0 >= nsub) return;
     const uint32_t t = t0 + threadIdx.x;
     const bool active = t < nsub;
     const size_t gi = (size_t)fr.sub_base + t;
     const unsigned long long cta_start =
-        blockIdx.x == 0 ? 0ull : (first ? pack_state(t0 * JH_SUBSEQ_BITS, 0, 0) : in[(size_t)fr.sub_base + t0 - 1]);
+        blockIdx.x == 0 ? 0ull : (first ? pack_state(t0 * sub_bits, 0, 0) : in[(size_t)fr.sub_base + t0 - 1]);
     if (!first && cta_start == b.start_used[(size_t)fr.sub_base + t0]) {  // (uniform over the CTA)
         if (active) out[gi] = in[gi];
         return;
@@ -88,7 +88,7 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
     uint32_t my_n = 0;
     bool dirty = false;
     if (first) {
-        my_end = pack_state((t + 1) * JH_SUBSEQ_BITS, 0, 0);  // the next thread's first guess: its own beginning, slot 0, DC
+        my_end = pack_state((t + 1) * sub_bits, 0, 0);  // the next thread's first guess: its own beginning, slot 0, DC
     } else if (active) {
         my_start = b.start_used[gi];
         my_end = in[gi];
@@ -96,7 +96,7 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
     s_end[threadIdx.x] = my_end;
     __syncthreads();
     const uint32_t* data = reinterpret_cast<const uint32_t*>(b.bytes + fr.data_off);
-    const uint32_t p_end = min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits), bpm = fr.blocks_per_mcu, slotmap = fr.slotmap;
+    const uint32_t p_end = min((t + 1) * sub_bits, fr.data_bits), bpm = fr.blocks_per_mcu, slotmap = fr.slotmap;
     for (int iter = 0; iter <= JHT; ++iter) {
         const unsigned long long ns = threadIdx.x == 0 ? cta_start : s_end[threadIdx.x - 1];
         bool ch = false;
@@ -156,7 +156,7 @@ jhuff_write_kernel(JpegHuffBatch b, const unsigned long long* __restrict__ fin) 
     if (start != b.start_used[gi]) atomicOr(b.status + blockIdx.y, 2);  // not the fixed point: the frame is not settled
     uint32_t p = (uint32_t)(start >> 32), slot = (uint32_t)(start >> 8) & 0xff, k = (uint32_t)start & 0xff;
     if (slot >= fr.blocks_per_mcu) slot = 0;
-    const uint32_t p_end = min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits), nblocks = fr.nblocks;
+    const uint32_t p_end = min((t + 1) * fr.sub_bits, fr.data_bits), nblocks = fr.nblocks;
     const HuffOut out{b.offs + fr.offs_base, b.entries + fr.ent_base, b.dcv + fr.offs_base, fr.ent_cap};
     const uint32_t n = huff_run<true>(tabs, fr.slotmap, fr.blocks_per_mcu, nblocks, reinterpret_cast<const uint32_t*>(b.bytes + fr.data_off),
                                       p, slot, k, p_end, out, base_blk, base_ent);

@@ -11,7 +11,8 @@
 using namespace uf;
 using namespace uf::jh;
 
-extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t cap_blocks, int* rounds, int* status, int max_rounds) {
+extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t cap_blocks, int* rounds, int* status, int max_rounds,
+                        int sub_bits) {
     JpegBitstream jb;
     try {
         jpeg_prepare_bitstream(jpeg, len, jb);
@@ -20,7 +21,12 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
     }
     if (!jb.gpu_ok) return 1;
     if (cap_blocks < jb.plan.nblocks) return 2;
+    if (sub_bits > 0) {  // (the engine picks this per run)
+        jb.huff.sub_bits = (uint32_t)sub_bits;
+        jb.huff.nsub = (jb.huff.data_bits + jb.huff.sub_bits - 1) / jb.huff.sub_bits;
+    }
     const JpegHuffFrame& fr = jb.huff;
+    const uint32_t SUB = fr.sub_bits;
     Tabs* tabs = new Tabs;
     jpeg_build_tabset(jb.key, tabs->set);
     for (int i = 0; i < 80; ++i) tabs->zz[i] = zigzag_natural(i);
@@ -34,7 +40,7 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
     auto launch = [&](bool first) {  // one jhuff_sync_kernel launch: CTAs in any order, they only read `in` of the launch before
         for (uint32_t t0 = 0; t0 < n; t0 += JHT) {
             const uint32_t lanes = std::min(JHT, n - t0);
-            const unsigned long long cta_start = t0 == 0 ? 0ull : (first ? pack_state(t0 * JH_SUBSEQ_BITS, 0, 0) : in[t0 - 1]);
+            const unsigned long long cta_start = t0 == 0 ? 0ull : (first ? pack_state(t0 * SUB, 0, 0) : in[t0 - 1]);
             if (!first && cta_start == start_used[t0]) {
                 for (uint32_t i = 0; i < lanes; ++i) out[t0 + i] = in[t0 + i];
                 continue;
@@ -44,7 +50,7 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
             bool dirty[JHT];
             for (uint32_t i = 0; i < JHT; ++i) {
                 my_start[i] = ~0ull; my_end[i] = 0; my_n[i] = 0; dirty[i] = false;
-                if (first) my_end[i] = pack_state((t0 + i + 1) * JH_SUBSEQ_BITS, 0, 0);
+                if (first) my_end[i] = pack_state((t0 + i + 1) * SUB, 0, 0);
                 else if (i < lanes) { my_start[i] = start_used[t0 + i]; my_end[i] = in[t0 + i]; }
                 s_end[i] = my_end[i];
             }
@@ -56,7 +62,7 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
                     if (i < lanes && ns != my_start[i]) {
                         uint32_t p = (uint32_t)(ns >> 32), slot = (uint32_t)(ns >> 8) & 0xff, k = (uint32_t)ns & 0xff;
                         if (slot >= fr.blocks_per_mcu) slot = 0;
-                        const uint32_t p_end = std::min((t0 + i + 1) * JH_SUBSEQ_BITS, fr.data_bits);
+                        const uint32_t p_end = std::min((t0 + i + 1) * SUB, fr.data_bits);
                         my_n[i] = huff_run<false>(*tabs, slotmap, bpm, 0, d, p, slot, k, p_end, HuffOut{}, 0, 0);
                         my_end[i] = pack_state(p, slot, k);
                         my_start[i] = ns;
@@ -78,7 +84,7 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
         }
         in.swap(out);
     };
-    *rounds = (int)std::min<uint32_t>((n + JHT - 1) / JHT, max_rounds > 0 ? (uint32_t)max_rounds : 3u);  // JH_MAX_ROUNDS
+    *rounds = (int)std::min<uint32_t>((n + JHT - 1) / JHT, max_rounds > 0 ? (uint32_t)max_rounds : 4u);  // JH_MAX_ROUNDS
     for (int r = 0; r < *rounds; ++r) launch(r == 0);
     *rounds = *rounds * 1000 + iters_max;  // launches * 1000 + the most in-CTA iterations any CTA took
     *status = 0;
@@ -96,7 +102,7 @@ extern "C" int huff_sim(const uint8_t* jpeg, size_t len, int16_t* coefs, size_t 
             if (start != start_used[t]) *status |= 2;
             uint32_t p = (uint32_t)(start >> 32), slot = (uint32_t)(start >> 8) & 0xff, k = (uint32_t)start & 0xff;
             if (slot >= bpm) slot = 0;
-            const uint32_t p_end = std::min((t + 1) * JH_SUBSEQ_BITS, fr.data_bits);
+            const uint32_t p_end = std::min((t + 1) * SUB, fr.data_bits);
             const uint32_t c = huff_run<true>(*tabs, slotmap, bpm, nb, d, p, slot, k, p_end, ho, base[t], base_ent);
             if (t == n - 1) {
                 offs[nb] = base_ent + (c >> 16);
