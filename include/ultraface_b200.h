@@ -215,12 +215,18 @@ UF_API int uf_jpeg_info_read(const uint8_t* jpeg, size_t len, uf_jpeg_info* out)
  * order inside a block; cap_blocks = its capacity in blocks. */
 UF_API int uf_jpeg_coefficients(const uint8_t* jpeg, size_t len, uf_jpeg_info* info, int16_t* coefs, size_t cap_blocks);
 
-/* ==== after the path: overlay + JPEG encode (partial) ===========================================
- * Replaces `draw_bboxes_on_image` + `turbojpeg::compress_image(&frame, 95, Subsamp::Sub2x2)` (inferer.rs:38-39, 58-92) for the
+/* ==== after the path: overlay + JPEG encode ====================================================
+ * Replaces `draw_bboxes_on_image` + `turbojpeg::compress_image(&frame, 95, Subsamp::Sub2x2)` (inferer.rs:38-39, 58-92).
  * RECTANGLES: every detection's outline is drawn as imageproc's `draw_hollow_rect` draws it — corners from the reference's
  * casts (x_tl as i32, (x_br - x_tl) as u32 ... of bbox * (scale_w, scale_h); the reference passes 1280 x 720 whatever the
  * frame, router.rs:66-67), four clipped 1-pixel segments in (0, 255, 0); a box whose width or height casts to 0 is skipped
- * (the reference would panic in Rect::of_size). The confidence TEXT the reference prints with rusttype is not drawn.
+ * (the reference would panic in Rect::of_size).
+ * TEXT (inferer.rs:80-88, `draw_text(.., x_tl as i32, y_tl as i32, Scale 16, DejaVuSansMono, "{:.2}%" of confidence * 100)`):
+ * drawn once a glyph atlas is set (uf_text_atlas_set below), detection by detection in the reference's order (rectangle,
+ * then its text), each glyph pixel blended as imageproc's draw_text_mut does: weighted_sum(pixel, colour, 1 - v, v) per
+ * channel in f32, clamped, truncated to u8. RASTERISING the font stays with the reference's own rasteriser: the binding
+ * renders the characters of the text once per caret position with rusttype at start-up and hands the coverage over
+ * (INTEGRATION.md shows the 20 lines of Rust); placing, clipping and blending are done here. Without an atlas no text.
  * The frame is then encoded as baseline JPEG, YCbCr 4:2:0, Annex K Huffman tables, jpeg_set_quality(quality) tables: colour
  * conversion, chroma downsampling, forward ISLOW DCT and quantisation on the GPU (the coefficients are libjpeg-turbo's, bit
  * for bit), Huffman coding on the host. out / cap: destination buffer; *out_len = bytes needed (UF_ERR_CAPACITY if > cap). */
@@ -235,7 +241,22 @@ UF_API int uf_annotate_reencode_jpeg(uf_model* m, const uint8_t* jpeg, size_t le
 UF_API int uf_jpeg_write_coefficients(uint32_t w, uint32_t h, uint32_t quality, const int16_t* coefs, size_t n_blocks, uint8_t* out,
                                       size_t cap, size_t* out_len);
 UF_API int uf_jpeg_quality_tables(uint32_t quality, uint16_t* lum64, uint16_t* chr64);
-/* parity hook: the frame with the rectangles drawn (RGB8, w * h * 3 bytes). */
+/* Glyph atlas for the text overlay. glyphs[pos * n_chars + k] = the glyph of charset[k] as the pos-th character of a text:
+ * x0 / y0 = its pixel_bounding_box().min relative to the text origin (what rusttype's layout gives for a caret started at
+ * (0, ascent)), w x h = the box, coverage[offset + gy * w + gx] = the value rusttype's draw() reports for pixel (gx, gy).
+ * w == 0: nothing to draw (a blank). Characters outside the charset and positions >= max_len are skipped. n_chars = 0 removes
+ * the atlas. */
+typedef struct uf_glyph {
+    int32_t x0, y0;
+    uint32_t w, h;
+    uint32_t offset;
+} uf_glyph;
+UF_API int uf_text_atlas_set(uf_model* m, const char* charset, uint32_t n_chars, uint32_t max_len, const uf_glyph* glyphs,
+                             const float* coverage, size_t n_coverage);
+/* host only: the text the overlay prints for a confidence — Rust's format!("{:.2}%", confidence * 100.0) on f32 (the product
+ * rounded to f32, its exact value printed with two decimals). Writes a NUL-terminated string (cap >= 16). */
+UF_API int uf_confidence_text(float confidence, char* out, size_t cap);
+/* parity hook: the frame with the overlay drawn (RGB8, w * h * 3 bytes). */
 UF_API int uf_draw_boxes_rgb(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets,
                              float scale_w, float scale_h, uint8_t* out_rgb);
 

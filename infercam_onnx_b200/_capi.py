@@ -18,6 +18,10 @@ UF_FLAG_NO_PRESTEM = 256
 UF_FLAG_JPEG_HOST_HUFFMAN = 512
 
 
+class uf_glyph(C.Structure):
+    _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("w", C.c_uint32), ("h", C.c_uint32), ("offset", C.c_uint32)]
+
+
 class uf_det(C.Structure):
     _fields_ = [("x0", C.c_float), ("y0", C.c_float), ("x1", C.c_float), ("y1", C.c_float), ("conf", C.c_float)]
 
@@ -108,6 +112,8 @@ SIGNATURES = {
                                             C.c_void_p, C.c_size_t, _p(C.c_size_t)]),
     "uf_jpeg_write_coefficients": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, _p(C.c_size_t)]),
     "uf_jpeg_quality_tables": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p]),
+    "uf_text_atlas_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "uf_confidence_text": (C.c_int, [C.c_float, C.c_char_p, C.c_size_t]),
     "uf_draw_boxes_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]),
     "uf_batcher_create": (C.c_int, [_p(uf_batcher_config), _void_pp]),
     "uf_batcher_create_ex": (C.c_int, [_p(uf_batcher_config), uf_batch_fn, C.c_void_p, _void_pp]),

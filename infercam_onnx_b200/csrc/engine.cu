@@ -274,6 +274,13 @@ struct uf_model {
     // hook scratch (uf_postproc / uf_preproc_*), grown on demand
     void* d_hook = nullptr;
     size_t d_hook_cap = 0;
+    // N3 text overlay: the glyph atlas handed over by the binding (uf_text_atlas_set)
+    std::mutex atlas_mu;
+    std::string atlas_chars;
+    uint32_t atlas_max_len = 0;
+    std::vector<uf_glyph> atlas_glyphs;   // [max_len][chars]
+    float* d_atlas = nullptr;             // coverage values
+    size_t atlas_n = 0;
     std::vector<uint8_t> tensor_readable;  // per plan tensor: materialised in the arena
     std::vector<TcWeights> tc_weights;
     std::unique_ptr<HostPool> host_pool;  // Huffman decoding workers, created on first use
@@ -1536,7 +1543,7 @@ uf_model::~uf_model() {
     taps.clear();
     for (auto& t : tc_weights) { cudaFree(t.d_hi); cudaFree(t.d_lo); }
     for (auto& lane : lanes) { cudaFree(lane->d_scores); cudaFree(lane->d_boxes); }
-    cudaFree(d_weights); cudaFree(d_lut); cudaFree(d_priors); cudaFree(d_hook);
+    cudaFree(d_weights); cudaFree(d_lut); cudaFree(d_priors); cudaFree(d_hook); cudaFree(d_atlas);
 }
 
 // ---- C ABI -----------------------------------------------------------------------------------
@@ -1802,7 +1809,14 @@ static uint32_t sat_u32(float v) {  // Rust `as u32`
     return (uint32_t)v;
 }
 
-static std::vector<int4> reference_rects(const uf_det* dets, uint32_t n, float width, float height) {
+static std::string confidence_text(float confidence) {
+    volatile float pct = confidence * 100.0f;  // f32 product, as the reference's `confidence * 100.0`
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.2f%%", (double)pct);  // the exact value of the f32, two decimals (Rust: "{:.2}%")
+    return buf;
+}
+
+static std::vector<int4> reference_rects(const uf_det* dets, uint32_t n, float width, float height, std::vector<uint32_t>* which = nullptr) {
     std::vector<int4> r;
     for (uint32_t i = 0; i < n; ++i) {
         // inferer.rs:69-75, f32 arithmetic, one rounding per operation
@@ -1815,6 +1829,7 @@ static std::vector<int4> reference_rects(const uf_det* dets, uint32_t n, float w
         const int64_t right = left + (int64_t)rw - 1, bottom = top + (int64_t)rh - 1;  // imageproc Rect::right / bottom
         auto cl = [](int64_t v) { return (int)std::max<int64_t>(-(1 << 30), std::min<int64_t>(1 << 30, v)); };  // clipping happens per pixel anyway
         r.push_back(make_int4(cl(left), cl(top), cl(right), cl(bottom)));
+        if (which) which->push_back(i);
     }
     return r;
 }
@@ -1822,8 +1837,46 @@ static std::vector<int4> reference_rects(const uf_det* dets, uint32_t n, float w
 // draws on the RGB frame at s.d_in (device) and, if `file` is given, encodes it; everything on slot 0 of the locked lane
 static void annotate_on_device(uf_model& m, Slot& s, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets, float scale_w, float scale_h,
                                int quality, std::vector<uint8_t>* file) {
-    std::vector<int4> rects = reference_rects(dets, n_dets, scale_w, scale_h);
-    // clip rectangles that lie wholly outside early (a box far off-frame would otherwise be a long empty loop)
+    std::vector<uint32_t> which;
+    std::vector<int4> rects = reference_rects(dets, n_dets, scale_w, scale_h, &which);
+    std::unique_lock<std::mutex> atlas_lk(m.atlas_mu);
+    if (!m.atlas_chars.empty() && !rects.empty()) {
+        // rectangles and text in the reference's order: one list, walked by one CTA (kernels_jpeg_enc.cu)
+        std::vector<uint32_t> gstart(rects.size() + 1, 0);
+        std::vector<OverlayGlyph> gl;
+        const uint32_t nc = (uint32_t)m.atlas_chars.size();
+        for (size_t k = 0; k < rects.size(); ++k) {
+            gstart[k] = (uint32_t)gl.size();
+            const int ox = rects[k].x, oy = rects[k].y;  // x_tl as i32, y_tl as i32
+            const std::string text = confidence_text(dets[which[k]].conf);
+            for (uint32_t pos = 0; pos < text.size() && pos < m.atlas_max_len; ++pos) {
+                const size_t ci = m.atlas_chars.find(text[pos]);
+                if (ci == std::string::npos) continue;
+                const uf_glyph& g = m.atlas_glyphs[(size_t)pos * nc + ci];
+                if (g.w == 0 || g.h == 0) continue;
+                const int64_t gx = (int64_t)ox + g.x0, gy = (int64_t)oy + g.y0;
+                if (gx >= (int64_t)w || gy >= (int64_t)h || gx + (int64_t)g.w <= 0 || gy + (int64_t)g.h <= 0) continue;  // wholly outside
+                gl.push_back(OverlayGlyph{(int32_t)gx, (int32_t)gy, g.w, g.h, g.offset});
+            }
+            // (clamping a rectangle's far-off corners changes nothing: pixels outside the frame are skipped one by one)
+            rects[k] = make_int4(std::max(rects[k].x, -1), std::max(rects[k].y, -1), std::min(rects[k].z, (int)w), std::min(rects[k].w, (int)h));
+            if (rects[k].z < rects[k].x || rects[k].w < rects[k].y) rects[k] = make_int4(-1, -1, -2, -2);  // wholly outside: empty loops
+        }
+        gstart[rects.size()] = (uint32_t)gl.size();
+        const size_t b_r = rects.size() * sizeof(int4), b_s = (gstart.size() * 4 + 15) / 16 * 16, b_g = gl.size() * sizeof(OverlayGlyph);
+        uint8_t* d = (uint8_t*)hook_scratch(m, b_r + b_s + b_g + 16);
+        CK(cudaMemcpyAsync(d, rects.data(), b_r, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(d + b_r, gstart.data(), gstart.size() * 4, cudaMemcpyHostToDevice, s.stream));
+        if (b_g) CK(cudaMemcpyAsync(d + b_r + b_s, gl.data(), b_g, cudaMemcpyHostToDevice, s.stream));
+        m.launches++;
+        launch_draw_overlay(s.d_in, (int)w, (int)h, reinterpret_cast<const int4*>(d), reinterpret_cast<const uint32_t*>(d + b_r),
+                            reinterpret_cast<const OverlayGlyph*>(d + b_r + b_s), m.d_atlas, (int)rects.size(), s.stream);
+        CK(cudaStreamSynchronize(s.stream));  // the lists are pageable host memory
+        rects.clear();
+    }
+    atlas_lk.unlock();
+    // no atlas: rectangles only, all at once (same colour: their order does not show). Clip rectangles that lie wholly
+    // outside early (a box far off-frame would otherwise be a long empty loop)
     std::vector<int4> vis;
     for (const int4& r : rects)
         if (r.z >= 0 && r.w >= 0 && r.x < (int)w && r.y < (int)h)
@@ -1851,6 +1904,50 @@ static void deliver_file(const std::vector<uint8_t>& file, uint8_t* out, size_t 
     *out_len = file.size();
     if (file.size() > cap || !out) throw ArgError(UF_ERR_CAPACITY, "output buffer smaller than the encoded file (" + std::to_string(file.size()) + " bytes)");
     memcpy(out, file.data(), file.size());
+}
+
+int uf_text_atlas_set(uf_model* m, const char* charset, uint32_t n_chars, uint32_t max_len, const uf_glyph* glyphs, const float* coverage,
+                      size_t n_coverage) {
+    return guarded([&] {
+        REQUIRE(m, "null argument");
+        std::lock_guard<std::mutex> lk(m->atlas_mu);
+        CK(cudaSetDevice(m->cfg.device));
+        if (n_chars == 0) {
+            m->atlas_chars.clear();
+            m->atlas_glyphs.clear();
+            m->atlas_max_len = 0;
+            return;
+        }
+        REQUIRE(charset && glyphs && max_len > 0 && max_len <= 64 && n_chars <= 128 && (coverage || n_coverage == 0), "bad argument");
+        const size_t ng = (size_t)n_chars * max_len;
+        for (size_t i = 0; i < ng; ++i) {
+            const uf_glyph& g = glyphs[i];
+            if (g.w == 0 || g.h == 0) continue;
+            if (g.w > 4096 || g.h > 4096 || (size_t)g.offset + (size_t)g.w * g.h > n_coverage)
+                throw ArgError(UF_ERR_INVALID_ARG, "glyph " + std::to_string(i) + " points outside the coverage array");
+        }
+        float* d = nullptr;
+        CK(cudaMalloc(&d, std::max<size_t>(n_coverage, 1) * sizeof(float)));
+        if (n_coverage) {
+            cudaError_t e = cudaMemcpy(d, coverage, n_coverage * sizeof(float), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(d); throw CudaError(std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
+        }
+        cudaFree(m->d_atlas);
+        m->d_atlas = d;
+        m->atlas_n = n_coverage;
+        m->atlas_chars.assign(charset, n_chars);
+        m->atlas_max_len = max_len;
+        m->atlas_glyphs.assign(glyphs, glyphs + ng);
+    });
+}
+
+int uf_confidence_text(float confidence, char* out, size_t cap) {
+    return guarded([&] {
+        REQUIRE(out && cap >= 16, "bad argument");
+        const std::string t = confidence_text(confidence);
+        if (t.size() + 1 > cap) throw ArgError(UF_ERR_CAPACITY, "text buffer too small");
+        memcpy(out, t.c_str(), t.size() + 1);
+    });
 }
 
 int uf_annotate_encode_jpeg(uf_model* m, const uint8_t* rgb, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets, float scale_w,

@@ -181,6 +181,12 @@ void launch_jpeg_decode(const JpegBatchDev& b, int frames, uint32_t max_nblocks,
 
 // ---- N3: rectangle overlay + JPEG encode front half (kernels_jpeg_enc.cu)
 void launch_draw_rects(uint8_t* rgb, int w, int h, const int4* d_rects, int n, cudaStream_t s);
+struct OverlayGlyph {  // one placed glyph: top-left pixel in the image, box, offset of its coverage values in the atlas
+    int32_t x, y;
+    uint32_t w, h, offset;
+};
+void launch_draw_overlay(uint8_t* rgb, int w, int h, const int4* d_rects, const uint32_t* d_glyph_start, const OverlayGlyph* d_glyphs,
+                         const float* d_coverage, int n, cudaStream_t s);
 void launch_jpeg_encode(const uint8_t* d_rgb, const JpegPlan& plan, uint8_t* d_planes, int16_t* d_coefs, cudaStream_t s);
 
 // ---- K9-K11: threshold + sort + greedy NMS, one CTA per frame (nn.rs:109-140,198-260)

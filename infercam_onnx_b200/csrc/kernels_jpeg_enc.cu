@@ -32,6 +32,53 @@ void launch_draw_rects(uint8_t* rgb, int w, int h, const int4* d_rects, int n, c
     if (n > 0) draw_rects_kernel<<<n, 128, 0, s>>>(rgb, w, h, d_rects, n);
 }
 
+// imageproc's Clamp<f32> for u8 after weighted_sum: below 255 and above 0 the float is truncated
+__device__ __forceinline__ uint8_t blend_u8(uint8_t pix, float col, float lw, float rw) {
+    const float x = __fadd_rn(__fmul_rn((float)pix, lw), __fmul_rn(col, rw));  // left * left_weight + right * right_weight, no fma
+    return x < 255.0f ? (x > 0.0f ? (uint8_t)x : (uint8_t)0) : (uint8_t)255;
+}
+
+// Rectangles AND text, detection by detection in the reference's order (a later detection's rectangle overwrites an earlier
+// one's text where they overlap, a glyph blends over whatever is there): one CTA walks the list, its threads share the
+// pixels of the item in hand. A frame has a handful of detections; this is nowhere near the encoder's cost.
+__global__ void __launch_bounds__(256)
+draw_overlay_kernel(uint8_t* __restrict__ rgb, int w, int h, const int4* __restrict__ rects, const uint32_t* __restrict__ glyph_start,
+                    const OverlayGlyph* __restrict__ glyphs, const float* __restrict__ coverage, int n) {
+    for (int d = 0; d < n; ++d) {
+        const int4 r = rects[d];
+        const int rw = r.z - r.x + 1, rh = r.w - r.y + 1;
+        auto put = [&](int x, int y) {
+            if (x >= 0 && x < w && y >= 0 && y < h) {
+                uint8_t* p = rgb + ((size_t)y * w + x) * 3;
+                p[0] = 0; p[1] = 255; p[2] = 0;
+            }
+        };
+        for (int i = threadIdx.x; i < rw; i += blockDim.x) { put(r.x + i, r.y); put(r.x + i, r.w); }
+        for (int i = threadIdx.x; i < rh; i += blockDim.x) { put(r.x, r.y + i); put(r.z, r.y + i); }
+        __syncthreads();
+        for (uint32_t g = glyph_start[d]; g < glyph_start[d + 1]; ++g) {
+            const OverlayGlyph G = glyphs[g];
+            const uint32_t npx = G.w * G.h;
+            for (uint32_t i = threadIdx.x; i < npx; i += blockDim.x) {
+                const uint32_t gy = i / G.w, gx = i - gy * G.w;
+                const int x = G.x + (int)gx, y = G.y + (int)gy;
+                if (x < 0 || x >= w || y < 0 || y >= h) continue;
+                const float v = coverage[G.offset + i], lw = __fsub_rn(1.0f, v);
+                uint8_t* p = rgb + ((size_t)y * w + x) * 3;
+                p[0] = blend_u8(p[0], 0.0f, lw, v);
+                p[1] = blend_u8(p[1], 255.0f, lw, v);
+                p[2] = blend_u8(p[2], 0.0f, lw, v);
+            }
+            __syncthreads();  // the next glyph's box may overlap this one's
+        }
+    }
+}
+
+void launch_draw_overlay(uint8_t* rgb, int w, int h, const int4* d_rects, const uint32_t* d_glyph_start, const OverlayGlyph* d_glyphs,
+                         const float* d_coverage, int n, cudaStream_t s) {
+    if (n > 0) draw_overlay_kernel<<<1, 256, 0, s>>>(rgb, w, h, d_rects, d_glyph_start, d_glyphs, d_coverage, n);
+}
+
 __device__ __forceinline__ void jrgb2ycc(const uint8_t* __restrict__ p, int& y, int& cb, int& cr) {
     const int r = p[0], g = p[1], b = p[2];
     y = (19595 * r + 38470 * g + 7471 * b + 32768) >> 16;

@@ -186,6 +186,17 @@ class UltrafaceModel(InferModel):
         d = np.ascontiguousarray(np.asarray(dets, np.float32).reshape(-1, 5))
         return d, d.ctypes.data_as(C.c_void_p), len(d)
 
+    def text_atlas_set(self, charset: str, max_len: int, glyphs, coverage) -> None:
+        """Glyph atlas for the confidence text (uf_text_atlas_set): glyphs[pos][k] = (x0, y0, w, h, offset) of charset[k] as the
+        pos-th character, coverage = flat f32 array. charset "" removes the atlas (rectangles only)."""
+        if not charset:
+            _check(_capi.load().uf_text_atlas_set(self._h, None, 0, 0, None, None, 0))
+            return
+        g = np.asarray(glyphs, np.int64).reshape(max_len * len(charset), 5)
+        arr = (_capi.uf_glyph * len(g))(*[_capi.uf_glyph(int(a), int(b), int(c), int(d), int(e)) for a, b, c, d, e in g])
+        cov = np.ascontiguousarray(coverage, np.float32).ravel()
+        _check(_capi.load().uf_text_atlas_set(self._h, charset.encode("ascii"), len(charset), max_len, arr, cov.ctypes.data_as(C.c_void_p), cov.size))
+
     def draw_boxes(self, rgb: np.ndarray, dets, scale_w: float, scale_h: float) -> np.ndarray:
         img = _as_rgb(rgb)
         out = np.empty_like(img)
@@ -359,6 +370,13 @@ def onnx_inspect(path: str, width: int, height: int) -> dict:
     buf = C.create_string_buffer(need.value)
     _check(lib.uf_onnx_inspect(os.fsencode(path), width, height, buf, need.value, C.byref(need)))
     return json.loads(buf.value.decode())
+
+
+def confidence_text(confidence: float) -> str:
+    """The text the overlay prints for a confidence (Rust: format!("{:.2}%", confidence * 100.0) on f32). Host only."""
+    buf = C.create_string_buffer(32)
+    _check(_capi.load().uf_confidence_text(float(np.float32(confidence)), buf, 32))
+    return buf.value.decode("ascii")
 
 
 def jpeg_info(jpeg: bytes) -> dict:

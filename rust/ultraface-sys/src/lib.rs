@@ -24,6 +24,16 @@ pub struct uf_det {
     pub conf: f32,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct uf_glyph {
+    pub x0: i32,
+    pub y0: i32,
+    pub w: u32,
+    pub h: u32,
+    pub offset: u32,
+}
+
 pub const UF_OK: c_int = 0;
 pub const UF_ERR_INVALID_ARG: c_int = 1;
 pub const UF_ERR_IO: c_int = 2;
@@ -201,6 +211,9 @@ extern "C" {
     pub fn uf_jpeg_write_coefficients(w: u32, h: u32, quality: u32, coefs: *const i16, n_blocks: usize, out: *mut u8, cap: usize,
                                       out_len: *mut usize) -> c_int;
     pub fn uf_jpeg_quality_tables(quality: u32, lum64: *mut u16, chr64: *mut u16) -> c_int;
+    pub fn uf_text_atlas_set(m: *mut uf_model, charset: *const c_char, n_chars: u32, max_len: u32, glyphs: *const uf_glyph,
+                             coverage: *const f32, n_coverage: usize) -> c_int;
+    pub fn uf_confidence_text(confidence: f32, out: *mut c_char, cap: usize) -> c_int;
     pub fn uf_draw_boxes_rgb(m: *mut uf_model, rgb: *const u8, w: u32, h: u32, dets: *const uf_det, n_dets: u32, scale_w: f32,
                              scale_h: f32, out_rgb: *mut u8) -> c_int;
     // stream batcher + router

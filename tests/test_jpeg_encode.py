@@ -118,3 +118,64 @@ def test_gpu_annotate_reencode_from_jpeg(make_onnx, test_pics):
                                       np.asarray(Image.open(io.BytesIO(ref)).convert("RGB")))
     finally:
         m.close()
+
+
+# ---- text overlay (inferer.rs:80-88) ----
+def _synthetic_atlas(seed=0, charset="0123456789.%", max_len=7):
+    """Random glyph boxes and coverage in the shape a rusttype atlas has: 8 px advance, boxes that touch or overlap their
+    neighbours by a column, coverage in [0, 1] with plenty of exact 0 and 1."""
+    rng = np.random.default_rng(seed)
+    glyphs, cov = [], []
+    for pos in range(max_len):
+        row = []
+        for _ in charset:
+            w, h = int(rng.integers(0, 11)), int(rng.integers(1, 14))
+            x0, y0 = pos * 8 + int(rng.integers(-1, 3)), int(rng.integers(0, 6))
+            v = rng.random(w * h).astype(np.float32)
+            v[rng.random(w * h) < 0.2] = 0.0
+            v[rng.random(w * h) < 0.2] = 1.0
+            row.append((x0, y0, w, h, sum(len(c) for c in cov)))
+            cov.append(v)
+        glyphs.append(row)
+    return charset, max_len, glyphs, np.concatenate(cov)
+
+
+def test_confidence_text_is_rusts_two_decimal_format():
+    """format!("{:.2}%", confidence * 100.0) on f32: the f32 product, its exact value rounded to two decimals."""
+    rng = np.random.default_rng(0)
+    for c in list(rng.random(200).astype(np.float32)) + [np.float32(v) for v in (0.5, 0.999999, 1.0, 0.70125, 0.9, 0.12345678)]:
+        assert nn.confidence_text(c) == odraw.confidence_text(c)
+    assert nn.confidence_text(0.5) == "50.00%" and nn.confidence_text(1.0) == "100.00%"
+    assert nn.confidence_text(np.float32(0.9)) == "90.00%"      # 0.9f32 * 100f32 rounds to exactly 90
+    assert nn.confidence_text(np.float32(0.97531)) == "97.53%"
+
+
+@pytest.mark.gpu
+def test_gpu_text_overlay_matches_the_oracle(make_onnx, test_pics):
+    """Rectangles and text in the reference's order, glyphs blended as imageproc's draw_text_mut does, clipped at the frame's
+    edges, over a random atlas (the real one comes from rusttype through the binding)."""
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240))
+    try:
+        atlas = _synthetic_atlas(3)
+        m.text_atlas_set(*atlas)
+        boxes = np.concatenate([_boxes(), np.float32([[0.11, 0.21, 0.33, 0.5, 0.6251],     # overlaps the first one's text
+                                                      [0.93, 0.01, 0.99, 0.2, 0.87654],     # text runs off the right edge
+                                                      [0.4, 0.985, 0.6, 0.999, 1.0],        # ... and off the bottom; 7 characters
+                                                      [-0.01, -0.01, 0.2, 0.1, 0.5]])])     # origin above / left of the frame
+        for pic, (sw, sh) in ((test_pics["omar-lopez-T6zu4jFhVwg"], (640.0, 462.0)), (test_pics["bruce-mars-ZXq7xoo98b0"], (1280.0, 720.0)),
+                              (test_pics["michael-dam-mEZ3PoFGs_k"][:100, :90], (90.0, 100.0))):
+            got = m.draw_boxes(pic, boxes, sw, sh)
+            want = odraw.draw_boxes(pic, boxes, sw, sh, atlas)
+            np.testing.assert_array_equal(got, want)
+            assert (want != odraw.draw_boxes(pic, boxes, sw, sh)).any()  # the text shows
+        # the encoded file carries the text too
+        pic = test_pics["omar-lopez-T6zu4jFhVwg"]
+        ours = m.annotate_encode_jpeg(pic, boxes, 640.0, 462.0, quality=95)
+        ref = _pil_jpeg(odraw.draw_boxes(pic, boxes, 640.0, 462.0, atlas), 95)
+        np.testing.assert_array_equal(nn.jpeg_coefficients(ours)[1], nn.jpeg_coefficients(ref)[1])
+        m.text_atlas_set("", 0, [], [])  # removed: rectangles only again
+        np.testing.assert_array_equal(m.draw_boxes(pic, boxes, 640.0, 462.0), odraw.draw_boxes(pic, boxes, 640.0, 462.0))
+        with pytest.raises(nn.UltrafaceError):
+            m.text_atlas_set("01", 1, [[(0, 0, 4, 4, 0), (0, 0, 4, 4, 10)]], np.zeros(20, np.float32))  # second glyph overruns
+    finally:
+        m.close()
