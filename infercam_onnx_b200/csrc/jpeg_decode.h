@@ -2,14 +2,16 @@
 //
 // The reference decodes every frame on the CPU with libjpeg-turbo before the path starts
 // (`turbojpeg::decompress_image`, /root/reference/infer_server/src/inferer.rs:35; README.md:62-64: ~15 ms per frame for
-// decode + encode). Here only the inherently serial part — Huffman decoding of the entropy-coded segment — stays on the
-// host (jpeg_entropy.cc, one frame per worker thread); it emits the quantised coefficients as a compact list of nonzeros,
-// which is what crosses PCIe (typically a third of the RGB bytes). Dequantisation, the inverse DCT, chroma upsampling and
-// YCbCr -> RGB run on the GPU (kernels_jpeg.cu) and restate libjpeg-turbo's DEFAULT decoder bit for bit: `jpeg_idct_islow`
-// (jidctint.c), `h2v1_fancy_upsample` / `h2v2_fancy_upsample` (jdsample.c) and `ycc_rgb_convert` (jdcolor.c), the
-// algorithms tjDecompress2 runs with flags = 0. Scope: baseline sequential JPEG (SOF0 / SOF1 Huffman, 8 bit), one
-// interleaved scan, 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 — what a V4L2 MJPG webcam sends (cam_sender/src/sensors.rs).
-// Progressive files are refused with UF_ERR_UNSUPPORTED.
+// decode + encode). Here the host parses the headers and removes the 0xFF00 byte stuffing (jpeg_entropy.cc:
+// jpeg_prepare_bitstream); the entropy-coded bytes themselves cross PCIe and are Huffman-decoded on the GPU
+// (kernels_jpeg_huff.cu) into per-block lists of nonzero coefficients. Dequantisation, the inverse DCT, chroma upsampling and
+// YCbCr -> RGB (kernels_jpeg.cu) restate libjpeg-turbo's DEFAULT decoder bit for bit: `jpeg_idct_islow` (jidctint.c),
+// `h2v1_fancy_upsample` / `h2v2_fancy_upsample` (jdsample.c) and `ycc_rgb_convert` (jdcolor.c), the algorithms tjDecompress2
+// runs with flags = 0. A sequential host Huffman decoder (jpeg_entropy.cc: jpeg_entropy_decode, one frame per worker thread,
+// same list format) takes the frames the device decoder declines — restart intervals, markers inside the scan, truncated or
+// damaged data — and everything under UF_FLAG_JPEG_HOST_HUFFMAN. Scope: baseline sequential JPEG (SOF0 / SOF1 Huffman,
+// 8 bit), one interleaved scan, 1 or 3 components, 4:4:4 / 4:2:2 / 4:2:0 — what a V4L2 MJPG webcam sends
+// (cam_sender/src/sensors.rs). Progressive files are refused with UF_ERR_UNSUPPORTED.
 #pragma once
 #include <cstddef>
 #include <cstdint>

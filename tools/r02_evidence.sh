@@ -24,6 +24,14 @@ ncu --set full --clock-control none -k regex:"nms_mask|nms_sweep|post_kernel" -s
   echo "## r02_full_nms"; python tools/ncu_brief.py /tmp/r02_full_nms.ncu-rep
 } > $O/r02_ncu_full_per_launch.txt 2>&1
 python tools/ncu_traffic.py /tmp/r02_full_stage.ncu-rep /tmp/r02_full_nms.ncu-rep > $O/r02_ncu_dram_bytes.csv 2>> $O/r02_evidence_err.log
+# the JPEG front end (N2): where its time goes (event pairs per kernel family), and full captures of one 128-frame stage's
+# Huffman / IDCT / colour launches
+python tools/jpeg_profile.py 512 > $O/r02_jpeg_profile.txt 2>&1
+ncu --set full --clock-control none -k regex:"jhuff|jpeg_idct|jpeg_color" -s 16 -c 8 -o /tmp/r02_full_jpeg -f python tools/jpeg_profile.py 512 > $O/r02_ncu_full3.log 2>&1
+{
+  echo "# ncu --set full --clock-control none, the launches of one stage of tools/jpeg_profile.py 512 (JPEG in, Huffman decoding on the GPU)"
+  python tools/ncu_brief.py /tmp/r02_full_jpeg.ncu-rep
+} > $O/r02_ncu_jpeg_per_launch.txt 2>&1
 ncu -i /tmp/r02_full_stage.ncu-rep --page raw --csv 2>/dev/null | python -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin)); hdr=rows[0]; ik=hdr.index('Kernel Name')

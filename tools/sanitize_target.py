@@ -1,6 +1,7 @@
 """Small workload touching every round-2 kernel once, for compute-sanitizer (memcheck / racecheck / initcheck):
 fused resize+stem (interior and border tiles, both nets' geometries), the NMS bit-matrix path (frames with > 512 candidates,
-odd candidate counts), JPEG decode (4:4:4 / 4:2:2 / 4:2:0 / grey, odd sizes), rectangles + JPEG encode, the batcher."""
+odd candidate counts), JPEG decode with Huffman decoding on the device and on the host (4:4:4 / 4:2:2 / 4:2:0 / grey, odd sizes,
+truncated and bit-flipped files that the device decoder hands back), rectangles + text + JPEG encode, the batcher."""
 import io
 import os
 import sys
@@ -33,9 +34,28 @@ jpegs = [enc(frames[0], 90, 1), enc(frames[3], 80, 2), enc(frames[3][:9, :17], 8
 g = io.BytesIO()
 Image.fromarray(frames[3]).convert("L").save(g, "JPEG", quality=90)
 jpegs.append(g.getvalue())
-dj, cj = m.run_batch_jpeg(jpegs, cap=64)
-for j in jpegs:
+cut = jpegs[0][: len(jpegs[0]) // 2] + b"\xff\xd9"                      # truncated: the device decoder declines, the host redoes it
+flip = bytearray(jpegs[3]); flip[len(flip) // 2] ^= 0x10                  # damaged in the middle of the scan
+big = enc(np.repeat(np.repeat(frames[0], 2, 0), 2, 1), 92, 1)             # 1280x960: several CTAs per frame
+dj, cj = m.run_batch_jpeg(jpegs + [cut, bytes(flip), big], cap=64)
+for j in jpegs + [cut, bytes(flip)]:
     m.jpeg_decode_rgb(j)
+    m.jpeg_coefficients_gpu(j)
+from infercam_onnx_b200 import _capi  # noqa: E402
+mhh = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=p, max_batch=8, flags=_capi.UF_FLAG_JPEG_HOST_HUFFMAN)
+assert mhh.run_batch_jpeg(jpegs + [cut, bytes(flip), big], cap=64)[1] == cj
+mhh.close()
+arng = np.random.default_rng(5)
+aglyphs, acov, off = [], [], 0
+for pos in range(7):
+    row = []
+    for _ in "0123456789.%":
+        gw, gh = int(arng.integers(0, 10)), int(arng.integers(1, 13))
+        row.append((pos * 8 + int(arng.integers(-1, 2)), int(arng.integers(0, 5)), gw, gh, off))
+        acov.append(arng.random(gw * gh).astype(np.float32))
+        off += gw * gh
+    aglyphs.append(row)
+m.text_atlas_set("0123456789.%", 7, aglyphs, np.concatenate(acov))
 boxes = np.float32([[0.1, 0.2, 0.3, 0.6, 0.9], [-0.2, -0.1, 0.25, 0.3, 0.7], [0.8, 0.7, 1.4, 1.3, 0.6], [0, 0, 1, 1, 0.5]])
 for f in (frames[0], frames[3], frames[3][:9, :17]):
     m.draw_boxes(f, boxes, float(f.shape[1]), float(f.shape[0]))
