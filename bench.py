@@ -157,6 +157,37 @@ def batcher_leg(nn, path, w, h, local, rank, world, pinned, B, steps, barrier, m
     return total, dt, st
 
 
+def ingest_leg(nn, path, w, h, local, rank, world, B, steps, barrier, max_over_ranks):
+    """The reference's whole receive path on this rank's shard of 1 024 streams: wire message (bincode ProtoMsg::FrameMsg,
+    protocol.rs:7-28, carrying a 75 KB MJPG frame) -> uf_batcher_ingest (parse, hashed(id) -> owner GPU, lossy queue) -> batches
+    on a 2 ms deadline -> JPEG decode incl. Huffman on the GPU -> detections -> poll. 10 C++ producer threads stand in for
+    the socket tasks (uf_debug_batcher_drive_msgs). Returns (frames, seconds, stats)."""
+    import struct
+    import cv2
+    from infercam_onnx_b200 import streams
+    from infercam_onnx_b200.batcher import StreamBatcher
+    files = []
+    for f in smooth_frames(32, seed=7):
+        ok, buf = cv2.imencode(".jpg", f[:, :, ::-1], [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                                       cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422])
+        files.append(buf.tobytes())
+    msgs = []
+    for k, s in enumerate(streams.shard_streams(1024, rank, world)):
+        sid, data = ("stream-%d" % s).encode(), files[k % len(files)]
+        msgs.append(struct.pack("<I", 1) + struct.pack("<Q", len(sid)) + sid + struct.pack("<Q", len(data)) + data)  # ProtoMsg::FrameMsg
+    b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, size=(w, h), devices=(local,), max_batch=128,
+                      max_delay=0.002, capacity=4 * B, workers=4, cap=64, max_frame_bytes=256 * 1024)
+    b.drive_msgs(msgs, 3 * B, producers=10)  # warm-up
+    barrier()
+    total = B * steps
+    sec, _ = b.drive_msgs(msgs, total, producers=10)
+    barrier()
+    dt = max_over_ranks(sec)
+    st = b.stats()
+    b.close()
+    return total, dt, st
+
+
 def jpeg_leg(nn, model, timed, steps, warmup, B, cap, threads):
     """e2e with frames arriving as baseline JPEG (uf_infer_batch_jpeg). Smooth synthetic frames, quality 85, 4:2:2 (what an
     MJPG webcam sends). Returns (seconds one call at a time, seconds with `threads` calls in flight, bytes/frame, ..., out)."""
@@ -458,6 +489,12 @@ def main():
                                    "s % n_gpus (streams.shard_streams), 10 C++ producer threads copy frames into the owner GPU's pinned "
                                    "pool (wall-clock timed), batches of <= 128 formed on a 2 ms deadline, 3 in flight",
                             "batches": st["batches"], "mean_batch": st["completed"] / max(1, st["batches"]), "dropped_then_retried": st["dropped"]}
+        done_i, dt_i, st_i = ingest_leg(nn, path, w, h, local, rank, world, B, args.steps, barrier, max_over_ranks)
+        extra["ingest"] = {"value": done_i * world / dt_i, "unit": "frames/s",
+                           "api": "uf_batcher_ingest / uf_batcher_poll (C ABI): bincode ProtoMsg::FrameMsg wire messages (75 KB MJPG frames, 1 024 "
+                                  "stream ids) -> parse -> hashed(id) % n_gpus -> lossy queue -> batches of <= 128 on a 2 ms deadline, 4 in flight -> "
+                                  "JPEG decode incl. Huffman on the GPU -> detections; 10 C++ producer threads, wall-clock timed",
+                           "batches": st_i["batches"], "mean_batch": st_i["completed"] / max(1, st_i["batches"]), "dropped_then_retried": st_i["dropped"]}
         nfl = max(1, args.in_flight)
         dt_j1, dt_jn, jpeg_b, coef_b, out_j = jpeg_leg(nn, model, timed, args.steps, max(args.warmup, 3), B, cap, nfl)
         from infercam_onnx_b200 import _capi

@@ -337,6 +337,11 @@ UF_API int uf_debug_batcher_drive(uf_batcher* b, const uint8_t* frames, uint32_t
                                   const uint64_t* streams, uint32_t n_streams, uint64_t total, uint32_t producers, double* seconds,
                                   uint64_t* detections);
 
+/* The same for wire messages: message i = msgs[i % n_msgs] (bincode ProtoMsg::FrameMsg carrying a JPEG), handed to
+ * uf_batcher_ingest — parse, key the stream, queue the payload on its GPU; decode + detection in the batcher's workers. */
+UF_API int uf_debug_batcher_drive_msgs(uf_batcher* b, const uint8_t* const* msgs, const size_t* lens, uint32_t n_msgs, uint64_t total,
+                                       uint32_t producers, double* seconds, uint64_t* detections);
+
 /* ---- ingest helpers, host only (N4) ----
  * `hashed(&id)` of infer_server/src/lib.rs:39-46: Rust's DefaultHasher (SipHash-1-3, zero keys) over the bytes of the
  * stream name followed by the 0xff terminator `str::hash` appends. */

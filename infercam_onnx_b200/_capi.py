@@ -132,6 +132,8 @@ SIGNATURES = {
     "uf_batcher_model": (C.c_int, [C.c_void_p, C.c_uint32, _void_pp]),
     "uf_debug_batcher_drive": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _p(C.c_uint64), C.c_uint32, C.c_uint64,
                                          C.c_uint32, _p(C.c_double), _p(C.c_uint64)]),
+    "uf_debug_batcher_drive_msgs": (C.c_int, [C.c_void_p, _p(C.c_char_p), _p(C.c_size_t), C.c_uint32, C.c_uint64, C.c_uint32,
+                                              _p(C.c_double), _p(C.c_uint64)]),
     "uf_stream_hash": (C.c_int, [C.c_char_p, C.c_size_t, _p(C.c_uint64)]),
     "uf_protomsg_parse": (C.c_int, [C.c_char_p, C.c_size_t, _p(C.c_uint32), _void_pp, _p(C.c_size_t), _void_pp, _p(C.c_size_t)]),
     "uf_debug_siphash": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_char_p, C.c_size_t, _p(C.c_uint64)]),

@@ -173,6 +173,15 @@ class StreamBatcher:
                                                    C.byref(sec), C.byref(det)))
         return float(sec.value), int(det.value)
 
+    def drive_msgs(self, msgs: Sequence[bytes], total: int, producers: int = 4):
+        """Measurement aid (uf_debug_batcher_drive_msgs): C++ producers hand wire messages (bincode ProtoMsg::FrameMsg with a JPEG
+        payload) to uf_batcher_ingest, a C++ loop polls; returns (seconds, detections)."""
+        arr = (C.c_char_p * len(msgs))(*msgs)
+        lens = (C.c_size_t * len(msgs))(*[len(x) for x in msgs])
+        sec, det = C.c_double(), C.c_uint64()
+        _check(_capi.load().uf_debug_batcher_drive_msgs(self._h, arr, lens, len(msgs), total, producers, C.byref(sec), C.byref(det)))
+        return float(sec.value), int(det.value)
+
     def flush(self, timeout: float = 30.0) -> None:
         _check(_capi.load().uf_batcher_flush(self._h, int(timeout * 1e3)))
 

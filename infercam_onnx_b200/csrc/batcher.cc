@@ -545,6 +545,46 @@ int uf_debug_batcher_drive(uf_batcher* b, const uint8_t* frames, uint32_t n_fram
     });
 }
 
+int uf_debug_batcher_drive_msgs(uf_batcher* b, const uint8_t* const* msgs, const size_t* lens, uint32_t n_msgs, uint64_t total,
+                                uint32_t producers, double* seconds, uint64_t* detections) {
+    return guarded([&] {
+        NEED(b && msgs && lens && n_msgs && producers && producers <= 64 && seconds, "bad argument");
+        std::atomic<uint64_t> next{0}, errors{0};
+        const auto t0 = Clock::now();
+        std::vector<std::thread> ts;
+        for (uint32_t p = 0; p < producers; ++p)
+            ts.emplace_back([&] {
+                for (;;) {
+                    const uint64_t i = next.fetch_add(1);
+                    if (i >= total) return;
+                    for (;;) {
+                        int32_t ok = 0;
+                        if (uf_batcher_ingest(b, msgs[i % n_msgs], lens[i % n_msgs], i, &ok, nullptr) != UF_OK) { errors++; break; }
+                        if (ok) break;
+                        std::this_thread::sleep_for(std::chrono::microseconds(50));
+                    }
+                }
+            });
+        std::vector<uf_result> res(1024);
+        std::vector<uf_det> dets((size_t)1024 * b->cfg.det_cap);
+        uint64_t got = 0, ndet = 0, failed = 0;
+        while (got + errors.load() < total) {
+            uint32_t n = 0;
+            if (uf_batcher_poll(b, res.data(), dets.data(), 1024, 20, &n) != UF_OK) break;
+            for (uint32_t k = 0; k < n; ++k) {
+                ndet += res[k].n_dets;
+                failed += res[k].status != 0;
+            }
+            got += n;
+        }
+        for (auto& t : ts) t.join();
+        *seconds = std::chrono::duration<double>(Clock::now() - t0).count();
+        if (detections) *detections = ndet;
+        if (errors.load()) throw Fail{UF_ERR_INVALID_ARG, "uf_batcher_ingest failed for " + std::to_string(errors.load()) + " messages"};
+        if (failed) throw Fail{UF_ERR_INVALID_ARG, std::to_string(failed) + " frames came back with an error status"};
+    });
+}
+
 int uf_stream_hash(const uint8_t* name, size_t len, uint64_t* out) {
     return guarded([&] {
         NEED(out && (name || len == 0), "null argument");

@@ -235,6 +235,8 @@ extern "C" {
     pub fn uf_batcher_stats_read(b: *const uf_batcher, out: *mut uf_batcher_stats) -> c_int;
     pub fn uf_batcher_owner(b: *const uf_batcher, stream: u64, device: *mut i32) -> c_int;
     pub fn uf_batcher_model(b: *mut uf_batcher, device_slot: u32, out: *mut *mut uf_model) -> c_int;
+    pub fn uf_debug_batcher_drive_msgs(b: *mut uf_batcher, msgs: *const *const u8, lens: *const usize, n_msgs: u32, total: u64,
+                                       producers: u32, seconds: *mut f64, detections: *mut u64) -> c_int;
     pub fn uf_debug_batcher_drive(b: *mut uf_batcher, frames: *const u8, n_frames: u32, w: u32, h: u32, streams: *const u64,
                                   n_streams: u32, total: u64, producers: u32, seconds: *mut f64, detections: *mut u64) -> c_int;
     // ingest helpers

@@ -234,7 +234,7 @@ def test_gpu_ingest_of_wire_messages_end_to_end(make_onnx, test_pics):
         jpegs.append(b.getvalue())
     rgbs = [np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(j)).convert("RGB"))) for j in jpegs]
     m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=16)
-    exp, _ = m.run_batch(rgbs, cap=64)
+    exp, exp_counts = m.run_batch(rgbs, cap=64)
     m.close()
     b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, devices=(0, 0), max_batch=8, max_delay=0.002,
                       capacity=256, workers=2, cap=64)
@@ -268,5 +268,9 @@ def test_gpu_ingest_of_wire_messages_end_to_end(make_onnx, test_pics):
         late = {r["tag"]: r for r in b.poll(16)}
         assert late[7777]["status"] != 0 and late[7778]["status"] == 0
         np.testing.assert_array_equal(late[7778]["dets"], exp[0][:64])
+        # the measurement driver (C++ producers + poll loop over the same entry points) counts every frame's detections
+        msgs = [ingest.protomsg_frame(names[i % len(names)], j) for i, j in enumerate(jpegs)]
+        sec, ndet = b.drive_msgs(msgs, 3 * len(msgs), producers=3)
+        assert sec > 0 and ndet == 3 * sum(exp_counts)
     finally:
         b.close()
