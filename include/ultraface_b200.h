@@ -235,6 +235,14 @@ UF_API int uf_annotate_encode_jpeg(uf_model* m, const uint8_t* rgb, uint32_t w, 
 /* Same with the frame given as the baseline JPEG it arrived as (decoded on the GPU, N2; never leaves the device as pixels). */
 UF_API int uf_annotate_reencode_jpeg(uf_model* m, const uint8_t* jpeg, size_t len, const uf_det* dets, uint32_t n_dets,
                                      float scale_w, float scale_h, uint32_t quality, uint8_t* out, size_t cap, size_t* out_len);
+/* Batch form, the whole of inferer.rs:35-39 for n frames on the GPU: Huffman decoding, IDCT, colour (N2), rectangles + text,
+ * colour conversion, downsampling, forward DCT, quantisation, Huffman CODING and byte stuffing; the host parses the incoming
+ * headers and writes the outgoing ones. dets = all frames' detections back to back, det_counts[i] of them belong to frame i.
+ * Frame i's file is written at out + i * out_stride, out_len[i] bytes; UF_ERR_CAPACITY if one does not fit (every out_len is
+ * still set). The files are byte for byte the ones uf_annotate_reencode_jpeg writes. */
+UF_API int uf_annotate_reencode_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, const uf_det* dets,
+                                           const uint32_t* det_counts, float scale_w, float scale_h, uint32_t quality, uint8_t* out,
+                                           size_t out_stride, size_t* out_len);
 /* host only: the Huffman-coding / file-writing half alone. coefs = quantised blocks of a w x h YCbCr 4:2:0 frame, per
  * component plane (Y, Cb, Cr; each padded to whole 16x16 MCUs) in raster order, natural order inside a block; tables =
  * jpeg_set_quality(quality). uf_jpeg_quality_tables returns those tables (natural order). */

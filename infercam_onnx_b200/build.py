@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libultraface_b200.so")
-SOURCES = ["engine.cu", "kernels_preproc.cu", "kernels_prestem.cu", "kernels_jpeg.cu", "kernels_jpeg_enc.cu", "kernels_jpeg_huff.cu", "jpeg_encode.cc", "kernels_conv.cu", "kernels_post.cu", "kernels_tc.cu", "onnx_graph.cc", "plan.cc", "tail_check.cc", "batcher.cc", "jpeg_entropy.cc",
+SOURCES = ["engine.cu", "kernels_preproc.cu", "kernels_prestem.cu", "kernels_jpeg.cu", "kernels_jpeg_enc.cu", "kernels_jpeg_henc.cu", "kernels_jpeg_huff.cu", "jpeg_encode.cc", "kernels_conv.cu", "kernels_post.cu", "kernels_tc.cu", "onnx_graph.cc", "plan.cc", "tail_check.cc", "batcher.cc", "jpeg_entropy.cc",
            "resize_taps.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall", "-Xptxas", "-v",

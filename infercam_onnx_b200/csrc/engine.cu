@@ -1834,19 +1834,27 @@ static std::vector<int4> reference_rects(const uf_det* dets, uint32_t n, float w
     return r;
 }
 
-// draws on the RGB frame at s.d_in (device) and, if `file` is given, encodes it; everything on slot 0 of the locked lane
-static void annotate_on_device(uf_model& m, Slot& s, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets, float scale_w, float scale_h,
-                               int quality, std::vector<uint8_t>* file) {
+// What the overlay of one frame consists of: rectangles, and — when the model holds a glyph atlas — the placed glyphs of
+// every detection's text (glyphs of detection k: [gstart[k], gstart[k + 1])). text = false: rectangles only, order-free.
+struct OverlayLists {
+    std::vector<int4> rects;
+    std::vector<uint32_t> gstart;
+    std::vector<OverlayGlyph> glyphs;
+    bool text = false;
+};
+
+// (m.atlas_mu held by the caller)
+static void build_overlay_lists(uf_model& m, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets, float scale_w, float scale_h,
+                                OverlayLists& L) {
     std::vector<uint32_t> which;
     std::vector<int4> rects = reference_rects(dets, n_dets, scale_w, scale_h, &which);
-    std::unique_lock<std::mutex> atlas_lk(m.atlas_mu);
-    if (!m.atlas_chars.empty() && !rects.empty()) {
+    L.rects.clear(); L.gstart.clear(); L.glyphs.clear();
+    L.text = !m.atlas_chars.empty();
+    if (L.text) {
         // rectangles and text in the reference's order: one list, walked by one CTA (kernels_jpeg_enc.cu)
-        std::vector<uint32_t> gstart(rects.size() + 1, 0);
-        std::vector<OverlayGlyph> gl;
         const uint32_t nc = (uint32_t)m.atlas_chars.size();
         for (size_t k = 0; k < rects.size(); ++k) {
-            gstart[k] = (uint32_t)gl.size();
+            L.gstart.push_back((uint32_t)L.glyphs.size());
             const int ox = rects[k].x, oy = rects[k].y;  // x_tl as i32, y_tl as i32
             const std::string text = confidence_text(dets[which[k]].conf);
             for (uint32_t pos = 0; pos < text.size() && pos < m.atlas_max_len; ++pos) {
@@ -1856,37 +1864,68 @@ static void annotate_on_device(uf_model& m, Slot& s, uint32_t w, uint32_t h, con
                 if (g.w == 0 || g.h == 0) continue;
                 const int64_t gx = (int64_t)ox + g.x0, gy = (int64_t)oy + g.y0;
                 if (gx >= (int64_t)w || gy >= (int64_t)h || gx + (int64_t)g.w <= 0 || gy + (int64_t)g.h <= 0) continue;  // wholly outside
-                gl.push_back(OverlayGlyph{(int32_t)gx, (int32_t)gy, g.w, g.h, g.offset});
+                L.glyphs.push_back(OverlayGlyph{(int32_t)gx, (int32_t)gy, g.w, g.h, g.offset});
             }
             // (clamping a rectangle's far-off corners changes nothing: pixels outside the frame are skipped one by one)
-            rects[k] = make_int4(std::max(rects[k].x, -1), std::max(rects[k].y, -1), std::min(rects[k].z, (int)w), std::min(rects[k].w, (int)h));
-            if (rects[k].z < rects[k].x || rects[k].w < rects[k].y) rects[k] = make_int4(-1, -1, -2, -2);  // wholly outside: empty loops
+            int4 r = make_int4(std::max(rects[k].x, -1), std::max(rects[k].y, -1), std::min(rects[k].z, (int)w), std::min(rects[k].w, (int)h));
+            if (r.z < r.x || r.w < r.y) r = make_int4(-1, -1, -2, -2);  // wholly outside: empty loops
+            L.rects.push_back(r);
         }
-        gstart[rects.size()] = (uint32_t)gl.size();
-        const size_t b_r = rects.size() * sizeof(int4), b_s = (gstart.size() * 4 + 15) / 16 * 16, b_g = gl.size() * sizeof(OverlayGlyph);
-        uint8_t* d = (uint8_t*)hook_scratch(m, b_r + b_s + b_g + 16);
-        CK(cudaMemcpyAsync(d, rects.data(), b_r, cudaMemcpyHostToDevice, s.stream));
-        CK(cudaMemcpyAsync(d + b_r, gstart.data(), gstart.size() * 4, cudaMemcpyHostToDevice, s.stream));
-        if (b_g) CK(cudaMemcpyAsync(d + b_r + b_s, gl.data(), b_g, cudaMemcpyHostToDevice, s.stream));
-        m.launches++;
-        launch_draw_overlay(s.d_in, (int)w, (int)h, reinterpret_cast<const int4*>(d), reinterpret_cast<const uint32_t*>(d + b_r),
-                            reinterpret_cast<const OverlayGlyph*>(d + b_r + b_s), m.d_atlas, (int)rects.size(), s.stream);
-        CK(cudaStreamSynchronize(s.stream));  // the lists are pageable host memory
-        rects.clear();
+        L.gstart.push_back((uint32_t)L.glyphs.size());
+        return;
     }
-    atlas_lk.unlock();
     // no atlas: rectangles only, all at once (same colour: their order does not show). Clip rectangles that lie wholly
     // outside early (a box far off-frame would otherwise be a long empty loop)
-    std::vector<int4> vis;
     for (const int4& r : rects)
         if (r.z >= 0 && r.w >= 0 && r.x < (int)w && r.y < (int)h)
-            vis.push_back(make_int4(std::max(r.x, -1), std::max(r.y, -1), std::min(r.z, (int)w), std::min(r.w, (int)h)));
-    if (!vis.empty()) {
-        int4* d_rects = (int4*)hook_scratch(m, vis.size() * sizeof(int4));
-        CK(cudaMemcpyAsync(d_rects, vis.data(), vis.size() * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
+            L.rects.push_back(make_int4(std::max(r.x, -1), std::max(r.y, -1), std::min(r.z, (int)w), std::min(r.w, (int)h)));
+}
+
+// uploads the lists of `cnt` frames in one piece and draws every frame's overlay on its RGB image (d_rgb[k], w[k] x h[k]).
+// Synchronises the stream before returning (the lists are pageable host memory).
+static void draw_overlays(uf_model& m, Slot& s, const std::vector<OverlayLists>& L, uint8_t* const* d_rgb, const uint32_t* w, const uint32_t* h) {
+    size_t n_r = 0, n_s = 0, n_g = 0;
+    for (const auto& l : L) { n_r += l.rects.size(); n_s += l.gstart.size(); n_g += l.glyphs.size(); }
+    if (n_r == 0) return;
+    const size_t b_r = n_r * sizeof(int4), b_s = (n_s * 4 + 15) / 16 * 16, b_g = n_g * sizeof(OverlayGlyph);
+    std::vector<uint8_t> host(b_r + b_s + b_g + 16);
+    int4* hr = reinterpret_cast<int4*>(host.data());
+    uint32_t* hs = reinterpret_cast<uint32_t*>(host.data() + b_r);
+    OverlayGlyph* hg = reinterpret_cast<OverlayGlyph*>(host.data() + b_r + b_s);
+    uint8_t* d = (uint8_t*)hook_scratch(m, host.size());
+    size_t ir = 0, is = 0, ig = 0;
+    struct Job { size_t r, s, g; };
+    std::vector<Job> jobs;
+    for (const auto& l : L) {
+        jobs.push_back(Job{ir, is, ig});
+        if (!l.rects.empty()) memcpy(hr + ir, l.rects.data(), l.rects.size() * sizeof(int4));
+        for (size_t k = 0; k < l.gstart.size(); ++k) hs[is + k] = l.gstart[k];  // (relative to the frame's first glyph)
+        if (!l.glyphs.empty()) memcpy(hg + ig, l.glyphs.data(), l.glyphs.size() * sizeof(OverlayGlyph));
+        ir += l.rects.size(); is += l.gstart.size(); ig += l.glyphs.size();
+    }
+    CK(cudaMemcpyAsync(d, host.data(), host.size(), cudaMemcpyHostToDevice, s.stream));
+    for (size_t k = 0; k < L.size(); ++k) {
+        if (L[k].rects.empty()) continue;
         m.launches++;
-        launch_draw_rects(s.d_in, (int)w, (int)h, d_rects, (int)vis.size(), s.stream);
-        CK(cudaStreamSynchronize(s.stream));  // `vis` is pageable host memory
+        const int4* dr = reinterpret_cast<const int4*>(d) + jobs[k].r;
+        if (L[k].text)
+            launch_draw_overlay(d_rgb[k], (int)w[k], (int)h[k], dr, reinterpret_cast<const uint32_t*>(d + b_r) + jobs[k].s,
+                                reinterpret_cast<const OverlayGlyph*>(d + b_r + b_s) + jobs[k].g, m.d_atlas, (int)L[k].rects.size(), s.stream);
+        else
+            launch_draw_rects(d_rgb[k], (int)w[k], (int)h[k], dr, (int)L[k].rects.size(), s.stream);
+    }
+    CK(cudaStreamSynchronize(s.stream));
+}
+
+// draws on the RGB frame at s.d_in (device) and, if `file` is given, encodes it; everything on slot 0 of the locked lane
+static void annotate_on_device(uf_model& m, Slot& s, uint32_t w, uint32_t h, const uf_det* dets, uint32_t n_dets, float scale_w, float scale_h,
+                               int quality, std::vector<uint8_t>* file) {
+    {
+        std::lock_guard<std::mutex> atlas_lk(m.atlas_mu);  // (held until the overlay has been drawn: the atlas is in use)
+        std::vector<OverlayLists> L(1);
+        build_overlay_lists(m, w, h, dets, n_dets, scale_w, scale_h, L[0]);
+        uint8_t* rgb = s.d_in;
+        draw_overlays(m, s, L, &rgb, &w, &h);
     }
     if (!file) return;
     const JpegPlan plan = jpeg_encode_plan(w, h, quality);
@@ -1984,6 +2023,190 @@ int uf_annotate_reencode_jpeg(uf_model* m, const uint8_t* jpeg, size_t len, cons
         std::vector<uint8_t> file;
         annotate_on_device(*m, s, jc.plan.w, jc.plan.h, dets, n_dets, scale_w, scale_h, (int)quality, &file);
         deliver_file(file, out, cap, out_len);
+    });
+}
+
+// One chunk of the batch form: frames [0, cnt) of jpeg/len, their detections at dets + det_first[k]; files to out + k * stride.
+// Everything runs on slot 0 of the caller's lane, stage after stage, with three waits for the device (decode status, the
+// sizes of the entropy-coded segments, the segments themselves).
+static void reencode_chunk(uf_model& m, Slot& s, const uint8_t* const* jpeg, const size_t* len, uint32_t cnt, const uf_det* dets,
+                           const uint32_t* det_first, const uint32_t* det_counts, float scale_w, float scale_h, int quality, uint8_t* out,
+                           size_t stride, size_t* out_len, uint32_t first_index) {
+    auto a256 = [](size_t v) { return (v + 255) / 256 * 256; };
+    // 1. headers, byte unstuffing (host threads)
+    std::vector<JpegBitstream> bs(cnt);
+    std::vector<JpegCoefs> hostc(cnt);
+    std::vector<JpegError> errs(cnt, JpegError{UF_OK, ""});
+    m.pool().parallel_for(cnt, [&](uint32_t i) {
+        try {
+            jpeg_prepare_bitstream(jpeg[i], len[i], bs[i]);
+            if (!bs[i].gpu_ok) jpeg_entropy_decode(jpeg[i], len[i], hostc[i]);
+        } catch (const JpegError& e) { errs[i] = e; }
+        catch (const std::exception& e) { errs[i] = JpegError{UF_ERR_INVALID_ARG, e.what()}; }
+    });
+    for (uint32_t i = 0; i < cnt; ++i)
+        if (errs[i].code != UF_OK) throw JpegError{errs[i].code, "frame " + std::to_string(first_index + i) + ": " + errs[i].msg};
+    // 2. sizes: RGB frames, decoder staging / scratch, encoder planes / coefficients / bit buffers
+    std::vector<size_t> rgb_off(cnt), pl_off(cnt), co_off(cnt);
+    std::vector<JpegPlan> eplan(cnt);
+    std::vector<FrameSrc> fr(cnt);
+    size_t rgb_bytes = 0, jpeg_need = 0, planes_dec = 0, huff_dec = 0, planes_enc = 0, coef_bytes = 0, nblk_all = 0, pack_words = 0, out_bytes = 0;
+    uint32_t max_nblk = 0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const JpegPlan& dp = bs[k].plan;
+        rgb_off[k] = rgb_bytes;
+        rgb_bytes += (size_t)dp.w * dp.h * 3;
+        if (k + 1 < cnt && (bs[k + 1].plan.w != dp.w || bs[k + 1].plan.h != dp.h || bs[k + 1].gpu_ok != bs[k].gpu_ok)) rgb_bytes = a256(rgb_bytes);
+        if (bs[k].gpu_ok) {
+            fr[k] = FrameSrc{nullptr, dp.w, dp.h, nullptr, &bs[k]};
+            jpeg_need += huff_stage_bytes(bs[k]);
+            huff_dec += huff_scratch_bytes(bs[k]);
+        } else {
+            fr[k] = FrameSrc{nullptr, dp.w, dp.h, &hostc[k], nullptr};
+            jpeg_need += jpeg_stage_bytes(hostc[k]);
+        }
+        // (a frame the device decoder hands back is redone through the host decoder's staging: reserve for it too)
+        planes_dec += dp.plane_bytes;
+        eplan[k] = jpeg_encode_plan(dp.w, dp.h, quality);
+        pl_off[k] = planes_enc;
+        planes_enc += a256(eplan[k].plane_bytes);
+        co_off[k] = coef_bytes;
+        coef_bytes += a256((size_t)eplan[k].plane_bytes * sizeof(int16_t));
+        nblk_all += eplan[k].nblocks;
+        max_nblk = std::max(max_nblk, eplan[k].nblocks);
+        pack_words += (size_t)eplan[k].nblocks * 24;          // 96 bytes of bit buffer per block (a q95 block takes ~20)
+        out_bytes += a256((size_t)eplan[k].nblocks * 120);    // + room for the stuffed zeros
+    }
+    const size_t e_frames = a256(coef_bytes), e_tab = a256(e_frames + cnt * sizeof(JpegEncFrame)), e_len = a256(e_tab + sizeof(JpegEncTables)),
+                 e_off = a256(e_len + nblk_all * 4), e_fb = a256(e_off + nblk_all * 4), e_ol = a256(e_fb + cnt * 4), e_pack = a256(e_ol + cnt * 4),
+                 e_out = a256(e_pack + pack_words * 4), e_end = e_out + out_bytes;
+    grow_input(s, rgb_bytes + 256);
+    grow_jpeg(s, std::max(jpeg_need, a256(cnt * sizeof(JpegEncFrame)) + sizeof(JpegEncTables) + 512), std::max(planes_dec, planes_enc));
+    grow_huff(s, std::max(huff_dec, e_end));
+    // 3. decode: runs of same-size frames; then the frames the device decoder handed back, one by one
+    size_t ju = 0, pu = 0, hu = 0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        s.h_jstatus[k] = 0;
+        if (fr[k].w > 8192 || fr[k].h > 8192) throw ArgError(UF_ERR_UNSUPPORTED, "frame " + std::to_string(first_index + k) + ": larger than 8192 x 8192");
+    }
+    for (uint32_t i = 0; i < cnt;) {
+        uint32_t j = i + 1;
+        while (j < cnt && fr[j].w == fr[i].w && fr[j].h == fr[i].h && (fr[j].jb != nullptr) == (fr[i].jb != nullptr)) ++j;
+        if (fr[i].jb) decode_jpeg_run_gpu(m, s, fr.data() + i, i, j - i, s.d_in + rgb_off[i], ju, pu, hu);
+        else decode_jpeg_run(m, s, fr.data() + i, j - i, s.d_in + rgb_off[i], ju, pu);
+        i = j;
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    s.jstatus_n = 0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        if (!fr[k].jb || s.h_jstatus[k] == 0) continue;
+        jpeg_entropy_decode(jpeg[k], len[k], hostc[k]);
+        grow_jpeg(s, jpeg_stage_bytes(hostc[k]), hostc[k].plan.plane_bytes);
+        FrameSrc one{nullptr, hostc[k].plan.w, hostc[k].plan.h, &hostc[k], nullptr};
+        size_t ju1 = 0, pu1 = 0;
+        decode_jpeg_run(m, s, &one, 1, s.d_in + rgb_off[k], ju1, pu1);
+        CK(cudaStreamSynchronize(s.stream));
+        m.jpeg_redone++;
+    }
+    // 4. overlay
+    {
+        std::lock_guard<std::mutex> atlas_lk(m.atlas_mu);
+        std::vector<OverlayLists> L(cnt);
+        std::vector<uint8_t*> rgb(cnt);
+        std::vector<uint32_t> ws(cnt), hs(cnt);
+        for (uint32_t k = 0; k < cnt; ++k) {
+            ws[k] = fr[k].w; hs[k] = fr[k].h; rgb[k] = s.d_in + rgb_off[k];
+            build_overlay_lists(m, ws[k], hs[k], dets + det_first[k], det_counts[k], scale_w, scale_h, L[k]);
+        }
+        draw_overlays(m, s, L, rgb.data(), ws.data(), hs.data());
+    }
+    // 5. colour conversion, downsampling, forward DCT, quantisation — then Huffman coding and byte stuffing, all frames at once
+    int16_t* d_coefs = reinterpret_cast<int16_t*>(s.d_huff);
+    JpegEncFrame* hf = reinterpret_cast<JpegEncFrame*>(s.h_jpeg);
+    size_t lb = 0, pw = 0, ob = 0;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const JpegPlan& p = eplan[k];
+        m.launches += 2;
+        launch_jpeg_encode(s.d_in + rgb_off[k], p, s.d_planes + pl_off[k], d_coefs + co_off[k] / sizeof(int16_t), s.stream);
+        JpegEncFrame f{};
+        f.coef_base = (uint32_t)(co_off[k] / 128);
+        f.mcus_x = p.mcus_x; f.mcus_y = p.mcus_y;
+        f.y_bw = p.plane_w[0] / 8; f.c_bw = p.plane_w[1] / 8;
+        f.cb_off = p.plane_off[1] / 64; f.cr_off = p.plane_off[2] / 64;
+        f.wib0 = (p.real_w[0] + 7) / 8; f.hib0 = (p.real_h[0] + 7) / 8;
+        f.nblocks = p.nblocks;
+        f.len_base = (uint32_t)lb; lb += p.nblocks;
+        f.pack_off = (uint32_t)pw; f.pack_cap_bits = p.nblocks * 24 * 32; pw += (size_t)p.nblocks * 24;
+        f.out_off = (uint32_t)ob; f.out_cap = (uint32_t)a256((size_t)p.nblocks * 120); ob += f.out_cap;
+        hf[k] = f;
+    }
+    JpegEncTables* ht = reinterpret_cast<JpegEncTables*>(s.h_jpeg + a256(cnt * sizeof(JpegEncFrame)));
+    jpeg_std_enc_tables(*ht);
+    CK(cudaMemcpyAsync(s.d_huff + e_frames, hf, cnt * sizeof(JpegEncFrame), cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_huff + e_tab, ht, sizeof(JpegEncTables), cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemsetAsync(s.d_huff + e_pack, 0, pack_words * 4, s.stream));
+    JpegEncBatch B{reinterpret_cast<const JpegEncFrame*>(s.d_huff + e_frames), d_coefs, reinterpret_cast<const JpegEncTables*>(s.d_huff + e_tab),
+                   reinterpret_cast<uint32_t*>(s.d_huff + e_len), reinterpret_cast<uint32_t*>(s.d_huff + e_off),
+                   reinterpret_cast<uint32_t*>(s.d_huff + e_fb), reinterpret_cast<uint32_t*>(s.d_huff + e_pack), s.d_huff + e_out,
+                   reinterpret_cast<uint32_t*>(s.d_huff + e_ol)};
+    m.launches += 4;
+    launch_jpeg_huffman_encode(B, (int)cnt, max_nblk, s.stream);
+    uint32_t* h_len = reinterpret_cast<uint32_t*>(s.h_jstatus);
+    CK(cudaMemcpyAsync(h_len, s.d_huff + e_ol, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    // 6. files: headers + segment + EOI, straight into the caller's buffer
+    std::vector<uint8_t> head, file;
+    bool too_small = false;
+    for (uint32_t k = 0; k < cnt; ++k) {
+        uint8_t* dst = out + (size_t)k * stride;
+        if (h_len[k] == 0xffffffffu) {  // did not fit the device buffers (far denser than any camera frame): host encoder
+            std::vector<int16_t> co((size_t)eplan[k].plane_bytes);
+            CK(cudaMemcpy(co.data(), d_coefs + co_off[k] / sizeof(int16_t), co.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
+            jpeg_write_file(eplan[k], co.data(), file);
+            out_len[k] = file.size();
+            if (file.size() > stride) too_small = true;
+            else memcpy(dst, file.data(), file.size());
+            continue;
+        }
+        jpeg_write_headers(eplan[k], head);
+        out_len[k] = head.size() + h_len[k] + 2;
+        if (out_len[k] > stride) { too_small = true; continue; }
+        memcpy(dst, head.data(), head.size());
+        CK(cudaMemcpyAsync(dst + head.size(), s.d_huff + e_out + hf[k].out_off, h_len[k], cudaMemcpyDeviceToHost, s.stream));
+        dst[head.size() + h_len[k]] = 0xff;
+        dst[head.size() + h_len[k] + 1] = 0xd9;
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaGetLastError());
+    if (too_small) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
+}
+
+int uf_annotate_reencode_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, const uf_det* dets,
+                                    const uint32_t* det_counts, float scale_w, float scale_h, uint32_t quality, uint8_t* out, size_t out_stride,
+                                    size_t* out_len) {
+    return guarded([&] {
+        REQUIRE(m && out_len && (n == 0 || (jpeg && len && det_counts && out)) && out_stride >= 1024, "bad argument");
+        for (uint32_t i = 0; i < n; ++i) REQUIRE(jpeg[i] && len[i] > 0, "null frame");
+        std::vector<uint32_t> first(n + 1, 0);
+        for (uint32_t i = 0; i < n; ++i) first[i + 1] = first[i] + det_counts[i];
+        REQUIRE(first[n] == 0 || dets, "null detections");
+        LaneLock ll(*m, false);
+        Slot& s = ll.lane->slots[0];
+        CK(cudaSetDevice(m->cfg.device));
+        const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(32, m->chunk));
+        bool too_small = false;
+        for (uint32_t f0 = 0; f0 < n; f0 += step) {
+            const uint32_t cnt = std::min(step, n - f0);
+            try {
+                reencode_chunk(*m, s, jpeg + f0, len + f0, cnt, dets, first.data() + f0, det_counts + f0, scale_w, scale_h, (int)quality,
+                               out + (size_t)f0 * out_stride, out_stride, out_len + f0, f0);
+            } catch (const ArgError& e) {
+                if (e.code != UF_ERR_CAPACITY) throw;
+                too_small = true;  // the other chunks still report their sizes
+            }
+        }
+        ll.lane->last_n = 0;
+        if (too_small) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
     });
 }
 

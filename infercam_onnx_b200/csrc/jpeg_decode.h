@@ -112,6 +112,12 @@ void jpeg_quality_tables(int quality, uint16_t lum[64], uint16_t chr[64]);   // 
 JpegPlan jpeg_encode_plan(uint32_t w, uint32_t h, int quality);              // YCbCr 4:2:0 geometry + tables
 // coefs: quantised blocks per component plane in raster order (see jpeg_encode.cc); writes a complete JFIF file
 void jpeg_write_file(const JpegPlan& p, const int16_t* coefs, std::vector<uint8_t>& out);
+void jpeg_write_headers(const JpegPlan& p, std::vector<uint8_t>& out);  // SOI .. SOS (the entropy-coded segment and EOI follow)
+struct JpegEncTables {     // Annex K tables in encoder form: (length << 16) | code; [0] luma, [1] chroma
+    uint32_t dc[2][16];
+    uint32_t ac[2][256];
+};
+void jpeg_std_enc_tables(JpegEncTables& t);                             // the Annex K tables as the device encoder reads them
 
 // Parses the headers only. Throws JpegError.
 JpegPlan jpeg_parse_header(const uint8_t* data, size_t len);

@@ -166,12 +166,8 @@ JpegPlan jpeg_encode_plan(uint32_t w, uint32_t h, int quality) {
     return p;
 }
 
-// coefs: quantised blocks per component PLANE in raster order ([plane_off[c] / 64 + by * (plane_w[c] / 8) + bx][64], natural
-// order inside a block), every block of the padded planes computed from edge-replicated samples. Blocks wholly outside the
-// component (libjpeg's dummy blocks: beyond ceil(real_w / 8) in a row, beyond ceil(real_h / 8) rows) are replaced here by
-// libjpeg's rule: all AC zero, DC = the DC of the block before it in the MCU.
-void jpeg_write_file(const JpegPlan& p, const int16_t* coefs, std::vector<uint8_t>& out) {
-    static const EncTable dc_l(kDcLumBits, kDcVals), dc_c(kDcChrBits, kDcVals), ac_l(kAcLumBits, kAcLumVals), ac_c(kAcChrBits, kAcChrVals);
+// SOI, JFIF APP0, DQT x 2, SOF0, DHT x 4, SOS
+void jpeg_write_headers(const JpegPlan& p, std::vector<uint8_t>& out) {
     out.clear();
     out.reserve((size_t)p.w * p.h / 2 + 1024);
     const uint8_t head[] = {0xff, 0xd8, 0xff, 0xe0, 0, 16, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0};  // JFIF 1.01, aspect 1:1
@@ -195,7 +191,28 @@ void jpeg_write_file(const JpegPlan& p, const int16_t* coefs, std::vector<uint8_
     put_dht(out, 0x11, kAcChrBits, kAcChrVals, 162);
     const uint8_t sos[] = {0xff, 0xda, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0};
     out.insert(out.end(), sos, sos + sizeof(sos));
+}
 
+void jpeg_std_enc_tables(JpegEncTables& t) {
+    static const EncTable dc_l(kDcLumBits, kDcVals), dc_c(kDcChrBits, kDcVals), ac_l(kAcLumBits, kAcLumVals), ac_c(kAcChrBits, kAcChrVals);
+    memset(&t, 0, sizeof(t));
+    for (int i = 0; i < 12; ++i) {
+        t.dc[0][i] = ((uint32_t)dc_l.len[i] << 16) | dc_l.code[i];
+        t.dc[1][i] = ((uint32_t)dc_c.len[i] << 16) | dc_c.code[i];
+    }
+    for (int i = 0; i < 256; ++i) {
+        t.ac[0][i] = ((uint32_t)ac_l.len[i] << 16) | ac_l.code[i];
+        t.ac[1][i] = ((uint32_t)ac_c.len[i] << 16) | ac_c.code[i];
+    }
+}
+
+// coefs: quantised blocks per component PLANE in raster order ([plane_off[c] / 64 + by * (plane_w[c] / 8) + bx][64], natural
+// order inside a block), every block of the padded planes computed from edge-replicated samples. Blocks wholly outside the
+// component (libjpeg's dummy blocks: beyond ceil(real_w / 8) in a row, beyond ceil(real_h / 8) rows) are replaced here by
+// libjpeg's rule: all AC zero, DC = the DC of the block before it in the MCU.
+void jpeg_write_file(const JpegPlan& p, const int16_t* coefs, std::vector<uint8_t>& out) {
+    static const EncTable dc_l(kDcLumBits, kDcVals), dc_c(kDcChrBits, kDcVals), ac_l(kAcLumBits, kAcLumVals), ac_c(kAcChrBits, kAcChrVals);
+    jpeg_write_headers(p, out);
     BitWriter bw(out);
     int last_dc[3] = {0, 0, 0};
     uint32_t wib[3], hib[3];

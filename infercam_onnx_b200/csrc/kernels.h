@@ -189,6 +189,35 @@ void launch_draw_overlay(uint8_t* rgb, int w, int h, const int4* d_rects, const 
                          const float* d_coverage, int n, cudaStream_t s);
 void launch_jpeg_encode(const uint8_t* d_rgb, const JpegPlan& plan, uint8_t* d_planes, int16_t* d_coefs, cudaStream_t s);
 
+// ---- N3: Huffman coding of quantised 4:2:0 frames on the GPU (kernels_jpeg_henc.cu)
+struct JpegEncTables;      // jpeg_decode.h
+struct JpegEncFrame {      // plain data, copied to the device as is
+    uint32_t coef_base;    // index of the frame's first block in the coefficient buffer (blocks per plane in raster order)
+    uint32_t mcus_x, mcus_y;
+    uint32_t y_bw, c_bw;   // blocks per row of the padded luma / chroma planes
+    uint32_t cb_off, cr_off;  // first block of the Cb / Cr plane, relative to coef_base
+    uint32_t wib0, hib0;   // luma blocks per row / column that hold image samples (beyond: libjpeg's dummy blocks)
+    uint32_t nblocks;      // mcus * 6, in MCU order
+    uint32_t len_base;     // index of the frame's first block in the bit-count / bit-offset arrays
+    uint32_t pack_off;     // word offset of the frame's bit buffer
+    uint32_t pack_cap_bits;
+    uint32_t out_off;      // byte offset of the frame's entropy-coded segment in the output buffer
+    uint32_t out_cap;
+    uint32_t pad_;
+};
+struct JpegEncBatch {
+    const JpegEncFrame* frames;
+    const int16_t* coefs;
+    const JpegEncTables* tables;
+    uint32_t* bitlen;      // [blocks of all frames]
+    uint32_t* bitoff;
+    uint32_t* frame_bits;  // [frames]
+    uint32_t* packed;      // zeroed by the caller
+    uint8_t* out;
+    uint32_t* out_len;     // [frames] bytes of the entropy-coded segment; 0xffffffff: did not fit (the host encoder takes the frame)
+};
+void launch_jpeg_huffman_encode(const JpegEncBatch& B, int frames, uint32_t max_nblocks, cudaStream_t s);
+
 // ---- K9-K11: threshold + sort + greedy NMS, one CTA per frame (nn.rs:109-140,198-260)
 struct PostBuffers {
     unsigned long long* sort_scratch;  // [frames][sort_cap] keys, used when candidates exceed smem

@@ -186,6 +186,24 @@ class UltrafaceModel(InferModel):
         d = np.ascontiguousarray(np.asarray(dets, np.float32).reshape(-1, 5))
         return d, d.ctypes.data_as(C.c_void_p), len(d)
 
+    def annotate_reencode_batch_jpeg(self, jpegs: Sequence[bytes], dets_per_frame, scale_w: float, scale_h: float, quality: int = 95,
+                                     out_stride: int = 0) -> List[bytes]:
+        """Batch form of annotate_encode_jpeg for JPEG input: decode, overlay and encode on the GPU (entropy coding included)."""
+        n = len(jpegs)
+        bufs = [C.create_string_buffer(bytes(j), len(j)) for j in jpegs]
+        ptrs = (C.c_void_p * max(n, 1))(*[C.cast(b, C.c_void_p) for b in bufs])
+        lens = (C.c_size_t * max(n, 1))(*[len(j) for j in jpegs])
+        flat = [np.asarray(d, np.float32).reshape(-1, 5) for d in dets_per_frame]
+        counts = (C.c_uint32 * max(n, 1))(*[len(d) for d in flat])
+        alld = np.ascontiguousarray(np.concatenate(flat) if flat else np.zeros((0, 5), np.float32))
+        if not out_stride:
+            out_stride = max(len(j) for j in jpegs) * 8 + (1 << 16) if n else 1024
+        out = np.empty(max(n, 1) * out_stride, np.uint8)
+        out_len = (C.c_size_t * max(n, 1))()
+        _check(_capi.load().uf_annotate_reencode_batch_jpeg(self._h, ptrs, lens, n, alld.ctypes.data_as(C.c_void_p), counts, scale_w, scale_h,
+                                                            quality, out.ctypes.data_as(C.c_void_p), out_stride, out_len))
+        return [out[i * out_stride:i * out_stride + out_len[i]].tobytes() for i in range(n)]
+
     def text_atlas_set(self, charset: str, max_len: int, glyphs, coverage) -> None:
         """Glyph atlas for the confidence text (uf_text_atlas_set): glyphs[pos][k] = (x0, y0, w, h, offset) of charset[k] as the
         pos-th character, coverage = flat f32 array. charset "" removes the atlas (rectangles only)."""

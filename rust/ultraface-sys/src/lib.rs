@@ -211,6 +211,9 @@ extern "C" {
     pub fn uf_jpeg_write_coefficients(w: u32, h: u32, quality: u32, coefs: *const i16, n_blocks: usize, out: *mut u8, cap: usize,
                                       out_len: *mut usize) -> c_int;
     pub fn uf_jpeg_quality_tables(quality: u32, lum64: *mut u16, chr64: *mut u16) -> c_int;
+    pub fn uf_annotate_reencode_batch_jpeg(m: *mut uf_model, jpeg: *const *const u8, len: *const usize, n: u32, dets: *const uf_det,
+                                           det_counts: *const u32, scale_w: f32, scale_h: f32, quality: u32, out: *mut u8,
+                                           out_stride: usize, out_len: *mut usize) -> c_int;
     pub fn uf_text_atlas_set(m: *mut uf_model, charset: *const c_char, n_chars: u32, max_len: u32, glyphs: *const uf_glyph,
                              coverage: *const f32, n_coverage: usize) -> c_int;
     pub fn uf_confidence_text(confidence: f32, out: *mut c_char, cap: usize) -> c_int;

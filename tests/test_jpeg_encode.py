@@ -179,3 +179,46 @@ def test_gpu_text_overlay_matches_the_oracle(make_onnx, test_pics):
             m.text_atlas_set("01", 1, [[(0, 0, 4, 4, 0), (0, 0, 4, 4, 10)]], np.zeros(20, np.float32))  # second glyph overruns
     finally:
         m.close()
+
+
+@pytest.mark.gpu
+def test_gpu_batch_reencode_writes_the_single_frame_files(make_onnx, test_pics):
+    """uf_annotate_reencode_batch_jpeg (everything on the GPU incl. Huffman decoding AND coding, byte stuffing) must write, byte
+    for byte, the files the per-frame call writes with the host Huffman coder — mixed sizes and samplings in one batch, odd
+    sizes (dummy blocks), a restart-interval frame and a truncated frame (both decoded by the host decoder), more frames than
+    one chunk, with and without the text overlay."""
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=make_onnx(320, 240), max_batch=64)
+    try:
+        rng = np.random.default_rng(11)
+        pics = list(test_pics.values())
+
+        def enc(a, q, ss, **kw):
+            b = io.BytesIO()
+            Image.fromarray(a).save(b, "JPEG", quality=q, subsampling=ss, **kw)
+            return b.getvalue()
+        jpegs = [enc(rng.integers(0, 256, (480, 640, 3), dtype=np.uint8), 92, 1) for _ in range(5)]          # dense: many 0xFF bytes
+        jpegs += [enc(p, 85, 2) for p in pics] + [enc(pics[0][:301, :333], 80, 1), enc(pics[1][:9, :17], 90, 0), enc(pics[2][:100, :90], 75, 2)]
+        jpegs += [enc(np.full((240, 320, 3), 128, np.uint8), 95, 2)]                                          # flat: one DC, all EOB
+        jpegs += [jpegs[6][: len(jpegs[6]) * 2 // 3] + b"\xff\xd9"]                                           # truncated
+        try:
+            import cv2
+            ok, buf = cv2.imencode(".jpg", pics[3][:, :, ::-1], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 5])
+            jpegs.append(buf.tobytes())
+        except ImportError:
+            pass
+        jpegs = jpegs * 3                                                                                     # > 32 frames: several chunks
+        dets = [_boxes()[: (i % 5) + (i % 2)] for i in range(len(jpegs))]                                     # incl. frames without detections
+        for atlas in (None, _synthetic_atlas(7)):
+            if atlas:
+                m.text_atlas_set(*atlas)
+            got = m.annotate_reencode_batch_jpeg(jpegs, dets, 640.0, 480.0, quality=95)
+            for i, (j, d) in enumerate(zip(jpegs, dets)):
+                want = m.annotate_encode_jpeg(j, d, 640.0, 480.0, quality=95)
+                assert got[i] == want, (i, len(got[i]), len(want), atlas is not None)
+        low = m.annotate_reencode_batch_jpeg(jpegs[:3], dets[:3], 640.0, 480.0, quality=30)
+        assert low[0] == m.annotate_encode_jpeg(jpegs[0], dets[0], 640.0, 480.0, quality=30)
+        with pytest.raises(nn.UltrafaceError) as e:
+            m.annotate_reencode_batch_jpeg(jpegs[:4], dets[:4], 640.0, 480.0, out_stride=2048)
+        assert e.value.code == 7  # UF_ERR_CAPACITY
+    finally:
+        m.close()
