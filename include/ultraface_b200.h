@@ -243,6 +243,13 @@ UF_API int uf_annotate_reencode_jpeg(uf_model* m, const uint8_t* jpeg, size_t le
 UF_API int uf_annotate_reencode_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, const uf_det* dets,
                                            const uint32_t* det_counts, float scale_w, float scale_h, uint32_t quality, uint8_t* out,
                                            size_t out_stride, size_t* out_len);
+/* The whole body of the reference's worker loop for n frames in one call (inferer.rs:35-46: decompress_image -> infer_faces ->
+ * draw_bboxes_on_image -> compress_image): the frames are decoded once, the hot path runs on the decoded pixels where they
+ * lie in device memory, the detections found (at most cap per frame, dets[i * cap ..], n_dets[i] = how many were selected) are
+ * drawn and the annotated frames encoded. Output buffers as above. */
+UF_API int uf_worker_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, float scale_w, float scale_h,
+                                uint32_t quality, uf_det* dets, uint32_t cap, uint32_t* n_dets, uint8_t* out, size_t out_stride,
+                                size_t* out_len);
 /* host only: the Huffman-coding / file-writing half alone. coefs = quantised blocks of a w x h YCbCr 4:2:0 frame, per
  * component plane (Y, Cb, Cr; each padded to whole 16x16 MCUs) in raster order, natural order inside a block; tables =
  * jpeg_set_quality(quality). uf_jpeg_quality_tables returns those tables (natural order). */

@@ -114,6 +114,8 @@ SIGNATURES = {
     "uf_jpeg_quality_tables": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p]),
     "uf_annotate_reencode_batch_jpeg": (C.c_int, [C.c_void_p, _p(C.c_void_p), _p(C.c_size_t), C.c_uint32, C.c_void_p, _p(C.c_uint32),
                                                   C.c_float, C.c_float, C.c_uint32, C.c_void_p, C.c_size_t, _p(C.c_size_t)]),
+    "uf_worker_batch_jpeg": (C.c_int, [C.c_void_p, _p(C.c_void_p), _p(C.c_size_t), C.c_uint32, C.c_float, C.c_float, C.c_uint32, C.c_void_p,
+                                       C.c_uint32, _p(C.c_uint32), C.c_void_p, C.c_size_t, _p(C.c_size_t)]),
     "uf_text_atlas_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "uf_confidence_text": (C.c_int, [C.c_float, C.c_char_p, C.c_size_t]),
     "uf_draw_boxes_rgb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]),

@@ -2029,9 +2029,12 @@ int uf_annotate_reencode_jpeg(uf_model* m, const uint8_t* jpeg, size_t len, cons
 // One chunk of the batch form: frames [0, cnt) of jpeg/len, their detections at dets + det_first[k]; files to out + k * stride.
 // Everything runs on slot 0 of the caller's lane, stage after stage, with three waits for the device (decode status, the
 // sizes of the entropy-coded segments, the segments themselves).
-static void reencode_chunk(uf_model& m, Slot& s, const uint8_t* const* jpeg, const size_t* len, uint32_t cnt, const uf_det* dets,
+// det_out != NULL: the detections are not given but FOUND here, on the decoded frames (the hot path, device-resident input),
+// returned in det_out / n_out and drawn.
+static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const* jpeg, const size_t* len, uint32_t cnt, const uf_det* dets,
                            const uint32_t* det_first, const uint32_t* det_counts, float scale_w, float scale_h, int quality, uint8_t* out,
-                           size_t stride, size_t* out_len, uint32_t first_index) {
+                           size_t stride, size_t* out_len, uint32_t first_index, uf_det* det_out = nullptr, uint32_t det_cap = 0,
+                           uint32_t* n_out = nullptr) {
     auto a256 = [](size_t v) { return (v + 255) / 256 * 256; };
     // 1. headers, byte unstuffing (host threads)
     std::vector<JpegBitstream> bs(cnt);
@@ -2107,6 +2110,29 @@ static void reencode_chunk(uf_model& m, Slot& s, const uint8_t* const* jpeg, con
         decode_jpeg_run(m, s, &one, 1, s.d_in + rgb_off[k], ju1, pu1);
         CK(cudaStreamSynchronize(s.stream));
         m.jpeg_redone++;
+    }
+    // 3b. the hot path on the decoded frames, run of same-size frames by run (they only read the pixels)
+    std::vector<uint32_t> found_first, found_counts;
+    if (det_out) {
+        for (uint32_t i = 0; i < cnt;) {
+            uint32_t j = i + 1;
+            while (j < cnt && fr[j].w == fr[i].w && fr[j].h == fr[i].h && rgb_off[j] == rgb_off[j - 1] + (size_t)fr[i].w * fr[i].h * 3) ++j;
+            const uint8_t* d_rgb = s.d_in + rgb_off[i];
+            const uint32_t w = fr[i].w, h = fr[i].h;
+            const size_t fb = (size_t)w * h * 3;
+            run_pipeline(m, ln, j - i, m.chunk, false, det_out + (size_t)i * det_cap, det_cap, n_out + i,
+                         [&](Slot& sl, uint32_t first, uint32_t c) { run_chunk_device(m, ln, sl, d_rgb + (size_t)first * fb, w, h, first, c); });
+            i = j;
+        }
+        found_first.resize(cnt);
+        found_counts.resize(cnt);
+        for (uint32_t k = 0; k < cnt; ++k) {
+            found_first[k] = k * det_cap;
+            found_counts[k] = std::min(n_out[k], det_cap);  // (the overlay shows what the caller gets)
+        }
+        dets = det_out;
+        det_first = found_first.data();
+        det_counts = found_counts.data();
     }
     // 4. overlay
     {
@@ -2198,11 +2224,36 @@ int uf_annotate_reencode_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, con
         for (uint32_t f0 = 0; f0 < n; f0 += step) {
             const uint32_t cnt = std::min(step, n - f0);
             try {
-                reencode_chunk(*m, s, jpeg + f0, len + f0, cnt, dets, first.data() + f0, det_counts + f0, scale_w, scale_h, (int)quality,
+                reencode_chunk(*m, *ll.lane, s, jpeg + f0, len + f0, cnt, dets, first.data() + f0, det_counts + f0, scale_w, scale_h, (int)quality,
                                out + (size_t)f0 * out_stride, out_stride, out_len + f0, f0);
             } catch (const ArgError& e) {
                 if (e.code != UF_ERR_CAPACITY) throw;
                 too_small = true;  // the other chunks still report their sizes
+            }
+        }
+        ll.lane->last_n = 0;
+        if (too_small) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
+    });
+}
+
+int uf_worker_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, float scale_w, float scale_h, uint32_t quality,
+                         uf_det* dets, uint32_t cap, uint32_t* n_dets, uint8_t* out, size_t out_stride, size_t* out_len) {
+    return guarded([&] {
+        REQUIRE(m && out_len && n_dets && cap > 0 && dets && (n == 0 || (jpeg && len && out)) && out_stride >= 1024, "bad argument");
+        for (uint32_t i = 0; i < n; ++i) REQUIRE(jpeg[i] && len[i] > 0, "null frame");
+        LaneLock ll(*m, false);
+        Slot& s = ll.lane->slots[0];
+        CK(cudaSetDevice(m->cfg.device));
+        const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(32, m->chunk));
+        bool too_small = false;
+        for (uint32_t f0 = 0; f0 < n; f0 += step) {
+            const uint32_t cnt = std::min(step, n - f0);
+            try {
+                reencode_chunk(*m, *ll.lane, s, jpeg + f0, len + f0, cnt, nullptr, nullptr, nullptr, scale_w, scale_h, (int)quality,
+                               out + (size_t)f0 * out_stride, out_stride, out_len + f0, f0, dets + (size_t)f0 * cap, cap, n_dets + f0);
+            } catch (const ArgError& e) {
+                if (e.code != UF_ERR_CAPACITY) throw;
+                too_small = true;
             }
         }
         ll.lane->last_n = 0;

@@ -204,6 +204,31 @@ class UltrafaceModel(InferModel):
                                                             quality, out.ctypes.data_as(C.c_void_p), out_stride, out_len))
         return [out[i * out_stride:i * out_stride + out_len[i]].tobytes() for i in range(n)]
 
+    def worker_batch_jpeg(self, jpegs: Sequence[bytes], scale_w: float, scale_h: float, quality: int = 95, cap: int = 64, out_stride: int = 0,
+                          keep_files: bool = True):
+        """The reference's worker loop body for a batch (uf_worker_batch_jpeg): JPEG in -> (detections per frame, counts,
+        annotated JPEG files)."""
+        n = len(jpegs)
+        key = ("worker", n, tuple(map(len, jpegs[:4])))
+        cached = getattr(self, "_worker_args", None)
+        if cached is None or cached[0] != key or cached[1] is not jpegs:
+            bufs = [C.create_string_buffer(bytes(j), len(j)) for j in jpegs]
+            ptrs = (C.c_void_p * max(n, 1))(*[C.cast(b, C.c_void_p) for b in bufs])
+            lens = (C.c_size_t * max(n, 1))(*[len(j) for j in jpegs])
+            self._worker_args = cached = (key, jpegs, bufs, ptrs, lens)
+        _, _, bufs, ptrs, lens = cached
+        if not out_stride:
+            out_stride = max(len(j) for j in jpegs) * 8 + (1 << 16) if n else 1024
+        out = np.empty(max(n, 1) * out_stride, np.uint8)
+        out_len = (C.c_size_t * max(n, 1))()
+        dets = np.zeros((max(n, 1), cap, 5), np.float32)
+        cnt = (C.c_uint32 * max(n, 1))()
+        _check(_capi.load().uf_worker_batch_jpeg(self._h, ptrs, lens, n, scale_w, scale_h, quality, dets.ctypes.data_as(C.c_void_p), cap, cnt,
+                                                 out.ctypes.data_as(C.c_void_p), out_stride, out_len))
+        counts = [int(cnt[i]) for i in range(n)]
+        files = [out[i * out_stride:i * out_stride + out_len[i]].tobytes() for i in range(n)] if keep_files else [int(out_len[i]) for i in range(n)]
+        return [dets[i, :min(counts[i], cap)] for i in range(n)], counts, files
+
     def text_atlas_set(self, charset: str, max_len: int, glyphs, coverage) -> None:
         """Glyph atlas for the confidence text (uf_text_atlas_set): glyphs[pos][k] = (x0, y0, w, h, offset) of charset[k] as the
         pos-th character, coverage = flat f32 array. charset "" removes the atlas (rectangles only)."""

@@ -214,6 +214,8 @@ extern "C" {
     pub fn uf_annotate_reencode_batch_jpeg(m: *mut uf_model, jpeg: *const *const u8, len: *const usize, n: u32, dets: *const uf_det,
                                            det_counts: *const u32, scale_w: f32, scale_h: f32, quality: u32, out: *mut u8,
                                            out_stride: usize, out_len: *mut usize) -> c_int;
+    pub fn uf_worker_batch_jpeg(m: *mut uf_model, jpeg: *const *const u8, len: *const usize, n: u32, scale_w: f32, scale_h: f32, quality: u32,
+                                dets: *mut uf_det, cap: u32, n_dets: *mut u32, out: *mut u8, out_stride: usize, out_len: *mut usize) -> c_int;
     pub fn uf_text_atlas_set(m: *mut uf_model, charset: *const c_char, n_chars: u32, max_len: u32, glyphs: *const uf_glyph,
                              coverage: *const f32, n_coverage: usize) -> c_int;
     pub fn uf_confidence_text(confidence: f32, out: *mut c_char, cap: usize) -> c_int;

@@ -222,3 +222,30 @@ def test_gpu_batch_reencode_writes_the_single_frame_files(make_onnx, test_pics):
         assert e.value.code == 7  # UF_ERR_CAPACITY
     finally:
         m.close()
+
+
+@pytest.mark.gpu
+def test_gpu_worker_batch_is_decode_detect_draw_encode(make_onnx, test_pics):
+    """uf_worker_batch_jpeg = the body of the reference's worker loop (inferer.rs:35-46) for a batch: its detections are
+    run_batch_jpeg's, its files are annotate_encode_jpeg's for those detections."""
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=64)
+    try:
+        rng = np.random.default_rng(12)
+        pics = list(test_pics.values())
+
+        def enc(a, q, ss):
+            b = io.BytesIO()
+            Image.fromarray(a).save(b, "JPEG", quality=q, subsampling=ss)
+            return b.getvalue()
+        jpegs = [enc(rng.integers(0, 256, (480, 640, 3), dtype=np.uint8), 90, 1) for _ in range(20)] + [enc(p, 85, 2) for p in pics]
+        jpegs += [enc(pics[0][:240, :320], 90, 0), enc(pics[1][:301, :333], 80, 1)] + [enc(rng.integers(0, 256, (480, 640, 3), dtype=np.uint8), 90, 1) for _ in range(14)]
+        m.text_atlas_set(*_synthetic_atlas(9))
+        want_d, want_c = m.run_batch_jpeg(jpegs, cap=64)
+        dets, counts, files = m.worker_batch_jpeg(jpegs, 1280.0, 720.0, quality=95, cap=64)
+        assert counts == want_c and sum(counts) > 0
+        for i in range(len(jpegs)):
+            np.testing.assert_array_equal(dets[i], want_d[i])
+            assert files[i] == m.annotate_encode_jpeg(jpegs[i], want_d[i], 1280.0, 720.0, quality=95), i
+    finally:
+        m.close()
