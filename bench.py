@@ -188,7 +188,7 @@ def ingest_leg(nn, path, w, h, local, rank, world, B, steps, barrier, max_over_r
     return total, dt, st
 
 
-def jpeg_leg(nn, model, timed, steps, warmup, B, cap, threads):
+def jpeg_leg(nn, model, timed, steps, warmup, B, cap, threads, worker=False):
     """e2e with frames arriving as baseline JPEG (uf_infer_batch_jpeg). Smooth synthetic frames, quality 85, 4:2:2 (what an
     MJPG webcam sends). Returns (seconds one call at a time, seconds with `threads` calls in flight, bytes/frame, ..., out)."""
     import cv2
@@ -201,6 +201,8 @@ def jpeg_leg(nn, model, timed, steps, warmup, B, cap, threads):
     jpegs = [files[i % len(files)] for i in range(B)]
     coef_bytes = [4 * (nn.jpeg_coefficients(j)[0]["nonzero"] + nn.jpeg_coefficients(j)[0]["nblocks"] + 1) + 700 for j in files]
     step = lambda: model.run_batch_jpeg(jpegs, cap=cap)  # noqa: E731
+    if worker:  # decode -> detect -> draw -> encode: annotated JPEG files out as well (uf_worker_batch_jpeg)
+        step = lambda: model.worker_batch_jpeg(jpegs, 1280.0, 720.0, quality=95, cap=cap, keep_files=False)  # noqa: E731
     dt1, _, out = timed(step, steps, warmup)
     dtn = dt1
     if threads > 1:
@@ -503,6 +505,16 @@ def main():
         dt_h1, dt_hn, _, _, out_h = jpeg_leg(nn, host_model, timed, args.steps, max(args.warmup, 3), B, cap, nfl)
         host_model.close()
         assert out_h[1] == out_j[1], "device and host Huffman decoding disagree"
+        dt_w1, dt_wn, _, _, out_w = jpeg_leg(nn, model, timed, args.steps, max(args.warmup, 3), B, cap, nfl, worker=True)
+        assert out_w[1] == out_j[1], "the worker call and the plain JPEG call disagree"
+        dt_w = min(dt_w1, dt_wn)
+        extra["worker"] = {"value": B * world * args.steps / dt_w, "unit": "frames/s", "ms_per_step": dt_w / args.steps * 1e3,
+                           "api": "uf_worker_batch_jpeg (C ABI): the body of the reference's worker loop (inferer.rs:35-46) for a batch — MJPG "
+                                  "frames in; Huffman decoding, IDCT, colour, detection, rectangles, colour, forward DCT, quantisation, "
+                                  "Huffman coding and byte stuffing on the GPU; detections and annotated quality-95 4:2:0 JPEG files out "
+                                  "(the reference: ~15 ms per frame for the two codecs alone, README.md:62-64)",
+                           "calls_in_flight": B * world * args.steps / dt_wn, "one_call_at_a_time": B * world * args.steps / dt_w1,
+                           "jpeg_bytes_out_per_frame": float(np.mean(out_w[2]))}
         dt_j, dt_h = min(dt_j1, dt_jn), min(dt_h1, dt_hn)
         extra["jpeg"] = {"value": B * world * args.steps / dt_j, "unit": "frames/s", "ms_per_step": dt_j / args.steps * 1e3,
                          "api": "uf_infer_batch_jpeg (C ABI): baseline JPEG files in host memory -> detections; the host parses the "

@@ -1881,39 +1881,36 @@ static void build_overlay_lists(uf_model& m, uint32_t w, uint32_t h, const uf_de
             L.rects.push_back(make_int4(std::max(r.x, -1), std::max(r.y, -1), std::min(r.z, (int)w), std::min(r.w, (int)h)));
 }
 
-// uploads the lists of `cnt` frames in one piece and draws every frame's overlay on its RGB image (d_rgb[k], w[k] x h[k]).
-// Synchronises the stream before returning (the lists are pageable host memory).
-static void draw_overlays(uf_model& m, Slot& s, const std::vector<OverlayLists>& L, uint8_t* const* d_rgb, const uint32_t* w, const uint32_t* h) {
+// uploads the lists of the frames in one piece and draws every frame's overlay (one launch, CTA = frame) on its RGB image at
+// rgb_base + rgb_off[k], w[k] x h[k]. Synchronises the stream before returning (the lists are pageable host memory).
+static void draw_overlays(uf_model& m, Slot& s, const std::vector<OverlayLists>& L, uint8_t* rgb_base, const size_t* rgb_off, const uint32_t* w,
+                          const uint32_t* h) {
     size_t n_r = 0, n_s = 0, n_g = 0;
     for (const auto& l : L) { n_r += l.rects.size(); n_s += l.gstart.size(); n_g += l.glyphs.size(); }
     if (n_r == 0) return;
-    const size_t b_r = n_r * sizeof(int4), b_s = (n_s * 4 + 15) / 16 * 16, b_g = n_g * sizeof(OverlayGlyph);
-    std::vector<uint8_t> host(b_r + b_s + b_g + 16);
-    int4* hr = reinterpret_cast<int4*>(host.data());
-    uint32_t* hs = reinterpret_cast<uint32_t*>(host.data() + b_r);
-    OverlayGlyph* hg = reinterpret_cast<OverlayGlyph*>(host.data() + b_r + b_s);
+    const size_t b_f = (L.size() * sizeof(OverlayFrame) + 15) / 16 * 16, b_r = n_r * sizeof(int4), b_s = (n_s * 4 + 15) / 16 * 16,
+                 b_g = n_g * sizeof(OverlayGlyph);
+    std::vector<uint8_t> host(b_f + b_r + b_s + b_g + 16);
+    OverlayFrame* hf = reinterpret_cast<OverlayFrame*>(host.data());
+    int4* hr = reinterpret_cast<int4*>(host.data() + b_f);
+    uint32_t* hs = reinterpret_cast<uint32_t*>(host.data() + b_f + b_r);
+    OverlayGlyph* hg = reinterpret_cast<OverlayGlyph*>(host.data() + b_f + b_r + b_s);
     uint8_t* d = (uint8_t*)hook_scratch(m, host.size());
     size_t ir = 0, is = 0, ig = 0;
-    struct Job { size_t r, s, g; };
-    std::vector<Job> jobs;
-    for (const auto& l : L) {
-        jobs.push_back(Job{ir, is, ig});
+    for (size_t k = 0; k < L.size(); ++k) {
+        const auto& l = L[k];
+        hf[k] = OverlayFrame{(unsigned long long)rgb_off[k], (int32_t)w[k], (int32_t)h[k], (uint32_t)ir, (uint32_t)l.rects.size(), (uint32_t)is,
+                             (uint32_t)ig, l.text ? 1u : 0u, 0u};
         if (!l.rects.empty()) memcpy(hr + ir, l.rects.data(), l.rects.size() * sizeof(int4));
-        for (size_t k = 0; k < l.gstart.size(); ++k) hs[is + k] = l.gstart[k];  // (relative to the frame's first glyph)
+        for (size_t q = 0; q < l.gstart.size(); ++q) hs[is + q] = l.gstart[q];  // (relative to the frame's first glyph)
         if (!l.glyphs.empty()) memcpy(hg + ig, l.glyphs.data(), l.glyphs.size() * sizeof(OverlayGlyph));
         ir += l.rects.size(); is += l.gstart.size(); ig += l.glyphs.size();
     }
     CK(cudaMemcpyAsync(d, host.data(), host.size(), cudaMemcpyHostToDevice, s.stream));
-    for (size_t k = 0; k < L.size(); ++k) {
-        if (L[k].rects.empty()) continue;
-        m.launches++;
-        const int4* dr = reinterpret_cast<const int4*>(d) + jobs[k].r;
-        if (L[k].text)
-            launch_draw_overlay(d_rgb[k], (int)w[k], (int)h[k], dr, reinterpret_cast<const uint32_t*>(d + b_r) + jobs[k].s,
-                                reinterpret_cast<const OverlayGlyph*>(d + b_r + b_s) + jobs[k].g, m.d_atlas, (int)L[k].rects.size(), s.stream);
-        else
-            launch_draw_rects(d_rgb[k], (int)w[k], (int)h[k], dr, (int)L[k].rects.size(), s.stream);
-    }
+    m.launches++;
+    launch_draw_overlay_batch(rgb_base, reinterpret_cast<const OverlayFrame*>(d), (int)L.size(), reinterpret_cast<const int4*>(d + b_f),
+                              reinterpret_cast<const uint32_t*>(d + b_f + b_r), reinterpret_cast<const OverlayGlyph*>(d + b_f + b_r + b_s),
+                              m.d_atlas, s.stream);
     CK(cudaStreamSynchronize(s.stream));
 }
 
@@ -1924,8 +1921,8 @@ static void annotate_on_device(uf_model& m, Slot& s, uint32_t w, uint32_t h, con
         std::lock_guard<std::mutex> atlas_lk(m.atlas_mu);  // (held until the overlay has been drawn: the atlas is in use)
         std::vector<OverlayLists> L(1);
         build_overlay_lists(m, w, h, dets, n_dets, scale_w, scale_h, L[0]);
-        uint8_t* rgb = s.d_in;
-        draw_overlays(m, s, L, &rgb, &w, &h);
+        const size_t zero = 0;
+        draw_overlays(m, s, L, s.d_in, &zero, &w, &h);
     }
     if (!file) return;
     const JpegPlan plan = jpeg_encode_plan(w, h, quality);
@@ -2084,7 +2081,8 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
                  e_off = a256(e_len + nblk_all * 4), e_fb = a256(e_off + nblk_all * 4), e_ol = a256(e_fb + cnt * 4), e_pack = a256(e_ol + cnt * 4),
                  e_out = a256(e_pack + pack_words * 4), e_end = e_out + out_bytes;
     grow_input(s, rgb_bytes + 256);
-    grow_jpeg(s, std::max(jpeg_need, a256(cnt * sizeof(JpegEncFrame)) + sizeof(JpegEncTables) + 512), std::max(planes_dec, planes_enc));
+    grow_jpeg(s, std::max(jpeg_need, a256(cnt * sizeof(JpegEncFrame)) + sizeof(JpegEncTables) + cnt * sizeof(JpegEncJob) + 1024),
+              std::max(planes_dec, planes_enc));
     grow_huff(s, std::max(huff_dec, e_end));
     // 3. decode: runs of same-size frames; then the frames the device decoder handed back, one by one
     size_t ju = 0, pu = 0, hu = 0;
@@ -2138,22 +2136,26 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
     {
         std::lock_guard<std::mutex> atlas_lk(m.atlas_mu);
         std::vector<OverlayLists> L(cnt);
-        std::vector<uint8_t*> rgb(cnt);
         std::vector<uint32_t> ws(cnt), hs(cnt);
         for (uint32_t k = 0; k < cnt; ++k) {
-            ws[k] = fr[k].w; hs[k] = fr[k].h; rgb[k] = s.d_in + rgb_off[k];
+            ws[k] = fr[k].w; hs[k] = fr[k].h;
             build_overlay_lists(m, ws[k], hs[k], dets + det_first[k], det_counts[k], scale_w, scale_h, L[k]);
         }
-        draw_overlays(m, s, L, rgb.data(), ws.data(), hs.data());
+        draw_overlays(m, s, L, s.d_in, rgb_off.data(), ws.data(), hs.data());
     }
     // 5. colour conversion, downsampling, forward DCT, quantisation — then Huffman coding and byte stuffing, all frames at once
     int16_t* d_coefs = reinterpret_cast<int16_t*>(s.d_huff);
     JpegEncFrame* hf = reinterpret_cast<JpegEncFrame*>(s.h_jpeg);
+    const size_t o_jobs = a256(a256(cnt * sizeof(JpegEncFrame)) + sizeof(JpegEncTables));
+    JpegEncJob* hj = reinterpret_cast<JpegEncJob*>(s.h_jpeg + o_jobs);
     size_t lb = 0, pw = 0, ob = 0;
+    uint32_t max_cw = 0, max_ch = 0, max_pblocks = 0;
     for (uint32_t k = 0; k < cnt; ++k) {
         const JpegPlan& p = eplan[k];
-        m.launches += 2;
-        launch_jpeg_encode(s.d_in + rgb_off[k], p, s.d_planes + pl_off[k], d_coefs + co_off[k] / sizeof(int16_t), s.stream);
+        hj[k] = JpegEncJob{p, (unsigned long long)rgb_off[k], (unsigned long long)pl_off[k], (unsigned long long)(co_off[k] / sizeof(int16_t))};
+        max_cw = std::max(max_cw, p.plane_w[1]);
+        max_ch = std::max(max_ch, p.plane_h[1]);
+        max_pblocks = std::max(max_pblocks, (p.plane_w[0] * p.plane_h[0] + 2 * p.plane_w[1] * p.plane_h[1]) / 64);
         JpegEncFrame f{};
         f.coef_base = (uint32_t)(co_off[k] / 128);
         f.mcus_x = p.mcus_x; f.mcus_y = p.mcus_y;
@@ -2168,6 +2170,10 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
     }
     JpegEncTables* ht = reinterpret_cast<JpegEncTables*>(s.h_jpeg + a256(cnt * sizeof(JpegEncFrame)));
     jpeg_std_enc_tables(*ht);
+    CK(cudaMemcpyAsync(s.d_jpeg + o_jobs, hj, cnt * sizeof(JpegEncJob), cudaMemcpyHostToDevice, s.stream));
+    m.launches += 2;
+    launch_jpeg_encode_batch(s.d_in, reinterpret_cast<const JpegEncJob*>(s.d_jpeg + o_jobs), (int)cnt, max_cw, max_ch, max_pblocks, s.d_planes,
+                             d_coefs, s.stream);
     CK(cudaMemcpyAsync(s.d_huff + e_frames, hf, cnt * sizeof(JpegEncFrame), cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_huff + e_tab, ht, sizeof(JpegEncTables), cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemsetAsync(s.d_huff + e_pack, 0, pack_words * 4, s.stream));
@@ -2180,31 +2186,49 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
     uint32_t* h_len = reinterpret_cast<uint32_t*>(s.h_jstatus);
     CK(cudaMemcpyAsync(h_len, s.d_huff + e_ol, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
-    // 6. files: headers + segment + EOI, straight into the caller's buffer
-    std::vector<uint8_t> head, file;
-    bool too_small = false;
-    for (uint32_t k = 0; k < cnt; ++k) {
-        uint8_t* dst = out + (size_t)k * stride;
-        if (h_len[k] == 0xffffffffu) {  // did not fit the device buffers (far denser than any camera frame): host encoder
-            std::vector<int16_t> co((size_t)eplan[k].plane_bytes);
-            CK(cudaMemcpy(co.data(), d_coefs + co_off[k] / sizeof(int16_t), co.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
-            jpeg_write_file(eplan[k], co.data(), file);
-            out_len[k] = file.size();
-            if (file.size() > stride) too_small = true;
-            else memcpy(dst, file.data(), file.size());
-            continue;
-        }
-        jpeg_write_headers(eplan[k], head);
-        out_len[k] = head.size() + h_len[k] + 2;
-        if (out_len[k] > stride) { too_small = true; continue; }
-        memcpy(dst, head.data(), head.size());
-        CK(cudaMemcpyAsync(dst + head.size(), s.d_huff + e_out + hf[k].out_off, h_len[k], cudaMemcpyDeviceToHost, s.stream));
-        dst[head.size() + h_len[k]] = 0xff;
-        dst[head.size() + h_len[k] + 1] = 0xd9;
-    }
+    // 6. files: the segments come back through the pinned staging buffer in one burst of copies, host threads then write
+    //    headers + segment + EOI into the caller's buffer
+    std::vector<size_t> seg_off(cnt, 0);
+    size_t seg_bytes = 0;
+    for (uint32_t k = 0; k < cnt; ++k)
+        if (h_len[k] != 0xffffffffu) { seg_off[k] = seg_bytes; seg_bytes += ((size_t)h_len[k] + 15) / 16 * 16; }
+    std::vector<uint32_t> seg_len(h_len, h_len + cnt);  // (h_len lives in the slot's status array)
+    std::vector<JpegEncFrame> encf(hf, hf + cnt);       // (and hf in the staging buffer that may be regrown now)
+    grow_jpeg(s, seg_bytes + 16, 0);
+    for (uint32_t k = 0; k < cnt; ++k)
+        if (seg_len[k] != 0xffffffffu && seg_len[k] > 0)
+            CK(cudaMemcpyAsync(s.h_jpeg + seg_off[k], s.d_huff + e_out + encf[k].out_off, seg_len[k], cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaGetLastError());
-    if (too_small) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
+    std::atomic<bool> too_small{false};
+    std::vector<std::string> fails(cnt);
+    m.pool().parallel_for(cnt, [&](uint32_t k) {
+        try {
+            uint8_t* dst = out + (size_t)k * stride;
+            std::vector<uint8_t> head;
+            if (seg_len[k] == 0xffffffffu) return;  // (below)
+            jpeg_write_headers(eplan[k], head);
+            out_len[k] = head.size() + seg_len[k] + 2;
+            if (out_len[k] > stride) { too_small = true; return; }
+            memcpy(dst, head.data(), head.size());
+            memcpy(dst + head.size(), s.h_jpeg + seg_off[k], seg_len[k]);
+            dst[head.size() + seg_len[k]] = 0xff;
+            dst[head.size() + seg_len[k] + 1] = 0xd9;
+        } catch (const std::exception& e) { fails[k] = e.what(); }
+    });
+    for (uint32_t k = 0; k < cnt; ++k) {
+        if (!fails[k].empty()) throw CudaError("frame " + std::to_string(first_index + k) + ": " + fails[k]);
+        if (seg_len[k] != 0xffffffffu) continue;
+        // did not fit the device buffers (far denser than any camera frame): the host encoder
+        std::vector<int16_t> co((size_t)eplan[k].plane_bytes);
+        std::vector<uint8_t> file;
+        CK(cudaMemcpy(co.data(), d_coefs + co_off[k] / sizeof(int16_t), co.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
+        jpeg_write_file(eplan[k], co.data(), file);
+        out_len[k] = file.size();
+        if (file.size() > stride) too_small = true;
+        else memcpy(out + (size_t)k * stride, file.data(), file.size());
+    }
+    if (too_small.load()) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
 }
 
 int uf_annotate_reencode_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, const uf_det* dets,
@@ -2219,7 +2243,7 @@ int uf_annotate_reencode_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, con
         LaneLock ll(*m, false);
         Slot& s = ll.lane->slots[0];
         CK(cudaSetDevice(m->cfg.device));
-        const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(32, m->chunk));
+        const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(64, m->chunk));
         bool too_small = false;
         for (uint32_t f0 = 0; f0 < n; f0 += step) {
             const uint32_t cnt = std::min(step, n - f0);
@@ -2244,7 +2268,7 @@ int uf_worker_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* 
         LaneLock ll(*m, false);
         Slot& s = ll.lane->slots[0];
         CK(cudaSetDevice(m->cfg.device));
-        const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(32, m->chunk));
+        const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(64, m->chunk));
         bool too_small = false;
         for (uint32_t f0 = 0; f0 < n; f0 += step) {
             const uint32_t cnt = std::min(step, n - f0);

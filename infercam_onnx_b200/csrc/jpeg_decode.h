@@ -113,6 +113,11 @@ JpegPlan jpeg_encode_plan(uint32_t w, uint32_t h, int quality);              // 
 // coefs: quantised blocks per component plane in raster order (see jpeg_encode.cc); writes a complete JFIF file
 void jpeg_write_file(const JpegPlan& p, const int16_t* coefs, std::vector<uint8_t>& out);
 void jpeg_write_headers(const JpegPlan& p, std::vector<uint8_t>& out);  // SOI .. SOS (the entropy-coded segment and EOI follow)
+struct JpegEncJob {        // one frame of a batch for the encoder's sample-domain kernels (kernels_jpeg_enc.cu)
+    JpegPlan plan;
+    unsigned long long rgb_off, planes_off;  // byte offsets of the frame's pixels / component planes
+    unsigned long long coef_off;             // offset of its coefficients, in int16 elements
+};
 struct JpegEncTables {     // Annex K tables in encoder form: (length << 16) | code; [0] luma, [1] chroma
     uint32_t dc[2][16];
     uint32_t ac[2][256];

@@ -185,9 +185,22 @@ struct OverlayGlyph {  // one placed glyph: top-left pixel in the image, box, of
     int32_t x, y;
     uint32_t w, h, offset;
 };
+struct OverlayFrame {  // batch form: one frame's share of the concatenated lists
+    unsigned long long rgb_off;  // byte offset of the frame's pixels
+    int32_t w, h;
+    uint32_t rect_first, n;      // rectangles (= detections drawn)
+    uint32_t gstart_first, glyph_first;
+    uint32_t text;               // 0: rectangles only
+    uint32_t pad_;
+};
+void launch_draw_overlay_batch(uint8_t* rgb_base, const OverlayFrame* d_frames, int frames, const int4* d_rects, const uint32_t* d_glyph_start,
+                               const OverlayGlyph* d_glyphs, const float* d_coverage, cudaStream_t s);
 void launch_draw_overlay(uint8_t* rgb, int w, int h, const int4* d_rects, const uint32_t* d_glyph_start, const OverlayGlyph* d_glyphs,
                          const float* d_coverage, int n, cudaStream_t s);
 void launch_jpeg_encode(const uint8_t* d_rgb, const JpegPlan& plan, uint8_t* d_planes, int16_t* d_coefs, cudaStream_t s);
+struct JpegEncJob;
+void launch_jpeg_encode_batch(const uint8_t* d_rgb_base, const JpegEncJob* d_jobs, int frames, uint32_t max_cw, uint32_t max_ch, uint32_t max_blocks,
+                              uint8_t* d_planes_base, int16_t* d_coefs_base, cudaStream_t s);
 
 // ---- N3: Huffman coding of quantised 4:2:0 frames on the GPU (kernels_jpeg_henc.cu)
 struct JpegEncTables;      // jpeg_decode.h

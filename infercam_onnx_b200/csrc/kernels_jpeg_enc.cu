@@ -41,9 +41,9 @@ __device__ __forceinline__ uint8_t blend_u8(uint8_t pix, float col, float lw, fl
 // Rectangles AND text, detection by detection in the reference's order (a later detection's rectangle overwrites an earlier
 // one's text where they overlap, a glyph blends over whatever is there): one CTA walks the list, its threads share the
 // pixels of the item in hand. A frame has a handful of detections; this is nowhere near the encoder's cost.
-__global__ void __launch_bounds__(256)
-draw_overlay_kernel(uint8_t* __restrict__ rgb, int w, int h, const int4* __restrict__ rects, const uint32_t* __restrict__ glyph_start,
-                    const OverlayGlyph* __restrict__ glyphs, const float* __restrict__ coverage, int n) {
+__device__ __forceinline__ void draw_overlay_frame(uint8_t* __restrict__ rgb, int w, int h, const int4* __restrict__ rects,
+                                                   const uint32_t* __restrict__ glyph_start, const OverlayGlyph* __restrict__ glyphs,
+                                                   const float* __restrict__ coverage, int n) {
     for (int d = 0; d < n; ++d) {
         const int4 r = rects[d];
         const int rw = r.z - r.x + 1, rh = r.w - r.y + 1;
@@ -56,6 +56,7 @@ draw_overlay_kernel(uint8_t* __restrict__ rgb, int w, int h, const int4* __restr
         for (int i = threadIdx.x; i < rw; i += blockDim.x) { put(r.x + i, r.y); put(r.x + i, r.w); }
         for (int i = threadIdx.x; i < rh; i += blockDim.x) { put(r.x, r.y + i); put(r.z, r.y + i); }
         __syncthreads();
+        if (!glyph_start) continue;  // rectangles only
         for (uint32_t g = glyph_start[d]; g < glyph_start[d + 1]; ++g) {
             const OverlayGlyph G = glyphs[g];
             const uint32_t npx = G.w * G.h;
@@ -74,9 +75,30 @@ draw_overlay_kernel(uint8_t* __restrict__ rgb, int w, int h, const int4* __restr
     }
 }
 
+__global__ void __launch_bounds__(256)
+draw_overlay_kernel(uint8_t* __restrict__ rgb, int w, int h, const int4* __restrict__ rects, const uint32_t* __restrict__ glyph_start,
+                    const OverlayGlyph* __restrict__ glyphs, const float* __restrict__ coverage, int n) {
+    draw_overlay_frame(rgb, w, h, rects, glyph_start, glyphs, coverage, n);
+}
+
+// batch form: CTA = frame
+__global__ void __launch_bounds__(256)
+draw_overlay_batch_kernel(uint8_t* __restrict__ rgb_base, const OverlayFrame* __restrict__ frames, const int4* __restrict__ rects,
+                          const uint32_t* __restrict__ glyph_start, const OverlayGlyph* __restrict__ glyphs, const float* __restrict__ coverage) {
+    const OverlayFrame F = frames[blockIdx.x];
+    if (F.n == 0) return;
+    draw_overlay_frame(rgb_base + F.rgb_off, F.w, F.h, rects + F.rect_first, F.text ? glyph_start + F.gstart_first : nullptr,
+                       glyphs + F.glyph_first, coverage, (int)F.n);
+}
+
 void launch_draw_overlay(uint8_t* rgb, int w, int h, const int4* d_rects, const uint32_t* d_glyph_start, const OverlayGlyph* d_glyphs,
                          const float* d_coverage, int n, cudaStream_t s) {
     if (n > 0) draw_overlay_kernel<<<1, 256, 0, s>>>(rgb, w, h, d_rects, d_glyph_start, d_glyphs, d_coverage, n);
+}
+
+void launch_draw_overlay_batch(uint8_t* rgb_base, const OverlayFrame* d_frames, int frames, const int4* d_rects, const uint32_t* d_glyph_start,
+                               const OverlayGlyph* d_glyphs, const float* d_coverage, cudaStream_t s) {
+    if (frames > 0) draw_overlay_batch_kernel<<<frames, 256, 0, s>>>(rgb_base, d_frames, d_rects, d_glyph_start, d_glyphs, d_coverage);
 }
 
 __device__ __forceinline__ void jrgb2ycc(const uint8_t* __restrict__ p, int& y, int& cb, int& cr) {
@@ -87,8 +109,7 @@ __device__ __forceinline__ void jrgb2ycc(const uint8_t* __restrict__ p, int& y, 
 }
 
 // thread = one chroma sample = a 2x2 quad of luma samples, over the PADDED planes
-__global__ void __launch_bounds__(256)
-jpeg_enc_color_kernel(const uint8_t* __restrict__ rgb, JpegPlan plan, uint8_t* __restrict__ planes) {
+__device__ __forceinline__ void jpeg_enc_color_body(const uint8_t* __restrict__ rgb, const JpegPlan& plan, uint8_t* __restrict__ planes) {
     const int cw = (int)plan.plane_w[1], ch = (int)plan.plane_h[1];
     const int cx = blockIdx.x * 32 + (threadIdx.x & 31), cy = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (cx >= cw || cy >= ch) return;
@@ -161,9 +182,19 @@ __device__ __forceinline__ void jfdct_1d(const int d[8], int o[8]) {
 
 constexpr int EB_PER_CTA = 32, EB_STRIDE = 72;
 
-__global__ void __launch_bounds__(EB_PER_CTA * 8)
-jpeg_fdct_kernel(const uint8_t* __restrict__ planes, JpegPlan plan, int16_t* __restrict__ coefs) {
-    __shared__ int ws[EB_PER_CTA * EB_STRIDE];
+__global__ void __launch_bounds__(256)
+jpeg_enc_color_kernel(const uint8_t* __restrict__ rgb, JpegPlan plan, uint8_t* __restrict__ planes) {
+    jpeg_enc_color_body(rgb, plan, planes);
+}
+
+// batch form: blockIdx.z = frame, the grid covers the largest frame
+__global__ void __launch_bounds__(256)
+jpeg_enc_color_batch_kernel(const uint8_t* __restrict__ rgb_base, const JpegEncJob* __restrict__ jobs, uint8_t* __restrict__ planes_base) {
+    const JpegEncJob& J = jobs[blockIdx.z];
+    jpeg_enc_color_body(rgb_base + J.rgb_off, J.plan, planes_base + J.planes_off);
+}
+
+__device__ __forceinline__ void jpeg_fdct_body(const uint8_t* __restrict__ planes, const JpegPlan& plan, int16_t* __restrict__ coefs, int* ws) {
     const int tid = threadIdx.x, t = tid & 7;
     const uint32_t blk = blockIdx.x * EB_PER_CTA + (tid >> 3);  // block index over the three planes, raster order inside each
     uint32_t nb[3];
@@ -202,6 +233,27 @@ jpeg_fdct_kernel(const uint8_t* __restrict__ planes, JpegPlan plan, int16_t* __r
         v = ((neg ? -v : v) + (q >> 1)) / q;
         dst[k * 8 + t] = (int16_t)(neg ? -v : v);
     }
+}
+
+__global__ void __launch_bounds__(EB_PER_CTA * 8)
+jpeg_fdct_kernel(const uint8_t* __restrict__ planes, JpegPlan plan, int16_t* __restrict__ coefs) {
+    __shared__ int ws[EB_PER_CTA * EB_STRIDE];
+    jpeg_fdct_body(planes, plan, coefs, ws);
+}
+
+__global__ void __launch_bounds__(EB_PER_CTA * 8)
+jpeg_fdct_batch_kernel(const uint8_t* __restrict__ planes_base, const JpegEncJob* __restrict__ jobs, int16_t* __restrict__ coefs_base) {
+    __shared__ int ws[EB_PER_CTA * EB_STRIDE];
+    const JpegEncJob& J = jobs[blockIdx.y];
+    jpeg_fdct_body(planes_base + J.planes_off, J.plan, coefs_base + J.coef_off, ws);
+}
+
+// `frames` jobs in two launches; max_* = the largest frame's extents
+void launch_jpeg_encode_batch(const uint8_t* d_rgb_base, const JpegEncJob* d_jobs, int frames, uint32_t max_cw, uint32_t max_ch, uint32_t max_blocks,
+                              uint8_t* d_planes_base, int16_t* d_coefs_base, cudaStream_t s) {
+    if (frames <= 0) return;
+    jpeg_enc_color_batch_kernel<<<dim3((max_cw + 31) / 32, (max_ch + 7) / 8, frames), 256, 0, s>>>(d_rgb_base, d_jobs, d_planes_base);
+    jpeg_fdct_batch_kernel<<<dim3((max_blocks + EB_PER_CTA - 1) / EB_PER_CTA, frames), EB_PER_CTA * 8, 0, s>>>(d_planes_base, d_jobs, d_coefs_base);
 }
 
 void launch_jpeg_encode(const uint8_t* d_rgb, const JpegPlan& plan, uint8_t* d_planes, int16_t* d_coefs, cudaStream_t s) {
