@@ -1,7 +1,8 @@
 """Small workload touching every round-2 kernel once, for compute-sanitizer (memcheck / racecheck / initcheck):
 fused resize+stem (interior and border tiles, both nets' geometries), the NMS bit-matrix path (frames with > 512 candidates,
 odd candidate counts), JPEG decode with Huffman decoding on the device and on the host (4:4:4 / 4:2:2 / 4:2:0 / grey, odd sizes,
-truncated and bit-flipped files that the device decoder hands back), rectangles + text + JPEG encode, the batcher."""
+truncated and bit-flipped files that the device decoder hands back), rectangles + text + JPEG encode (per frame with the host
+Huffman coder, and the batch forms with Huffman coding on the device), the batcher."""
 import io
 import os
 import sys
@@ -61,6 +62,9 @@ for f in (frames[0], frames[3], frames[3][:9, :17]):
     m.draw_boxes(f, boxes, float(f.shape[1]), float(f.shape[0]))
     m.annotate_encode_jpeg(np.ascontiguousarray(f), boxes, float(f.shape[1]), float(f.shape[0]), 95)
 m.annotate_encode_jpeg(jpegs[1], boxes, 333.0, 301.0, 90)
+wd, wc, wf = m.worker_batch_jpeg(jpegs + [cut, bytes(flip)], 640.0, 480.0, quality=95, cap=64)   # decode, detect, draw, encode in one call
+rb = m.annotate_reencode_batch_jpeg(jpegs[:3], [boxes, boxes[:1], boxes[:0]], 640.0, 480.0, quality=60)
+assert rb[0] == m.annotate_encode_jpeg(jpegs[0], boxes, 640.0, 480.0, 60)
 for K, seed in ((700, 1), (4420, 2), (5001, 3)):
     s = rng.random((K, 2)).astype(np.float32)
     c0 = rng.random((K, 2)).astype(np.float32) * 0.6 + 0.2
