@@ -300,6 +300,11 @@ typedef struct uf_batcher_config {
     uint32_t workers;            /* batches in flight per device (0 = 2) */
     uint32_t det_cap;            /* detections returned per frame (0 = 64) */
     uint32_t max_frame_bytes;    /* pinned slot size (0 = 1280 * 720 * 3) */
+    /* the rest of the worker loop (inferer.rs:38-46): frames submitted as JPEG come back annotated and re-encoded */
+    uint32_t annotate_quality;   /* 0 = detections only; 1..100 = draw the detections and encode at this quality (the reference: 95) */
+    float annotate_scale_w;      /* what the relative boxes are multiplied by (0 = 1280, router.rs:66) */
+    float annotate_scale_h;      /* (0 = 720, router.rs:67) */
+    uint32_t annotate_max_bytes; /* room per annotated file (0 = 1 MiB); a larger file fails its frame with UF_ERR_CAPACITY */
 } uf_batcher_config;
 
 typedef struct uf_result {
@@ -310,6 +315,8 @@ typedef struct uf_result {
     uint32_t n_dets;             /* faces selected (may exceed det_cap; only min(n_dets, det_cap) were returned) */
     uint32_t batch_size;         /* frames in the batch this frame rode in */
     uint64_t latency_us;         /* commit -> result queued */
+    uint32_t file_bytes;         /* annotate mode: size of the frame's annotated JPEG (uf_batcher_poll_frames), else 0 */
+    uint32_t reserved_;
 } uf_result;
 
 typedef struct uf_batcher_stats {
@@ -341,6 +348,10 @@ UF_API int uf_batcher_try_submit_jpeg(uf_batcher* b, uint64_t stream, const uint
 UF_API int uf_batcher_ingest(uf_batcher* b, const uint8_t* msg, size_t len, uint64_t user_tag, int32_t* accepted, uint64_t* stream);
 /* Up to cap finished frames: res[i] + dets[i * det_cap ..]. Waits at most timeout_ms for the first one. */
 UF_API int uf_batcher_poll(uf_batcher* b, uf_result* res, uf_det* dets, uint32_t cap, uint32_t timeout_ms, uint32_t* n_out);
+/* annotate mode: the same, and the annotated JPEG of frame i at files + i * file_stride (res[i].file_bytes bytes);
+ * file_stride >= the configuration's annotate_max_bytes. Glyph atlas: uf_text_atlas_set on uf_batcher_model(b, slot). */
+UF_API int uf_batcher_poll_frames(uf_batcher* b, uf_result* res, uf_det* dets, uint8_t* files, size_t file_stride, uint32_t cap,
+                                  uint32_t timeout_ms, uint32_t* n_out);
 UF_API int uf_batcher_flush(uf_batcher* b, uint32_t timeout_ms); /* returns when everything committed so far is pollable */
 UF_API int uf_batcher_stats_read(const uf_batcher* b, uf_batcher_stats* out);
 UF_API int uf_batcher_owner(const uf_batcher* b, uint64_t stream, int32_t* device);

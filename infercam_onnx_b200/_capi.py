@@ -53,12 +53,14 @@ class uf_jpeg_info(C.Structure):
 class uf_batcher_config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("model", uf_config), ("devices", C.POINTER(C.c_int32)), ("n_devices", C.c_uint32),
                 ("max_batch", C.c_uint32), ("max_delay_us", C.c_uint32), ("capacity", C.c_uint32), ("workers", C.c_uint32),
-                ("det_cap", C.c_uint32), ("max_frame_bytes", C.c_uint32)]
+                ("det_cap", C.c_uint32), ("max_frame_bytes", C.c_uint32), ("annotate_quality", C.c_uint32), ("annotate_scale_w", C.c_float),
+                ("annotate_scale_h", C.c_float), ("annotate_max_bytes", C.c_uint32)]
 
 
 class uf_result(C.Structure):
     _fields_ = [("stream", C.c_uint64), ("user_tag", C.c_uint64), ("device", C.c_int32), ("status", C.c_int32),
-                ("n_dets", C.c_uint32), ("batch_size", C.c_uint32), ("latency_us", C.c_uint64)]
+                ("n_dets", C.c_uint32), ("batch_size", C.c_uint32), ("latency_us", C.c_uint64), ("file_bytes", C.c_uint32),
+                ("reserved_", C.c_uint32)]
 
 
 class uf_batcher_stats(C.Structure):
@@ -130,6 +132,7 @@ SIGNATURES = {
     "uf_batcher_try_submit_jpeg": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_uint64, _p(C.c_int32)]),
     "uf_batcher_ingest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, _p(C.c_int32), _p(C.c_uint64)]),
     "uf_batcher_poll": (C.c_int, [C.c_void_p, _p(uf_result), _p(uf_det), C.c_uint32, C.c_uint32, _p(C.c_uint32)]),
+    "uf_batcher_poll_frames": (C.c_int, [C.c_void_p, _p(uf_result), _p(uf_det), C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, _p(C.c_uint32)]),
     "uf_batcher_flush": (C.c_int, [C.c_void_p, C.c_uint32]),
     "uf_batcher_stats_read": (C.c_int, [C.c_void_p, _p(uf_batcher_stats)]),
     "uf_batcher_owner": (C.c_int, [C.c_void_p, C.c_uint64, _p(C.c_int32)]),

@@ -48,7 +48,8 @@ class StreamBatcher:
     def __init__(self, variant: UltrafaceVariant = UltrafaceVariant.W320H240, max_iou: float = 0.5, min_confidence: float = 0.5, *,
                  onnx_path: Optional[str] = None, size: Optional[Tuple[int, int]] = None, devices: Sequence[int] = (0,),
                  max_batch: int = 64, max_delay: float = 0.002, capacity: int = 0, workers: int = 2, cap: int = 64,
-                 max_frame_bytes: int = 0, backend: Optional[Callable] = None, flags: int = 0, host_chunk: int = 0):
+                 max_frame_bytes: int = 0, backend: Optional[Callable] = None, flags: int = 0, host_chunk: int = 0,
+                 annotate_quality: int = 0, annotate_scale: Tuple[float, float] = (0.0, 0.0), annotate_max_bytes: int = 0):
         """backend: test seam — a Python callable (device, frames: list of HxWx3 arrays) -> list of [n,5] arrays that stands
         in for the batched GPU call (`uf_batcher_create_ex`); the product passes None and gets one handle per device."""
         lib = _capi.load()
@@ -66,6 +67,9 @@ class StreamBatcher:
         cfg.devices, cfg.n_devices = self._devs, len(devices)
         cfg.max_batch, cfg.max_delay_us = max_batch, max(1, int(max_delay * 1e6))
         cfg.capacity, cfg.workers, cfg.det_cap, cfg.max_frame_bytes = capacity, workers, cap, max_frame_bytes
+        cfg.annotate_quality, cfg.annotate_max_bytes = annotate_quality, annotate_max_bytes
+        cfg.annotate_scale_w, cfg.annotate_scale_h = annotate_scale
+        self.file_stride = annotate_max_bytes or (1 << 20)
         self.cap, self.devices = cap, list(devices)
         self._cb = None
         h = C.c_void_p()
@@ -152,6 +156,19 @@ class StreamBatcher:
                                             int(timeout * 1e3), C.byref(n)))
         return [dict(stream=int(r.stream), tag=int(r.user_tag), device=int(r.device), status=int(r.status), n_dets=int(r.n_dets),
                      batch_size=int(r.batch_size), latency_us=int(r.latency_us), dets=dets[i, : min(r.n_dets, self.cap)].copy())
+                for i, r in enumerate(res[: n.value])]
+
+    def poll_frames(self, max_results: int = 64, timeout: float = 0.0) -> List[dict]:
+        """Annotate mode (uf_batcher_poll_frames): poll() plus `file` = the frame's annotated JPEG (b"" for RGB-submitted frames)."""
+        res = (_capi.uf_result * max_results)()
+        dets = np.zeros((max_results, self.cap, 5), np.float32)
+        files = np.empty(max_results * self.file_stride, np.uint8)
+        n = C.c_uint32()
+        _check(_capi.load().uf_batcher_poll_frames(self._h, res, dets.ctypes.data_as(C.POINTER(_capi.uf_det)), files.ctypes.data_as(C.c_void_p),
+                                                   self.file_stride, max_results, int(timeout * 1e3), C.byref(n)))
+        return [dict(stream=int(r.stream), tag=int(r.user_tag), device=int(r.device), status=int(r.status), n_dets=int(r.n_dets),
+                     batch_size=int(r.batch_size), latency_us=int(r.latency_us), dets=dets[i, : min(r.n_dets, self.cap)].copy(),
+                     file=files[i * self.file_stride: i * self.file_stride + r.file_bytes].tobytes())
                 for i, r in enumerate(res[: n.value])]
 
     def _dispatch(self) -> None:

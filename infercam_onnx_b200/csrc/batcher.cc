@@ -43,6 +43,7 @@ struct Ticket {            // one pinned slot
 struct Done {
     uf_result res;
     std::vector<uf_det> dets;
+    std::vector<uint8_t> file;  // annotate mode: the annotated JPEG
 };
 
 struct Device {
@@ -90,6 +91,19 @@ void worker_loop(uf_batcher* b, Device* d) {
     std::vector<uint32_t> ws, hs, counts;
     std::vector<size_t> lens;
     std::vector<uf_det> dets;
+    // annotate mode (frames submitted as JPEG): the whole loop body of inferer.rs:35-46 in one call per batch
+    const bool annotate = !b->backend && b->cfg.annotate_quality > 0;
+    const size_t file_stride = b->cfg.annotate_max_bytes;
+    std::vector<uint8_t> files;
+    std::vector<size_t> file_lens;
+    auto jpeg_call = [&](uint32_t first, uint32_t cnt) -> int {
+        if (!annotate)
+            return uf_infer_batch_jpeg(d->model, ptrs.data() + first, lens.data() + first, cnt, dets.data() + (size_t)first * det_cap, det_cap,
+                                       counts.data() + first);
+        return uf_worker_batch_jpeg(d->model, ptrs.data() + first, lens.data() + first, cnt, b->cfg.annotate_scale_w, b->cfg.annotate_scale_h,
+                                    b->cfg.annotate_quality, dets.data() + (size_t)first * det_cap, det_cap, counts.data() + first,
+                                    files.data() + (size_t)first * file_stride, file_stride, file_lens.data() + first);
+    };
     if (!b->backend) cudaSetDevice(d->ordinal);
     for (;;) {
         uint64_t seq;
@@ -127,17 +141,17 @@ void worker_loop(uf_batcher* b, Device* d) {
             rc_rgb = rc_jpeg = b->backend(b->backend_user, d->ordinal, ptrs.data(), ws.data(), hs.data(), n, dets.data(), det_cap, counts.data());
         } else {
             if (n_rgb) rc_rgb = uf_infer_batch(d->model, ptrs.data(), ws.data(), hs.data(), n_rgb, dets.data(), det_cap, counts.data());
-            if (n > n_rgb)
-                rc_jpeg = uf_infer_batch_jpeg(d->model, ptrs.data() + n_rgb, lens.data() + n_rgb, n - n_rgb,
-                                              dets.data() + (size_t)n_rgb * det_cap, det_cap, counts.data() + n_rgb);
+            if (annotate) {
+                files.resize((size_t)n * file_stride);
+                file_lens.assign(n, 0);
+            }
+            if (n > n_rgb) rc_jpeg = jpeg_call(n_rgb, n - n_rgb);
         }
         // one undecodable file fails the whole JPEG call: isolate it so that its batch-mates are not skipped with it
         std::vector<int> rc_each;
         if (!b->backend && rc_jpeg != UF_OK && n - n_rgb > 1) {
             rc_each.assign(n, UF_OK);
-            for (uint32_t i = n_rgb; i < n; ++i)
-                rc_each[i] = uf_infer_batch_jpeg(d->model, ptrs.data() + i, lens.data() + i, 1, dets.data() + (size_t)i * det_cap, det_cap,
-                                                 counts.data() + i);
+            for (uint32_t i = n_rgb; i < n; ++i) rc_each[i] = jpeg_call(i, 1);
         }
         const auto now = Clock::now();
         std::vector<Done> out(n);
@@ -151,6 +165,10 @@ void worker_loop(uf_batcher* b, Device* d) {
             if (rc == UF_OK) {
                 const uint32_t k = counts[i] < det_cap ? counts[i] : det_cap;
                 o.dets.assign(dets.begin() + (size_t)i * det_cap, dets.begin() + (size_t)i * det_cap + k);
+                if (annotate && i >= n_rgb) {
+                    o.file.assign(files.begin() + (size_t)i * file_stride, files.begin() + (size_t)i * file_stride + file_lens[i]);
+                    o.res.file_bytes = (uint32_t)file_lens[i];
+                }
             }
         }
         {
@@ -262,6 +280,10 @@ int uf_batcher_create_ex(const uf_batcher_config* cfg, uf_batch_fn backend, void
         if (c.workers == 0) c.workers = 2;
         if (c.det_cap == 0) c.det_cap = 64;
         if (c.max_frame_bytes == 0) c.max_frame_bytes = 1280 * 720 * 3;
+        if (c.annotate_scale_w == 0.0f) c.annotate_scale_w = 1280.0f;
+        if (c.annotate_scale_h == 0.0f) c.annotate_scale_h = 720.0f;
+        if (c.annotate_max_bytes == 0) c.annotate_max_bytes = 1u << 20;
+        NEED(c.annotate_quality <= 100 && c.annotate_max_bytes >= 1024, "annotate_quality / annotate_max_bytes out of range");
         NEED(c.workers <= 8 && c.max_batch <= 4096 && c.capacity <= (1u << 20), "workers / max_batch / capacity out of range");
         std::vector<int32_t> ords(cfg->devices ? cfg->devices : nullptr, cfg->devices ? cfg->devices + cfg->n_devices : nullptr);
         if (ords.empty()) ords.push_back(0);
@@ -466,6 +488,28 @@ int uf_batcher_poll(uf_batcher* b, uf_result* res, uf_det* dets, uint32_t cap, u
             Done& o = b->done.front();
             res[n] = o.res;
             if (!o.dets.empty()) memcpy(dets + (size_t)n * b->cfg.det_cap, o.dets.data(), o.dets.size() * sizeof(uf_det));
+            b->done.pop_front();
+            ++n;
+        }
+        *n_out = n;
+    });
+}
+
+int uf_batcher_poll_frames(uf_batcher* b, uf_result* res, uf_det* dets, uint8_t* files, size_t file_stride, uint32_t cap, uint32_t timeout_ms,
+                           uint32_t* n_out) {
+    return guarded([&] {
+        NEED(b && n_out && (cap == 0 || (res && dets && files)), "null argument");
+        NEED(file_stride >= b->cfg.annotate_max_bytes, "file_stride smaller than uf_batcher_config.annotate_max_bytes");
+        *n_out = 0;
+        std::unique_lock<std::mutex> lk(b->done_mu);
+        if (b->done.empty() && timeout_ms)
+            b->done_cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return !b->done.empty(); });
+        uint32_t n = 0;
+        while (n < cap && !b->done.empty()) {
+            Done& o = b->done.front();
+            res[n] = o.res;
+            if (!o.dets.empty()) memcpy(dets + (size_t)n * b->cfg.det_cap, o.dets.data(), o.dets.size() * sizeof(uf_det));
+            if (!o.file.empty()) memcpy(files + (size_t)n * file_stride, o.file.data(), o.file.size());
             b->done.pop_front();
             ++n;
         }

@@ -120,6 +120,10 @@ pub struct uf_batcher_config {
     pub workers: u32,
     pub det_cap: u32,
     pub max_frame_bytes: u32,
+    pub annotate_quality: u32,
+    pub annotate_scale_w: f32,
+    pub annotate_scale_h: f32,
+    pub annotate_max_bytes: u32,
 }
 
 #[repr(C)]
@@ -132,6 +136,8 @@ pub struct uf_result {
     pub n_dets: u32,
     pub batch_size: u32,
     pub latency_us: u64,
+    pub file_bytes: u32,
+    pub reserved_: u32,
 }
 
 #[repr(C)]
@@ -236,6 +242,8 @@ extern "C" {
     pub fn uf_batcher_ingest(b: *mut uf_batcher, msg: *const u8, len: usize, user_tag: u64, accepted: *mut i32, stream: *mut u64) -> c_int;
     pub fn uf_batcher_poll(b: *mut uf_batcher, res: *mut uf_result, dets: *mut uf_det, cap: u32, timeout_ms: u32,
                            n_out: *mut u32) -> c_int;
+    pub fn uf_batcher_poll_frames(b: *mut uf_batcher, res: *mut uf_result, dets: *mut uf_det, files: *mut u8, file_stride: usize, cap: u32,
+                                  timeout_ms: u32, n_out: *mut u32) -> c_int;
     pub fn uf_batcher_flush(b: *mut uf_batcher, timeout_ms: u32) -> c_int;
     pub fn uf_batcher_stats_read(b: *const uf_batcher, out: *mut uf_batcher_stats) -> c_int;
     pub fn uf_batcher_owner(b: *const uf_batcher, stream: u64, device: *mut i32) -> c_int;

@@ -274,3 +274,47 @@ def test_gpu_ingest_of_wire_messages_end_to_end(make_onnx, test_pics):
         assert sec > 0 and ndet == 3 * sum(exp_counts)
     finally:
         b.close()
+
+
+@pytest.mark.gpu
+def test_gpu_batcher_annotate_mode_returns_the_reference_loop_output(make_onnx, test_pics):
+    """annotate_quality > 0: a frame submitted as JPEG comes back with its detections AND the annotated, re-encoded frame —
+    everything `Inferer::run` does per frame (inferer.rs:35-46) — equal to the per-frame calls on the same handle."""
+    import io
+
+    from PIL import Image
+
+    from oracle import ingest
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    rng = np.random.default_rng(21)
+    frames = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(5)] + list(test_pics.values())[:3]
+    jpegs = []
+    for f in frames:
+        bio = io.BytesIO()
+        Image.fromarray(f).save(bio, "JPEG", quality=88, subsampling=1)
+        jpegs.append(bio.getvalue())
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=16)
+    exp_d, exp_c = m.run_batch_jpeg(jpegs, cap=64)
+    exp_f = [m.annotate_encode_jpeg(j, d, 1280.0, 720.0, quality=95) for j, d in zip(jpegs, exp_d)]
+    m.close()
+    b = StreamBatcher(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=8, max_delay=0.002, capacity=64, workers=2, cap=64,
+                      annotate_quality=95, annotate_max_bytes=1 << 20)
+    try:
+        for rep in range(2):
+            for i, j in enumerate(jpegs):
+                assert b.ingest(ingest.protomsg_frame("cam-%d" % (i % 3), j), tag=rep * 100 + i)[0]
+        assert b.try_submit(7, frames[0], tag=999)           # an RGB frame: detections only
+        assert b.ingest(ingest.protomsg_frame("cam-0", b"\xff\xd8 not a jpeg"), tag=998)[0]
+        b.flush()
+        res = {r["tag"]: r for r in b.poll_frames(64)}
+        assert len(res) == 2 * len(jpegs) + 2
+        for rep in range(2):
+            for i in range(len(jpegs)):
+                r = res[rep * 100 + i]
+                assert r["status"] == 0 and r["n_dets"] == exp_c[i]
+                np.testing.assert_array_equal(r["dets"], exp_d[i])
+                assert r["file"] == exp_f[i], (rep, i, len(r["file"]), len(exp_f[i]))
+        assert res[999]["status"] == 0 and res[999]["file"] == b"" and res[999]["n_dets"] > 0
+        assert res[998]["status"] != 0 and res[998]["file"] == b""
+    finally:
+        b.close()
