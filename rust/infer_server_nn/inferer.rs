@@ -56,6 +56,13 @@ impl Inferer {
             workers: 2,
             det_cap: DET_CAP as u32,
             max_frame_bytes: 1280 * 720 * 3,
+            // 0: this glue draws and re-encodes on the CPU as the reference does. Set to 95 (and hand the frames over as JPEG with
+            // `uf_batcher_ingest` / `uf_batcher_try_submit_jpeg`, polling with `uf_batcher_poll_frames`) and the library returns
+            // the annotated, re-encoded frame itself: decode, draw and encode then run on the GPU too.
+            annotate_quality: 0,
+            annotate_scale_w: 0.0,
+            annotate_scale_h: 0.0,
+            annotate_max_bytes: 0,
         };
         let mut batcher = std::ptr::null_mut();
         let rc = unsafe { sys::uf_batcher_create(&cfg, &mut batcher) };
