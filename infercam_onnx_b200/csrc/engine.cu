@@ -133,6 +133,8 @@ struct Slot {
     size_t jpeg_cap = 0;
     uint8_t* d_planes = nullptr;
     size_t planes_cap = 0;
+    uint8_t* d_ovl = nullptr;    // overlay lists of the frames being annotated (per slot: calls on different lanes run concurrently)
+    size_t ovl_cap = 0;
     uint8_t* d_huff = nullptr;   // GPU Huffman scratch: subsequence states, block counts, dense coefficient blocks
     size_t huff_cap = 0;
     int* h_jstatus = nullptr;    // pinned [chunk + 1]: per frame of the stage 0 = decoded on the GPU, else redo on the host; [chunk] = round flag
@@ -1536,7 +1538,7 @@ uf_model::~uf_model() {
         for (auto& g : s.graphs) cudaGraphExecDestroy(g.second);
         cudaFree(s.d_in); cudaFree(s.d_resized); cudaFree(s.d_arena); cudaFree(s.d_dets); cudaFree(s.d_sel);
         cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort); cudaFree(s.d_big_n); cudaFree(s.d_mask);
-        cudaFreeHost(s.h_jpeg); cudaFree(s.d_jpeg); cudaFree(s.d_planes); cudaFree(s.d_huff); cudaFreeHost(s.h_jstatus);
+        cudaFreeHost(s.h_jpeg); cudaFree(s.d_jpeg); cudaFree(s.d_planes); cudaFree(s.d_huff); cudaFree(s.d_ovl); cudaFreeHost(s.h_jstatus);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_dets);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -1895,7 +1897,15 @@ static void draw_overlays(uf_model& m, Slot& s, const std::vector<OverlayLists>&
     int4* hr = reinterpret_cast<int4*>(host.data() + b_f);
     uint32_t* hs = reinterpret_cast<uint32_t*>(host.data() + b_f + b_r);
     OverlayGlyph* hg = reinterpret_cast<OverlayGlyph*>(host.data() + b_f + b_r + b_s);
-    uint8_t* d = (uint8_t*)hook_scratch(m, host.size());
+    if (host.size() > s.ovl_cap) {
+        CK(cudaStreamSynchronize(s.stream));
+        cudaFree(s.d_ovl);
+        s.d_ovl = nullptr;
+        s.ovl_cap = 0;
+        CK(cudaMalloc(&s.d_ovl, host.size() * 2));
+        s.ovl_cap = host.size() * 2;
+    }
+    uint8_t* d = s.d_ovl;
     size_t ir = 0, is = 0, ig = 0;
     for (size_t k = 0; k < L.size(); ++k) {
         const auto& l = L[k];

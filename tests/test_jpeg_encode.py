@@ -249,3 +249,39 @@ def test_gpu_worker_batch_is_decode_detect_draw_encode(make_onnx, test_pics):
             assert files[i] == m.annotate_encode_jpeg(jpegs[i], want_d[i], 1280.0, 720.0, quality=95), i
     finally:
         m.close()
+
+
+@pytest.mark.gpu
+def test_gpu_worker_calls_in_flight_do_not_share_scratch(make_onnx, test_pics):
+    """Several host threads on one handle (one lane each): every call's detections and files are the single-threaded ones."""
+    import threading
+
+    path = make_onnx(320, 240, cls_bias=-0.75)
+    m = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, max_batch=32, lanes=4)
+    try:
+        rng = np.random.default_rng(13)
+        m.text_atlas_set(*_synthetic_atlas(4))
+
+        def enc(a, q, ss):
+            b = io.BytesIO()
+            Image.fromarray(a).save(b, "JPEG", quality=q, subsampling=ss)
+            return b.getvalue()
+        sets = [[enc(rng.integers(0, 256, (480, 640, 3), dtype=np.uint8), 85 + t, 1) for _ in range(6 + 3 * t)] +
+                [enc(p, 80 + t, 2) for p in list(test_pics.values())[t:t + 3]] for t in range(4)]
+        want = [m.worker_batch_jpeg(js, 1280.0, 720.0, quality=95, cap=64) for js in sets]
+        got = [None] * 4
+        errs = []
+
+        def work(t):
+            try:
+                for _ in range(6):
+                    got[t] = m.worker_batch_jpeg(sets[t], 1280.0, 720.0, quality=95, cap=64)
+                    assert got[t][1] == want[t][1] and got[t][2] == want[t][2]
+            except Exception as e:  # noqa: BLE001
+                errs.append((t, repr(e)))
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs
+    finally:
+        m.close()
