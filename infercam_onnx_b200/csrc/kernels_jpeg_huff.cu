@@ -66,15 +66,21 @@ __device__ __forceinline__ unsigned long long cta_sum(unsigned long long v, unsi
 // min(ceil(nsub / JHT), JH_MAX_ROUNDS) launches are made — a fixed number, no flag to read back, nothing for the host to
 // wait on — and the write pass CHECKS the fixed point (every thread's start state is its predecessor's end state); a frame
 // that fails the check is handed to the host decoder like any other the device declines. A CTA whose incoming state did
-// not change since its last run copies its end states and leaves.
+// not change since its last run copies its end states and leaves. In every iteration the subsequences that have to be
+// decoded again are packed to the front of the CTA (ballot + prefix), so that however few and scattered they are, the
+// decode runs in full warps.
 __global__ void __launch_bounds__(JHT)
 jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out) {
     __shared__ __align__(16) Tabs tabs;
-    __shared__ unsigned long long s_end[JHT];
+    // per subsequence of the CTA: the start state of its last decode, the end state that gave, what it counted
+    __shared__ unsigned long long s_start[JHT], s_end[JHT], s_ns[JHT];
+    __shared__ uint32_t s_cnt[JHT], s_woff[JHT / 32];
+    __shared__ uint16_t s_list[JHT];
+    __shared__ uint8_t s_dirty[JHT];
     const JpegHuffFrame& fr = b.frames[blockIdx.y];
     const uint32_t nsub = fr.nsub, t0 = blockIdx.x * JHT, sub_bits = fr.sub_bits;
     if (t0 >= nsub) return;
-    const uint32_t t = t0 + threadIdx.x;
+    const uint32_t tid = threadIdx.x, t = t0 + tid, lane = tid & 31, warp = tid >> 5;
     const bool active = t < nsub;
     const size_t gi = (size_t)fr.sub_base + t;
     const unsigned long long cta_start =
@@ -84,39 +90,54 @@ jhuff_sync_kernel(JpegHuffBatch b, int first, const unsigned long long* __restri
         return;
     }
     load_tabs(tabs, b.tabsets[fr.tabset]);
-    unsigned long long my_start = ~0ull, my_end = 0;
-    uint32_t my_n = 0;
-    bool dirty = false;
-    if (first) {
-        my_end = pack_state((t + 1) * sub_bits, 0, 0);  // the next thread's first guess: its own beginning, slot 0, DC
-    } else if (active) {
-        my_start = b.start_used[gi];
-        my_end = in[gi];
-    }
-    s_end[threadIdx.x] = my_end;
+    s_start[tid] = (!first && active) ? b.start_used[gi] : ~0ull;
+    // first launch: a thread's "end state" is the next thread's first guess — its own beginning, slot 0, DC
+    s_end[tid] = first ? pack_state((t + 1) * sub_bits, 0, 0) : (active ? in[gi] : 0ull);
+    s_cnt[tid] = 0;
+    s_dirty[tid] = 0;
     __syncthreads();
     const uint32_t* data = reinterpret_cast<const uint32_t*>(b.bytes + fr.data_off);
-    const uint32_t p_end = min((t + 1) * sub_bits, fr.data_bits), bpm = fr.blocks_per_mcu, slotmap = fr.slotmap;
+    const uint32_t data_bits = fr.data_bits, bpm = fr.blocks_per_mcu, slotmap = fr.slotmap;
     for (int iter = 0; iter <= JHT; ++iter) {
-        const unsigned long long ns = threadIdx.x == 0 ? cta_start : s_end[threadIdx.x - 1];
-        bool ch = false;
-        if (active && ns != my_start) {
-            uint32_t p = (uint32_t)(ns >> 32), slot = (uint32_t)(ns >> 8) & 0xff, k = (uint32_t)ns & 0xff;
-            if (slot >= bpm) slot = 0;
-            my_n = huff_run<false>(tabs, slotmap, bpm, 0, data, p, slot, k, p_end, HuffOut{}, 0, 0);
-            my_end = pack_state(p, slot, k);
-            my_start = ns;
-            ch = dirty = true;
+        // who has to decode again: every subsequence whose predecessor's end state is not the state it started from last time
+        const unsigned long long ns = tid == 0 ? cta_start : s_end[tid - 1];
+        const bool need = active && ns != s_start[tid];
+        const uint32_t bal = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) s_woff[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < JHT / 32; ++w) {
+            const uint32_t c = s_woff[w];
+            if (w < (int)warp) base += c;
+            total += c;
         }
-        __syncthreads();  // every thread has read its neighbour's state
-        if (ch) s_end[threadIdx.x] = my_end;
-        if (!__syncthreads_or(ch)) break;
+        if (total == 0) break;  // (uniform) the CTA agrees with itself
+        if (need) {  // those are packed to the front, so that the decode below runs in full warps however few they are
+            const uint32_t pos = base + __popc(bal & ((1u << lane) - 1u));
+            s_list[pos] = (uint16_t)tid;
+            s_ns[pos] = ns;
+        }
+        __syncthreads();
+        if (tid < total) {
+            const uint32_t i = s_list[tid];
+            const unsigned long long st = s_ns[tid];
+            uint32_t p = (uint32_t)(st >> 32), slot = (uint32_t)(st >> 8) & 0xff, k = (uint32_t)st & 0xff;
+            if (slot >= bpm) slot = 0;
+            const uint32_t p_end = min((t0 + i + 1) * sub_bits, data_bits);
+            const uint32_t n = huff_run<false>(tabs, slotmap, bpm, 0, data, p, slot, k, p_end, HuffOut{}, 0, 0);
+            s_start[i] = st;
+            s_end[i] = pack_state(p, slot, k);
+            s_cnt[i] = n;
+            s_dirty[i] = 1;
+        }
+        __syncthreads();
     }
     if (active) {
-        out[gi] = my_end;
-        if (dirty) {
-            b.start_used[gi] = my_start;
-            b.counts[gi] = my_n;
+        out[gi] = s_end[tid];
+        if (s_dirty[tid]) {
+            b.start_used[gi] = s_start[tid];
+            b.counts[gi] = s_cnt[tid];
         }
     }
 }
