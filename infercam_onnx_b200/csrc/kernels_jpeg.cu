@@ -122,25 +122,6 @@ jpeg_idct_kernel(JpegBatchDev b) {
     *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
 }
 
-// upsampled chroma sample at output (x, y): libjpeg-turbo's fancy (triangle) upsampling
-__device__ __forceinline__ int jup(const uint8_t* __restrict__ plane, int pw, int rw, int rh, int hr, int vr, int x, int y) {
-    if (hr == 1) return plane[(size_t)y * pw + x];  // (4:4:4; 4:4:0 is refused by the parser)
-    const int cx = x >> 1;
-    if (vr == 1) {  // h2v1_fancy_upsample
-        const uint8_t* in = plane + (size_t)y * pw;
-        if (x & 1) return cx == rw - 1 ? in[cx] : (in[cx] * 3 + in[cx + 1] + 2) >> 2;
-        return cx == 0 ? in[0] : (in[cx] * 3 + in[cx - 1] + 1) >> 2;
-    }
-    // h2v2_fancy_upsample: the nearer input row counts 3, the farther 1; context rows replicate the first / last real row
-    const int cy = y >> 1;
-    const int oy = min(max((y & 1) ? cy + 1 : cy - 1, 0), rh - 1);
-    const uint8_t* in0 = plane + (size_t)cy * pw;
-    const uint8_t* in1 = plane + (size_t)oy * pw;
-    const int thiscol = in0[cx] * 3 + in1[cx];
-    if (x & 1) return cx == rw - 1 ? (thiscol * 4 + 7) >> 4 : (thiscol * 3 + in0[cx + 1] * 3 + in1[cx + 1] + 7) >> 4;
-    return cx == 0 ? (thiscol * 4 + 8) >> 4 : (thiscol * 3 + in0[cx - 1] * 3 + in1[cx - 1] + 8) >> 4;
-}
-
 __device__ __forceinline__ unsigned jclamp(int v) { return (unsigned)min(max(v, 0), 255); }
 
 // jdcolor.c: Cr_r_tab[cr] = (FIX(1.40200) * (cr-128) + ONE_HALF) >> 16, Cb_b_tab likewise with 1.77200,
@@ -152,41 +133,68 @@ __device__ __forceinline__ void jycc(int y, int cb, int cr, unsigned& r, unsigne
     bl = jclamp(y + ((116130 * cb + 32768) >> 16));
 }
 
+// The chroma samples of a quad of pixels x0 .. x0 + 3 (x0 a multiple of 4) of row y at once: the four chroma columns it
+// touches are fetched once (jup would fetch them per pixel). Same arithmetic as jup, pixel for pixel.
+__device__ __forceinline__ void jup_quad(const uint8_t* __restrict__ plane, int pw, int rw, int rh, int hr, int vr, int x0, int y, int nx, int out[4]) {
+    if (hr == 1) {
+        const uint8_t* in = plane + (size_t)y * pw + x0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[k] = k < nx ? in[k] : 0;
+        return;
+    }
+    const int c0 = x0 >> 1;  // pixels 0, 1 -> chroma column c0; pixels 2, 3 -> c0 + 1
+    const bool has_a = c0 > 0, has_c = c0 + 1 < rw, has_d = c0 + 2 < rw;
+    if (vr == 1) {  // h2v1_fancy_upsample
+        const uint8_t* in = plane + (size_t)y * pw + c0;
+        const int a = has_a ? in[-1] : 0, bq = in[0], c = has_c ? in[1] : 0, d = has_d ? in[2] : 0;
+        out[0] = has_a ? (bq * 3 + a + 1) >> 2 : bq;
+        out[1] = has_c ? (bq * 3 + c + 2) >> 2 : bq;       // (c0 == rw - 1: the last column repeats)
+        out[2] = (c * 3 + bq + 1) >> 2;
+        out[3] = has_d ? (c * 3 + d + 2) >> 2 : c;
+        return;
+    }
+    // h2v2_fancy_upsample: the nearer input row counts 3, the farther 1; context rows replicate the first / last real row
+    const int cy = y >> 1;
+    const int oy = min(max((y & 1) ? cy + 1 : cy - 1, 0), rh - 1);
+    const uint8_t* in0 = plane + (size_t)cy * pw + c0;
+    const uint8_t* in1 = plane + (size_t)oy * pw + c0;
+    const int ta = has_a ? in0[-1] * 3 + in1[-1] : 0, tb = in0[0] * 3 + in1[0], tc = has_c ? in0[1] * 3 + in1[1] : 0,
+              td = has_d ? in0[2] * 3 + in1[2] : 0;
+    out[0] = has_a ? (tb * 3 + ta + 8) >> 4 : (tb * 4 + 8) >> 4;
+    out[1] = has_c ? (tb * 3 + tc + 7) >> 4 : (tb * 4 + 7) >> 4;
+    out[2] = (tc * 3 + tb + 8) >> 4;
+    out[3] = has_d ? (tc * 3 + td + 7) >> 4 : (tc * 4 + 7) >> 4;
+}
+
 __global__ void __launch_bounds__(256)
 jpeg_color_kernel(JpegBatchDev b) {
-    __shared__ JpegPlan plan;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(b.plans + blockIdx.y);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&plan);
-        for (int i = threadIdx.x; i < (int)(sizeof(JpegPlan) / 4); i += 256) dst[i] = src[i];
-    }
-    __syncthreads();
+    const JpegPlan& plan = b.plans[blockIdx.y];  // (a few fields, the same for every thread: served from L1)
+    if (b.status && b.status[blockIdx.y] != 0) return;  // declined by the device Huffman decoder: redone on the host
     const int w = (int)plan.w, h = (int)plan.h;
     const int quads = (w + 3) >> 2;
-    const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (q >= (long long)quads * h) return;
-    const int y = (int)(q / quads), x0 = (int)(q - (long long)y * quads) * 4;
+    const uint32_t q = blockIdx.x * 256u + threadIdx.x;  // (frames are at most 16384 x 16384: quads * h < 2^32)
+    if (q >= (uint32_t)quads * (uint32_t)h) return;
+    const int y = (int)(q / (uint32_t)quads), x0 = (int)(q - (uint32_t)y * (uint32_t)quads) * 4;
     const uint8_t* planes = b.planes + (((size_t)plan.planes_off_hi << 32) | plan.planes_off_lo);
     uint8_t* rgb = b.rgb + (((size_t)plan.rgb_off_hi << 32) | plan.rgb_off_lo) + ((size_t)y * w + x0) * 3;
     const uint8_t* yp = planes + plan.plane_off[0] + (size_t)y * plan.plane_w[0] + x0;
     unsigned px[12];
     const int nx = min(4, w - x0);
+    const uchar4 y4 = *reinterpret_cast<const uchar4*>(yp);  // (x0 and the plane's width and offset are multiples of 4 or more)
+    const int ys[4] = {y4.x, y4.y, y4.z, y4.w};
     if (plan.ncomp == 1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) px[3 * k] = px[3 * k + 1] = px[3 * k + 2] = k < nx ? yp[k] : 0;
+        for (int k = 0; k < 4; ++k) px[3 * k] = px[3 * k + 1] = px[3 * k + 2] = k < nx ? ys[k] : 0;
     } else {
-        const uint8_t* cbp = planes + plan.plane_off[1];
-        const uint8_t* crp = planes + plan.plane_off[2];
         const int hr = (int)(plan.hmax / plan.hs[1]), vr = (int)(plan.vmax / plan.vs[1]);
         const int pw = (int)plan.plane_w[1], rw = (int)plan.real_w[1], rh = (int)plan.real_h[1];
+        int cb[4], cr[4];
+        jup_quad(planes + plan.plane_off[1], pw, rw, rh, hr, vr, x0, y, nx, cb);
+        jup_quad(planes + plan.plane_off[2], pw, rw, rh, hr, vr, x0, y, nx, cr);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (k < nx) {
-                const int cb = jup(cbp, pw, rw, rh, hr, vr, x0 + k, y), cr = jup(crp, pw, rw, rh, hr, vr, x0 + k, y);
-                jycc(yp[k], cb, cr, px[3 * k], px[3 * k + 1], px[3 * k + 2]);
-            } else {
-                px[3 * k] = px[3 * k + 1] = px[3 * k + 2] = 0;
-            }
+            if (k < nx) jycc(ys[k], cb[k], cr[k], px[3 * k], px[3 * k + 1], px[3 * k + 2]);
+            else px[3 * k] = px[3 * k + 1] = px[3 * k + 2] = 0;
         }
     }
     if (nx == 4 && (reinterpret_cast<size_t>(rgb) & 3) == 0) {
