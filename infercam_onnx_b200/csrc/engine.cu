@@ -117,6 +117,8 @@ constexpr int DET_FAST = 128;  // detections per frame copied back with the coun
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaEvent_t done_ev = nullptr;  // blocking-sync event at the end of a host-input stage (see wait_slot)
+    bool sleep_wait = false;        // the pending stage recorded done_ev
     uint8_t* d_in = nullptr;
     size_t d_in_cap = 0;
     uint8_t* d_resized = nullptr;
@@ -256,6 +258,10 @@ struct uf_model {
     Plan plan;
     int K = 0;
     uint32_t chunk = 0, host_chunk = 0, jpeg_chunk = 0, nslots = 0;
+    // frames in a host-input stage from which its waiter sleeps on a blocking event instead of spinning (UF_SLEEP_WAIT_FROM).
+    // 0 = never, the default: measured on one GPU, a sleeping waiter wakes late enough to cost the in-flight path 40 %; it is
+    // there for hosts that run many ranks on few cores.
+    uint32_t sleep_wait_from = 0;
     uint32_t jh_threads = 150000, jh_bits = 0;  // device Huffman: threads a run should have / forced bits per thread (tuning knobs)
     std::vector<Step> steps;
     std::vector<size_t> w_off, b_off;  // per plan op, floats into d_weights
@@ -674,6 +680,7 @@ static void alloc_lane(uf_model& m, Lane& ln) {
     uint64_t ws = 0;
     for (auto& s : ln.slots) {
         CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s.done_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         s.d_in_cap = (size_t)m.chunk * 640 * 480 * 3;
         CK(cudaMalloc(&s.d_in, s.d_in_cap));
         CK(cudaMalloc(&s.d_resized, (size_t)m.chunk * H * W * 3));
@@ -918,6 +925,10 @@ static void run_cnn(uf_model& m, Slot& s, const U8View& input, int frames, size_
 }
 
 static void wait_slot(uf_model& m, Slot& s) {
+    if (s.sleep_wait) {
+        s.sleep_wait = false;
+        CK(cudaEventSynchronize(s.done_ev));
+    }
     CK(cudaStreamSynchronize(s.stream));
     if (m.profiling) collect_profile(m, s);
 }
@@ -1358,6 +1369,9 @@ static void run_chunk_host(uf_model& m, Lane& ln, Slot& s, const FrameSrc* fr, u
     if (all_double) input = U8View{s.d_in, (long long)fr[0].w * fr[0].h * 3, (int)fr[0].h, (int)fr[0].w};
     run_body(m, ln, s, input, first, (int)n);
     s.pending = true; s.first = first; s.n = n;
+    // (optional, see uf_model::sleep_wait_from)
+    s.sleep_wait = m.sleep_wait_from > 0 && n >= m.sleep_wait_from;
+    if (s.sleep_wait) CK(cudaEventRecord(s.done_ev, s.stream));
 }
 
 // One chunk of device-resident frames (identical size, contiguous) on slot s.
@@ -1396,6 +1410,7 @@ static void abandon_lane(uf_model& m, Lane& ln) {
         }
         cudaStreamSynchronize(s.stream);
         s.pending = false;
+        s.sleep_wait = false;
         s.ev_used = 0;
         s.n = 0;
         s.jstatus_n = 0;
@@ -1497,6 +1512,7 @@ static uf_model* load_model(const uf_config& cfg_in) {
     if (cfg.host_chunk) m->host_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, cfg.host_chunk));
     m->jpeg_chunk = std::max(m->host_chunk, std::min<uint32_t>(chunk, 128));
     if (const char* e = getenv("UF_JPEG_CHUNK")) m->jpeg_chunk = std::max<uint32_t>(1, std::min<uint32_t>(chunk, (uint32_t)atoi(e)));  // tuning knob
+    if (const char* e = getenv("UF_SLEEP_WAIT_FROM")) m->sleep_wait_from = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("UF_JH_THREADS")) m->jh_threads = (uint32_t)std::max(1, atoi(e));
     if (const char* e = getenv("UF_JH_BITS"); e && atoi(e) > 0) m->jh_bits = std::max(JH_MIN_SUBSEQ_BITS, std::min(JH_MAX_SUBSEQ_BITS, (uint32_t)atoi(e) / 32 * 32));
     uint32_t nslots = cfg.slots ? cfg.slots : 4;
@@ -1540,6 +1556,7 @@ uf_model::~uf_model() {
         cudaFree(s.d_det_idx); cudaFree(s.d_counts); cudaFree(s.d_sort); cudaFree(s.d_big_n); cudaFree(s.d_mask);
         cudaFreeHost(s.h_jpeg); cudaFree(s.d_jpeg); cudaFree(s.d_planes); cudaFree(s.d_huff); cudaFree(s.d_ovl); cudaFreeHost(s.h_jstatus);
         cudaFreeHost(s.h_counts); cudaFreeHost(s.h_dets);
+        if (s.done_ev) cudaEventDestroy(s.done_ev);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     taps.clear();
@@ -2033,6 +2050,14 @@ int uf_annotate_reencode_jpeg(uf_model* m, const uint8_t* jpeg, size_t len, cons
     });
 }
 
+// waits for everything queued on the slot's stream, asleep (the waits of the annotate path are long: a stage of frames each)
+static void sleep_sync(uf_model& m, Slot& s) {
+    (void)m;
+    CK(cudaEventRecord(s.done_ev, s.stream));
+    CK(cudaEventSynchronize(s.done_ev));
+    CK(cudaStreamSynchronize(s.stream));
+}
+
 // One chunk of the batch form: frames [0, cnt) of jpeg/len, their detections at dets + det_first[k]; files to out + k * stride.
 // Everything runs on slot 0 of the caller's lane, stage after stage, with three waits for the device (decode status, the
 // sizes of the entropy-coded segments, the segments themselves).
@@ -2107,7 +2132,7 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
         else decode_jpeg_run(m, s, fr.data() + i, j - i, s.d_in + rgb_off[i], ju, pu);
         i = j;
     }
-    CK(cudaStreamSynchronize(s.stream));
+    sleep_sync(m, s);
     s.jstatus_n = 0;
     for (uint32_t k = 0; k < cnt; ++k) {
         if (!fr[k].jb || s.h_jstatus[k] == 0) continue;
@@ -2116,7 +2141,7 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
         FrameSrc one{nullptr, hostc[k].plan.w, hostc[k].plan.h, &hostc[k], nullptr};
         size_t ju1 = 0, pu1 = 0;
         decode_jpeg_run(m, s, &one, 1, s.d_in + rgb_off[k], ju1, pu1);
-        CK(cudaStreamSynchronize(s.stream));
+        sleep_sync(m, s);
         m.jpeg_redone++;
     }
     // 3b. the hot path on the decoded frames, run of same-size frames by run (they only read the pixels)
@@ -2195,7 +2220,7 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
     launch_jpeg_huffman_encode(B, (int)cnt, max_nblk, s.stream);
     uint32_t* h_len = reinterpret_cast<uint32_t*>(s.h_jstatus);
     CK(cudaMemcpyAsync(h_len, s.d_huff + e_ol, cnt * 4, cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
+    sleep_sync(m, s);
     // 6. files: the segments come back through the pinned staging buffer in one burst of copies, host threads then write
     //    headers + segment + EOI into the caller's buffer
     std::vector<size_t> seg_off(cnt, 0);
@@ -2208,7 +2233,7 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
     for (uint32_t k = 0; k < cnt; ++k)
         if (seg_len[k] != 0xffffffffu && seg_len[k] > 0)
             CK(cudaMemcpyAsync(s.h_jpeg + seg_off[k], s.d_huff + e_out + encf[k].out_off, seg_len[k], cudaMemcpyDeviceToHost, s.stream));
-    CK(cudaStreamSynchronize(s.stream));
+    sleep_sync(m, s);
     CK(cudaGetLastError());
     std::atomic<bool> too_small{false};
     std::vector<std::string> fails(cnt);

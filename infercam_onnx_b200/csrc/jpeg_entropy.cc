@@ -79,12 +79,13 @@ struct HuffTable {
             if (k >= -128 && k <= 127) fast_ac[i] = (int16_t)((k * 256) + (run * 16) + (len + mag));
         }
     }
-    void set(const uint8_t* b, const uint8_t* v, int n) {
+    // derive_now = false: only bits / vals are wanted (the device decoder builds its own tables from them)
+    void set(const uint8_t* b, const uint8_t* v, int n, bool derive_now = true) {
         memcpy(bits, b, 16);
         memset(vals, 0, sizeof(vals));
         memcpy(vals, v, (size_t)n);
         defined = true;
-        derive();
+        if (derive_now) derive();
     }
 };
 
@@ -182,7 +183,7 @@ struct Parsed {
 
 uint32_t be16(const uint8_t* p) { return ((uint32_t)p[0] << 8) | p[1]; }
 
-void parse(const uint8_t* d, size_t len, Parsed& P, bool want_scan) {
+void parse(const uint8_t* d, size_t len, Parsed& P, bool want_scan, bool derive_tables = true) {
     if (len < 4 || d[0] != 0xff || d[1] != 0xd8) fail(UF_ERR_INVALID_ARG, "no SOI marker");
     size_t i = 2;
     for (;;) {
@@ -234,7 +235,7 @@ void parse(const uint8_t* d, size_t len, Parsed& P, bool want_scan) {
                     if (code > (1 << (k + 1))) fail(UF_ERR_INVALID_ARG, "DHT is not a prefix code");
                     code <<= 1;
                 }
-                (tc ? P.ac[th] : P.dc[th]).set(s + q + 1, s + q + 17, cnt);
+                (tc ? P.ac[th] : P.dc[th]).set(s + q + 1, s + q + 17, cnt, derive_tables);
                 q += 17 + cnt;
             }
         } else if (m == 0xdb) {  // DQT (zigzag order in the file)
@@ -348,11 +349,11 @@ void jpeg_build_tabset(const JpegHuffKey& key, JpegHuffTabSet& out) {
 
 void jpeg_prepare_bitstream(const uint8_t* data, size_t len, JpegBitstream& out) {
     Parsed P;
-    parse(data, len, P, true);
-    if (!P.dc[0].defined) P.dc[0].set(kStdDcLumBits, kStdDcVals, 12);
-    if (!P.dc[1].defined) P.dc[1].set(kStdDcChrBits, kStdDcVals, 12);
-    if (!P.ac[0].defined) P.ac[0].set(kStdAcLumBits, kStdAcLumVals, 162);
-    if (!P.ac[1].defined) P.ac[1].set(kStdAcChrBits, kStdAcChrVals, 162);
+    parse(data, len, P, true, false);  // (the decoder tables are not derived here: the device decoder wants the DHT content only)
+    if (!P.dc[0].defined) P.dc[0].set(kStdDcLumBits, kStdDcVals, 12, false);
+    if (!P.dc[1].defined) P.dc[1].set(kStdDcChrBits, kStdDcVals, 12, false);
+    if (!P.ac[0].defined) P.ac[0].set(kStdAcLumBits, kStdAcLumVals, 162, false);
+    if (!P.ac[1].defined) P.ac[1].set(kStdAcChrBits, kStdAcChrVals, 162, false);
     const JpegPlan& p = P.plan;
     out.plan = p;
     JpegHuffFrame& h = out.huff;
