@@ -372,6 +372,8 @@ def main():
         return float(t.item())
 
     tmp = tempfile.TemporaryDirectory()
+    if world > 1:  # one rank per GPU on one host: split the host's cores between the ranks' worker pools
+        os.environ.setdefault("UF_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // world)))
     path, w, h = make_model_file(tmp.name, args)
     B = args.batch
     model = nn.UltrafaceModel.new(nn.UltrafaceVariant.W320H240, 0.5, 0.5, onnx_path=path, size=(w, h), device=local,

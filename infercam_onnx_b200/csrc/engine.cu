@@ -179,6 +179,8 @@ public:
     HostPool() {
         unsigned n = std::thread::hardware_concurrency();
         n = std::max(1u, std::min(n ? n - 1 : 1u, 31u));
+        // several ranks on one host: every rank's pool sized for the whole machine only makes them fight (UF_HOST_THREADS)
+        if (const char* e = getenv("UF_HOST_THREADS")) n = std::max(1u, std::min(n, (unsigned)std::max(1, atoi(e))));
         for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
     }
     ~HostPool() {

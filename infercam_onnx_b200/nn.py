@@ -156,10 +156,10 @@ class UltrafaceModel(InferModel):
     def run_batch_jpeg(self, jpegs: Sequence[bytes], cap: int = 256) -> List[np.ndarray]:
         """N2: frames as baseline JPEG files (bytes); Huffman decoding on host threads, the rest on the GPU."""
         n = len(jpegs)
-        bufs = [C.create_string_buffer(bytes(j), len(j)) for j in jpegs]
-        ptrs = (C.c_void_p * max(n, 1))(*[C.addressof(b) for b in bufs])
-        lens = (C.c_size_t * max(n, 1))(*[len(j) for j in jpegs])
-        return self._run_batch_raw(lambda out, cnt: _capi.load().uf_infer_batch_jpeg(self._h, ptrs, lens, n, out, cap, cnt), n, cap)
+        ptrs, lens, keep = _jpeg_args(jpegs)
+        out = self._run_batch_raw(lambda out, cnt: _capi.load().uf_infer_batch_jpeg(self._h, ptrs, lens, n, out, cap, cnt), n, cap)
+        del keep
+        return out
 
     def jpeg_decode_rgb(self, jpeg: bytes) -> np.ndarray:
         """Parity hook: the RGB8 pixels the GPU decode kernels produce for one JPEG file."""
@@ -190,9 +190,7 @@ class UltrafaceModel(InferModel):
                                      out_stride: int = 0) -> List[bytes]:
         """Batch form of annotate_encode_jpeg for JPEG input: decode, overlay and encode on the GPU (entropy coding included)."""
         n = len(jpegs)
-        bufs = [C.create_string_buffer(bytes(j), len(j)) for j in jpegs]
-        ptrs = (C.c_void_p * max(n, 1))(*[C.cast(b, C.c_void_p) for b in bufs])
-        lens = (C.c_size_t * max(n, 1))(*[len(j) for j in jpegs])
+        ptrs, lens, keep = _jpeg_args(jpegs)
         flat = [np.asarray(d, np.float32).reshape(-1, 5) for d in dets_per_frame]
         counts = (C.c_uint32 * max(n, 1))(*[len(d) for d in flat])
         alld = np.ascontiguousarray(np.concatenate(flat) if flat else np.zeros((0, 5), np.float32))
@@ -212,9 +210,7 @@ class UltrafaceModel(InferModel):
         key = ("worker", n, tuple(map(len, jpegs[:4])))
         cached = getattr(self, "_worker_args", None)
         if cached is None or cached[0] != key or cached[1] is not jpegs:
-            bufs = [C.create_string_buffer(bytes(j), len(j)) for j in jpegs]
-            ptrs = (C.c_void_p * max(n, 1))(*[C.cast(b, C.c_void_p) for b in bufs])
-            lens = (C.c_size_t * max(n, 1))(*[len(j) for j in jpegs])
+            ptrs, lens, bufs = _jpeg_args(jpegs)
             self._worker_args = cached = (key, jpegs, bufs, ptrs, lens)
         _, _, bufs, ptrs, lens = cached
         if not out_stride:
@@ -395,6 +391,16 @@ class UltrafaceModel(InferModel):
         n = C.c_uint64()
         _check(_capi.load().uf_launch_count(self._h, C.byref(n)))
         return int(n.value)
+
+
+def _jpeg_args(jpegs: Sequence[bytes]):
+    """(array of pointers, array of lengths, what must stay alive during the call) for a list of JPEG files — pointers INTO the
+    bytes objects, no copy of the files."""
+    n = len(jpegs)
+    keep = [j if isinstance(j, bytes) else bytes(j) for j in jpegs]
+    cptrs = (C.c_char_p * max(n, 1))(*keep)
+    lens = (C.c_size_t * max(n, 1))(*[len(j) for j in keep])
+    return C.cast(cptrs, C.POINTER(C.c_void_p)), lens, (keep, cptrs)
 
 
 def _as_rgb(a: np.ndarray) -> np.ndarray:
