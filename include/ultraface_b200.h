@@ -186,11 +186,14 @@ UF_API int uf_resize_taps(uint32_t src_len, uint32_t dst_len, int32_t* left, int
 
 /* ==== JPEG in front of the path ================================================================
  * Replaces `turbojpeg::decompress_image` (inferer.rs:35): frames arrive as baseline JPEG (what a V4L2 MJPG webcam sends,
- * cam_sender/src/sensors.rs); Huffman decoding runs on host threads, dequantisation + inverse DCT + chroma upsampling +
- * YCbCr->RGB on the GPU, bit-exact with libjpeg-turbo's default decoder (ISLOW IDCT, fancy upsampling), and the decoded
- * frame goes straight into the resize. What crosses PCIe is the list of nonzero coefficients (4 bytes each + 4 bytes per
- * 8x8 block), not 3 bytes per pixel. Baseline / extended-sequential Huffman, 8 bit, one interleaved scan, grey or YCbCr
- * 4:4:4 / 4:2:2 / 4:2:0; anything else (progressive, arithmetic, CMYK ...) is UF_ERR_UNSUPPORTED. */
+ * cam_sender/src/sensors.rs); the host parses the headers and removes the 0xFF00 byte stuffing, the entropy-coded bytes
+ * cross PCIe as they are (75 KB instead of 3 bytes per pixel) and Huffman decoding, dequantisation, inverse DCT, chroma
+ * upsampling and YCbCr->RGB run on the GPU, bit-exact with libjpeg-turbo's default decoder (ISLOW IDCT, fancy upsampling);
+ * the decoded frame goes straight into the resize. Frames with restart intervals, markers inside the scan, or data that
+ * does not decode to exactly the frame's blocks are Huffman-decoded on host threads instead (same results; what crosses
+ * PCIe is then the list of nonzero coefficients), as is everything under UF_FLAG_JPEG_HOST_HUFFMAN. Baseline /
+ * extended-sequential Huffman, 8 bit, one interleaved scan, grey or YCbCr 4:4:4 / 4:2:2 / 4:2:0; anything else
+ * (progressive, arithmetic, CMYK ...) is UF_ERR_UNSUPPORTED. */
 typedef struct uf_jpeg_info {
     uint32_t w, h, ncomp;
     uint32_t hs[3], vs[3];      /* sampling factors */

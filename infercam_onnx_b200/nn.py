@@ -154,7 +154,8 @@ class UltrafaceModel(InferModel):
             lambda out, cnt: _capi.load().uf_infer_batch_device(self._h, C.c_void_p(device_ptr), w, h, n, out, cap, cnt), n, cap)
 
     def run_batch_jpeg(self, jpegs: Sequence[bytes], cap: int = 256) -> List[np.ndarray]:
-        """N2: frames as baseline JPEG files (bytes); Huffman decoding on host threads, the rest on the GPU."""
+        """N2: frames as baseline JPEG files (bytes), decoded on the GPU (Huffman decoding included; host fallback for frames
+        with restart intervals or damaged data)."""
         n = len(jpegs)
         ptrs, lens, keep = _jpeg_args(jpegs)
         out = self._run_batch_raw(lambda out, cnt: _capi.load().uf_infer_batch_jpeg(self._h, ptrs, lens, n, out, cap, cnt), n, cap)
