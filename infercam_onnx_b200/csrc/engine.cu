@@ -2268,6 +2268,46 @@ static void reencode_chunk(uf_model& m, Lane& ln, Slot& s, const uint8_t* const*
     if (too_small.load()) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
 }
 
+// The chunks of a batch for the annotate path, several at a time: a chunk walks its stages one after another with waits in
+// between, so up to one host thread per lane takes chunks from the list and runs each on a lane of its own (a caller with
+// one thread then gets what a caller with several calls in flight gets). fn(lane, slot, first frame, count).
+static void run_annotate_chunks(uf_model& m, uint32_t n, const std::function<void(Lane&, Slot&, uint32_t, uint32_t)>& fn) {
+    const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(64, m.chunk));
+    const uint32_t nchunks = (n + step - 1) / step;
+    std::atomic<uint32_t> next{0};
+    std::atomic<bool> too_small{false}, stop{false};
+    std::exception_ptr err;
+    std::mutex err_mu;
+    auto work = [&] {
+        cudaSetDevice(m.cfg.device);
+        for (;;) {
+            const uint32_t c = next.fetch_add(1);
+            if (c >= nchunks || stop.load()) return;
+            try {
+                LaneLock ll(m, false);
+                fn(*ll.lane, ll.lane->slots[0], c * step, std::min(step, n - c * step));
+                ll.lane->last_n = 0;
+            } catch (const ArgError& e) {
+                if (e.code == UF_ERR_CAPACITY) { too_small = true; continue; }  // the other chunks still report their sizes
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (!err) err = std::current_exception();
+                stop = true;
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (!err) err = std::current_exception();
+                stop = true;
+            }
+        }
+    };
+    const uint32_t nthreads = m.profiling ? 1 : std::min<uint32_t>(nchunks, (uint32_t)std::min<size_t>(m.lanes.size(), 4));
+    std::vector<std::thread> ts;
+    for (uint32_t t = 1; t < nthreads; ++t) ts.emplace_back(work);
+    work();
+    for (auto& t : ts) t.join();
+    if (err) std::rethrow_exception(err);
+    if (too_small.load()) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
+}
+
 int uf_annotate_reencode_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* len, uint32_t n, const uf_det* dets,
                                     const uint32_t* det_counts, float scale_w, float scale_h, uint32_t quality, uint8_t* out, size_t out_stride,
                                     size_t* out_len) {
@@ -2277,23 +2317,11 @@ int uf_annotate_reencode_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, con
         std::vector<uint32_t> first(n + 1, 0);
         for (uint32_t i = 0; i < n; ++i) first[i + 1] = first[i] + det_counts[i];
         REQUIRE(first[n] == 0 || dets, "null detections");
-        LaneLock ll(*m, false);
-        Slot& s = ll.lane->slots[0];
         CK(cudaSetDevice(m->cfg.device));
-        const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(64, m->chunk));
-        bool too_small = false;
-        for (uint32_t f0 = 0; f0 < n; f0 += step) {
-            const uint32_t cnt = std::min(step, n - f0);
-            try {
-                reencode_chunk(*m, *ll.lane, s, jpeg + f0, len + f0, cnt, dets, first.data() + f0, det_counts + f0, scale_w, scale_h, (int)quality,
-                               out + (size_t)f0 * out_stride, out_stride, out_len + f0, f0);
-            } catch (const ArgError& e) {
-                if (e.code != UF_ERR_CAPACITY) throw;
-                too_small = true;  // the other chunks still report their sizes
-            }
-        }
-        ll.lane->last_n = 0;
-        if (too_small) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
+        run_annotate_chunks(*m, n, [&](Lane& ln, Slot& s, uint32_t f0, uint32_t cnt) {
+            reencode_chunk(*m, ln, s, jpeg + f0, len + f0, cnt, dets, first.data() + f0, det_counts + f0, scale_w, scale_h, (int)quality,
+                           out + (size_t)f0 * out_stride, out_stride, out_len + f0, f0);
+        });
     });
 }
 
@@ -2302,23 +2330,11 @@ int uf_worker_batch_jpeg(uf_model* m, const uint8_t* const* jpeg, const size_t* 
     return guarded([&] {
         REQUIRE(m && out_len && n_dets && cap > 0 && dets && (n == 0 || (jpeg && len && out)) && out_stride >= 1024, "bad argument");
         for (uint32_t i = 0; i < n; ++i) REQUIRE(jpeg[i] && len[i] > 0, "null frame");
-        LaneLock ll(*m, false);
-        Slot& s = ll.lane->slots[0];
         CK(cudaSetDevice(m->cfg.device));
-        const uint32_t step = std::max<uint32_t>(1, std::min<uint32_t>(64, m->chunk));
-        bool too_small = false;
-        for (uint32_t f0 = 0; f0 < n; f0 += step) {
-            const uint32_t cnt = std::min(step, n - f0);
-            try {
-                reencode_chunk(*m, *ll.lane, s, jpeg + f0, len + f0, cnt, nullptr, nullptr, nullptr, scale_w, scale_h, (int)quality,
-                               out + (size_t)f0 * out_stride, out_stride, out_len + f0, f0, dets + (size_t)f0 * cap, cap, n_dets + f0);
-            } catch (const ArgError& e) {
-                if (e.code != UF_ERR_CAPACITY) throw;
-                too_small = true;
-            }
-        }
-        ll.lane->last_n = 0;
-        if (too_small) throw ArgError(UF_ERR_CAPACITY, "an encoded file is larger than out_stride (out_len holds the sizes)");
+        run_annotate_chunks(*m, n, [&](Lane& ln, Slot& s, uint32_t f0, uint32_t cnt) {
+            reencode_chunk(*m, ln, s, jpeg + f0, len + f0, cnt, nullptr, nullptr, nullptr, scale_w, scale_h, (int)quality,
+                           out + (size_t)f0 * out_stride, out_stride, out_len + f0, f0, dets + (size_t)f0 * cap, cap, n_dets + f0);
+        });
     });
 }
 
