@@ -261,8 +261,8 @@ struct uf_model {
     int K = 0;
     uint32_t chunk = 0, host_chunk = 0, jpeg_chunk = 0, nslots = 0;
     // frames in a host-input stage from which its waiter sleeps on a blocking event instead of spinning (UF_SLEEP_WAIT_FROM).
-    // 0 = never, the default: measured on one GPU, a sleeping waiter wakes late enough to cost the in-flight path 40 %; it is
-    // there for hosts that run many ranks on few cores.
+    // 0 = never, the default: measured on one GPU, a sleeping waiter wakes late enough to cost the in-flight path 40 %, and
+    // with 8 ranks on 32 cores it changed nothing (+-1 %). Kept as a knob for hosts with fewer cores than waiting threads.
     uint32_t sleep_wait_from = 0;
     uint32_t jh_threads = 150000, jh_bits = 0;  // device Huffman: threads a run should have / forced bits per thread (tuning knobs)
     std::vector<Step> steps;
