@@ -5,15 +5,16 @@
 //
 // A Huffman stream can only be decoded from a known state (bit position, block slot in the MCU, coefficient index), and the
 // state at any point depends on everything before it. The way round it (self-synchronising parallel decoding, Klein & Wiseman;
-// Weissenberger & Schmidt's GPU formulation) is to cut the stream into subsequences of JH_SUBSEQ_BITS, let one thread decode
+// Weissenberger & Schmidt's GPU formulation) is to cut the stream into subsequences of 256-2048 bits (picked per run, engine.cu), let one thread decode
 // each from a GUESSED state, and iterate: in every round thread t restarts from the END state thread t-1 reached in the
 // round before. Thread 0 starts from the true state, so the correct prefix grows by at least one subsequence per round —
 // and usually by many, because a decoder started in a wrong state falls into step with the true one after a few dozen
 // symbols. The fixed point (no end state changes) IS the sequential decode: end[t] = decode(end[t-1]) for all t, end[-1] true.
-// The rounds run inside a CTA over its 128 subsequences, and once per launch across CTAs (jhuff_sync_kernel).
+// The rounds run inside a CTA over its 256 subsequences, and once per launch across CTAs (jhuff_sync_kernel).
 // Then a prefix sum of the blocks started and nonzero coefficients met per subsequence gives every thread its output
 // position, a second pass writes the coefficients as the compact per-block lists the IDCT kernel reads (DC differences
-// apart), and a per-component scan turns DC differences into values. The coefficients are the host decoder's, hence libjpeg-turbo's, bit for bit (tests/test_jpeg.py).
+// apart), and a per-component scan turns DC differences into values. The coefficients are the host decoder's, hence
+// libjpeg-turbo's, bit for bit (tests/test_jpeg.py).
 #include "jpeg_decode.h"
 #include "jpeg_huff_core.h"
 #include "kernels.h"
@@ -24,7 +25,7 @@ using namespace jh;
 
 namespace {
 
-constexpr int JHT = 256;         // threads per CTA (one subsequence each): a CTA spans 8 KB of the stream
+constexpr int JHT = 256;         // threads per CTA (one subsequence each): a CTA spans 8-64 KB of the stream
 constexpr int JH_MAX_ROUNDS = 4;  // launches of the synchronisation kernel (see jhuff_sync_kernel)
 
 __constant__ uint8_t c_zigzag[80] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
