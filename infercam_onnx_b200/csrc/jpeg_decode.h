@@ -118,6 +118,20 @@ struct JpegEncJob {        // one frame of a batch for the encoder's sample-doma
     unsigned long long rgb_off, planes_off;  // byte offsets of the frame's pixels / component planes
     unsigned long long coef_off;             // offset of its coefficients, in int16 elements
 };
+struct JpegEncFrame {      // plain data, copied to the device as is
+    uint32_t coef_base;    // index of the frame's first block in the coefficient buffer (blocks per plane in raster order)
+    uint32_t mcus_x, mcus_y;
+    uint32_t y_bw, c_bw;   // blocks per row of the padded luma / chroma planes
+    uint32_t cb_off, cr_off;  // first block of the Cb / Cr plane, relative to coef_base
+    uint32_t wib0, hib0;   // luma blocks per row / column that hold image samples (beyond: libjpeg's dummy blocks)
+    uint32_t nblocks;      // mcus * 6, in MCU order
+    uint32_t len_base;     // index of the frame's first block in the bit-count / bit-offset arrays
+    uint32_t pack_off;     // word offset of the frame's bit buffer
+    uint32_t pack_cap_bits;
+    uint32_t out_off;      // byte offset of the frame's entropy-coded segment in the output buffer
+    uint32_t out_cap;
+    uint32_t pad_;
+};
 struct JpegEncTables {     // Annex K tables in encoder form: (length << 16) | code; [0] luma, [1] chroma
     uint32_t dc[2][16];
     uint32_t ac[2][256];

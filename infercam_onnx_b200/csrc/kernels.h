@@ -204,20 +204,7 @@ void launch_jpeg_encode_batch(const uint8_t* d_rgb_base, const JpegEncJob* d_job
 
 // ---- N3: Huffman coding of quantised 4:2:0 frames on the GPU (kernels_jpeg_henc.cu)
 struct JpegEncTables;      // jpeg_decode.h
-struct JpegEncFrame {      // plain data, copied to the device as is
-    uint32_t coef_base;    // index of the frame's first block in the coefficient buffer (blocks per plane in raster order)
-    uint32_t mcus_x, mcus_y;
-    uint32_t y_bw, c_bw;   // blocks per row of the padded luma / chroma planes
-    uint32_t cb_off, cr_off;  // first block of the Cb / Cr plane, relative to coef_base
-    uint32_t wib0, hib0;   // luma blocks per row / column that hold image samples (beyond: libjpeg's dummy blocks)
-    uint32_t nblocks;      // mcus * 6, in MCU order
-    uint32_t len_base;     // index of the frame's first block in the bit-count / bit-offset arrays
-    uint32_t pack_off;     // word offset of the frame's bit buffer
-    uint32_t pack_cap_bits;
-    uint32_t out_off;      // byte offset of the frame's entropy-coded segment in the output buffer
-    uint32_t out_cap;
-    uint32_t pad_;
-};
+struct JpegEncFrame;       // jpeg_decode.h
 struct JpegEncBatch {
     const JpegEncFrame* frames;
     const int16_t* coefs;

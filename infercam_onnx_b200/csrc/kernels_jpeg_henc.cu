@@ -15,21 +15,18 @@
 // The host prepends the headers and appends EOI (jpeg_write_headers). libjpeg's dummy blocks (luma blocks of an edge MCU that
 // lie wholly outside the image) are coded as it codes them: AC zero, DC = the DC of the block before in the MCU.
 #include "jpeg_decode.h"
+#include "jpeg_henc_core.h"
 #include "kernels.h"
 
 namespace uf {
+
+using namespace he;
 
 namespace {
 
 __constant__ uint8_t c_enc_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                          41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                          30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-
-struct EncSmem {
-    uint32_t dc[2][16];   // (length << 16) | code, [0] luma [1] chroma
-    uint32_t ac[2][256];
-    uint8_t zz[64];
-};
 
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
     int incl = v;
@@ -42,62 +39,12 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
     return incl - v;
 }
 
-// n bits (1..32) of v at bit position pos of the big-endian bit buffer P
-__device__ __forceinline__ void put32(uint32_t* __restrict__ P, uint32_t v, uint32_t n, uint32_t pos) {
-    const uint32_t sh = pos & 31u, w = pos >> 5, avail = 32u - sh;
-    if (n <= avail) {
-        atomicOr(P + w, v << (avail - n));
-    } else {
-        atomicOr(P + w, v >> (n - avail));
-        atomicOr(P + w + 1, v << (32u - (n - avail)));
-    }
-}
-
-__device__ __forceinline__ void put64(uint32_t* __restrict__ P, unsigned long long bits, uint32_t len, uint32_t pos, uint32_t cap_bits) {
-    if (len == 0 || pos + len > cap_bits) return;  // (an overflowing frame is flagged by the scan kernel and redone on the host)
-    if (len > 32) {
-        put32(P, (uint32_t)(bits >> 32), len - 32, pos);
-        put32(P, (uint32_t)bits, 32, pos + len - 32);
-    } else {
-        put32(P, (uint32_t)bits & (len == 32 ? 0xffffffffu : ((1u << len) - 1u)), len, pos);
-    }
-}
-
-// the bits of one coefficient: AC at zigzag position k (k >= 1) with the nonzero mask M of the block, or the DC difference
-__device__ __forceinline__ void coef_bits(const EncSmem& T, int chroma, uint32_t k, int v, unsigned long long M, unsigned long long& bits,
-                                          uint32_t& len) {
-    bits = 0;
-    len = 0;
-    if (k != 0 && v == 0) return;
-    int a = v, m = v;
-    if (v < 0) { a = -v; m = v - 1; }
-    const uint32_t size = 32u - (uint32_t)__clz(a);  // bit length of |v| (0 for 0)
-    const uint32_t mag = (uint32_t)m & ((1u << size) - 1u);
-    if (k == 0) {
-        const uint32_t e = T.dc[chroma][size];
-        bits = ((unsigned long long)(e & 0xffffu) << size) | mag;
-        len = (e >> 16) + size;
-        return;
-    }
-    const unsigned long long below = M & ((1ull << k) - 1ull);
-    const uint32_t pk = below ? 63u - (uint32_t)__clzll((long long)below) : 0u;  // the nonzero before it (0: the DC position)
-    uint32_t run = k - 1u - pk;
-    const uint32_t zrl = T.ac[chroma][0xf0];
-    for (; run > 15; run -= 16) {
-        bits = (bits << (zrl >> 16)) | (zrl & 0xffffu);
-        len += zrl >> 16;
-    }
-    const uint32_t e = T.ac[chroma][(run << 4) | size];
-    bits = (((bits << (e >> 16)) | (e & 0xffffu)) << size) | mag;
-    len += (e >> 16) + size;
-}
-
 }  // namespace
 
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
 jenc_block_kernel(JpegEncBatch B) {
-    __shared__ EncSmem T;
+    __shared__ EncTabs T;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(B.tables);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
@@ -108,38 +55,12 @@ jenc_block_kernel(JpegEncBatch B) {
     const JpegEncFrame& F = B.frames[blockIdx.y];
     const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= F.nblocks) return;
-    const uint32_t mcu = b / 6, s = b - mcu * 6, my = mcu / F.mcus_x, mx = mcu - my * F.mcus_x;
-    const int chroma = s >= 4;
     const int16_t* coefs = B.coefs + (size_t)F.coef_base * 64;
-    // source block, libjpeg's dummy-block rule, the DC predictor (all lanes compute the same few values)
-    auto y_blk = [&](uint32_t mx_, uint32_t my_, uint32_t s_, bool& dummy) -> uint32_t {
-        const uint32_t bx = 2 * mx_ + (s_ & 1u), by = 2 * my_ + (s_ >> 1);
-        dummy = bx >= F.wib0 || by >= F.hib0;
-        return by * F.y_bw + bx;
-    };
-    auto y_eff_dc = [&](uint32_t mx_, uint32_t my_, uint32_t s_) -> int {  // DC as coded: a dummy block repeats the block before it
-        bool d;
-        uint32_t blk = y_blk(mx_, my_, s_, d);
-        while (d && s_ > 0) blk = y_blk(mx_, my_, --s_, d);
-        return coefs[(size_t)blk * 64];
-    };
-    bool dummy = false;
-    uint32_t src;
-    int dc, pred = 0;
-    if (!chroma) {
-        src = y_blk(mx, my, s, dummy);
-        dc = y_eff_dc(mx, my, s);
-        if (s > 0) pred = y_eff_dc(mx, my, s - 1);
-        else if (mcu > 0) { const uint32_t pm = mcu - 1, py = pm / F.mcus_x; pred = y_eff_dc(pm - py * F.mcus_x, py, 3); }
-    } else {
-        const uint32_t base = s == 4 ? F.cb_off : F.cr_off;
-        src = base + my * F.c_bw + mx;
-        dc = coefs[(size_t)src * 64];
-        if (mcu > 0) { const uint32_t pm = mcu - 1, py = pm / F.mcus_x; pred = coefs[(size_t)(base + py * F.c_bw + (pm - py * F.mcus_x)) * 64]; }
-    }
-    const int16_t* blk = coefs + (size_t)src * 64;
-    const int v1 = lane == 0 ? dc - pred : (dummy ? 0 : (int)blk[T.zz[lane]]);
-    const int v2 = dummy ? 0 : (int)blk[T.zz[lane + 32]];
+    const BlockSrc S = block_source(F, coefs, b);  // (all lanes compute the same few values)
+    const int chroma = S.chroma;
+    const int16_t* blk = coefs + (size_t)S.src * 64;
+    const int v1 = lane == 0 ? S.dc_diff : (S.dummy ? 0 : (int)blk[T.zz[lane]]);
+    const int v2 = S.dummy ? 0 : (int)blk[T.zz[lane + 32]];
     const uint32_t m1 = __ballot_sync(0xffffffffu, v1 != 0) & ~1u, m2 = __ballot_sync(0xffffffffu, v2 != 0);
     const unsigned long long M = (unsigned long long)m1 | ((unsigned long long)m2 << 32);
     unsigned long long bits1, bits2;
@@ -149,7 +70,7 @@ jenc_block_kernel(JpegEncBatch B) {
     int tot1, tot2;
     const int off1 = warp_excl_scan((int)len1, (int)lane, tot1);
     const int off2 = warp_excl_scan((int)len2, (int)lane, tot2);
-    const uint32_t last = M ? 63u - (uint32_t)__clzll((long long)M) : 0u;
+    const uint32_t last = M ? top_bit64(M) : 0u;
     const uint32_t eob = last < 63 ? T.ac[chroma][0] : 0u;  // trailing zeros: EOB
     const uint32_t total = (uint32_t)(tot1 + tot2) + (eob >> 16);
     if (!WRITE) {
@@ -204,13 +125,9 @@ jenc_stuff_kernel(JpegEncBatch B) {
         if (threadIdx.x == 0) B.out_len[blockIdx.x] = 0xffffffffu;
         return;
     }
-    const uint32_t nbytes = (bits + 7) / 8, rem = bits & 7u;
+    const uint32_t nbytes = (bits + 7) / 8;
     const uint32_t* P = B.packed + F.pack_off;
-    auto byte_at = [&](uint32_t i) -> uint32_t {
-        uint32_t v = (P[i >> 2] >> (24u - 8u * (i & 3u))) & 0xffu;
-        if (i == nbytes - 1 && rem) v |= (1u << (8u - rem)) - 1u;
-        return v;
-    };
+    auto byte_at = [&](uint32_t i) -> uint32_t { return packed_byte(P, i, bits); };
     const uint32_t per = (nbytes + 1023) / 1024, i0 = min(threadIdx.x * per, nbytes), i1 = min(i0 + per, nbytes);
     uint32_t ff = 0;
     for (uint32_t i = i0; i < i1; ++i) ff += byte_at(i) == 0xffu;

@@ -285,3 +285,42 @@ def test_gpu_worker_calls_in_flight_do_not_share_scratch(make_onnx, test_pics):
         assert not errs, errs
     finally:
         m.close()
+
+
+@pytest.fixture(scope="module")
+def henc_sim_lib(tmp_path_factory):
+    import ctypes as C
+    import pathlib
+    import subprocess
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    so = tmp_path_factory.mktemp("henc") / "henc_sim.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", f"-I{root / 'include'}", "-o", str(so),
+                    str(root / "tests/helpers/henc_sim.cc"), str(root / "infercam_onnx_b200/csrc/jpeg_encode.cc")], check=True)
+    lib = C.CDLL(str(so))
+    lib.henc_sim.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    return lib
+
+
+@pytest.mark.parametrize("shape,quality", [((480, 640), 95), ((462, 640), 95), ((301, 333), 80), ((9, 17), 95), ((16, 8), 50), ((240, 320), 100)])
+def test_device_huffman_coder_plan_on_the_host(test_pics, henc_sim_lib, shape, quality):
+    """The device coder's plan — bits per block, prefix sum, bits OR-ed into a bit buffer at their offsets, padding, byte
+    stuffing — walked serially on the CPU by tests/helpers/henc_sim.cc over the SAME per-block code the kernels compile
+    (csrc/jpeg_henc_core.h: block source incl. libjpeg's dummy blocks, DC predictor, the bits of a coefficient), must write
+    the file the sequential writer writes (itself checked against libjpeg-turbo above)."""
+    import ctypes as C
+
+    lib = henc_sim_lib
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    base = test_pics["omar-lopez-T6zu4jFhVwg"]
+    pic = (np.resize(base, (h, w, 3)) if h > base.shape[0] or w > base.shape[1] else base[:h, :w]).astype(np.int16)
+    for noise in (0, 40):  # the photo; the photo under heavy noise (long codes, ZRL runs, many 0xFF bytes)
+        arr = (pic + rng.integers(-noise, noise + 1, pic.shape)).clip(0, 255).astype(np.uint8)
+        info, coefs = nn.jpeg_coefficients(_pil_jpeg(arr, quality))
+        planes = _to_plane_raster(info, coefs)
+        want = nn.jpeg_write_coefficients(w, h, quality, planes)
+        out = np.empty(len(want) + 4096, np.uint8)
+        n = C.c_size_t()
+        rc = lib.henc_sim(w, h, quality, planes.ctypes.data, out.ctypes.data, out.size, C.byref(n))
+        assert rc == 0 and bytes(out[: n.value]) == want, (rc, n.value, len(want))
