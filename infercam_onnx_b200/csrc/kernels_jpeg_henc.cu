@@ -10,7 +10,7 @@
 //   jenc_scan_kernel          CTA per frame: exclusive prefix sum -> bit offset of every block, bits of the frame
 //   jenc_block_kernel<true>   the same walk, now assembling every coefficient's bits ([ZRL ...] code magnitude, <= 59 bits)
 //                             and OR-ing them into the zeroed bit buffer at (block offset + lane offset)
-//   jenc_stuff_kernel         CTA per frame: pad the last byte with 1-bits, insert 0x00 after every 0xFF byte (count per
+//   jenc_stuff_kernel         8 CTAs per frame: pad the last byte with 1-bits, insert 0x00 after every 0xFF byte (count per
 //                             thread, prefix sum, copy) -> the entropy-coded segment as it stands in the file
 // The host prepends the headers and appends EOI (jpeg_write_headers). libjpeg's dummy blocks (luma blocks of an edge MCU that
 // lie wholly outside the image) are coded as it codes them: AC zero, DC = the DC of the block before in the MCU.
@@ -115,49 +115,76 @@ jenc_scan_kernel(JpegEncBatch B) {
     if (threadIdx.x == 0) B.frame_bits[blockIdx.x] = all;
 }
 
-// bit buffer -> the entropy-coded segment: last byte padded with 1-bits, 0x00 after every 0xFF
+// bit buffer -> the entropy-coded segment: last byte padded with 1-bits, 0x00 after every 0xFF. A frame is cut into
+// JENC_STUFF_SPLIT pieces, one CTA each: a CTA counts the 0xFF bytes of everything before its piece (whole words, straight
+// from L2), then those of its own piece per thread, scans, and copies its bytes to where they land.
+constexpr int JENC_STUFF_SPLIT = 8;
+
 __global__ void __launch_bounds__(1024)
 jenc_stuff_kernel(JpegEncBatch B) {
     __shared__ uint32_t s_warp[32];
-    const JpegEncFrame& F = B.frames[blockIdx.x];
-    const uint32_t bits = B.frame_bits[blockIdx.x];
+    const JpegEncFrame& F = B.frames[blockIdx.y];
+    const uint32_t bits = B.frame_bits[blockIdx.y];
     if (bits > F.pack_cap_bits) {  // does not fit the bit buffer: the host encoder takes the frame
-        if (threadIdx.x == 0) B.out_len[blockIdx.x] = 0xffffffffu;
+        if (blockIdx.x == 0 && threadIdx.x == 0) B.out_len[blockIdx.y] = 0xffffffffu;
         return;
     }
     const uint32_t nbytes = (bits + 7) / 8;
-    const uint32_t* P = B.packed + F.pack_off;
-    auto byte_at = [&](uint32_t i) -> uint32_t { return packed_byte(P, i, bits); };
-    const uint32_t per = (nbytes + 1023) / 1024, i0 = min(threadIdx.x * per, nbytes), i1 = min(i0 + per, nbytes);
-    uint32_t ff = 0;
-    for (uint32_t i = i0; i < i1; ++i) ff += byte_at(i) == 0xffu;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = ff;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += y;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t before = incl - ff, all = 0;
-    for (uint32_t w = 0; w < 32; ++w) {
-        if (w < warp) before += s_warp[w];
-        all += s_warp[w];
-    }
-    const uint32_t out_len = nbytes + all;
-    if (out_len > F.out_cap) {
-        if (threadIdx.x == 0) B.out_len[blockIdx.x] = 0xffffffffu;
+    const uint32_t seg = ((nbytes + JENC_STUFF_SPLIT - 1) / JENC_STUFF_SPLIT + 3u) & ~3u;  // whole words
+    const uint32_t s0 = min(blockIdx.x * seg, nbytes), s1 = min(s0 + seg, nbytes);
+    if (s0 >= s1) {
+        if (nbytes == 0 && blockIdx.x == 0 && threadIdx.x == 0) B.out_len[blockIdx.y] = 0;
         return;
     }
-    uint8_t* out = B.out + F.out_off;
-    uint32_t pos = i0 + before;
-    for (uint32_t i = i0; i < i1; ++i) {
-        const uint32_t v = byte_at(i);
-        out[pos++] = (uint8_t)v;
-        if (v == 0xffu) out[pos++] = 0;
+    const uint32_t* P = B.packed + F.pack_off;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto cta_scan = [&](uint32_t v, uint32_t& all) -> uint32_t {  // exclusive prefix over the CTA's threads, and the total
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        __syncthreads();  // (s_warp may still be read from the previous use)
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = incl - v;
+        all = 0;
+        for (uint32_t w = 0; w < 32; ++w) {
+            if (w < warp) before += s_warp[w];
+            all += s_warp[w];
+        }
+        return before;
+    };
+    // 0xFF bytes in front of the piece (s0 is a multiple of 4 and lies before the padded last byte)
+    uint32_t cnt = 0;
+    for (uint32_t w = threadIdx.x; w < s0 / 4; w += 1024) {
+        const uint32_t x = P[w];
+        cnt += ((x >> 24) == 0xffu) + (((x >> 16) & 0xffu) == 0xffu) + (((x >> 8) & 0xffu) == 0xffu) + ((x & 0xffu) == 0xffu);
     }
-    if (threadIdx.x == 0) B.out_len[blockIdx.x] = out_len;
+    uint32_t front = 0;
+    cta_scan(cnt, front);
+    // the piece itself
+    const uint32_t per = (s1 - s0 + 1023) / 1024, i0 = min(s0 + threadIdx.x * per, s1), i1 = min(i0 + per, s1);
+    uint32_t ff = 0;
+    for (uint32_t i = i0; i < i1; ++i) ff += packed_byte(P, i, bits) == 0xffu;
+    uint32_t inside = 0;
+    const uint32_t before = cta_scan(ff, inside);
+    uint8_t* out = B.out + F.out_off;
+    uint32_t pos = i0 + front + before;
+    for (uint32_t i = i0; i < i1; ++i) {
+        const uint32_t v = packed_byte(P, i, bits);
+        if (pos < F.out_cap) out[pos] = (uint8_t)v;
+        ++pos;
+        if (v == 0xffu) {
+            if (pos < F.out_cap) out[pos] = 0;
+            ++pos;
+        }
+    }
+    if (s1 == nbytes && threadIdx.x == 0) {  // the piece that holds the last byte knows the length of the whole segment
+        const uint32_t out_len = nbytes + front + inside;
+        B.out_len[blockIdx.y] = out_len > F.out_cap ? 0xffffffffu : out_len;
+    }
 }
 
 void launch_jpeg_huffman_encode(const JpegEncBatch& B, int frames, uint32_t max_nblocks, cudaStream_t s) {
@@ -166,7 +193,7 @@ void launch_jpeg_huffman_encode(const JpegEncBatch& B, int frames, uint32_t max_
     jenc_block_kernel<false><<<grid, 256, 0, s>>>(B);
     jenc_scan_kernel<<<frames, 1024, 0, s>>>(B);
     jenc_block_kernel<true><<<grid, 256, 0, s>>>(B);
-    jenc_stuff_kernel<<<frames, 1024, 0, s>>>(B);
+    jenc_stuff_kernel<<<dim3(JENC_STUFF_SPLIT, frames), 1024, 0, s>>>(B);
 }
 
 }  // namespace uf
