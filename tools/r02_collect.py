@@ -25,7 +25,7 @@ def copy(name, dst=None):
 
 for n in ("r02_bench.json", "r02_bench_reference_arm.json", "r02_bench_cfg5_rfb320_allpriors.json", "r02_bench_cfg5_rfb640_b64_p1.json",
           "r02_bench_cfg5_rfb640_b64_p5.json", "r02_bench_cfg5_rfb640_b64_p50.json", "r02_pytest_gpu.log", "r02_ncu_launches_bench.csv",
-          "r02_bench_2gpu.json", "r02_jpeg_profile.txt", "r02_ncu_jpeg_per_launch.txt"):
+          "r02_bench_2gpu.json", "r02_jpeg_profile.txt", "r02_ncu_jpeg_per_launch.txt", "r02_ncu_jpeg_enc_per_launch.txt", "r02_bench_4gpu.json", "r02_bench_8gpu.json"):
     copy(n)
 
 # per-kernel share of the step from the launch list (cold-cache, serialised: shares, not absolutes)
