@@ -149,6 +149,34 @@ def test_failed_batches_skip_their_frames():
 
 
 # ------------------------------------------------------------------------------------------------
+def test_annotate_mode_configuration_and_poll_frames_contract():
+    """Host logic of the annotate mode (no GPU: injected backend, which never annotates): configuration bounds, the room
+    poll_frames needs per file, and that frames of a backend run come back without a file."""
+    be = FakeBackend()
+    with pytest.raises(nn.UltrafaceError):
+        StreamBatcher(backend=be, max_frame_bytes=64, annotate_quality=101)
+    with pytest.raises(nn.UltrafaceError):
+        StreamBatcher(backend=be, max_frame_bytes=64, annotate_quality=95, annotate_max_bytes=100)
+    b = StreamBatcher(backend=be, max_batch=4, max_delay=0.001, capacity=64, workers=1, max_frame_bytes=64, annotate_quality=95,
+                      annotate_max_bytes=4096)
+    try:
+        for i in range(6):
+            assert b.try_submit(i % 2, _frame(i), tag=i)
+        b.flush()
+        res = b.poll_frames(16)
+        assert sorted(r["tag"] for r in res) == list(range(6))
+        assert all(r["status"] == 0 and r["file"] == b"" and r["n_dets"] == 1 for r in res)
+        b.file_stride = 1024  # less room than the configuration promises a file may need
+        assert b.try_submit(0, _frame(7), tag=7)
+        b.flush()
+        with pytest.raises(nn.UltrafaceError):
+            b.poll_frames(4)
+        b.file_stride = 4096
+        assert [r["tag"] for r in b.poll_frames(4)] == [7]  # the refused poll took nothing off the queue
+    finally:
+        b.close()
+
+
 @pytest.mark.gpu
 def test_gpu_batcher_matches_oracle(make_onnx, test_pics):
     """The product batcher (its own handle, pinned pool, batches in flight) against the ORACLE end to end."""
