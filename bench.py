@@ -398,28 +398,42 @@ def main():
             import threading
             share = [steps // threads + (1 if i < steps % threads else 0) for i in range(threads)]
             last = [None] * threads
+            errs = []  # an exception in a host thread must fail the leg, not shorten its timed region
 
             def worker(i):
-                for _ in range(share[i]):
-                    last[i] = fn()
+                try:
+                    for _ in range(share[i]):
+                        last[i] = fn()
+                except BaseException as e:  # noqa: BLE001
+                    errs.append(e)
             inner = fn
 
             def run_all():
                 ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads) if share[i]]
                 [t.start() for t in ts]
                 [t.join() for t in ts]
+                if errs:
+                    raise errs[0]
                 return last[0]
             # warm EVERY lane: a lane captures its CUDA graphs on its second visit of a stage shape, and a call takes the first
             # free lane — so the calls of a warm-up round start together (all lanes busy at once), three rounds
             gate = threading.Barrier(threads)
 
             def warm():
-                for _ in range(3):
-                    gate.wait()
-                    inner()
+                try:
+                    for _ in range(3):
+                        gate.wait(timeout=300)
+                        inner()
+                except threading.BrokenBarrierError:
+                    pass
+                except BaseException as e:  # noqa: BLE001
+                    errs.append(e)
+                    gate.abort()  # (a failed call must not leave the other threads waiting at the gate)
             ws = [threading.Thread(target=warm) for _ in range(threads)]
             [t.start() for t in ws]
             [t.join() for t in ws]
+            if errs:
+                raise errs[0]
             run_all()
             best = None
             for _ in range(2):  # two timed regions of K steps each, the faster one counts (host threads: scheduling noise)
